@@ -1,0 +1,147 @@
+/* libsmcb200 — C ABI of the B200-native particle-filter hot path.
+ *
+ * Drop-in boundary for SequentialMonteCarlo.jl's particle-filter path (the reference is pure Julia
+ * and has no FFI layer of its own; each entry point below names the Julia function it replaces,
+ * file:line under /root/reference).  Julia binds these with `ccall((:sym, "libsmcb200"), Cint, ...)`
+ * — see INTEGRATION.md; the Python host mirror binds them with ctypes
+ * (sequential_monte_carlo_b200/_lib.py).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative smcb_status; the message of the last
+ *     failure is smcb_last_error(ctx) (ctx may be NULL for a failure of smcb_create);
+ *   - all pointers are HOST pointers owned by the caller, copied in/out synchronously, never
+ *     retained, unless the parameter name ends in `_dev` (device pointers on the context's GPU);
+ *   - all indices are 0-based (the Julia shim adds 1 to ancestors);
+ *   - state clouds are SoA: x[k*N + i] is component k of particle i (UCSV: k=0 x, 1 log σε, 2 log ση);
+ *   - a model is (kind, 8 doubles): see smcb_model_kind;
+ *   - randomness is the counter-based Philox stream of docs/SPEC.md: (seed, epoch, stream) name a
+ *     sweep; the context hands out a fresh epoch to every init / log_likelihood call, or the caller
+ *     pins it with smcb_set_rng for reproducibility;
+ *   - there is no CPU fallback: without a CUDA device smcb_create fails with SMCB_ERR_CUDA.
+ *   - a context is not thread-safe; distinct contexts may be used from distinct threads.
+ */
+#ifndef SMCB200_H
+#define SMCB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct smcb_ctx smcb_ctx;     /* one GPU, one stream, one single-filter slot */
+typedef struct smcb_batch smcb_batch; /* M independent filters of N particles (θ-level samplers) */
+
+typedef enum {
+  SMCB_OK = 0,
+  SMCB_ERR_BAD_ARG = -1,
+  SMCB_ERR_CUDA = -2,
+  SMCB_ERR_OOM = -3,
+  SMCB_ERR_STATE = -4, /* e.g. step before init */
+  SMCB_ERR_UNSUPPORTED = -5
+} smcb_status;
+
+/* params[8] per model (unused trailing entries ignored):
+ *   LG1D  A, B, Q, R, x0, σ0   (Q, R, σ0 are variances)   state_space_models.jl:46-58,74-109
+ *         unobserved_components(σε,ση,x0) is LG1D(1,1,σε,ση,x0,σε)              :119-128
+ *   SV    μ, ρ, σ              x1~N(μ,σ²/(1-ρ²)), x'~N(μ+ρ(x-μ),σ), y~N(0,exp(x/2))  (absent upstream)
+ *   UCSV  γε, γη, x0, logσε0, logση0                       state_space_models.jl:215-259 */
+typedef enum { SMCB_LG1D = 0, SMCB_SV = 1, SMCB_UCSV = 2 } smcb_model_kind;
+
+/* MULTINOMIAL is the reference's distribution (i.i.d., unsorted; particles.jl:17-19);
+ * STRATIFIED / SYSTEMATIC give sorted ancestors and are the bandwidth-optimal modes. */
+typedef enum { SMCB_MULTINOMIAL = 0, SMCB_STRATIFIED = 1, SMCB_SYSTEMATIC = 2 } smcb_resampler;
+
+#define SMCB_PARAM_STRIDE 8
+
+/* ------------------------------------------------------------------ context */
+int smcb_create(int device, uint64_t seed, smcb_ctx** out);
+int smcb_destroy(smcb_ctx* ctx);
+const char* smcb_last_error(const smcb_ctx* ctx);
+int smcb_version(void);
+int smcb_state_dim(int kind);
+/* next sweep uses (seed, epoch); later sweeps epoch+1, ... */
+int smcb_set_rng(smcb_ctx* ctx, uint64_t seed, uint32_t epoch);
+int smcb_get_epoch(const smcb_ctx* ctx, uint32_t* next_epoch);
+/* keep every step's ancestor vector of the single filter (for parity tests; costs 4 B/particle/step) */
+int smcb_record_ancestors(smcb_ctx* ctx, int enable);
+/* per-kernel CUDA-event timing of the single filter (bench.py roofline); off by default */
+int smcb_set_profiling(smcb_ctx* ctx, int enable);
+/* device time of the last sweep / step, and per-kernel-class totals when profiling is on:
+ * ms[0] whole call, ms[1] scan (quantise + look-back prefix sum + Σe, Σe²), ms[2] search+gather+
+ * propagate+weight, ms[3] init, ms[4] stats-only; launches[0..4] the matching launch counts. */
+int smcb_get_timing(const smcb_ctx* ctx, double ms[5], int64_t launches[5]);
+int smcb_synchronize(smcb_ctx* ctx);
+
+/* ------------------------------------------------------------------ utilities */
+/* normalize(logw) -> (logμ, w, ess)                                   particles.jl:5-15
+ * w may be NULL. */
+int smcb_normalize(smcb_ctx* ctx, const double* logw, int64_t n, double* logmu, double* w, double* ess);
+/* resample(w, n) -> ancestors                                          particles.jl:17-19
+ * draws come from Philox (seed, epoch) of the context at (stream, t, purpose). */
+int smcb_resample(smcb_ctx* ctx, const double* w, int64_t n, int resampler, uint32_t stream, uint32_t t,
+                  uint32_t purpose, int64_t* ancestors);
+
+/* ------------------------------------------------------------------ one filter (large N) */
+/* bootstrap_filter(N, y, model) -> (x, w, logμ)                        particles.jl:87-105
+ * the cloud stays on the device; read it back with smcb_fetch_state. */
+int smcb_bootstrap_init(smcb_ctx* ctx, int kind, const double* params, int64_t N, double y, uint32_t stream,
+                        double* logmu, double* ess);
+/* bootstrap_filter!(states, weights, y, model) -> (logμ, w, ess)       particles.jl:107-129
+ * params may be NULL (keep the model given to init). */
+int smcb_bootstrap_step(smcb_ctx* ctx, const double* params, double y, int resampler, double* logmu,
+                        double* ess);
+/* log_likelihood(N, y, model) -> (x, w, logZ)                          particles.jl:132-147
+ * one call for the whole series; logmu_out / ess_out (length T) may be NULL. */
+int smcb_log_likelihood(smcb_ctx* ctx, int kind, const double* params, int64_t N, const double* y, int64_t T,
+                        int resampler, uint32_t stream, double* logZ, double* logmu_out, double* ess_out);
+/* x [d*N] SoA, w [N] normalised weights, logw [N] unnormalised log-weights; any may be NULL */
+int smcb_fetch_state(smcb_ctx* ctx, double* x, double* w, double* logw);
+/* ancestors of steps t = 1 .. T-1 ([T-1][N], row t-1 = step t) if recording was on, else the
+ * last step's only (rows = 1).  rows_cap = rows the buffer can take. */
+int smcb_fetch_ancestors(smcb_ctx* ctx, int64_t* ancestors, int64_t rows_cap, int64_t* rows_out);
+/* device views of the current cloud (valid until the next call on ctx) */
+int smcb_device_state(smcb_ctx* ctx, const double** x_dev, const double** logw_dev, int64_t* ld);
+
+/* ------------------------------------------------------------------ M filters at once (θ-level) */
+/* Replaces the Threads.@threads / serial loops over θ-particles:
+ *   smc_samplers.jl:112-121 (rejuvenate!), :174-180 (exchange!), :223-229 (density_tempered),
+ *   :289-293 (smc²), :325-335 (smc²!).
+ * Filter m uses Philox stream (stream0 + m): give the GLOBAL θ index so that results do not depend
+ * on how θ is sharded across GPUs.  params is [M][8]; active[m]==0 skips filter m (out-of-support
+ * proposals, :116) and reports logμ = logZ = -inf.  active may be NULL (all active). */
+int smcb_batch_create(smcb_ctx* ctx, int kind, int64_t M, int64_t N, smcb_batch** out);
+int smcb_batch_destroy(smcb_batch* b);
+int smcb_batch_init(smcb_batch* b, const double* params, const uint8_t* active, double y, uint32_t stream0,
+                    double* logmu, double* ess);
+int smcb_batch_step(smcb_batch* b, const double* params, double y, int resampler, double* logmu, double* ess);
+/* whole series for every θ in ONE launch; the final clouds stay in b */
+int smcb_batch_log_likelihood(smcb_batch* b, const double* params, const uint8_t* active, const double* y,
+                              int64_t T, int resampler, uint32_t stream0, double* logZ);
+/* θ-resample: slot m takes a deep copy of slot parents[m] (x, log-weights, rng identity)
+ *   smc_samplers.jl:74-84 (with the w-permutation / aliasing defects D3, D4 fixed) */
+int smcb_batch_gather(smcb_batch* b, const int32_t* parents);
+/* MH accept: slots with accept[m]!=0 take the cloud of the same slot of `proposal`
+ *   smc_samplers.jl:130-133 */
+int smcb_batch_accept(smcb_batch* current, const smcb_batch* proposal, const uint8_t* accept);
+/* x [M][d][N], w [M][N] normalised, logw [M][N]; any may be NULL */
+int smcb_batch_fetch(smcb_batch* b, double* x, double* w, double* logw);
+/* cross-GPU moves of whole clouds (θ-resample across ranks): pack slot m into / unpack from a
+ * device buffer of smcb_batch_cloud_bytes(b) bytes that the caller sends with NCCL / P2P */
+int64_t smcb_batch_cloud_bytes(const smcb_batch* b);
+int smcb_batch_pack(smcb_batch* b, const int32_t* slots, int64_t n, void* buf_dev);
+int smcb_batch_unpack(smcb_batch* b, const int32_t* slots, int64_t n, const void* buf_dev);
+int smcb_batch_get_timing(const smcb_batch* b, double* ms_last_call, int64_t* launches_total);
+
+/* Kalman filter for LG1D, M models at once                             kalman_filter.jl:29-70
+ * params [M][8]; x, sigma [M] in/out; loglik [M] out (step log-likelihoods) */
+int smcb_kalman_batch_step(smcb_ctx* ctx, const double* params, int64_t M, double y, double* x, double* sigma,
+                           double* loglik);
+/* log_likelihood(y, model::LinearModel); matched_init=1 skips the first predict */
+int smcb_kalman_batch_loglik(smcb_ctx* ctx, const double* params, const uint8_t* active, int64_t M,
+                             const double* y, int64_t T, int matched_init, double* loglik, double* x,
+                             double* sigma);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMCB200_H */

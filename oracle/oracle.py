@@ -1,0 +1,256 @@
+"""ctypes front-end of oracle/liboracle.so plus numpy restatements of the reference's host-level
+functions.  TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+
+PARITY UNPINNED: the reference (/root/reference, Julia) has no tests or golden vectors and cannot
+run in this image; see oracle/smc_oracle.c for what pins this oracle instead.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+KIND_LG1D, KIND_SV, KIND_UCSV = 0, 1, 2
+MULTINOMIAL, STRATIFIED, SYSTEMATIC = 0, 1, 2
+P_INIT, P_TRANS, P_RESAMPLE, P_PRIOR, P_THETA_RESAMPLE, P_MH_PROPOSAL, P_MH_ACCEPT, P_SIMULATE = 1, 2, 3, 4, 5, 6, 7, 8
+
+_dp = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
+_u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
+_i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
+_u32p = np.ctypeslib.ndpointer(np.uint32, flags="C_CONTIGUOUS")
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "liboracle.so")
+    src = [os.path.join(_HERE, f) for f in ("smc_oracle.c", "det_math.h")]
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(so):
+            build()
+        L = C.CDLL(so)
+        L.smco_log_likelihood.restype = C.c_double
+        L.smco_kalman_step.restype = C.c_double
+        L.smco_kalman_loglik.restype = C.c_double
+        _LIB = L
+    return _LIB
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def params8(p):
+    out = np.zeros(8)
+    p = np.asarray(p, dtype=np.float64).ravel()
+    out[: p.size] = p
+    return out
+
+
+def state_dim(kind):
+    return 3 if kind == KIND_UCSV else 1
+
+
+def quant_shift(n):
+    return int(lib().smco_quant_shift(C.c_int64(n)))
+
+
+# ---------------------------------------------------------------- det math / RNG primitives
+def philox(ctr, key):
+    out = np.zeros(4, np.uint32)
+    lib().smco_philox(_p(np.asarray(ctr, np.uint32)), _p(np.asarray(key, np.uint32)), _p(out))
+    return out
+
+
+def det_exp(x):
+    x = np.ascontiguousarray(x, np.float64)
+    y = np.empty_like(x)
+    lib().smco_exp(_p(x), _p(y), C.c_int64(x.size))
+    return y
+
+
+def det_log(x):
+    x = np.ascontiguousarray(x, np.float64)
+    y = np.empty_like(x)
+    lib().smco_log(_p(x), _p(y), C.c_int64(x.size))
+    return y
+
+
+def det_sincos2pi(u):
+    u = np.ascontiguousarray(u, np.float64)
+    s, c = np.empty_like(u), np.empty_like(u)
+    lib().smco_sincos2pi(_p(u), _p(s), _p(c), C.c_int64(u.size))
+    return s, c
+
+
+def det_quant(x, S):
+    x = np.ascontiguousarray(x, np.float64)
+    q = np.empty(x.shape, np.uint64)
+    lib().smco_quant(_p(x), C.c_int(S), _p(q), C.c_int64(x.size))
+    return q
+
+
+def normals(seed, epoch, stream, t, kind, comp, n):
+    out = np.empty(n)
+    lib().smco_normals(C.c_uint64(seed), C.c_uint32(epoch), C.c_uint32(stream), C.c_uint32(t), C.c_uint32(kind),
+                       C.c_uint32(comp), C.c_int64(n), _p(out))
+    return out
+
+
+def uniforms64(seed, epoch, stream, t, kind, n):
+    out = np.empty(n, np.uint64)
+    lib().smco_uniforms64(C.c_uint64(seed), C.c_uint32(epoch), C.c_uint32(stream), C.c_uint32(t), C.c_uint32(kind),
+                          C.c_int64(n), _p(out))
+    return out
+
+
+def uniforms01(seed, epoch, stream, t, kind, n):
+    """(U64 >> 11) * 2^-53 in [0,1) — used by the host-level MH accept draw."""
+    return (uniforms64(seed, epoch, stream, t, kind, n) >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
+
+
+# ---------------------------------------------------------------- a1 / a2
+def normalize(logw):
+    """normalize(logw) -> (logmu, w, ess)   /root/reference/src/particles.jl:5-15"""
+    logw = np.ascontiguousarray(logw, np.float64)
+    w = np.empty_like(logw)
+    lm, es = C.c_double(), C.c_double()
+    lib().smco_normalize(_p(logw), C.c_int64(logw.size), C.byref(lm), _p(w), C.byref(es))
+    return lm.value, w, es.value
+
+
+def normalize_numpy(logw):
+    """Line-by-line numpy restatement of normalize with libm exp (tolerance cross-check)."""
+    maxw = np.max(logw)
+    w = np.exp(logw - maxw)
+    sumw = np.sum(w)
+    logmu = maxw + np.log(sumw) - np.log(len(logw))
+    w = w / sumw
+    return logmu, w, 1.0 / np.sum(w ** 2)
+
+
+def ancestors(logw, resampler, seed, epoch, stream, t):
+    """SPEC §5 ancestors from unnormalised log-weights (replaces resample, particles.jl:17-19)."""
+    logw = np.ascontiguousarray(logw, np.float64)
+    a = np.empty(logw.size, np.int64)
+    lib().smco_ancestors(_p(logw), C.c_int64(logw.size), C.c_int(resampler), C.c_uint64(seed), C.c_uint32(epoch),
+                         C.c_uint32(stream), C.c_uint32(t), _p(a))
+    return a
+
+
+def ancestors_numpy(logw, resampler, seed, epoch, stream, t):
+    """Independent numpy restatement of SPEC §5 (python ints for the 128-bit products)."""
+    n = len(logw)
+    S = quant_shift(n)
+    q = det_quant(np.asarray(logw) - np.max(logw), S)
+    Cs = np.cumsum(q, dtype=np.uint64)
+    Q = int(Cs[-1])
+    R = (2 ** 64 - 1) // n
+    U = [int(v) for v in uniforms64(seed, epoch, stream, t, P_RESAMPLE, n)]
+    out = np.empty(n, np.int64)
+    for i in range(n):
+        if Q == 0:
+            out[i] = i
+            continue
+        if resampler == MULTINOMIAL:
+            F = U[i]
+        elif resampler == STRATIFIED:
+            F = i * R + ((U[i] * R) >> 64)
+        else:
+            F = i * R + ((U[0] * R) >> 64)
+        tau = (F * Q) >> 64
+        out[i] = np.searchsorted(Cs, np.uint64(tau), side="right")
+    return out
+
+
+def resample_w(w, resampler, seed, epoch, stream, t, purpose=P_RESAMPLE):
+    w = np.ascontiguousarray(w, np.float64)
+    a = np.empty(w.size, np.int64)
+    lib().smco_resample_w(_p(w), C.c_int64(w.size), C.c_int(resampler), C.c_uint64(seed), C.c_uint32(epoch),
+                          C.c_uint32(stream), C.c_uint32(t), C.c_uint32(purpose), _p(a))
+    return a
+
+
+# ---------------------------------------------------------------- a3 / a4 / a5
+def bootstrap_init(kind, params, n, y0, seed, epoch=0, stream=0):
+    """bootstrap_filter(N, y, model) -> (x [d,n], logw)   particles.jl:87-105 (weights left unnormalised)"""
+    x = np.empty((state_dim(kind), n))
+    logw = np.empty(n)
+    lib().smco_bootstrap_init(C.c_int(kind), _p(params8(params)), C.c_int64(n), C.c_double(y0), C.c_uint64(seed),
+                              C.c_uint32(epoch), C.c_uint32(stream), _p(x), _p(logw))
+    return x, logw
+
+
+def bootstrap_step(kind, params, x, logw, y, t, resampler, seed, epoch=0, stream=0):
+    """bootstrap_filter!(x, w, y, model): mutates x, logw in place; returns the ancestors.  particles.jl:107-129"""
+    n = logw.size
+    anc = np.empty(n, np.int64)
+    lib().smco_bootstrap_step(C.c_int(kind), _p(params8(params)), C.c_int64(n), C.c_double(y), C.c_uint32(t),
+                              C.c_int(resampler), C.c_uint64(seed), C.c_uint32(epoch), C.c_uint32(stream), _p(x),
+                              _p(logw), _p(anc))
+    return anc
+
+
+def log_likelihood(kind, params, n, y, resampler, seed, epoch=0, stream=0, want_anc=False):
+    """log_likelihood(N, y, model)   particles.jl:132-147.  Returns dict(x, logw, logZ, logmu[T], ess[T], anc)."""
+    y = np.ascontiguousarray(y, np.float64)
+    T = y.size
+    x = np.empty((state_dim(kind), n))
+    logw = np.empty(n)
+    logmu, ess = np.empty(T), np.empty(T)
+    anc = np.zeros((T, n), np.int64) if want_anc else None
+    logZ = lib().smco_log_likelihood(C.c_int(kind), _p(params8(params)), C.c_int64(n), _p(y), C.c_int64(T),
+                                     C.c_int(resampler), C.c_uint64(seed), C.c_uint32(epoch), C.c_uint32(stream),
+                                     _p(x), _p(logw), _p(logmu), _p(ess), _p(anc))
+    return dict(x=x, logw=logw, logZ=logZ, logmu=logmu, ess=ess, anc=anc)
+
+
+def batch_log_likelihood(kind, params, active, n, y, resampler, seed, epoch, stream0=0, want_state=True):
+    """M filters threaded over theta (smc_samplers.jl:112-121,223-229).  params: [M,8]."""
+    params = np.ascontiguousarray(params, np.float64)
+    M = params.shape[0]
+    y = np.ascontiguousarray(y, np.float64)
+    d = state_dim(kind)
+    logZ = np.empty(M)
+    x = np.empty((M, d, n)) if want_state else None
+    logw = np.empty((M, n)) if want_state else None
+    act = None if active is None else np.ascontiguousarray(active, np.uint8)
+    lib().smco_batch_log_likelihood(C.c_int(kind), _p(params), _p(act), C.c_int64(M), C.c_int64(n), _p(y),
+                                    C.c_int64(y.size), C.c_int(resampler), C.c_uint64(seed), C.c_uint32(epoch),
+                                    C.c_uint32(stream0), _p(logZ), _p(x), _p(logw))
+    return logZ, x, logw
+
+
+def num_threads():
+    return int(lib().smco_num_threads())
+
+
+# ---------------------------------------------------------------- Kalman / simulate
+def kalman_step(params, x, S, y, predict=True):
+    xs, Ss = C.c_double(x), C.c_double(S)
+    ll = lib().smco_kalman_step(_p(params8(params)), C.byref(xs), C.byref(Ss), C.c_double(y), C.c_int(int(predict)))
+    return xs.value, Ss.value, ll
+
+
+def kalman_loglik(params, y, matched_init=False):
+    y = np.ascontiguousarray(y, np.float64)
+    xT, ST = C.c_double(), C.c_double()
+    ll = lib().smco_kalman_loglik(_p(params8(params)), _p(y), C.c_int64(y.size), C.c_int(int(matched_init)),
+                                  C.byref(xT), C.byref(ST))
+    return xT.value, ST.value, ll
+
+
+def simulate(kind, params, T, seed):
+    x = np.empty((state_dim(kind), T))
+    y = np.empty(T)
+    lib().smco_simulate(C.c_int(kind), _p(params8(params)), C.c_int64(T), C.c_uint64(seed), _p(x), _p(y))
+    return x, y

@@ -1,0 +1,307 @@
+/* ORACLE — test infrastructure only.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs may load this; the product never does.
+ *
+ * CPU restatement of the reference's particle-filter path, one function per reference function,
+ * with the un-pinned third-party pieces (RNG, Normal sampler, categorical sampler) replaced by the
+ * frozen definitions of docs/SPEC.md.  Structure deliberately mirrors the Julia code: a
+ * per-particle loop, resampling on every step, fresh temporaries on every step.
+ *
+ *   smco_normalize          <- normalize            /root/reference/src/particles.jl:5-15
+ *   smco_ancestors          <- resample             /root/reference/src/particles.jl:17-19 (SPEC §5)
+ *   smco_bootstrap_init     <- bootstrap_filter     /root/reference/src/particles.jl:87-105
+ *   smco_bootstrap_step     <- bootstrap_filter!    /root/reference/src/particles.jl:107-129
+ *   smco_log_likelihood     <- log_likelihood       /root/reference/src/particles.jl:132-147
+ *   smco_batch_log_likelihood <- the Threads.@threads loops /root/reference/src/smc_samplers.jl:112-121,223-229
+ *   model_*                 <- LinearModel / UCSV methods /root/reference/src/state_space_models.jl:74-109,215-259
+ *   smco_kalman_*           <- kalman_filter / log_likelihood /root/reference/src/kalman_filter.jl:29-70
+ *   smco_simulate           <- simulate             /root/reference/src/state_space_models.jl:11-26
+ *
+ * PARITY UNPINNED: the reference has no tests, fixtures or golden vectors and
+ * cannot be run here (Julia absent, module does not load).  What pins this file instead: Philox
+ * KATs, libm agreement of the det-math, the Kalman likelihood on LG models, closed-form normalize
+ * cases (tests/test_oracle.py).
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include "det_math.h"
+
+enum { KIND_LG1D = 0, KIND_SV = 1, KIND_UCSV = 2 };
+enum { RS_MULTINOMIAL = 0, RS_STRATIFIED = 1, RS_SYSTEMATIC = 2 };
+enum { P_INIT = 1, P_TRANS = 2, P_RESAMPLE = 3, P_SIMULATE = 8 };
+
+int smco_state_dim(int kind) { return kind == KIND_UCSV ? 3 : 1; }
+
+/* ------------------------------------------------------------------ vector math for the tests */
+void smco_philox(const uint32_t *ctr, const uint32_t *key, uint32_t *out) { o_philox(ctr, key, out); }
+void smco_exp(const double *x, double *y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = o_exp(x[i]); }
+void smco_log(const double *x, double *y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = o_log(x[i]); }
+void smco_sincos2pi(const double *u, double *s, double *c, int64_t n) {
+  for (int64_t i = 0; i < n; ++i) o_sincos2pi(u[i], &s[i], &c[i]);
+}
+void smco_quant(const double *x, int S, uint64_t *q, int64_t n) { for (int64_t i = 0; i < n; ++i) q[i] = o_quant(x[i], S); }
+void smco_normals(uint64_t seed, uint32_t epoch, uint32_t stream, uint32_t t, uint32_t kind, uint32_t comp,
+                  int64_t n, double *out) {
+  for (int64_t i = 0; i < n; ++i) out[i] = o_normal(seed, epoch, (uint32_t)i, stream, t, kind, comp);
+}
+void smco_uniforms64(uint64_t seed, uint32_t epoch, uint32_t stream, uint32_t t, uint32_t kind, int64_t n,
+                     uint64_t *out) {
+  for (int64_t i = 0; i < n; ++i) out[i] = o_uniform64(seed, epoch, (uint32_t)i, stream, t, kind);
+}
+int smco_quant_shift(int64_t n) {
+  int c = 0;
+  while (((int64_t)1 << c) < n) ++c;
+  return 61 - c;
+}
+
+/* ------------------------------------------------------------------ models (SPEC §4) */
+void smco_derive(int kind, const double *P, double *D) {
+  for (int i = 0; i < 8; ++i) D[i] = 0.0;
+  if (kind == KIND_LG1D) { /* A,B,Q,R,x0,s0 : state_space_models.jl:74-109 */
+    double sr = sqrt(P[3]);
+    D[0] = P[0]; D[1] = P[1]; D[2] = sqrt(P[2]); D[3] = P[4]; D[4] = sqrt(P[5]);
+    D[5] = 1.0 / sr;
+    D[6] = -(o_log(sr) + O_HALF_LOG_2PI);
+  } else if (kind == KIND_SV) {
+    D[0] = P[0]; D[1] = P[1]; D[2] = P[2];
+    D[3] = P[2] / sqrt(1.0 - P[1] * P[1]);
+  } else { /* UCSV: state_space_models.jl:215-259 */
+    D[0] = P[0]; D[1] = P[1]; D[2] = P[2]; D[3] = P[3]; D[4] = P[4];
+    D[5] = o_exp(0.5 * P[3]);
+  }
+}
+
+/* x: the d state components of one particle; z: d standard normals */
+static void model_init(int kind, const double *D, const double *z, double *x) {
+  if (kind == KIND_LG1D) {
+    x[0] = fma(D[4], z[0], D[3]);                 /* Normal(x0, sqrt(s0)) :105-109 */
+  } else if (kind == KIND_SV) {
+    x[0] = fma(D[3], z[0], D[0]);
+  } else {
+    x[0] = fma(D[5], z[0], D[2]);                 /* Normal(x0, exp(0.5 lse0)) :255 */
+    x[1] = fma(D[0], z[1], D[3]);                 /* Normal(lse0, ge) :256 */
+    x[2] = fma(D[1], z[2], D[4]);                 /* Normal(lsn0, gn) :257 */
+  }
+}
+static void model_transition(int kind, const double *D, const double *z, const double *xp, double *x) {
+  if (kind == KIND_LG1D) {
+    x[0] = fma(D[2], z[0], D[0] * xp[0]);         /* Normal(A x, sqrt(Q)) :87-94 */
+  } else if (kind == KIND_SV) {
+    x[0] = fma(D[2], z[0], fma(D[1], xp[0] - D[0], D[0]));
+  } else {
+    double sd = o_exp(0.5 * xp[1]);               /* previous log-vol :238 */
+    x[0] = fma(sd, z[0], xp[0]);
+    x[1] = fma(D[0], z[1], xp[1]);
+    x[2] = fma(D[1], z[2], xp[2]);
+  }
+}
+static double model_logweight(int kind, const double *D, const double *x, double y) {
+  if (kind == KIND_LG1D) {                        /* logpdf(Normal(B x, sqrt(R)), y) :96-103 */
+    double v = (y - D[1] * x[0]) * D[5];
+    return fma(-0.5 * v, v, D[6]);
+  } else if (kind == KIND_SV) {
+    return fma(-0.5 * (y * y), o_exp(-x[0]), -(fma(0.5, x[0], O_HALF_LOG_2PI)));
+  } else {                                        /* Normal(x, exp(0.5 lsn)) with current lsn :244-247 */
+    double d = y - x[0];
+    return fma(-0.5 * (d * d), o_exp(-x[2]), -(fma(0.5, x[2], O_HALF_LOG_2PI)));
+  }
+}
+
+/* ------------------------------------------------------------------ a1 normalize */
+void smco_normalize(const double *logw, int64_t n, double *logmu, double *w, double *ess) {
+  double maxw = -INFINITY;
+  for (int64_t i = 0; i < n; ++i) if (logw[i] > maxw) maxw = logw[i];      /* :6 */
+  double *e = (double *)malloc(sizeof(double) * (size_t)n);
+  double sumw = 0.0;
+  for (int64_t i = 0; i < n; ++i) { e[i] = o_exp(logw[i] - maxw); sumw += e[i]; } /* :7-8 */
+  *logmu = maxw + log(sumw) - log((double)n);                              /* :10 */
+  double s2 = 0.0;
+  for (int64_t i = 0; i < n; ++i) { double wi = e[i] / sumw; if (w) w[i] = wi; s2 += wi * wi; } /* :11-12 */
+  *ess = 1.0 / s2;
+  free(e);
+}
+
+/* ------------------------------------------------------------------ a2 resample (SPEC §5) */
+static void ancestors_from_q(const uint64_t *q, int64_t n, int resampler, uint64_t seed, uint32_t epoch,
+                             uint32_t stream, uint32_t t, uint32_t purpose, int64_t *anc) {
+  uint64_t *C = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)n);
+  uint64_t run = 0;
+  for (int64_t j = 0; j < n; ++j) { run += q[j]; C[j] = run; }
+  uint64_t Q = run;
+  uint64_t R = 0xFFFFFFFFFFFFFFFFull / (uint64_t)n;
+  uint64_t U0 = o_uniform64(seed, epoch, 0, stream, t, purpose);
+  for (int64_t i = 0; i < n; ++i) {
+    if (Q == 0) { anc[i] = i; continue; }
+    uint64_t F;
+    if (resampler == RS_MULTINOMIAL) F = o_uniform64(seed, epoch, (uint32_t)i, stream, t, purpose);
+    else if (resampler == RS_STRATIFIED) F = (uint64_t)i * R + o_mulhi(o_uniform64(seed, epoch, (uint32_t)i, stream, t, purpose), R);
+    else F = (uint64_t)i * R + o_mulhi(U0, R);
+    uint64_t tau = o_mulhi(F, Q);
+    int64_t lo = 0, hi = n;                   /* a = #{j : C_j <= tau} */
+    while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (C[mid] <= tau) lo = mid + 1; else hi = mid; }
+    anc[i] = lo;
+  }
+  free(C);
+}
+
+void smco_ancestors(const double *logw, int64_t n, int resampler, uint64_t seed, uint32_t epoch, uint32_t stream,
+                    uint32_t t, int64_t *anc) {
+  int S = smco_quant_shift(n);
+  double mx = -INFINITY;
+  for (int64_t i = 0; i < n; ++i) if (logw[i] > mx) mx = logw[i];
+  uint64_t *q = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)n);
+  for (int64_t i = 0; i < n; ++i) q[i] = o_quant(logw[i] - mx, S);
+  ancestors_from_q(q, n, resampler, seed, epoch, stream, t, P_RESAMPLE, anc);
+  free(q);
+}
+
+/* standalone resample(w): q_i = trunc((w_i / max w) 2^S) */
+void smco_resample_w(const double *w, int64_t n, int resampler, uint64_t seed, uint32_t epoch, uint32_t stream,
+                     uint32_t t, uint32_t purpose, int64_t *anc) {
+  int S = smco_quant_shift(n);
+  double mx = 0.0;
+  for (int64_t i = 0; i < n; ++i) if (w[i] > mx) mx = w[i];
+  uint64_t *q = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)n);
+  double scale = o_from_bits((uint64_t)(1023 + S) << 52);
+  for (int64_t i = 0; i < n; ++i) q[i] = (mx > 0.0 && w[i] > 0.0) ? (uint64_t)((w[i] / mx) * scale) : 0;
+  ancestors_from_q(q, n, resampler, seed, epoch, stream, t, purpose, anc);
+  free(q);
+}
+
+/* ------------------------------------------------------------------ a3 bootstrap_filter */
+/* x is SoA [d][n]. */
+void smco_bootstrap_init(int kind, const double *P, int64_t n, double y, uint64_t seed, uint32_t epoch,
+                         uint32_t stream, double *x, double *logw) {
+  double D[8];
+  smco_derive(kind, P, D);
+  int d = smco_state_dim(kind);
+  for (int64_t i = 0; i < n; ++i) {                                         /* :96-99 */
+    double z[3] = {0, 0, 0}, xi[3];
+    for (int k = 0; k < d; ++k) z[k] = o_normal(seed, epoch, (uint32_t)i, stream, 0, P_INIT, (uint32_t)k);
+    model_init(kind, D, z, xi);
+    for (int k = 0; k < d; ++k) x[(int64_t)k * n + i] = xi[k];
+    logw[i] = model_logweight(kind, D, xi, y);
+  }
+}
+
+/* ------------------------------------------------------------------ a4 bootstrap_filter! */
+void smco_bootstrap_step(int kind, const double *P, int64_t n, double y, uint32_t t, int resampler, uint64_t seed,
+                         uint32_t epoch, uint32_t stream, double *x, double *logw, int64_t *anc_out) {
+  double D[8];
+  smco_derive(kind, P, D);
+  int d = smco_state_dim(kind);
+  int64_t *a = (int64_t *)malloc(sizeof(int64_t) * (size_t)n);              /* a = resample(weights) :117 */
+  smco_ancestors(logw, n, resampler, seed, epoch, stream, t, a);
+  double *xp = (double *)malloc(sizeof(double) * (size_t)(n * d));         /* xp = deepcopy(x[a]) :119 */
+  for (int k = 0; k < d; ++k)
+    for (int64_t i = 0; i < n; ++i) xp[(int64_t)k * n + i] = x[(int64_t)k * n + a[i]];
+  for (int64_t i = 0; i < n; ++i) {                                         /* :122-125 */
+    double z[3] = {0, 0, 0}, par[3] = {0, 0, 0}, xi[3];
+    for (int k = 0; k < d; ++k) {
+      z[k] = o_normal(seed, epoch, (uint32_t)i, stream, t, P_TRANS, (uint32_t)k);
+      par[k] = xp[(int64_t)k * n + i];
+    }
+    model_transition(kind, D, z, par, xi);
+    for (int k = 0; k < d; ++k) x[(int64_t)k * n + i] = xi[k];
+    logw[i] = model_logweight(kind, D, xi, y);
+  }
+  if (anc_out) memcpy(anc_out, a, sizeof(int64_t) * (size_t)n);
+  free(xp);
+  free(a);
+}
+
+/* ------------------------------------------------------------------ a5 log_likelihood */
+double smco_log_likelihood(int kind, const double *P, int64_t n, const double *y, int64_t T, int resampler,
+                           uint64_t seed, uint32_t epoch, uint32_t stream, double *x, double *logw,
+                           double *logmu_out, double *ess_out, int64_t *anc_out) {
+  int d = smco_state_dim(kind);
+  double *xl = x ? x : (double *)malloc(sizeof(double) * (size_t)(n * d));
+  double *lw = logw ? logw : (double *)malloc(sizeof(double) * (size_t)n);
+  double logZ = 0.0, lm, es;
+  smco_bootstrap_init(kind, P, n, y[0], seed, epoch, stream, xl, lw);       /* :139 */
+  smco_normalize(lw, n, &lm, NULL, &es);
+  logZ = lm;
+  if (logmu_out) logmu_out[0] = lm;
+  if (ess_out) ess_out[0] = es;
+  for (int64_t t = 1; t < T; ++t) {                                         /* :141-144 */
+    smco_bootstrap_step(kind, P, n, y[t], (uint32_t)t, resampler, seed, epoch, stream, xl, lw,
+                        anc_out ? anc_out + t * n : NULL);
+    smco_normalize(lw, n, &lm, NULL, &es);
+    logZ += lm;
+    if (logmu_out) logmu_out[t] = lm;
+    if (ess_out) ess_out[t] = es;
+  }
+  if (!x) free(xl);
+  if (!logw) free(lw);
+  return logZ;
+}
+
+/* M independent filters, threaded over theta like Threads.@threads (smc_samplers.jl:112,223).
+ * Filter m uses Philox stream (stream0 + m); inactive filters (out-of-support proposals, :116) are
+ * skipped and report logZ = -inf. x: [M][d][n], logw: [M][n]; either may be NULL. */
+void smco_batch_log_likelihood(int kind, const double *P, const uint8_t *active, int64_t M, int64_t n,
+                               const double *y, int64_t T, int resampler, uint64_t seed, uint32_t epoch,
+                               uint32_t stream0, double *logZ, double *x, double *logw) {
+  int d = smco_state_dim(kind);
+#pragma omp parallel for schedule(static)
+  for (int64_t m = 0; m < M; ++m) {
+    if (active && !active[m]) { logZ[m] = -INFINITY; continue; }
+    logZ[m] = smco_log_likelihood(kind, P + 8 * m, n, y, T, resampler, seed, epoch, stream0 + (uint32_t)m,
+                                  x ? x + m * d * n : NULL, logw ? logw + m * n : NULL, NULL, NULL, NULL);
+  }
+}
+
+int smco_num_threads(void) {
+#ifdef _OPENMP
+  return omp_get_max_threads();
+#else
+  return 1;
+#endif
+}
+
+/* ------------------------------------------------------------------ a16 Kalman (scalar) */
+/* kalman_filter.jl:29-53: predict, then update, returns the step log-likelihood */
+double smco_kalman_step(const double *P, double *xt, double *St, double yt, int predict) {
+  double A = P[0], B = P[1], Q = P[2], R = P[3];
+  double x = *xt, S = *St;
+  if (predict) { x = A * x; S = (A * A) * S + Q; }
+  double sig = (B * B) * S + R;
+  double dy = yt - B * x;
+  x = x + (S * B) * (1.0 / sig) * dy;
+  S = S - ((S * B) * (S * B)) * (1.0 / sig);
+  *xt = x; *St = S;
+  return -0.5 * (log(2.0 * M_PI) + log(sig) + (dy / sig * dy));
+}
+/* kalman_filter.jl:55-70. matched_init=1 skips the first predict so the target equals the
+ * particle filter's (x1 ~ N(x0, s0) with no transition). */
+double smco_kalman_loglik(const double *P, const double *y, int64_t T, int matched_init, double *xT, double *ST) {
+  double x = P[4], S = P[5], ll = 0.0;
+  for (int64_t t = 0; t < T; ++t) ll += smco_kalman_step(P, &x, &S, y[t], !(matched_init && t == 0));
+  if (xT) *xT = x;
+  if (ST) *ST = S;
+  return ll;
+}
+
+/* ------------------------------------------------------------------ simulate */
+/* state_space_models.jl:11-26 with Philox purpose 8: stream 0 = state noise, stream 1 = obs noise.
+ * The observation draw inverts the model's weight function: y = mean + sd * z. */
+void smco_simulate(int kind, const double *P, int64_t T, uint64_t seed, double *x, double *y) {
+  double D[8];
+  smco_derive(kind, P, D);
+  int d = smco_state_dim(kind);
+  double cur[3] = {0, 0, 0}, nxt[3];
+  for (int64_t t = 0; t < T; ++t) {
+    double z[3] = {0, 0, 0};
+    for (int k = 0; k < d; ++k) z[k] = o_normal(seed, 0, (uint32_t)t, 0, 0, P_SIMULATE, (uint32_t)k);
+    if (t == 0) model_init(kind, D, z, nxt); else model_transition(kind, D, z, cur, nxt);
+    for (int k = 0; k < d; ++k) { cur[k] = nxt[k]; x[(int64_t)k * T + t] = cur[k]; }
+    double zo = o_normal(seed, 0, (uint32_t)t, 1, 0, P_SIMULATE, 0);
+    double mean, sd;
+    if (kind == KIND_LG1D) { mean = D[1] * cur[0]; sd = sqrt(P[3]); }
+    else if (kind == KIND_SV) { mean = 0.0; sd = o_exp(0.5 * cur[0]); }
+    else { mean = cur[0]; sd = o_exp(0.5 * cur[2]); }
+    y[t] = fma(sd, zo, mean);
+  }
+}

@@ -1,0 +1,329 @@
+"""ctypes binding of libsmcb200.so (include/smcb200.h) — the only way the Python host code reaches
+the GPU.  There is no CPU fallback: a missing library or a missing CUDA device raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+LG1D, SV, UCSV = 0, 1, 2
+MULTINOMIAL, STRATIFIED, SYSTEMATIC = 0, 1, 2
+PARAM_STRIDE = 8
+# Philox purposes of the host-level streams (docs/SPEC.md §2)
+P_PRIOR, P_THETA_RESAMPLE, P_MH_PROPOSAL, P_MH_ACCEPT, P_SIMULATE = 4, 5, 6, 7, 8
+
+_c_ctx = C.c_void_p
+_c_batch = C.c_void_p
+_dp = C.POINTER(C.c_double)
+_i64p = C.POINTER(C.c_int64)
+
+# name -> (restype, argtypes); every symbol include/smcb200.h declares
+SIGNATURES = {
+    "smcb_create": (C.c_int, [C.c_int, C.c_uint64, C.POINTER(_c_ctx)]),
+    "smcb_destroy": (C.c_int, [_c_ctx]),
+    "smcb_last_error": (C.c_char_p, [_c_ctx]),
+    "smcb_version": (C.c_int, []),
+    "smcb_state_dim": (C.c_int, [C.c_int]),
+    "smcb_set_rng": (C.c_int, [_c_ctx, C.c_uint64, C.c_uint32]),
+    "smcb_get_epoch": (C.c_int, [_c_ctx, C.POINTER(C.c_uint32)]),
+    "smcb_record_ancestors": (C.c_int, [_c_ctx, C.c_int]),
+    "smcb_set_profiling": (C.c_int, [_c_ctx, C.c_int]),
+    "smcb_get_timing": (C.c_int, [_c_ctx, _dp, _i64p]),
+    "smcb_synchronize": (C.c_int, [_c_ctx]),
+    "smcb_normalize": (C.c_int, [_c_ctx, C.c_void_p, C.c_int64, _dp, C.c_void_p, _dp]),
+    "smcb_resample": (C.c_int, [_c_ctx, C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "smcb_bootstrap_init": (C.c_int, [_c_ctx, C.c_int, C.c_void_p, C.c_int64, C.c_double, C.c_uint32, _dp, _dp]),
+    "smcb_bootstrap_step": (C.c_int, [_c_ctx, C.c_void_p, C.c_double, C.c_int, _dp, _dp]),
+    "smcb_log_likelihood": (C.c_int, [_c_ctx, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_uint32,
+                                      _dp, C.c_void_p, C.c_void_p]),
+    "smcb_fetch_state": (C.c_int, [_c_ctx, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "smcb_fetch_ancestors": (C.c_int, [_c_ctx, C.c_void_p, C.c_int64, _i64p]),
+    "smcb_device_state": (C.c_int, [_c_ctx, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i64p]),
+    "smcb_batch_create": (C.c_int, [_c_ctx, C.c_int, C.c_int64, C.c_int64, C.POINTER(_c_batch)]),
+    "smcb_batch_destroy": (C.c_int, [_c_batch]),
+    "smcb_batch_init": (C.c_int, [_c_batch, C.c_void_p, C.c_void_p, C.c_double, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "smcb_batch_step": (C.c_int, [_c_batch, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
+    "smcb_batch_log_likelihood": (C.c_int, [_c_batch, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_uint32,
+                                            C.c_void_p]),
+    "smcb_batch_gather": (C.c_int, [_c_batch, C.c_void_p]),
+    "smcb_batch_accept": (C.c_int, [_c_batch, _c_batch, C.c_void_p]),
+    "smcb_batch_fetch": (C.c_int, [_c_batch, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "smcb_batch_cloud_bytes": (C.c_int64, [_c_batch]),
+    "smcb_batch_pack": (C.c_int, [_c_batch, C.c_void_p, C.c_int64, C.c_void_p]),
+    "smcb_batch_unpack": (C.c_int, [_c_batch, C.c_void_p, C.c_int64, C.c_void_p]),
+    "smcb_batch_get_timing": (C.c_int, [_c_batch, _dp, _i64p]),
+    "smcb_kalman_batch_step": (C.c_int, [_c_ctx, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "smcb_kalman_batch_loglik": (C.c_int, [_c_ctx, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int,
+                                           C.c_void_p, C.c_void_p, C.c_void_p]),
+}
+
+_LIB = None
+
+
+class SMCBError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libsmcb200 error {code}: {msg}")
+        self.code = code
+
+
+def library_path():
+    return _build.LIB_PATH
+
+
+def load():
+    """dlopen libsmcb200.so (building it first if the sources are newer) and bind every symbol."""
+    global _LIB
+    if _LIB is None:
+        path = _build.LIB_PATH
+        if not os.path.exists(path):
+            path = _build.build_library()
+        lib = C.CDLL(path)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = lib
+    return _LIB
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def params8(p):
+    """[..., k<=8] -> contiguous [..., 8] float64 parameter block(s)."""
+    p = np.asarray(p, dtype=np.float64)
+    out = np.zeros(p.shape[:-1] + (PARAM_STRIDE,), dtype=np.float64)
+    out[..., : p.shape[-1]] = p
+    return np.ascontiguousarray(out)
+
+
+def state_dim(kind):
+    return 3 if kind == UCSV else 1
+
+
+class Context:
+    """One GPU + one stream + one single-filter slot (smcb_ctx)."""
+
+    def __init__(self, device=0, seed=0):
+        self._lib = load()
+        self._h = _c_ctx()
+        rc = self._lib.smcb_create(int(device), C.c_uint64(int(seed) & (2 ** 64 - 1)), C.byref(self._h))
+        if rc != 0:
+            msg = self._lib.smcb_last_error(None)
+            raise SMCBError(rc, msg.decode() if msg else "smcb_create failed")
+        self.device = int(device)
+        self.seed = int(seed)
+        self._N = 0
+        self._kind = LG1D
+        self._T = 0
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.smcb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self._lib.smcb_last_error(self._h)
+            raise SMCBError(rc, msg.decode() if msg else "")
+
+    # ---- rng / instrumentation
+    def set_rng(self, seed, epoch=0):
+        self.seed = int(seed)
+        self._check(self._lib.smcb_set_rng(self._h, C.c_uint64(int(seed) & (2 ** 64 - 1)), int(epoch)))
+
+    def next_epoch(self):
+        e = C.c_uint32()
+        self._check(self._lib.smcb_get_epoch(self._h, C.byref(e)))
+        return e.value
+
+    def record_ancestors(self, on=True):
+        self._check(self._lib.smcb_record_ancestors(self._h, int(bool(on))))
+
+    def set_profiling(self, on=True):
+        self._check(self._lib.smcb_set_profiling(self._h, int(bool(on))))
+
+    def timing(self):
+        ms = (C.c_double * 5)()
+        n = (C.c_int64 * 5)()
+        self._check(self._lib.smcb_get_timing(self._h, ms, n))
+        keys = ("total", "scan", "prop", "init", "stats")
+        return {k: float(ms[i]) for i, k in enumerate(keys)}, {k: int(n[i]) for i, k in enumerate(keys)}
+
+    def synchronize(self):
+        self._check(self._lib.smcb_synchronize(self._h))
+
+    # ---- utilities
+    def normalize(self, logw, want_w=True):
+        logw = np.ascontiguousarray(logw, np.float64)
+        w = np.empty_like(logw) if want_w else None
+        lm, es = C.c_double(), C.c_double()
+        self._check(self._lib.smcb_normalize(self._h, _ptr(logw), logw.size, C.byref(lm), _ptr(w), C.byref(es)))
+        return lm.value, w, es.value
+
+    def resample(self, w, resampler=MULTINOMIAL, stream=0, t=0, purpose=3):
+        w = np.ascontiguousarray(w, np.float64)
+        a = np.empty(w.size, np.int64)
+        self._check(self._lib.smcb_resample(self._h, _ptr(w), w.size, int(resampler), int(stream), int(t), int(purpose), _ptr(a)))
+        return a
+
+    # ---- one filter
+    def bootstrap_init(self, kind, params, N, y, stream=0):
+        p = params8(params)
+        lm, es = C.c_double(), C.c_double()
+        self._check(self._lib.smcb_bootstrap_init(self._h, int(kind), _ptr(p), int(N), float(y), int(stream), C.byref(lm), C.byref(es)))
+        self._N, self._kind, self._T = int(N), int(kind), 1
+        return lm.value, es.value
+
+    def bootstrap_step(self, y, resampler=MULTINOMIAL, params=None):
+        p = None if params is None else params8(params)
+        lm, es = C.c_double(), C.c_double()
+        self._check(self._lib.smcb_bootstrap_step(self._h, _ptr(p), float(y), int(resampler), C.byref(lm), C.byref(es)))
+        self._T += 1
+        return lm.value, es.value
+
+    def log_likelihood(self, kind, params, N, y, resampler=MULTINOMIAL, stream=0, per_step=False):
+        p = params8(params)
+        y = np.ascontiguousarray(y, np.float64)
+        T = y.size
+        z = C.c_double()
+        lm = np.empty(T) if per_step else None
+        es = np.empty(T) if per_step else None
+        self._check(self._lib.smcb_log_likelihood(self._h, int(kind), _ptr(p), int(N), _ptr(y), T, int(resampler), int(stream),
+                                                  C.byref(z), _ptr(lm), _ptr(es)))
+        self._N, self._kind, self._T = int(N), int(kind), T
+        return (z.value, lm, es) if per_step else z.value
+
+    def fetch_state(self, want_x=True, want_w=True, want_logw=False):
+        d = state_dim(self._kind)
+        x = np.empty((d, self._N)) if want_x else None
+        w = np.empty(self._N) if want_w else None
+        lw = np.empty(self._N) if want_logw else None
+        self._check(self._lib.smcb_fetch_state(self._h, _ptr(x), _ptr(w), _ptr(lw)))
+        return x, w, lw
+
+    def fetch_ancestors(self, rows):
+        a = np.empty((max(int(rows), 1), self._N), np.int64)
+        got = C.c_int64()
+        self._check(self._lib.smcb_fetch_ancestors(self._h, _ptr(a), a.shape[0], C.byref(got)))
+        return a[: got.value]
+
+    # ---- Kalman
+    def kalman_step(self, params, x, sigma, y):
+        p = params8(params).reshape(-1, PARAM_STRIDE)
+        M = p.shape[0]
+        x = np.ascontiguousarray(np.broadcast_to(np.asarray(x, np.float64), (M,))).copy()
+        s = np.ascontiguousarray(np.broadcast_to(np.asarray(sigma, np.float64), (M,))).copy()
+        ll = np.empty(M)
+        self._check(self._lib.smcb_kalman_batch_step(self._h, _ptr(p), M, float(y), _ptr(x), _ptr(s), _ptr(ll)))
+        return x, s, ll
+
+    def kalman_loglik(self, params, y, matched_init=False, active=None):
+        p = params8(params).reshape(-1, PARAM_STRIDE)
+        M = p.shape[0]
+        y = np.ascontiguousarray(y, np.float64)
+        act = None if active is None else np.ascontiguousarray(active, np.uint8)
+        ll, x, s = np.empty(M), np.empty(M), np.empty(M)
+        self._check(self._lib.smcb_kalman_batch_loglik(self._h, _ptr(p), _ptr(act), M, _ptr(y), y.size, int(bool(matched_init)),
+                                                       _ptr(ll), _ptr(x), _ptr(s)))
+        return ll, x, s
+
+    def batch(self, kind, M, N):
+        return Batch(self, kind, M, N)
+
+
+class Batch:
+    """M filters of N particles (smcb_batch): the particle-of-filters of SMC² / PMMH sweeps."""
+
+    def __init__(self, ctx, kind, M, N):
+        self.ctx = ctx
+        self._lib = ctx._lib
+        self.kind, self.M, self.N = int(kind), int(M), int(N)
+        self.d = state_dim(self.kind)
+        self._h = _c_batch()
+        ctx._check(self._lib.smcb_batch_create(ctx._h, self.kind, self.M, self.N, C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
+            self._lib.smcb_batch_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _params(self, params):
+        if params is None:
+            return None
+        p = params8(params).reshape(-1, PARAM_STRIDE)
+        if p.shape[0] != self.M:
+            raise ValueError(f"params must have {self.M} rows")
+        return p
+
+    @staticmethod
+    def _mask(m):
+        return None if m is None else np.ascontiguousarray(m, np.uint8)
+
+    def init(self, params, y, stream0=0, active=None):
+        p, act = self._params(params), self._mask(active)
+        lm, es = np.empty(self.M), np.empty(self.M)
+        self.ctx._check(self._lib.smcb_batch_init(self._h, _ptr(p), _ptr(act), float(y), int(stream0), _ptr(lm), _ptr(es)))
+        return lm, es
+
+    def step(self, y, resampler=MULTINOMIAL, params=None):
+        p = self._params(params)
+        lm, es = np.empty(self.M), np.empty(self.M)
+        self.ctx._check(self._lib.smcb_batch_step(self._h, _ptr(p), float(y), int(resampler), _ptr(lm), _ptr(es)))
+        return lm, es
+
+    def log_likelihood(self, params, y, resampler=MULTINOMIAL, stream0=0, active=None):
+        p, act = self._params(params), self._mask(active)
+        y = np.ascontiguousarray(y, np.float64)
+        z = np.empty(self.M)
+        self.ctx._check(self._lib.smcb_batch_log_likelihood(self._h, _ptr(p), _ptr(act), _ptr(y), y.size, int(resampler),
+                                                            int(stream0), _ptr(z)))
+        return z
+
+    def gather(self, parents):
+        a = np.ascontiguousarray(parents, np.int32)
+        if a.size != self.M:
+            raise ValueError("parents must have M entries")
+        self.ctx._check(self._lib.smcb_batch_gather(self._h, _ptr(a)))
+
+    def accept(self, proposal, accept):
+        m = self._mask(accept)
+        self.ctx._check(self._lib.smcb_batch_accept(self._h, proposal._h, _ptr(m)))
+
+    def fetch(self, want_x=True, want_w=True, want_logw=False):
+        x = np.empty((self.M, self.d, self.N)) if want_x else None
+        w = np.empty((self.M, self.N)) if want_w else None
+        lw = np.empty((self.M, self.N)) if want_logw else None
+        self.ctx._check(self._lib.smcb_batch_fetch(self._h, _ptr(x), _ptr(w), _ptr(lw)))
+        return x, w, lw
+
+    def cloud_bytes(self):
+        return int(self._lib.smcb_batch_cloud_bytes(self._h))
+
+    def pack(self, slots, buf_dev_ptr):
+        s = np.ascontiguousarray(slots, np.int32)
+        self.ctx._check(self._lib.smcb_batch_pack(self._h, _ptr(s), s.size, C.c_void_p(int(buf_dev_ptr))))
+
+    def unpack(self, slots, buf_dev_ptr):
+        s = np.ascontiguousarray(slots, np.int32)
+        self.ctx._check(self._lib.smcb_batch_unpack(self._h, _ptr(s), s.size, C.c_void_p(int(buf_dev_ptr))))
+
+    def timing(self):
+        ms, n = C.c_double(), C.c_int64()
+        self.ctx._check(self._lib.smcb_batch_get_timing(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value

@@ -1,0 +1,63 @@
+"""Builds libsmcb200.so (hand-written sm_100a CUDA + the C ABI of include/smcb200.h) in-tree.
+
+nvcc cross-compiles without a GPU.  -fmad=false: only the fma() calls written in the sources fuse
+(docs/SPEC.md), which is what makes ancestors and states bit-identical to the CPU oracle.
+"""
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_DIR = os.path.join(_HERE, "lib")
+LIB_PATH = os.path.join(LIB_DIR, "libsmcb200.so")
+SOURCES = ["smcb_filter.cu", "smcb_batch.cu", "smcb_capi.cu"]
+HEADERS = ["smcb_common.cuh", "smcb_detmath.cuh", "smcb_models.cuh", "smcb_filter.cuh", "smcb_batch.cuh",
+           os.path.join("..", "..", "include", "smcb200.h")]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off",
+    "-diag-suppress", "177",
+]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    return "nvcc"
+
+
+def _stale():
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_library(force=False, verbose=False):
+    """Compile every CUDA source into sequential_monte_carlo_b200/lib/libsmcb200.so; returns its path."""
+    if not force and not _stale():
+        return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    objs = []
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(LIB_DIR, src.replace(".cu", ".o"))
+        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for cmd, p in procs:
+        out, _ = p.communicate()
+        if verbose or p.returncode != 0:
+            sys.stderr.write(out)
+        if p.returncode != 0:
+            raise RuntimeError("nvcc failed: " + " ".join(cmd))
+    link = [_nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
+    subprocess.check_call(link)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

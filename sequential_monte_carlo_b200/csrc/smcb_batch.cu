@@ -1,0 +1,691 @@
+// Batched bootstrap filters: one CTA per θ-particle, cloud + CDF resident in shared memory for the
+// whole series, so a sweep of T observations is ONE launch and touches HBM only for the final
+// clouds (docs/SPEC.md §5-§7; same arithmetic as the grid-wide kernels of smcb_filter.cu, so the
+// ancestors are bit-identical to the oracle's).
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+#include "smcb_batch.cuh"
+
+namespace smcb {
+
+namespace {
+
+struct BatchArgs {
+  const double* derived;   // [M][8]
+  const uint8_t* active;   // [M] or null
+  const double* y;         // observations consumed by this launch, y[0] is for time t_begin
+  double* x;               // [M][d][ld]
+  double* logw;            // [M][ld]
+  StepStats* stats;        // [M]
+  double* logz_out;        // [M]  Σ logμ over the steps this launch accounts for
+  double* ess_out;         // [M]
+  int64_t N, ld;
+  int S;
+  uint64_t R;
+  RngKey key;
+  uint32_t stream0;
+  uint32_t t_begin, t_end;  // inclusive range of time indices assimilated by this launch
+  int resampler;
+  int from_init;            // t_begin == 0 draws the cloud; else continue from (x, logw, stats)
+  int x_in_smem;
+  int64_t npad;             // N rounded up to even
+};
+
+__device__ __forceinline__ int smem_lower_count(const uint64_t* C, int lo, int hi, uint64_t tau) {
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (C[mid] <= tau) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+template <class Model, int PAIRS, int MAXT>
+__global__ void __launch_bounds__(MAXT) batch_kernel(const BatchArgs a) {
+  constexpr int D = Model::D;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ unsigned long long s_wq[PAIRS][32];
+  __shared__ double s_f[3][32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nthreads = blockDim.x, nwarps = nthreads >> 5;
+  const int64_t m = blockIdx.x;
+  if (a.active && !a.active[m]) {
+    if (tid == 0) {
+      a.logz_out[m] = -INFINITY;
+      a.ess_out[m] = 0.0;
+    }
+    return;
+  }
+  const int N = (int)a.N;
+  const int64_t ld = a.ld;
+  const int npairs = (N + 1) >> 1;
+  uint64_t* s_cdf = reinterpret_cast<uint64_t*>(smem_raw);
+  double* xs = a.x_in_smem ? reinterpret_cast<double*>(smem_raw + sizeof(uint64_t) * a.npad) : (a.x + m * D * ld);
+  const int64_t ldx = a.x_in_smem ? a.npad : ld;
+  double* gx = a.x + m * D * ld;
+  double* glw = a.logw + m * ld;
+
+  Model mdl;
+  mdl.load(a.derived + m * kParamStride);
+  const uint32_t stream = a.stream0 + (uint32_t)m;
+  const double logN = log((double)N);
+
+  double lw[PAIRS][2];
+  double mx = -INFINITY;
+  double logz = 0.0;
+  bool account = true;
+
+  // block-uniform max of the thread-local log-weights (exact, order-independent)
+  auto block_max_all = [&](double v) -> double {
+    v = warp_max(v);
+    if (lane == 0) s_f[2][warp] = v;
+    __syncthreads();
+    double r = (lane < nwarps) ? s_f[2][lane] : -INFINITY;
+    return warp_max(r);
+  };
+
+  if (!a.from_init) {
+    // continue from the stored cloud
+#pragma unroll
+    for (int r = 0; r < PAIRS; ++r) {
+      const int p = r * nthreads + tid;
+      const int i = 2 * p;
+      lw[r][0] = (i < N) ? glw[i] : -INFINITY;
+      lw[r][1] = (i + 1 < N) ? glw[i + 1] : -INFINITY;
+      if (a.x_in_smem && p < npairs) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          xs[k * ldx + i] = gx[k * ld + i];
+          if (i + 1 < N) xs[k * ldx + i + 1] = gx[k * ld + i + 1];
+        }
+      }
+    }
+    mx = a.stats[m].mx;
+    account = false;  // the stored weights' logμ was reported by the launch that produced them
+    __syncthreads();
+  }
+
+  for (uint32_t t = a.t_begin; t <= a.t_end; ++t) {
+    const double y = a.y[t - a.t_begin];
+    if (t == 0 && a.from_init) {
+      // bootstrap_filter: x_i ~ initial_dist; logw_i = logpdf(observation(x_i), y1)   particles.jl:96-99
+#pragma unroll
+      for (int r = 0; r < PAIRS; ++r) {
+        const int p = r * nthreads + tid;
+        const int i = 2 * p;
+        lw[r][0] = lw[r][1] = -INFINITY;
+        if (p < npairs) {
+          double za[D], zb[D], xa[D], xb[D];
+#pragma unroll
+          for (int k = 0; k < D; ++k) normal_pair_at(a.key, (uint32_t)p, stream, 0u, PURPOSE_INIT, (uint32_t)k, za[k], zb[k]);
+          mdl.init(za, xa);
+          mdl.init(zb, xb);
+          lw[r][0] = mdl.logweight(xa, y);
+#pragma unroll
+          for (int k = 0; k < D; ++k) xs[k * ldx + i] = xa[k];
+          if (i + 1 < N) {
+            lw[r][1] = mdl.logweight(xb, y);
+#pragma unroll
+            for (int k = 0; k < D; ++k) xs[k * ldx + i + 1] = xb[k];
+          }
+        }
+      }
+    } else {
+      // ---- normalize(previous logw) and its fixed-point CDF                         particles.jl:5-15,117
+      unsigned long long q0[PAIRS], tq[PAIRS], winc[PAIRS];
+      double se = 0.0, se2 = 0.0;
+#pragma unroll
+      for (int r = 0; r < PAIRS; ++r) {
+        double e0 = 0.0, e1 = 0.0;
+        uint64_t qa = 0, qb = 0;
+        const int i = 2 * (r * nthreads + tid);
+        if (i < N) det_exp_quant(lw[r][0] - mx, a.S, e0, qa);
+        if (i + 1 < N) det_exp_quant(lw[r][1] - mx, a.S, e1, qb);
+        se += e0; se2 += e0 * e0;
+        se += e1; se2 += e1 * e1;
+        q0[r] = qa;
+        tq[r] = qa + qb;
+        winc[r] = warp_scan_u64(tq[r], lane);
+        if (lane == 31) s_wq[r][warp] = winc[r];
+      }
+      se = warp_sum(se);
+      se2 = warp_sum(se2);
+      if (lane == 0) {
+        s_f[0][warp] = se;
+        s_f[1][warp] = se2;
+      }
+      __syncthreads();  // A
+      unsigned long long segbase = 0;
+#pragma unroll
+      for (int r = 0; r < PAIRS; ++r) {
+        const unsigned long long v = (lane < nwarps) ? s_wq[r][lane] : 0ull;
+        const unsigned long long vinc = warp_scan_u64(v, lane);
+        const unsigned long long wexcl = __shfl_sync(kFullMask, vinc - v, warp);
+        const unsigned long long segtot = __shfl_sync(kFullMask, vinc, 31);
+        const unsigned long long excl = segbase + wexcl + (winc[r] - tq[r]);
+        const int i = 2 * (r * nthreads + tid);
+        if (i < a.npad) {
+          s_cdf[i] = excl + q0[r];
+          s_cdf[i + 1] = excl + tq[r];
+        }
+        segbase += segtot;
+      }
+      const unsigned long long Q = segbase;
+      {
+        double e1 = (lane < nwarps) ? s_f[0][lane] : 0.0, e2 = (lane < nwarps) ? s_f[1][lane] : 0.0;
+        e1 = warp_sum(e1);
+        e2 = warp_sum(e2);
+        if (account) logz += mx + log(e1) - logN;  // logμ of the previous step           particles.jl:10
+        account = true;
+        (void)e2;
+      }
+      __syncthreads();  // B: CDF complete
+      // ---- a = resample(w); xp = x[a]                                                particles.jl:117-119
+      uint64_t sys_off = 0;
+      if (a.resampler == RESAMPLE_SYSTEMATIC)
+        sys_off = mulhi64(uniform64_at(a.key, 0u, stream, t, PURPOSE_RESAMPLE), a.R);
+      double xpa[PAIRS][D], xpb[PAIRS][D];
+#pragma unroll
+      for (int r = 0; r < PAIRS; ++r) {
+        const int p = r * nthreads + tid;
+        const int i = 2 * p;
+        if (p < npairs) {
+          int a0 = i, a1 = (i + 1 < N) ? i + 1 : i;
+          if (Q != 0) {
+            uint64_t ua = sys_off, ub = sys_off;
+            if (a.resampler != RESAMPLE_SYSTEMATIC) {
+              const Philox4 b = philox4x32_10((uint32_t)p, stream, t, purpose_word(PURPOSE_RESAMPLE, 0, a.key.epoch),
+                                              a.key.k0, a.key.k1);
+              ua = uniform64_of(b, 0);
+              ub = uniform64_of(b, 1);
+            }
+            uint64_t F0, F1;
+            if (a.resampler == RESAMPLE_MULTINOMIAL) {
+              F0 = ua;
+              F1 = ub;
+            } else if (a.resampler == RESAMPLE_STRATIFIED) {
+              F0 = (uint64_t)i * a.R + mulhi64(ua, a.R);
+              F1 = (uint64_t)(i + 1) * a.R + mulhi64(ub, a.R);
+            } else {
+              F0 = (uint64_t)i * a.R + ua;
+              F1 = (uint64_t)(i + 1) * a.R + ub;
+            }
+            const uint64_t t0 = mulhi64(F0, Q), t1 = mulhi64(F1, Q);
+            a0 = smem_lower_count(s_cdf, 0, N - 1, t0);
+            a1 = smem_lower_count(s_cdf, (a.resampler == RESAMPLE_MULTINOMIAL) ? 0 : a0, N - 1, t1);
+          }
+#pragma unroll
+          for (int k = 0; k < D; ++k) {
+            xpa[r][k] = xs[k * ldx + a0];
+            xpb[r][k] = xs[k * ldx + a1];
+          }
+        }
+      }
+      __syncthreads();  // C: every parent read before the cloud is overwritten
+      // ---- x_i ~ transition(xp_i); logw_i = logpdf(observation(x_i), y)              particles.jl:122-125
+#pragma unroll
+      for (int r = 0; r < PAIRS; ++r) {
+        const int p = r * nthreads + tid;
+        const int i = 2 * p;
+        lw[r][0] = lw[r][1] = -INFINITY;
+        if (p < npairs) {
+          double za[D], zb[D], xa[D], xb[D];
+#pragma unroll
+          for (int k = 0; k < D; ++k)
+            normal_pair_at(a.key, (uint32_t)p, stream, t, PURPOSE_TRANSITION, (uint32_t)k, za[k], zb[k]);
+          mdl.transition(za, xpa[r], xa);
+          lw[r][0] = mdl.logweight(xa, y);
+#pragma unroll
+          for (int k = 0; k < D; ++k) xs[k * ldx + i] = xa[k];
+          if (i + 1 < N) {
+            mdl.transition(zb, xpb[r], xb);
+            lw[r][1] = mdl.logweight(xb, y);
+#pragma unroll
+            for (int k = 0; k < D; ++k) xs[k * ldx + i + 1] = xb[k];
+          }
+        }
+      }
+    }
+    double v = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < PAIRS; ++r) {
+      if (lw[r][0] > v) v = lw[r][0];
+      if (lw[r][1] > v) v = lw[r][1];
+    }
+    mx = block_max_all(v);  // sync D
+  }
+
+  // ---- normalize(final logw): logμ, ess, stats for the next launch
+  {
+    double se = 0.0, se2 = 0.0;
+#pragma unroll
+    for (int r = 0; r < PAIRS; ++r) {
+      const int i = 2 * (r * nthreads + tid);
+      if (i < N) { const double e = det_exp(lw[r][0] - mx); se += e; se2 += e * e; }
+      if (i + 1 < N) { const double e = det_exp(lw[r][1] - mx); se += e; se2 += e * e; }
+    }
+    se = warp_sum(se);
+    se2 = warp_sum(se2);
+    __syncthreads();
+    if (lane == 0) {
+      s_f[0][warp] = se;
+      s_f[1][warp] = se2;
+    }
+    __syncthreads();
+    double e1 = (lane < nwarps) ? s_f[0][lane] : 0.0, e2 = (lane < nwarps) ? s_f[1][lane] : 0.0;
+    e1 = warp_sum(e1);
+    e2 = warp_sum(e2);
+    if (account) logz += mx + log(e1) - logN;
+    if (tid == 0) {
+      a.stats[m].mx = mx;
+      a.stats[m].sum = e1;
+      a.stats[m].sum2 = e2;
+      a.logz_out[m] = logz;
+      a.ess_out[m] = (e1 * e1) / e2;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < PAIRS; ++r) {
+    const int p = r * nthreads + tid;
+    const int i = 2 * p;
+    if (p < npairs) {
+      if (i + 1 < N) {
+        *reinterpret_cast<double2*>(glw + i) = make_double2(lw[r][0], lw[r][1]);
+        if (a.x_in_smem) {
+#pragma unroll
+          for (int k = 0; k < D; ++k)
+            *reinterpret_cast<double2*>(gx + k * ld + i) = make_double2(xs[k * ldx + i], xs[k * ldx + i + 1]);
+        }
+      } else {
+        glw[i] = lw[r][0];
+        if (a.x_in_smem) {
+#pragma unroll
+          for (int k = 0; k < D; ++k) gx[k * ld + i] = xs[k * ldx + i];
+        }
+      }
+    }
+  }
+}
+
+// rows = whole clouds: dst slot <- src slot, 16 bytes per thread per trip
+__global__ void copy_clouds_kernel(double* __restrict__ dx, const double* __restrict__ sx, double* __restrict__ dlw,
+                                   const double* __restrict__ slw, StepStats* __restrict__ dst, const StepStats* __restrict__ sst,
+                                   const int32_t* __restrict__ dslot, const int32_t* __restrict__ sslot,
+                                   const uint8_t* __restrict__ mask, int64_t xrow, int64_t wrow) {
+  const int64_t j = blockIdx.x;
+  if (mask && !mask[j]) return;
+  const int64_t d = dslot ? dslot[j] : j, s = sslot ? sslot[j] : j;
+  const double2* s2 = reinterpret_cast<const double2*>(sx + s * xrow);
+  double2* d2 = reinterpret_cast<double2*>(dx + d * xrow);
+  for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < xrow / 2; i += (int64_t)gridDim.y * blockDim.x) d2[i] = s2[i];
+  const double2* w2 = reinterpret_cast<const double2*>(slw + s * wrow);
+  double2* e2 = reinterpret_cast<double2*>(dlw + d * wrow);
+  for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < wrow / 2; i += (int64_t)gridDim.y * blockDim.x) e2[i] = w2[i];
+  if (blockIdx.y == 0 && threadIdx.x == 0) dst[d] = sst[s];
+}
+
+// pack / unpack whole clouds into a flat device buffer: per slot [x: d*ld][logw: ld][stats: 4 doubles]
+__global__ void pack_clouds_kernel(double* __restrict__ x, double* __restrict__ lw, StepStats* __restrict__ st,
+                                   const int32_t* __restrict__ slots, double* __restrict__ buf, int64_t xrow, int64_t wrow,
+                                   int to_buffer) {
+  const int64_t j = blockIdx.x;
+  const int64_t s = slots[j];
+  double* b = buf + j * (xrow + wrow + 4);
+  double* gx = x + s * xrow;
+  double* gw = lw + s * wrow;
+  for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < xrow; i += (int64_t)gridDim.y * blockDim.x) {
+    if (to_buffer) b[i] = gx[i];
+    else gx[i] = b[i];
+  }
+  for (int64_t i = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; i < wrow; i += (int64_t)gridDim.y * blockDim.x) {
+    if (to_buffer) b[xrow + i] = gw[i];
+    else gw[i] = b[xrow + i];
+  }
+  if (blockIdx.y == 0 && threadIdx.x == 0) {
+    double* sb = b + xrow + wrow;
+    if (to_buffer) { sb[0] = st[s].mx; sb[1] = st[s].sum; sb[2] = st[s].sum2; sb[3] = 0.0; }
+    else { st[s].mx = sb[0]; st[s].sum = sb[1]; st[s].sum2 = sb[2]; }
+  }
+}
+
+__global__ void batch_weights_kernel(const double* __restrict__ logw, const StepStats* __restrict__ st, double* __restrict__ w,
+                                     int64_t N, int64_t ld) {
+  const int64_t m = blockIdx.y;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) w[m * N + i] = det_exp(logw[m * ld + i] - st[m].mx) / st[m].sum;
+}
+
+// scalar Kalman recursion, one thread per model                                 kalman_filter.jl:29-70
+__global__ void kalman_kernel(const double* __restrict__ params, const uint8_t* __restrict__ active, int64_t M,
+                              const double* __restrict__ y, int64_t T, int predict_first, double* __restrict__ loglik,
+                              double* __restrict__ xio, double* __restrict__ sio, int use_state) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  if (active && !active[m]) {
+    loglik[m] = -INFINITY;
+    return;
+  }
+  const double* P = params + m * kParamStride;
+  const double A = P[0], B = P[1], Q = P[2], R = P[3];
+  double x = use_state ? xio[m] : P[4];
+  double S = use_state ? sio[m] : P[5];
+  double ll = 0.0;
+  for (int64_t t = 0; t < T; ++t) {
+    if (predict_first || t > 0) {  // :33-34
+      x = A * x;
+      S = (A * A) * S + Q;
+    }
+    const double sig = (B * B) * S + R;       // :37
+    const double dy = y[t] - B * x;           // :38
+    const double inv = 1.0 / sig;
+    x = x + (S * B) * inv * dy;               // :41
+    S = S - ((S * B) * (S * B)) * inv;        // :42
+    ll += -0.5 * (log(2.0 * M_PI) + log(sig) + (dy / sig * dy));  // :45
+  }
+  loglik[m] = ll;
+  if (xio) xio[m] = x;
+  if (sio) sio[m] = S;
+}
+
+template <class Model, int PAIRS, int MAXT>
+void launch_batch(const BatchArgs& a, int64_t M, int threads, size_t smem, cudaStream_t stream) {
+  auto kern = batch_kernel<Model, PAIRS, MAXT>;
+  SMCB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<(unsigned)M, threads, smem, stream>>>(a);
+  SMCB_CUDA_TRY(cudaGetLastError());
+}
+
+template <class Model>
+void launch_batch_model(const BatchArgs& a, int64_t M, int pairs, int threads, size_t smem, cudaStream_t stream) {
+  if (pairs == 2) {
+    if (threads <= 256) launch_batch<Model, 2, 256>(a, M, threads, smem, stream);
+    else if (threads <= 512) launch_batch<Model, 2, 512>(a, M, threads, smem, stream);
+    else launch_batch<Model, 2, 1024>(a, M, threads, smem, stream);
+  } else if (pairs == 1) {
+    if (threads <= 512) launch_batch<Model, 1, 512>(a, M, threads, smem, stream);
+    else launch_batch<Model, 1, 1024>(a, M, threads, smem, stream);
+  } else {
+    if (threads <= 512) launch_batch<Model, 4, 512>(a, M, threads, smem, stream);
+    else launch_batch<Model, 4, 1024>(a, M, threads, smem, stream);
+  }
+}
+
+constexpr size_t kSmemBudget = 227 * 1024 - 2048;  // dynamic part; static scratch is < 2 KB
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+BatchFilter::BatchFilter(int device, cudaStream_t stream, int kind, int64_t M, int64_t N)
+    : device_(device), stream_(stream), kind_(kind), d_(0), M_(M), N_(N) {
+  if (kind < 0 || kind >= KIND_COUNT) throw Error{SMCB_ERR_BAD_ARG, "unknown model kind"};
+  if (M < 1 || M > (1 << 24)) throw Error{SMCB_ERR_BAD_ARG, "M must be in [1, 2^24]"};
+  if (N < 1 || N > 8192) throw Error{SMCB_ERR_UNSUPPORTED, "batched filters support N in [1, 8192] (use the single filter above)"};
+  d_ = state_dim(kind);
+  ld_ = (N + 31) & ~int64_t(31);
+  S_ = quant_shift((uint64_t)N);
+  R_ = strata_width((uint64_t)N);
+  SMCB_CUDA_TRY(cudaSetDevice(device_));
+  for (int i = 0; i < 2; ++i) {
+    SMCB_CUDA_TRY(cudaMalloc(&x_[i], sizeof(double) * M * d_ * ld_));
+    SMCB_CUDA_TRY(cudaMalloc(&logw_[i], sizeof(double) * M * ld_));
+    SMCB_CUDA_TRY(cudaMalloc(&stats_[i], sizeof(StepStats) * M));
+    SMCB_CUDA_TRY(cudaMemsetAsync(x_[i], 0, sizeof(double) * M * d_ * ld_, stream_));
+    SMCB_CUDA_TRY(cudaMemsetAsync(logw_[i], 0, sizeof(double) * M * ld_, stream_));
+    SMCB_CUDA_TRY(cudaMemsetAsync(stats_[i], 0, sizeof(StepStats) * M, stream_));
+    SMCB_CUDA_TRY(cudaEventCreate(&ev_[i]));
+  }
+  SMCB_CUDA_TRY(cudaMalloc(&derived_, sizeof(double) * M * kParamStride));
+  SMCB_CUDA_TRY(cudaMalloc(&active_, M));
+  SMCB_CUDA_TRY(cudaMalloc(&out_dev_, sizeof(double) * 2 * M));
+  host_tmp_.resize((size_t)(M * kParamStride));
+}
+
+BatchFilter::~BatchFilter() {
+  cudaSetDevice(device_);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(x_[i]); cudaFree(logw_[i]); cudaFree(stats_[i]);
+    if (ev_[i]) cudaEventDestroy(ev_[i]);
+  }
+  cudaFree(derived_); cudaFree(active_); cudaFree(y_dev_); cudaFree(out_dev_); cudaFree(w_tmp_); cudaFree(slots_dev_);
+}
+
+void BatchFilter::begin_call() {
+  SMCB_CUDA_TRY(cudaSetDevice(device_));
+  SMCB_CUDA_TRY(cudaEventRecord(ev_[0], stream_));
+}
+
+void BatchFilter::end_call() {
+  SMCB_CUDA_TRY(cudaEventRecord(ev_[1], stream_));
+  SMCB_CUDA_TRY(cudaStreamSynchronize(stream_));
+  float ms = 0;
+  SMCB_CUDA_TRY(cudaEventElapsedTime(&ms, ev_[0], ev_[1]));
+  last_ms_ = ms;
+}
+
+void BatchFilter::upload_params(const double* params, const uint8_t* active) {
+  if (params) {
+    for (int64_t m = 0; m < M_; ++m) derive_params(kind_, params + m * kParamStride, host_tmp_.data() + m * kParamStride);
+    SMCB_CUDA_TRY(cudaMemcpyAsync(derived_, host_tmp_.data(), sizeof(double) * M_ * kParamStride, cudaMemcpyHostToDevice, stream_));
+    SMCB_CUDA_TRY(cudaStreamSynchronize(stream_));  // host_tmp_ is reused
+    has_params_ = true;
+  }
+  use_active_ = active != nullptr;
+  if (active) SMCB_CUDA_TRY(cudaMemcpyAsync(active_, active, M_, cudaMemcpyHostToDevice, stream_));
+}
+
+void BatchFilter::launch(bool from_init, uint32_t t_begin, uint32_t t_end, int resampler, int64_t) {
+  const int64_t npairs = (N_ + 1) / 2;
+  int pairs = 2;
+  if ((npairs + pairs - 1) / pairs > 1024) pairs = 4;
+  if (const char* e = std::getenv("SMCB_BATCH_PAIRS")) {
+    const int v = std::atoi(e);
+    if ((v == 1 || v == 2 || v == 4) && (npairs + v - 1) / v <= 1024) pairs = v;
+  }
+  int threads = (int)(((npairs + pairs - 1) / pairs + 31) / 32 * 32);
+  const int64_t npad = (N_ + 1) & ~int64_t(1);
+  const size_t cdf_bytes = sizeof(uint64_t) * (size_t)npad;
+  const size_t x_bytes = sizeof(double) * (size_t)npad * d_;
+  const bool x_in_smem = cdf_bytes + x_bytes <= kSmemBudget;
+  const size_t smem = cdf_bytes + (x_in_smem ? x_bytes : 0);
+  if (smem > kSmemBudget) throw Error{SMCB_ERR_UNSUPPORTED, "CDF does not fit in shared memory"};
+  BatchArgs a;
+  a.derived = derived_;
+  a.active = use_active_ ? active_ : nullptr;
+  a.y = y_dev_;
+  a.x = x_[cur_];
+  a.logw = logw_[cur_];
+  a.stats = stats_[cur_];
+  a.logz_out = out_dev_;
+  a.ess_out = out_dev_ + M_;
+  a.N = N_; a.ld = ld_; a.S = S_; a.R = R_;
+  a.key = key_; a.stream0 = stream0_;
+  a.t_begin = t_begin; a.t_end = t_end;
+  a.resampler = resampler;
+  a.from_init = from_init ? 1 : 0;
+  a.x_in_smem = x_in_smem ? 1 : 0;
+  a.npad = npad;
+  switch (kind_) {
+    case KIND_LG1D: launch_batch_model<ModelLG1D>(a, M_, pairs, threads, smem, stream_); break;
+    case KIND_SV: launch_batch_model<ModelSV>(a, M_, pairs, threads, smem, stream_); break;
+    default: launch_batch_model<ModelUCSV>(a, M_, pairs, threads, smem, stream_); break;
+  }
+  ++launches_;
+}
+
+static void ensure_y(double*& y_dev, int64_t& cap, int64_t T) {
+  if (cap < T) {
+    cudaFree(y_dev);
+    y_dev = nullptr;
+    cap = 0;
+    SMCB_CUDA_TRY(cudaMalloc(&y_dev, sizeof(double) * T));
+    cap = T;
+  }
+}
+
+void BatchFilter::init(const double* params, const uint8_t* active, double y0, const RngKey& key, uint32_t stream0,
+                       double* logmu, double* ess) {
+  begin_call();
+  upload_params(params, active);
+  ensure_y(y_dev_, y_cap_, 1);
+  SMCB_CUDA_TRY(cudaMemcpyAsync(y_dev_, &y0, sizeof(double), cudaMemcpyHostToDevice, stream_));
+  key_ = key; stream0_ = stream0; t_ = 0;
+  launch(true, 0, 0, RESAMPLE_SYSTEMATIC, 1);
+  if (logmu) SMCB_CUDA_TRY(cudaMemcpyAsync(logmu, out_dev_, sizeof(double) * M_, cudaMemcpyDeviceToHost, stream_));
+  if (ess) SMCB_CUDA_TRY(cudaMemcpyAsync(ess, out_dev_ + M_, sizeof(double) * M_, cudaMemcpyDeviceToHost, stream_));
+  end_call();
+  live_ = true;
+}
+
+void BatchFilter::step(const double* params, double y, int resampler, double* logmu, double* ess) {
+  if (!live_) throw Error{SMCB_ERR_STATE, "batch_step before batch_init / batch_log_likelihood"};
+  if (resampler < 0 || resampler > 2) throw Error{SMCB_ERR_BAD_ARG, "unknown resampler"};
+  begin_call();
+  upload_params(params, nullptr);
+  ensure_y(y_dev_, y_cap_, 1);
+  SMCB_CUDA_TRY(cudaMemcpyAsync(y_dev_, &y, sizeof(double), cudaMemcpyHostToDevice, stream_));
+  launch(false, t_ + 1, t_ + 1, resampler, 1);
+  t_ += 1;
+  if (logmu) SMCB_CUDA_TRY(cudaMemcpyAsync(logmu, out_dev_, sizeof(double) * M_, cudaMemcpyDeviceToHost, stream_));
+  if (ess) SMCB_CUDA_TRY(cudaMemcpyAsync(ess, out_dev_ + M_, sizeof(double) * M_, cudaMemcpyDeviceToHost, stream_));
+  end_call();
+}
+
+void BatchFilter::run(const double* params, const uint8_t* active, const double* y, int64_t T, int resampler,
+                      const RngKey& key, uint32_t stream0, double* logZ) {
+  if (resampler < 0 || resampler > 2) throw Error{SMCB_ERR_BAD_ARG, "unknown resampler"};
+  begin_call();
+  upload_params(params, active);
+  ensure_y(y_dev_, y_cap_, T);
+  SMCB_CUDA_TRY(cudaMemcpyAsync(y_dev_, y, sizeof(double) * T, cudaMemcpyHostToDevice, stream_));
+  key_ = key; stream0_ = stream0;
+  launch(true, 0, (uint32_t)(T - 1), resampler, T);
+  t_ = (uint32_t)(T - 1);
+  SMCB_CUDA_TRY(cudaMemcpyAsync(logZ, out_dev_, sizeof(double) * M_, cudaMemcpyDeviceToHost, stream_));
+  end_call();
+  live_ = true;
+}
+
+void BatchFilter::upload_slots(const int32_t* a, const int32_t* b, int64_t n) {
+  if (slot_cap_ < n) {
+    cudaFree(slots_dev_);
+    slots_dev_ = nullptr;
+    slot_cap_ = 0;
+    SMCB_CUDA_TRY(cudaMalloc(&slots_dev_, sizeof(int32_t) * 2 * n));
+    slot_cap_ = n;
+  }
+  if (a) SMCB_CUDA_TRY(cudaMemcpyAsync(slots_dev_, a, sizeof(int32_t) * n, cudaMemcpyHostToDevice, stream_));
+  if (b) SMCB_CUDA_TRY(cudaMemcpyAsync(slots_dev_ + slot_cap_, b, sizeof(int32_t) * n, cudaMemcpyHostToDevice, stream_));
+}
+
+void BatchFilter::gather(const int32_t* parents) {
+  if (!live_) throw Error{SMCB_ERR_STATE, "batch_gather before any filtering"};
+  for (int64_t m = 0; m < M_; ++m)
+    if (parents[m] < 0 || parents[m] >= M_) throw Error{SMCB_ERR_BAD_ARG, "batch_gather: parent index out of range"};
+  begin_call();
+  upload_slots(parents, nullptr, M_);
+  const int64_t xrow = d_ * ld_, wrow = ld_;
+  dim3 grid((unsigned)M_, (unsigned)std::max<int64_t>(1, std::min<int64_t>(8, xrow / 2 / 256)));
+  copy_clouds_kernel<<<grid, 256, 0, stream_>>>(x_[cur_ ^ 1], x_[cur_], logw_[cur_ ^ 1], logw_[cur_], stats_[cur_ ^ 1],
+                                                stats_[cur_], nullptr, slots_dev_, nullptr, xrow, wrow);
+  SMCB_CUDA_TRY(cudaGetLastError());
+  ++launches_;
+  cur_ ^= 1;
+  end_call();
+}
+
+void BatchFilter::accept_from(const BatchFilter& prop, const uint8_t* accept) {
+  if (prop.M_ != M_ || prop.N_ != N_ || prop.kind_ != kind_ || prop.device_ != device_)
+    throw Error{SMCB_ERR_BAD_ARG, "batch_accept: batches differ in shape, model or device"};
+  if (!prop.live_) throw Error{SMCB_ERR_STATE, "batch_accept: proposal batch holds no clouds"};
+  begin_call();
+  SMCB_CUDA_TRY(cudaMemcpyAsync(active_, accept, M_, cudaMemcpyHostToDevice, stream_));
+  use_active_ = false;
+  const int64_t xrow = d_ * ld_, wrow = ld_;
+  dim3 grid((unsigned)M_, (unsigned)std::max<int64_t>(1, std::min<int64_t>(8, xrow / 2 / 256)));
+  copy_clouds_kernel<<<grid, 256, 0, stream_>>>(x_[cur_], prop.x_[prop.cur_], logw_[cur_], prop.logw_[prop.cur_], stats_[cur_],
+                                                prop.stats_[prop.cur_], nullptr, nullptr, active_, xrow, wrow);
+  SMCB_CUDA_TRY(cudaGetLastError());
+  ++launches_;
+  if (!live_) { t_ = prop.t_; key_ = prop.key_; stream0_ = prop.stream0_; live_ = true; }
+  end_call();
+}
+
+void BatchFilter::fetch(double* x_host, double* w_host, double* logw_host) {
+  if (!live_) throw Error{SMCB_ERR_STATE, "no batch state to fetch"};
+  SMCB_CUDA_TRY(cudaSetDevice(device_));
+  if (x_host)
+    SMCB_CUDA_TRY(cudaMemcpy2DAsync(x_host, sizeof(double) * N_, x_[cur_], sizeof(double) * ld_, sizeof(double) * N_, M_ * d_,
+                                    cudaMemcpyDeviceToHost, stream_));
+  if (logw_host)
+    SMCB_CUDA_TRY(cudaMemcpy2DAsync(logw_host, sizeof(double) * N_, logw_[cur_], sizeof(double) * ld_, sizeof(double) * N_, M_,
+                                    cudaMemcpyDeviceToHost, stream_));
+  if (w_host) {
+    if (!w_tmp_) SMCB_CUDA_TRY(cudaMalloc(&w_tmp_, sizeof(double) * M_ * N_));
+    dim3 grid((unsigned)((N_ + 255) / 256), (unsigned)M_);
+    batch_weights_kernel<<<grid, 256, 0, stream_>>>(logw_[cur_], stats_[cur_], w_tmp_, N_, ld_);
+    SMCB_CUDA_TRY(cudaGetLastError());
+    SMCB_CUDA_TRY(cudaMemcpyAsync(w_host, w_tmp_, sizeof(double) * M_ * N_, cudaMemcpyDeviceToHost, stream_));
+  }
+  SMCB_CUDA_TRY(cudaStreamSynchronize(stream_));
+}
+
+int64_t BatchFilter::cloud_bytes() const { return (int64_t)sizeof(double) * ((d_ + 1) * ld_ + 4); }
+
+void BatchFilter::pack(const int32_t* slots, int64_t n, void* buf_dev, bool to_buffer) {
+  if (n == 0) return;
+  for (int64_t j = 0; j < n; ++j)
+    if (slots[j] < 0 || slots[j] >= M_) throw Error{SMCB_ERR_BAD_ARG, "batch_pack: slot out of range"};
+  begin_call();
+  upload_slots(slots, nullptr, n);
+  const int64_t xrow = d_ * ld_, wrow = ld_;
+  dim3 grid((unsigned)n, (unsigned)std::max<int64_t>(1, std::min<int64_t>(8, xrow / 256)));
+  pack_clouds_kernel<<<grid, 256, 0, stream_>>>(x_[cur_], logw_[cur_], stats_[cur_], slots_dev_, static_cast<double*>(buf_dev),
+                                                xrow, wrow, to_buffer ? 1 : 0);
+  SMCB_CUDA_TRY(cudaGetLastError());
+  ++launches_;
+  if (!to_buffer) live_ = true;
+  end_call();
+}
+
+// ------------------------------------------------------------------------------------------------
+void kalman_batch(int device, cudaStream_t stream, const double* params, const uint8_t* active, int64_t M,
+                  const double* y, int64_t T, bool predict_first, double* loglik, double* x, double* sigma,
+                  bool use_state) {
+  SMCB_CUDA_TRY(cudaSetDevice(device));
+  double *dp = nullptr, *dy = nullptr, *dl = nullptr, *dx = nullptr, *ds = nullptr;
+  uint8_t* da = nullptr;
+  auto cleanup = [&] { cudaFree(dp); cudaFree(dy); cudaFree(dl); cudaFree(dx); cudaFree(ds); cudaFree(da); };
+  try {
+    SMCB_CUDA_TRY(cudaMalloc(&dp, sizeof(double) * M * kParamStride));
+    SMCB_CUDA_TRY(cudaMalloc(&dy, sizeof(double) * T));
+    SMCB_CUDA_TRY(cudaMalloc(&dl, sizeof(double) * M));
+    SMCB_CUDA_TRY(cudaMalloc(&dx, sizeof(double) * M));
+    SMCB_CUDA_TRY(cudaMalloc(&ds, sizeof(double) * M));
+    SMCB_CUDA_TRY(cudaMemcpyAsync(dp, params, sizeof(double) * M * kParamStride, cudaMemcpyHostToDevice, stream));
+    SMCB_CUDA_TRY(cudaMemcpyAsync(dy, y, sizeof(double) * T, cudaMemcpyHostToDevice, stream));
+    if (active) {
+      SMCB_CUDA_TRY(cudaMalloc(&da, M));
+      SMCB_CUDA_TRY(cudaMemcpyAsync(da, active, M, cudaMemcpyHostToDevice, stream));
+    }
+    if (use_state) {
+      SMCB_CUDA_TRY(cudaMemcpyAsync(dx, x, sizeof(double) * M, cudaMemcpyHostToDevice, stream));
+      SMCB_CUDA_TRY(cudaMemcpyAsync(ds, sigma, sizeof(double) * M, cudaMemcpyHostToDevice, stream));
+    }
+    kalman_kernel<<<(unsigned)((M + 127) / 128), 128, 0, stream>>>(dp, da, M, dy, T, predict_first ? 1 : 0, dl, dx, ds,
+                                                                   use_state ? 1 : 0);
+    SMCB_CUDA_TRY(cudaGetLastError());
+    SMCB_CUDA_TRY(cudaMemcpyAsync(loglik, dl, sizeof(double) * M, cudaMemcpyDeviceToHost, stream));
+    if (x) SMCB_CUDA_TRY(cudaMemcpyAsync(x, dx, sizeof(double) * M, cudaMemcpyDeviceToHost, stream));
+    if (sigma) SMCB_CUDA_TRY(cudaMemcpyAsync(sigma, ds, sizeof(double) * M, cudaMemcpyDeviceToHost, stream));
+    SMCB_CUDA_TRY(cudaStreamSynchronize(stream));
+  } catch (...) {
+    cleanup();
+    throw;
+  }
+  cleanup();
+}
+
+}  // namespace smcb

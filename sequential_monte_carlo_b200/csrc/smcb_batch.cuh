@@ -1,0 +1,88 @@
+// M independent bootstrap filters of N particles each, one CTA per θ-particle, the whole time
+// loop inside one launch (the "particle of filters" of SMC² and the PMMH sweeps of rejuvenate!).
+// Replaces the loops over θ at /root/reference/src/smc_samplers.jl:112-121,223-229,289-293,325-335.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "smcb_common.cuh"
+#include "smcb_filter.cuh"
+#include "smcb_models.cuh"
+
+namespace smcb {
+
+class BatchFilter {
+ public:
+  BatchFilter(int device, cudaStream_t stream, int kind, int64_t M, int64_t N);
+  ~BatchFilter();
+  BatchFilter(const BatchFilter&) = delete;
+  BatchFilter& operator=(const BatchFilter&) = delete;
+
+  // M × bootstrap_filter(N, y, model(θ_m))                       smc_samplers.jl:289-293
+  void init(const double* params, const uint8_t* active, double y0, const RngKey& key, uint32_t stream0,
+            double* logmu, double* ess);
+  // M × bootstrap_filter!(x[m], w[m], y, model(θ_m))              smc_samplers.jl:325-335
+  void step(const double* params, double y, int resampler, double* logmu, double* ess);
+  // M × log_likelihood(N, y, model(θ_m))                          smc_samplers.jl:117-121,223-229
+  void run(const double* params, const uint8_t* active, const double* y, int64_t T, int resampler,
+           const RngKey& key, uint32_t stream0, double* logZ);
+
+  void gather(const int32_t* parents);                             // smc_samplers.jl:74-84
+  void accept_from(const BatchFilter& prop, const uint8_t* accept);  // smc_samplers.jl:130-133
+  void fetch(double* x_host, double* w_host, double* logw_host);
+  int64_t cloud_bytes() const;
+  void pack(const int32_t* slots, int64_t n, void* buf_dev, bool to_buffer);
+
+  double last_ms() const { return last_ms_; }
+  int64_t launches() const { return launches_; }
+  int64_t M() const { return M_; }
+  int64_t N() const { return N_; }
+
+ private:
+  void upload_params(const double* params, const uint8_t* active);
+  void launch(bool from_init, uint32_t t_begin, uint32_t t_end, int resampler, int64_t y_count);
+  void begin_call();
+  void end_call();
+  void upload_slots(const int32_t* a, const int32_t* b, int64_t n);
+
+  int device_;
+  cudaStream_t stream_;
+  int kind_, d_;
+  int64_t M_, N_, ld_;
+  int S_;
+  uint64_t R_;
+  RngKey key_{};
+  uint32_t stream0_ = 0;
+  uint32_t t_ = 0;
+  bool live_ = false;
+  bool has_params_ = false;
+
+  double* x_[2] = {nullptr, nullptr};     // [M][d][ld], [1] is the gather target
+  double* logw_[2] = {nullptr, nullptr};  // [M][ld]
+  StepStats* stats_[2] = {nullptr, nullptr};
+  int cur_ = 0;
+  double* derived_ = nullptr;  // [M][8]
+  uint8_t* active_ = nullptr;  // [M]
+  bool use_active_ = false;
+  double* y_dev_ = nullptr;
+  int64_t y_cap_ = 0;
+  double* out_dev_ = nullptr;  // [2][M]: Σ logμ, ess
+  double* w_tmp_ = nullptr;
+  int32_t* slots_dev_ = nullptr;  // [2][slot_cap_]
+  int64_t slot_cap_ = 0;
+  std::vector<double> host_tmp_;
+
+  cudaEvent_t ev_[2] = {nullptr, nullptr};
+  double last_ms_ = 0;
+  int64_t launches_ = 0;
+};
+
+// kalman_filter / log_likelihood(y, model) for M LG1D models (kalman_filter.jl:29-70).
+// use_state: start from x/sigma given by the caller (one-step API); else from (x0, σ0) of params.
+void kalman_batch(int device, cudaStream_t stream, const double* params, const uint8_t* active, int64_t M,
+                  const double* y, int64_t T, bool predict_first, double* loglik, double* x, double* sigma,
+                  bool use_state);
+
+}  // namespace smcb

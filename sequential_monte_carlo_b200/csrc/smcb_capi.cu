@@ -1,0 +1,344 @@
+// extern "C" boundary of libsmcb200 (include/smcb200.h).  No C++ types or exceptions cross it.
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <memory>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/smcb200.h"
+#include "smcb_batch.cuh"
+#include "smcb_filter.cuh"
+
+using namespace smcb;
+
+struct smcb_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  uint64_t seed = 0;
+  uint32_t next_epoch = 0;
+  std::string err;
+  std::unique_ptr<SingleFilter> filter;
+  std::unique_ptr<SingleFilter> scratch;  // normalize / resample utilities
+  std::vector<StepStats> stats;
+  RngKey key(uint32_t epoch) const { return RngKey{(uint32_t)seed, (uint32_t)(seed >> 32), epoch & 0xFFFFFFu}; }
+};
+
+struct smcb_batch {
+  smcb_ctx* ctx = nullptr;
+  std::unique_ptr<BatchFilter> impl;
+};
+
+namespace {
+
+thread_local std::string g_create_error;
+
+template <class F>
+int guarded(smcb_ctx* ctx, F&& f) {
+  try {
+    f();
+    return SMCB_OK;
+  } catch (const Error& e) {
+    if (ctx) ctx->err = e.msg; else g_create_error = e.msg;
+    return e.code;
+  } catch (const std::bad_alloc&) {
+    if (ctx) ctx->err = "host allocation failed"; else g_create_error = "host allocation failed";
+    return SMCB_ERR_OOM;
+  } catch (const std::exception& e) {
+    if (ctx) ctx->err = e.what(); else g_create_error = e.what();
+    return SMCB_ERR_CUDA;
+  }
+}
+
+inline void need(bool ok, const char* what) {
+  if (!ok) throw Error{SMCB_ERR_BAD_ARG, what};
+}
+
+inline void stats_to(const StepStats& s, int64_t N, double* logmu, double* ess) {
+  // normalize(): logμ = max + log Σe − log N ; ess = (Σe)² / Σe²      particles.jl:10-13
+  if (logmu) *logmu = s.mx + std::log(s.sum) - std::log((double)N);
+  if (ess) *ess = (s.sum * s.sum) / s.sum2;
+}
+
+}  // namespace
+
+extern "C" {
+
+int smcb_version(void) { return 100; }
+
+int smcb_state_dim(int kind) { return (kind >= 0 && kind < KIND_COUNT) ? state_dim(kind) : SMCB_ERR_BAD_ARG; }
+
+int smcb_create(int device, uint64_t seed, smcb_ctx** out) {
+  if (!out) return SMCB_ERR_BAD_ARG;
+  *out = nullptr;
+  return guarded(nullptr, [&] {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+      throw Error{SMCB_ERR_CUDA, std::string("no CUDA device: libsmcb200 has no CPU fallback (") +
+                                     (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0") + ")"};
+    need(device >= 0 && device < count, "device index out of range");
+    SMCB_CUDA_TRY(cudaSetDevice(device));
+    std::unique_ptr<smcb_ctx> c(new smcb_ctx);
+    c->device = device;
+    c->seed = seed;
+    SMCB_CUDA_TRY(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    c->filter.reset(new SingleFilter(device, c->stream));
+    c->scratch.reset(new SingleFilter(device, c->stream));
+    *out = c.release();
+  });
+}
+
+int smcb_destroy(smcb_ctx* ctx) {
+  if (!ctx) return SMCB_OK;
+  cudaSetDevice(ctx->device);
+  ctx->filter.reset();
+  ctx->scratch.reset();
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return SMCB_OK;
+}
+
+const char* smcb_last_error(const smcb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int smcb_set_rng(smcb_ctx* ctx, uint64_t seed, uint32_t epoch) {
+  if (!ctx) return SMCB_ERR_BAD_ARG;
+  ctx->seed = seed;
+  ctx->next_epoch = epoch & 0xFFFFFFu;
+  return SMCB_OK;
+}
+
+int smcb_get_epoch(const smcb_ctx* ctx, uint32_t* next_epoch) {
+  if (!ctx || !next_epoch) return SMCB_ERR_BAD_ARG;
+  *next_epoch = ctx->next_epoch;
+  return SMCB_OK;
+}
+
+int smcb_record_ancestors(smcb_ctx* ctx, int enable) {
+  if (!ctx) return SMCB_ERR_BAD_ARG;
+  ctx->filter->set_record_ancestors(enable != 0);
+  return SMCB_OK;
+}
+
+int smcb_set_profiling(smcb_ctx* ctx, int enable) {
+  if (!ctx) return SMCB_ERR_BAD_ARG;
+  ctx->filter->set_profiling(enable != 0);
+  return SMCB_OK;
+}
+
+int smcb_get_timing(const smcb_ctx* ctx, double ms[5], int64_t launches[5]) {
+  if (!ctx || !ms || !launches) return SMCB_ERR_BAD_ARG;
+  ctx->filter->timing(ms, launches);
+  return SMCB_OK;
+}
+
+int smcb_synchronize(smcb_ctx* ctx) {
+  if (!ctx) return SMCB_ERR_BAD_ARG;
+  return guarded(ctx, [&] {
+    SMCB_CUDA_TRY(cudaSetDevice(ctx->device));
+    SMCB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+// ------------------------------------------------------------------ utilities
+int smcb_normalize(smcb_ctx* ctx, const double* logw, int64_t n, double* logmu, double* w, double* ess) {
+  if (!ctx) return SMCB_ERR_BAD_ARG;
+  return guarded(ctx, [&] {
+    need(logw && n >= 1, "normalize: logw must be non-null and n >= 1");
+    StepStats st;
+    ctx->scratch->normalize_vector(logw, n, &st, w);
+    stats_to(st, n, logmu, ess);
+  });
+}
+
+int smcb_resample(smcb_ctx* ctx, const double* w, int64_t n, int resampler, uint32_t stream, uint32_t t,
+                  uint32_t purpose, int64_t* ancestors) {
+  if (!ctx) return SMCB_ERR_BAD_ARG;
+  return guarded(ctx, [&] {
+    need(w && ancestors && n >= 1, "resample: w, ancestors must be non-null and n >= 1");
+    need(purpose >= 1 && purpose <= 15, "resample: purpose must be in [1, 15]");
+    ctx->scratch->resample_vector(w, n, resampler, ctx->key(ctx->next_epoch), stream, t, purpose, ancestors);
+  });
+}
+
+// ------------------------------------------------------------------ one filter
+int smcb_bootstrap_init(smcb_ctx* ctx, int kind, const double* params, int64_t N, double y, uint32_t stream,
+                        double* logmu, double* ess) {
+  if (!ctx) return SMCB_ERR_BAD_ARG;
+  return guarded(ctx, [&] {
+    need(params != nullptr, "bootstrap_init: params is null");
+    StepStats st;
+    ctx->filter->init(kind, params, N, y, ctx->key(ctx->next_epoch), stream, &st);
+    ctx->next_epoch = (ctx->next_epoch + 1) & 0xFFFFFFu;
+    stats_to(st, N, logmu, ess);
+  });
+}
+
+int smcb_bootstrap_step(smcb_ctx* ctx, const double* params, double y, int resampler, double* logmu, double* ess) {
+  if (!ctx) return SMCB_ERR_BAD_ARG;
+  return guarded(ctx, [&] {
+    StepStats st;
+    ctx->filter->step(params, y, resampler, &st);
+    stats_to(st, ctx->filter->N(), logmu, ess);
+  });
+}
+
+int smcb_log_likelihood(smcb_ctx* ctx, int kind, const double* params, int64_t N, const double* y, int64_t T,
+                        int resampler, uint32_t stream, double* logZ, double* logmu_out, double* ess_out) {
+  if (!ctx) return SMCB_ERR_BAD_ARG;
+  return guarded(ctx, [&] {
+    need(params && y && T >= 1, "log_likelihood: params, y must be non-null and T >= 1");
+    ctx->stats.resize((size_t)T);
+    ctx->filter->run(kind, params, N, y, T, resampler, ctx->key(ctx->next_epoch), stream, ctx->stats.data());
+    ctx->next_epoch = (ctx->next_epoch + 1) & 0xFFFFFFu;
+    double z = 0.0;
+    for (int64_t t = 0; t < T; ++t) {
+      double lm, es;
+      stats_to(ctx->stats[(size_t)t], N, &lm, &es);
+      z += lm;  // logZ += logμ      particles.jl:143
+      if (logmu_out) logmu_out[t] = lm;
+      if (ess_out) ess_out[t] = es;
+    }
+    if (logZ) *logZ = z;
+  });
+}
+
+int smcb_fetch_state(smcb_ctx* ctx, double* x, double* w, double* logw) {
+  if (!ctx) return SMCB_ERR_BAD_ARG;
+  return guarded(ctx, [&] { ctx->filter->fetch(x, w, logw); });
+}
+
+int smcb_fetch_ancestors(smcb_ctx* ctx, int64_t* ancestors, int64_t rows_cap, int64_t* rows_out) {
+  if (!ctx) return SMCB_ERR_BAD_ARG;
+  return guarded(ctx, [&] {
+    need(ancestors && rows_cap >= 0, "fetch_ancestors: bad buffer");
+    const int64_t r = ctx->filter->fetch_ancestors(ancestors, rows_cap);
+    if (rows_out) *rows_out = r;
+  });
+}
+
+int smcb_device_state(smcb_ctx* ctx, const double** x_dev, const double** logw_dev, int64_t* ld) {
+  if (!ctx) return SMCB_ERR_BAD_ARG;
+  return guarded(ctx, [&] {
+    if (!ctx->filter->live()) throw Error{SMCB_ERR_STATE, "no filter state"};
+    if (x_dev) *x_dev = ctx->filter->dev_x();
+    if (logw_dev) *logw_dev = ctx->filter->dev_logw();
+    if (ld) *ld = ctx->filter->ld();
+  });
+}
+
+// ------------------------------------------------------------------ batch
+int smcb_batch_create(smcb_ctx* ctx, int kind, int64_t M, int64_t N, smcb_batch** out) {
+  if (!ctx || !out) return SMCB_ERR_BAD_ARG;
+  *out = nullptr;
+  return guarded(ctx, [&] {
+    std::unique_ptr<smcb_batch> b(new smcb_batch);
+    b->ctx = ctx;
+    b->impl.reset(new BatchFilter(ctx->device, ctx->stream, kind, M, N));
+    *out = b.release();
+  });
+}
+
+int smcb_batch_destroy(smcb_batch* b) {
+  if (!b) return SMCB_OK;
+  cudaSetDevice(b->ctx->device);
+  delete b;
+  return SMCB_OK;
+}
+
+int smcb_batch_init(smcb_batch* b, const double* params, const uint8_t* active, double y, uint32_t stream0,
+                    double* logmu, double* ess) {
+  if (!b) return SMCB_ERR_BAD_ARG;
+  smcb_ctx* ctx = b->ctx;
+  return guarded(ctx, [&] {
+    need(params != nullptr, "batch_init: params is null");
+    b->impl->init(params, active, y, ctx->key(ctx->next_epoch), stream0, logmu, ess);
+    ctx->next_epoch = (ctx->next_epoch + 1) & 0xFFFFFFu;
+  });
+}
+
+int smcb_batch_step(smcb_batch* b, const double* params, double y, int resampler, double* logmu, double* ess) {
+  if (!b) return SMCB_ERR_BAD_ARG;
+  return guarded(b->ctx, [&] { b->impl->step(params, y, resampler, logmu, ess); });
+}
+
+int smcb_batch_log_likelihood(smcb_batch* b, const double* params, const uint8_t* active, const double* y,
+                              int64_t T, int resampler, uint32_t stream0, double* logZ) {
+  if (!b) return SMCB_ERR_BAD_ARG;
+  smcb_ctx* ctx = b->ctx;
+  return guarded(ctx, [&] {
+    need(params && y && T >= 1 && logZ, "batch_log_likelihood: params, y, logZ must be non-null and T >= 1");
+    b->impl->run(params, active, y, T, resampler, ctx->key(ctx->next_epoch), stream0, logZ);
+    ctx->next_epoch = (ctx->next_epoch + 1) & 0xFFFFFFu;
+  });
+}
+
+int smcb_batch_gather(smcb_batch* b, const int32_t* parents) {
+  if (!b) return SMCB_ERR_BAD_ARG;
+  return guarded(b->ctx, [&] {
+    need(parents != nullptr, "batch_gather: parents is null");
+    b->impl->gather(parents);
+  });
+}
+
+int smcb_batch_accept(smcb_batch* current, const smcb_batch* proposal, const uint8_t* accept) {
+  if (!current || !proposal) return SMCB_ERR_BAD_ARG;
+  return guarded(current->ctx, [&] {
+    need(accept != nullptr, "batch_accept: accept is null");
+    current->impl->accept_from(*proposal->impl, accept);
+  });
+}
+
+int smcb_batch_fetch(smcb_batch* b, double* x, double* w, double* logw) {
+  if (!b) return SMCB_ERR_BAD_ARG;
+  return guarded(b->ctx, [&] { b->impl->fetch(x, w, logw); });
+}
+
+int64_t smcb_batch_cloud_bytes(const smcb_batch* b) { return b ? b->impl->cloud_bytes() : 0; }
+
+int smcb_batch_pack(smcb_batch* b, const int32_t* slots, int64_t n, void* buf_dev) {
+  if (!b) return SMCB_ERR_BAD_ARG;
+  return guarded(b->ctx, [&] {
+    need(n >= 0 && (n == 0 || (slots && buf_dev)), "batch_pack: bad arguments");
+    b->impl->pack(slots, n, buf_dev, true);
+  });
+}
+
+int smcb_batch_unpack(smcb_batch* b, const int32_t* slots, int64_t n, const void* buf_dev) {
+  if (!b) return SMCB_ERR_BAD_ARG;
+  return guarded(b->ctx, [&] {
+    need(n >= 0 && (n == 0 || (slots && buf_dev)), "batch_unpack: bad arguments");
+    b->impl->pack(slots, n, const_cast<void*>(buf_dev), false);
+  });
+}
+
+int smcb_batch_get_timing(const smcb_batch* b, double* ms_last_call, int64_t* launches_total) {
+  if (!b) return SMCB_ERR_BAD_ARG;
+  if (ms_last_call) *ms_last_call = b->impl->last_ms();
+  if (launches_total) *launches_total = b->impl->launches();
+  return SMCB_OK;
+}
+
+// ------------------------------------------------------------------ Kalman
+int smcb_kalman_batch_step(smcb_ctx* ctx, const double* params, int64_t M, double y, double* x, double* sigma,
+                           double* loglik) {
+  if (!ctx) return SMCB_ERR_BAD_ARG;
+  return guarded(ctx, [&] {
+    need(params && x && sigma && loglik && M >= 1, "kalman_batch_step: bad arguments");
+    kalman_batch(ctx->device, ctx->stream, params, nullptr, M, &y, 1, /*predict_first=*/true, loglik, x, sigma,
+                 /*use_state=*/true);
+  });
+}
+
+int smcb_kalman_batch_loglik(smcb_ctx* ctx, const double* params, const uint8_t* active, int64_t M, const double* y,
+                             int64_t T, int matched_init, double* loglik, double* x, double* sigma) {
+  if (!ctx) return SMCB_ERR_BAD_ARG;
+  return guarded(ctx, [&] {
+    need(params && y && loglik && M >= 1 && T >= 1, "kalman_batch_loglik: bad arguments");
+    kalman_batch(ctx->device, ctx->stream, params, active, M, y, T, /*predict_first=*/!matched_init, loglik, x, sigma,
+                 /*use_state=*/false);
+  });
+}
+
+}  // extern "C"

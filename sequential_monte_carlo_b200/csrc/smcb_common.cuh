@@ -1,0 +1,85 @@
+// Shared device helpers for the particle-filter kernels: ordered-double encoding for an exact,
+// order-independent atomic max, warp/block reductions, cache-hinted loads.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/smcb200.h"  // smcb_status error codes
+#include "smcb_detmath.cuh"
+
+namespace smcb {
+
+struct Error {
+  int code;
+  std::string msg;
+};
+
+#define SMCB_CUDA_TRY(expr)                                                                     \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      throw ::smcb::Error{_e == cudaErrorMemoryAllocation ? ::SMCB_ERR_OOM                \
+                                                          : ::SMCB_ERR_CUDA,              \
+                          std::string(#expr) + ": " + cudaGetErrorString(_e)};                  \
+    }                                                                                           \
+  } while (0)
+
+#if defined(__CUDACC__)
+
+constexpr unsigned kFullMask = 0xFFFFFFFFu;
+
+// monotone map double -> uint64 so that atomicMax on the image is max on the doubles
+__device__ __forceinline__ unsigned long long encode_ordered(double d) {
+  unsigned long long b = (unsigned long long)__double_as_longlong(d);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double decode_ordered(unsigned long long e) {
+  unsigned long long b = (e >> 63) ? (e & 0x7FFFFFFFFFFFFFFFull) : ~e;
+  return __longlong_as_double((long long)b);
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    double t = __shfl_xor_sync(kFullMask, v, o);
+    v = (t > v) ? t : v;
+  }
+  return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+  return v;
+}
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);
+  return v;
+}
+// inclusive scan across the lanes of a warp
+__device__ __forceinline__ unsigned long long warp_scan_u64(unsigned long long v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned long long t = __shfl_up_sync(kFullMask, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+__device__ __forceinline__ double ld_cg(const double* p) { return __ldcg(p); }
+
+// number of entries C[lo..hi) that are <= tau, plus lo  (ancestor index, SPEC §5)
+template <class Ptr>
+__device__ __forceinline__ int64_t lower_count(Ptr C, int64_t lo, int64_t hi, uint64_t tau) {
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (C[mid] <= tau) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+#endif  // __CUDACC__
+
+}  // namespace smcb

@@ -1,0 +1,116 @@
+// One large-N bootstrap particle filter resident on one GPU (grid-wide kernels).
+// Host-side driver for bootstrap_filter / bootstrap_filter! / log_likelihood
+// (/root/reference/src/particles.jl:87-147).  Kernels are in smcb_filter.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <vector>
+
+#include "smcb_common.cuh"
+#include "smcb_models.cuh"
+
+namespace smcb {
+
+struct FilterCtrl {
+  unsigned long long maxslot[2];  // ordered-encoded max(logw), slot = t & 1
+  unsigned long long total;       // Q = C[N-1] of the last scan
+  unsigned int scan_ticket;       // dynamic tile ids of the look-back scan
+  unsigned int scan_done;
+};
+
+struct StepStats {  // normalize() ingredients for one time step (SPEC §6)
+  double mx, sum, sum2;
+};
+
+enum { TK_TOTAL = 0, TK_SCAN = 1, TK_PROP = 2, TK_INIT = 3, TK_STATS = 4, TK_COUNT = 5 };
+
+class SingleFilter {
+ public:
+  SingleFilter(int device, cudaStream_t stream) : device_(device), stream_(stream) {}
+  ~SingleFilter();
+
+  // bootstrap_filter(N, y, model): draws the cloud and weights it against y0
+  void init(int kind, const double* params, int64_t N, double y0, const RngKey& key, uint32_t stream_id,
+            StepStats* st);
+  // bootstrap_filter!(x, w, y, model); params may be null (keep)
+  void step(const double* params, double y, int resampler, StepStats* st);
+  // log_likelihood(N, y, model): init + T-1 steps, one host sync at the end; stats_out[T]
+  void run(int kind, const double* params, int64_t N, const double* y, int64_t T, int resampler,
+           const RngKey& key, uint32_t stream_id, StepStats* stats_out);
+
+  // normalize(logw) / resample(w) on caller vectors (scratch use of this object; clobbers its state)
+  void normalize_vector(const double* logw_host, int64_t n, StepStats* st, double* w_host);
+  void resample_vector(const double* w_host, int64_t n, int resampler, const RngKey& key, uint32_t stream_id,
+                       uint32_t t, uint32_t purpose, int64_t* anc_host);
+
+  void fetch(double* x_host, double* w_host, double* logw_host);
+  int64_t fetch_ancestors(int64_t* anc_host, int64_t rows_cap);
+
+  void set_record_ancestors(bool on) { record_anc_ = on; }
+  void set_profiling(bool on) { profiling_ = on; }
+  void timing(double ms[TK_COUNT], int64_t launches[TK_COUNT]) const;
+
+  int64_t N() const { return N_; }
+  int64_t ld() const { return ld_; }
+  int kind() const { return kind_; }
+  uint32_t t() const { return t_; }
+  bool live() const { return N_ > 0; }
+  const double* dev_x() const { return x_[cur_]; }
+  const double* dev_logw() const { return logw_; }
+
+ private:
+  void ensure_capacity(int kind, int64_t N, int64_t anc_rows);
+  void load_vector(const double* host, int64_t n, bool is_log);
+  void begin_call();
+  void end_call();
+  void launch_init(double y0);
+  void launch_prop(double y, int resampler);
+  void launch_scan(int64_t stat_index, bool write_cdf);
+  void mark(int klass, bool start);
+  void release();
+
+  int device_;
+  cudaStream_t stream_;
+  int kind_ = -1;
+  int d_ = 0;
+  int64_t N_ = 0, ld_ = 0, cap_N_ = 0, cap_d_ = 0, cap_stats_ = 0, cap_anc_rows_ = 0;
+  int S_ = 0;
+  uint64_t R_ = 0;
+  uint32_t t_ = 0;
+  uint32_t stream_id_ = 0;
+  RngKey key_{};
+  Derived dv_{};
+  bool record_anc_ = false;
+  bool profiling_ = false;
+  bool from_w_ = false;
+  int64_t anc_rows_ = 0;  // rows currently valid in anc_
+  int cur_ = 0;
+  StepStats last_{};
+
+  double* x_[2] = {nullptr, nullptr};
+  double* logw_ = nullptr;
+  double* w_tmp_ = nullptr;
+  uint64_t* cdf_ = nullptr;
+  int32_t* anc_ = nullptr;
+  FilterCtrl* ctrl_ = nullptr;
+  unsigned long long* desc_ = nullptr;  // [2][ntiles_cap]
+  double* psum_ = nullptr;
+  double* psum2_ = nullptr;
+  StepStats* stats_dev_ = nullptr;
+  int64_t ntiles_cap_ = 0;
+
+  // timing
+  cudaEvent_t ev_call_[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> ev_pool_;
+  struct Mark {
+    int klass;
+    size_t e0, e1;
+  };
+  std::vector<Mark> marks_;
+  size_t ev_used_ = 0;
+  double ms_[TK_COUNT] = {0, 0, 0, 0, 0};
+  int64_t launches_[TK_COUNT] = {0, 0, 0, 0, 0};
+};
+
+}  // namespace smcb
