@@ -1,0 +1,272 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the particle-filter hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--logn 24] [--T 1000]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one `log_likelihood(N, y, model)` sweep (bootstrap PF, resample every step) of the
+univariate LinearGaussian lg_mod([0.5,0.9,0.8]) over T synthetic observations — BASELINE.json
+configs[1] at its largest size (N = 2^24, T = 1000) — through the C ABI of libsmcb200.so.
+
+  value  particle-updates/s (N*T per sweep), device time of the sweeps (CUDA events on the library's
+         stream; the only inputs, y[T] and 6 parameters, travel as kernel arguments)
+  e2e    the same metric through the public Python API `log_likelihood(N, y, model) -> (x, w, logZ)`
+         with host buffers: wall clock including the D2H copy of the final cloud and weights
+  roofline  the fused step (sum + bounds + propagate kernels) against the measured HBM peak using
+         SURVEY.md §8(d)'s 56 algorithmic bytes per particle-update; per-kernel split alongside
+  cpu_baseline  the CPU oracle (a port of the Julia reference; Julia is not in this image) timed on
+         the host cores on a bounded sample
+
+N > 1 GPUs: a single filter does not shard (global scan + gather every step: "replicas only",
+DESIGN.md §5) — every rank runs its own filter on its own Philox stream (weak scaling).  The
+θ-sharded SMC² numbers (the path that does shard) ride along in the "smc2" object.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LG_THETA = [0.5, 0.9, 0.8]                       # README.md:21  (A, Q, R)
+LG_PARAMS = [0.5, 1.0, 0.9, 0.8, 0.0, 1.0]       # A, B, Q, R, x0, σ0
+BYTES_PER_UPDATE = 56
+DATA_SEED = 1998
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.thread.join(timeout=2)
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1])); power.append(float(r[2]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_sample(steps, logn_sample=20, T_sample=16):
+    """The oracle's log_likelihood (port of particles.jl:132-147; single-threaded like the reference)."""
+    from oracle import oracle as o
+    o.build()
+    N = 1 << logn_sample
+    _, y = o.simulate(0, LG_PARAMS, T_sample, DATA_SEED)
+    times = []
+    for s in range(steps):
+        t0 = time.perf_counter()
+        o.log_likelihood(0, LG_PARAMS, N, y, o.SYSTEMATIC, seed=DATA_SEED, epoch=s)
+        times.append(time.perf_counter() - t0)
+    return N * T_sample / statistics.mean(times), f"LG1D N=2^{logn_sample}, T={T_sample}, systematic, oracle/smc_oracle.c (gcc -O2), linear in N*T"
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    v, sample = cpu_sample(max(args.steps, 1) + 0, 20, 16)
+    N, T = 1 << args.logn, args.T
+    line = {
+        "impl": "reference", "metric": "particle-updates/sec (N×T) bootstrap PF", "value": v, "unit": "particle-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * N * T / v,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(N, T),
+        "cpu_baseline": {"value": v, "unit": "particle-updates/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "Julia is not installed in this image and the reference module does not load as shipped (SURVEY F2/F7): the "
+                "reference arm is the C port of its algorithm; the reference PF is single-threaded (particles.jl:122)",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(N, T):
+    return {"workload": f"log_likelihood bootstrap PF, univariate LinearGaussian lg_mod([0.5,0.9,0.8]), N=2^{N.bit_length() - 1} "
+                        f"particles, T={T}, systematic resampling every step (BASELINE.json configs[1])",
+            "N": N, "T": T, "resampler": "systematic", "model": None, "l2": "working set (x ping-pong + logw, 0.4 GB) larger than L2",
+            "parallelism": "replicas (one filter per GPU)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--logn", type=int, default=24)
+    ap.add_argument("--T", type=int, default=1000)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-smc2", action="store_true", help="skip the θ-sharded SMC² leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import sequential_monte_carlo_b200 as smc
+    from sequential_monte_carlo_b200 import particles, state_space_models as ssm
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libsmcb200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    N, T = 1 << args.logn, args.T
+    _, y = smc._lib.simulate(smc.KIND_LG1D, LG_PARAMS, T, DATA_SEED)
+    model = ssm.LinearGaussian(LG_THETA[0], 1.0, LG_THETA[1], LG_THETA[2], 0.0)
+    particles.set_default_context(smc.Context(local, seed=DATA_SEED + rank))
+    ctx = particles.default_context()
+    rs = smc.SYSTEMATIC
+
+    # ---- kernel-level arm: sweeps with device-resident state, device-event timing
+    for _ in range(args.warmup):
+        ctx.log_likelihood(smc.KIND_LG1D, LG_PARAMS, N, y, rs, stream=rank)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    dev_ms, launches = 0.0, 0
+    for _ in range(args.steps):
+        ctx.log_likelihood(smc.KIND_LG1D, LG_PARAMS, N, y, rs, stream=rank)
+        ms, n = ctx.timing()
+        dev_ms += ms["total"]
+        launches += n["total"]
+    barrier()
+    wall_kernel = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    # ---- per-kernel durations (CUDA events around every launch; same workload, K sweeps)
+    ctx.set_profiling(True)
+    kms = {"scan": 0.0, "prop": 0.0, "init": 0.0, "stats": 0.0, "bounds": 0.0}
+    kn = dict.fromkeys(kms, 0)
+    for _ in range(max(1, min(args.steps, 2))):
+        ctx.log_likelihood(smc.KIND_LG1D, LG_PARAMS, N, y, rs, stream=rank)
+        ms, n = ctx.timing()
+        for k in kms:
+            kms[k] += ms.get(k, 0.0)
+            kn[k] += n.get(k, 0)
+    ctx.set_profiling(False)
+
+    # ---- end-to-end arm: public API with host buffers, D2H of (x, w) inside the timed region
+    for _ in range(1):
+        particles.log_likelihood(N, y, model, resampler="systematic")
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        x, w, logZ = particles.log_likelihood(N, y, model, resampler="systematic")
+        _ = float(logZ) + float(w[0]) + float(x[0])
+    barrier()
+    wall_e2e = time.perf_counter() - t0
+
+    tmax = torch.tensor([dev_ms, wall_kernel, wall_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dev_ms_max, wall_kernel_max, wall_e2e_max = (float(v) for v in tmax.tolist())
+
+    units = N * T * args.steps * world
+    value = units / (dev_ms_max * 1e-3)
+    e2e = units / wall_e2e_max
+    peak, peak_src = measured_peak()
+    step_us = {k: (1e3 * kms[k] / kn[k] if kn[k] else None) for k in kms}
+    fused = sum(v for k, v in step_us.items() if k in ("scan", "bounds", "prop") and v)
+    achieved = BYTES_PER_UPDATE * N / (fused * 1e-6) / 1e9 if fused else None
+
+    line = {
+        "metric": "particle-updates/sec (N×T) bootstrap PF", "value": value, "unit": "particle-updates/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic (simulate(), Philox seed 1998)",
+        "config": workload_config(N, T),
+        "e2e": {"value": e2e, "unit": "particle-updates/s", "h2d_bytes_per_step": int(8 * T + 64),
+                "d2h_bytes_per_step": int(16 * N + 8), "ms_per_step": 1e3 * wall_e2e_max / args.steps},
+        "gpu_launches": launches,
+        "wall_ms_per_step_kernel_arm": 1e3 * wall_kernel_max / args.steps,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
+                     "traffic": load_traffic(), "peak_source": peak_src,
+                     "kernel": "one filter step = sum_kernel + bounds_kernel + prop_kernel (56 algorithmic B/particle-update, SURVEY §8d)",
+                     "avg_us_per_launch": step_us},
+        "clocks": clocks,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu:
+        v, sample = cpu_sample(2, 20, 16)
+        line["cpu_baseline"] = {"value": v, "unit": "particle-updates/s", "cores": 1, "kind": "port", "sample": sample}
+    if not args.no_smc2:
+        try:
+            from sequential_monte_carlo_b200 import bench_smc2
+            line["smc2"] = bench_smc2.run(local, rank, world)
+        except Exception as e:  # the headline line must still print
+            line["smc2"] = {"error": repr(e)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def load_traffic():
+    """dram bytes per fused step from the committed ncu capture (profiles/), or null."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p))["dram_bytes_per_step"]
+    except Exception:
+        return None
+
+
+if __name__ == "__main__":
+    main()

@@ -97,7 +97,8 @@ int smcb_log_likelihood(smcb_ctx* ctx, int kind, const double* params, int64_t N
 /* x [d*N] SoA, w [N] normalised weights, logw [N] unnormalised log-weights; any may be NULL */
 int smcb_fetch_state(smcb_ctx* ctx, double* x, double* w, double* logw);
 /* ancestors of steps t = 1 .. T-1 ([T-1][N], row t-1 = step t) if recording was on, else the
- * last step's only (rows = 1).  rows_cap = rows the buffer can take. */
+ * last step's only when stepping with bootstrap_step (rows = 1); 0 rows when recording is off.
+ * rows_cap = rows the buffer can take. */
 int smcb_fetch_ancestors(smcb_ctx* ctx, int64_t* ancestors, int64_t rows_cap, int64_t* rows_out);
 /* device views of the current cloud (valid until the next call on ctx) */
 int smcb_device_state(smcb_ctx* ctx, const double** x_dev, const double** logw_dev, int64_t* ld);
@@ -140,6 +141,20 @@ int smcb_kalman_batch_step(smcb_ctx* ctx, const double* params, int64_t M, doubl
 int smcb_kalman_batch_loglik(smcb_ctx* ctx, const double* params, const uint8_t* active, int64_t M,
                              const double* y, int64_t T, int matched_init, double* loglik, double* x,
                              double* sigma);
+
+/* ------------------------------------------------------------------ host-side helpers (no GPU) */
+/* The θ-level samplers draw priors, MH proposals and accept uniforms on the host from the same
+ * Philox stream and the same deterministic Box-Muller as the device (docs/SPEC.md §2-§3), so a run
+ * is reproducible bit-for-bit across GPU counts.  These run on the CPU and need no context. */
+int smcb_rng_normals(uint64_t seed, uint32_t epoch, uint32_t stream, uint32_t t, uint32_t purpose, uint32_t comp,
+                     int64_t n, double* out);
+int smcb_rng_uniforms64(uint64_t seed, uint32_t epoch, uint32_t stream, uint32_t t, uint32_t purpose, int64_t n,
+                        uint64_t* out);
+/* simulate(model, T) -> (x [d][T], y [T])                               state_space_models.jl:11-28 */
+int smcb_simulate(int kind, const double* params, int64_t T, uint64_t seed, double* x, double* y);
+/* device self-test of the deterministic math (parity tests): fn 0 exp, 1 log, 2 sincos2pi (out0=sin,
+ * out1=cos), 3 quantise with shift S = (int)aux -> out0 holds uint64 bit patterns */
+int smcb_selftest_math(smcb_ctx* ctx, int fn, const double* in, int64_t n, double aux, double* out0, double* out1);
 
 #ifdef __cplusplus
 }

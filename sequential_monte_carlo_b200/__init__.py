@@ -4,6 +4,18 @@ density_tempered).  Python host mirror over the C ABI of include/smcb200.h; all 
 hand-written sm_100a CUDA (csrc/).  No CPU fallback.
 """
 from . import _lib
-from ._lib import LG1D, SV, UCSV, MULTINOMIAL, STRATIFIED, SYSTEMATIC, Context, Batch, SMCBError  # noqa: F401
+from ._lib import MULTINOMIAL, STRATIFIED, SYSTEMATIC, Context, Batch, SMCBError  # noqa: F401
+from ._lib import LG1D as KIND_LG1D, SV as KIND_SV, UCSV as KIND_UCSV  # noqa: F401
 
 __version__ = "0.1.0"
+
+from .state_space_models import (StateSpaceModel, LinearModel, UnivariateLinearGaussian, LinearGaussian,  # noqa: E402,F401
+                                 unobserved_components, UC, UCSV, unobserved_components_stochastic_volatility,
+                                 StochasticVolatility, SV, simulate, preallocate)
+from .particles import (normalize, reweight, resample, bootstrap_filter, bootstrap_filter_, log_likelihood,  # noqa: E402,F401
+                        default_context, set_default_context)
+from .priors import Normal, LogNormal, Uniform, TruncatedNormal, product_distribution  # noqa: E402,F401
+from .smc_samplers import (SMC, smc2, smc2_step, density_tempered, expected_parameters, random_walk_kernel,  # noqa: E402,F401
+                           LocalComm, TorchComm)
+from .ibis import IBIS  # noqa: E402,F401
+from . import kalman_filter, ibis, smc_samplers, particles, state_space_models, priors  # noqa: E402,F401

@@ -57,6 +57,10 @@ SIGNATURES = {
     "smcb_kalman_batch_step": (C.c_int, [_c_ctx, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "smcb_kalman_batch_loglik": (C.c_int, [_c_ctx, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p]),
+    "smcb_rng_normals": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int64, C.c_void_p]),
+    "smcb_rng_uniforms64": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int64, C.c_void_p]),
+    "smcb_simulate": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "smcb_selftest_math": (C.c_int, [_c_ctx, C.c_int, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p]),
 }
 
 _LIB = None
@@ -102,6 +106,41 @@ def params8(p):
 
 def state_dim(kind):
     return 3 if kind == UCSV else 1
+
+
+def rng_normals(seed, epoch, stream, t, purpose, comp, n):
+    """n standard normals of the host-level Philox stream (docs/SPEC.md §2); CPU only."""
+    out = np.empty(int(n))
+    rc = load().smcb_rng_normals(C.c_uint64(int(seed) & (2 ** 64 - 1)), int(epoch), int(stream), int(t), int(purpose), int(comp),
+                                 int(n), _ptr(out))
+    if rc != 0:
+        raise SMCBError(rc, "smcb_rng_normals: bad arguments")
+    return out
+
+
+def rng_uniforms64(seed, epoch, stream, t, purpose, n):
+    out = np.empty(int(n), np.uint64)
+    rc = load().smcb_rng_uniforms64(C.c_uint64(int(seed) & (2 ** 64 - 1)), int(epoch), int(stream), int(t), int(purpose), int(n),
+                                    _ptr(out))
+    if rc != 0:
+        raise SMCBError(rc, "smcb_rng_uniforms64: bad arguments")
+    return out
+
+
+def rng_uniforms01(seed, epoch, stream, t, purpose, n):
+    """(U64 >> 11) * 2^-53 in [0, 1)."""
+    return (rng_uniforms64(seed, epoch, stream, t, purpose, n) >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
+
+
+def simulate(kind, params, T, seed):
+    """simulate(model, T) -> (x [d, T], y [T])   /root/reference/src/state_space_models.jl:11-28; CPU only."""
+    p = params8(params)
+    x = np.empty((state_dim(kind), int(T)))
+    y = np.empty(int(T))
+    rc = load().smcb_simulate(int(kind), _ptr(p), int(T), C.c_uint64(int(seed) & (2 ** 64 - 1)), _ptr(x), _ptr(y))
+    if rc != 0:
+        raise SMCBError(rc, "smcb_simulate: bad arguments")
+    return x, y
 
 
 class Context:
@@ -216,6 +255,12 @@ class Context:
         got = C.c_int64()
         self._check(self._lib.smcb_fetch_ancestors(self._h, _ptr(a), a.shape[0], C.byref(got)))
         return a[: got.value]
+
+    def selftest_math(self, fn, values, aux=0.0):
+        v = np.ascontiguousarray(values, np.float64)
+        o0, o1 = np.empty_like(v), np.empty_like(v)
+        self._check(self._lib.smcb_selftest_math(self._h, int(fn), _ptr(v), v.size, float(aux), _ptr(o0), _ptr(o1)))
+        return o0, o1
 
     # ---- Kalman
     def kalman_step(self, params, x, sigma, y):

@@ -16,7 +16,7 @@ HEADERS = ["smcb_common.cuh", "smcb_detmath.cuh", "smcb_models.cuh", "smcb_filte
            os.path.join("..", "..", "include", "smcb200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off",
+    "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off", "-Xcompiler", "-mfma",
     "-diag-suppress", "177",
 ]
 

@@ -341,4 +341,101 @@ int smcb_kalman_batch_loglik(smcb_ctx* ctx, const double* params, const uint8_t*
   });
 }
 
+// ------------------------------------------------------------------ host-side helpers
+int smcb_rng_normals(uint64_t seed, uint32_t epoch, uint32_t stream, uint32_t t, uint32_t purpose, uint32_t comp,
+                     int64_t n, double* out) {
+  if (!out || n < 0 || purpose > 15 || comp > 15) return SMCB_ERR_BAD_ARG;
+  const RngKey key{(uint32_t)seed, (uint32_t)(seed >> 32), epoch & 0xFFFFFFu};
+  for (int64_t p = 0; 2 * p < n; ++p) {
+    double z0, z1;
+    normal_pair_at(key, (uint32_t)p, stream, t, purpose, comp, z0, z1);
+    out[2 * p] = z0;
+    if (2 * p + 1 < n) out[2 * p + 1] = z1;
+  }
+  return SMCB_OK;
+}
+
+int smcb_rng_uniforms64(uint64_t seed, uint32_t epoch, uint32_t stream, uint32_t t, uint32_t purpose, int64_t n,
+                        uint64_t* out) {
+  if (!out || n < 0 || purpose > 15) return SMCB_ERR_BAD_ARG;
+  const RngKey key{(uint32_t)seed, (uint32_t)(seed >> 32), epoch & 0xFFFFFFu};
+  for (int64_t i = 0; i < n; ++i) out[i] = uniform64_at(key, (uint32_t)i, stream, t, purpose);
+  return SMCB_OK;
+}
+
+}  // extern "C"
+
+namespace {
+template <class Model>
+void simulate_model(const double* D, const double* P, int64_t T, uint64_t seed, double* x, double* y) {
+  // state noise: purpose SIMULATE stream 0 component k, index t; observation noise: stream 1
+  const RngKey key{(uint32_t)seed, (uint32_t)(seed >> 32), 0u};
+  Model mdl;
+  mdl.load(D);
+  constexpr int DIM = Model::D;
+  double cur[DIM], nxt[DIM], z[DIM];
+  for (int64_t t = 0; t < T; ++t) {
+    for (int k = 0; k < DIM; ++k) {
+      double z0, z1;
+      normal_pair_at(key, (uint32_t)(t >> 1), 0u, 0u, PURPOSE_SIMULATE, (uint32_t)k, z0, z1);
+      z[k] = (t & 1) ? z1 : z0;
+    }
+    if (t == 0) mdl.init(z, nxt); else mdl.transition(z, cur, nxt);
+    for (int k = 0; k < DIM; ++k) { cur[k] = nxt[k]; x[(int64_t)k * T + t] = cur[k]; }
+    double z0, z1;
+    normal_pair_at(key, (uint32_t)(t >> 1), 1u, 0u, PURPOSE_SIMULATE, 0u, z0, z1);
+    const double zo = (t & 1) ? z1 : z0;
+    double mean, sd;
+    if (Model::KIND == KIND_LG1D) { mean = D[1] * cur[0]; sd = sqrt(P[3]); }
+    else if (Model::KIND == KIND_SV) { mean = 0.0; sd = det_exp(0.5 * cur[0]); }
+    else { mean = cur[0]; sd = det_exp(0.5 * cur[DIM - 1]); }
+    y[t] = fma(sd, zo, mean);
+  }
+}
+
+__global__ void selftest_kernel(int fn, const double* in, int64_t n, double aux, double* o0, double* o1) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double v = in[i];
+  if (fn == 0) o0[i] = det_exp(v);
+  else if (fn == 1) o0[i] = det_log(v);
+  else if (fn == 2) { double s, c; det_sincos2pi(v, s, c); o0[i] = s; o1[i] = c; }
+  else { double e; uint64_t q; det_exp_quant(v, (int)aux, e, q); o0[i] = u64_as_double(q); o1[i] = e; }
+}
+}  // namespace
+
+extern "C" {
+
+int smcb_simulate(int kind, const double* params, int64_t T, uint64_t seed, double* x, double* y) {
+  if (!params || !x || !y || T < 1 || kind < 0 || kind >= KIND_COUNT) return SMCB_ERR_BAD_ARG;
+  double D[kParamStride];
+  derive_params(kind, params, D);
+  if (kind == KIND_LG1D) simulate_model<ModelLG1D>(D, params, T, seed, x, y);
+  else if (kind == KIND_SV) simulate_model<ModelSV>(D, params, T, seed, x, y);
+  else simulate_model<ModelUCSV>(D, params, T, seed, x, y);
+  return SMCB_OK;
+}
+
+int smcb_selftest_math(smcb_ctx* ctx, int fn, const double* in, int64_t n, double aux, double* out0, double* out1) {
+  if (!ctx) return SMCB_ERR_BAD_ARG;
+  return guarded(ctx, [&] {
+    need(in && out0 && n >= 1 && fn >= 0 && fn <= 3, "selftest_math: bad arguments");
+    SMCB_CUDA_TRY(cudaSetDevice(ctx->device));
+    double *di = nullptr, *d0 = nullptr, *d1 = nullptr;
+    cudaError_t e = cudaMalloc(&di, sizeof(double) * n);
+    if (e == cudaSuccess) e = cudaMalloc(&d0, sizeof(double) * n);
+    if (e == cudaSuccess) e = cudaMalloc(&d1, sizeof(double) * n);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(di, in, sizeof(double) * n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) {
+      selftest_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>(fn, di, n, aux, d0, d1);
+      e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out0, d0, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && out1 && fn >= 2) e = cudaMemcpyAsync(out1, d1, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(di); cudaFree(d0); cudaFree(d1);
+    SMCB_CUDA_TRY(e);
+  });
+}
+
 }  // extern "C"

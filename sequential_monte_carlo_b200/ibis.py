@@ -1,0 +1,123 @@
+"""IBIS — host mirror of /root/reference/src/ibis.jl: the θ-level sampler of SMC² with the exact
+Kalman filter as inner filter (LG1D only; no state particles).  The M scalar recursions run as one
+device launch (csrc/smcb_batch.cu: kalman_kernel)."""
+import math
+import sys
+
+import numpy as np
+
+from . import _lib
+from .particles import default_context, resampler_id
+from .smc_samplers import _propose, random_walk_kernel
+
+
+class IBIS:
+    """mutable struct IBIS + constructor (ibis.jl:3-52).  Fields θ, ω, x, Σ, ess, ess_min, M, chain,
+    logZ, model, prior, kernel, acc_threshold, acc_ratio as in the reference."""
+
+    def __init__(self, M, model, prior, chain, ess_threshold, min_ar=-1.0, *, seed=1998, theta_resampler="multinomial", ctx=None):
+        self.M, self.chain, self.model, self.prior = int(M), int(chain), model, prior
+        self.seed = int(seed)
+        self.theta_resampler = resampler_id(theta_resampler)
+        self.ctx = ctx or default_context()
+        self.kernel = random_walk_kernel
+        self.θ = prior.sample(self.M, self.seed)                     # :34
+        self.ω = np.full(self.M, 1.0 / self.M)                       # :35
+        P = self._params(self.θ)
+        self.x = P[:, 4].copy()                                      # [mod.x0 for mod in mods]   :38
+        self.Σ = P[:, 5].copy()                                      # [mod.σ0 for mod in mods]   :39
+        self.logZ = np.zeros(self.M)
+        self.ess, self.ess_min = 1.0 * self.M, self.M * float(ess_threshold)
+        self.acc_threshold, self.acc_ratio = float(min_ar), 0.0
+        self._n_resample = self._n_rejuv = 0
+
+    def _params(self, θ):
+        ms = [self.model(th) for th in θ]
+        if ms and ms[0].kind != _lib.LG1D:
+            raise TypeError("IBIS needs a LinearModel (the inner filter is the Kalman filter, ibis.jl:100,172)")
+        return np.stack([m.params8() for m in ms])
+
+
+def resample_(ibis):
+    """resample!(ibis) (ibis.jl:72-84) — permutes θ, x, Σ, logZ."""
+    ibis.ctx.set_rng(ibis.seed, 0)
+    a = ibis.ctx.resample(ibis.ω, ibis.theta_resampler, stream=0, t=ibis._n_resample, purpose=_lib.P_THETA_RESAMPLE)
+    ibis._n_resample += 1
+    ibis.θ, ibis.x, ibis.Σ, ibis.logZ = ibis.θ[a], ibis.x[a], ibis.Σ[a], ibis.logZ[a]
+    ibis.ω = np.full(ibis.M, 1.0 / ibis.M)
+    return a
+
+
+def rejuvenate_(ibis, y, ξ=1.0, verbose=False):
+    """rejuvenate!(ibis, y, ξ, verbose) (ibis.jl:86-125)"""
+    y = np.ascontiguousarray(y, np.float64)
+    M, d = ibis.θ.shape
+    acc = np.zeros(M, bool)
+    Σk, univariate = ibis.kernel(ibis.θ)
+    scales = 0.5 * np.arange(ibis.chain, 0, -1)
+    if verbose:
+        sys.stdout.write("\t[rejuvenating]")
+    ordinal = ibis._n_rejuv
+    ibis._n_rejuv += 1
+    lp_cur = np.array([ibis.prior.logpdf(th) for th in ibis.θ])
+    for c in range(ibis.chain):
+        z = np.stack([_lib.rng_normals(ibis.seed, ordinal, k, c, _lib.P_MH_PROPOSAL, 0, M) for k in range(d)], axis=1)
+        θ_prop = _propose(ibis.θ, Σk, univariate, scales[c], z)
+        ok = np.array([ibis.prior.insupport(th) for th in θ_prop])
+        P = ibis._params(np.where(ok[:, None], θ_prop, ibis.θ))
+        logZ_prop, x_prop, Σ_prop = ibis.ctx.kalman_loglik(P, y, matched_init=False, active=ok.astype(np.uint8))   # :100
+        lp_prop = np.array([ibis.prior.logpdf(th) if o else -math.inf for th, o in zip(θ_prop, ok)])
+        with np.errstate(invalid="ignore", divide="ignore"):
+            ratio = ξ * (logZ_prop - ibis.logZ) + (lp_prop - lp_cur)
+            u = _lib.rng_uniforms01(ibis.seed, ordinal, 0, c, _lib.P_MH_ACCEPT, M)
+            accept = ok & (logZ_prop + lp_prop > -math.inf) & (np.log(u) < ratio)
+        ibis.logZ = np.where(accept, logZ_prop, ibis.logZ)
+        ibis.θ = np.where(accept[:, None], θ_prop, ibis.θ)
+        ibis.x = np.where(accept, x_prop, ibis.x)
+        ibis.Σ = np.where(accept, Σ_prop, ibis.Σ)
+        lp_cur = np.where(accept, lp_prop, lp_cur)
+        acc |= accept
+    ibis.ω = np.full(M, 1.0 / M)
+    ibis.acc_ratio = float(acc.sum()) / M
+    if verbose:
+        sys.stdout.write("\tacc_rate: %1.5f" % ibis.acc_ratio)
+    return ibis
+
+
+def smc2(ibis, y):
+    """smc²(ibis, y) (ibis.jl:128-147)"""
+    y = np.ascontiguousarray(y, np.float64)
+    ibis.x, ibis.Σ, ll = ibis.ctx.kalman_step(ibis._params(ibis.θ), ibis.x, ibis.Σ, y[0])
+    ibis.logZ = ll.copy()
+    _, ibis.ω, ibis.ess = ibis.ctx.normalize(ll)
+    return ibis
+
+
+def smc2_step(ibis, y, t, verbose=True):
+    """smc²!(ibis, y, t) (ibis.jl:154-189); t 0-based."""
+    y = np.ascontiguousarray(y, np.float64)
+    if verbose:
+        sys.stdout.write("t = %4d\tess = %4.3f" % (t, ibis.ess))
+    ibis.rejuvenated = False
+    if ibis.ess < ibis.ess_min:
+        resample_(ibis)
+        rejuvenate_(ibis, y[:t], 1.0, verbose)
+        ibis.rejuvenated = True
+    with np.errstate(divide="ignore"):
+        logω = np.log(ibis.ω)
+    ibis.x, ibis.Σ, ll = ibis.ctx.kalman_step(ibis._params(ibis.θ), ibis.x, ibis.Σ, y[t])   # :172-177
+    logω = logω + ll
+    ibis.logZ = ibis.logZ + ll
+    _, ibis.ω, ibis.ess = ibis.ctx.normalize(logω)
+    if verbose:
+        sys.stdout.write("\n")
+    return ibis
+
+
+def expected_parameters(ibis, reference_style=False):
+    """ibis.jl:54-58 (same D6 quirk as SMC's)"""
+    ω = ibis.ω
+    if reference_style:
+        e = np.exp(ω - ω.max())
+        ω = e / e.sum()
+    return (ibis.θ * ω[:, None]).sum(axis=0)[:, None]

@@ -1,0 +1,407 @@
+"""θ-level samplers — host mirror of /root/reference/src/smc_samplers.jl.
+
+    SMC(N, M, model, prior, chain, ess_threshold, min_ar=-1.0)        smc_samplers.jl:5-59
+    smc2(smc, y)                       (Julia: smc²)                  :288-301
+    smc2_step(smc, y, t, verbose)      (Julia: smc²!)                 :308-340
+    density_tempered(smc, y, verbose)                                 :222-281
+    expected_parameters(smc)                                          :61-65
+    resample_ / rejuvenate_ / random_walk_kernel                      :74-148
+
+The reference loops over θ-particles on the host (`Threads.@threads`, or serially in smc²!) and runs
+one CPU particle filter per θ.  Here every such loop is ONE batched launch over all θ
+(`_lib.Batch`, csrc/smcb_batch.cu); the host keeps only the M-length control flow.  With a
+communicator the θ-particles are sharded across GPUs (one process per GPU): every rank holds whole
+state clouds for its slice, the M-length vectors are replicated through all-gathers, and the
+clouds of resampled parents move between GPUs.  Results do not depend on the
+number of GPUs: Philox streams are indexed by the global θ index.
+
+Python spelling: `t` is the 0-based index of the observation being assimilated (Julia's t-1);
+ancestors are 0-based.  Decisions on the reference's defects D3–D7 are in DESIGN.md.
+"""
+import math
+import sys
+
+import numpy as np
+
+from . import _lib
+from .particles import default_context, resampler_id
+
+
+# ----------------------------------------------------------------------------- communicator
+class LocalComm:
+    """world of one GPU"""
+    rank, world = 0, 1
+
+    def all_gather(self, local):
+        return np.ascontiguousarray(local)
+
+    def exchange(self, send, recv_counts, nbytes):  # pragma: no cover - never called with world == 1
+        raise RuntimeError("no peers")
+
+
+class TorchComm:
+    """One process per GPU over torch.distributed (NCCL on GPUs; gloo in the CPU tests).
+    all_gather moves the replicated M-length vectors; exchange moves packed clouds point-to-point."""
+
+    def __init__(self, device=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+        self.device = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
+                                                          if dist.get_backend() == "nccl" else torch.device("cpu"))
+
+    def all_gather(self, local):
+        t = self.torch.from_numpy(np.ascontiguousarray(local, np.float64)).to(self.device)
+        out = self.torch.empty((self.world * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device)
+        self.dist.all_gather_into_tensor(out, t)   # rank-major concatenation along dim 0
+        return out.cpu().numpy()
+
+    def exchange(self, send, recv_counts, nbytes):
+        """send: {dst_rank: uint8 tensor of k*nbytes}; recv_counts: {src_rank: k}.  Returns {src: tensor}."""
+        ops, recv = [], {}
+        for src, k in sorted(recv_counts.items()):
+            recv[src] = self.torch.empty(k * nbytes, dtype=self.torch.uint8, device=self.device)
+            ops.append(self.dist.P2POp(self.dist.irecv, recv[src], src))
+        for dst, buf in sorted(send.items()):
+            ops.append(self.dist.P2POp(self.dist.isend, buf, dst))
+        if ops:
+            for w in self.dist.batch_isend_irecv(ops):
+                w.wait()
+            if self.device.type == "cuda":
+                self.torch.cuda.synchronize(self.device)
+        return recv
+
+
+def exchange_plan(parents, rank, world):
+    """Who sends which cloud where after a θ-resample (replicated, deterministic).
+    Returns (local_parents[Mloc] int32, send {dst: [src local slots]}, recv {src: [dst local slots]})."""
+    parents = np.asarray(parents, np.int64)
+    M = parents.size
+    Mloc = M // world
+    owner = parents // Mloc
+    dst_rank = np.arange(M) // Mloc
+    lo = rank * Mloc
+    local_parents = np.arange(Mloc, dtype=np.int32)
+    mine = slice(lo, lo + Mloc)
+    is_local = owner[mine] == rank
+    local_parents[is_local] = (parents[mine][is_local] - lo).astype(np.int32)
+    send, recv = {}, {}
+    for m in np.flatnonzero(owner != dst_rank):  # increasing m on both sides => matching order
+        if owner[m] == rank:
+            send.setdefault(int(dst_rank[m]), []).append(int(parents[m] - lo))
+        if dst_rank[m] == rank:
+            recv.setdefault(int(owner[m]), []).append(int(m - lo))
+    return local_parents, send, recv
+
+
+# ----------------------------------------------------------------------------- proposal kernel
+def random_walk_kernel(θ):
+    """smc_samplers.jl:87-101.  θ: [M, d].  Returns Σ (d×d) such that proposals are
+    MvNormal(x, scale·Σ); for d = 1 the reference uses σ = 2.83²·var + 1e-10 as a standard
+    deviation (Normal(x, scale·σ)) — kept, and encoded as Σ = σ² with scale applied to σ."""
+    θ = np.asarray(θ, np.float64)
+    M, d = θ.shape
+    c = θ - θ.mean(axis=0)
+    cov = (c.T @ c) / (M - 1)
+    if d == 1:
+        dθ = 2.83 ** 2
+        σ = 1.0e-2 if abs(cov[0, 0]) < 1.0e-8 else dθ * cov[0, 0] + 1.0e-10
+        return np.array([[σ]]), True
+    dθ = 2.83 ** 2 / d
+    if math.sqrt(float(np.sum(cov * cov))) < 1.0e-8:
+        return 1.0e-2 * np.eye(d), False
+    return dθ * cov + 1.0e-10 * np.eye(d), False
+
+
+def _propose(θ, Σ, univariate, scale, z):
+    if univariate:
+        return θ + (scale * Σ[0, 0]) * z
+    L = np.linalg.cholesky(scale * Σ)
+    return θ + z @ L.T
+
+
+# ----------------------------------------------------------------------------- the sampler
+class SMC:
+    """mutable struct SMC (smc_samplers.jl:5-27) + constructor (:29-59).
+
+    N state particles per θ, M θ-particles.  Public fields as in the reference:
+    θ [M, d], ω [M], ess, ess_min, N, M, chain, logZ [M], model, prior, kernel, acc_threshold,
+    acc_ratio; `x` and `w` are read from the device on access ([M_local, d, N] / [M_local, N]).
+    """
+
+    def __init__(self, N, M, model, prior, chain, ess_threshold, min_ar=-1.0, *, seed=1998, resampler="multinomial",
+                 theta_resampler="multinomial", ctx=None, comm=None):
+        self.N, self.M, self.chain = int(N), int(M), int(chain)
+        self.model, self.prior = model, prior
+        self.kernel = random_walk_kernel
+        self.acc_threshold, self.acc_ratio = float(min_ar), 0.0
+        self.seed = int(seed)
+        self.resampler = resampler_id(resampler)
+        self.theta_resampler = resampler_id(theta_resampler)
+        self.comm = comm or LocalComm()
+        if self.M % self.comm.world:
+            raise ValueError(f"M={self.M} must be divisible by the number of GPUs ({self.comm.world})")
+        self.Mloc = self.M // self.comm.world
+        self.lo = self.comm.rank * self.Mloc
+        self.ctx = ctx or default_context()
+        self.θ = prior.sample(self.M, self.seed)                       # θ = map(m -> rand(prior), 1:M)      :38
+        self.ω = np.full(self.M, 1.0 / self.M)                         # :39
+        self.logZ = np.zeros(self.M)                                   # :44
+        self.ess = 1.0 * self.M                                        # :45
+        self.ess_min = self.M * float(ess_threshold)                   # :46
+        m0 = model(self.θ[0])
+        self.kind, self.d = m0.kind, m0.state_dim
+        self._cur = self.ctx.batch(self.kind, self.Mloc, self.N)
+        self._prop = None
+        self._epoch = 1          # ordinal of the next batched sweep (device Philox epoch)
+        self._n_resample = 0     # ordinal of the next θ-resample
+        self._n_rejuv = 0        # ordinal of the next rejuvenation (host Philox epoch)
+        self.stats = {"sweeps": 0, "particle_updates": 0, "device_ms": 0.0, "clouds_moved": 0}
+
+    # -- helpers
+    def _params(self, θ):
+        return np.stack([self.model(th).params8() for th in θ])
+
+    def _local(self, v):
+        return v[self.lo: self.lo + self.Mloc]
+
+    def _next_epoch(self):
+        e = self._epoch
+        self._epoch += 1
+        self.ctx.set_rng(self.seed, e)
+        return e
+
+    def _account(self, batch, steps):
+        ms, _ = batch.timing()
+        self.stats["sweeps"] += 1
+        self.stats["particle_updates"] += self.Mloc * self.N * steps
+        self.stats["device_ms"] += ms
+
+    @property
+    def x(self):
+        return self._cur.fetch(want_x=True, want_w=False)[0]
+
+    @property
+    def w(self):
+        return self._cur.fetch(want_x=False, want_w=True)[1]
+
+    def close(self):
+        for b in (self._cur, self._prop):
+            if b is not None:
+                b.close()
+        self._cur = self._prop = None
+
+    def __repr__(self):
+        return f"ess     = {round(self.ess, 3)}\nmean(θ) = {expected_parameters(self).ravel()}"
+
+
+def expected_parameters(smc, reference_style=False):
+    """Σ ω_m θ_m as a d×1 matrix (smc_samplers.jl:61-65).  The reference passes the already
+    normalised ω through `reweight` (a softmax of ω itself), which is almost the
+    unweighted mean; reference_style=True reproduces that."""
+    ω = smc.ω
+    if reference_style:
+        e = np.exp(ω - ω.max())
+        ω = e / e.sum()
+    return (smc.θ * ω[:, None]).sum(axis=0)[:, None]
+
+
+def resample_(smc):
+    """resample!(smc) (smc_samplers.jl:74-84): multinomial ancestors on ω; θ, logZ and the state
+    clouds (x AND w: D3; deep copies: D4) follow their parents; ω becomes uniform (D5)."""
+    smc.ctx.set_rng(smc.seed, 0)
+    a = smc.ctx.resample(smc.ω, smc.theta_resampler, stream=0, t=smc._n_resample, purpose=_lib.P_THETA_RESAMPLE)
+    smc._n_resample += 1
+    smc.θ = smc.θ[a]
+    smc.logZ = smc.logZ[a]
+    smc.ω = np.full(smc.M, 1.0 / smc.M)
+    smc.stats["clouds_moved"] += redistribute(_BatchStore(smc._cur, smc.comm), a, smc.comm)
+    return a
+
+
+class _BatchStore:
+    """adapter: the clouds of a device batch as seen by redistribute()"""
+
+    def __init__(self, batch, comm):
+        self.batch, self.comm = batch, comm
+        self.nbytes = batch.cloud_bytes()
+
+    def pack(self, slots):
+        torch = self.comm.torch
+        buf = torch.empty(len(slots) * self.nbytes, dtype=torch.uint8, device=self.comm.device)
+        self.batch.pack(slots, buf.data_ptr())
+        return buf
+
+    def gather(self, local_parents):
+        self.batch.gather(local_parents)
+
+    def unpack(self, slots, buf):
+        self.batch.unpack(slots, buf.data_ptr())
+
+
+def redistribute(store, parents, comm):
+    """Move whole clouds so that global slot m holds a deep copy of the cloud of parents[m]:
+    rank-local parents by an on-device gather, remote parents by pack -> point-to-point -> unpack
+    (smc_samplers.jl:82 `smc.x = smc.x[a]`, across GPUs).  Returns the number of clouds received."""
+    if comm.world == 1:
+        store.gather(np.asarray(parents, np.int32))
+        return 0
+    local_parents, send, recv = exchange_plan(parents, comm.rank, comm.world)
+    sendbufs = {dst: store.pack(slots) for dst, slots in send.items()}   # read the pre-gather clouds
+    got = comm.exchange(sendbufs, {src: len(s) for src, s in recv.items()}, store.nbytes)
+    store.gather(local_parents)
+    moved = 0
+    for src, slots in recv.items():
+        store.unpack(slots, got[src])
+        moved += len(slots)
+    return moved
+
+
+def rejuvenate_(smc, y, ξ=1.0, verbose=False):
+    """rejuvenate!(smc, y, ξ, verbose) (smc_samplers.jl:103-148): `chain` PMMH moves per θ-particle;
+    each move is one full particle filter over y — all M of them in one batched launch."""
+    y = np.ascontiguousarray(y, np.float64)
+    M, d = smc.θ.shape
+    acc = np.zeros(M, bool)
+    Σ, univariate = smc.kernel(smc.θ)                                  # pmmh_kernel = smc.kernel(smc.θ)   :107
+    scales = 0.5 * np.arange(smc.chain, 0, -1)                         # 0.5*reverse(1:chain)              :108
+    if verbose:
+        sys.stdout.write("\t[rejuvenating]")
+    if smc._prop is None:
+        smc._prop = smc.ctx.batch(smc.kind, smc.Mloc, smc.N)
+    ordinal = smc._n_rejuv
+    smc._n_rejuv += 1
+    lp_cur = np.array([smc.prior.logpdf(th) for th in smc.θ])
+    for c in range(smc.chain):
+        z = np.stack([_lib.rng_normals(smc.seed, ordinal, k, c, _lib.P_MH_PROPOSAL, 0, M) for k in range(d)], axis=1)
+        θ_prop = _propose(smc.θ, Σ, univariate, scales[c], z)          # rand(pmmh_kernel(θ[m], scales[c]))  :114
+        ok = np.array([smc.prior.insupport(th) for th in θ_prop])      # insupport(prior, θ_prop)            :116
+        params = np.zeros((M, _lib.PARAM_STRIDE))
+        safe = np.where(ok[:, None], θ_prop, smc.θ)
+        params[:] = smc._params(safe)
+        smc._next_epoch()
+        z_loc = smc._prop.log_likelihood(smc._local(params), y, smc.resampler, stream0=smc.lo,
+                                         active=smc._local(ok).astype(np.uint8))     # log_likelihood(N, y, model(θ_prop)) :117-121
+        smc._account(smc._prop, y.size)
+        logZ_prop = smc.comm.all_gather(z_loc)
+        lp_prop = np.array([smc.prior.logpdf(th) if o else -math.inf for th, o in zip(θ_prop, ok)])
+        with np.errstate(invalid="ignore"):
+            acc_ratio = ξ * (logZ_prop - smc.logZ) + (lp_prop - lp_cur)                # :123-127
+            u = _lib.rng_uniforms01(smc.seed, ordinal, 0, c, _lib.P_MH_ACCEPT, M)
+            with np.errstate(divide="ignore"):
+                accept = ok & (logZ_prop + lp_prop > -math.inf) & (np.log(u) < acc_ratio)   # :129
+        smc.logZ = np.where(accept, logZ_prop, smc.logZ)                                # :130-133
+        smc.θ = np.where(accept[:, None], θ_prop, smc.θ)
+        lp_cur = np.where(accept, lp_prop, lp_cur)
+        smc._cur.accept(smc._prop, smc._local(accept).astype(np.uint8))
+        acc |= accept
+    smc.ω = np.full(M, 1.0 / M)                                         # ω[m] = 1.0 (then normalised)       :139
+    smc.acc_ratio = float(acc.sum()) / M                                # :142
+    if verbose:
+        sys.stdout.write("\tacc_rate: %1.5f" % smc.acc_ratio)
+    return smc
+
+
+def exchange_(smc, y, verbose=False):
+    """exchange!(smc, y, verbose) (smc_samplers.jl:163-189): if the acceptance ratio fell below
+    acc_threshold and N <= 4096, double N, re-filter every θ and reweight by exp(new_logZ - logZ)."""
+    if not (smc.acc_ratio < smc.acc_threshold):
+        return
+    if smc.N > 4096:
+        sys.stdout.write("\n\t[cannot exceed max state particles]")
+        return
+    smc.N *= 2
+    if verbose:
+        sys.stdout.write("\t%d particles added" % smc.N)
+    y = np.ascontiguousarray(y, np.float64)
+    old, oldp = smc._cur, smc._prop
+    smc._cur = smc.ctx.batch(smc.kind, smc.Mloc, smc.N)
+    smc._prop = None
+    old.close()
+    if oldp is not None:
+        oldp.close()
+    smc._next_epoch()
+    z_loc = smc._cur.log_likelihood(smc._local(smc._params(smc.θ)), y, smc.resampler, stream0=smc.lo)
+    smc._account(smc._cur, y.size)
+    new_logZ = smc.comm.all_gather(z_loc)
+    _, smc.ω, smc.ess = smc.ctx.normalize(new_logZ - smc.logZ)
+    smc.logZ = new_logZ
+
+
+def density_tempered(smc, y, verbose=True):
+    """density_tempered(smc, y) (smc_samplers.jl:222-281), Duan & Fulop's density-tempered SMC."""
+    y = np.ascontiguousarray(y, np.float64)
+    smc._next_epoch()
+    z_loc = smc._cur.log_likelihood(smc._local(smc._params(smc.θ)), y, smc.resampler, stream0=smc.lo)   # :223-229
+    smc._account(smc._cur, y.size)
+    smc.logZ = smc.comm.all_gather(z_loc)
+    _, smc.ω, smc.ess = smc.ctx.normalize(smc.logZ)                    # :232
+    ξ = 0.0
+    smc.schedule = []
+    while ξ < 1.0:
+        resample_flag = True
+        lower = oldξ = ξ
+        upper = 2.0
+        newξ = None
+        while upper - lower > 1.0e-6:                                   # bisection for ξ                    :240-258
+            newξ = (upper + lower) / 2.0
+            logω = (newξ - oldξ) * smc.logZ
+            _, smc.ω, smc.ess = smc.ctx.normalize(logω)
+            if smc.ess == smc.ess_min:
+                break
+            elif smc.ess < smc.ess_min:
+                upper = newξ
+            else:
+                lower = newξ
+        if newξ >= 1.0:                                                 # corner solution                    :261-266
+            resample_flag = False
+            newξ = 1.0
+            logω = (newξ - oldξ) * smc.logZ
+            _, smc.ω, smc.ess = smc.ctx.normalize(logω)
+        ξ = newξ
+        smc.schedule.append((ξ, smc.ess))
+        if verbose:
+            sys.stdout.write("ξ = %1.5f\tess = %4.3f" % (ξ, smc.ess))
+        if resample_flag:
+            resample_(smc)                                              # :272
+            rejuvenate_(smc, y, ξ, verbose)                             # :275
+        if verbose:
+            sys.stdout.write("\n")
+    return smc
+
+
+def smc2(smc, y):
+    """smc²(smc, y) (smc_samplers.jl:288-301): M bootstrap filters at the first observation."""
+    y = np.ascontiguousarray(y, np.float64)
+    smc._next_epoch()
+    lm_loc, _ = smc._cur.init(smc._local(smc._params(smc.θ)), y[0], stream0=smc.lo)
+    smc._account(smc._cur, 1)
+    logmu = smc.comm.all_gather(lm_loc)
+    smc.logZ = logmu.copy()                                             # smc.logZ = smc.ω                   :297
+    _, smc.ω, smc.ess = smc.ctx.normalize(logmu)                        # :298
+    return smc
+
+
+def smc2_step(smc, y, t, verbose=True):
+    """smc²!(smc, y, t) (smc_samplers.jl:308-340); t is the 0-based index of the new observation."""
+    y = np.ascontiguousarray(y, np.float64)
+    if verbose:
+        sys.stdout.write("t = %4d\tess = %4.3f" % (t, smc.ess))
+    smc.rejuvenated = False
+    if smc.ess < smc.ess_min:                                           # :312
+        resample_(smc)                                                  # :314
+        rejuvenate_(smc, y[:t], 1.0, verbose)                           # rejuvenate!(smc, y[1:t-1])         :317
+        exchange_(smc, y[:t], verbose)                                  # :320
+        smc.rejuvenated = True
+    with np.errstate(divide="ignore"):
+        logω = np.log(smc.ω)                                            # :324
+    lm_loc, _ = smc._cur.step(y[t], smc.resampler, params=smc._local(smc._params(smc.θ)))   # M × bootstrap_filter!  :325-331
+    smc._account(smc._cur, 1)
+    logmu = smc.comm.all_gather(lm_loc)
+    logω = logω + logmu                                                 # :333
+    smc.logZ = smc.logZ + logmu                                         # :334
+    _, smc.ω, smc.ess = smc.ctx.normalize(logω)                         # :338
+    if verbose:
+        sys.stdout.write("\n")
+    return smc

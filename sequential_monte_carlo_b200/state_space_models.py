@@ -1,0 +1,128 @@
+"""State-space models — host mirror of /root/reference/src/state_space_models.jl.
+
+A model is (kind, 8 parameters) handed to the device functors of csrc/smcb_models.cuh; nothing is
+evaluated on the host.  Both spellings of the reference are provided: the on-disk
+`UnivariateLinearGaussian(A=…, B=…, Q=…, R=…)`, `unobserved_components`, `UCSV`, and the README /
+example spelling `StateSpaceModel(LinearGaussian(A,B,Q,R,x0),(1,1))`, `UC(...)`.
+"""
+import numpy as np
+
+from . import _lib
+
+
+class _ModelMeta(type):
+    def __call__(cls, *args, **kwargs):
+        if cls is StateSpaceModel:  # README constructor: StateSpaceModel(spec, dims) -> spec
+            spec = args[0] if args else kwargs.get("spec")
+            dims = args[1] if len(args) > 1 else kwargs.get("dims")
+            if not isinstance(spec, StateSpaceModel):
+                raise TypeError("StateSpaceModel(spec, dims): spec must be a model such as LinearGaussian(...) or UCSV(...)")
+            if dims is not None and tuple(dims) != (spec.state_dim, 1):
+                raise ValueError(f"dims {tuple(dims)} do not match the model's ({spec.state_dim}, 1)")
+            return spec
+        return super().__call__(*args, **kwargs)
+
+
+class StateSpaceModel(metaclass=_ModelMeta):
+    """abstract type StateSpaceModel (state_space_models.jl:9).  `StateSpaceModel(spec, dims)` — the
+    README constructor (README.md:12-15) — returns `spec` itself after checking `dims`."""
+    kind = None
+    state_dim = 1
+
+    def params(self):
+        raise NotImplementedError
+
+    def params8(self):
+        return _lib.params8(self.params())
+
+
+class LinearModel(StateSpaceModel):
+    """struct LinearModel (state_space_models.jl:46-58), univariate methods (:74-109).
+    x[t] ~ N(A x[t-1], Q), y[t] ~ N(B x[t], R), x[1] ~ N(x0, σ0); Q, R, σ0 are variances."""
+    kind = _lib.LG1D
+
+    def __init__(self, A, B, Q, R, x0=0.0, σ0=1.0):
+        for name, v in (("A", A), ("B", B), ("Q", Q), ("R", R), ("x0", x0), ("σ0", σ0)):
+            if np.ndim(v) != 0:
+                raise NotImplementedError(f"{name}: multivariate linear models are outside the accelerated path (SURVEY §8f N4)")
+        self.A, self.B, self.Q, self.R, self.x0, self.σ0 = (float(v) for v in (A, B, Q, R, x0, σ0))
+
+    def params(self):
+        return [self.A, self.B, self.Q, self.R, self.x0, self.σ0]
+
+    def __repr__(self):
+        return f"LinearModel(A={self.A}, B={self.B}, Q={self.Q}, R={self.R}, x0={self.x0}, σ0={self.σ0})"
+
+
+def UnivariateLinearGaussian(*, A, B, Q, R, x0=0.0, σ0=1.0):
+    """state_space_models.jl:74-77"""
+    return LinearModel(A, B, Q, R, x0, σ0)
+
+
+def LinearGaussian(A, B, Q, R, x0=0.0, σ0=1.0):
+    """README spelling: LinearGaussian(θ[1], 1.0, θ[2], θ[3], 0.0)  (README.md:12-15)"""
+    return LinearModel(A, B, Q, R, x0, σ0)
+
+
+def unobserved_components(σε=None, ση=None, x0=0.0, **kw):
+    """local level model (state_space_models.jl:119-128): LG1D with A=B=1, Q=σε, R=ση, σ0=σε"""
+    σε = kw.get("sigma_eps", σε)
+    ση = kw.get("sigma_eta", ση)
+    return LinearModel(1.0, 1.0, σε, ση, x0, σε)
+
+
+UC = unobserved_components  # examples/inflation_example.jl:28-31
+
+
+class UCSV(StateSpaceModel):
+    """struct UCSV (state_space_models.jl:215-259): state (x, log σε, log ση).
+    `UCSV(γ, x0, (log_σε, log_ση))`; a scalar γ is used for both volatilities (example spelling,
+    examples/inflation_example.jl:229-232)."""
+    kind = _lib.UCSV
+    state_dim = 3
+
+    def __init__(self, γ, x0, log_σ0):
+        g = (float(γ), float(γ)) if np.ndim(γ) == 0 else (float(γ[0]), float(γ[1]))
+        self.γ, self.x0, self.log_σ0 = g, float(x0), (float(log_σ0[0]), float(log_σ0[1]))
+
+    def params(self):
+        return [self.γ[0], self.γ[1], self.x0, self.log_σ0[0], self.log_σ0[1]]
+
+    def __repr__(self):
+        return f"UCSV(γ={self.γ}, x0={self.x0}, log_σ0={self.log_σ0})"
+
+
+def unobserved_components_stochastic_volatility(*, x0, γε, γη, log_σε, log_ση):
+    """state_space_models.jl:225-227"""
+    return UCSV((γε, γη), x0, (log_σε, log_ση))
+
+
+class StochasticVolatility(StateSpaceModel):
+    """Canonical SV model (absent from the reference's src/; shown in
+    visuals/stochastic_volatility_animation_1000.gif with panels μ, ρ, σ):
+    x[1] ~ N(μ, σ²/(1-ρ²)), x[t] ~ N(μ + ρ (x[t-1]-μ), σ²), y[t] ~ N(0, exp(x[t]))."""
+    kind = _lib.SV
+
+    def __init__(self, μ, ρ, σ):
+        self.μ, self.ρ, self.σ = float(μ), float(ρ), float(σ)
+
+    def params(self):
+        return [self.μ, self.ρ, self.σ]
+
+    def __repr__(self):
+        return f"StochasticVolatility(μ={self.μ}, ρ={self.ρ}, σ={self.σ})"
+
+
+SV = StochasticVolatility
+
+
+def simulate(model, T, seed=1998):
+    """simulate([rng,] model, T) -> (x, y)  (state_space_models.jl:11-28).  The rng argument of the
+    reference becomes a Philox seed.  x has shape [T] (or [T, 3] for UCSV, one row per period)."""
+    x, y = _lib.simulate(model.kind, model.params(), int(T), int(seed))
+    return (x[0] if model.state_dim == 1 else np.ascontiguousarray(x.T)), y
+
+
+def preallocate(model, N):
+    """preallocate(model, N) (state_space_models.jl:80-85, 229-231)"""
+    return np.zeros(N) if model.state_dim == 1 else np.zeros((N, model.state_dim))

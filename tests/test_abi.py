@@ -1,0 +1,67 @@
+"""CPU tests of the drop-in boundary: libsmcb200.so builds, loads, exports every symbol that
+include/smcb200.h declares, fails loudly without a GPU, and its host-side helpers (Philox normals,
+simulate) are bit-identical to the oracle's."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import sequential_monte_carlo_b200 as smc
+from sequential_monte_carlo_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "smcb200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(smcb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _declared()
+    assert len(names) >= 35
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/smcb200.h but not exported"
+    assert set(names) == set(_lib.SIGNATURES), "ctypes signature table out of sync with the header"
+    assert lib.smcb_version() == 100
+    assert lib.smcb_state_dim(smc.KIND_UCSV) == 3 and lib.smcb_state_dim(smc.KIND_LG1D) == 1 and lib.smcb_state_dim(9) == -1
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(smc.SMCBError) as e:
+        smc.Context(0, 1)
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "sequential_monte_carlo_b200")
+    for d, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(d, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+                assert "liboracle" not in txt and '#include "../../oracle' not in txt, f
+
+
+def test_host_rng_matches_oracle(oracle):
+    for purpose, comp in ((4, 0), (6, 2), (8, 1)):
+        a = _lib.rng_normals(1998, 5, 7, 11, purpose, comp, 1001)
+        b = oracle.normals(1998, 5, 7, 11, purpose, comp, 1001)
+        np.testing.assert_array_equal(a, b)
+    np.testing.assert_array_equal(_lib.rng_uniforms64(3, 1, 2, 9, 7, 77), oracle.uniforms64(3, 1, 2, 9, 7, 77))
+    np.testing.assert_array_equal(_lib.rng_uniforms01(3, 1, 2, 9, 7, 77), oracle.uniforms01(3, 1, 2, 9, 7, 77))
+
+
+@pytest.mark.parametrize("kind,params", [(0, [0.5, 1.0, 0.9, 0.8, 0.0, 1.0]), (1, [-1.0, 0.9, 0.3]), (2, [0.2, 0.2, 3.0, 1.0, 1.0])])
+def test_simulate_matches_oracle(oracle, kind, params):
+    x, y = _lib.simulate(kind, params, 500, 1998)
+    xo, yo = oracle.simulate(kind, params, 500, 1998)
+    np.testing.assert_array_equal(x, xo)
+    np.testing.assert_array_equal(y, yo)
+    assert x.shape == (3 if kind == 2 else 1, 500)

@@ -10,20 +10,20 @@ RTOL = 1e-10
 
 
 def _thetas(kind, M, rng):
-    if kind == smc.LG1D:
+    if kind == smc.KIND_LG1D:
         return np.stack([rng.uniform(-0.9, 0.9, M), np.ones(M), rng.uniform(0.3, 2, M), rng.uniform(0.3, 2, M),
                          np.zeros(M), np.ones(M)], 1)
-    if kind == smc.SV:
+    if kind == smc.KIND_SV:
         return np.stack([rng.normal(-1, 0.5, M), rng.uniform(0.5, 0.98, M), rng.uniform(0.1, 0.6, M)], 1)
     return np.stack([rng.uniform(0.05, 0.5, M), rng.uniform(0.05, 0.5, M), rng.normal(3, 1, M), rng.uniform(0, 2, M),
                      rng.uniform(0, 2, M)], 1)
 
 
-TRUE = {smc.LG1D: [0.5, 1.0, 0.9, 0.8, 0.0, 1.0], smc.SV: [-1.0, 0.9, 0.3], smc.UCSV: [0.2, 0.2, 3.0, 1.0, 1.0]}
+TRUE = {smc.KIND_LG1D: [0.5, 1.0, 0.9, 0.8, 0.0, 1.0], smc.KIND_SV: [-1.0, 0.9, 0.3], smc.KIND_UCSV: [0.2, 0.2, 3.0, 1.0, 1.0]}
 
 
-@pytest.mark.parametrize("kind,N", [(smc.LG1D, 1024), (smc.LG1D, 1000), (smc.LG1D, 33), (smc.LG1D, 8192), (smc.SV, 2048),
-                                     (smc.UCSV, 4096), (smc.UCSV, 777), (smc.UCSV, 8192), (smc.SV, 1)])
+@pytest.mark.parametrize("kind,N", [(smc.KIND_LG1D, 1024), (smc.KIND_LG1D, 1000), (smc.KIND_LG1D, 33), (smc.KIND_LG1D, 8192), (smc.KIND_SV, 2048),
+                                     (smc.KIND_UCSV, 4096), (smc.KIND_UCSV, 777), (smc.KIND_UCSV, 8192), (smc.KIND_SV, 1)])
 def test_batch_log_likelihood_bit_exact(ctx, oracle, kind, N):
     M, T = 12, 30 if N <= 4096 else 8
     rng = np.random.default_rng(N)
@@ -51,7 +51,7 @@ def test_batch_log_likelihood_bit_exact(ctx, oracle, kind, N):
 
 def test_batch_matches_single_filter(ctx, oracle):
     """the same (seed, epoch, stream) gives the same cloud from the grid-wide and the CTA-resident kernels"""
-    kind, N, T, M = smc.LG1D, 4096, 25, 4
+    kind, N, T, M = smc.KIND_LG1D, 4096, 25, 4
     _, y = oracle.simulate(kind, TRUE[kind], T, 7)
     P = smc._lib.params8(_thetas(kind, M, np.random.default_rng(3)))
     b = ctx.batch(kind, M, N)
@@ -68,7 +68,7 @@ def test_batch_matches_single_filter(ctx, oracle):
     b.close()
 
 
-@pytest.mark.parametrize("kind", [smc.LG1D, smc.UCSV])
+@pytest.mark.parametrize("kind", [smc.KIND_LG1D, smc.KIND_UCSV])
 def test_batch_init_step_gather_accept(ctx, oracle, kind):
     """smc² / smc²! skeleton: init at y1, steps, θ-resample gather, accept from a proposal batch."""
     M, N, T = 10, 1024, 12
@@ -131,7 +131,7 @@ def test_batch_init_step_gather_accept(ctx, oracle, kind):
 
 def test_batch_pack_unpack_roundtrip(ctx, oracle):
     import torch
-    kind, M, N = smc.UCSV, 6, 500
+    kind, M, N = smc.KIND_UCSV, 6, 500
     _, y = oracle.simulate(kind, TRUE[kind], 5, 3)
     P = smc._lib.params8(_thetas(kind, M, np.random.default_rng(8)))
     a, b = ctx.batch(kind, M, N), ctx.batch(kind, M, N)
@@ -157,9 +157,9 @@ def test_batch_pack_unpack_roundtrip(ctx, oracle):
 
 def test_batch_errors(ctx):
     with pytest.raises(smc.SMCBError) as e:
-        ctx.batch(smc.LG1D, 4, 1 << 15)
+        ctx.batch(smc.KIND_LG1D, 4, 1 << 15)
     assert e.value.code == -5
-    b = ctx.batch(smc.LG1D, 4, 64)
+    b = ctx.batch(smc.KIND_LG1D, 4, 64)
     with pytest.raises(smc.SMCBError):
         b.step(0.0)
     with pytest.raises(smc.SMCBError):
@@ -170,8 +170,8 @@ def test_batch_errors(ctx):
 def test_kalman_batch(ctx, oracle):
     rng = np.random.default_rng(2)
     M, T = 37, 60
-    P = smc._lib.params8(_thetas(smc.LG1D, M, rng))
-    _, y = oracle.simulate(smc.LG1D, TRUE[smc.LG1D], T, 4)
+    P = smc._lib.params8(_thetas(smc.KIND_LG1D, M, rng))
+    _, y = oracle.simulate(smc.KIND_LG1D, TRUE[smc.KIND_LG1D], T, 4)
     act = np.ones(M, np.uint8)
     act[5] = 0
     for matched in (False, True):

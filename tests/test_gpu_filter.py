@@ -13,9 +13,9 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-10  # fp64 tolerance of the north star for logZ, weights, quantiles
 
 MODELS = {
-    smc.LG1D: [0.5, 1.0, 0.9, 0.8, 0.0, 1.0],       # lg_mod([0.5,0.9,0.8])  README.md:12-22
-    smc.SV: [-1.0, 0.9, 0.3],
-    smc.UCSV: [0.2, 0.2, 3.0, 1.0, 1.0],            # examples/inflation_example.jl:229-239 shape
+    smc.KIND_LG1D: [0.5, 1.0, 0.9, 0.8, 0.0, 1.0],       # lg_mod([0.5,0.9,0.8])  README.md:12-22
+    smc.KIND_SV: [-1.0, 0.9, 0.3],
+    smc.KIND_UCSV: [0.2, 0.2, 3.0, 1.0, 1.0],            # examples/inflation_example.jl:229-239 shape
 }
 
 
@@ -54,7 +54,7 @@ def _compare_run(ctx, oracle, kind, N, T, resampler, seed=7, epoch=3, stream=0):
 
 
 @pytest.mark.parametrize("resampler", [smc.MULTINOMIAL, smc.STRATIFIED, smc.SYSTEMATIC])
-@pytest.mark.parametrize("kind", [smc.LG1D, smc.SV, smc.UCSV])
+@pytest.mark.parametrize("kind", [smc.KIND_LG1D, smc.KIND_SV, smc.KIND_UCSV])
 def test_config1_bit_exact(ctx, oracle, kind, resampler):
     """BASELINE config 1 shape: N=1024, T=100."""
     _compare_run(ctx, oracle, kind, 1024, 100, resampler)
@@ -63,24 +63,24 @@ def test_config1_bit_exact(ctx, oracle, kind, resampler):
 @pytest.mark.parametrize("N", [1, 2, 3, 31, 1001, 2048, 2049, 5000, 70001])
 def test_ragged_sizes(ctx, oracle, N):
     for resampler in (smc.MULTINOMIAL, smc.SYSTEMATIC):
-        _compare_run(ctx, oracle, smc.LG1D, N, 12, resampler, seed=11, epoch=N % 97)
-    _compare_run(ctx, oracle, smc.UCSV, N, 6, smc.STRATIFIED, seed=5, epoch=1, stream=9)
+        _compare_run(ctx, oracle, smc.KIND_LG1D, N, 12, resampler, seed=11, epoch=N % 97)
+    _compare_run(ctx, oracle, smc.KIND_UCSV, N, 6, smc.STRATIFIED, seed=5, epoch=1, stream=9)
 
 
 def test_single_observation(ctx, oracle):
-    _compare_run(ctx, oracle, smc.LG1D, 777, 1, smc.SYSTEMATIC)
+    _compare_run(ctx, oracle, smc.KIND_LG1D, 777, 1, smc.SYSTEMATIC)
 
 
 def test_medium_n_many_tiles(ctx, oracle):
     """2^18 particles: 128 scan tiles, 256 propagate CTAs — exercises the look-back chain."""
-    _compare_run(ctx, oracle, smc.LG1D, 1 << 18, 8, smc.SYSTEMATIC)
-    _compare_run(ctx, oracle, smc.SV, 1 << 17, 5, smc.MULTINOMIAL)
+    _compare_run(ctx, oracle, smc.KIND_LG1D, 1 << 18, 8, smc.SYSTEMATIC)
+    _compare_run(ctx, oracle, smc.KIND_SV, 1 << 17, 5, smc.MULTINOMIAL)
 
 
 def test_degenerate_weights_window_fallback(ctx, oracle):
     """A sharp likelihood (tiny R) concentrates the weight on few particles, so some CTAs see CDF
     windows wider than the staging buffer and take the global-search path."""
-    kind, N, T = smc.LG1D, 1 << 16, 6
+    kind, N, T = smc.KIND_LG1D, 1 << 16, 6
     y = _data(oracle, kind, T)
     for resampler, R in ((smc.SYSTEMATIC, 1e-6), (smc.STRATIFIED, 1e-9), (smc.SYSTEMATIC, 1e-9)):
         params = [0.5, 1.0, 0.9, R, 0.0, 1.0]
@@ -99,7 +99,7 @@ def test_degenerate_weights_window_fallback(ctx, oracle):
 
 def test_stepping_api_matches_whole_series(ctx, oracle):
     """bootstrap_filter + bootstrap_filter! one observation at a time (README.md:33-61 usage)."""
-    kind, N, T = smc.LG1D, 4096, 20
+    kind, N, T = smc.KIND_LG1D, 4096, 20
     y = _data(oracle, kind, T)
     ctx.set_rng(21, 5)
     logZ, logmu, ess = ctx.log_likelihood(kind, MODELS[kind], N, y, smc.STRATIFIED, 2, per_step=True)
@@ -131,14 +131,14 @@ def test_step_before_init_is_an_error():
     with pytest.raises(smc.SMCBError):
         c.log_likelihood(7, [0.0], 10, [0.0])
     with pytest.raises(smc.SMCBError):
-        c.log_likelihood(smc.LG1D, MODELS[smc.LG1D], 0, [0.0])
+        c.log_likelihood(smc.KIND_LG1D, MODELS[smc.KIND_LG1D], 0, [0.0])
     c.close()
 
 
 def test_pf_vs_kalman(ctx, oracle):
     """log_likelihood(N,y,model) vs log_likelihood(y,model) (kalman_filter.jl:55-70) on LG1D.
     The PF's target is the matched-init Kalman likelihood."""
-    kind, T = smc.LG1D, 100
+    kind, T = smc.KIND_LG1D, 100
     y = _data(oracle, kind, T)
     _, _, kf_matched = oracle.kalman_loglik(MODELS[kind], y, matched_init=True)
     _, _, kf_ref = oracle.kalman_loglik(MODELS[kind], y, matched_init=False)

@@ -1,0 +1,159 @@
+"""CPU tests of the host-side θ-level logic: priors, proposal kernel, the cloud-exchange plan of a
+θ-resample and the torch.distributed plumbing (gloo, world_size 2) that the multi-GPU path uses."""
+import math
+import os
+import socket
+
+import numpy as np
+import pytest
+
+import sequential_monte_carlo_b200 as smc
+from sequential_monte_carlo_b200 import smc_samplers as ss
+
+
+def test_priors_match_oracle_restatement(oracle):
+    from oracle import samplers as S
+    pr = smc.product_distribution([smc.TruncatedNormal(0, 1, -1, 1), smc.LogNormal(), smc.Uniform(0, 2), smc.Normal(3, 2)])
+    po = S.OProduct([S.OTruncatedNormal(0, 1, -1, 1), S.OLogNormal(), S.OUniform(0, 2), S.ONormal(3, 2)])
+    a, b = pr.sample(300, 1998), po.sample(300, 1998)
+    np.testing.assert_array_equal(a, b)
+    assert np.all(np.abs(a[:, 0]) <= 1) and np.all(a[:, 1] > 0) and np.all((a[:, 2] >= 0) & (a[:, 2] <= 2))
+    for th in a[:20]:
+        assert pr.logpdf(th) == po.logpdf(th) and pr.insupport(th)
+    assert not pr.insupport([1.5, 1.0, 1.0, 0.0]) and pr.logpdf([0.0, -1.0, 1.0, 0.0]) == -math.inf
+    # densities integrate to one (trapezoid) — pins the closed forms
+    for d, lo, hi in ((smc.TruncatedNormal(0.3, 0.7, -1, 1), -1, 1), (smc.LogNormal(0.2, 0.5), 1e-9, 60), (smc.Normal(3, 2), -20, 26)):
+        g = np.linspace(lo, hi, 200001)
+        assert np.trapezoid(np.exp([d.logpdf(v) for v in g]), g) == pytest.approx(1.0, abs=1e-6)
+
+
+def test_random_walk_kernel(oracle):
+    from oracle import samplers as S
+    rng = np.random.default_rng(0)
+    th = rng.normal(size=(200, 3)) * [0.1, 1.0, 3.0]
+    Sg, uni = ss.random_walk_kernel(th)
+    So, unio = S.o_random_walk_kernel(th)
+    np.testing.assert_array_equal(Sg, So)
+    assert not uni and not unio
+    np.testing.assert_allclose(Sg, 2.83 ** 2 / 3 * np.cov(th.T) + 1e-10 * np.eye(3), rtol=1e-12)      # smc_samplers.jl:97-98
+    Sg, _ = ss.random_walk_kernel(np.ones((50, 2)))
+    np.testing.assert_array_equal(Sg, 1e-2 * np.eye(2))                                               # degenerate branch
+    S1, uni = ss.random_walk_kernel(th[:, :1])
+    assert uni and S1[0, 0] == pytest.approx(2.83 ** 2 * np.var(th[:, 0], ddof=1) + 1e-10)            # :87-92
+
+
+class _NumpyStore:
+    """clouds as rows of a numpy array; what _BatchStore does on the device"""
+
+    def __init__(self, rows, torch):
+        self.rows, self.torch, self.nbytes = rows.copy(), torch, rows.shape[1] * 8
+
+    def pack(self, slots):
+        return self.torch.from_numpy(self.rows[slots].copy().view(np.uint8).reshape(-1))
+
+    def gather(self, local_parents):
+        self.rows = self.rows[local_parents].copy()
+
+    def unpack(self, slots, buf):
+        self.rows[slots] = buf.numpy().view(np.float64).reshape(len(slots), -1)
+
+
+class _FakeComm:
+    """in-process stand-in that runs all ranks' plans against each other"""
+
+    def __init__(self, rank, world, mailbox):
+        self.rank, self.world, self.mailbox = rank, world, mailbox
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_exchange_plan_is_consistent(world):
+    rng = np.random.default_rng(world)
+    M = 8 * world
+    for _ in range(20):
+        parents = np.sort(rng.integers(0, M, M)) if rng.random() < 0.5 else rng.integers(0, M, M)
+        plans = [ss.exchange_plan(parents, r, world) for r in range(world)]
+        Mloc = M // world
+        for r, (lp, send, recv) in enumerate(plans):
+            assert lp.shape == (Mloc,) and lp.min() >= 0 and lp.max() < Mloc
+            for dst, slots in send.items():
+                assert dst != r and len(slots) == len(plans[dst][2][r])        # what r sends to dst, dst expects from r
+            for src, slots in recv.items():
+                assert src != r and len(slots) == len(plans[src][1][r])
+        # emulate: global cloud id = its value; after redistribution slot m must hold parents[m]
+        clouds = [np.arange(r * Mloc, (r + 1) * Mloc, dtype=np.float64) for r in range(world)]
+        packed = {(r, dst): clouds[r][slots].copy() for r, (lp, send, recv) in enumerate(plans) for dst, slots in send.items()}
+        new = []
+        for r, (lp, send, recv) in enumerate(plans):
+            c = clouds[r][lp].copy()
+            for src, slots in recv.items():
+                c[slots] = packed[(src, r)]
+            new.append(c)
+        np.testing.assert_array_equal(np.concatenate(new), parents.astype(np.float64))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, out):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        comm = ss.TorchComm()
+        assert comm.device.type == "cpu" and comm.rank == rank and comm.world == world
+        M, width = 12, 5
+        Mloc = M // world
+        g = comm.all_gather(np.arange(Mloc, dtype=np.float64) + 100 * rank)         # the replicated M-vectors
+        assert g.shape == (M,) and g[Mloc] == 100.0 * (1 if world > 1 else 0)
+        g2 = comm.all_gather(np.full((Mloc, 3), float(rank)))
+        assert g2.shape == (M, 3) and g2[-1, 0] == world - 1
+        rows = (np.arange(rank * Mloc, (rank + 1) * Mloc, dtype=np.float64)[:, None] * 10 + np.arange(width)[None, :])
+        store = _NumpyStore(rows, torch)
+        parents = np.array([11, 0, 0, 7, 7, 7, 1, 2, 6, 6, 5, 0])
+        moved = ss.redistribute(store, parents, comm)
+        want = parents[rank * Mloc:(rank + 1) * Mloc, None] * 10.0 + np.arange(width)[None, :]
+        np.testing.assert_array_equal(store.rows, want)
+        out.put((rank, int(moved)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_redistribution_over_gloo():
+    """world_size 2, gloo: all-gather of the M-vectors + point-to-point cloud moves after a θ-resample."""
+    import torch.multiprocessing as mp
+    ctxm = mp.get_context("spawn")
+    out = ctxm.Queue()
+    port = _free_port()
+    procs = [ctxm.Process(target=_gloo_worker, args=(r, 2, port, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    got = dict(out.get(timeout=5) for _ in range(2))
+    assert got[0] == 4 and got[1] == 4   # clouds whose parent lives on the other rank
+
+
+def test_model_constructors():
+    m = smc.StateSpaceModel(smc.LinearGaussian(0.5, 1.0, 0.9, 0.8, 0.0), (1, 1))       # README.md:12-15
+    assert m.params() == [0.5, 1.0, 0.9, 0.8, 0.0, 1.0] and m.kind == smc.KIND_LG1D
+    u = smc.UnivariateLinearGaussian(A=0.5, B=1.0, Q=0.9, R=0.8)                        # state_space_models.jl:74-77
+    assert u.params() == m.params()
+    uc = smc.unobserved_components(0.3, 0.7, 2.0)                                       # :119-128
+    assert uc.params() == [1.0, 1.0, 0.3, 0.7, 2.0, 0.3]
+    v = smc.StateSpaceModel(smc.UCSV(0.2, 3.0, (1.0, 0.5)), (3, 1))                     # examples/inflation_example.jl:229-232
+    assert v.params() == [0.2, 0.2, 3.0, 1.0, 0.5] and v.state_dim == 3
+    w = smc.unobserved_components_stochastic_volatility(x0=3.0, γε=0.1, γη=0.2, log_σε=1.0, log_ση=0.5)
+    assert w.params() == [0.1, 0.2, 3.0, 1.0, 0.5]
+    with pytest.raises(ValueError):
+        smc.StateSpaceModel(smc.UCSV(0.2, 3.0, (1.0, 0.5)), (1, 1))
+    with pytest.raises(NotImplementedError):
+        smc.LinearGaussian(np.eye(2), np.ones((1, 2)), np.eye(2), 1.0)
+    x, y = smc.simulate(v, 50, seed=3)
+    assert x.shape == (50, 3) and y.shape == (50,)

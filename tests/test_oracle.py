@@ -1,0 +1,182 @@
+"""CPU tests of the oracle itself (no GPU): what pins it, given that the reference ships no tests
+or golden vectors (SURVEY.md §4, §8c — parity unpinned): Philox known answers, libm agreement of
+the deterministic math, closed-form normalize cases, an independent numpy restatement of the
+resampler, the Kalman likelihood on LG models, and the committed regression vectors."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+LG = [0.5, 1.0, 0.9, 0.8, 0.0, 1.0]
+
+
+def ulp_diff(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b) / np.spacing(np.maximum(np.abs(b), np.finfo(float).tiny))
+
+
+def test_philox_known_answers(oracle):
+    for v in json.load(open(os.path.join(GOLD, "philox_kat.json"))):
+        out = oracle.philox(v["ctr"], v["key"])
+        assert ["%08x" % int(w) for w in out] == v["out"]
+
+
+def test_detmath_vs_libm(oracle):
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-700, 700, 20000), rng.uniform(-2, 2, 20000), [0.0, -0.0, 1.0, -1.0]])
+    assert ulp_diff(oracle.det_exp(x), np.exp(x)).max() <= 2
+    assert oracle.det_exp(np.array([-701.0, -np.inf]))[0] == 0.0 and oracle.det_exp(np.array([-np.inf]))[0] == 0.0
+    assert np.isinf(oracle.det_exp(np.array([701.0]))[0])
+    u = np.concatenate([rng.random(20000), 2.0 ** -rng.uniform(1, 53, 20000), [2.0 ** -53, 1 - 2.0 ** -53, 0.5, 1.0]])
+    assert ulp_diff(oracle.det_log(u), np.log(u)).max() <= 2
+    v = rng.random(40000)
+    s, c = oracle.det_sincos2pi(v)
+    # absolute error: near the zeros of sin/cos the reduced argument is exact, the result tiny
+    # (np.sin(2*pi*v) itself carries up to 2*pi*v*2^-53 = 7e-16 of argument-rounding error)
+    assert np.abs(s - np.sin(2 * np.pi * v)).max() < 1.2e-15 and np.abs(c - np.cos(2 * np.pi * v)).max() < 1.2e-15
+    assert np.abs(s * s + c * c - 1).max() < 5e-16
+    s, c = oracle.det_sincos2pi(np.array([0.0, 0.25, 0.5, 0.75]))
+    np.testing.assert_array_equal(s, [0.0, 1.0, -0.0, -1.0])
+    np.testing.assert_array_equal(c, [1.0, 0.0, -1.0, -0.0])
+
+
+def test_detmath_golden_bits(oracle):
+    g = json.load(open(os.path.join(GOLD, "detmath_vectors.json")))
+    for name, fn in (("exp", oracle.det_exp), ("log", oracle.det_log)):
+        xs = np.array([float.fromhex(k) for k in g[name]])
+        assert [float(v).hex() for v in fn(xs)] == list(g[name].values())
+    us = np.array([float.fromhex(k) for k in g["sin2pi"]])
+    s, c = oracle.det_sincos2pi(us)
+    assert [float(v).hex() for v in s] == list(g["sin2pi"].values())
+    assert [float(v).hex() for v in c] == list(g["cos2pi"].values())
+    assert [float(v).hex() for v in oracle.normals(1998, 1, 2, 3, 2, 0, 8)] == g["normals_head"]
+    assert [int(v) for v in oracle.uniforms64(1998, 1, 2, 3, 3, 8)] == g["uniforms_head"]
+
+
+def test_normals_are_standard_normal(oracle):
+    z = oracle.normals(5, 0, 0, 0, 2, 0, 400000)
+    assert abs(z.mean()) < 4 / math.sqrt(z.size)
+    assert abs(z.var() - 1) < 0.01
+    assert abs(np.mean(z ** 3)) < 0.02 and abs(np.mean(z ** 4) - 3) < 0.06
+    assert abs(np.corrcoef(z[0::2], z[1::2])[0, 1]) < 0.01     # the two Box-Muller outputs
+    u = oracle.uniforms01(5, 0, 0, 0, 3, 200000)
+    assert 0 <= u.min() and u.max() < 1 and abs(u.mean() - 0.5) < 0.005
+
+
+def test_quantiser(oracle):
+    S = oracle.quant_shift(1024)
+    assert S == 51 and oracle.quant_shift(1025) == 50 and oracle.quant_shift(1) == 61
+    q = oracle.det_quant(np.array([0.0, -math.log(2), -800.0, -np.inf, np.nan]), S)
+    assert q[0] == 2 ** S and abs(int(q[1]) - 2 ** (S - 1)) <= 4 and q[2] == 0 and q[3] == 0 and q[4] == 0
+    x = -np.random.default_rng(1).uniform(0, 60, 1000)
+    q = oracle.det_quant(x, S).astype(np.float64)
+    np.testing.assert_allclose(q, np.floor(np.exp(x) * 2.0 ** S), rtol=1e-12, atol=1)
+
+
+def test_normalize_closed_forms(oracle):
+    lm, w, ess = oracle.normalize(np.full(100, -7.5))
+    assert lm == pytest.approx(-7.5, abs=1e-14) and ess == pytest.approx(100.0) and np.allclose(w, 0.01)
+    lw = np.full(50, -np.inf)
+    lw[3] = 1.25
+    lm, w, ess = oracle.normalize(lw)
+    assert ess == 1.0 and w[3] == 1.0 and lm == pytest.approx(1.25 - math.log(50))
+    rng = np.random.default_rng(2)
+    lw = rng.normal(size=5000) * 4
+    a, b = oracle.normalize(lw), oracle.normalize_numpy(lw)   # C (det exp) vs numpy (libm) restatement
+    assert a[0] == pytest.approx(b[0], rel=1e-13) and a[2] == pytest.approx(b[2], rel=1e-12)
+    np.testing.assert_allclose(a[1], b[1], rtol=1e-13)
+    assert np.isnan(oracle.normalize(np.full(4, -np.inf))[0])     # reference behaviour (no guard), particles.jl:5-15
+
+
+@pytest.mark.parametrize("resampler", [0, 1, 2])
+def test_ancestors_c_vs_numpy(oracle, resampler):
+    rng = np.random.default_rng(3)
+    for n in (1, 2, 7, 500, 1024):
+        lw = rng.normal(size=n) * 3
+        a = oracle.ancestors(lw, resampler, 11, 2, 5, 9)
+        b = oracle.ancestors_numpy(lw, resampler, 11, 2, 5, 9)
+        np.testing.assert_array_equal(a, b)
+        assert a.min() >= 0 and a.max() < n
+        if resampler != 0:
+            assert np.all(np.diff(a) >= 0)                      # stratified / systematic are sorted
+    lw = np.full(64, -np.inf)
+    np.testing.assert_array_equal(oracle.ancestors(lw, resampler, 1, 0, 0, 1), np.arange(64))   # Q = 0
+    lw = np.full(64, -np.inf)
+    lw[40] = 0.0
+    assert np.all(oracle.ancestors(lw, resampler, 1, 0, 0, 1) == 40)
+
+
+def test_resampler_is_unbiased(oracle):
+    rng = np.random.default_rng(4)
+    n = 256
+    lw = rng.normal(size=n) * 1.5
+    w = np.exp(lw - lw.max())
+    w /= w.sum()
+    for resampler in (0, 1, 2):
+        counts = np.zeros(n)
+        reps = 400
+        for r in range(reps):
+            counts += np.bincount(oracle.ancestors(lw, resampler, 99, r, 0, 1), minlength=n)
+        z = (counts - reps * n * w) / np.sqrt(reps * n * w * (1 - w) + 1e-12)
+        assert np.abs(z).max() < 5.5 and abs(z.mean()) < 0.5
+        if resampler:  # low-variance schemes: every count within 1 of n w per draw
+            assert np.all(np.abs(counts / reps - n * w) < 1.0)
+
+
+def test_kalman_matches_closed_form(oracle):
+    # one step by hand: kalman_filter.jl:29-53
+    A, B, Q, R, x0, s0 = 0.5, 1.0, 0.9, 0.8, 0.0, 1.0
+    y = 0.7
+    xp, Sp = A * x0, A * A * s0 + Q
+    sig = B * B * Sp + R
+    x1 = xp + Sp * B / sig * (y - B * xp)
+    S1 = Sp - (Sp * B) ** 2 / sig
+    ll = -0.5 * (math.log(2 * math.pi) + math.log(sig) + (y - B * xp) ** 2 / sig)
+    x, S, l = oracle.kalman_step(LG, x0, s0, y)
+    assert x == pytest.approx(x1, rel=1e-14) and S == pytest.approx(S1, rel=1e-14) and l == pytest.approx(ll, rel=1e-14)
+
+
+def test_particle_filter_targets_kalman_likelihood(oracle):
+    """E[Ẑ] = Z: log-mean-exp of PF estimates vs the matched-init Kalman likelihood."""
+    _, y = oracle.simulate(0, LG, 60, 1998)
+    _, _, kf = oracle.kalman_loglik(LG, y, matched_init=True)
+    _, _, kf_ref = oracle.kalman_loglik(LG, y, matched_init=False)
+    for resampler in (0, 2):
+        vals = np.array([oracle.log_likelihood(0, LG, 2048, y, resampler, 500 + r)["logZ"] for r in range(30)])
+        lme = np.log(np.mean(np.exp(vals - vals.max()))) + vals.max()
+        assert abs(lme - kf) < 4 * vals.std(ddof=1) / math.sqrt(30) + 0.02
+    assert 0 < abs(kf - kf_ref) < 0.3
+
+
+def test_oracle_regression_vectors(oracle):
+    for v in json.load(open(os.path.join(GOLD, "oracle_vectors.json"))):
+        _, y = oracle.simulate(v["kind"], v["params"], v["T"], v["data_seed"])
+        assert [float(a).hex() for a in y[:4]] == v["y_hex"]
+        r = oracle.log_likelihood(v["kind"], v["params"], v["N"], y, v["resampler"], v["seed"], v["epoch"], v["stream"],
+                                  want_anc=True)
+        assert float(r["logZ"]).hex() == v["logZ_hex"]
+        assert [float(a).hex() for a in r["x"][:, -1]] == v["x_last_hex"]
+        assert float(np.sum(r["x"])).hex() == v["x_sum_hex"]
+        assert [int(a) for a in r["anc"][1][:16]] == v["anc_t1_head"]
+        assert int(np.sum(r["anc"][1:] * (np.arange(v["N"]) + 1)) % (2 ** 61 - 1)) == v["anc_checksum"]
+
+
+def test_batch_oracle_equals_loop(oracle):
+    rng = np.random.default_rng(6)
+    M, N, T = 5, 100, 12
+    P = np.zeros((M, 8))
+    P[:, :6] = np.stack([rng.uniform(-0.9, 0.9, M), np.ones(M), rng.uniform(0.3, 2, M), rng.uniform(0.3, 2, M), np.zeros(M),
+                         np.ones(M)], 1)
+    _, y = oracle.simulate(0, LG, T, 3)
+    act = np.array([1, 1, 0, 1, 1], np.uint8)
+    z, x, lw = oracle.batch_log_likelihood(0, P, act, N, y, 0, 8, 4, 20)
+    for m in range(M):
+        if not act[m]:
+            assert np.isneginf(z[m])
+            continue
+        r = oracle.log_likelihood(0, P[m], N, y, 0, 8, 4, 20 + m)
+        assert r["logZ"] == z[m]
+        np.testing.assert_array_equal(r["x"], x[m])

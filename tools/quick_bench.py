@@ -16,12 +16,12 @@ for logn in ([20, 22, 24] if len(sys.argv) < 2 else [int(a) for a in sys.argv[1:
             TT = 12
         else:
             TT = T
-        ctx.log_likelihood(smc.LG1D, LG, N, y[:5], rs)  # warm-up
+        ctx.log_likelihood(smc.KIND_LG1D, LG, N, y[:5], rs)  # warm-up
         ctx.set_profiling(False)
-        z = ctx.log_likelihood(smc.LG1D, LG, N, y[:TT], rs)
+        z = ctx.log_likelihood(smc.KIND_LG1D, LG, N, y[:TT], rs)
         ms, n = ctx.timing()
         ctx.set_profiling(True)
-        ctx.log_likelihood(smc.LG1D, LG, N, y[:TT], rs)
+        ctx.log_likelihood(smc.KIND_LG1D, LG, N, y[:TT], rs)
         msp, npf = ctx.timing()
         ctx.set_profiling(False)
         pups = N * TT / (ms["total"] * 1e-3)
@@ -30,8 +30,8 @@ for logn in ([20, 22, 24] if len(sys.argv) < 2 else [int(a) for a in sys.argv[1:
         print(json.dumps(rec), flush=True)
         out.append(rec)
 # batched: config 3 shape (512 x 1024, T=100), config 4 (1024 x 2048 SV, T=500), config 5 per-GPU (512 x 4096 UCSV, T=241)
-for kind, M, N, T, P in ((smc.LG1D, 512, 1024, 100, LG), (smc.SV, 1024, 2048, 500, [-1.0, 0.9, 0.3]),
-                         (smc.UCSV, 512, 4096, 241, [0.2, 0.2, 3.0, 1.0, 1.0]), (smc.LG1D, 4096, 1024, 100, LG)):
+for kind, M, N, T, P in ((smc.KIND_LG1D, 512, 1024, 100, LG), (smc.KIND_SV, 1024, 2048, 500, [-1.0, 0.9, 0.3]),
+                         (smc.KIND_UCSV, 512, 4096, 241, [0.2, 0.2, 3.0, 1.0, 1.0]), (smc.KIND_LG1D, 4096, 1024, 100, LG)):
     b = ctx.batch(kind, M, N)
     Pm = np.tile(smc._lib.params8(P), (M, 1))
     y = rng.normal(size=T)
