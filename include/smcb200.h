@@ -67,9 +67,9 @@ int smcb_record_ancestors(smcb_ctx* ctx, int enable);
 /* per-kernel CUDA-event timing of the single filter (bench.py roofline); off by default */
 int smcb_set_profiling(smcb_ctx* ctx, int enable);
 /* device time of the last sweep / step, and per-kernel-class totals when profiling is on:
- * ms[0] whole call, ms[1] scan (quantise + look-back prefix sum + Σe, Σe²), ms[2] search+gather+
- * propagate+weight, ms[3] init, ms[4] stats-only; launches[0..4] the matching launch counts. */
-int smcb_get_timing(const smcb_ctx* ctx, double ms[5], int64_t launches[5]);
+ * ms[0] whole call, ms[1] sum/scan (quantise + prefix sums + Σe, Σe²), ms[2] search+gather+propagate+
+ * weight, ms[3] init, ms[4] stats-only, ms[5] bounds; launches[0..5] the matching launch counts. */
+int smcb_get_timing(const smcb_ctx* ctx, double ms[6], int64_t launches[6]);
 int smcb_synchronize(smcb_ctx* ctx);
 
 /* ------------------------------------------------------------------ utilities */

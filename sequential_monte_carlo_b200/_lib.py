@@ -192,10 +192,10 @@ class Context:
         self._check(self._lib.smcb_set_profiling(self._h, int(bool(on))))
 
     def timing(self):
-        ms = (C.c_double * 5)()
-        n = (C.c_int64 * 5)()
+        ms = (C.c_double * 6)()
+        n = (C.c_int64 * 6)()
         self._check(self._lib.smcb_get_timing(self._h, ms, n))
-        keys = ("total", "scan", "prop", "init", "stats")
+        keys = ("total", "scan", "prop", "init", "stats", "bounds")
         return {k: float(ms[i]) for i, k in enumerate(keys)}, {k: int(n[i]) for i, k in enumerate(keys)}
 
     def synchronize(self):

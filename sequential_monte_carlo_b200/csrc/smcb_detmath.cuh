@@ -115,22 +115,37 @@ SMCB_HD uint32_t purpose_word(uint32_t kind, uint32_t comp, uint32_t epoch) {
 #define SMCB_HALF_LOG_2PI 0x1.d67f1c864beb5p-1
 #define SMCB_SQRT2 0x1.6a09e667f3bcdp+0
 
+// Polynomial coefficients, highest degree first.  On the device they live in constant memory so
+// that DFMA takes them as c[bank][offset] operands; as literals ptxas re-materialises every one
+// with two UMOVs per use (11-19 % of all issued instructions in the first ncu captures).
+#if defined(__CUDA_ARCH__)
+#define SMCB_COEF_DECL static __constant__ double
+#else
+#define SMCB_COEF_DECL static const double
+#endif
+SMCB_COEF_DECL kExpC[10] = {0x1.af38a9b0ec855p-26, 0x1.289185613a3d6p-22, 0x1.71de0dae63bb3p-19, 0x1.a019b90d2ae7ap-16,
+                            0x1.a01a01a7c41d5p-13, 0x1.6c16c1788bd90p-10, 0x1.11111111109b3p-7,  0x1.5555555553d63p-5,
+                            0x1.5555555555556p-3,  0x1.0000000000001p-1};
+SMCB_COEF_DECL kLogC[7] = {0x1.2b5900de53b32p-3, 0x1.39fe51a7c18f9p-3, 0x1.7462b51cb66b1p-3, 0x1.c71c62e3f11e6p-3,
+                           0x1.2492492df281ap-2, 0x1.99999999952d7p-2, 0x1.5555555555558p-1};
+SMCB_COEF_DECL kSinC[7] = {0x1.e3f362f896ffep-25, -0x1.e300715607854p-19, 0x1.50782fd9b7104p-13, -0x1.32d2cce2e55bfp-8,
+                           0x1.466bc677587f3p-4,  -0x1.4abbce625be41p-1,  0x1.921fb54442d18p+0};
+SMCB_COEF_DECL kCosC[8] = {-0x1.b2649ccb4360dp-28, 0x1.f9cc40b4d973bp-22, -0x1.a6d1ec788deb9p-16, 0x1.e1f50683554a4p-11,
+                           -0x1.55d3c7e3c90f2p-6,  0x1.03c1f081b5aacp-2,  -0x1.3bd3cc9be45dep+0,  0x1.0000000000000p+0};
+SMCB_COEF_DECL kMathC[6] = {SMCB_MAGIC, SMCB_LN2_HI, SMCB_LN2_LO, SMCB_LOG2E, SMCB_HALF_LOG_2PI, SMCB_SQRT2};
+
 // exp(x) = p * 2^k, p in about [0.707, 1.415]
 SMCB_HD void det_exp_parts(double x, double& p, int& k) {
-  double kf = (x * SMCB_LOG2E + SMCB_MAGIC) - SMCB_MAGIC;
-  k = (int)kf;
-  double r = fma(-kf, SMCB_LN2_HI, x);
-  r = fma(-kf, SMCB_LN2_LO, r);
-  double e = 0x1.af38a9b0ec855p-26;
-  e = fma(e, r, 0x1.289185613a3d6p-22);
-  e = fma(e, r, 0x1.71de0dae63bb3p-19);
-  e = fma(e, r, 0x1.a019b90d2ae7ap-16);
-  e = fma(e, r, 0x1.a01a01a7c41d5p-13);
-  e = fma(e, r, 0x1.6c16c1788bd90p-10);
-  e = fma(e, r, 0x1.11111111109b3p-7);
-  e = fma(e, r, 0x1.5555555553d63p-5);
-  e = fma(e, r, 0x1.5555555555556p-3);
-  e = fma(e, r, 0x1.0000000000001p-1);
+  // t = x*log2(e) + 1.5*2^52 holds round(x*log2 e) in its low mantissa bits: k comes from the bit
+  // pattern (no F2I), kf = t - MAGIC is the same integer as a double (SPEC §3: k = int(kf)).
+  const double t = x * kMathC[3] + kMathC[0];
+  const double kf = t - kMathC[0];
+  k = (int)(uint32_t)double_as_u64(t);
+  double r = fma(-kf, kMathC[1], x);
+  r = fma(-kf, kMathC[2], r);
+  double e = kExpC[0];
+#pragma unroll
+  for (int i = 1; i < 10; ++i) e = fma(e, r, kExpC[i]);
   p = 1.0 + fma(r * r, e, r);
 }
 
@@ -171,48 +186,36 @@ SMCB_HD double det_log(double u) {
   uint64_t b = double_as_u64(u);
   int e = (int)((b >> 52) & 0x7FF) - 1023;
   double m = u64_as_double((b & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull);
-  if (m > SMCB_SQRT2) {
+  if (m > kMathC[5]) {
     m *= 0.5;
     e += 1;
   }
   double f = m - 1.0;
   double s = f / (2.0 + f);
   double z = s * s;
-  double r = 0x1.2b5900de53b32p-3;
-  r = fma(r, z, 0x1.39fe51a7c18f9p-3);
-  r = fma(r, z, 0x1.7462b51cb66b1p-3);
-  r = fma(r, z, 0x1.c71c62e3f11e6p-3);
-  r = fma(r, z, 0x1.2492492df281ap-2);
-  r = fma(r, z, 0x1.99999999952d7p-2);
-  r = fma(r, z, 0x1.5555555555558p-1);
+  double r = kLogC[0];
+#pragma unroll
+  for (int i = 1; i < 7; ++i) r = fma(r, z, kLogC[i]);
   double lm = fma(s * z, r, s + s);
   double ef = (double)e;
-  return fma(ef, SMCB_LN2_HI, fma(ef, SMCB_LN2_LO, lm));
+  return fma(ef, kMathC[1], fma(ef, kMathC[2], lm));
 }
 
 // sin(2 pi u), cos(2 pi u), u in [0,1)
 SMCB_HD void det_sincos2pi(double u, double& sn, double& cs) {
   double a = 4.0 * u;
-  double nf = (a + SMCB_MAGIC) - SMCB_MAGIC;
+  const double tn = a + kMathC[0];
+  double nf = tn - kMathC[0];
   double r = a - nf;
-  int n = (int)nf & 3;
+  int n = (int)(uint32_t)double_as_u64(tn) & 3;   // low mantissa bits of a + 1.5*2^52 = round(a)
   double z = r * r;
-  double s = 0x1.e3f362f896ffep-25;
-  s = fma(s, z, -0x1.e300715607854p-19);
-  s = fma(s, z, 0x1.50782fd9b7104p-13);
-  s = fma(s, z, -0x1.32d2cce2e55bfp-8);
-  s = fma(s, z, 0x1.466bc677587f3p-4);
-  s = fma(s, z, -0x1.4abbce625be41p-1);
-  s = fma(s, z, 0x1.921fb54442d18p+0);
+  double s = kSinC[0];
+#pragma unroll
+  for (int i = 1; i < 7; ++i) s = fma(s, z, kSinC[i]);
   double sr = r * s;
-  double c = -0x1.b2649ccb4360dp-28;
-  c = fma(c, z, 0x1.f9cc40b4d973bp-22);
-  c = fma(c, z, -0x1.a6d1ec788deb9p-16);
-  c = fma(c, z, 0x1.e1f50683554a4p-11);
-  c = fma(c, z, -0x1.55d3c7e3c90f2p-6);
-  c = fma(c, z, 0x1.03c1f081b5aacp-2);
-  c = fma(c, z, -0x1.3bd3cc9be45dep+0);
-  c = fma(c, z, 0x1.0000000000000p+0);
+  double c = kCosC[0];
+#pragma unroll
+  for (int i = 1; i < 8; ++i) c = fma(c, z, kCosC[i]);
   double s1 = (n & 1) ? c : sr;
   double c1 = (n & 1) ? sr : c;
   // n=0:(sr,cr) 1:(cr,-sr) 2:(-sr,-cr) 3:(-cr,sr)

@@ -61,6 +61,7 @@ __global__ void reset_ctrl_kernel(FilterCtrl* ctrl) {
   ctrl->maxslot[0] = encode_ordered(-INFINITY);
   ctrl->maxslot[1] = encode_ordered(-INFINITY);
   ctrl->total = 0;
+  ctrl->sys_off = 0;
   ctrl->scan_ticket = 0;
   ctrl->scan_done = 0;
 }
@@ -412,6 +413,421 @@ __global__ void __launch_bounds__(kPropThreads)
   if (tid == 0) atomicMax(&ctrl->maxslot[t & 1u], encode_ordered(bm));
 }
 
+// ================================================================================================
+// Sorted resamplers (stratified / systematic): the two-launch step  sum -> prop2.
+//
+// The CDF never exists in HBM.  sum_kernel quantises the weights (q, one u64 per particle), keeps
+// per-chunk prefix sums (one u64 per 128 particles) and, in its last CTA, scans the <= 8192 tile
+// totals; prop2_kernel locates the chunks its first/last threshold fall in (32-ary warp search of
+// the L2-resident tile index), rebuilds those chunks of the CDF in shared memory from q (exact
+// integer arithmetic, so the ancestors equal those of a materialised CDF), searches, gathers,
+// propagates and weights.  HBM traffic per particle-update (LG1D fp64): logw 8 R + q 8 W | q 8 R +
+// x 8 R + x' 8 W + logw' 8 W = 48 B, against 56 B with a materialised CDF and ancestor vector.
+// Both kernels are bound by instruction issue (FP64 transcendentals), not by HBM: see DESIGN.md.
+constexpr int kChunk = 128;                              // particles per index entry (one warp x 4)
+constexpr int kSumThreads = 512;
+constexpr int kSubTile = kSumThreads * 8;                // 4096 particles per CTA trip (2 chunks per warp)
+constexpr int kChunksPerSub = kSubTile / kChunk;         // 32
+constexpr int kMaxTiles = 8192;                          // tile totals scanned by the last CTA of sum_kernel
+constexpr int kP2Threads = 256;
+constexpr int kP2Pairs = 2;
+constexpr int kP2Particles = kP2Threads * kP2Pairs * 2;  // 1024 particles per CTA
+constexpr int kSegChunks = 32;                           // chunks of CDF rebuilt per pass (4096 entries, 32 KB)
+
+struct StepIndex {
+  unsigned long long* chunk_excl;  // [nchunks] exclusive prefix of the chunk inside its tile
+  unsigned long long* tile_tot;    // [ntiles]
+  unsigned long long* tile_excl;   // [ntiles] global exclusive prefix of the tile
+  unsigned long long* tile_incl;   // [ntiles]
+  int ntiles;
+  int chunks_per_tile;
+  int64_t tile_items;
+};
+
+__global__ void __launch_bounds__(kSumThreads)
+    sum_kernel(const double* __restrict__ logw, unsigned long long* __restrict__ qout, int64_t N, int S, FilterCtrl* ctrl,
+               StepIndex ix, double* psum, double* psum2, StepStats* stats_out, int slot, int resampler, uint64_t Rw,
+               RngKey key, uint32_t stream, uint32_t t) {
+  constexpr int NW = kSumThreads / 32;
+  __shared__ unsigned long long s_wq[kChunksPerSub];
+  __shared__ double s_we[NW], s_we2[NW];
+  __shared__ unsigned long long s_scan[NW];
+  __shared__ bool s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned tile = blockIdx.x;
+  const double mx = decode_ordered(ctrl->maxslot[slot]);
+  const int nsub = ix.chunks_per_tile / kChunksPerSub;
+  unsigned long long running = 0;  // meaningful in warp 0
+  double se = 0.0, se2 = 0.0;
+  for (int sub = 0; sub < nsub; ++sub) {
+    const int64_t sub0 = (int64_t)tile * ix.tile_items + (int64_t)sub * kSubTile;
+    unsigned long long tq[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {  // chunk (warp + 16 h) of this trip
+      const int64_t base = sub0 + (int64_t)(warp + NW * h) * kChunk + lane * 4;
+      double lw[4];
+      unsigned long long q[4] = {0, 0, 0, 0};
+      if (base + 4 <= N) {
+        const double2 a = __ldg(reinterpret_cast<const double2*>(logw + base));
+        const double2 b = __ldg(reinterpret_cast<const double2*>(logw + base + 2));
+        lw[0] = a.x; lw[1] = a.y; lw[2] = b.x; lw[3] = b.y;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) lw[k] = (base + k < N) ? logw[base + k] : -INFINITY;
+      }
+      tq[h] = 0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (base + k < N) {
+          double e;
+          uint64_t qq;
+          det_exp_quant(lw[k] - mx, S, e, qq);
+          se += e;
+          se2 += e * e;
+          q[k] = qq;
+          tq[h] += qq;
+        }
+      }
+      if (base + 4 <= N) {
+        *reinterpret_cast<ulonglong2*>(qout + base) = make_ulonglong2(q[0], q[1]);
+        *reinterpret_cast<ulonglong2*>(qout + base + 2) = make_ulonglong2(q[2], q[3]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (base + k < N) qout[base + k] = q[k];
+      }
+      tq[h] = warp_sum_u64(tq[h]);
+    }
+    if (sub > 0) __syncthreads();  // warp 0 is done with the previous trip's s_wq
+    if (lane == 0) {
+      s_wq[warp] = tq[0];
+      s_wq[warp + NW] = tq[1];
+    }
+    __syncthreads();
+    if (warp == 0) {  // exclusive offsets of the trip's 32 chunks inside the tile
+      const unsigned long long v = s_wq[lane];
+      const unsigned long long vinc = warp_scan_u64(v, lane);
+      ix.chunk_excl[(int64_t)tile * ix.chunks_per_tile + sub * kChunksPerSub + lane] = running + (vinc - v);
+      running += __shfl_sync(kFullMask, vinc, 31);
+    }
+  }
+  se = warp_sum(se);
+  se2 = warp_sum(se2);
+  if (lane == 0) {
+    s_we[warp] = se;
+    s_we2[warp] = se2;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    double e1 = (lane < NW) ? s_we[lane] : 0.0, e2 = (lane < NW) ? s_we2[lane] : 0.0;
+    e1 = warp_sum(e1);
+    e2 = warp_sum(e2);
+    if (lane == 0) {
+      psum[tile] = e1;
+      psum2[tile] = e2;
+      ix.tile_tot[tile] = running;
+      __threadfence();
+      s_last = (atomicAdd(&ctrl->scan_done, 1u) == (unsigned)ix.ntiles - 1);
+    }
+  }
+  __syncthreads();
+  if (!s_last) return;
+  // ---- last CTA out: Σe, Σe² in a fixed order (deterministic), scan of the tile totals, Q, systematic offset
+  constexpr int PER = kMaxTiles / kSumThreads;  // 16 contiguous tiles per thread
+  double a = 0.0, b = 0.0;
+  unsigned long long v[PER], run = 0;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int j = tid * PER + k;
+    v[k] = 0;
+    if (j < ix.ntiles) {
+      a += __ldcg(&psum[j]);
+      b += __ldcg(&psum2[j]);
+      v[k] = __ldcg(&ix.tile_tot[j]);
+    }
+    run += v[k];
+  }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  const unsigned long long winc = warp_scan_u64(run, lane);
+  if (lane == 0) {
+    s_we[warp] = a;
+    s_we2[warp] = b;
+  }
+  if (lane == 31) s_scan[warp] = winc;
+  __syncthreads();
+  const unsigned long long wv = (lane < NW) ? s_scan[lane] : 0ull;
+  const unsigned long long wvinc = warp_scan_u64(wv, lane);
+  const unsigned long long wexcl = __shfl_sync(kFullMask, wvinc - wv, warp);
+  const unsigned long long Q = __shfl_sync(kFullMask, wvinc, NW - 1);
+  unsigned long long acc = wexcl + (winc - run);
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int j = tid * PER + k;
+    if (j < ix.ntiles) {
+      ix.tile_excl[j] = acc;
+      acc += v[k];
+      ix.tile_incl[j] = acc;
+    }
+  }
+  if (warp == 0) {
+    double e1 = (lane < NW) ? s_we[lane] : 0.0, e2 = (lane < NW) ? s_we2[lane] : 0.0;
+    e1 = warp_sum(e1);
+    e2 = warp_sum(e2);
+    if (lane == 0) {
+      stats_out->mx = mx;
+      stats_out->sum = e1;
+      stats_out->sum2 = e2;
+      ctrl->total = Q;
+      ctrl->sys_off = (resampler == RESAMPLE_SYSTEMATIC) ? mulhi64(uniform64_at(key, 0u, stream, t, PURPOSE_RESAMPLE), Rw) : 0ull;
+      ctrl->scan_done = 0;
+      ctrl->maxslot[slot ^ 1] = encode_ordered(-INFINITY);
+    }
+  }
+}
+
+// #{ t in [0,n) : v[t] <= tau } by one warp, 32 probes per round (v sorted ascending)
+__device__ __forceinline__ int warp_count_le(const unsigned long long* __restrict__ v, int n, uint64_t tau, int lane) {
+  int lo = 0, hi = n;
+  while (hi > lo) {
+    const int len = hi - lo;
+    const int step = (len + 31) >> 5;
+    const int p = lo + lane * step + (step - 1);
+    const bool le = (p < hi) && (__ldg(&v[p]) <= tau);
+    const int c = __popc(__ballot_sync(kFullMask, le));
+    lo += c * step;
+    if (c == 32) break;
+    const int nh = lo + step - 1;
+    hi = nh < hi ? nh : hi;
+  }
+  return lo;
+}
+
+// chunk holding the ancestor of threshold tau (one warp); tau < Q
+__device__ __forceinline__ int locate_chunk(const StepIndex& ix, uint64_t tau, int lane) {
+  int T = warp_count_le(ix.tile_incl, ix.ntiles, tau, lane);
+  if (T > ix.ntiles - 1) T = ix.ntiles - 1;
+  const uint64_t rem = tau - __ldg(&ix.tile_excl[T]);
+  const unsigned long long* ce = ix.chunk_excl + (int64_t)T * ix.chunks_per_tile;
+  // chunks c' >= 1 of the tile whose start offset is <= rem come before (or are) the target
+  const int c = warp_count_le(ce + 1, ix.chunks_per_tile - 1, rem, lane);
+  return T * ix.chunks_per_tile + c;
+}
+
+// count of s_cdf[0..L) <= tau, branch-free: P = smallest power of two >= L
+__device__ __forceinline__ int window_count_le(const unsigned long long* s_cdf, int L, int P, uint64_t tau) {
+  int pos = 0;
+  for (int step = P >> 1; step > 0; step >>= 1) {
+    const int idx = pos + step - 1;
+    if (idx < L && s_cdf[idx] <= tau) pos += step;
+  }
+  if (pos < L && s_cdf[pos] <= tau) ++pos;  // P/2 + ... + 1 = P - 1 entries covered by the loop
+  return pos;
+}
+
+template <class Model>
+__global__ void __launch_bounds__(kP2Threads)
+    prop2_kernel(Derived dv, double y, int N, int64_t ld, int resampler, uint64_t Rw, RngKey key, uint32_t stream, uint32_t t,
+                 StepIndex ix, const unsigned long long* __restrict__ qprev, const double* __restrict__ xprev,
+                 double* __restrict__ xnew, double* __restrict__ logw, int32_t* __restrict__ anc_out, FilterCtrl* ctrl) {
+  constexpr int D = Model::D;
+  constexpr int NW = kP2Threads / 32;
+  __shared__ __align__(16) unsigned long long s_cdf[kSegChunks * kChunk];
+  __shared__ double sh[32];
+  __shared__ unsigned long long s_min[NW];
+  __shared__ int s_bound[2];
+  __shared__ int s_next;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  Model mdl;
+  mdl.load(dv.d);
+  const uint64_t Q = ctrl->total;
+  const uint64_t sys_off = ctrl->sys_off;
+  const int npairs = (N + 1) >> 1;
+  const int pair0 = blockIdx.x * (kP2Threads * kP2Pairs);
+  const int i_first = 2 * pair0;
+  int i_last = i_first + kP2Particles - 1;
+  if (i_last > N - 1) i_last = N - 1;
+  const int nchunks_total = (N + kChunk - 1) / kChunk;
+
+  // warps 0/1 find the chunks of the first / last threshold of this CTA in the L2-resident index
+  if (Q != 0 && warp < 2) {
+    const int ib = (warp == 0) ? i_first : i_last;
+    uint64_t u = sys_off;
+    if (resampler == RESAMPLE_STRATIFIED) u = uniform64_at(key, (uint32_t)ib, stream, t, PURPOSE_RESAMPLE);
+    const uint64_t tau = threshold_of(resampler, (uint64_t)ib, Rw, u, Q);
+    const int c = locate_chunk(ix, tau, lane);
+    if (lane == 0) s_bound[warp] = c;
+  }
+
+  // thresholds of my particles
+  uint64_t tau0[kP2Pairs], tau1[kP2Pairs];
+  int a0[kP2Pairs], a1[kP2Pairs];
+  bool open0[kP2Pairs], open1[kP2Pairs];
+#pragma unroll
+  for (int r = 0; r < kP2Pairs; ++r) {
+    const int p = pair0 + r * kP2Threads + tid;
+    const int i = 2 * p;
+    a0[r] = i;
+    a1[r] = i + 1;
+    open0[r] = (Q != 0) && (i < N);
+    open1[r] = (Q != 0) && (i + 1 < N);
+    tau0[r] = tau1[r] = 0;
+    if (open0[r]) {
+      uint64_t ua = sys_off, ub = sys_off;
+      if (resampler == RESAMPLE_STRATIFIED) {
+        const Philox4 b = philox4x32_10((uint32_t)p, stream, t, purpose_word(PURPOSE_RESAMPLE, 0, key.epoch), key.k0, key.k1);
+        ua = uniform64_of(b, 0);
+        ub = uniform64_of(b, 1);
+      }
+      tau0[r] = threshold_of(resampler, (uint64_t)i, Rw, ua, Q);
+      tau1[r] = threshold_of(resampler, (uint64_t)i + 1, Rw, ub, Q);
+    }
+  }
+  __syncthreads();
+  int cs = 0, c_hi = 0;
+  if (Q != 0) {
+    cs = s_bound[0];
+    c_hi = s_bound[1];
+  }
+
+  // rebuild the CDF window chunk by chunk (every warp owns whole chunks: no cross-warp dependency)
+  while (Q != 0) {
+    int nseg = c_hi - cs + 1;
+    if (nseg > kSegChunks) nseg = kSegChunks;
+    if (nseg < 1) nseg = 1;
+    for (int cc = warp; cc < nseg; cc += NW) {
+      const int c = cs + cc;
+      const int item0 = c * kChunk + lane * 4;
+      unsigned long long q[4] = {0, 0, 0, 0};
+      if (item0 + 4 <= N) {
+        const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2*>(qprev + item0));
+        const ulonglong2 b = __ldg(reinterpret_cast<const ulonglong2*>(qprev + item0 + 2));
+        q[0] = a.x; q[1] = a.y; q[2] = b.x; q[3] = b.y;
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (item0 + k < N) q[k] = qprev[item0 + k];
+      }
+      unsigned long long cbase = 0;
+      if (c < nchunks_total) cbase = __ldg(&ix.tile_excl[c / ix.chunks_per_tile]) + __ldg(&ix.chunk_excl[c]);
+      q[1] += q[0];
+      q[2] += q[1];
+      q[3] += q[2];
+      const unsigned long long winc = warp_scan_u64(q[3], lane);
+      const unsigned long long off = cbase + (winc - q[3]);
+      ulonglong2* dst = reinterpret_cast<ulonglong2*>(&s_cdf[cc * kChunk + lane * 4]);
+      dst[0] = make_ulonglong2(off + q[0], off + q[1]);
+      dst[1] = make_ulonglong2(off + q[2], off + q[3]);
+    }
+    __syncthreads();
+    int L = nseg * kChunk;
+    const int seg_start = cs * kChunk;
+    if (seg_start + L > N) L = N - seg_start;
+    int P = 128;
+    while (P < L) P <<= 1;
+    const unsigned long long c_end = s_cdf[L - 1];
+    bool mine_done = true;
+    unsigned long long my_min = ~0ull;
+#pragma unroll
+    for (int r = 0; r < kP2Pairs; ++r) {
+      int pos = -1;
+      if (open0[r]) {
+        if (tau0[r] < c_end) {
+          pos = window_count_le(s_cdf, L, P, tau0[r]);
+          a0[r] = seg_start + pos;
+          open0[r] = false;
+        } else {
+          mine_done = false;
+          my_min = tau0[r] < my_min ? tau0[r] : my_min;
+        }
+      }
+      if (open1[r]) {
+        if (tau1[r] < c_end) {
+          int pos1;
+          if (pos >= 0) {  // tau1 >= tau0: the neighbour's ancestor is almost always within a few entries
+            pos1 = pos;
+            int probes = 0;
+            while (s_cdf[pos1] <= tau1[r]) {  // terminates: tau1 < c_end = s_cdf[L-1]
+              ++pos1;
+              if (++probes == 4) {
+                pos1 = window_count_le(s_cdf, L, P, tau1[r]);
+                break;
+              }
+            }
+          } else {
+            pos1 = window_count_le(s_cdf, L, P, tau1[r]);
+          }
+          a1[r] = seg_start + pos1;
+          open1[r] = false;
+        } else {
+          mine_done = false;
+          my_min = tau1[r] < my_min ? tau1[r] : my_min;
+        }
+      }
+    }
+    if (__syncthreads_and(mine_done)) break;
+    // rare: the window is wider than one pass (very uneven weights) — jump to the chunk that
+    // holds the smallest unresolved threshold
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long v = __shfl_xor_sync(kFullMask, my_min, o);
+      my_min = v < my_min ? v : my_min;
+    }
+    if (lane == 0) s_min[warp] = my_min;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned long long v = (lane < NW) ? s_min[lane] : ~0ull;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long w = __shfl_xor_sync(kFullMask, v, o);
+        v = w < v ? w : v;
+      }
+      const int c = locate_chunk(ix, v, lane);
+      if (lane == 0) s_next = c;
+    }
+    __syncthreads();
+    cs = s_next;
+  }
+
+  double vmax = -INFINITY;
+#pragma unroll
+  for (int r = 0; r < kP2Pairs; ++r) {
+    const int p = pair0 + r * kP2Threads + tid;
+    if (p >= npairs) continue;
+    const int i = 2 * p;
+    const bool two = (i + 1 < N);
+    double za[D], zb[D], xpa[D], xpb[D], xa[D], xb[D];
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+      xpa[k] = __ldg(&xprev[k * ld + a0[r]]);
+      xpb[k] = two ? __ldg(&xprev[k * ld + a1[r]]) : xpa[k];
+    }
+#pragma unroll
+    for (int k = 0; k < D; ++k) normal_pair_at(key, (uint32_t)p, stream, t, PURPOSE_TRANSITION, (uint32_t)k, za[k], zb[k]);
+    mdl.transition(za, xpa, xa);
+    mdl.transition(zb, xpb, xb);
+    const double la = mdl.logweight(xa, y);
+    const double lb = mdl.logweight(xb, y);
+    if (two) {
+#pragma unroll
+      for (int k = 0; k < D; ++k) *reinterpret_cast<double2*>(xnew + k * ld + i) = make_double2(xa[k], xb[k]);
+      *reinterpret_cast<double2*>(logw + i) = make_double2(la, lb);
+      if (anc_out) *reinterpret_cast<int2*>(anc_out + i) = make_int2(a0[r], a1[r]);
+      if (la > vmax) vmax = la;
+      if (lb > vmax) vmax = lb;
+    } else {
+#pragma unroll
+      for (int k = 0; k < D; ++k) xnew[k * ld + i] = xa[k];
+      logw[i] = la;
+      if (anc_out) anc_out[i] = a0[r];
+      if (la > vmax) vmax = la;
+    }
+  }
+  const double bm = block_max(vmax, sh);
+  if (tid == 0) atomicMax(&ctrl->maxslot[t & 1u], encode_ordered(bm));
+}
+
 // w_i = exp(logw_i - max) / Σe   (normalize, particles.jl:11) — only when the caller fetches w
 __global__ void weights_kernel(const double* __restrict__ logw, double* __restrict__ w, int64_t N, StepStats st) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -468,9 +884,11 @@ SingleFilter::~SingleFilter() {
 }
 
 void SingleFilter::release() {
-  cudaFree(x_[0]); cudaFree(x_[1]); cudaFree(logw_); cudaFree(w_tmp_); cudaFree(cdf_); cudaFree(anc_);
+  cudaFree(x_[0]); cudaFree(x_[1]); cudaFree(logw_[0]); cudaFree(logw_[1]); cudaFree(w_tmp_); cudaFree(cdf_); cudaFree(anc_);
   cudaFree(ctrl_); cudaFree(desc_); cudaFree(psum_); cudaFree(psum2_); cudaFree(stats_dev_);
-  x_[0] = x_[1] = logw_ = w_tmp_ = psum_ = psum2_ = nullptr;
+  cudaFree(chunk_excl_); cudaFree(tile_arrays_); cudaFree(bound_chunk_);
+  chunk_excl_ = tile_arrays_ = nullptr; bound_chunk_ = nullptr; chunk_cap_ = bound_cap_ = 0;
+  x_[0] = x_[1] = logw_[0] = logw_[1] = w_tmp_ = psum_ = psum2_ = nullptr;
   cdf_ = nullptr; anc_ = nullptr; ctrl_ = nullptr; desc_ = nullptr; stats_dev_ = nullptr;
   cap_N_ = cap_d_ = cap_stats_ = cap_anc_rows_ = ntiles_cap_ = 0;
 }
@@ -479,15 +897,15 @@ void SingleFilter::ensure_capacity(int kind, int64_t N, int64_t anc_rows) {
   const int d = state_dim(kind);
   const int64_t ld = (N + 31) & ~int64_t(31);
   if (ld > cap_N_ || d > cap_d_) {
-    cudaFree(x_[0]); cudaFree(x_[1]); cudaFree(logw_); cudaFree(w_tmp_); cudaFree(cdf_);
+    cudaFree(x_[0]); cudaFree(x_[1]); cudaFree(logw_[0]); cudaFree(logw_[1]); cudaFree(w_tmp_); cudaFree(cdf_);
     cudaFree(desc_); cudaFree(psum_); cudaFree(psum2_);
-    x_[0] = x_[1] = logw_ = w_tmp_ = psum_ = psum2_ = nullptr; cdf_ = nullptr; desc_ = nullptr;
+    x_[0] = x_[1] = logw_[0] = logw_[1] = w_tmp_ = psum_ = psum2_ = nullptr; cdf_ = nullptr; desc_ = nullptr;
     cap_N_ = 0;
     const int64_t cd = std::max<int64_t>(d, cap_d_);
     SMCB_CUDA_TRY(cudaMalloc(&x_[0], sizeof(double) * ld * cd));
     SMCB_CUDA_TRY(cudaMalloc(&x_[1], sizeof(double) * ld * cd));
-    SMCB_CUDA_TRY(cudaMalloc(&logw_, sizeof(double) * ld));
-    SMCB_CUDA_TRY(cudaMalloc(&cdf_, sizeof(uint64_t) * ld));
+    SMCB_CUDA_TRY(cudaMalloc(&logw_[0], sizeof(double) * ld));
+    SMCB_CUDA_TRY(cudaMalloc(&logw_[1], sizeof(double) * ld));
     ntiles_cap_ = (ld + kScanTile - 1) / kScanTile;
     SMCB_CUDA_TRY(cudaMalloc(&desc_, sizeof(unsigned long long) * 2 * ntiles_cap_));
     SMCB_CUDA_TRY(cudaMalloc(&psum_, sizeof(double) * ntiles_cap_));
@@ -497,6 +915,17 @@ void SingleFilter::ensure_capacity(int kind, int64_t N, int64_t anc_rows) {
     cudaFree(anc_); anc_ = nullptr; cap_anc_rows_ = 0;
   }
   if (!ctrl_) SMCB_CUDA_TRY(cudaMalloc(&ctrl_, sizeof(FilterCtrl)));
+  if (!tile_arrays_) SMCB_CUDA_TRY(cudaMalloc(&tile_arrays_, sizeof(unsigned long long) * 3 * kMaxTiles));
+  {
+    const int64_t nsub = (cap_N_ + kSubTile - 1) / kSubTile;
+    const int64_t k = (nsub + kMaxTiles - 1) / kMaxTiles;
+    const int64_t chunks = ((cap_N_ + kSubTile * k - 1) / (kSubTile * k)) * kChunksPerSub * k;
+    if (chunks > chunk_cap_) {
+      cudaFree(chunk_excl_); chunk_excl_ = nullptr; chunk_cap_ = 0;
+      SMCB_CUDA_TRY(cudaMalloc(&chunk_excl_, sizeof(unsigned long long) * chunks));
+      chunk_cap_ = chunks;
+    }
+  }
   if (anc_rows > cap_anc_rows_ || !anc_) {
     cudaFree(anc_); anc_ = nullptr;
     const int64_t rows = std::max<int64_t>(anc_rows, 1);
@@ -538,7 +967,7 @@ void SingleFilter::end_call() {
     SMCB_CUDA_TRY(cudaEventElapsedTime(&ms, ev_pool_[m.e0], ev_pool_[m.e1]));
     ms_[m.klass] += ms;
   }
-  launches_[TK_TOTAL] = launches_[TK_SCAN] + launches_[TK_PROP] + launches_[TK_INIT] + launches_[TK_STATS];
+  launches_[TK_TOTAL] = launches_[TK_SCAN] + launches_[TK_PROP] + launches_[TK_INIT] + launches_[TK_STATS] + launches_[TK_BOUNDS];
 }
 
 void SingleFilter::timing(double ms[TK_COUNT], int64_t launches[TK_COUNT]) const {
@@ -554,7 +983,7 @@ void SingleFilter::launch_init(double y0) {
   mark(TK_INIT, true);
   dispatch_model(kind_, [&](auto m) {
     using M = decltype(m);
-    init_kernel<M><<<grid, 256, 0, stream_>>>(dv_, y0, N_, ld_, key_, stream_id_, x_[cur_], logw_, ctrl_);
+    init_kernel<M><<<grid, 256, 0, stream_>>>(dv_, y0, N_, ld_, key_, stream_id_, x_[cur_], logw_[cur_], ctrl_);
   });
   mark(TK_INIT, false);
   SMCB_CUDA_TRY(cudaGetLastError());
@@ -566,14 +995,16 @@ void SingleFilter::launch_scan(int64_t stat_index, bool write_cdf) {
   unsigned long long* dc = desc_ + (size_t)(t_ & 1u) * ntiles_cap_;
   unsigned long long* dn = desc_ + (size_t)((t_ + 1) & 1u) * ntiles_cap_;
   const int klass = write_cdf ? TK_SCAN : TK_STATS;
+  if ((write_cdf || from_w_) && !cdf_) SMCB_CUDA_TRY(cudaMalloc(&cdf_, sizeof(uint64_t) * cap_N_));  // multinomial / utilities only
+  const double* lw = logw_[cur_];
   mark(klass, true);
   StepStats* so = stats_dev_ + stat_index;
   if (from_w_)
-    scan_kernel<true, true><<<ntiles, kScanThreads, 0, stream_>>>(logw_, cdf_, N_, S_, ctrl_, dc, dn, psum_, psum2_, so, slot, ntiles);
+    scan_kernel<true, true><<<ntiles, kScanThreads, 0, stream_>>>(lw, cdf_, N_, S_, ctrl_, dc, dn, psum_, psum2_, so, slot, ntiles);
   else if (write_cdf)
-    scan_kernel<true, false><<<ntiles, kScanThreads, 0, stream_>>>(logw_, cdf_, N_, S_, ctrl_, dc, dn, psum_, psum2_, so, slot, ntiles);
+    scan_kernel<true, false><<<ntiles, kScanThreads, 0, stream_>>>(lw, cdf_, N_, S_, ctrl_, dc, dn, psum_, psum2_, so, slot, ntiles);
   else
-    scan_kernel<false, false><<<ntiles, kScanThreads, 0, stream_>>>(logw_, cdf_, N_, S_, ctrl_, dc, dn, psum_, psum2_, so, slot, ntiles);
+    scan_kernel<false, false><<<ntiles, kScanThreads, 0, stream_>>>(lw, cdf_, N_, S_, ctrl_, dc, dn, psum_, psum2_, so, slot, ntiles);
   mark(klass, false);
   SMCB_CUDA_TRY(cudaGetLastError());
 }
@@ -592,7 +1023,53 @@ void SingleFilter::launch_prop(double y, int resampler) {
   dispatch_model(kind_, [&](auto m) {
     using M = decltype(m);
     prop_kernel<M><<<grid, kPropThreads, 0, stream_>>>(dv_, y, N_, ld_, resampler, R_, key_, stream_id_, t, cdf_,
-                                                       x_[cur_], x_[cur_ ^ 1], logw_, anc, ctrl_);
+                                                       x_[cur_], x_[cur_ ^ 1], logw_[cur_ ^ 1], anc, ctrl_);
+  });
+  mark(TK_PROP, false);
+  SMCB_CUDA_TRY(cudaGetLastError());
+  cur_ ^= 1;
+  t_ = t;
+}
+
+// one bootstrap_filter! step: stats of the current weights (-> stats_dev_[stat_index]) and the move to t_+1
+void SingleFilter::launch_step(int64_t stat_index, double y, int resampler) {
+  if (resampler == RESAMPLE_MULTINOMIAL) {  // unsorted thresholds: materialised CDF + per-particle global search
+    launch_scan(stat_index, true);
+    launch_prop(y, resampler);
+    return;
+  }
+  const int64_t nsub = (N_ + kSubTile - 1) / kSubTile;
+  const int64_t k = (nsub + kMaxTiles - 1) / kMaxTiles;
+  StepIndex ix;
+  ix.tile_items = kSubTile * k;
+  ix.ntiles = (int)((N_ + ix.tile_items - 1) / ix.tile_items);
+  ix.chunks_per_tile = (int)(kChunksPerSub * k);
+  ix.chunk_excl = chunk_excl_;
+  ix.tile_tot = tile_arrays_;
+  ix.tile_excl = tile_arrays_ + kMaxTiles;
+  ix.tile_incl = tile_arrays_ + 2 * kMaxTiles;
+  if (!cdf_) SMCB_CUDA_TRY(cudaMalloc(&cdf_, sizeof(uint64_t) * cap_N_));  // holds q here (the CDF on the multinomial path)
+  const int64_t npairs = (N_ + 1) / 2;
+  const unsigned nblocks = (unsigned)((npairs + kP2Threads * kP2Pairs - 1) / (kP2Threads * kP2Pairs));
+  const uint32_t t = t_ + 1;
+  mark(TK_SCAN, true);
+  sum_kernel<<<ix.ntiles, kSumThreads, 0, stream_>>>(logw_[cur_], reinterpret_cast<unsigned long long*>(cdf_), N_, S_, ctrl_, ix, psum_,
+                                                     psum2_, stats_dev_ + stat_index, (int)(t_ & 1u), resampler, R_, key_,
+                                                     stream_id_, t);
+  mark(TK_SCAN, false);
+  SMCB_CUDA_TRY(cudaGetLastError());
+  int32_t* anc = nullptr;
+  if (record_anc_) {
+    const int64_t row = std::min<int64_t>(anc_rows_, cap_anc_rows_ - 1);
+    anc = anc_ + row * cap_N_;
+    anc_rows_ = row + 1;
+  }
+  mark(TK_PROP, true);
+  dispatch_model(kind_, [&](auto m) {
+    using M = decltype(m);
+    prop2_kernel<M><<<nblocks, kP2Threads, 0, stream_>>>(dv_, y, (int)N_, ld_, resampler, R_, key_, stream_id_, t, ix,
+                                                         reinterpret_cast<const unsigned long long*>(cdf_), x_[cur_], x_[cur_ ^ 1],
+                                                         logw_[cur_ ^ 1], anc, ctrl_);
   });
   mark(TK_PROP, false);
   SMCB_CUDA_TRY(cudaGetLastError());
@@ -636,8 +1113,7 @@ void SingleFilter::step(const double* params, double y, int resampler, StepStats
   if (params) derive_params(kind_, params, dv_.d);
   if (!record_anc_) anc_rows_ = 0;
   begin_call();
-  launch_scan(0, true);
-  launch_prop(y, resampler);
+  launch_step(0, y, resampler);
   launch_scan(0, false);
   SMCB_CUDA_TRY(cudaMemcpyAsync(&last_, stats_dev_, sizeof(StepStats), cudaMemcpyDeviceToHost, stream_));
   end_call();
@@ -663,8 +1139,7 @@ void SingleFilter::run(int kind, const double* params, int64_t N, const double* 
   begin_call();
   launch_init(y[0]);
   for (int64_t t = 1; t < T; ++t) {
-    launch_scan(t - 1, true);  // stats of time t-1 + CDF
-    launch_prop(y[t], resampler);
+    launch_step(t - 1, y[t], resampler);  // stats of time t-1, then the step to time t
   }
   launch_scan(T - 1, false);
   std::vector<StepStats> tmp;
@@ -680,10 +1155,10 @@ void SingleFilter::fetch(double* x_host, double* w_host, double* logw_host) {
     SMCB_CUDA_TRY(cudaMemcpy2DAsync(x_host, sizeof(double) * N_, x_[cur_], sizeof(double) * ld_, sizeof(double) * N_,
                                     d_, cudaMemcpyDeviceToHost, stream_));
   if (logw_host)
-    SMCB_CUDA_TRY(cudaMemcpyAsync(logw_host, logw_, sizeof(double) * N_, cudaMemcpyDeviceToHost, stream_));
+    SMCB_CUDA_TRY(cudaMemcpyAsync(logw_host, logw_[cur_], sizeof(double) * N_, cudaMemcpyDeviceToHost, stream_));
   if (w_host) {
     if (!w_tmp_) SMCB_CUDA_TRY(cudaMalloc(&w_tmp_, sizeof(double) * cap_N_));
-    weights_kernel<<<(unsigned)((N_ + 255) / 256), 256, 0, stream_>>>(logw_, w_tmp_, N_, last_);
+    weights_kernel<<<(unsigned)((N_ + 255) / 256), 256, 0, stream_>>>(logw_[cur_], w_tmp_, N_, last_);
     SMCB_CUDA_TRY(cudaGetLastError());
     SMCB_CUDA_TRY(cudaMemcpyAsync(w_host, w_tmp_, sizeof(double) * N_, cudaMemcpyDeviceToHost, stream_));
   }
@@ -719,9 +1194,9 @@ void SingleFilter::load_vector(const double* host, int64_t n, bool is_log) {
   t_ = 0; cur_ = 0; anc_rows_ = 0; from_w_ = !is_log;
   SMCB_CUDA_TRY(cudaMemsetAsync(desc_, 0, sizeof(unsigned long long) * 2 * ntiles_cap_, stream_));
   reset_ctrl_kernel<<<1, 1, 0, stream_>>>(ctrl_);
-  SMCB_CUDA_TRY(cudaMemcpyAsync(logw_, host, sizeof(double) * n, cudaMemcpyHostToDevice, stream_));
+  SMCB_CUDA_TRY(cudaMemcpyAsync(logw_[cur_], host, sizeof(double) * n, cudaMemcpyHostToDevice, stream_));
   const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, 1184);
-  max_kernel<<<grid, 256, 0, stream_>>>(logw_, n, ctrl_);
+  max_kernel<<<grid, 256, 0, stream_>>>(logw_[cur_], n, ctrl_);
   SMCB_CUDA_TRY(cudaGetLastError());
 }
 

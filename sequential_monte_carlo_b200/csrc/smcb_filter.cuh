@@ -15,6 +15,7 @@ namespace smcb {
 struct FilterCtrl {
   unsigned long long maxslot[2];  // ordered-encoded max(logw), slot = t & 1
   unsigned long long total;       // Q = C[N-1] of the last scan
+  unsigned long long sys_off;     // mulhi(U(0), R) of the systematic resampler for the coming step
   unsigned int scan_ticket;       // dynamic tile ids of the look-back scan
   unsigned int scan_done;
 };
@@ -23,7 +24,7 @@ struct StepStats {  // normalize() ingredients for one time step (SPEC §6)
   double mx, sum, sum2;
 };
 
-enum { TK_TOTAL = 0, TK_SCAN = 1, TK_PROP = 2, TK_INIT = 3, TK_STATS = 4, TK_COUNT = 5 };
+enum { TK_TOTAL = 0, TK_SCAN = 1, TK_PROP = 2, TK_INIT = 3, TK_STATS = 4, TK_BOUNDS = 5, TK_COUNT = 6 };
 
 class SingleFilter {
  public:
@@ -57,7 +58,7 @@ class SingleFilter {
   uint32_t t() const { return t_; }
   bool live() const { return N_ > 0; }
   const double* dev_x() const { return x_[cur_]; }
-  const double* dev_logw() const { return logw_; }
+  const double* dev_logw() const { return logw_[cur_]; }
 
  private:
   void ensure_capacity(int kind, int64_t N, int64_t anc_rows);
@@ -66,6 +67,7 @@ class SingleFilter {
   void end_call();
   void launch_init(double y0);
   void launch_prop(double y, int resampler);
+  void launch_step(int64_t stat_index, double y, int resampler);  // one bootstrap_filter! step
   void launch_scan(int64_t stat_index, bool write_cdf);
   void mark(int klass, bool start);
   void release();
@@ -89,12 +91,17 @@ class SingleFilter {
   StepStats last_{};
 
   double* x_[2] = {nullptr, nullptr};
-  double* logw_ = nullptr;
+  double* logw_[2] = {nullptr, nullptr};  // ping-pong with x_: the fused step reads the old weights while writing the new
   double* w_tmp_ = nullptr;
   uint64_t* cdf_ = nullptr;
   int32_t* anc_ = nullptr;
   FilterCtrl* ctrl_ = nullptr;
   unsigned long long* desc_ = nullptr;  // [2][ntiles_cap]
+  // chunk/tile index of the sorted-resampler step (sum -> bounds -> prop2)
+  unsigned long long* chunk_excl_ = nullptr;
+  unsigned long long* tile_arrays_ = nullptr;  // [3][kMaxTiles]: tot, excl, incl
+  int32_t* bound_chunk_ = nullptr;
+  int64_t chunk_cap_ = 0, bound_cap_ = 0;
   double* psum_ = nullptr;
   double* psum2_ = nullptr;
   StepStats* stats_dev_ = nullptr;
@@ -109,8 +116,8 @@ class SingleFilter {
   };
   std::vector<Mark> marks_;
   size_t ev_used_ = 0;
-  double ms_[TK_COUNT] = {0, 0, 0, 0, 0};
-  int64_t launches_[TK_COUNT] = {0, 0, 0, 0, 0};
+  double ms_[TK_COUNT] = {0, 0, 0, 0, 0, 0};
+  int64_t launches_[TK_COUNT] = {0, 0, 0, 0, 0, 0};
 };
 
 }  // namespace smcb

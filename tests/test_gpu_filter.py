@@ -77,6 +77,11 @@ def test_medium_n_many_tiles(ctx, oracle):
     _compare_run(ctx, oracle, smc.KIND_SV, 1 << 17, 5, smc.MULTINOMIAL)
 
 
+def test_above_2_pow_24_multi_trip_tiles(ctx, oracle):
+    """N > 2^24: the sum kernel's CTAs make several trips per tile (tile index capped at 8192 tiles)."""
+    _compare_run(ctx, oracle, smc.KIND_LG1D, (1 << 24) + 4097, 3, smc.SYSTEMATIC)
+
+
 def test_degenerate_weights_window_fallback(ctx, oracle):
     """A sharp likelihood (tiny R) concentrates the weight on few particles, so some CTAs see CDF
     windows wider than the staging buffer and take the global-search path."""
@@ -114,8 +119,9 @@ def test_stepping_api_matches_whole_series(ctx, oracle):
     x, w, _ = ctx.fetch_state()
     np.testing.assert_array_equal(x, x_all)
     np.testing.assert_array_equal(w, w_all)
-    np.testing.assert_array_equal(np.array(lms), logmu)
-    np.testing.assert_array_equal(np.array(ess2), ess)
+    # the per-step statistics come from two kernels with different (fixed) summation orders
+    np.testing.assert_allclose(np.array(lms), logmu, rtol=1e-13)
+    np.testing.assert_allclose(np.array(ess2), ess, rtol=1e-13)
     # and against the oracle's step function
     xo, lwo = oracle.bootstrap_init(kind, MODELS[kind], N, y[0], 21, 5, 2)
     for t in range(1, T):
