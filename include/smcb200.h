@@ -71,6 +71,10 @@ int smcb_set_profiling(smcb_ctx* ctx, int enable);
  * weight, ms[3] init, ms[4] stats-only, ms[5] bounds; launches[0..5] the matching launch counts. */
 int smcb_get_timing(const smcb_ctx* ctx, double ms[6], int64_t launches[6]);
 int smcb_synchronize(smcb_ctx* ctx);
+/* page-locked host buffers for fast fetches (PCIe D2H at link rate instead of pageable staging);
+ * the Python / Julia shims keep one per result array and wrap it as an array view */
+int smcb_alloc_pinned(smcb_ctx* ctx, int64_t bytes, void** out);
+int smcb_free_pinned(smcb_ctx* ctx, void* ptr);
 
 /* ------------------------------------------------------------------ utilities */
 /* normalize(logw) -> (logμ, w, ess)                                   particles.jl:5-15

@@ -32,6 +32,8 @@ SIGNATURES = {
     "smcb_set_profiling": (C.c_int, [_c_ctx, C.c_int]),
     "smcb_get_timing": (C.c_int, [_c_ctx, _dp, _i64p]),
     "smcb_synchronize": (C.c_int, [_c_ctx]),
+    "smcb_alloc_pinned": (C.c_int, [_c_ctx, C.c_int64, C.POINTER(C.c_void_p)]),
+    "smcb_free_pinned": (C.c_int, [_c_ctx, C.c_void_p]),
     "smcb_normalize": (C.c_int, [_c_ctx, C.c_void_p, C.c_int64, _dp, C.c_void_p, _dp]),
     "smcb_resample": (C.c_int, [_c_ctx, C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
     "smcb_bootstrap_init": (C.c_int, [_c_ctx, C.c_int, C.c_void_p, C.c_int64, C.c_double, C.c_uint32, _dp, _dp]),
@@ -158,11 +160,30 @@ class Context:
         self._N = 0
         self._kind = LG1D
         self._T = 0
+        self._pinned = {}
 
     def close(self):
         if getattr(self, "_h", None):
+            for ptr, _ in getattr(self, "_pinned", {}).values():
+                self._lib.smcb_free_pinned(self._h, ptr)
+            self._pinned = {}
             self._lib.smcb_destroy(self._h)
             self._h = None
+
+    def pinned_array(self, name, shape):
+        """float64 numpy view of a page-locked buffer owned by this context (reused by later calls
+        with the same name: copy it if you need the values after the next fetch)."""
+        n = int(np.prod(shape))
+        ent = self._pinned.get(name)
+        if ent is None or ent[1] < n:
+            if ent is not None:
+                self._lib.smcb_free_pinned(self._h, ent[0])
+            ptr = C.c_void_p()
+            self._check(self._lib.smcb_alloc_pinned(self._h, 8 * n, C.byref(ptr)))
+            ent = (ptr, n)
+            self._pinned[name] = ent
+        buf = (C.c_double * n).from_address(ent[0].value)
+        return np.frombuffer(buf, dtype=np.float64, count=n).reshape(shape)
 
     def __del__(self):
         try:
@@ -244,9 +265,10 @@ class Context:
 
     def fetch_state(self, want_x=True, want_w=True, want_logw=False):
         d = state_dim(self._kind)
-        x = np.empty((d, self._N)) if want_x else None
-        w = np.empty(self._N) if want_w else None
-        lw = np.empty(self._N) if want_logw else None
+        big = self._N >= (1 << 17)   # large clouds land in page-locked buffers (views, reused by the next fetch)
+        x = (self.pinned_array("x", (d, self._N)) if big else np.empty((d, self._N))) if want_x else None
+        w = (self.pinned_array("w", (self._N,)) if big else np.empty(self._N)) if want_w else None
+        lw = (self.pinned_array("logw", (self._N,)) if big else np.empty(self._N)) if want_logw else None
         self._check(self._lib.smcb_fetch_state(self._h, _ptr(x), _ptr(w), _ptr(lw)))
         return x, w, lw
 

@@ -141,6 +141,22 @@ int smcb_synchronize(smcb_ctx* ctx) {
   });
 }
 
+int smcb_alloc_pinned(smcb_ctx* ctx, int64_t bytes, void** out) {
+  if (!ctx || !out || bytes <= 0) return SMCB_ERR_BAD_ARG;
+  *out = nullptr;
+  return guarded(ctx, [&] {
+    SMCB_CUDA_TRY(cudaSetDevice(ctx->device));
+    SMCB_CUDA_TRY(cudaMallocHost(out, (size_t)bytes));
+  });
+}
+
+int smcb_free_pinned(smcb_ctx* ctx, void* ptr) {
+  if (!ctx) return SMCB_ERR_BAD_ARG;
+  return guarded(ctx, [&] {
+    if (ptr) SMCB_CUDA_TRY(cudaFreeHost(ptr));
+  });
+}
+
 // ------------------------------------------------------------------ utilities
 int smcb_normalize(smcb_ctx* ctx, const double* logw, int64_t n, double* logmu, double* w, double* ess) {
   if (!ctx) return SMCB_ERR_BAD_ARG;

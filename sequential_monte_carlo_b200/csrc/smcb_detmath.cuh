@@ -162,24 +162,21 @@ SMCB_HD double det_exp(double x) {
   return scale_pow2(p, k);
 }
 
-// e = exp(x) and q = min(trunc(exp(x) * 2^S), 2^S) for x <= 0  (SPEC §3 det_quant)
+// e = exp(x) and q = min(trunc(exp(x) * 2^S), 2^S) for x <= 0  (SPEC §3 det_quant).
+// Branch-free (selects only) so that independent evaluations interleave in the FP64 pipe.
 SMCB_HD void det_exp_quant(double x, int S, double& e, uint64_t& q) {
-  if (!(x >= -700.0)) {
-    e = (x < -700.0) ? 0.0 : x;  // NaN propagates into the float sums; q = 0
-    q = 0;
-    return;
-  }
+  const bool valid = (x >= -700.0);             // false for x < -700, -inf and NaN
+  const double xc = valid ? x : -700.0;
   double p;
   int k;
-  det_exp_parts(x, p, k);
-  e = scale_pow2(p, k);
-  if (k + S < 0) {
-    q = 0;
-  } else {
-    uint64_t v = (uint64_t)scale_pow2(p, k + S);
-    uint64_t cap = (uint64_t)1 << S;
-    q = v < cap ? v : cap;
-  }
+  det_exp_parts(xc, p, k);
+  const double ev = scale_pow2(p, k);
+  e = valid ? ev : ((x < -700.0) ? 0.0 : x);    // NaN propagates into the float sums; q = 0
+  const int ks = k + S;
+  const uint64_t v = (uint64_t)scale_pow2(p, ks < 0 ? 0 : ks);
+  const uint64_t cap = (uint64_t)1 << S;
+  const uint64_t vq = v < cap ? v : cap;
+  q = (valid && ks >= 0) ? vq : 0;
 }
 
 SMCB_HD double det_log(double u) {

@@ -424,10 +424,11 @@ __global__ void __launch_bounds__(kPropThreads)
 // propagates and weights.  HBM traffic per particle-update (LG1D fp64): logw 8 R + q 8 W | q 8 R +
 // x 8 R + x' 8 W + logw' 8 W = 48 B, against 56 B with a materialised CDF and ancestor vector.
 // Both kernels are bound by instruction issue (FP64 transcendentals), not by HBM: see DESIGN.md.
-constexpr int kChunk = 128;                              // particles per index entry (one warp x 4)
-constexpr int kSumThreads = 512;
-constexpr int kSubTile = kSumThreads * 8;                // 4096 particles per CTA trip (2 chunks per warp)
-constexpr int kChunksPerSub = kSubTile / kChunk;         // 32
+constexpr int kChunk = 128;                              // particles per index entry (one warp trip: 32 lanes x 4)
+constexpr int kSumThreads = 256;                         // 8 warps, one tile per warp, no block barrier in the main loop
+constexpr int kSumWarps = kSumThreads / 32;
+constexpr int kTileUnit = 2048;                          // particles per tile (x k above 2^24): 16 chunks
+constexpr int kChunksPerUnit = kTileUnit / kChunk;       // 16
 constexpr int kMaxTiles = 8192;                          // tile totals scanned by the last CTA of sum_kernel
 constexpr int kP2Threads = 256;
 constexpr int kP2Pairs = 2;
@@ -439,54 +440,57 @@ struct StepIndex {
   unsigned long long* tile_tot;    // [ntiles]
   unsigned long long* tile_excl;   // [ntiles] global exclusive prefix of the tile
   unsigned long long* tile_incl;   // [ntiles]
+  int32_t* bound_chunk;            // [nblocks + 1] chunk holding the ancestor of each propagate CTA's first particle
   int ntiles;
   int chunks_per_tile;
   int64_t tile_items;
 };
 
-__global__ void __launch_bounds__(kSumThreads)
+__global__ void __launch_bounds__(kSumThreads, 4)
     sum_kernel(const double* __restrict__ logw, unsigned long long* __restrict__ qout, int64_t N, int S, FilterCtrl* ctrl,
                StepIndex ix, double* psum, double* psum2, StepStats* stats_out, int slot, int resampler, uint64_t Rw,
                RngKey key, uint32_t stream, uint32_t t) {
-  constexpr int NW = kSumThreads / 32;
-  __shared__ unsigned long long s_wq[kChunksPerSub];
-  __shared__ double s_we[NW], s_we2[NW];
-  __shared__ unsigned long long s_scan[NW];
+  __shared__ double s_we[kSumWarps], s_we2[kSumWarps];
+  __shared__ unsigned long long s_scan[kSumWarps];
   __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const unsigned tile = blockIdx.x;
+  const int tile = blockIdx.x * kSumWarps + warp;
   const double mx = decode_ordered(ctrl->maxslot[slot]);
-  const int nsub = ix.chunks_per_tile / kChunksPerSub;
-  unsigned long long running = 0;  // meaningful in warp 0
-  double se = 0.0, se2 = 0.0;
-  for (int sub = 0; sub < nsub; ++sub) {
-    const int64_t sub0 = (int64_t)tile * ix.tile_items + (int64_t)sub * kSubTile;
-    unsigned long long tq[2];
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {  // chunk (warp + 16 h) of this trip
-      const int64_t base = sub0 + (int64_t)(warp + NW * h) * kChunk + lane * 4;
-      double lw[4];
-      unsigned long long q[4] = {0, 0, 0, 0};
+  if (tile < ix.ntiles) {
+    // one warp walks its tile chunk by chunk: the running prefix stays in registers
+    unsigned long long running = 0;
+    double se = 0.0, se2 = 0.0;
+    const int64_t tile0 = (int64_t)tile * ix.tile_items;
+    unsigned long long* ce = ix.chunk_excl + (int64_t)tile * ix.chunks_per_tile;
+    // software pipeline: the next chunk's log-weights are in flight while this one is quantised
+    double nx[4];
+    auto load_chunk = [&](int c, double* out) {
+      const int64_t base = tile0 + (int64_t)c * kChunk + lane * 4;
       if (base + 4 <= N) {
         const double2 a = __ldg(reinterpret_cast<const double2*>(logw + base));
         const double2 b = __ldg(reinterpret_cast<const double2*>(logw + base + 2));
-        lw[0] = a.x; lw[1] = a.y; lw[2] = b.x; lw[3] = b.y;
+        out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
       } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k) lw[k] = (base + k < N) ? logw[base + k] : -INFINITY;
+        for (int k = 0; k < 4; ++k) out[k] = (base + k < N) ? logw[base + k] : -INFINITY;
       }
-      tq[h] = 0;
+    };
+    load_chunk(0, nx);
+#pragma unroll 1
+    for (int c = 0; c < ix.chunks_per_tile; ++c) {
+      const int64_t base = tile0 + (int64_t)c * kChunk + lane * 4;
+      double lw[4] = {nx[0], nx[1], nx[2], nx[3]};
+      if (c + 1 < ix.chunks_per_tile) load_chunk(c + 1, nx);
+      unsigned long long q[4], tq = 0;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (base + k < N) {
-          double e;
-          uint64_t qq;
-          det_exp_quant(lw[k] - mx, S, e, qq);
-          se += e;
-          se2 += e * e;
-          q[k] = qq;
-          tq[h] += qq;
-        }
+      for (int k = 0; k < 4; ++k) {  // out-of-range items carry logw = -inf: e = 0, q = 0
+        double e;
+        uint64_t qq;
+        det_exp_quant(lw[k] - mx, S, e, qq);
+        se += e;
+        se2 += e * e;
+        q[k] = qq;
+        tq += qq;
       }
       if (base + 4 <= N) {
         *reinterpret_cast<ulonglong2*>(qout + base) = make_ulonglong2(q[0], q[1]);
@@ -496,56 +500,36 @@ __global__ void __launch_bounds__(kSumThreads)
         for (int k = 0; k < 4; ++k)
           if (base + k < N) qout[base + k] = q[k];
       }
-      tq[h] = warp_sum_u64(tq[h]);
+      tq = warp_sum_u64(tq);
+      if (lane == 0) ce[c] = running;
+      running += tq;
     }
-    if (sub > 0) __syncthreads();  // warp 0 is done with the previous trip's s_wq
+    se = warp_sum(se);
+    se2 = warp_sum(se2);
     if (lane == 0) {
-      s_wq[warp] = tq[0];
-      s_wq[warp + NW] = tq[1];
+      psum[tile] = se;
+      psum2[tile] = se2;
+      ix.tile_tot[tile] = running;
     }
-    __syncthreads();
-    if (warp == 0) {  // exclusive offsets of the trip's 32 chunks inside the tile
-      const unsigned long long v = s_wq[lane];
-      const unsigned long long vinc = warp_scan_u64(v, lane);
-      ix.chunk_excl[(int64_t)tile * ix.chunks_per_tile + sub * kChunksPerSub + lane] = running + (vinc - v);
-      running += __shfl_sync(kFullMask, vinc, 31);
-    }
-  }
-  se = warp_sum(se);
-  se2 = warp_sum(se2);
-  if (lane == 0) {
-    s_we[warp] = se;
-    s_we2[warp] = se2;
   }
   __syncthreads();
-  if (warp == 0) {
-    double e1 = (lane < NW) ? s_we[lane] : 0.0, e2 = (lane < NW) ? s_we2[lane] : 0.0;
-    e1 = warp_sum(e1);
-    e2 = warp_sum(e2);
-    if (lane == 0) {
-      psum[tile] = e1;
-      psum2[tile] = e2;
-      ix.tile_tot[tile] = running;
-      __threadfence();
-      s_last = (atomicAdd(&ctrl->scan_done, 1u) == (unsigned)ix.ntiles - 1);
-    }
+  if (tid == 0) {
+    __threadfence();
+    s_last = (atomicAdd(&ctrl->scan_done, 1u) == gridDim.x - 1);
   }
   __syncthreads();
   if (!s_last) return;
   // ---- last CTA out: Σe, Σe² in a fixed order (deterministic), scan of the tile totals, Q, systematic offset
-  constexpr int PER = kMaxTiles / kSumThreads;  // 16 contiguous tiles per thread
+  constexpr int PER = kMaxTiles / kSumThreads;  // 32 contiguous tiles per thread
   double a = 0.0, b = 0.0;
-  unsigned long long v[PER], run = 0;
-#pragma unroll
+  unsigned long long run = 0;
   for (int k = 0; k < PER; ++k) {
     const int j = tid * PER + k;
-    v[k] = 0;
     if (j < ix.ntiles) {
       a += __ldcg(&psum[j]);
       b += __ldcg(&psum2[j]);
-      v[k] = __ldcg(&ix.tile_tot[j]);
+      run += __ldcg(&ix.tile_tot[j]);
     }
-    run += v[k];
   }
   a = warp_sum(a);
   b = warp_sum(b);
@@ -556,22 +540,22 @@ __global__ void __launch_bounds__(kSumThreads)
   }
   if (lane == 31) s_scan[warp] = winc;
   __syncthreads();
-  const unsigned long long wv = (lane < NW) ? s_scan[lane] : 0ull;
+  const unsigned long long wv = (lane < kSumWarps) ? s_scan[lane] : 0ull;
   const unsigned long long wvinc = warp_scan_u64(wv, lane);
   const unsigned long long wexcl = __shfl_sync(kFullMask, wvinc - wv, warp);
-  const unsigned long long Q = __shfl_sync(kFullMask, wvinc, NW - 1);
+  const unsigned long long Q = __shfl_sync(kFullMask, wvinc, kSumWarps - 1);
   unsigned long long acc = wexcl + (winc - run);
-#pragma unroll
   for (int k = 0; k < PER; ++k) {
     const int j = tid * PER + k;
     if (j < ix.ntiles) {
+      const unsigned long long v = __ldcg(&ix.tile_tot[j]);
       ix.tile_excl[j] = acc;
-      acc += v[k];
+      acc += v;
       ix.tile_incl[j] = acc;
     }
   }
   if (warp == 0) {
-    double e1 = (lane < NW) ? s_we[lane] : 0.0, e2 = (lane < NW) ? s_we2[lane] : 0.0;
+    double e1 = (lane < kSumWarps) ? s_we[lane] : 0.0, e2 = (lane < kSumWarps) ? s_we2[lane] : 0.0;
     e1 = warp_sum(e1);
     e2 = warp_sum(e2);
     if (lane == 0) {
@@ -614,15 +598,44 @@ __device__ __forceinline__ int locate_chunk(const StepIndex& ix, uint64_t tau, i
   return T * ix.chunks_per_tile + c;
 }
 
-// count of s_cdf[0..L) <= tau, branch-free: P = smallest power of two >= L
-__device__ __forceinline__ int window_count_le(const unsigned long long* s_cdf, int L, int P, uint64_t tau) {
+// One warp per propagate CTA boundary: the chunk its first threshold falls in (4 dependent reads of
+// the L2-resident index).  A separate 5 us launch so that these round trips are not on the critical
+// path of every propagate CTA.
+__global__ void __launch_bounds__(256)
+    bounds_kernel(StepIndex ix, const FilterCtrl* ctrl, int N, int resampler, uint64_t Rw, RngKey key, uint32_t stream, uint32_t t,
+                  int nbounds) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b >= nbounds) return;
+  const uint64_t Q = ctrl->total;
+  if (Q == 0) return;
+  int i = b * kP2Particles;
+  if (i > N - 1) i = N - 1;  // the last boundary is the last particle
+  uint64_t u = ctrl->sys_off;
+  if (resampler == RESAMPLE_STRATIFIED) u = uniform64_at(key, (uint32_t)i, stream, t, PURPOSE_RESAMPLE);
+  const uint64_t tau = threshold_of(resampler, (uint64_t)i, Rw, u, Q);
+  const int c = locate_chunk(ix, tau, lane);
+  if (lane == 0) ix.bound_chunk[b] = c;
+}
+
+__device__ __forceinline__ unsigned long long lds_u64(uint32_t saddr) {
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(saddr));
+  return v;
+}
+
+// #{ j in [0,P) : cdf[j] <= tau } over a shared-memory window padded with ~0 up to the power of two
+// P (<= 4096), branch-free; sbase is the window's address in the shared state space.  Explicit
+// ld.shared: through a generic pointer ptxas re-derives the shared window base on every probe.
+__device__ __forceinline__ int window_count_le(uint32_t sbase, int P, uint64_t tau) {
   int pos = 0;
-  for (int step = P >> 1; step > 0; step >>= 1) {
-    const int idx = pos + step - 1;
-    if (idx < L && s_cdf[idx] <= tau) pos += step;
+#pragma unroll
+  for (int step = 2048; step > 0; step >>= 1) {
+    if (step < P) {  // block-uniform
+      if (lds_u64(sbase + 8u * (uint32_t)(pos + step - 1)) <= tau) pos += step;
+    }
   }
-  if (pos < L && s_cdf[pos] <= tau) ++pos;  // P/2 + ... + 1 = P - 1 entries covered by the loop
-  return pos;
+  return pos;  // entry P-1 is a sentinel or the window's last value, both > tau
 }
 
 template <class Model>
@@ -635,35 +648,26 @@ __global__ void __launch_bounds__(kP2Threads)
   __shared__ __align__(16) unsigned long long s_cdf[kSegChunks * kChunk];
   __shared__ double sh[32];
   __shared__ unsigned long long s_min[NW];
-  __shared__ int s_bound[2];
   __shared__ int s_next;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_cdf);
   Model mdl;
   mdl.load(dv.d);
   const uint64_t Q = ctrl->total;
   const uint64_t sys_off = ctrl->sys_off;
   const int npairs = (N + 1) >> 1;
   const int pair0 = blockIdx.x * (kP2Threads * kP2Pairs);
-  const int i_first = 2 * pair0;
-  int i_last = i_first + kP2Particles - 1;
-  if (i_last > N - 1) i_last = N - 1;
   const int nchunks_total = (N + kChunk - 1) / kChunk;
 
-  // warps 0/1 find the chunks of the first / last threshold of this CTA in the L2-resident index
-  if (Q != 0 && warp < 2) {
-    const int ib = (warp == 0) ? i_first : i_last;
-    uint64_t u = sys_off;
-    if (resampler == RESAMPLE_STRATIFIED) u = uniform64_at(key, (uint32_t)ib, stream, t, PURPOSE_RESAMPLE);
-    const uint64_t tau = threshold_of(resampler, (uint64_t)ib, Rw, u, Q);
-    const int c = locate_chunk(ix, tau, lane);
-    if (lane == 0) s_bound[warp] = c;
-  }
-
-  // thresholds of my particles
   uint64_t tau0[kP2Pairs], tau1[kP2Pairs];
   int a0[kP2Pairs], a1[kP2Pairs];
   bool open0[kP2Pairs], open1[kP2Pairs];
+  int cs = 0, c_hi = 0;
+  if (Q != 0) {
+    cs = __ldg(&ix.bound_chunk[blockIdx.x]);
+    c_hi = __ldg(&ix.bound_chunk[blockIdx.x + 1]);  // chunk of the next CTA's first threshold >= my last one
+  }
 #pragma unroll
   for (int r = 0; r < kP2Pairs; ++r) {
     const int p = pair0 + r * kP2Threads + tid;
@@ -684,19 +688,21 @@ __global__ void __launch_bounds__(kP2Threads)
       tau1[r] = threshold_of(resampler, (uint64_t)i + 1, Rw, ub, Q);
     }
   }
-  __syncthreads();
-  int cs = 0, c_hi = 0;
-  if (Q != 0) {
-    cs = s_bound[0];
-    c_hi = s_bound[1];
-  }
 
-  // rebuild the CDF window chunk by chunk (every warp owns whole chunks: no cross-warp dependency)
+  // rebuild the CDF window chunk by chunk from q (every warp owns whole chunks: no cross-warp dependency)
   while (Q != 0) {
     int nseg = c_hi - cs + 1;
     if (nseg > kSegChunks) nseg = kSegChunks;
     if (nseg < 1) nseg = 1;
-    for (int cc = warp; cc < nseg; cc += NW) {
+    int pchunks = 1;
+    while (pchunks < nseg) pchunks <<= 1;
+    for (int cc = warp; cc < pchunks; cc += NW) {
+      ulonglong2* dst = reinterpret_cast<ulonglong2*>(&s_cdf[cc * kChunk + lane * 4]);
+      if (cc >= nseg) {  // sentinel padding up to the power of two
+        dst[0] = make_ulonglong2(~0ull, ~0ull);
+        dst[1] = make_ulonglong2(~0ull, ~0ull);
+        continue;
+      }
       const int c = cs + cc;
       const int item0 = c * kChunk + lane * 4;
       unsigned long long q[4] = {0, 0, 0, 0};
@@ -711,22 +717,19 @@ __global__ void __launch_bounds__(kP2Threads)
       }
       unsigned long long cbase = 0;
       if (c < nchunks_total) cbase = __ldg(&ix.tile_excl[c / ix.chunks_per_tile]) + __ldg(&ix.chunk_excl[c]);
+      else cbase = Q;  // past the end: flat at Q, never selected (tau < Q)
       q[1] += q[0];
       q[2] += q[1];
       q[3] += q[2];
       const unsigned long long winc = warp_scan_u64(q[3], lane);
       const unsigned long long off = cbase + (winc - q[3]);
-      ulonglong2* dst = reinterpret_cast<ulonglong2*>(&s_cdf[cc * kChunk + lane * 4]);
       dst[0] = make_ulonglong2(off + q[0], off + q[1]);
       dst[1] = make_ulonglong2(off + q[2], off + q[3]);
     }
     __syncthreads();
-    int L = nseg * kChunk;
+    const int P = pchunks * kChunk;
     const int seg_start = cs * kChunk;
-    if (seg_start + L > N) L = N - seg_start;
-    int P = 128;
-    while (P < L) P <<= 1;
-    const unsigned long long c_end = s_cdf[L - 1];
+    const unsigned long long c_end = lds_u64(sbase + 8u * (uint32_t)(nseg * kChunk - 1));
     bool mine_done = true;
     unsigned long long my_min = ~0ull;
 #pragma unroll
@@ -734,7 +737,7 @@ __global__ void __launch_bounds__(kP2Threads)
       int pos = -1;
       if (open0[r]) {
         if (tau0[r] < c_end) {
-          pos = window_count_le(s_cdf, L, P, tau0[r]);
+          pos = window_count_le(sbase, P, tau0[r]);
           a0[r] = seg_start + pos;
           open0[r] = false;
         } else {
@@ -748,15 +751,15 @@ __global__ void __launch_bounds__(kP2Threads)
           if (pos >= 0) {  // tau1 >= tau0: the neighbour's ancestor is almost always within a few entries
             pos1 = pos;
             int probes = 0;
-            while (s_cdf[pos1] <= tau1[r]) {  // terminates: tau1 < c_end = s_cdf[L-1]
+            while (lds_u64(sbase + 8u * (uint32_t)pos1) <= tau1[r]) {  // ends: tau1 < c_end
               ++pos1;
               if (++probes == 4) {
-                pos1 = window_count_le(s_cdf, L, P, tau1[r]);
+                pos1 = window_count_le(sbase, P, tau1[r]);
                 break;
               }
             }
           } else {
-            pos1 = window_count_le(s_cdf, L, P, tau1[r]);
+            pos1 = window_count_le(sbase, P, tau1[r]);
           }
           a1[r] = seg_start + pos1;
           open1[r] = false;
@@ -799,7 +802,7 @@ __global__ void __launch_bounds__(kP2Threads)
     const bool two = (i + 1 < N);
     double za[D], zb[D], xpa[D], xpb[D], xa[D], xb[D];
 #pragma unroll
-    for (int k = 0; k < D; ++k) {
+    for (int k = 0; k < D; ++k) {  // parents first: the loads fly while the normals are drawn
       xpa[k] = __ldg(&xprev[k * ld + a0[r]]);
       xpb[k] = two ? __ldg(&xprev[k * ld + a1[r]]) : xpa[k];
     }
@@ -917,9 +920,15 @@ void SingleFilter::ensure_capacity(int kind, int64_t N, int64_t anc_rows) {
   if (!ctrl_) SMCB_CUDA_TRY(cudaMalloc(&ctrl_, sizeof(FilterCtrl)));
   if (!tile_arrays_) SMCB_CUDA_TRY(cudaMalloc(&tile_arrays_, sizeof(unsigned long long) * 3 * kMaxTiles));
   {
-    const int64_t nsub = (cap_N_ + kSubTile - 1) / kSubTile;
-    const int64_t k = (nsub + kMaxTiles - 1) / kMaxTiles;
-    const int64_t chunks = ((cap_N_ + kSubTile * k - 1) / (kSubTile * k)) * kChunksPerSub * k;
+    const int64_t nunit = (cap_N_ + kTileUnit - 1) / kTileUnit;
+    const int64_t k = (nunit + kMaxTiles - 1) / kMaxTiles;
+    const int64_t chunks = ((cap_N_ + kTileUnit * k - 1) / (kTileUnit * k)) * kChunksPerUnit * k;
+    const int64_t nb = (cap_N_ / 2 + kP2Threads * kP2Pairs) / (kP2Threads * kP2Pairs) + 2;
+    if (nb > bound_cap_) {
+      cudaFree(bound_chunk_); bound_chunk_ = nullptr; bound_cap_ = 0;
+      SMCB_CUDA_TRY(cudaMalloc(&bound_chunk_, sizeof(int32_t) * nb));
+      bound_cap_ = nb;
+    }
     if (chunks > chunk_cap_) {
       cudaFree(chunk_excl_); chunk_excl_ = nullptr; chunk_cap_ = 0;
       SMCB_CUDA_TRY(cudaMalloc(&chunk_excl_, sizeof(unsigned long long) * chunks));
@@ -1038,25 +1047,31 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler) {
     launch_prop(y, resampler);
     return;
   }
-  const int64_t nsub = (N_ + kSubTile - 1) / kSubTile;
-  const int64_t k = (nsub + kMaxTiles - 1) / kMaxTiles;
+  const int64_t nunit = (N_ + kTileUnit - 1) / kTileUnit;
+  const int64_t k = (nunit + kMaxTiles - 1) / kMaxTiles;
   StepIndex ix;
-  ix.tile_items = kSubTile * k;
+  ix.tile_items = kTileUnit * k;
   ix.ntiles = (int)((N_ + ix.tile_items - 1) / ix.tile_items);
-  ix.chunks_per_tile = (int)(kChunksPerSub * k);
+  ix.chunks_per_tile = (int)(kChunksPerUnit * k);
   ix.chunk_excl = chunk_excl_;
   ix.tile_tot = tile_arrays_;
   ix.tile_excl = tile_arrays_ + kMaxTiles;
   ix.tile_incl = tile_arrays_ + 2 * kMaxTiles;
+  ix.bound_chunk = bound_chunk_;
   if (!cdf_) SMCB_CUDA_TRY(cudaMalloc(&cdf_, sizeof(uint64_t) * cap_N_));  // holds q here (the CDF on the multinomial path)
   const int64_t npairs = (N_ + 1) / 2;
   const unsigned nblocks = (unsigned)((npairs + kP2Threads * kP2Pairs - 1) / (kP2Threads * kP2Pairs));
   const uint32_t t = t_ + 1;
   mark(TK_SCAN, true);
-  sum_kernel<<<ix.ntiles, kSumThreads, 0, stream_>>>(logw_[cur_], reinterpret_cast<unsigned long long*>(cdf_), N_, S_, ctrl_, ix, psum_,
+  sum_kernel<<<(ix.ntiles + kSumWarps - 1) / kSumWarps, kSumThreads, 0, stream_>>>(logw_[cur_], reinterpret_cast<unsigned long long*>(cdf_), N_, S_, ctrl_, ix, psum_,
                                                      psum2_, stats_dev_ + stat_index, (int)(t_ & 1u), resampler, R_, key_,
                                                      stream_id_, t);
   mark(TK_SCAN, false);
+  SMCB_CUDA_TRY(cudaGetLastError());
+  const int nbounds = (int)nblocks + 1;
+  mark(TK_BOUNDS, true);
+  bounds_kernel<<<(nbounds + 7) / 8, 256, 0, stream_>>>(ix, ctrl_, (int)N_, resampler, R_, key_, stream_id_, t, nbounds);
+  mark(TK_BOUNDS, false);
   SMCB_CUDA_TRY(cudaGetLastError());
   int32_t* anc = nullptr;
   if (record_anc_) {

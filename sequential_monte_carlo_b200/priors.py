@@ -22,6 +22,13 @@ class Distribution:
     def insupport(self, x):
         return bool(np.isfinite(x))
 
+    # vectorised forms over M values (used by the samplers; same formulas with numpy ufuncs)
+    def insupport_v(self, x):
+        return np.isfinite(x)
+
+    def logpdf_v(self, x):
+        return np.array([self.logpdf(float(v)) for v in x])
+
     def sample(self, M, seed, k):
         raise NotImplementedError
 
@@ -31,6 +38,10 @@ class Normal(Distribution):
         self.μ, self.σ = float(μ), float(σ)
 
     def logpdf(self, x):
+        z = (x - self.μ) / self.σ
+        return -0.5 * z * z - math.log(self.σ) - _HALF_LOG_2PI
+
+    def logpdf_v(self, x):
         z = (x - self.μ) / self.σ
         return -0.5 * z * z - math.log(self.σ) - _HALF_LOG_2PI
 
@@ -52,6 +63,15 @@ class LogNormal(Distribution):
         z = (lx - self.μ) / self.σ
         return -lx - math.log(self.σ) - _HALF_LOG_2PI - 0.5 * z * z
 
+    def insupport_v(self, x):
+        return np.isfinite(x) & (x > 0.0)
+
+    def logpdf_v(self, x):
+        ok = self.insupport_v(x)
+        lx = np.log(np.where(ok, x, 1.0))
+        z = (lx - self.μ) / self.σ
+        return np.where(ok, -lx - math.log(self.σ) - _HALF_LOG_2PI - 0.5 * z * z, -math.inf)
+
     def sample(self, M, seed, k):
         return np.exp(self.μ + self.σ * _lib.rng_normals(seed, 0, k, 0, _lib.P_PRIOR, 0, M))
 
@@ -65,6 +85,12 @@ class Uniform(Distribution):
 
     def logpdf(self, x):
         return -math.log(self.b - self.a) if self.insupport(x) else -math.inf
+
+    def insupport_v(self, x):
+        return (x >= self.a) & (x <= self.b)
+
+    def logpdf_v(self, x):
+        return np.where(self.insupport_v(x), -math.log(self.b - self.a), -math.inf)
 
     def sample(self, M, seed, k):
         return self.a + (self.b - self.a) * _lib.rng_uniforms01(seed, 0, k, 0, _lib.P_PRIOR, M)
@@ -85,6 +111,13 @@ class TruncatedNormal(Distribution):
             return -math.inf
         z = (x - self.μ) / self.σ
         return -0.5 * z * z - math.log(self.σ) - _HALF_LOG_2PI - self._logmass
+
+    def insupport_v(self, x):
+        return (x >= self.lo) & (x <= self.hi)
+
+    def logpdf_v(self, x):
+        z = (x - self.μ) / self.σ
+        return np.where(self.insupport_v(x), -0.5 * z * z - math.log(self.σ) - _HALF_LOG_2PI - self._logmass, -math.inf)
 
     def sample(self, M, seed, k):
         out = np.empty(M)
@@ -117,6 +150,19 @@ class Product(Distribution):
         s = 0.0
         for c, v in zip(self.components, θ):
             s += c.logpdf(float(v))
+        return s
+
+    def insupport_v(self, θ):
+        """[M] bool for θ [M, d]"""
+        ok = np.ones(θ.shape[0], bool)
+        for k, c in enumerate(self.components):
+            ok &= c.insupport_v(θ[:, k])
+        return ok
+
+    def logpdf_v(self, θ):
+        s = np.zeros(θ.shape[0])
+        for k, c in enumerate(self.components):
+            s = s + c.logpdf_v(θ[:, k])
         return s
 
     def sample(self, M, seed):

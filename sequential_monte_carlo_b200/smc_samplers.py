@@ -25,6 +25,7 @@ import numpy as np
 
 from . import _lib
 from .particles import default_context, resampler_id
+from .state_space_models import params_of
 
 
 # ----------------------------------------------------------------------------- communicator
@@ -50,6 +51,15 @@ class TorchComm:
         self.rank, self.world = dist.get_rank(), dist.get_world_size()
         self.device = device if device is not None else (torch.device("cuda", torch.cuda.current_device())
                                                           if dist.get_backend() == "nccl" else torch.device("cpu"))
+        self.warm_up()
+
+    def warm_up(self):
+        """NCCL builds its all-gather rings and every point-to-point channel lazily (hundreds of ms on
+        first use): touch them once here, outside anybody's timed region."""
+        self.all_gather(np.zeros(1))
+        if self.world > 1:
+            one = {r: self.torch.zeros(8, dtype=self.torch.uint8, device=self.device) for r in range(self.world) if r != self.rank}
+            self.exchange(one, {r: 1 for r in one}, 8)
 
     def all_gather(self, local):
         t = self.torch.from_numpy(np.ascontiguousarray(local, np.float64)).to(self.device)
@@ -150,18 +160,28 @@ class SMC:
         self.logZ = np.zeros(self.M)                                   # :44
         self.ess = 1.0 * self.M                                        # :45
         self.ess_min = self.M * float(ess_threshold)                   # :46
-        m0 = model(self.θ[0])
+        self._P, m0 = params_of(model, self.θ)      # [M, 8] parameter blocks, kept in step with θ
         self.kind, self.d = m0.kind, m0.state_dim
         self._cur = self.ctx.batch(self.kind, self.Mloc, self.N)
         self._prop = None
         self._epoch = 1          # ordinal of the next batched sweep (device Philox epoch)
         self._n_resample = 0     # ordinal of the next θ-resample
         self._n_rejuv = 0        # ordinal of the next rejuvenation (host Philox epoch)
+        self._params_dirty = True  # device copy of the parameter blocks is stale
         self.stats = {"sweeps": 0, "particle_updates": 0, "device_ms": 0.0, "clouds_moved": 0}
 
     # -- helpers
     def _params(self, θ):
-        return np.stack([self.model(th).params8() for th in θ])
+        return params_of(self.model, θ)[0]
+
+    def _prior_v(self, θ):
+        """(insupport [M], logpdf [M]) of the prior for θ [M, d] — vectorised when the prior offers it"""
+        if hasattr(self.prior, "insupport_v"):
+            ok = self.prior.insupport_v(θ)
+            with np.errstate(invalid="ignore", divide="ignore"):
+                return ok, np.where(ok, self.prior.logpdf_v(θ), -math.inf)
+        ok = np.array([self.prior.insupport(th) for th in θ])
+        return ok, np.array([self.prior.logpdf(th) if o else -math.inf for th, o in zip(θ, ok)])
 
     def _local(self, v):
         return v[self.lo: self.lo + self.Mloc]
@@ -214,9 +234,11 @@ def resample_(smc):
     a = smc.ctx.resample(smc.ω, smc.theta_resampler, stream=0, t=smc._n_resample, purpose=_lib.P_THETA_RESAMPLE)
     smc._n_resample += 1
     smc.θ = smc.θ[a]
+    smc._P = smc._P[a]
     smc.logZ = smc.logZ[a]
     smc.ω = np.full(smc.M, 1.0 / smc.M)
     smc.stats["clouds_moved"] += redistribute(_BatchStore(smc._cur, smc.comm), a, smc.comm)
+    smc._params_dirty = True
     return a
 
 
@@ -272,20 +294,17 @@ def rejuvenate_(smc, y, ξ=1.0, verbose=False):
         smc._prop = smc.ctx.batch(smc.kind, smc.Mloc, smc.N)
     ordinal = smc._n_rejuv
     smc._n_rejuv += 1
-    lp_cur = np.array([smc.prior.logpdf(th) for th in smc.θ])
+    _, lp_cur = smc._prior_v(smc.θ)
     for c in range(smc.chain):
         z = np.stack([_lib.rng_normals(smc.seed, ordinal, k, c, _lib.P_MH_PROPOSAL, 0, M) for k in range(d)], axis=1)
         θ_prop = _propose(smc.θ, Σ, univariate, scales[c], z)          # rand(pmmh_kernel(θ[m], scales[c]))  :114
-        ok = np.array([smc.prior.insupport(th) for th in θ_prop])      # insupport(prior, θ_prop)            :116
-        params = np.zeros((M, _lib.PARAM_STRIDE))
-        safe = np.where(ok[:, None], θ_prop, smc.θ)
-        params[:] = smc._params(safe)
+        ok, lp_prop = smc._prior_v(θ_prop)                             # insupport(prior, θ_prop)            :116
+        params = smc._params(np.where(ok[:, None], θ_prop, smc.θ))
         smc._next_epoch()
         z_loc = smc._prop.log_likelihood(smc._local(params), y, smc.resampler, stream0=smc.lo,
                                          active=smc._local(ok).astype(np.uint8))     # log_likelihood(N, y, model(θ_prop)) :117-121
         smc._account(smc._prop, y.size)
         logZ_prop = smc.comm.all_gather(z_loc)
-        lp_prop = np.array([smc.prior.logpdf(th) if o else -math.inf for th, o in zip(θ_prop, ok)])
         with np.errstate(invalid="ignore"):
             acc_ratio = ξ * (logZ_prop - smc.logZ) + (lp_prop - lp_cur)                # :123-127
             u = _lib.rng_uniforms01(smc.seed, ordinal, 0, c, _lib.P_MH_ACCEPT, M)
@@ -293,11 +312,13 @@ def rejuvenate_(smc, y, ξ=1.0, verbose=False):
                 accept = ok & (logZ_prop + lp_prop > -math.inf) & (np.log(u) < acc_ratio)   # :129
         smc.logZ = np.where(accept, logZ_prop, smc.logZ)                                # :130-133
         smc.θ = np.where(accept[:, None], θ_prop, smc.θ)
+        smc._P = np.where(accept[:, None], params, smc._P)
         lp_cur = np.where(accept, lp_prop, lp_cur)
         smc._cur.accept(smc._prop, smc._local(accept).astype(np.uint8))
         acc |= accept
     smc.ω = np.full(M, 1.0 / M)                                         # ω[m] = 1.0 (then normalised)       :139
     smc.acc_ratio = float(acc.sum()) / M                                # :142
+    smc._params_dirty = True
     if verbose:
         sys.stdout.write("\tacc_rate: %1.5f" % smc.acc_ratio)
     return smc
@@ -322,7 +343,7 @@ def exchange_(smc, y, verbose=False):
     if oldp is not None:
         oldp.close()
     smc._next_epoch()
-    z_loc = smc._cur.log_likelihood(smc._local(smc._params(smc.θ)), y, smc.resampler, stream0=smc.lo)
+    z_loc = smc._cur.log_likelihood(smc._local(smc._P), y, smc.resampler, stream0=smc.lo)
     smc._account(smc._cur, y.size)
     new_logZ = smc.comm.all_gather(z_loc)
     _, smc.ω, smc.ess = smc.ctx.normalize(new_logZ - smc.logZ)
@@ -333,7 +354,7 @@ def density_tempered(smc, y, verbose=True):
     """density_tempered(smc, y) (smc_samplers.jl:222-281), Duan & Fulop's density-tempered SMC."""
     y = np.ascontiguousarray(y, np.float64)
     smc._next_epoch()
-    z_loc = smc._cur.log_likelihood(smc._local(smc._params(smc.θ)), y, smc.resampler, stream0=smc.lo)   # :223-229
+    z_loc = smc._cur.log_likelihood(smc._local(smc._P), y, smc.resampler, stream0=smc.lo)   # :223-229
     smc._account(smc._cur, y.size)
     smc.logZ = smc.comm.all_gather(z_loc)
     _, smc.ω, smc.ess = smc.ctx.normalize(smc.logZ)                    # :232
@@ -375,7 +396,7 @@ def smc2(smc, y):
     """smc²(smc, y) (smc_samplers.jl:288-301): M bootstrap filters at the first observation."""
     y = np.ascontiguousarray(y, np.float64)
     smc._next_epoch()
-    lm_loc, _ = smc._cur.init(smc._local(smc._params(smc.θ)), y[0], stream0=smc.lo)
+    lm_loc, _ = smc._cur.init(smc._local(smc._P), y[0], stream0=smc.lo)
     smc._account(smc._cur, 1)
     logmu = smc.comm.all_gather(lm_loc)
     smc.logZ = logmu.copy()                                             # smc.logZ = smc.ω                   :297
@@ -396,7 +417,8 @@ def smc2_step(smc, y, t, verbose=True):
         smc.rejuvenated = True
     with np.errstate(divide="ignore"):
         logω = np.log(smc.ω)                                            # :324
-    lm_loc, _ = smc._cur.step(y[t], smc.resampler, params=smc._local(smc._params(smc.θ)))   # M × bootstrap_filter!  :325-331
+    lm_loc, _ = smc._cur.step(y[t], smc.resampler, params=smc._local(smc._P) if smc._params_dirty else None)   # M × bootstrap_filter!  :325-331
+    smc._params_dirty = False
     smc._account(smc._cur, 1)
     logmu = smc.comm.all_gather(lm_loc)
     logω = logω + logmu                                                 # :333

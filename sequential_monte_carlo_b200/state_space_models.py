@@ -10,6 +10,35 @@ import numpy as np
 from . import _lib
 
 
+class ParamColumn(np.ndarray):
+    """One component of θ for ALL θ-particles at once (length M).  The samplers call the user's
+    `model(θ)` once with θ[k] = ParamColumn instead of M times with scalars (the reference's
+    `model.(θ)` broadcast, ibis.jl:37); model constructors accept these and keep arrays."""
+
+    def __new__(cls, a):
+        return np.asarray(a, dtype=np.float64).view(cls)
+
+
+def _field(name, v):
+    if isinstance(v, ParamColumn):
+        return v
+    if np.ndim(v) != 0:
+        raise NotImplementedError(f"{name}: multivariate linear models are outside the accelerated path (SURVEY §8f N4)")
+    return float(v)
+
+
+def _stack_params(vals):
+    """[k] scalars / ParamColumns -> [8] list or [M, 8] array"""
+    cols = [v for v in vals if isinstance(v, ParamColumn)]
+    if not cols:
+        return [float(v) for v in vals]
+    M = len(cols[0])
+    out = np.zeros((M, len(vals)))
+    for k, v in enumerate(vals):
+        out[:, k] = np.asarray(v)
+    return out
+
+
 class _ModelMeta(type):
     def __call__(cls, *args, **kwargs):
         if cls is StateSpaceModel:  # README constructor: StateSpaceModel(spec, dims) -> spec
@@ -42,13 +71,11 @@ class LinearModel(StateSpaceModel):
     kind = _lib.LG1D
 
     def __init__(self, A, B, Q, R, x0=0.0, σ0=1.0):
-        for name, v in (("A", A), ("B", B), ("Q", Q), ("R", R), ("x0", x0), ("σ0", σ0)):
-            if np.ndim(v) != 0:
-                raise NotImplementedError(f"{name}: multivariate linear models are outside the accelerated path (SURVEY §8f N4)")
-        self.A, self.B, self.Q, self.R, self.x0, self.σ0 = (float(v) for v in (A, B, Q, R, x0, σ0))
+        self.A, self.B, self.Q, self.R, self.x0, self.σ0 = (_field(n, v) for n, v in (("A", A), ("B", B), ("Q", Q), ("R", R),
+                                                                                        ("x0", x0), ("σ0", σ0)))
 
     def params(self):
-        return [self.A, self.B, self.Q, self.R, self.x0, self.σ0]
+        return _stack_params([self.A, self.B, self.Q, self.R, self.x0, self.σ0])
 
     def __repr__(self):
         return f"LinearModel(A={self.A}, B={self.B}, Q={self.Q}, R={self.R}, x0={self.x0}, σ0={self.σ0})"
@@ -82,11 +109,14 @@ class UCSV(StateSpaceModel):
     state_dim = 3
 
     def __init__(self, γ, x0, log_σ0):
-        g = (float(γ), float(γ)) if np.ndim(γ) == 0 else (float(γ[0]), float(γ[1]))
-        self.γ, self.x0, self.log_σ0 = g, float(x0), (float(log_σ0[0]), float(log_σ0[1]))
+        if isinstance(γ, ParamColumn) or np.ndim(γ) == 0:
+            g = (_field("γ", γ), _field("γ", γ))
+        else:
+            g = (_field("γε", γ[0]), _field("γη", γ[1]))
+        self.γ, self.x0, self.log_σ0 = g, _field("x0", x0), (_field("log_σε", log_σ0[0]), _field("log_ση", log_σ0[1]))
 
     def params(self):
-        return [self.γ[0], self.γ[1], self.x0, self.log_σ0[0], self.log_σ0[1]]
+        return _stack_params([self.γ[0], self.γ[1], self.x0, self.log_σ0[0], self.log_σ0[1]])
 
     def __repr__(self):
         return f"UCSV(γ={self.γ}, x0={self.x0}, log_σ0={self.log_σ0})"
@@ -104,16 +134,31 @@ class StochasticVolatility(StateSpaceModel):
     kind = _lib.SV
 
     def __init__(self, μ, ρ, σ):
-        self.μ, self.ρ, self.σ = float(μ), float(ρ), float(σ)
+        self.μ, self.ρ, self.σ = _field("μ", μ), _field("ρ", ρ), _field("σ", σ)
 
     def params(self):
-        return [self.μ, self.ρ, self.σ]
+        return _stack_params([self.μ, self.ρ, self.σ])
 
     def __repr__(self):
         return f"StochasticVolatility(μ={self.μ}, ρ={self.ρ}, σ={self.σ})"
 
 
 SV = StochasticVolatility
+
+
+def params_of(model, θ):
+    """[M, 8] parameter blocks of model(θ_m) for every row of θ [M, d]: one vectorised call with
+    ParamColumns when the user's constructor allows it, else M scalar calls."""
+    θ = np.asarray(θ, np.float64)
+    try:
+        m = model([ParamColumn(θ[:, k]) for k in range(θ.shape[1])])
+        P = np.asarray(m.params(), np.float64)
+        if P.ndim == 2 and P.shape[0] == θ.shape[0]:
+            return _lib.params8(P), m
+    except Exception:
+        pass
+    ms = [model(th) for th in θ]
+    return np.stack([mm.params8() for mm in ms]), ms[0]
 
 
 def simulate(model, T, seed=1998):
