@@ -414,40 +414,43 @@ __global__ void __launch_bounds__(kPropThreads)
 }
 
 // ================================================================================================
-// Sorted resamplers (stratified / systematic): the two-launch step  sum -> prop2.
+// Sorted resamplers (stratified / systematic): the three-launch step  sum -> bounds -> prop2.
 //
-// The CDF never exists in HBM.  sum_kernel quantises the weights (q, one u64 per particle), keeps
-// per-chunk prefix sums (one u64 per 128 particles) and, in its last CTA, scans the <= 8192 tile
-// totals; prop2_kernel locates the chunks its first/last threshold fall in (32-ary warp search of
-// the L2-resident tile index), rebuilds those chunks of the CDF in shared memory from q (exact
-// integer arithmetic, so the ancestors equal those of a materialised CDF), searches, gathers,
-// propagates and weights.  HBM traffic per particle-update (LG1D fp64): logw 8 R + q 8 W | q 8 R +
-// x 8 R + x' 8 W + logw' 8 W = 48 B, against 56 B with a materialised CDF and ancestor vector.
-// Both kernels are bound by instruction issue (FP64 transcendentals), not by HBM: see DESIGN.md.
-constexpr int kChunk = 128;                              // particles per index entry (one warp trip: 32 lanes x 4)
-constexpr int kSumThreads = 256;                         // 8 warps, one tile per warp, no block barrier in the main loop
+// sum_kernel quantises the weights and writes the TILE-LOCAL inclusive CDF cl (one u64 per particle;
+// one warp walks one tile, so the running prefix never leaves its registers) plus one total per tile;
+// its last CTA scans the <= 8192 tile totals (exact integers, so every ancestor equals the one a
+// sequential CDF would give).  bounds_kernel finds, for every propagate CTA, the ancestor of its
+// first particle (32-ary warp searches of the tile index and of one tile).  prop2_kernel stages
+// exactly the CDF entries between its own and the next CTA's bound in shared memory (adding the tile
+// offsets), and every thread resolves 8 CONSECUTIVE particles: one branch-free binary search for
+// the first, then a forward walk that re-reads shared memory only when the ancestor advances; the
+// systematic thresholds tau_i = hi64((i R + u) Q) are advanced by one 128-bit add of R Q.  It then
+// gathers the parents, draws the transition (Philox + Box-Muller), weights, and feeds the exact max.
+// HBM traffic per particle-update (LG1D fp64): logw 8 R + cl 8 W | cl 8 R + x 8 R + x' 8 W +
+// logw' 8 W = 48 B; neither the global CDF nor the ancestor vector is materialised.
+constexpr int kChunk = 128;                            // particles per warp trip of sum_kernel (32 lanes x 4)
+constexpr int kSumThreads = 256;                       // 8 warps, one tile per warp, no block barrier in the main loop
 constexpr int kSumWarps = kSumThreads / 32;
-constexpr int kTileUnit = 2048;                          // particles per tile (x k above 2^24): 16 chunks
-constexpr int kChunksPerUnit = kTileUnit / kChunk;       // 16
-constexpr int kMaxTiles = 8192;                          // tile totals scanned by the last CTA of sum_kernel
-constexpr int kP2Threads = 256;
-constexpr int kP2Pairs = 2;
-constexpr int kP2Particles = kP2Threads * kP2Pairs * 2;  // 1024 particles per CTA
-constexpr int kSegChunks = 32;                           // chunks of CDF rebuilt per pass (4096 entries, 32 KB)
+constexpr int kSumCtasPerSm = 4;
+constexpr int kMaxTiles = 8192;                        // tile totals scanned by the last CTA of sum_kernel
+constexpr int kP2Threads = 128;
+constexpr int kP2Per = 8;                              // consecutive particles per thread
+constexpr int kP2Particles = kP2Threads * kP2Per;      // 1024 particles per CTA
+constexpr int kWinCap = 2048;                          // CDF entries staged per pass (16 KB)
 
 struct StepIndex {
-  unsigned long long* chunk_excl;  // [nchunks] exclusive prefix of the chunk inside its tile
-  unsigned long long* tile_tot;    // [ntiles]
-  unsigned long long* tile_excl;   // [ntiles] global exclusive prefix of the tile
-  unsigned long long* tile_incl;   // [ntiles]
-  int32_t* bound_chunk;            // [nblocks + 1] chunk holding the ancestor of each propagate CTA's first particle
+  unsigned long long* tile_tot;   // [ntiles]
+  unsigned long long* tile_excl;  // [ntiles] global exclusive prefix of the tile
+  unsigned long long* tile_incl;  // [ntiles]
+  int32_t* bound_pos;             // [nblocks + 1] ancestor of each propagate CTA's first particle (last: of particle N-1)
+  int32_t* bound_tile;            // [nblocks + 1] its tile
   int ntiles;
   int chunks_per_tile;
-  int64_t tile_items;
+  int tile_items;
 };
 
-__global__ void __launch_bounds__(kSumThreads, 4)
-    sum_kernel(const double* __restrict__ logw, unsigned long long* __restrict__ qout, int64_t N, int S, FilterCtrl* ctrl,
+__global__ void __launch_bounds__(kSumThreads, kSumCtasPerSm)
+    sum_kernel(const double* __restrict__ logw, unsigned long long* __restrict__ cl, int64_t N, int S, FilterCtrl* ctrl,
                StepIndex ix, double* psum, double* psum2, StepStats* stats_out, int slot, int resampler, uint64_t Rw,
                RngKey key, uint32_t stream, uint32_t t) {
   __shared__ double s_we[kSumWarps], s_we2[kSumWarps];
@@ -461,14 +464,19 @@ __global__ void __launch_bounds__(kSumThreads, 4)
     unsigned long long running = 0;
     double se = 0.0, se2 = 0.0;
     const int64_t tile0 = (int64_t)tile * ix.tile_items;
-    unsigned long long* ce = ix.chunk_excl + (int64_t)tile * ix.chunks_per_tile;
+    int nch = ix.chunks_per_tile;
+    {
+      const int64_t left = N - tile0;
+      const int64_t need = (left + kChunk - 1) / kChunk;
+      if (need < nch) nch = (int)need;
+    }
     // software pipeline: the next chunk's log-weights are in flight while this one is quantised
     double nx[4];
     auto load_chunk = [&](int c, double* out) {
       const int64_t base = tile0 + (int64_t)c * kChunk + lane * 4;
       if (base + 4 <= N) {
-        const double2 a = __ldg(reinterpret_cast<const double2*>(logw + base));
-        const double2 b = __ldg(reinterpret_cast<const double2*>(logw + base + 2));
+        const double2 a = __ldcs(reinterpret_cast<const double2*>(logw + base));
+        const double2 b = __ldcs(reinterpret_cast<const double2*>(logw + base + 2));
         out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
       } else {
 #pragma unroll
@@ -477,11 +485,11 @@ __global__ void __launch_bounds__(kSumThreads, 4)
     };
     load_chunk(0, nx);
 #pragma unroll 1
-    for (int c = 0; c < ix.chunks_per_tile; ++c) {
+    for (int c = 0; c < nch; ++c) {
       const int64_t base = tile0 + (int64_t)c * kChunk + lane * 4;
       double lw[4] = {nx[0], nx[1], nx[2], nx[3]};
-      if (c + 1 < ix.chunks_per_tile) load_chunk(c + 1, nx);
-      unsigned long long q[4], tq = 0;
+      if (c + 1 < nch) load_chunk(c + 1, nx);
+      unsigned long long q[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {  // out-of-range items carry logw = -inf: e = 0, q = 0
         double e;
@@ -490,19 +498,21 @@ __global__ void __launch_bounds__(kSumThreads, 4)
         se += e;
         se2 += e * e;
         q[k] = qq;
-        tq += qq;
       }
+      q[1] += q[0];
+      q[2] += q[1];
+      q[3] += q[2];
+      const unsigned long long winc = warp_scan_u64(q[3], lane);
+      const unsigned long long off = running + (winc - q[3]);
       if (base + 4 <= N) {
-        *reinterpret_cast<ulonglong2*>(qout + base) = make_ulonglong2(q[0], q[1]);
-        *reinterpret_cast<ulonglong2*>(qout + base + 2) = make_ulonglong2(q[2], q[3]);
+        *reinterpret_cast<ulonglong2*>(cl + base) = make_ulonglong2(off + q[0], off + q[1]);
+        *reinterpret_cast<ulonglong2*>(cl + base + 2) = make_ulonglong2(off + q[2], off + q[3]);
       } else {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          if (base + k < N) qout[base + k] = q[k];
+          if (base + k < N) cl[base + k] = off + q[k];
       }
-      tq = warp_sum_u64(tq);
-      if (lane == 0) ce[c] = running;
-      running += tq;
+      running += __shfl_sync(kFullMask, winc, 31);
     }
     se = warp_sum(se);
     se2 = warp_sum(se2);
@@ -523,6 +533,7 @@ __global__ void __launch_bounds__(kSumThreads, 4)
   constexpr int PER = kMaxTiles / kSumThreads;  // 32 contiguous tiles per thread
   double a = 0.0, b = 0.0;
   unsigned long long run = 0;
+#pragma unroll 8
   for (int k = 0; k < PER; ++k) {
     const int j = tid * PER + k;
     if (j < ix.ntiles) {
@@ -545,6 +556,7 @@ __global__ void __launch_bounds__(kSumThreads, 4)
   const unsigned long long wexcl = __shfl_sync(kFullMask, wvinc - wv, warp);
   const unsigned long long Q = __shfl_sync(kFullMask, wvinc, kSumWarps - 1);
   unsigned long long acc = wexcl + (winc - run);
+#pragma unroll 8
   for (int k = 0; k < PER; ++k) {
     const int j = tid * PER + k;
     if (j < ix.ntiles) {
@@ -587,35 +599,42 @@ __device__ __forceinline__ int warp_count_le(const unsigned long long* __restric
   return lo;
 }
 
-// chunk holding the ancestor of threshold tau (one warp); tau < Q
-__device__ __forceinline__ int locate_chunk(const StepIndex& ix, uint64_t tau, int lane) {
+// ancestor (global particle index) of threshold tau < Q by one warp: tile index, then the tile's local CDF
+__device__ __forceinline__ int locate_pos(const StepIndex& ix, const unsigned long long* __restrict__ cl, int N, uint64_t tau,
+                                          int lane, int& tile_out) {
   int T = warp_count_le(ix.tile_incl, ix.ntiles, tau, lane);
   if (T > ix.ntiles - 1) T = ix.ntiles - 1;
   const uint64_t rem = tau - __ldg(&ix.tile_excl[T]);
-  const unsigned long long* ce = ix.chunk_excl + (int64_t)T * ix.chunks_per_tile;
-  // chunks c' >= 1 of the tile whose start offset is <= rem come before (or are) the target
-  const int c = warp_count_le(ce + 1, ix.chunks_per_tile - 1, rem, lane);
-  return T * ix.chunks_per_tile + c;
+  const int t0 = T * ix.tile_items;
+  int n = N - t0;
+  if (n > ix.tile_items) n = ix.tile_items;
+  int c = warp_count_le(cl + t0, n, rem, lane);
+  if (c > n - 1) c = n - 1;
+  tile_out = T;
+  return t0 + c;
 }
 
-// One warp per propagate CTA boundary: the chunk its first threshold falls in (4 dependent reads of
-// the L2-resident index).  A separate 5 us launch so that these round trips are not on the critical
-// path of every propagate CTA.
+// One warp per propagate CTA boundary.  A separate launch so that these dependent round trips are
+// not on the critical path of every propagate CTA.
 __global__ void __launch_bounds__(256)
-    bounds_kernel(StepIndex ix, const FilterCtrl* ctrl, int N, int resampler, uint64_t Rw, RngKey key, uint32_t stream, uint32_t t,
-                  int nbounds) {
+    bounds_kernel(StepIndex ix, const unsigned long long* __restrict__ cl, const FilterCtrl* ctrl, int N, int resampler,
+                  uint64_t Rw, RngKey key, uint32_t stream, uint32_t t, int nbounds) {
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (b >= nbounds) return;
   const uint64_t Q = ctrl->total;
   if (Q == 0) return;
-  int i = b * kP2Particles;
+  int64_t i = (int64_t)b * kP2Particles;
   if (i > N - 1) i = N - 1;  // the last boundary is the last particle
   uint64_t u = ctrl->sys_off;
   if (resampler == RESAMPLE_STRATIFIED) u = uniform64_at(key, (uint32_t)i, stream, t, PURPOSE_RESAMPLE);
   const uint64_t tau = threshold_of(resampler, (uint64_t)i, Rw, u, Q);
-  const int c = locate_chunk(ix, tau, lane);
-  if (lane == 0) ix.bound_chunk[b] = c;
+  int T;
+  const int pos = locate_pos(ix, cl, N, tau, lane, T);
+  if (lane == 0) {
+    ix.bound_pos[b] = pos;
+    ix.bound_tile[b] = T;
+  }
 }
 
 __device__ __forceinline__ unsigned long long lds_u64(uint32_t saddr) {
@@ -623,208 +642,231 @@ __device__ __forceinline__ unsigned long long lds_u64(uint32_t saddr) {
   asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(saddr));
   return v;
 }
-
-// #{ j in [0,P) : cdf[j] <= tau } over a shared-memory window padded with ~0 up to the power of two
-// P (<= 4096), branch-free; sbase is the window's address in the shared state space.  Explicit
-// ld.shared: through a generic pointer ptxas re-derives the shared window base on every probe.
-__device__ __forceinline__ int window_count_le(uint32_t sbase, int P, uint64_t tau) {
-  int pos = 0;
-#pragma unroll
-  for (int step = 2048; step > 0; step >>= 1) {
-    if (step < P) {  // block-uniform
-      if (lds_u64(sbase + 8u * (uint32_t)(pos + step - 1)) <= tau) pos += step;
-    }
-  }
-  return pos;  // entry P-1 is a sentinel or the window's last value, both > tau
+template <int BYTE_OFF>
+__device__ __forceinline__ unsigned long long lds_u64_off(uint32_t saddr) {
+  unsigned long long v;
+  asm volatile("ld.shared.u64 %0, [%1+%2];" : "=l"(v) : "r"(saddr), "n"(BYTE_OFF));
+  return v;
 }
 
-template <class Model>
-__global__ void __launch_bounds__(kP2Threads)
-    prop2_kernel(Derived dv, double y, int N, int64_t ld, int resampler, uint64_t Rw, RngKey key, uint32_t stream, uint32_t t,
-                 StepIndex ix, const unsigned long long* __restrict__ qprev, const double* __restrict__ xprev,
-                 double* __restrict__ xnew, double* __restrict__ logw, int32_t* __restrict__ anc_out, FilterCtrl* ctrl) {
+// Shared-state-space address of entry #{ j in [0,kWinCap) : cdf[j] <= tau } of a window padded with
+// ~0 up to kWinCap entries; branch-free, the probe offsets are immediates.  sbase is the window's
+// address in the shared state space (explicit ld.shared: through a generic pointer ptxas re-derives
+// the shared window base on every probe).  Entry kWinCap-1 is a sentinel or the window's last
+// value, both > tau, so it is never probed past.
+template <int STEP>
+__device__ __forceinline__ uint32_t window_search_addr(uint32_t a, uint64_t tau) {
+  if (lds_u64_off<8 * (STEP - 1)>(a) <= tau) a += 8u * STEP;
+  if constexpr (STEP > 1) return window_search_addr<STEP / 2>(a, tau);
+  else return a;
+}
+__device__ __forceinline__ int window_count_le(uint32_t sbase, uint64_t tau) {
+  return (int)((window_search_addr<kWinCap / 2>(sbase, tau) - sbase) >> 3);
+}
+
+// s_cdf[0..kWinCap) <- global CDF entries [s0, s0+len) (tile-local values + tile offsets), ~0 beyond; s0 even.
+__device__ __forceinline__ void stage_window(unsigned long long* s_cdf, const StepIndex& ix,
+                                            const unsigned long long* __restrict__ cl, int s0, int len, int T, int tid) {
+  const int end = s0 + len;
+  // sentinel padding [len rounded down to even, kWinCap)
+  for (int j = (len & ~1) + 2 * tid; j < kWinCap; j += 2 * kP2Threads)
+    *reinterpret_cast<ulonglong2*>(&s_cdf[j]) = make_ulonglong2(~0ull, ~0ull);
+  int tlo = s0;
+  while (tlo < end) {
+    const int tend_full = (T + 1) * ix.tile_items;
+    const int thi = tend_full < end ? tend_full : end;
+    const unsigned long long base = __ldg(&ix.tile_excl[T]);
+    for (int j = tlo + 2 * tid; j < thi; j += 2 * kP2Threads) {  // tlo even, tile_items even
+      const ulonglong2 v = __ldcs(reinterpret_cast<const ulonglong2*>(cl + j));
+      ulonglong2 o;
+      o.x = v.x + base;
+      o.y = (j + 1 < thi) ? v.y + base : ~0ull;
+      *reinterpret_cast<ulonglong2*>(&s_cdf[j - s0]) = o;
+    }
+    tlo = thi;
+    ++T;
+  }
+}
+
+template <class Model, int RESAMPLER>
+__global__ void __launch_bounds__(kP2Threads, 8)
+    prop2_kernel(Derived dv, double y, int N, int64_t ld, uint64_t Rw, RngKey key, uint32_t stream, uint32_t t, StepIndex ix,
+                 const unsigned long long* __restrict__ cl, const double* __restrict__ xprev, double* __restrict__ xnew,
+                 double* __restrict__ logw, int32_t* __restrict__ anc_out, FilterCtrl* ctrl) {
   constexpr int D = Model::D;
   constexpr int NW = kP2Threads / 32;
-  __shared__ __align__(16) unsigned long long s_cdf[kSegChunks * kChunk];
+  __shared__ __align__(16) unsigned long long s_cdf[kWinCap];
   __shared__ double sh[32];
   __shared__ unsigned long long s_min[NW];
-  __shared__ int s_next;
+  __shared__ int s_next[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(s_cdf);
+  uint32_t sbase;
+  asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"((uint32_t)__cvta_generic_to_shared(s_cdf)));  // opaque: kept in a register, not re-derived
   Model mdl;
   mdl.load(dv.d);
   const uint64_t Q = ctrl->total;
-  const uint64_t sys_off = ctrl->sys_off;
-  const int npairs = (N + 1) >> 1;
-  const int pair0 = blockIdx.x * (kP2Threads * kP2Pairs);
-  const int nchunks_total = (N + kChunk - 1) / kChunk;
+  const int i0 = blockIdx.x * kP2Particles + tid * kP2Per;  // first particle of this thread (multiple of 8)
 
-  uint64_t tau0[kP2Pairs], tau1[kP2Pairs];
-  int a0[kP2Pairs], a1[kP2Pairs];
-  bool open0[kP2Pairs], open1[kP2Pairs];
-  int cs = 0, c_hi = 0;
-  if (Q != 0) {
-    cs = __ldg(&ix.bound_chunk[blockIdx.x]);
-    c_hi = __ldg(&ix.bound_chunk[blockIdx.x + 1]);  // chunk of the next CTA's first threshold >= my last one
-  }
+  int anc[kP2Per];
 #pragma unroll
-  for (int r = 0; r < kP2Pairs; ++r) {
-    const int p = pair0 + r * kP2Threads + tid;
-    const int i = 2 * p;
-    a0[r] = i;
-    a1[r] = i + 1;
-    open0[r] = (Q != 0) && (i < N);
-    open1[r] = (Q != 0) && (i + 1 < N);
-    tau0[r] = tau1[r] = 0;
-    if (open0[r]) {
-      uint64_t ua = sys_off, ub = sys_off;
-      if (resampler == RESAMPLE_STRATIFIED) {
-        const Philox4 b = philox4x32_10((uint32_t)p, stream, t, purpose_word(PURPOSE_RESAMPLE, 0, key.epoch), key.k0, key.k1);
-        ua = uniform64_of(b, 0);
-        ub = uniform64_of(b, 1);
-      }
-      tau0[r] = threshold_of(resampler, (uint64_t)i, Rw, ua, Q);
-      tau1[r] = threshold_of(resampler, (uint64_t)i + 1, Rw, ub, Q);
-    }
-  }
+  for (int k = 0; k < kP2Per; ++k) anc[k] = (i0 + k < N) ? i0 + k : N - 1;
 
-  // rebuild the CDF window chunk by chunk from q (every warp owns whole chunks: no cross-warp dependency)
-  while (Q != 0) {
-    int nseg = c_hi - cs + 1;
-    if (nseg > kSegChunks) nseg = kSegChunks;
-    if (nseg < 1) nseg = 1;
-    int pchunks = 1;
-    while (pchunks < nseg) pchunks <<= 1;
-    for (int cc = warp; cc < pchunks; cc += NW) {
-      ulonglong2* dst = reinterpret_cast<ulonglong2*>(&s_cdf[cc * kChunk + lane * 4]);
-      if (cc >= nseg) {  // sentinel padding up to the power of two
-        dst[0] = make_ulonglong2(~0ull, ~0ull);
-        dst[1] = make_ulonglong2(~0ull, ~0ull);
-        continue;
+  if (Q != 0) {
+    // thresholds of the thread's particles (SPEC §5): tau_i = hi64(F_i Q)
+    uint64_t tau[kP2Per];
+    if (RESAMPLER == RESAMPLE_SYSTEMATIC) {
+      // F_i = i R + u; F_{i+1} Q = F_i Q + R Q, carried as a 128-bit value
+      const uint64_t F0 = (uint64_t)i0 * Rw + ctrl->sys_off;
+      uint64_t plo = F0 * Q, phi = mulhi64(F0, Q);
+      const uint64_t dlo = Rw * Q, dhi = mulhi64(Rw, Q);
+#pragma unroll
+      for (int k = 0; k < kP2Per; ++k) {
+        tau[k] = phi;
+        const uint64_t nlo = plo + dlo;
+        phi += dhi + (nlo < plo ? 1ull : 0ull);
+        plo = nlo;
       }
-      const int c = cs + cc;
-      const int item0 = c * kChunk + lane * 4;
-      unsigned long long q[4] = {0, 0, 0, 0};
-      if (item0 + 4 <= N) {
-        const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2*>(qprev + item0));
-        const ulonglong2 b = __ldg(reinterpret_cast<const ulonglong2*>(qprev + item0 + 2));
-        q[0] = a.x; q[1] = a.y; q[2] = b.x; q[3] = b.y;
+    } else {
+#pragma unroll
+      for (int r = 0; r < kP2Per / 2; ++r) {
+        const int i = i0 + 2 * r;
+        const Philox4 b = philox4x32_10((uint32_t)(i >> 1), stream, t, purpose_word(PURPOSE_RESAMPLE, 0, key.epoch), key.k0, key.k1);
+        tau[2 * r] = threshold_of(RESAMPLER, (uint64_t)i, Rw, uniform64_of(b, 0), Q);
+        tau[2 * r + 1] = threshold_of(RESAMPLER, (uint64_t)i + 1, Rw, uniform64_of(b, 1), Q);
+      }
+    }
+    const int a_lo = __ldg(&ix.bound_pos[blockIdx.x]);
+    const int a_hi = __ldg(&ix.bound_pos[blockIdx.x + 1]);  // ancestor of the next CTA's first particle >= all of mine
+    int T0 = __ldg(&ix.bound_tile[blockIdx.x]);
+    int s0 = a_lo & ~1;
+    if (a_hi - s0 + 1 <= kWinCap) {
+      // ---- common case: the whole window fits one pass.  C[a_hi] > every tau of this CTA, so the
+      // walk below always stops inside the staged entries.
+      stage_window(s_cdf, ix, cl, s0, a_hi - s0 + 1, T0, tid);
+      __syncthreads();
+      uint32_t a = window_search_addr<kWinCap / 2>(sbase, tau[0]);
+      unsigned long long cur = lds_u64(a);
+      anc[0] = s0 + (int)((a - sbase) >> 3);
+      if ((blockIdx.x + 1) * kP2Particles <= N) {  // every particle of the CTA exists: no bounds checks in the walk
+#pragma unroll
+        for (int k = 1; k < kP2Per; ++k) {
+          while (cur <= tau[k]) {
+            a += 8u;
+            cur = lds_u64(a);
+          }
+          anc[k] = s0 + (int)((a - sbase) >> 3);
+        }
+      } else if (i0 < N) {
+#pragma unroll
+        for (int k = 1; k < kP2Per; ++k) {
+          if (i0 + k < N) {
+            while (cur <= tau[k]) {
+              a += 8u;
+              cur = lds_u64(a);
+            }
+          }
+          anc[k] = s0 + (int)((a - sbase) >> 3);
+        }
       } else {
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          if (item0 + k < N) q[k] = qprev[item0 + k];
+        for (int k = 0; k < kP2Per; ++k) anc[k] = N - 1;
       }
-      unsigned long long cbase = 0;
-      if (c < nchunks_total) cbase = __ldg(&ix.tile_excl[c / ix.chunks_per_tile]) + __ldg(&ix.chunk_excl[c]);
-      else cbase = Q;  // past the end: flat at Q, never selected (tau < Q)
-      q[1] += q[0];
-      q[2] += q[1];
-      q[3] += q[2];
-      const unsigned long long winc = warp_scan_u64(q[3], lane);
-      const unsigned long long off = cbase + (winc - q[3]);
-      dst[0] = make_ulonglong2(off + q[0], off + q[1]);
-      dst[1] = make_ulonglong2(off + q[2], off + q[3]);
-    }
-    __syncthreads();
-    const int P = pchunks * kChunk;
-    const int seg_start = cs * kChunk;
-    const unsigned long long c_end = lds_u64(sbase + 8u * (uint32_t)(nseg * kChunk - 1));
-    bool mine_done = true;
-    unsigned long long my_min = ~0ull;
+    } else {
+      // ---- wide window (very uneven weights): pass by pass, each pass starting at the ancestor of
+      // the smallest unresolved threshold; per-particle binary search inside the staged segment
+      int next = 0;  // first unresolved particle of this thread
+      int nvalid = N - i0;
+      nvalid = nvalid < 0 ? 0 : (nvalid > kP2Per ? kP2Per : nvalid);
+      while (true) {
+        int len = a_hi - s0 + 1;
+        const bool final_seg = len <= kWinCap;
+        if (!final_seg) len = kWinCap;
+        stage_window(s_cdf, ix, cl, s0, len, T0, tid);
+        __syncthreads();
+        const unsigned long long c_end = final_seg ? ~0ull : lds_u64(sbase + 8u * (uint32_t)(len - 1));
+        unsigned long long my_min = ~0ull;
 #pragma unroll
-    for (int r = 0; r < kP2Pairs; ++r) {
-      int pos = -1;
-      if (open0[r]) {
-        if (tau0[r] < c_end) {
-          pos = window_count_le(sbase, P, tau0[r]);
-          a0[r] = seg_start + pos;
-          open0[r] = false;
-        } else {
-          mine_done = false;
-          my_min = tau0[r] < my_min ? tau0[r] : my_min;
-        }
-      }
-      if (open1[r]) {
-        if (tau1[r] < c_end) {
-          int pos1;
-          if (pos >= 0) {  // tau1 >= tau0: the neighbour's ancestor is almost always within a few entries
-            pos1 = pos;
-            int probes = 0;
-            while (lds_u64(sbase + 8u * (uint32_t)pos1) <= tau1[r]) {  // ends: tau1 < c_end
-              ++pos1;
-              if (++probes == 4) {
-                pos1 = window_count_le(sbase, P, tau1[r]);
-                break;
-              }
+        for (int k = 0; k < kP2Per; ++k) {
+          if (k >= next && k < nvalid) {
+            if (tau[k] < c_end) {
+              anc[k] = s0 + window_count_le(sbase, tau[k]);
+              next = k + 1;
+            } else if (tau[k] < my_min) {
+              my_min = tau[k];
             }
-          } else {
-            pos1 = window_count_le(sbase, P, tau1[r]);
           }
-          a1[r] = seg_start + pos1;
-          open1[r] = false;
-        } else {
-          mine_done = false;
-          my_min = tau1[r] < my_min ? tau1[r] : my_min;
         }
+        if (__syncthreads_and(next >= nvalid)) break;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const unsigned long long v = __shfl_xor_sync(kFullMask, my_min, o);
+          my_min = v < my_min ? v : my_min;
+        }
+        if (lane == 0) s_min[warp] = my_min;
+        __syncthreads();
+        if (warp == 0) {
+          unsigned long long v = (lane < NW) ? s_min[lane] : ~0ull;
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long w = __shfl_xor_sync(kFullMask, v, o);
+            v = w < v ? w : v;
+          }
+          int T;
+          const int p = locate_pos(ix, cl, N, v, lane, T);
+          if (lane == 0) {
+            s_next[0] = p;
+            s_next[1] = T;
+          }
+        }
+        __syncthreads();
+        s0 = s_next[0] & ~1;
+        T0 = s_next[1];
+        if (s0 / ix.tile_items != T0) T0 = s0 / ix.tile_items;  // rounding down to even never leaves the tile (tile_items even)
       }
     }
-    if (__syncthreads_and(mine_done)) break;
-    // rare: the window is wider than one pass (very uneven weights) — jump to the chunk that
-    // holds the smallest unresolved threshold
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const unsigned long long v = __shfl_xor_sync(kFullMask, my_min, o);
-      my_min = v < my_min ? v : my_min;
-    }
-    if (lane == 0) s_min[warp] = my_min;
-    __syncthreads();
-    if (warp == 0) {
-      unsigned long long v = (lane < NW) ? s_min[lane] : ~0ull;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long w = __shfl_xor_sync(kFullMask, v, o);
-        v = w < v ? w : v;
-      }
-      const int c = locate_chunk(ix, v, lane);
-      if (lane == 0) s_next = c;
-    }
-    __syncthreads();
-    cs = s_next;
   }
 
   double vmax = -INFINITY;
+  if (i0 < N) {
+    double xp[kP2Per][D];
+    if (D == 1) {  // parents first: the loads fly while the normals are drawn
 #pragma unroll
-  for (int r = 0; r < kP2Pairs; ++r) {
-    const int p = pair0 + r * kP2Threads + tid;
-    if (p >= npairs) continue;
-    const int i = 2 * p;
-    const bool two = (i + 1 < N);
-    double za[D], zb[D], xpa[D], xpb[D], xa[D], xb[D];
-#pragma unroll
-    for (int k = 0; k < D; ++k) {  // parents first: the loads fly while the normals are drawn
-      xpa[k] = __ldg(&xprev[k * ld + a0[r]]);
-      xpb[k] = two ? __ldg(&xprev[k * ld + a1[r]]) : xpa[k];
+      for (int k = 0; k < kP2Per; ++k) xp[k][0] = __ldg(&xprev[anc[k]]);
     }
 #pragma unroll
-    for (int k = 0; k < D; ++k) normal_pair_at(key, (uint32_t)p, stream, t, PURPOSE_TRANSITION, (uint32_t)k, za[k], zb[k]);
-    mdl.transition(za, xpa, xa);
-    mdl.transition(zb, xpb, xb);
-    const double la = mdl.logweight(xa, y);
-    const double lb = mdl.logweight(xb, y);
-    if (two) {
+    for (int r = 0; r < kP2Per / 2; ++r) {
+      const int i = i0 + 2 * r;
+      if (i >= N) break;
+      const bool two = (i + 1 < N);
+      double za[D], zb[D], xa[D], xb[D];
+      if (D > 1) {
 #pragma unroll
-      for (int k = 0; k < D; ++k) *reinterpret_cast<double2*>(xnew + k * ld + i) = make_double2(xa[k], xb[k]);
-      *reinterpret_cast<double2*>(logw + i) = make_double2(la, lb);
-      if (anc_out) *reinterpret_cast<int2*>(anc_out + i) = make_int2(a0[r], a1[r]);
-      if (la > vmax) vmax = la;
-      if (lb > vmax) vmax = lb;
-    } else {
+        for (int c = 0; c < D; ++c) {
+          xp[2 * r][c] = __ldg(&xprev[c * ld + anc[2 * r]]);
+          xp[2 * r + 1][c] = __ldg(&xprev[c * ld + anc[2 * r + 1]]);
+        }
+      }
 #pragma unroll
-      for (int k = 0; k < D; ++k) xnew[k * ld + i] = xa[k];
-      logw[i] = la;
-      if (anc_out) anc_out[i] = a0[r];
-      if (la > vmax) vmax = la;
+      for (int c = 0; c < D; ++c) normal_pair_at(key, (uint32_t)(i >> 1), stream, t, PURPOSE_TRANSITION, (uint32_t)c, za[c], zb[c]);
+      mdl.transition(za, xp[2 * r], xa);
+      mdl.transition(zb, xp[2 * r + 1], xb);
+      const double la = mdl.logweight(xa, y);
+      const double lb = mdl.logweight(xb, y);
+      if (two) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) *reinterpret_cast<double2*>(xnew + c * ld + i) = make_double2(xa[c], xb[c]);
+        *reinterpret_cast<double2*>(logw + i) = make_double2(la, lb);
+        if (anc_out) *reinterpret_cast<int2*>(anc_out + i) = make_int2(anc[2 * r], anc[2 * r + 1]);
+        if (la > vmax) vmax = la;
+        if (lb > vmax) vmax = lb;
+      } else {
+#pragma unroll
+        for (int c = 0; c < D; ++c) xnew[c * ld + i] = xa[c];
+        logw[i] = la;
+        if (anc_out) anc_out[i] = anc[2 * r];
+        if (la > vmax) vmax = la;
+      }
     }
   }
   const double bm = block_max(vmax, sh);
@@ -889,8 +931,8 @@ SingleFilter::~SingleFilter() {
 void SingleFilter::release() {
   cudaFree(x_[0]); cudaFree(x_[1]); cudaFree(logw_[0]); cudaFree(logw_[1]); cudaFree(w_tmp_); cudaFree(cdf_); cudaFree(anc_);
   cudaFree(ctrl_); cudaFree(desc_); cudaFree(psum_); cudaFree(psum2_); cudaFree(stats_dev_);
-  cudaFree(chunk_excl_); cudaFree(tile_arrays_); cudaFree(bound_chunk_);
-  chunk_excl_ = tile_arrays_ = nullptr; bound_chunk_ = nullptr; chunk_cap_ = bound_cap_ = 0;
+  cudaFree(tile_arrays_); cudaFree(bound_arrays_);
+  tile_arrays_ = nullptr; bound_arrays_ = nullptr; bound_cap_ = 0;
   x_[0] = x_[1] = logw_[0] = logw_[1] = w_tmp_ = psum_ = psum2_ = nullptr;
   cdf_ = nullptr; anc_ = nullptr; ctrl_ = nullptr; desc_ = nullptr; stats_dev_ = nullptr;
   cap_N_ = cap_d_ = cap_stats_ = cap_anc_rows_ = ntiles_cap_ = 0;
@@ -911,8 +953,9 @@ void SingleFilter::ensure_capacity(int kind, int64_t N, int64_t anc_rows) {
     SMCB_CUDA_TRY(cudaMalloc(&logw_[1], sizeof(double) * ld));
     ntiles_cap_ = (ld + kScanTile - 1) / kScanTile;
     SMCB_CUDA_TRY(cudaMalloc(&desc_, sizeof(unsigned long long) * 2 * ntiles_cap_));
-    SMCB_CUDA_TRY(cudaMalloc(&psum_, sizeof(double) * ntiles_cap_));
-    SMCB_CUDA_TRY(cudaMalloc(&psum2_, sizeof(double) * ntiles_cap_));
+    const int64_t npart = std::max<int64_t>(ntiles_cap_, kMaxTiles);  // per-tile partial sums of either scan flavour
+    SMCB_CUDA_TRY(cudaMalloc(&psum_, sizeof(double) * npart));
+    SMCB_CUDA_TRY(cudaMalloc(&psum2_, sizeof(double) * npart));
     cap_N_ = ld;
     cap_d_ = cd;
     cudaFree(anc_); anc_ = nullptr; cap_anc_rows_ = 0;
@@ -920,20 +963,17 @@ void SingleFilter::ensure_capacity(int kind, int64_t N, int64_t anc_rows) {
   if (!ctrl_) SMCB_CUDA_TRY(cudaMalloc(&ctrl_, sizeof(FilterCtrl)));
   if (!tile_arrays_) SMCB_CUDA_TRY(cudaMalloc(&tile_arrays_, sizeof(unsigned long long) * 3 * kMaxTiles));
   {
-    const int64_t nunit = (cap_N_ + kTileUnit - 1) / kTileUnit;
-    const int64_t k = (nunit + kMaxTiles - 1) / kMaxTiles;
-    const int64_t chunks = ((cap_N_ + kTileUnit * k - 1) / (kTileUnit * k)) * kChunksPerUnit * k;
-    const int64_t nb = (cap_N_ / 2 + kP2Threads * kP2Pairs) / (kP2Threads * kP2Pairs) + 2;
+    const int64_t nb = cap_N_ / kP2Particles + 3;
     if (nb > bound_cap_) {
-      cudaFree(bound_chunk_); bound_chunk_ = nullptr; bound_cap_ = 0;
-      SMCB_CUDA_TRY(cudaMalloc(&bound_chunk_, sizeof(int32_t) * nb));
+      cudaFree(bound_arrays_); bound_arrays_ = nullptr; bound_cap_ = 0;
+      SMCB_CUDA_TRY(cudaMalloc(&bound_arrays_, sizeof(int32_t) * 2 * nb));
       bound_cap_ = nb;
     }
-    if (chunks > chunk_cap_) {
-      cudaFree(chunk_excl_); chunk_excl_ = nullptr; chunk_cap_ = 0;
-      SMCB_CUDA_TRY(cudaMalloc(&chunk_excl_, sizeof(unsigned long long) * chunks));
-      chunk_cap_ = chunks;
-    }
+  }
+  if (num_sms_ == 0) {
+    int v = 0;
+    SMCB_CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device_));
+    num_sms_ = v > 0 ? v : 148;
   }
   if (anc_rows > cap_anc_rows_ || !anc_) {
     cudaFree(anc_); anc_ = nullptr;
@@ -1047,30 +1087,33 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler) {
     launch_prop(y, resampler);
     return;
   }
-  const int64_t nunit = (N_ + kTileUnit - 1) / kTileUnit;
-  const int64_t k = (nunit + kMaxTiles - 1) / kMaxTiles;
+  // tile geometry: one warp per tile, one full wave of resident warps when N allows, at most kMaxTiles tiles
+  const int64_t nchunks = (N_ + kChunk - 1) / kChunk;
+  const int64_t resident = (int64_t)num_sms_ * kSumCtasPerSm * kSumWarps;
+  int64_t cpt = std::max<int64_t>((nchunks + resident - 1) / resident, (nchunks + kMaxTiles - 1) / kMaxTiles);
+  cpt = std::max<int64_t>(cpt, 1);
   StepIndex ix;
-  ix.tile_items = kTileUnit * k;
-  ix.ntiles = (int)((N_ + ix.tile_items - 1) / ix.tile_items);
-  ix.chunks_per_tile = (int)(kChunksPerUnit * k);
-  ix.chunk_excl = chunk_excl_;
+  ix.chunks_per_tile = (int)cpt;
+  ix.tile_items = (int)(cpt * kChunk);
+  ix.ntiles = (int)((nchunks + cpt - 1) / cpt);
   ix.tile_tot = tile_arrays_;
   ix.tile_excl = tile_arrays_ + kMaxTiles;
   ix.tile_incl = tile_arrays_ + 2 * kMaxTiles;
-  ix.bound_chunk = bound_chunk_;
-  if (!cdf_) SMCB_CUDA_TRY(cudaMalloc(&cdf_, sizeof(uint64_t) * cap_N_));  // holds q here (the CDF on the multinomial path)
-  const int64_t npairs = (N_ + 1) / 2;
-  const unsigned nblocks = (unsigned)((npairs + kP2Threads * kP2Pairs - 1) / (kP2Threads * kP2Pairs));
+  ix.bound_pos = bound_arrays_;
+  ix.bound_tile = bound_arrays_ + bound_cap_;
+  if (!cdf_) SMCB_CUDA_TRY(cudaMalloc(&cdf_, sizeof(uint64_t) * cap_N_));  // holds the tile-local CDF here (the global CDF on the multinomial path)
+  unsigned long long* cl = reinterpret_cast<unsigned long long*>(cdf_);
+  const unsigned nblocks = (unsigned)((N_ + kP2Particles - 1) / kP2Particles);
   const uint32_t t = t_ + 1;
   mark(TK_SCAN, true);
-  sum_kernel<<<(ix.ntiles + kSumWarps - 1) / kSumWarps, kSumThreads, 0, stream_>>>(logw_[cur_], reinterpret_cast<unsigned long long*>(cdf_), N_, S_, ctrl_, ix, psum_,
-                                                     psum2_, stats_dev_ + stat_index, (int)(t_ & 1u), resampler, R_, key_,
-                                                     stream_id_, t);
+  sum_kernel<<<(ix.ntiles + kSumWarps - 1) / kSumWarps, kSumThreads, 0, stream_>>>(logw_[cur_], cl, N_, S_, ctrl_, ix, psum_, psum2_,
+                                                                                  stats_dev_ + stat_index, (int)(t_ & 1u), resampler,
+                                                                                  R_, key_, stream_id_, t);
   mark(TK_SCAN, false);
   SMCB_CUDA_TRY(cudaGetLastError());
   const int nbounds = (int)nblocks + 1;
   mark(TK_BOUNDS, true);
-  bounds_kernel<<<(nbounds + 7) / 8, 256, 0, stream_>>>(ix, ctrl_, (int)N_, resampler, R_, key_, stream_id_, t, nbounds);
+  bounds_kernel<<<(nbounds + 7) / 8, 256, 0, stream_>>>(ix, cl, ctrl_, (int)N_, resampler, R_, key_, stream_id_, t, nbounds);
   mark(TK_BOUNDS, false);
   SMCB_CUDA_TRY(cudaGetLastError());
   int32_t* anc = nullptr;
@@ -1082,9 +1125,12 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler) {
   mark(TK_PROP, true);
   dispatch_model(kind_, [&](auto m) {
     using M = decltype(m);
-    prop2_kernel<M><<<nblocks, kP2Threads, 0, stream_>>>(dv_, y, (int)N_, ld_, resampler, R_, key_, stream_id_, t, ix,
-                                                         reinterpret_cast<const unsigned long long*>(cdf_), x_[cur_], x_[cur_ ^ 1],
-                                                         logw_[cur_ ^ 1], anc, ctrl_);
+    if (resampler == RESAMPLE_SYSTEMATIC)
+      prop2_kernel<M, RESAMPLE_SYSTEMATIC><<<nblocks, kP2Threads, 0, stream_>>>(dv_, y, (int)N_, ld_, R_, key_, stream_id_, t, ix, cl, x_[cur_],
+                                                                                 x_[cur_ ^ 1], logw_[cur_ ^ 1], anc, ctrl_);
+    else
+      prop2_kernel<M, RESAMPLE_STRATIFIED><<<nblocks, kP2Threads, 0, stream_>>>(dv_, y, (int)N_, ld_, R_, key_, stream_id_, t, ix, cl, x_[cur_],
+                                                                                 x_[cur_ ^ 1], logw_[cur_ ^ 1], anc, ctrl_);
   });
   mark(TK_PROP, false);
   SMCB_CUDA_TRY(cudaGetLastError());

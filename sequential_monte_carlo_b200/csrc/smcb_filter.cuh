@@ -97,11 +97,11 @@ class SingleFilter {
   int32_t* anc_ = nullptr;
   FilterCtrl* ctrl_ = nullptr;
   unsigned long long* desc_ = nullptr;  // [2][ntiles_cap]
-  // chunk/tile index of the sorted-resampler step (sum -> bounds -> prop2)
-  unsigned long long* chunk_excl_ = nullptr;
+  // tile index of the sorted-resampler step (sum -> bounds -> prop2)
   unsigned long long* tile_arrays_ = nullptr;  // [3][kMaxTiles]: tot, excl, incl
-  int32_t* bound_chunk_ = nullptr;
-  int64_t chunk_cap_ = 0, bound_cap_ = 0;
+  int32_t* bound_arrays_ = nullptr;            // [2][bound_cap_]: ancestor of each propagate CTA's first particle, its tile
+  int64_t bound_cap_ = 0;
+  int num_sms_ = 0;
   double* psum_ = nullptr;
   double* psum2_ = nullptr;
   StepStats* stats_dev_ = nullptr;
