@@ -62,6 +62,7 @@ __global__ void reset_ctrl_kernel(FilterCtrl* ctrl) {
   ctrl->maxslot[1] = encode_ordered(-INFINITY);
   ctrl->total = 0;
   ctrl->sys_off = 0;
+  ctrl->rq_lo = ctrl->rq_hi = 0;
   ctrl->scan_ticket = 0;
   ctrl->scan_done = 0;
 }
@@ -432,7 +433,8 @@ constexpr int kChunk = 128;                            // particles per warp tri
 constexpr int kSumThreads = 256;                       // 8 warps, one tile per warp, no block barrier in the main loop
 constexpr int kSumWarps = kSumThreads / 32;
 constexpr int kSumCtasPerSm = 4;
-constexpr int kMaxTiles = 8192;                        // tile totals scanned by the last CTA of sum_kernel
+constexpr int kMaxTiles = 8192;                        // tiles of one step (one warp each)
+constexpr int kMaxSumCtas = kMaxTiles / kSumWarps;     // CTA totals scanned by the last CTA of sum_kernel
 constexpr int kP2Threads = 128;
 constexpr int kP2Per = 8;                              // consecutive particles per thread
 constexpr int kP2Particles = kP2Threads * kP2Per;      // 1024 particles per CTA
@@ -440,6 +442,8 @@ constexpr int kWinCap = 2048;                          // CDF entries staged per
 
 struct StepIndex {
   unsigned long long* tile_tot;   // [ntiles]
+  unsigned long long* tile_lexcl; // [ntiles] exclusive prefix of the tile inside its sum_kernel CTA (8 tiles)
+  unsigned long long* cta_tot;    // [ntiles / 8] total of each sum_kernel CTA
   unsigned long long* tile_excl;  // [ntiles] global exclusive prefix of the tile
   unsigned long long* tile_incl;  // [ntiles]
   int32_t* bound_pos;             // [nblocks + 1] ancestor of each propagate CTA's first particle (last: of particle N-1)
@@ -455,6 +459,7 @@ __global__ void __launch_bounds__(kSumThreads, kSumCtasPerSm)
                RngKey key, uint32_t stream, uint32_t t) {
   __shared__ double s_we[kSumWarps], s_we2[kSumWarps];
   __shared__ unsigned long long s_scan[kSumWarps];
+  __shared__ unsigned long long s_cta_excl[kMaxSumCtas];
   __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x * kSumWarps + warp;
@@ -517,34 +522,60 @@ __global__ void __launch_bounds__(kSumThreads, kSumCtasPerSm)
     se = warp_sum(se);
     se2 = warp_sum(se2);
     if (lane == 0) {
-      psum[tile] = se;
-      psum2[tile] = se2;
-      ix.tile_tot[tile] = running;
+      s_we[warp] = se;
+      s_we2[warp] = se2;
+      s_scan[warp] = running;
     }
+  } else if (lane == 0) {
+    s_we[warp] = 0.0;
+    s_we2[warp] = 0.0;
+    s_scan[warp] = 0ull;
   }
   __syncthreads();
   if (tid == 0) {
+    // the CTA's 8 consecutive tiles: CTA-local exclusive prefixes and one total per CTA, so that the
+    // last CTA only has to scan gridDim.x (<= 1024) values; Σe, Σe² in a fixed order (deterministic)
+    unsigned long long acc = 0;
+    double a = 0.0, b = 0.0;
+#pragma unroll
+    for (int w = 0; w < kSumWarps; ++w) {
+      const int tl = blockIdx.x * kSumWarps + w;
+      if (tl < ix.ntiles) {
+        ix.tile_lexcl[tl] = acc;
+        ix.tile_tot[tl] = s_scan[w];
+      }
+      acc += s_scan[w];
+      a += s_we[w];
+      b += s_we2[w];
+    }
+    ix.cta_tot[blockIdx.x] = acc;
+    psum[blockIdx.x] = a;
+    psum2[blockIdx.x] = b;
     __threadfence();
     s_last = (atomicAdd(&ctrl->scan_done, 1u) == gridDim.x - 1);
   }
   __syncthreads();
   if (!s_last) return;
-  // ---- last CTA out: Σe, Σe² in a fixed order (deterministic), scan of the tile totals, Q, systematic offset
-  constexpr int PER = kMaxTiles / kSumThreads;  // 32 contiguous tiles per thread
+  // ---- last CTA out: scan of the CTA totals, global tile offsets, Q, systematic offset, Σe, Σe²
+  constexpr int PER = kMaxSumCtas / kSumThreads;  // 4 contiguous CTA totals per thread
+  const int nctas = (int)gridDim.x;
   double a = 0.0, b = 0.0;
-  unsigned long long run = 0;
-#pragma unroll 8
+  unsigned long long cv[PER], run = 0;
+#pragma unroll
   for (int k = 0; k < PER; ++k) {
     const int j = tid * PER + k;
-    if (j < ix.ntiles) {
+    cv[k] = 0;
+    if (j < nctas) {
       a += __ldcg(&psum[j]);
       b += __ldcg(&psum2[j]);
-      run += __ldcg(&ix.tile_tot[j]);
+      cv[k] = __ldcg(&ix.cta_tot[j]);
     }
+    run += cv[k];
   }
   a = warp_sum(a);
   b = warp_sum(b);
   const unsigned long long winc = warp_scan_u64(run, lane);
+  __syncthreads();  // s_we / s_scan are reused
   if (lane == 0) {
     s_we[warp] = a;
     s_we2[warp] = b;
@@ -556,15 +587,17 @@ __global__ void __launch_bounds__(kSumThreads, kSumCtasPerSm)
   const unsigned long long wexcl = __shfl_sync(kFullMask, wvinc - wv, warp);
   const unsigned long long Q = __shfl_sync(kFullMask, wvinc, kSumWarps - 1);
   unsigned long long acc = wexcl + (winc - run);
-#pragma unroll 8
+#pragma unroll
   for (int k = 0; k < PER; ++k) {
-    const int j = tid * PER + k;
-    if (j < ix.ntiles) {
-      const unsigned long long v = __ldcg(&ix.tile_tot[j]);
-      ix.tile_excl[j] = acc;
-      acc += v;
-      ix.tile_incl[j] = acc;
-    }
+    s_cta_excl[tid * PER + k] = acc;
+    acc += cv[k];
+  }
+  __syncthreads();
+  for (int j = tid; j < ix.ntiles; j += kSumThreads) {  // independent, coalesced
+    const unsigned long long ex = s_cta_excl[j / kSumWarps] + __ldcg(&ix.tile_lexcl[j]);
+    const unsigned long long tot = __ldcg(&ix.tile_tot[j]);
+    ix.tile_excl[j] = ex;
+    ix.tile_incl[j] = ex + tot;
   }
   if (warp == 0) {
     double e1 = (lane < kSumWarps) ? s_we[lane] : 0.0, e2 = (lane < kSumWarps) ? s_we2[lane] : 0.0;
@@ -575,6 +608,8 @@ __global__ void __launch_bounds__(kSumThreads, kSumCtasPerSm)
       stats_out->sum = e1;
       stats_out->sum2 = e2;
       ctrl->total = Q;
+      ctrl->rq_lo = Rw * Q;
+      ctrl->rq_hi = mulhi64(Rw, Q);
       ctrl->sys_off = (resampler == RESAMPLE_SYSTEMATIC) ? mulhi64(uniform64_at(key, 0u, stream, t, PURPOSE_RESAMPLE), Rw) : 0ull;
       ctrl->scan_done = 0;
       ctrl->maxslot[slot ^ 1] = encode_ordered(-INFINITY);
@@ -718,14 +753,12 @@ __global__ void __launch_bounds__(kP2Threads, 8)
     if (RESAMPLER == RESAMPLE_SYSTEMATIC) {
       // F_i = i R + u; F_{i+1} Q = F_i Q + R Q, carried as a 128-bit value
       const uint64_t F0 = (uint64_t)i0 * Rw + ctrl->sys_off;
-      uint64_t plo = F0 * Q, phi = mulhi64(F0, Q);
-      const uint64_t dlo = Rw * Q, dhi = mulhi64(Rw, Q);
+      unsigned long long plo = F0 * Q, phi = mulhi64(F0, Q);
+      const unsigned long long dlo = ctrl->rq_lo, dhi = ctrl->rq_hi;  // R Q, written by sum_kernel
 #pragma unroll
       for (int k = 0; k < kP2Per; ++k) {
         tau[k] = phi;
-        const uint64_t nlo = plo + dlo;
-        phi += dhi + (nlo < plo ? 1ull : 0ull);
-        plo = nlo;
+        asm("add.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, %3;" : "+l"(plo), "+l"(phi) : "l"(dlo), "l"(dhi));
       }
     } else {
 #pragma unroll
@@ -961,7 +994,7 @@ void SingleFilter::ensure_capacity(int kind, int64_t N, int64_t anc_rows) {
     cudaFree(anc_); anc_ = nullptr; cap_anc_rows_ = 0;
   }
   if (!ctrl_) SMCB_CUDA_TRY(cudaMalloc(&ctrl_, sizeof(FilterCtrl)));
-  if (!tile_arrays_) SMCB_CUDA_TRY(cudaMalloc(&tile_arrays_, sizeof(unsigned long long) * 3 * kMaxTiles));
+  if (!tile_arrays_) SMCB_CUDA_TRY(cudaMalloc(&tile_arrays_, sizeof(unsigned long long) * 5 * kMaxTiles));
   {
     const int64_t nb = cap_N_ / kP2Particles + 3;
     if (nb > bound_cap_) {
@@ -1099,6 +1132,8 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler) {
   ix.tile_tot = tile_arrays_;
   ix.tile_excl = tile_arrays_ + kMaxTiles;
   ix.tile_incl = tile_arrays_ + 2 * kMaxTiles;
+  ix.tile_lexcl = tile_arrays_ + 3 * kMaxTiles;
+  ix.cta_tot = tile_arrays_ + 4 * kMaxTiles;
   ix.bound_pos = bound_arrays_;
   ix.bound_tile = bound_arrays_ + bound_cap_;
   if (!cdf_) SMCB_CUDA_TRY(cudaMalloc(&cdf_, sizeof(uint64_t) * cap_N_));  // holds the tile-local CDF here (the global CDF on the multinomial path)

@@ -16,6 +16,7 @@ struct FilterCtrl {
   unsigned long long maxslot[2];  // ordered-encoded max(logw), slot = t & 1
   unsigned long long total;       // Q = C[N-1] of the last scan
   unsigned long long sys_off;     // mulhi(U(0), R) of the systematic resampler for the coming step
+  unsigned long long rq_lo, rq_hi;  // R * Q as a 128-bit value: the increment of (i R + u) Q per particle
   unsigned int scan_ticket;       // dynamic tile ids of the look-back scan
   unsigned int scan_done;
 };
@@ -98,7 +99,7 @@ class SingleFilter {
   FilterCtrl* ctrl_ = nullptr;
   unsigned long long* desc_ = nullptr;  // [2][ntiles_cap]
   // tile index of the sorted-resampler step (sum -> bounds -> prop2)
-  unsigned long long* tile_arrays_ = nullptr;  // [3][kMaxTiles]: tot, excl, incl
+  unsigned long long* tile_arrays_ = nullptr;  // [5][kMaxTiles]: tot, excl, incl, lexcl, cta_tot
   int32_t* bound_arrays_ = nullptr;            // [2][bound_cap_]: ancestor of each propagate CTA's first particle, its tile
   int64_t bound_cap_ = 0;
   int num_sms_ = 0;
