@@ -195,7 +195,7 @@ def main():
 
     # ---- per-kernel durations (CUDA events around every launch; same workload, K sweeps)
     ctx.set_profiling(True)
-    kms = {"scan": 0.0, "prop": 0.0, "init": 0.0, "stats": 0.0, "bounds": 0.0}
+    kms = {"scan": 0.0, "prop": 0.0, "init": 0.0, "stats": 0.0, "bounds": 0.0, "anc": 0.0}
     kn = dict.fromkeys(kms, 0)
     for _ in range(max(1, min(args.steps, 2))):
         ctx.log_likelihood(smc.KIND_LG1D, LG_PARAMS, N, y, rs, stream=rank)
@@ -226,7 +226,7 @@ def main():
     e2e = units / wall_e2e_max
     peak, peak_src = measured_peak()
     step_us = {k: (1e3 * kms[k] / kn[k] if kn[k] else None) for k in kms}
-    fused = sum(v for k, v in step_us.items() if k in ("scan", "bounds", "prop") and v)
+    fused = sum(v for k, v in step_us.items() if k in ("scan", "bounds", "anc", "prop") and v)
     achieved = BYTES_PER_UPDATE * N / (fused * 1e-6) / 1e9 if fused else None
 
     line = {

@@ -67,9 +67,10 @@ int smcb_record_ancestors(smcb_ctx* ctx, int enable);
 /* per-kernel CUDA-event timing of the single filter (bench.py roofline); off by default */
 int smcb_set_profiling(smcb_ctx* ctx, int enable);
 /* device time of the last sweep / step, and per-kernel-class totals when profiling is on:
- * ms[0] whole call, ms[1] sum/scan (quantise + prefix sums + Σe, Σe²), ms[2] search+gather+propagate+
- * weight, ms[3] init, ms[4] stats-only, ms[5] bounds; launches[0..5] the matching launch counts. */
-int smcb_get_timing(const smcb_ctx* ctx, double ms[6], int64_t launches[6]);
+ * ms[0] whole call, ms[1] sum/scan (quantise + prefix sums + Σe, Σe²), ms[2] gather+propagate+weight
+ * (plus the ancestor search on the multinomial path), ms[3] init, ms[4] stats-only, ms[5] window bounds,
+ * ms[6] ancestor search of the sorted resamplers; launches[0..6] the matching launch counts. */
+int smcb_get_timing(const smcb_ctx* ctx, double ms[7], int64_t launches[7]);
 int smcb_synchronize(smcb_ctx* ctx);
 /* page-locked host buffers for fast fetches (PCIe D2H at link rate instead of pageable staging);
  * the Python / Julia shims keep one per result array and wrap it as an array view */

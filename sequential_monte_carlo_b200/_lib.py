@@ -213,10 +213,10 @@ class Context:
         self._check(self._lib.smcb_set_profiling(self._h, int(bool(on))))
 
     def timing(self):
-        ms = (C.c_double * 6)()
-        n = (C.c_int64 * 6)()
+        ms = (C.c_double * 7)()
+        n = (C.c_int64 * 7)()
         self._check(self._lib.smcb_get_timing(self._h, ms, n))
-        keys = ("total", "scan", "prop", "init", "stats", "bounds")
+        keys = ("total", "scan", "prop", "init", "stats", "bounds", "anc")
         return {k: float(ms[i]) for i, k in enumerate(keys)}, {k: int(n[i]) for i, k in enumerate(keys)}
 
     def synchronize(self):

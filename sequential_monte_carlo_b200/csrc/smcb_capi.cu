@@ -127,7 +127,7 @@ int smcb_set_profiling(smcb_ctx* ctx, int enable) {
   return SMCB_OK;
 }
 
-int smcb_get_timing(const smcb_ctx* ctx, double ms[6], int64_t launches[6]) {
+int smcb_get_timing(const smcb_ctx* ctx, double ms[7], int64_t launches[7]) {
   if (!ctx || !ms || !launches) return SMCB_ERR_BAD_ARG;
   ctx->filter->timing(ms, launches);
   return SMCB_OK;

@@ -47,6 +47,13 @@ __device__ __forceinline__ double warp_max(double v) {
   }
   return v;
 }
+// max over the warp of ordered-encoded doubles with two 32-bit REDUX instead of five 64-bit shuffle rounds
+__device__ __forceinline__ unsigned long long warp_max_ordered(unsigned long long e) {
+  const unsigned hi = (unsigned)(e >> 32), lo = (unsigned)e;
+  const unsigned mh = __reduce_max_sync(kFullMask, hi);
+  const unsigned ml = __reduce_max_sync(kFullMask, hi == mh ? lo : 0u);
+  return ((unsigned long long)mh << 32) | ml;
+}
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);

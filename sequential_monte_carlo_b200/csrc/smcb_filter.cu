@@ -17,7 +17,9 @@
 // logw' 8 W = 48 B (the ancestor vector is never materialised unless recording is on).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <type_traits>
 
 #include "smcb_filter.cuh"
 
@@ -436,7 +438,8 @@ constexpr int kSumCtasPerSm = 4;
 constexpr int kMaxTiles = 8192;                        // tiles of one step (one warp each)
 constexpr int kMaxSumCtas = kMaxTiles / kSumWarps;     // CTA totals scanned by the last CTA of sum_kernel
 constexpr int kP2Threads = 128;
-constexpr int kP2Per = 8;                              // consecutive particles per thread
+// consecutive particles per thread (9, an odd stride in the shared window, measured slower than 8)
+constexpr int kP2Per = 8;
 constexpr int kP2Particles = kP2Threads * kP2Per;      // 1024 particles per CTA
 constexpr int kWinCap = 2048;                          // CDF entries staged per pass (16 KB)
 
@@ -723,52 +726,30 @@ __device__ __forceinline__ void stage_window(unsigned long long* s_cdf, const St
   }
 }
 
-template <class Model, int RESAMPLER>
-__global__ void __launch_bounds__(kP2Threads, 8)
-    prop2_kernel(Derived dv, double y, int N, int64_t ld, uint64_t Rw, RngKey key, uint32_t stream, uint32_t t, StepIndex ix,
-                 const unsigned long long* __restrict__ cl, const double* __restrict__ xprev, double* __restrict__ xnew,
-                 double* __restrict__ logw, int32_t* __restrict__ anc_out, FilterCtrl* ctrl) {
-  constexpr int D = Model::D;
+// resample (particles.jl:117) for the sorted resamplers: the ancestor of every particle, written as
+// int32.  Model-independent and light in registers, so that many warps hide the dependent
+// shared-memory reads of the search and the walk.  Every thread owns kP2Per CONSECUTIVE particles.
+template <int RESAMPLER>
+__global__ void __launch_bounds__(kP2Threads, 10)
+    anc_kernel(int N, uint64_t Rw, RngKey key, uint32_t stream, uint32_t t, StepIndex ix, const unsigned long long* __restrict__ cl,
+               int32_t* __restrict__ anc_out, const FilterCtrl* __restrict__ ctrl) {
   constexpr int NW = kP2Threads / 32;
   __shared__ __align__(16) unsigned long long s_cdf[kWinCap];
-  __shared__ double sh[32];
   __shared__ unsigned long long s_min[NW];
   __shared__ int s_next[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t sbase;
   asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"((uint32_t)__cvta_generic_to_shared(s_cdf)));  // opaque: kept in a register, not re-derived
-  Model mdl;
-  mdl.load(dv.d);
   const uint64_t Q = ctrl->total;
-  const int i0 = blockIdx.x * kP2Particles + tid * kP2Per;  // first particle of this thread (multiple of 8)
+  const int i0 = blockIdx.x * kP2Particles + tid * kP2Per;  // first particle of this thread
+  const bool full_cta = (blockIdx.x + 1) * kP2Particles <= N;
 
   int anc[kP2Per];
 #pragma unroll
-  for (int k = 0; k < kP2Per; ++k) anc[k] = (i0 + k < N) ? i0 + k : N - 1;
+  for (int k = 0; k < kP2Per; ++k) anc[k] = (i0 + k < N) ? i0 + k : N - 1;  // Q == 0: every particle is its own ancestor (SPEC §5)
 
   if (Q != 0) {
-    // thresholds of the thread's particles (SPEC §5): tau_i = hi64(F_i Q)
-    uint64_t tau[kP2Per];
-    if (RESAMPLER == RESAMPLE_SYSTEMATIC) {
-      // F_i = i R + u; F_{i+1} Q = F_i Q + R Q, carried as a 128-bit value
-      const uint64_t F0 = (uint64_t)i0 * Rw + ctrl->sys_off;
-      unsigned long long plo = F0 * Q, phi = mulhi64(F0, Q);
-      const unsigned long long dlo = ctrl->rq_lo, dhi = ctrl->rq_hi;  // R Q, written by sum_kernel
-#pragma unroll
-      for (int k = 0; k < kP2Per; ++k) {
-        tau[k] = phi;
-        asm("add.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, %3;" : "+l"(plo), "+l"(phi) : "l"(dlo), "l"(dhi));
-      }
-    } else {
-#pragma unroll
-      for (int r = 0; r < kP2Per / 2; ++r) {
-        const int i = i0 + 2 * r;
-        const Philox4 b = philox4x32_10((uint32_t)(i >> 1), stream, t, purpose_word(PURPOSE_RESAMPLE, 0, key.epoch), key.k0, key.k1);
-        tau[2 * r] = threshold_of(RESAMPLER, (uint64_t)i, Rw, uniform64_of(b, 0), Q);
-        tau[2 * r + 1] = threshold_of(RESAMPLER, (uint64_t)i + 1, Rw, uniform64_of(b, 1), Q);
-      }
-    }
     const int a_lo = __ldg(&ix.bound_pos[blockIdx.x]);
     const int a_hi = __ldg(&ix.bound_pos[blockIdx.x + 1]);  // ancestor of the next CTA's first particle >= all of mine
     int T0 = __ldg(&ix.bound_tile[blockIdx.x]);
@@ -777,37 +758,58 @@ __global__ void __launch_bounds__(kP2Threads, 8)
       // ---- common case: the whole window fits one pass.  C[a_hi] > every tau of this CTA, so the
       // walk below always stops inside the staged entries.
       stage_window(s_cdf, ix, cl, s0, a_hi - s0 + 1, T0, tid);
-      __syncthreads();
-      uint32_t a = window_search_addr<kWinCap / 2>(sbase, tau[0]);
-      unsigned long long cur = lds_u64(a);
-      anc[0] = s0 + (int)((a - sbase) >> 3);
-      if ((blockIdx.x + 1) * kP2Particles <= N) {  // every particle of the CTA exists: no bounds checks in the walk
+      // thresholds (SPEC §5): tau_i = hi64(F_i Q); systematic: F_{i+1} Q = F_i Q + R Q as a 128-bit value
+      unsigned long long plo = 0, phi = 0, dlo = 0, dhi = 0;
+      uint64_t tau[kP2Per];
+      if (RESAMPLER == RESAMPLE_SYSTEMATIC) {
+        const uint64_t F0 = (uint64_t)i0 * Rw + ctrl->sys_off;
+        plo = F0 * Q;
+        phi = mulhi64(F0, Q);
+        dlo = ctrl->rq_lo;  // R Q, written by sum_kernel
+        dhi = ctrl->rq_hi;
+      } else {
 #pragma unroll
-        for (int k = 1; k < kP2Per; ++k) {
-          while (cur <= tau[k]) {
-            a += 8u;
-            cur = lds_u64(a);
-          }
-          anc[k] = s0 + (int)((a - sbase) >> 3);
+        for (int k = 0; k < kP2Per; ++k)
+          tau[k] = threshold_of(RESAMPLER, (uint64_t)(i0 + k), Rw, uniform64_at(key, (uint32_t)(i0 + k), stream, t, PURPOSE_RESAMPLE), Q);
+      }
+      auto tau_at = [&](int k) -> uint64_t {
+        if (RESAMPLER == RESAMPLE_SYSTEMATIC) {
+          const uint64_t v = phi;
+          asm("add.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, %3;" : "+l"(plo), "+l"(phi) : "l"(dlo), "l"(dhi));
+          return v;
         }
-      } else if (i0 < N) {
+        return tau[k];
+      };
+      __syncthreads();
+      auto walk = [&](auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        uint32_t a = window_search_addr<kWinCap / 2>(sbase, tau_at(0));
+        unsigned long long cur = lds_u64(a);
+        anc[0] = s0 + (int)((a - sbase) >> 3);
 #pragma unroll
         for (int k = 1; k < kP2Per; ++k) {
-          if (i0 + k < N) {
-            while (cur <= tau[k]) {
+          const uint64_t tk = tau_at(k);
+          if (FULL || i0 + k < N) {
+            while (cur <= tk) {
               a += 8u;
               cur = lds_u64(a);
             }
           }
           anc[k] = s0 + (int)((a - sbase) >> 3);
         }
-      } else {
-#pragma unroll
-        for (int k = 0; k < kP2Per; ++k) anc[k] = N - 1;
-      }
+      };
+      if (full_cta) walk(std::true_type{});
+      else if (i0 < N) walk(std::false_type{});
     } else {
       // ---- wide window (very uneven weights): pass by pass, each pass starting at the ancestor of
       // the smallest unresolved threshold; per-particle binary search inside the staged segment
+      uint64_t tau[kP2Per];
+#pragma unroll
+      for (int k = 0; k < kP2Per; ++k) {
+        uint64_t u = ctrl->sys_off;
+        if (RESAMPLER != RESAMPLE_SYSTEMATIC) u = uniform64_at(key, (uint32_t)(i0 + k), stream, t, PURPOSE_RESAMPLE);
+        tau[k] = threshold_of(RESAMPLER, (uint64_t)(i0 + k), Rw, u, Q);
+      }
       int next = 0;  // first unresolved particle of this thread
       int nvalid = N - i0;
       nvalid = nvalid < 0 ? 0 : (nvalid > kP2Per ? kP2Per : nvalid);
@@ -853,57 +855,110 @@ __global__ void __launch_bounds__(kP2Threads, 8)
           }
         }
         __syncthreads();
-        s0 = s_next[0] & ~1;
+        s0 = s_next[0] & ~1;  // rounding down to even never leaves the tile (tile_items even)
         T0 = s_next[1];
-        if (s0 / ix.tile_items != T0) T0 = s0 / ix.tile_items;  // rounding down to even never leaves the tile (tile_items even)
       }
     }
   }
+  if (full_cta) {
+#pragma unroll
+    for (int q = 0; q < kP2Per / 4; ++q)
+      reinterpret_cast<int4*>(anc_out + i0)[q] = make_int4(anc[4 * q], anc[4 * q + 1], anc[4 * q + 2], anc[4 * q + 3]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < kP2Per; ++k)
+      if (i0 + k < N) anc_out[i0 + k] = anc[k];
+  }
+}
 
-  double vmax = -INFINITY;
-  if (i0 < N) {
-    double xp[kP2Per][D];
-    if (D == 1) {  // parents first: the loads fly while the normals are drawn
+// x_i ~ transition(x[a_i]); logw_i = logpdf(observation(x_i), y)   (particles.jl:119-125): a streaming
+// pass, kMovePairs pairs (4 consecutive particles) per thread for two independent Philox / Box-Muller
+// chains; parents gathered through the (sorted, hence near-coalesced) ancestor vector.
+constexpr int kMoveThreads = 256;
+constexpr int kMovePairs = 1;
+template <class Model, bool FULL>
+__device__ __forceinline__ double move_particles(const Model& mdl, double y, int N, int64_t ld, const RngKey& key, uint32_t stream, uint32_t t,
+                                                 int i0, const int32_t* __restrict__ anc, const double* __restrict__ xprev,
+                                                 double* __restrict__ xnew, double* __restrict__ logw) {
+  constexpr int D = Model::D;
+  constexpr int PER = 2 * kMovePairs;
+  int a[PER];
+  if (FULL) {
 #pragma unroll
-      for (int k = 0; k < kP2Per; ++k) xp[k][0] = __ldg(&xprev[anc[k]]);
+    for (int q = 0; q < PER / 2; ++q) {
+      const int2 v = __ldcs(reinterpret_cast<const int2*>(anc + i0) + q);
+      a[2 * q] = v.x; a[2 * q + 1] = v.y;
     }
+  } else {
 #pragma unroll
-    for (int r = 0; r < kP2Per / 2; ++r) {
-      const int i = i0 + 2 * r;
-      if (i >= N) break;
-      const bool two = (i + 1 < N);
-      double za[D], zb[D], xa[D], xb[D];
-      if (D > 1) {
+    for (int k = 0; k < PER; ++k) a[k] = (i0 + k < N) ? anc[i0 + k] : 0;
+  }
+  double xp[PER][D];
+  if (D == 1) {  // all parents requested before the first normal is drawn
 #pragma unroll
-        for (int c = 0; c < D; ++c) {
-          xp[2 * r][c] = __ldg(&xprev[c * ld + anc[2 * r]]);
-          xp[2 * r + 1][c] = __ldg(&xprev[c * ld + anc[2 * r + 1]]);
-        }
+    for (int k = 0; k < PER; ++k) xp[k][0] = __ldg(&xprev[a[k]]);
+  }
+  double vmax = -INFINITY;
+#pragma unroll
+  for (int r = 0; r < kMovePairs; ++r) {
+    const int i = i0 + 2 * r;
+    if (!FULL && i >= N) break;
+    if (D > 1) {
+#pragma unroll
+      for (int c = 0; c < D; ++c) {
+        xp[2 * r][c] = __ldg(&xprev[c * ld + a[2 * r]]);
+        xp[2 * r + 1][c] = __ldg(&xprev[c * ld + a[2 * r + 1]]);
       }
+    }
+    double za[D], zb[D], xa[D], xb[D];
 #pragma unroll
-      for (int c = 0; c < D; ++c) normal_pair_at(key, (uint32_t)(i >> 1), stream, t, PURPOSE_TRANSITION, (uint32_t)c, za[c], zb[c]);
-      mdl.transition(za, xp[2 * r], xa);
-      mdl.transition(zb, xp[2 * r + 1], xb);
-      const double la = mdl.logweight(xa, y);
-      const double lb = mdl.logweight(xb, y);
-      if (two) {
+    for (int c = 0; c < D; ++c) normal_pair_at(key, (uint32_t)(i >> 1), stream, t, PURPOSE_TRANSITION, (uint32_t)c, za[c], zb[c]);
+    mdl.transition(za, xp[2 * r], xa);
+    mdl.transition(zb, xp[2 * r + 1], xb);
+    const double la = mdl.logweight(xa, y);
+    const double lb = mdl.logweight(xb, y);
+    if (FULL || i + 1 < N) {
 #pragma unroll
-        for (int c = 0; c < D; ++c) *reinterpret_cast<double2*>(xnew + c * ld + i) = make_double2(xa[c], xb[c]);
-        *reinterpret_cast<double2*>(logw + i) = make_double2(la, lb);
-        if (anc_out) *reinterpret_cast<int2*>(anc_out + i) = make_int2(anc[2 * r], anc[2 * r + 1]);
-        if (la > vmax) vmax = la;
-        if (lb > vmax) vmax = lb;
-      } else {
+      for (int c = 0; c < D; ++c) *reinterpret_cast<double2*>(xnew + c * ld + i) = make_double2(xa[c], xb[c]);
+      *reinterpret_cast<double2*>(logw + i) = make_double2(la, lb);
+      if (la > vmax) vmax = la;  // `>` ignores NaN like the CPU loop
+      if (lb > vmax) vmax = lb;
+    } else {
 #pragma unroll
-        for (int c = 0; c < D; ++c) xnew[c * ld + i] = xa[c];
-        logw[i] = la;
-        if (anc_out) anc_out[i] = anc[2 * r];
-        if (la > vmax) vmax = la;
-      }
+      for (int c = 0; c < D; ++c) xnew[c * ld + i] = xa[c];
+      logw[i] = la;
+      if (la > vmax) vmax = la;
     }
   }
-  const double bm = block_max(vmax, sh);
-  if (tid == 0) atomicMax(&ctrl->maxslot[t & 1u], encode_ordered(bm));
+  return vmax;
+}
+
+template <class Model>
+__global__ void __launch_bounds__(kMoveThreads, (Model::D == 1) ? 6 : 4)
+    move_kernel(Derived dv, double y, int N, int64_t ld, RngKey key, uint32_t stream, uint32_t t, const int32_t* __restrict__ anc,
+                const double* __restrict__ xprev, double* __restrict__ xnew, double* __restrict__ logw, FilterCtrl* ctrl) {
+  constexpr int PER = 2 * kMovePairs;
+  constexpr int NW = kMoveThreads / 32;
+  __shared__ unsigned long long s_max[NW];
+  const int tid = threadIdx.x;
+  Model mdl;
+  mdl.load(dv.d);
+  const int i0 = (blockIdx.x * kMoveThreads + tid) * PER;
+  double vmax;
+  if ((blockIdx.x + 1) * (kMoveThreads * PER) <= N)
+    vmax = move_particles<Model, true>(mdl, y, N, ld, key, stream, t, i0, anc, xprev, xnew, logw);
+  else
+    vmax = move_particles<Model, false>(mdl, y, N, ld, key, stream, t, i0, anc, xprev, xnew, logw);
+  // exact max(logw) for the next normalize(): ordered encoding, REDUX per warp, one atomic per CTA
+  const unsigned long long wm = warp_max_ordered(encode_ordered(vmax));
+  if ((tid & 31) == 0) s_max[tid >> 5] = wm;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long m = s_max[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) m = s_max[w] > m ? s_max[w] : m;
+    atomicMax(&ctrl->maxslot[t & 1u], m);
+  }
 }
 
 // w_i = exp(logw_i - max) / Σe   (normalize, particles.jl:11) — only when the caller fetches w
@@ -1049,7 +1104,7 @@ void SingleFilter::end_call() {
     SMCB_CUDA_TRY(cudaEventElapsedTime(&ms, ev_pool_[m.e0], ev_pool_[m.e1]));
     ms_[m.klass] += ms;
   }
-  launches_[TK_TOTAL] = launches_[TK_SCAN] + launches_[TK_PROP] + launches_[TK_INIT] + launches_[TK_STATS] + launches_[TK_BOUNDS];
+  launches_[TK_TOTAL] = launches_[TK_SCAN] + launches_[TK_PROP] + launches_[TK_INIT] + launches_[TK_STATS] + launches_[TK_BOUNDS] + launches_[TK_ANC];
 }
 
 void SingleFilter::timing(double ms[TK_COUNT], int64_t launches[TK_COUNT]) const {
@@ -1151,21 +1206,25 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler) {
   bounds_kernel<<<(nbounds + 7) / 8, 256, 0, stream_>>>(ix, cl, ctrl_, (int)N_, resampler, R_, key_, stream_id_, t, nbounds);
   mark(TK_BOUNDS, false);
   SMCB_CUDA_TRY(cudaGetLastError());
-  int32_t* anc = nullptr;
+  int32_t* anc = anc_;  // row 0 doubles as the scratch ancestor vector when nothing is recorded
   if (record_anc_) {
     const int64_t row = std::min<int64_t>(anc_rows_, cap_anc_rows_ - 1);
     anc = anc_ + row * cap_N_;
     anc_rows_ = row + 1;
   }
+  mark(TK_ANC, true);
+  if (resampler == RESAMPLE_SYSTEMATIC)
+    anc_kernel<RESAMPLE_SYSTEMATIC><<<nblocks, kP2Threads, 0, stream_>>>((int)N_, R_, key_, stream_id_, t, ix, cl, anc, ctrl_);
+  else
+    anc_kernel<RESAMPLE_STRATIFIED><<<nblocks, kP2Threads, 0, stream_>>>((int)N_, R_, key_, stream_id_, t, ix, cl, anc, ctrl_);
+  mark(TK_ANC, false);
+  SMCB_CUDA_TRY(cudaGetLastError());
+  const unsigned mblocks = (unsigned)((N_ + kMoveThreads * 2 * kMovePairs - 1) / (kMoveThreads * 2 * kMovePairs));
   mark(TK_PROP, true);
   dispatch_model(kind_, [&](auto m) {
     using M = decltype(m);
-    if (resampler == RESAMPLE_SYSTEMATIC)
-      prop2_kernel<M, RESAMPLE_SYSTEMATIC><<<nblocks, kP2Threads, 0, stream_>>>(dv_, y, (int)N_, ld_, R_, key_, stream_id_, t, ix, cl, x_[cur_],
-                                                                                 x_[cur_ ^ 1], logw_[cur_ ^ 1], anc, ctrl_);
-    else
-      prop2_kernel<M, RESAMPLE_STRATIFIED><<<nblocks, kP2Threads, 0, stream_>>>(dv_, y, (int)N_, ld_, R_, key_, stream_id_, t, ix, cl, x_[cur_],
-                                                                                 x_[cur_ ^ 1], logw_[cur_ ^ 1], anc, ctrl_);
+    move_kernel<M><<<mblocks, kMoveThreads, 0, stream_>>>(dv_, y, (int)N_, ld_, key_, stream_id_, t, anc, x_[cur_], x_[cur_ ^ 1],
+                                                         logw_[cur_ ^ 1], ctrl_);
   });
   mark(TK_PROP, false);
   SMCB_CUDA_TRY(cudaGetLastError());

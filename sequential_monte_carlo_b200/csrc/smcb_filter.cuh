@@ -25,7 +25,7 @@ struct StepStats {  // normalize() ingredients for one time step (SPEC §6)
   double mx, sum, sum2;
 };
 
-enum { TK_TOTAL = 0, TK_SCAN = 1, TK_PROP = 2, TK_INIT = 3, TK_STATS = 4, TK_BOUNDS = 5, TK_COUNT = 6 };
+enum { TK_TOTAL = 0, TK_SCAN = 1, TK_PROP = 2, TK_INIT = 3, TK_STATS = 4, TK_BOUNDS = 5, TK_ANC = 6, TK_COUNT = 7 };
 
 class SingleFilter {
  public:
@@ -117,8 +117,8 @@ class SingleFilter {
   };
   std::vector<Mark> marks_;
   size_t ev_used_ = 0;
-  double ms_[TK_COUNT] = {0, 0, 0, 0, 0, 0};
-  int64_t launches_[TK_COUNT] = {0, 0, 0, 0, 0, 0};
+  double ms_[TK_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+  int64_t launches_[TK_COUNT] = {0, 0, 0, 0, 0, 0, 0};
 };
 
 }  // namespace smcb

@@ -209,3 +209,20 @@ def test_resample_utility(ctx, oracle):
     expect = (w * n * reps).reshape(64, -1).sum(1)
     chi2 = ((bins - expect) ** 2 / expect).sum()
     assert chi2 < 63 + 6 * np.sqrt(2 * 63)
+
+
+def test_device_detmath_bit_exact(ctx, oracle):
+    """The deterministic math of docs/SPEC.md §3 evaluated ON THE DEVICE equals the oracle bit for bit:
+    exp, log, sincos2pi and the quantiser."""
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(-720, 10, 50000), -rng.exponential(3.0, 50000), [0.0, -0.0, -700.0, -745.0, -np.inf]])
+    np.testing.assert_array_equal(ctx.selftest_math(0, x)[0], oracle.det_exp(x))
+    u = np.concatenate([rng.random(100000), 2.0 ** -rng.uniform(1, 53, 100000), [2.0 ** -53, 1 - 2.0 ** -53, 0.5, 0.685546875]])
+    np.testing.assert_array_equal(ctx.selftest_math(1, u)[0], oracle.det_log(u))
+    s, c = ctx.selftest_math(2, u)
+    so, co = oracle.det_sincos2pi(u)
+    np.testing.assert_array_equal(s, so)
+    np.testing.assert_array_equal(c, co)
+    S = oracle.quant_shift(1 << 24)
+    q, _ = ctx.selftest_math(3, x[x <= 0], aux=S)
+    np.testing.assert_array_equal(q.view(np.uint64), oracle.det_quant(x[x <= 0], S))

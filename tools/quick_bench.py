@@ -26,7 +26,9 @@ for logn in ([20, 22, 24] if len(sys.argv) < 2 else [int(a) for a in sys.argv[1:
         ctx.set_profiling(False)
         pups = N * TT / (ms["total"] * 1e-3)
         rec = dict(N=N, T=TT, resampler=name, total_ms=ms["total"], gpups=pups / 1e9, frac56=pups * 56 / 6551.4e9,
-                   scan_us=1e3 * msp["scan"] / max(npf["scan"], 1), prop_us=1e3 * msp["prop"] / max(npf["prop"], 1), logZ=z)
+                   scan_us=1e3 * msp["scan"] / max(npf["scan"], 1), bounds_us=1e3 * msp["bounds"] / max(npf["bounds"], 1),
+                   anc_us=1e3 * msp["anc"] / max(npf["anc"], 1), prop_us=1e3 * msp["prop"] / max(npf["prop"], 1),
+                   init_us=1e3 * msp["init"] / max(npf["init"], 1), logZ=z)
         print(json.dumps(rec), flush=True)
         out.append(rec)
 # batched: config 3 shape (512 x 1024, T=100), config 4 (1024 x 2048 SV, T=500), config 5 per-GPU (512 x 4096 UCSV, T=241)
