@@ -12,8 +12,9 @@ configs[1] at its largest size (N = 2^24, T = 1000) — through the C ABI of lib
          stream; the only inputs, y[T] and 6 parameters, travel as kernel arguments)
   e2e    the same metric through the public Python API `log_likelihood(N, y, model) -> (x, w, logZ)`
          with host buffers: wall clock including the D2H copy of the final cloud and weights
-  roofline  the fused step (sum + bounds + propagate kernels) against the measured HBM peak using
-         SURVEY.md §8(d)'s 56 algorithmic bytes per particle-update; per-kernel split alongside
+  roofline  one filter step (sum + bounds + ancestor + move kernels) against the measured HBM peak using
+         SURVEY.md §8(d)'s 56 algorithmic bytes per particle-update; the per-kernel split (algorithmic
+         bytes, µs, GB/s of each of the four launches) rides along in roofline.per_kernel
   cpu_baseline  the CPU oracle (a port of the Julia reference; Julia is not in this image) timed on
          the host cores on a bounded sample
 
@@ -95,7 +96,12 @@ class ClockSampler:
                 "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def cpu_sample(steps, logn_sample=20, T_sample=16):
+# algorithmic bytes per particle-update of each launch of one step (LG1D fp64): they add up to the 56 B of SURVEY §8(d)
+KERNEL_BYTES = {"scan": 16, "bounds": 0, "anc": 12, "prop": 28}
+KERNEL_NAMES = {"scan": "sum_kernel", "bounds": "bounds_kernel", "anc": "anc_kernel", "prop": "move_kernel"}
+
+
+def cpu_sample(steps, logn_sample=20, T_sample=64):
     """The oracle's log_likelihood (port of particles.jl:132-147; single-threaded like the reference)."""
     from oracle import oracle as o
     o.build()
@@ -112,7 +118,7 @@ def cpu_sample(steps, logn_sample=20, T_sample=16):
 def run_reference(args, rank):
     if rank != 0:
         return
-    v, sample = cpu_sample(max(args.steps, 1) + 0, 20, 16)
+    v, sample = cpu_sample(max(args.steps, 1) + 0, 20, 32)
     N, T = 1 << args.logn, args.T
     line = {
         "impl": "reference", "metric": "particle-updates/sec (N×T) bootstrap PF", "value": v, "unit": "particle-updates/s",
@@ -226,7 +232,12 @@ def main():
     e2e = units / wall_e2e_max
     peak, peak_src = measured_peak()
     step_us = {k: (1e3 * kms[k] / kn[k] if kn[k] else None) for k in kms}
-    fused = sum(v for k, v in step_us.items() if k in ("scan", "bounds", "anc", "prop") and v)
+    # average duration of one step (its four launches) inside the timed sweeps: CUDA events around the whole sweep on
+    # the library's stream, minus the two launches that are not steps (init at t=1, the final stats-only pass).  The
+    # per-launch events below add ~2.5 us of event overhead to every launch, so their sum is reported but not used.
+    fused_events = sum(v for k, v in step_us.items() if k in ("scan", "bounds", "anc", "prop") and v)
+    sweep_us = 1e3 * dev_ms_max / args.steps
+    fused = (sweep_us - (step_us["init"] or 0.0) - (step_us["stats"] or 0.0)) / max(T - 1, 1) if T > 1 else None
     achieved = BYTES_PER_UPDATE * N / (fused * 1e-6) / 1e9 if fused else None
 
     line = {
@@ -240,12 +251,17 @@ def main():
         "wall_ms_per_step_kernel_arm": 1e3 * wall_kernel_max / args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
                      "traffic": load_traffic(), "peak_source": peak_src,
-                     "kernel": "one filter step = sum_kernel + bounds_kernel + prop_kernel (56 algorithmic B/particle-update, SURVEY §8d)",
-                     "avg_us_per_launch": step_us},
+                     "kernel": "one filter step = sum_kernel + bounds_kernel + anc_kernel + move_kernel "
+                               "(16 + 0 + 12 + 28 = 56 algorithmic B/particle-update, SURVEY §8d)",
+                     "step_us": fused, "step_us_sum_of_per_launch_events": fused_events,
+                     "avg_us_per_launch": step_us,
+                     "per_kernel": {KERNEL_NAMES[k]: {"bytes_per_update": KERNEL_BYTES[k], "us": step_us[k],
+                                                      "GB/s": (KERNEL_BYTES[k] * N / (step_us[k] * 1e-6) / 1e9) if step_us[k] else None}
+                                    for k in KERNEL_BYTES}},
         "clocks": clocks,
     }
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, sample = cpu_sample(2, 20, 16)
+        v, sample = cpu_sample(2, 20, 64)
         line["cpu_baseline"] = {"value": v, "unit": "particle-updates/s", "cores": 1, "kind": "port", "sample": sample}
     if not args.no_smc2:
         try:
@@ -260,7 +276,8 @@ def main():
 
 
 def load_traffic():
-    """dram bytes per fused step from the committed ncu capture (profiles/), or null."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of the four launches of one step at N=2^24, from the committed
+    `ncu --set full` capture (profiles/traffic.json names the report), or null."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         return json.load(open(p))["dram_bytes_per_step"]
