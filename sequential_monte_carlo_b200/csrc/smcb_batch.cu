@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(MAXT) batch_kernel(const BatchArgs a) {
             uint64_t ua = sys_off, ub = sys_off;
             if (a.resampler != RESAMPLE_SYSTEMATIC) {
               const Philox4 b = philox4x32_10((uint32_t)p, stream, t, purpose_word(PURPOSE_RESAMPLE, 0, a.key.epoch),
-                                              a.key.k0, a.key.k1);
+                                              a.key);
               ua = uniform64_of(b, 0);
               ub = uniform64_of(b, 1);
             }

@@ -22,7 +22,7 @@ struct smcb_ctx {
   std::unique_ptr<SingleFilter> filter;
   std::unique_ptr<SingleFilter> scratch;  // normalize / resample utilities
   std::vector<StepStats> stats;
-  RngKey key(uint32_t epoch) const { return RngKey{(uint32_t)seed, (uint32_t)(seed >> 32), epoch & 0xFFFFFFu}; }
+  RngKey key(uint32_t epoch) const { return make_rng_key((uint32_t)seed, (uint32_t)(seed >> 32), epoch & 0xFFFFFFu); }
 };
 
 struct smcb_batch {
@@ -361,7 +361,7 @@ int smcb_kalman_batch_loglik(smcb_ctx* ctx, const double* params, const uint8_t*
 int smcb_rng_normals(uint64_t seed, uint32_t epoch, uint32_t stream, uint32_t t, uint32_t purpose, uint32_t comp,
                      int64_t n, double* out) {
   if (!out || n < 0 || purpose > 15 || comp > 15) return SMCB_ERR_BAD_ARG;
-  const RngKey key{(uint32_t)seed, (uint32_t)(seed >> 32), epoch & 0xFFFFFFu};
+  const RngKey key = make_rng_key((uint32_t)seed, (uint32_t)(seed >> 32), epoch & 0xFFFFFFu);
   for (int64_t p = 0; 2 * p < n; ++p) {
     double z0, z1;
     normal_pair_at(key, (uint32_t)p, stream, t, purpose, comp, z0, z1);
@@ -374,7 +374,7 @@ int smcb_rng_normals(uint64_t seed, uint32_t epoch, uint32_t stream, uint32_t t,
 int smcb_rng_uniforms64(uint64_t seed, uint32_t epoch, uint32_t stream, uint32_t t, uint32_t purpose, int64_t n,
                         uint64_t* out) {
   if (!out || n < 0 || purpose > 15) return SMCB_ERR_BAD_ARG;
-  const RngKey key{(uint32_t)seed, (uint32_t)(seed >> 32), epoch & 0xFFFFFFu};
+  const RngKey key = make_rng_key((uint32_t)seed, (uint32_t)(seed >> 32), epoch & 0xFFFFFFu);
   for (int64_t i = 0; i < n; ++i) out[i] = uniform64_at(key, (uint32_t)i, stream, t, purpose);
   return SMCB_OK;
 }
@@ -385,7 +385,7 @@ namespace {
 template <class Model>
 void simulate_model(const double* D, const double* P, int64_t T, uint64_t seed, double* x, double* y) {
   // state noise: purpose SIMULATE stream 0 component k, index t; observation noise: stream 1
-  const RngKey key{(uint32_t)seed, (uint32_t)(seed >> 32), 0u};
+  const RngKey key = make_rng_key((uint32_t)seed, (uint32_t)(seed >> 32), 0u);
   Model mdl;
   mdl.load(D);
   constexpr int DIM = Model::D;

@@ -100,7 +100,43 @@ enum : uint32_t {
 struct RngKey {
   uint32_t k0, k1;    // seed halves
   uint32_t epoch;     // 24-bit sweep ordinal
+  // the ten round keys (k0 + r W0, k1 + r W1), derived once on the host: as a kernel argument they sit
+  // in the constant bank and feed the round's XOR directly (no per-thread key schedule)
+  uint32_t rk[10][2];
 };
+
+SMCB_HD RngKey make_rng_key(uint32_t k0, uint32_t k1, uint32_t epoch) {
+  RngKey key;
+  key.k0 = k0;
+  key.k1 = k1;
+  key.epoch = epoch;
+  for (int r = 0; r < 10; ++r) {
+    key.rk[r][0] = k0 + (uint32_t)r * 0x9E3779B9u;
+    key.rk[r][1] = k1 + (uint32_t)r * 0xBB67AE85u;
+  }
+  return key;
+}
+
+SMCB_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const RngKey& key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0, lo0, hi1, lo1;
+    philox_mulhilo(0xD2511F53u, c0, hi0, lo0);
+    philox_mulhilo(0xCD9E8D57u, c2, hi1, lo1);
+    uint32_t n0 = hi1 ^ c1 ^ key.rk[r][0];
+    uint32_t n2 = hi0 ^ c3 ^ key.rk[r][1];
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+  }
+  Philox4 o;
+  o.r0 = c0;
+  o.r1 = c1;
+  o.r2 = c2;
+  o.r3 = c3;
+  return o;
+}
 
 SMCB_HD uint32_t purpose_word(uint32_t kind, uint32_t comp, uint32_t epoch) {
   return ((kind | (comp << 4)) << 24) | (epoch & 0xFFFFFFu);
@@ -240,7 +276,7 @@ SMCB_HD void normal_pair(const Philox4& b, double& z0, double& z1) {
 
 SMCB_HD void normal_pair_at(const RngKey& key, uint32_t pair, uint32_t stream, uint32_t t,
                             uint32_t kind, uint32_t comp, double& z0, double& z1) {
-  Philox4 b = philox4x32_10(pair, stream, t, purpose_word(kind, comp, key.epoch), key.k0, key.k1);
+  Philox4 b = philox4x32_10(pair, stream, t, purpose_word(kind, comp, key.epoch), key);
   normal_pair(b, z0, z1);
 }
 
@@ -250,7 +286,7 @@ SMCB_HD uint64_t uniform64_of(const Philox4& b, uint32_t i) {
 
 SMCB_HD uint64_t uniform64_at(const RngKey& key, uint32_t i, uint32_t stream, uint32_t t,
                               uint32_t kind) {
-  Philox4 b = philox4x32_10(i >> 1, stream, t, purpose_word(kind, 0, key.epoch), key.k0, key.k1);
+  Philox4 b = philox4x32_10(i >> 1, stream, t, purpose_word(kind, 0, key.epoch), key);
   return uniform64_of(b, i);
 }
 

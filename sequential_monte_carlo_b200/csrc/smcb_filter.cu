@@ -335,7 +335,7 @@ __global__ void __launch_bounds__(kPropThreads)
       for (int k = 0; k < D; ++k)
         normal_pair_at(key, (uint32_t)p, stream, t, PURPOSE_TRANSITION, (uint32_t)k, za[r][k], zb[r][k]);
       if (resampler != RESAMPLE_SYSTEMATIC) {
-        const Philox4 b = philox4x32_10((uint32_t)p, stream, t, purpose_word(PURPOSE_RESAMPLE, 0, key.epoch), key.k0, key.k1);
+        const Philox4 b = philox4x32_10((uint32_t)p, stream, t, purpose_word(PURPOSE_RESAMPLE, 0, key.epoch), key);
         ua[r] = uniform64_of(b, 0);
         ub[r] = uniform64_of(b, 1);
       }
@@ -652,26 +652,77 @@ __device__ __forceinline__ int locate_pos(const StepIndex& ix, const unsigned lo
   return t0 + c;
 }
 
-// One warp per propagate CTA boundary.  A separate launch so that these dependent round trips are
-// not on the critical path of every propagate CTA.
+// two independent searches in lock step (one warp): the dependent round trips of the two overlap
+__device__ __forceinline__ void warp_count_le2(const unsigned long long* __restrict__ v0, const unsigned long long* __restrict__ v1, int n0,
+                                               int n1, uint64_t tau0, uint64_t tau1, int lane, int& r0, int& r1) {
+  int lo0 = 0, hi0 = n0, lo1 = 0, hi1 = n1;
+  while (hi0 > lo0 || hi1 > lo1) {
+    const int st0 = (hi0 - lo0 + 31) >> 5, st1 = (hi1 - lo1 + 31) >> 5;
+    const int p0 = lo0 + lane * st0 + (st0 - 1), p1 = lo1 + lane * st1 + (st1 - 1);
+    const bool in0 = (hi0 > lo0) && (p0 < hi0), in1 = (hi1 > lo1) && (p1 < hi1);
+    unsigned long long e0 = 0, e1 = 0;
+    if (in0) e0 = __ldg(&v0[p0]);
+    if (in1) e1 = __ldg(&v1[p1]);
+    const int c0 = __popc(__ballot_sync(kFullMask, in0 && e0 <= tau0));
+    const int c1 = __popc(__ballot_sync(kFullMask, in1 && e1 <= tau1));
+    if (hi0 > lo0) {
+      lo0 += c0 * st0;
+      if (c0 == 32) hi0 = lo0;  // (only when every probe was in range and <= tau: the rest is empty)
+      else { const int nh = lo0 + st0 - 1; hi0 = nh < hi0 ? nh : hi0; }
+    }
+    if (hi1 > lo1) {
+      lo1 += c1 * st1;
+      if (c1 == 32) hi1 = lo1;
+      else { const int nh = lo1 + st1 - 1; hi1 = nh < hi1 ? nh : hi1; }
+    }
+  }
+  r0 = lo0;
+  r1 = lo1;
+}
+
+// One warp per TWO propagate-CTA boundaries (b and b + half), searched in lock step so that the whole
+// grid is one wave of dependent round trips instead of two.  A separate launch so that these round
+// trips are not on the critical path of every ancestor CTA.
 __global__ void __launch_bounds__(256)
     bounds_kernel(StepIndex ix, const unsigned long long* __restrict__ cl, const FilterCtrl* ctrl, int N, int resampler,
                   uint64_t Rw, RngKey key, uint32_t stream, uint32_t t, int nbounds) {
   const int lane = threadIdx.x & 31;
-  const int b = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (b >= nbounds) return;
+  const int half = (nbounds + 1) >> 1;
+  const int b0 = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (b0 >= half) return;
+  const int b1 = b0 + half;
+  const bool has1 = b1 < nbounds;
   const uint64_t Q = ctrl->total;
   if (Q == 0) return;
-  int64_t i = (int64_t)b * kP2Particles;
-  if (i > N - 1) i = N - 1;  // the last boundary is the last particle
-  uint64_t u = ctrl->sys_off;
-  if (resampler == RESAMPLE_STRATIFIED) u = uniform64_at(key, (uint32_t)i, stream, t, PURPOSE_RESAMPLE);
-  const uint64_t tau = threshold_of(resampler, (uint64_t)i, Rw, u, Q);
-  int T;
-  const int pos = locate_pos(ix, cl, N, tau, lane, T);
+  uint64_t tau[2];
+#pragma unroll
+  for (int s = 0; s < 2; ++s) {
+    int64_t i = (int64_t)(s ? (has1 ? b1 : b0) : b0) * kP2Particles;
+    if (i > N - 1) i = N - 1;  // the last boundary is the last particle
+    uint64_t u = ctrl->sys_off;
+    if (resampler == RESAMPLE_STRATIFIED) u = uniform64_at(key, (uint32_t)i, stream, t, PURPOSE_RESAMPLE);
+    tau[s] = threshold_of(resampler, (uint64_t)i, Rw, u, Q);
+  }
+  int T0, T1;
+  warp_count_le2(ix.tile_incl, ix.tile_incl, ix.ntiles, ix.ntiles, tau[0], tau[1], lane, T0, T1);
+  if (T0 > ix.ntiles - 1) T0 = ix.ntiles - 1;
+  if (T1 > ix.ntiles - 1) T1 = ix.ntiles - 1;
+  const uint64_t rem0 = tau[0] - __ldg(&ix.tile_excl[T0]), rem1 = tau[1] - __ldg(&ix.tile_excl[T1]);
+  const int t0 = T0 * ix.tile_items, t1 = T1 * ix.tile_items;
+  int n0 = N - t0, n1 = N - t1;
+  if (n0 > ix.tile_items) n0 = ix.tile_items;
+  if (n1 > ix.tile_items) n1 = ix.tile_items;
+  int c0, c1;
+  warp_count_le2(cl + t0, cl + t1, n0, n1, rem0, rem1, lane, c0, c1);
+  if (c0 > n0 - 1) c0 = n0 - 1;
+  if (c1 > n1 - 1) c1 = n1 - 1;
   if (lane == 0) {
-    ix.bound_pos[b] = pos;
-    ix.bound_tile[b] = T;
+    ix.bound_pos[b0] = t0 + c0;
+    ix.bound_tile[b0] = T0;
+    if (has1) {
+      ix.bound_pos[b1] = t1 + c1;
+      ix.bound_tile[b1] = T1;
+    }
   }
 }
 
@@ -1203,7 +1254,7 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler) {
   SMCB_CUDA_TRY(cudaGetLastError());
   const int nbounds = (int)nblocks + 1;
   mark(TK_BOUNDS, true);
-  bounds_kernel<<<(nbounds + 7) / 8, 256, 0, stream_>>>(ix, cl, ctrl_, (int)N_, resampler, R_, key_, stream_id_, t, nbounds);
+  bounds_kernel<<<((nbounds + 1) / 2 + 7) / 8, 256, 0, stream_>>>(ix, cl, ctrl_, (int)N_, resampler, R_, key_, stream_id_, t, nbounds);
   mark(TK_BOUNDS, false);
   SMCB_CUDA_TRY(cudaGetLastError());
   int32_t* anc = anc_;  // row 0 doubles as the scratch ancestor vector when nothing is recorded
