@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <utility>
 
 #include "../../include/smcb200.h"  // smcb_status error codes
 #include "smcb_detmath.cuh"
@@ -28,6 +29,29 @@ struct Error {
 #if defined(__CUDACC__)
 
 constexpr unsigned kFullMask = 0xFFFFFFFFu;
+
+// Programmatic dependent launch (sm_90+): the four kernels of a filter step form a strict chain, so
+// every kernel lets its successor's CTAs become resident at once (they fill the SM slots freed by
+// this grid's tail) and blocks until its predecessor has completed and flushed before it reads
+// anything the predecessor wrote.  Hides launch latency and ramp-up at every kernel boundary.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// launch with the programmatic-stream-serialization attribute (the kernel must call pdl_wait())
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);
+}
 
 // monotone map double -> uint64 so that atomicMax on the image is max on the doubles
 __device__ __forceinline__ unsigned long long encode_ordered(double d) {

@@ -466,6 +466,8 @@ __global__ void __launch_bounds__(kSumThreads, kSumCtasPerSm)
   __shared__ bool s_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tile = blockIdx.x * kSumWarps + warp;
+  pdl_launch_dependents();
+  pdl_wait();  // logw and its max come from the previous step's move kernel
   const double mx = decode_ordered(ctrl->maxslot[slot]);
   if (tile < ix.ntiles) {
     // one warp walks its tile chunk by chunk: the running prefix stays in registers
@@ -692,6 +694,8 @@ __global__ void __launch_bounds__(256)
   if (b0 >= half) return;
   const int b1 = b0 + half;
   const bool has1 = b1 < nbounds;
+  pdl_launch_dependents();
+  pdl_wait();  // the tile index and Q come from sum_kernel
   const uint64_t Q = ctrl->total;
   if (Q == 0) return;
   uint64_t tau[2];
@@ -792,6 +796,8 @@ __global__ void __launch_bounds__(kP2Threads, 10)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t sbase;
   asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"((uint32_t)__cvta_generic_to_shared(s_cdf)));  // opaque: kept in a register, not re-derived
+  pdl_launch_dependents();
+  pdl_wait();  // the window bounds come from bounds_kernel
   const uint64_t Q = ctrl->total;
   const int i0 = blockIdx.x * kP2Particles + tid * kP2Per;  // first particle of this thread
   const bool full_cta = (blockIdx.x + 1) * kP2Particles <= N;
@@ -995,6 +1001,8 @@ __global__ void __launch_bounds__(kMoveThreads, (Model::D == 1) ? 6 : 4)
   Model mdl;
   mdl.load(dv.d);
   const int i0 = (blockIdx.x * kMoveThreads + tid) * PER;
+  pdl_launch_dependents();
+  pdl_wait();  // the ancestors come from anc_kernel
   double vmax;
   if ((blockIdx.x + 1) * (kMoveThreads * PER) <= N)
     vmax = move_particles<Model, true>(mdl, y, N, ld, key, stream, t, i0, anc, xprev, xnew, logw);
@@ -1247,14 +1255,14 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler) {
   const unsigned nblocks = (unsigned)((N_ + kP2Particles - 1) / kP2Particles);
   const uint32_t t = t_ + 1;
   mark(TK_SCAN, true);
-  sum_kernel<<<(ix.ntiles + kSumWarps - 1) / kSumWarps, kSumThreads, 0, stream_>>>(logw_[cur_], cl, N_, S_, ctrl_, ix, psum_, psum2_,
-                                                                                  stats_dev_ + stat_index, (int)(t_ & 1u), resampler,
-                                                                                  R_, key_, stream_id_, t);
+  SMCB_CUDA_TRY(launch_pdl(sum_kernel, dim3((ix.ntiles + kSumWarps - 1) / kSumWarps), dim3(kSumThreads), stream_, logw_[cur_], cl, N_, S_, ctrl_, ix,
+                           psum_, psum2_, stats_dev_ + stat_index, (int)(t_ & 1u), resampler, R_, key_, stream_id_, t));
   mark(TK_SCAN, false);
   SMCB_CUDA_TRY(cudaGetLastError());
   const int nbounds = (int)nblocks + 1;
   mark(TK_BOUNDS, true);
-  bounds_kernel<<<((nbounds + 1) / 2 + 7) / 8, 256, 0, stream_>>>(ix, cl, ctrl_, (int)N_, resampler, R_, key_, stream_id_, t, nbounds);
+  SMCB_CUDA_TRY(launch_pdl(bounds_kernel, dim3(((nbounds + 1) / 2 + 7) / 8), dim3(256), stream_, ix, cl, ctrl_, (int)N_, resampler, R_, key_,
+                           stream_id_, t, nbounds));
   mark(TK_BOUNDS, false);
   SMCB_CUDA_TRY(cudaGetLastError());
   int32_t* anc = anc_;  // row 0 doubles as the scratch ancestor vector when nothing is recorded
@@ -1265,17 +1273,19 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler) {
   }
   mark(TK_ANC, true);
   if (resampler == RESAMPLE_SYSTEMATIC)
-    anc_kernel<RESAMPLE_SYSTEMATIC><<<nblocks, kP2Threads, 0, stream_>>>((int)N_, R_, key_, stream_id_, t, ix, cl, anc, ctrl_);
+    SMCB_CUDA_TRY(launch_pdl(anc_kernel<RESAMPLE_SYSTEMATIC>, dim3(nblocks), dim3(kP2Threads), stream_, (int)N_, R_, key_, stream_id_, t, ix, cl, anc,
+                             ctrl_));
   else
-    anc_kernel<RESAMPLE_STRATIFIED><<<nblocks, kP2Threads, 0, stream_>>>((int)N_, R_, key_, stream_id_, t, ix, cl, anc, ctrl_);
+    SMCB_CUDA_TRY(launch_pdl(anc_kernel<RESAMPLE_STRATIFIED>, dim3(nblocks), dim3(kP2Threads), stream_, (int)N_, R_, key_, stream_id_, t, ix, cl, anc,
+                             ctrl_));
   mark(TK_ANC, false);
   SMCB_CUDA_TRY(cudaGetLastError());
   const unsigned mblocks = (unsigned)((N_ + kMoveThreads * 2 * kMovePairs - 1) / (kMoveThreads * 2 * kMovePairs));
   mark(TK_PROP, true);
   dispatch_model(kind_, [&](auto m) {
     using M = decltype(m);
-    move_kernel<M><<<mblocks, kMoveThreads, 0, stream_>>>(dv_, y, (int)N_, ld_, key_, stream_id_, t, anc, x_[cur_], x_[cur_ ^ 1],
-                                                         logw_[cur_ ^ 1], ctrl_);
+    SMCB_CUDA_TRY(launch_pdl(move_kernel<M>, dim3(mblocks), dim3(kMoveThreads), stream_, dv_, y, (int)N_, ld_, key_, stream_id_, t, anc, x_[cur_],
+                             x_[cur_ ^ 1], logw_[cur_ ^ 1], ctrl_));
   });
   mark(TK_PROP, false);
   SMCB_CUDA_TRY(cudaGetLastError());
