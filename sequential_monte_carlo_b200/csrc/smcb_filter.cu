@@ -742,28 +742,27 @@ __device__ __forceinline__ unsigned long long lds_u64_off(uint32_t saddr) {
   return v;
 }
 
-// Shared-state-space address of entry #{ j in [0,kWinCap) : cdf[j] <= tau } of a window padded with
-// ~0 up to kWinCap entries; branch-free, the probe offsets are immediates.  sbase is the window's
-// address in the shared state space (explicit ld.shared: through a generic pointer ptxas re-derives
-// the shared window base on every probe).  Entry kWinCap-1 is a sentinel or the window's last
-// value, both > tau, so it is never probed past.
+// Shared-state-space address of entry #{ j in [0,len) : cdf[j] <= tau } of a window of len <= kWinCap
+// staged entries; branch-free.  `last` is the address of entry len-1, whose value is > tau (the
+// window's last value, or a ~0 sentinel): a probe past the window reads that entry instead, so
+// nothing beyond the staged entries has to be initialised.  sbase is the window's address in the
+// shared state space (explicit ld.shared: through a generic pointer ptxas re-derives the shared
+// window base on every probe).
 template <int STEP>
-__device__ __forceinline__ uint32_t window_search_addr(uint32_t a, uint64_t tau) {
-  if (lds_u64_off<8 * (STEP - 1)>(a) <= tau) a += 8u * STEP;
-  if constexpr (STEP > 1) return window_search_addr<STEP / 2>(a, tau);
+__device__ __forceinline__ uint32_t window_search_addr(uint32_t a, uint32_t last, uint64_t tau) {
+  const uint32_t probe = a + 8u * (STEP - 1);
+  if (lds_u64(probe < last ? probe : last) <= tau) a += 8u * STEP;
+  if constexpr (STEP > 1) return window_search_addr<STEP / 2>(a, last, tau);
   else return a;
 }
-__device__ __forceinline__ int window_count_le(uint32_t sbase, uint64_t tau) {
-  return (int)((window_search_addr<kWinCap / 2>(sbase, tau) - sbase) >> 3);
+__device__ __forceinline__ int window_count_le(uint32_t sbase, int len, uint64_t tau) {
+  return (int)((window_search_addr<kWinCap / 2>(sbase, sbase + 8u * (uint32_t)(len - 1), tau) - sbase) >> 3);
 }
 
-// s_cdf[0..kWinCap) <- global CDF entries [s0, s0+len) (tile-local values + tile offsets), ~0 beyond; s0 even.
+// s_cdf[0..len) <- global CDF entries [s0, s0+len) (tile-local values + tile offsets); s0 even.
 __device__ __forceinline__ void stage_window(unsigned long long* s_cdf, const StepIndex& ix,
                                             const unsigned long long* __restrict__ cl, int s0, int len, int T, int tid) {
   const int end = s0 + len;
-  // sentinel padding [len rounded down to even, kWinCap)
-  for (int j = (len & ~1) + 2 * tid; j < kWinCap; j += 2 * kP2Threads)
-    *reinterpret_cast<ulonglong2*>(&s_cdf[j]) = make_ulonglong2(~0ull, ~0ull);
   int tlo = s0;
   while (tlo < end) {
     const int tend_full = (T + 1) * ix.tile_items;
@@ -773,7 +772,7 @@ __device__ __forceinline__ void stage_window(unsigned long long* s_cdf, const St
       const ulonglong2 v = __ldcs(reinterpret_cast<const ulonglong2*>(cl + j));
       ulonglong2 o;
       o.x = v.x + base;
-      o.y = (j + 1 < thi) ? v.y + base : ~0ull;
+      o.y = v.y + base;  // the odd entry past the window (if any) is never read
       *reinterpret_cast<ulonglong2*>(&s_cdf[j - s0]) = o;
     }
     tlo = thi;
@@ -815,6 +814,7 @@ __global__ void __launch_bounds__(kP2Threads, 10)
       // ---- common case: the whole window fits one pass.  C[a_hi] > every tau of this CTA, so the
       // walk below always stops inside the staged entries.
       stage_window(s_cdf, ix, cl, s0, a_hi - s0 + 1, T0, tid);
+      const uint32_t s_last = sbase + 8u * (uint32_t)(a_hi - s0);  // C[a_hi] > every tau of this CTA
       // thresholds (SPEC §5): tau_i = hi64(F_i Q); systematic: F_{i+1} Q = F_i Q + R Q as a 128-bit value
       unsigned long long plo = 0, phi = 0, dlo = 0, dhi = 0;
       uint64_t tau[kP2Per];
@@ -840,7 +840,7 @@ __global__ void __launch_bounds__(kP2Threads, 10)
       __syncthreads();
       auto walk = [&](auto full_tag) {
         constexpr bool FULL = decltype(full_tag)::value;
-        uint32_t a = window_search_addr<kWinCap / 2>(sbase, tau_at(0));
+        uint32_t a = window_search_addr<kWinCap / 2>(sbase, s_last, tau_at(0));
         unsigned long long cur = lds_u64(a);
         anc[0] = s0 + (int)((a - sbase) >> 3);
 #pragma unroll
@@ -882,7 +882,7 @@ __global__ void __launch_bounds__(kP2Threads, 10)
         for (int k = 0; k < kP2Per; ++k) {
           if (k >= next && k < nvalid) {
             if (tau[k] < c_end) {
-              anc[k] = s0 + window_count_le(sbase, tau[k]);
+              anc[k] = s0 + window_count_le(sbase, len, tau[k]);
               next = k + 1;
             } else if (tau[k] < my_min) {
               my_min = tau[k];
