@@ -784,7 +784,7 @@ __device__ __forceinline__ void stage_window(unsigned long long* s_cdf, const St
 // int32.  Model-independent and light in registers, so that many warps hide the dependent
 // shared-memory reads of the search and the walk.  Every thread owns kP2Per CONSECUTIVE particles.
 template <int RESAMPLER>
-__global__ void __launch_bounds__(kP2Threads, 10)
+__global__ void __launch_bounds__(kP2Threads, 10)  // 48 registers: 12 CTAs/SM spills (79 us), 8 CTAs/SM 72 us, 10 CTAs/SM 68 us at N = 2^24
     anc_kernel(int N, uint64_t Rw, RngKey key, uint32_t stream, uint32_t t, StepIndex ix, const unsigned long long* __restrict__ cl,
                int32_t* __restrict__ anc_out, const FilterCtrl* __restrict__ ctrl) {
   constexpr int NW = kP2Threads / 32;
