@@ -932,7 +932,7 @@ __global__ void __launch_bounds__(kP2Threads, 10)  // 48 registers: 12 CTAs/SM s
 // pass, kMovePairs pairs (4 consecutive particles) per thread for two independent Philox / Box-Muller
 // chains; parents gathered through the (sorted, hence near-coalesced) ancestor vector.
 constexpr int kMoveThreads = 256;
-constexpr int kMovePairs = 1;
+constexpr int kMovePairs = 2;
 template <class Model, bool FULL>
 __device__ __forceinline__ double move_particles(const Model& mdl, double y, int N, int64_t ld, const RngKey& key, uint32_t stream, uint32_t t,
                                                  int i0, const int32_t* __restrict__ anc, const double* __restrict__ xprev,
@@ -991,7 +991,7 @@ __device__ __forceinline__ double move_particles(const Model& mdl, double y, int
 }
 
 template <class Model>
-__global__ void __launch_bounds__(kMoveThreads, (Model::D == 1) ? 6 : 4)
+__global__ void __launch_bounds__(kMoveThreads, (Model::D == 1) ? 6 : 3)
     move_kernel(Derived dv, double y, int N, int64_t ld, RngKey key, uint32_t stream, uint32_t t, const int32_t* __restrict__ anc,
                 const double* __restrict__ xprev, double* __restrict__ xnew, double* __restrict__ logw, FilterCtrl* ctrl) {
   constexpr int PER = 2 * kMovePairs;
