@@ -755,6 +755,16 @@ __device__ __forceinline__ uint32_t window_search_addr(uint32_t a, uint32_t last
   if constexpr (STEP > 1) return window_search_addr<STEP / 2>(a, last, tau);
   else return a;
 }
+// two independent searches in lock step: both probes of a round are in flight together
+template <int STEP>
+__device__ __forceinline__ void window_search_addr2(uint32_t& a0, uint32_t& a1, uint32_t last, uint64_t tau0, uint64_t tau1) {
+  const uint32_t p0 = a0 + 8u * (STEP - 1), p1 = a1 + 8u * (STEP - 1);
+  const unsigned long long e0 = lds_u64(p0 < last ? p0 : last);
+  const unsigned long long e1 = lds_u64(p1 < last ? p1 : last);
+  if (e0 <= tau0) a0 += 8u * STEP;
+  if (e1 <= tau1) a1 += 8u * STEP;
+  if constexpr (STEP > 1) window_search_addr2<STEP / 2>(a0, a1, last, tau0, tau1);
+}
 __device__ __forceinline__ int window_count_le(uint32_t sbase, int len, uint64_t tau) {
   return (int)((window_search_addr<kWinCap / 2>(sbase, sbase + 8u * (uint32_t)(len - 1), tau) - sbase) >> 3);
 }
@@ -816,14 +826,79 @@ __global__ void __launch_bounds__(kP2Threads, 10)  // 48 registers: 12 CTAs/SM s
       stage_window(s_cdf, ix, cl, s0, a_hi - s0 + 1, T0, tid);
       const uint32_t s_last = sbase + 8u * (uint32_t)(a_hi - s0);  // C[a_hi] > every tau of this CTA
       // thresholds (SPEC §5): tau_i = hi64(F_i Q); systematic: F_{i+1} Q = F_i Q + R Q as a 128-bit value
-      unsigned long long plo = 0, phi = 0, dlo = 0, dhi = 0;
+      unsigned long long dlo = 0, dhi = 0;
+      if (RESAMPLER == RESAMPLE_SYSTEMATIC) {
+        dlo = ctrl->rq_lo;  // R Q, written by sum_kernel
+        dhi = ctrl->rq_hi;
+      }
+      if (full_cta) {
+        // Full CTA: every thread resolves TWO runs of kP2Per/2 consecutive particles half a CTA apart, in
+        // lock step — two independent ld.shared chains per thread hide each other's latency, a walk
+        // round serves both runs, and the lanes of a warp sit kP2Per/2 entries apart in the window.
+        constexpr int H = kP2Per / 2;
+        const int iA = blockIdx.x * kP2Particles + tid * H, iB = iA + kP2Particles / 2;
+        unsigned long long alo = 0, ahi = 0, blo = 0, bhi = 0;
+        uint64_t tA[H], tB[H];
+        if (RESAMPLER == RESAMPLE_SYSTEMATIC) {
+          const uint64_t FA = (uint64_t)iA * Rw + ctrl->sys_off, FB = (uint64_t)iB * Rw + ctrl->sys_off;
+          alo = FA * Q; ahi = mulhi64(FA, Q);
+          blo = FB * Q; bhi = mulhi64(FB, Q);
+        } else {
+#pragma unroll
+          for (int k = 0; k < H; ++k) {
+            tA[k] = threshold_of(RESAMPLER, (uint64_t)(iA + k), Rw, uniform64_at(key, (uint32_t)(iA + k), stream, t, PURPOSE_RESAMPLE), Q);
+            tB[k] = threshold_of(RESAMPLER, (uint64_t)(iB + k), Rw, uniform64_at(key, (uint32_t)(iB + k), stream, t, PURPOSE_RESAMPLE), Q);
+          }
+        }
+        auto next_tau = [&](int k, unsigned long long& lo, unsigned long long& hi, const uint64_t* tv) -> uint64_t {
+          if (RESAMPLER == RESAMPLE_SYSTEMATIC) {
+            const uint64_t v = hi;
+            asm("add.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, %3;" : "+l"(lo), "+l"(hi) : "l"(dlo), "l"(dhi));
+            return v;
+          }
+          return tv[k];
+        };
+        __syncthreads();
+        uint32_t aA = sbase, aB = sbase;
+        {
+          const uint64_t t0 = next_tau(0, alo, ahi, tA), t1 = next_tau(0, blo, bhi, tB);
+          window_search_addr2<kWinCap / 2>(aA, aB, s_last, t0, t1);
+        }
+        unsigned long long curA = lds_u64(aA), curB = lds_u64(aB);
+        int ancA[H], ancB[H];
+        ancA[0] = s0 + (int)((aA - sbase) >> 3);
+        ancB[0] = s0 + (int)((aB - sbase) >> 3);
+#pragma unroll
+        for (int k = 1; k < H; ++k) {
+          const uint64_t t0 = next_tau(k, alo, ahi, tA), t1 = next_tau(k, blo, bhi, tB);
+          bool mA = curA <= t0, mB = curB <= t1;
+          while (mA || mB) {
+            if (mA) {
+              aA += 8u;
+              curA = lds_u64(aA);
+            }
+            if (mB) {
+              aB += 8u;
+              curB = lds_u64(aB);
+            }
+            mA = curA <= t0;
+            mB = curB <= t1;
+          }
+          ancA[k] = s0 + (int)((aA - sbase) >> 3);
+          ancB[k] = s0 + (int)((aB - sbase) >> 3);
+        }
+        static_assert(H == 4, "the vector stores below assume 4 particles per run");
+        *reinterpret_cast<int4*>(anc_out + iA) = make_int4(ancA[0], ancA[1], ancA[2], ancA[3]);
+        *reinterpret_cast<int4*>(anc_out + iB) = make_int4(ancB[0], ancB[1], ancB[2], ancB[3]);
+        return;
+      }
+      // the last, partial CTA: 8 consecutive particles per thread with bounds checks
+      unsigned long long plo = 0, phi = 0;
       uint64_t tau[kP2Per];
       if (RESAMPLER == RESAMPLE_SYSTEMATIC) {
         const uint64_t F0 = (uint64_t)i0 * Rw + ctrl->sys_off;
         plo = F0 * Q;
         phi = mulhi64(F0, Q);
-        dlo = ctrl->rq_lo;  // R Q, written by sum_kernel
-        dhi = ctrl->rq_hi;
       } else {
 #pragma unroll
         for (int k = 0; k < kP2Per; ++k)
@@ -838,15 +913,14 @@ __global__ void __launch_bounds__(kP2Threads, 10)  // 48 registers: 12 CTAs/SM s
         return tau[k];
       };
       __syncthreads();
-      auto walk = [&](auto full_tag) {
-        constexpr bool FULL = decltype(full_tag)::value;
+      if (i0 < N) {
         uint32_t a = window_search_addr<kWinCap / 2>(sbase, s_last, tau_at(0));
         unsigned long long cur = lds_u64(a);
         anc[0] = s0 + (int)((a - sbase) >> 3);
 #pragma unroll
         for (int k = 1; k < kP2Per; ++k) {
           const uint64_t tk = tau_at(k);
-          if (FULL || i0 + k < N) {
+          if (i0 + k < N) {
             while (cur <= tk) {
               a += 8u;
               cur = lds_u64(a);
@@ -854,9 +928,7 @@ __global__ void __launch_bounds__(kP2Threads, 10)  // 48 registers: 12 CTAs/SM s
           }
           anc[k] = s0 + (int)((a - sbase) >> 3);
         }
-      };
-      if (full_cta) walk(std::true_type{});
-      else if (i0 < N) walk(std::false_type{});
+      }
     } else {
       // ---- wide window (very uneven weights): pass by pass, each pass starting at the ancestor of
       // the smallest unresolved threshold; per-particle binary search inside the staged segment
