@@ -115,6 +115,28 @@ def cpu_sample(steps, logn_sample=20, T_sample=64):
     return N * T_sample / statistics.mean(times), f"LG1D N=2^{logn_sample}, T={T_sample}, systematic, oracle/smc_oracle.c (gcc -O2), linear in N*T"
 
 
+def cpu_rejuvenation_sample(N=1024, T=100, seconds=8.0):
+    """The reference's dominant cost beside it (SURVEY §8d ii): one `Threads.@threads for m` sweep of full particle
+    filters (rejuvenate!, smc_samplers.jl:112-121) by the CPU oracle, OpenMP over θ with every host thread, on a
+    bounded number of θ-particles.  bench.py is one of the few places allowed to execute oracle/ (as the baseline)."""
+    from oracle import oracle as o
+    o.build()
+    threads = o.num_threads()
+    P = np.tile(o.params8([0.5, 1.0, 0.9, 0.8, 0.0, 1.0]), (threads, 1))
+    _, y = o.simulate(0, P[0], T, 1998)
+    M, t1 = threads, 0.0
+    while True:                                    # grow the sample until it runs for about `seconds`
+        Pm = np.tile(P[:1], (M, 1))
+        t0 = time.perf_counter()
+        o.batch_log_likelihood(0, Pm, None, N, y, o.MULTINOMIAL, 1998, 0, 0, want_state=False)
+        t1 = time.perf_counter() - t0
+        if t1 > seconds / 4 or M >= 4096:
+            break
+        M *= 4
+    return {"value": M * N * T / t1, "unit": "particle-updates/s", "cores": threads, "kind": "port",
+            "sample": f"one rejuvenation sweep: {M} theta x {N} particles x T={T}, multinomial, oracle/smc_oracle.c OpenMP over theta"}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -265,6 +287,8 @@ def main():
         try:
             from sequential_monte_carlo_b200 import bench_smc2
             line["smc2"] = bench_smc2.run(local, rank, world)
+            if rank == 0 and world == 1 and not args.no_cpu:
+                line["smc2"]["cpu_baseline"] = cpu_rejuvenation_sample(1024, 100)
         except Exception as e:  # the headline line must still print
             line["smc2"] = {"error": repr(e)}
     if rank == 0:
