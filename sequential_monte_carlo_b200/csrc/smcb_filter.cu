@@ -735,38 +735,38 @@ __device__ __forceinline__ unsigned long long lds_u64(uint32_t saddr) {
   asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(saddr));
   return v;
 }
-template <int BYTE_OFF>
-__device__ __forceinline__ unsigned long long lds_u64_off(uint32_t saddr) {
-  unsigned long long v;
-  asm volatile("ld.shared.u64 %0, [%1+%2];" : "=l"(v) : "r"(saddr), "n"(BYTE_OFF));
-  return v;
-}
+// The CDF window lives in shared memory with ONE PAD SLOT PER 16 ENTRIES: entry p sits in slot
+// p + (p >> 4).  A binary search probes p = 16 m + 15, 32 m + 31, ... — in a dense array all lanes of a
+// half-warp hit the same bank pair (16-way conflicts); with the pad the slot is 17 m + 15 and the lanes
+// spread over all 16 bank pairs.  The same holds for the walk, where the lanes sit 4 entries apart.
+constexpr int kWinSlots = kWinCap + kWinCap / 16;
+__device__ __forceinline__ uint32_t win_addr(uint32_t sbase, int p) { return sbase + 8u * (uint32_t)(p + (p >> 4)); }
+__device__ __forceinline__ unsigned long long win_load(uint32_t sbase, int p) { return lds_u64(win_addr(sbase, p)); }
 
-// Shared-state-space address of entry #{ j in [0,len) : cdf[j] <= tau } of a window of len <= kWinCap
-// staged entries; branch-free.  `last` is the address of entry len-1, whose value is > tau (the
-// window's last value, or a ~0 sentinel): a probe past the window reads that entry instead, so
-// nothing beyond the staged entries has to be initialised.  sbase is the window's address in the
-// shared state space (explicit ld.shared: through a generic pointer ptxas re-derives the shared
+// #{ j in [0,len) : cdf[j] <= tau } of a window of len <= kWinCap staged entries; branch-free.
+// Entry `last` = len-1 is > tau (the window's last value): a probe past the window reads that entry
+// instead, so nothing beyond the staged entries has to be initialised.  sbase is the window's address
+// in the shared state space (explicit ld.shared: through a generic pointer ptxas re-derives the shared
 // window base on every probe).
 template <int STEP>
-__device__ __forceinline__ uint32_t window_search_addr(uint32_t a, uint32_t last, uint64_t tau) {
-  const uint32_t probe = a + 8u * (STEP - 1);
-  if (lds_u64(probe < last ? probe : last) <= tau) a += 8u * STEP;
-  if constexpr (STEP > 1) return window_search_addr<STEP / 2>(a, last, tau);
-  else return a;
+__device__ __forceinline__ int window_search(uint32_t sbase, int pos, int last, uint64_t tau) {
+  const int probe = pos + (STEP - 1);
+  if (win_load(sbase, probe < last ? probe : last) <= tau) pos += STEP;
+  if constexpr (STEP > 1) return window_search<STEP / 2>(sbase, pos, last, tau);
+  else return pos;
 }
 // two independent searches in lock step: both probes of a round are in flight together
 template <int STEP>
-__device__ __forceinline__ void window_search_addr2(uint32_t& a0, uint32_t& a1, uint32_t last, uint64_t tau0, uint64_t tau1) {
-  const uint32_t p0 = a0 + 8u * (STEP - 1), p1 = a1 + 8u * (STEP - 1);
-  const unsigned long long e0 = lds_u64(p0 < last ? p0 : last);
-  const unsigned long long e1 = lds_u64(p1 < last ? p1 : last);
-  if (e0 <= tau0) a0 += 8u * STEP;
-  if (e1 <= tau1) a1 += 8u * STEP;
-  if constexpr (STEP > 1) window_search_addr2<STEP / 2>(a0, a1, last, tau0, tau1);
+__device__ __forceinline__ void window_search2(uint32_t sbase, int& p0, int& p1, int last, uint64_t tau0, uint64_t tau1) {
+  const int q0 = p0 + (STEP - 1), q1 = p1 + (STEP - 1);
+  const unsigned long long e0 = win_load(sbase, q0 < last ? q0 : last);
+  const unsigned long long e1 = win_load(sbase, q1 < last ? q1 : last);
+  if (e0 <= tau0) p0 += STEP;
+  if (e1 <= tau1) p1 += STEP;
+  if constexpr (STEP > 1) window_search2<STEP / 2>(sbase, p0, p1, last, tau0, tau1);
 }
 __device__ __forceinline__ int window_count_le(uint32_t sbase, int len, uint64_t tau) {
-  return (int)((window_search_addr<kWinCap / 2>(sbase, sbase + 8u * (uint32_t)(len - 1), tau) - sbase) >> 3);
+  return window_search<kWinCap / 2>(sbase, 0, len - 1, tau);
 }
 
 // s_cdf[0..len) <- global CDF entries [s0, s0+len) (tile-local values + tile offsets); s0 even.
@@ -780,10 +780,10 @@ __device__ __forceinline__ void stage_window(unsigned long long* s_cdf, const St
     const unsigned long long base = __ldg(&ix.tile_excl[T]);
     for (int j = tlo + 2 * tid; j < thi; j += 2 * kP2Threads) {  // tlo even, tile_items even
       const ulonglong2 v = __ldcs(reinterpret_cast<const ulonglong2*>(cl + j));
-      ulonglong2 o;
-      o.x = v.x + base;
-      o.y = v.y + base;  // the odd entry past the window (if any) is never read
-      *reinterpret_cast<ulonglong2*>(&s_cdf[j - s0]) = o;
+      const int p = j - s0;  // even: p and p + 1 share a 16-entry row, their slots are adjacent
+      unsigned long long* dst = s_cdf + (p + (p >> 4));
+      dst[0] = v.x + base;
+      dst[1] = v.y + base;  // the odd entry past the window (if any) is never read
     }
     tlo = thi;
     ++T;
@@ -798,7 +798,7 @@ __global__ void __launch_bounds__(kP2Threads, 10)  // 48 registers: 12 CTAs/SM s
     anc_kernel(int N, uint64_t Rw, RngKey key, uint32_t stream, uint32_t t, StepIndex ix, const unsigned long long* __restrict__ cl,
                int32_t* __restrict__ anc_out, const FilterCtrl* __restrict__ ctrl) {
   constexpr int NW = kP2Threads / 32;
-  __shared__ __align__(16) unsigned long long s_cdf[kWinCap];
+  __shared__ __align__(16) unsigned long long s_cdf[kWinSlots];
   __shared__ unsigned long long s_min[NW];
   __shared__ int s_next[2];
 
@@ -824,7 +824,7 @@ __global__ void __launch_bounds__(kP2Threads, 10)  // 48 registers: 12 CTAs/SM s
       // ---- common case: the whole window fits one pass.  C[a_hi] > every tau of this CTA, so the
       // walk below always stops inside the staged entries.
       stage_window(s_cdf, ix, cl, s0, a_hi - s0 + 1, T0, tid);
-      const uint32_t s_last = sbase + 8u * (uint32_t)(a_hi - s0);  // C[a_hi] > every tau of this CTA
+      const int p_last = a_hi - s0;  // C[a_hi] > every tau of this CTA
       // thresholds (SPEC §5): tau_i = hi64(F_i Q); systematic: F_{i+1} Q = F_i Q + R Q as a 128-bit value
       unsigned long long dlo = 0, dhi = 0;
       if (RESAMPLER == RESAMPLE_SYSTEMATIC) {
@@ -859,33 +859,33 @@ __global__ void __launch_bounds__(kP2Threads, 10)  // 48 registers: 12 CTAs/SM s
           return tv[k];
         };
         __syncthreads();
-        uint32_t aA = sbase, aB = sbase;
+        int pA = 0, pB = 0;
         {
           const uint64_t t0 = next_tau(0, alo, ahi, tA), t1 = next_tau(0, blo, bhi, tB);
-          window_search_addr2<kWinCap / 2>(aA, aB, s_last, t0, t1);
+          window_search2<kWinCap / 2>(sbase, pA, pB, p_last, t0, t1);
         }
-        unsigned long long curA = lds_u64(aA), curB = lds_u64(aB);
+        unsigned long long curA = win_load(sbase, pA), curB = win_load(sbase, pB);
         int ancA[H], ancB[H];
-        ancA[0] = s0 + (int)((aA - sbase) >> 3);
-        ancB[0] = s0 + (int)((aB - sbase) >> 3);
+        ancA[0] = s0 + pA;
+        ancB[0] = s0 + pB;
 #pragma unroll
         for (int k = 1; k < H; ++k) {
           const uint64_t t0 = next_tau(k, alo, ahi, tA), t1 = next_tau(k, blo, bhi, tB);
           bool mA = curA <= t0, mB = curB <= t1;
           while (mA || mB) {
             if (mA) {
-              aA += 8u;
-              curA = lds_u64(aA);
+              ++pA;
+              curA = win_load(sbase, pA);
             }
             if (mB) {
-              aB += 8u;
-              curB = lds_u64(aB);
+              ++pB;
+              curB = win_load(sbase, pB);
             }
             mA = curA <= t0;
             mB = curB <= t1;
           }
-          ancA[k] = s0 + (int)((aA - sbase) >> 3);
-          ancB[k] = s0 + (int)((aB - sbase) >> 3);
+          ancA[k] = s0 + pA;
+          ancB[k] = s0 + pB;
         }
         static_assert(H == 4, "the vector stores below assume 4 particles per run");
         *reinterpret_cast<int4*>(anc_out + iA) = make_int4(ancA[0], ancA[1], ancA[2], ancA[3]);
@@ -914,19 +914,19 @@ __global__ void __launch_bounds__(kP2Threads, 10)  // 48 registers: 12 CTAs/SM s
       };
       __syncthreads();
       if (i0 < N) {
-        uint32_t a = window_search_addr<kWinCap / 2>(sbase, s_last, tau_at(0));
-        unsigned long long cur = lds_u64(a);
-        anc[0] = s0 + (int)((a - sbase) >> 3);
+        int p = window_search<kWinCap / 2>(sbase, 0, p_last, tau_at(0));
+        unsigned long long cur = win_load(sbase, p);
+        anc[0] = s0 + p;
 #pragma unroll
         for (int k = 1; k < kP2Per; ++k) {
           const uint64_t tk = tau_at(k);
           if (i0 + k < N) {
             while (cur <= tk) {
-              a += 8u;
-              cur = lds_u64(a);
+              ++p;
+              cur = win_load(sbase, p);
             }
           }
-          anc[k] = s0 + (int)((a - sbase) >> 3);
+          anc[k] = s0 + p;
         }
       }
     } else {
@@ -948,7 +948,7 @@ __global__ void __launch_bounds__(kP2Threads, 10)  // 48 registers: 12 CTAs/SM s
         if (!final_seg) len = kWinCap;
         stage_window(s_cdf, ix, cl, s0, len, T0, tid);
         __syncthreads();
-        const unsigned long long c_end = final_seg ? ~0ull : lds_u64(sbase + 8u * (uint32_t)(len - 1));
+        const unsigned long long c_end = final_seg ? ~0ull : win_load(sbase, len - 1);
         unsigned long long my_min = ~0ull;
 #pragma unroll
         for (int k = 0; k < kP2Per; ++k) {
