@@ -743,30 +743,37 @@ constexpr int kWinSlots = kWinCap + kWinCap / 16;
 __device__ __forceinline__ uint32_t win_addr(uint32_t sbase, int p) { return sbase + 8u * (uint32_t)(p + (p >> 4)); }
 __device__ __forceinline__ unsigned long long win_load(uint32_t sbase, int p) { return lds_u64(win_addr(sbase, p)); }
 
-// #{ j in [0,len) : cdf[j] <= tau } of a window of len <= kWinCap staged entries; branch-free.
-// Entry `last` = len-1 is > tau (the window's last value): a probe past the window reads that entry
-// instead, so nothing beyond the staged entries has to be initialised.  sbase is the window's address
-// in the shared state space (explicit ld.shared: through a generic pointer ptxas re-derives the shared
-// window base on every probe).
+// #{ j in [0,len) : cdf[j] <= tau } of a window of len <= kWinCap staged entries; branch-free, and run
+// entirely on SLOT addresses: before the step of size STEP the position is a multiple of 2 STEP, so
+// the probe pos + STEP - 1 sits (STEP-1) + ((STEP-1) >> 4) slots after it and advancing moves
+// STEP + (STEP >> 4) slots — both immediates.  `last` = address of entry len-1, whose value is > tau:
+// a probe past the window reads that entry instead, so nothing beyond the staged entries has to be
+// initialised.  sbase is the window's address in the shared state space (explicit ld.shared: through
+// a generic pointer ptxas re-derives the shared window base on every probe).
 template <int STEP>
-__device__ __forceinline__ int window_search(uint32_t sbase, int pos, int last, uint64_t tau) {
-  const int probe = pos + (STEP - 1);
-  if (win_load(sbase, probe < last ? probe : last) <= tau) pos += STEP;
-  if constexpr (STEP > 1) return window_search<STEP / 2>(sbase, pos, last, tau);
-  else return pos;
+__device__ __forceinline__ uint32_t window_search_slot(uint32_t a, uint32_t last, uint64_t tau) {
+  const uint32_t probe = a + 8u * ((STEP - 1) + ((STEP - 1) >> 4));
+  if (lds_u64(probe < last ? probe : last) <= tau) a += 8u * (STEP + (STEP >> 4));
+  if constexpr (STEP > 1) return window_search_slot<STEP / 2>(a, last, tau);
+  else return a;
 }
 // two independent searches in lock step: both probes of a round are in flight together
 template <int STEP>
-__device__ __forceinline__ void window_search2(uint32_t sbase, int& p0, int& p1, int last, uint64_t tau0, uint64_t tau1) {
-  const int q0 = p0 + (STEP - 1), q1 = p1 + (STEP - 1);
-  const unsigned long long e0 = win_load(sbase, q0 < last ? q0 : last);
-  const unsigned long long e1 = win_load(sbase, q1 < last ? q1 : last);
-  if (e0 <= tau0) p0 += STEP;
-  if (e1 <= tau1) p1 += STEP;
-  if constexpr (STEP > 1) window_search2<STEP / 2>(sbase, p0, p1, last, tau0, tau1);
+__device__ __forceinline__ void window_search_slot2(uint32_t& a0, uint32_t& a1, uint32_t last, uint64_t tau0, uint64_t tau1) {
+  const uint32_t q0 = a0 + 8u * ((STEP - 1) + ((STEP - 1) >> 4)), q1 = a1 + 8u * ((STEP - 1) + ((STEP - 1) >> 4));
+  const unsigned long long e0 = lds_u64(q0 < last ? q0 : last);
+  const unsigned long long e1 = lds_u64(q1 < last ? q1 : last);
+  if (e0 <= tau0) a0 += 8u * (STEP + (STEP >> 4));
+  if (e1 <= tau1) a1 += 8u * (STEP + (STEP >> 4));
+  if constexpr (STEP > 1) window_search_slot2<STEP / 2>(a0, a1, last, tau0, tau1);
+}
+// entry index of a slot address: slot - slot / 17 (exact for slot < 70000: 61681 / 2^20 ~ 1/17)
+__device__ __forceinline__ int win_entry(uint32_t sbase, uint32_t a) {
+  const uint32_t slot = (a - sbase) >> 3;
+  return (int)(slot - ((slot * 61681u) >> 20));
 }
 __device__ __forceinline__ int window_count_le(uint32_t sbase, int len, uint64_t tau) {
-  return window_search<kWinCap / 2>(sbase, 0, len - 1, tau);
+  return win_entry(sbase, window_search_slot<kWinCap / 2>(sbase, win_addr(sbase, len - 1), tau));
 }
 
 // s_cdf[0..len) <- global CDF entries [s0, s0+len) (tile-local values + tile offsets); s0 even.
@@ -859,10 +866,13 @@ __global__ void __launch_bounds__(kP2Threads, 10)  // 48 registers: 12 CTAs/SM s
           return tv[k];
         };
         __syncthreads();
-        int pA = 0, pB = 0;
+        int pA, pB;
         {
           const uint64_t t0 = next_tau(0, alo, ahi, tA), t1 = next_tau(0, blo, bhi, tB);
-          window_search2<kWinCap / 2>(sbase, pA, pB, p_last, t0, t1);
+          uint32_t aA = sbase, aB = sbase;
+          window_search_slot2<kWinCap / 2>(aA, aB, win_addr(sbase, p_last), t0, t1);
+          pA = win_entry(sbase, aA);
+          pB = win_entry(sbase, aB);
         }
         unsigned long long curA = win_load(sbase, pA), curB = win_load(sbase, pB);
         int ancA[H], ancB[H];
@@ -914,7 +924,7 @@ __global__ void __launch_bounds__(kP2Threads, 10)  // 48 registers: 12 CTAs/SM s
       };
       __syncthreads();
       if (i0 < N) {
-        int p = window_search<kWinCap / 2>(sbase, 0, p_last, tau_at(0));
+        int p = window_count_le(sbase, p_last + 1, tau_at(0));
         unsigned long long cur = win_load(sbase, p);
         anc[0] = s0 + p;
 #pragma unroll
