@@ -215,6 +215,28 @@ SMCB_HD void det_exp_quant(double x, int S, double& e, uint64_t& q) {
   q = (valid && ks >= 0) ? vq : 0;
 }
 
+#if defined(__CUDACC__)
+// det_exp_quant for the streaming sum kernel, x = logw - max <= 0 (or -inf / NaN): the same q bit for bit;
+// e differs from det_exp only below x = -700, where it is exp(-700) ~ 1e-304 instead of 0 (it only
+// enters the sums of SPEC §6, compared at 1e-10).  The x < -700 / -inf cases are clamped with one
+// integer compare on the high word, NaN is carried by one predicate.
+__device__ __forceinline__ void det_exp_quant_stream(double x, int S, double& e, uint64_t& q) {
+  const uint32_t hi = (uint32_t)(double_as_u64(x) >> 32);
+  const bool isnan = (x != x);
+  const double xc = (hi >= 0xC085E000u) ? -700.0 : x;  // x <= -700, -inf (and negative-sign NaN: handled below)
+  double p;
+  int k;
+  det_exp_parts(xc, p, k);
+  const double ev = scale_pow2(p, k);
+  e = isnan ? x : ev;
+  const int ks = k + S;
+  const uint64_t v = (uint64_t)scale_pow2(p, ks < 0 ? 0 : ks);
+  const uint64_t cap = (uint64_t)1 << S;
+  const uint64_t vq = v < cap ? v : cap;
+  q = (ks >= 0 && !isnan) ? vq : 0;
+}
+#endif
+
 SMCB_HD double det_log(double u) {
   uint64_t b = double_as_u64(u);
   int e = (int)((b >> 52) & 0x7FF) - 1023;

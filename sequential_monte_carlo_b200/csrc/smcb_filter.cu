@@ -504,7 +504,7 @@ __global__ void __launch_bounds__(kSumThreads, kSumCtasPerSm)
       for (int k = 0; k < 4; ++k) {  // out-of-range items carry logw = -inf: e = 0, q = 0
         double e;
         uint64_t qq;
-        det_exp_quant(lw[k] - mx, S, e, qq);
+        det_exp_quant_stream(lw[k] - mx, S, e, qq);
         se += e;
         se2 += e * e;
         q[k] = qq;
