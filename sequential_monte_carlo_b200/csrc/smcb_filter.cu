@@ -816,7 +816,7 @@ __global__ void __launch_bounds__(kP2Threads, 10)  // 48 registers: 12 CTAs/SM s
   pdl_wait();  // the window bounds come from bounds_kernel
   const uint64_t Q = ctrl->total;
   const int i0 = blockIdx.x * kP2Particles + tid * kP2Per;  // first particle of this thread
-  const bool full_cta = (blockIdx.x + 1) * kP2Particles <= N;
+  const bool full_cta = (int64_t)(blockIdx.x + 1) * kP2Particles <= (int64_t)N;
 
   int anc[kP2Per];
 #pragma unroll
@@ -1086,7 +1086,7 @@ __global__ void __launch_bounds__(kMoveThreads, (Model::D == 1) ? 6 : 3)
   pdl_launch_dependents();
   pdl_wait();  // the ancestors come from anc_kernel
   double vmax;
-  if ((blockIdx.x + 1) * (kMoveThreads * PER) <= N)
+  if ((int64_t)(blockIdx.x + 1) * (kMoveThreads * PER) <= (int64_t)N)
     vmax = move_particles<Model, true>(mdl, y, N, ld, key, stream, t, i0, anc, xprev, xnew, logw);
   else
     vmax = move_particles<Model, false>(mdl, y, N, ld, key, stream, t, i0, anc, xprev, xnew, logw);
