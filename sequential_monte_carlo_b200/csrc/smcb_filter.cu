@@ -1,20 +1,19 @@
 // Grid-wide kernels of one large-N bootstrap particle filter (docs/SPEC.md §5-§7).
 //
-// One time step = two launches (reference: bootstrap_filter!, /root/reference/src/particles.jl:107-129)
+// One time step of bootstrap_filter! (/root/reference/src/particles.jl:107-129):
 //
+//   sorted resamplers (stratified / systematic) — four launches chained by programmatic dependent
+//   launch, see the block comment further down:   sum_kernel -> bounds_kernel -> anc_kernel -> move_kernel
+//
+//   multinomial (the reference's i.i.d. law, unsorted thresholds) — two launches:
 //   scan_kernel  normalize() + the CDF of resample():  reads logw, quantises exp(logw - max) to
 //                fixed point, single-pass decoupled look-back prefix sum in uint64 (exact, so
 //                ancestors do not depend on the tiling), writes the CDF, reduces Σe, Σe² (-> logμ,
 //                ess of the previous step) in a fixed order.             particles.jl:5-15,117
-//   prop_kernel  resample + gather + transition + observation logpdf fused: each CTA owns a
-//                contiguous particle range, finds the CDF window of its first/last threshold with
-//                a 32-ary warp search, stages the window in shared memory, every thread
-//                binary-searches its two ancestors there, gathers the parents, draws the
-//                transition with Philox/Box-Muller, writes x', logw' with 16-byte stores and
+//   prop_kernel  resample + gather + transition + observation logpdf fused: every thread
+//                binary-searches the global CDF for its two ancestors, gathers the parents, draws
+//                the transition with Philox/Box-Muller, writes x', logw' with 16-byte stores and
 //                contributes to the exact max(logw') for the next scan.  particles.jl:117-125
-//
-// HBM traffic per particle-update (LG1D fp64): logw 8 R + cdf 8 W | cdf 8 R + x 8 R + x' 8 W +
-// logw' 8 W = 48 B (the ancestor vector is never materialised unless recording is on).
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -417,20 +416,22 @@ __global__ void __launch_bounds__(kPropThreads)
 }
 
 // ================================================================================================
-// Sorted resamplers (stratified / systematic): the three-launch step  sum -> bounds -> prop2.
+// Sorted resamplers (stratified / systematic): the four-launch step  sum -> bounds -> anc -> move.
 //
 // sum_kernel quantises the weights and writes the TILE-LOCAL inclusive CDF cl (one u64 per particle;
 // one warp walks one tile, so the running prefix never leaves its registers) plus one total per tile;
-// its last CTA scans the <= 8192 tile totals (exact integers, so every ancestor equals the one a
-// sequential CDF would give).  bounds_kernel finds, for every propagate CTA, the ancestor of its
-// first particle (32-ary warp searches of the tile index and of one tile).  prop2_kernel stages
-// exactly the CDF entries between its own and the next CTA's bound in shared memory (adding the tile
-// offsets), and every thread resolves 8 CONSECUTIVE particles: one branch-free binary search for
-// the first, then a forward walk that re-reads shared memory only when the ancestor advances; the
-// systematic thresholds tau_i = hi64((i R + u) Q) are advanced by one 128-bit add of R Q.  It then
-// gathers the parents, draws the transition (Philox + Box-Muller), weights, and feeds the exact max.
-// HBM traffic per particle-update (LG1D fp64): logw 8 R + cl 8 W | cl 8 R + x 8 R + x' 8 W +
-// logw' 8 W = 48 B; neither the global CDF nor the ancestor vector is materialised.
+// every CTA publishes the prefixes of its 8 tiles and one CTA total, the last CTA scans the <= 1024
+// CTA totals (exact integers, so every ancestor equals the one a sequential CDF would give).
+// bounds_kernel finds, for every ancestor CTA, the ancestor of its first particle (32-ary warp
+// searches of the tile index and of one tile).  anc_kernel stages exactly the CDF entries between its
+// own and the next CTA's bound in shared memory (adding the tile offsets; one pad slot per 16
+// entries against bank conflicts) and every thread resolves two runs of 4 CONSECUTIVE particles in
+// lock step: one branch-free binary search per run, then a forward walk that re-reads shared memory
+// only when the ancestor advances; the systematic thresholds tau_i = hi64((i R + u) Q) are advanced
+// by one 128-bit add of R Q.  move_kernel gathers the parents through the sorted int32 ancestor
+// vector, draws the transition (Philox + Box-Muller), weights, and feeds the exact max.
+// HBM traffic per particle-update (LG1D fp64): logw 8 R + cl 8 W | cl 8 R + anc 4 W | anc 4 R + x 8 R
+// + x' 8 W + logw' 8 W = 56 B, the algorithmic figure of SURVEY.md §8(d).
 constexpr int kChunk = 128;                            // particles per warp trip of sum_kernel (32 lanes x 4)
 constexpr int kSumThreads = 256;                       // 8 warps, one tile per warp, no block barrier in the main loop
 constexpr int kSumWarps = kSumThreads / 32;
