@@ -460,7 +460,15 @@ struct StepIndex {
 __global__ void __launch_bounds__(kSumThreads, kSumCtasPerSm)
     sum_kernel(const double* __restrict__ logw, unsigned long long* __restrict__ cl, int64_t N, int S, FilterCtrl* ctrl,
                StepIndex ix, double* psum, double* psum2, StepStats* stats_out, int slot, int resampler, uint64_t Rw,
-               RngKey key, uint32_t stream, uint32_t t) {
+               RngKey key, uint32_t stream, uint32_t t, int from_x, Derived dv, double ycur) {
+  // from_x: `logw` points at the LG1D states x and the log-weight logpdf(observation(x), ycur) is
+  // recomputed here (2 fma, bit-identical to what move_kernel maximised over) instead of being
+  // written by move_kernel and read back: 8 B per particle-update less through HBM.
+  // (the constants stay in the kernel-argument bank: ModelLG1D::logweight with B = d[1], ir = d[5], c = d[6])
+  auto lg_logweight = [&](double x) {
+    const double v = (ycur - dv.d[1] * x) * dv.d[5];
+    return fma(-0.5 * v, v, dv.d[6]);
+  };
   __shared__ double s_we[kSumWarps], s_we2[kSumWarps];
   __shared__ unsigned long long s_scan[kSumWarps];
   __shared__ unsigned long long s_cta_excl[kMaxSumCtas];
@@ -500,6 +508,11 @@ __global__ void __launch_bounds__(kSumThreads, kSumCtasPerSm)
       const int64_t base = tile0 + (int64_t)c * kChunk + lane * 4;
       double lw[4] = {nx[0], nx[1], nx[2], nx[3]};
       if (c + 1 < nch) load_chunk(c + 1, nx);
+      if (from_x) {  // out-of-range items were loaded as -inf: their "weight" must stay -inf
+        const bool whole = base + 4 <= N;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) lw[k] = (whole || base + k < N) ? lg_logweight(lw[k]) : -INFINITY;
+      }
       unsigned long long q[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {  // out-of-range items carry logw = -inf: e = 0, q = 0
@@ -1019,7 +1032,7 @@ constexpr int kMovePairs = 2;
 template <class Model, bool FULL>
 __device__ __forceinline__ double move_particles(const Model& mdl, double y, int N, int64_t ld, const RngKey& key, uint32_t stream, uint32_t t,
                                                  int i0, const int32_t* __restrict__ anc, const double* __restrict__ xprev,
-                                                 double* __restrict__ xnew, double* __restrict__ logw) {
+                                                 double* __restrict__ xnew, double* __restrict__ logw /* null: not stored */) {
   constexpr int D = Model::D;
   constexpr int PER = 2 * kMovePairs;
   int a[PER];
@@ -1060,13 +1073,13 @@ __device__ __forceinline__ double move_particles(const Model& mdl, double y, int
     if (FULL || i + 1 < N) {
 #pragma unroll
       for (int c = 0; c < D; ++c) *reinterpret_cast<double2*>(xnew + c * ld + i) = make_double2(xa[c], xb[c]);
-      *reinterpret_cast<double2*>(logw + i) = make_double2(la, lb);
+      if (logw) *reinterpret_cast<double2*>(logw + i) = make_double2(la, lb);
       if (la > vmax) vmax = la;  // `>` ignores NaN like the CPU loop
       if (lb > vmax) vmax = lb;
     } else {
 #pragma unroll
       for (int c = 0; c < D; ++c) xnew[c * ld + i] = xa[c];
-      logw[i] = la;
+      if (logw) logw[i] = la;
       if (la > vmax) vmax = la;
     }
   }
@@ -1101,6 +1114,14 @@ __global__ void __launch_bounds__(kMoveThreads, (Model::D == 1) ? 6 : 3)
     for (int w = 1; w < NW; ++w) m = s_max[w] > m ? s_max[w] : m;
     atomicMax(&ctrl->maxslot[t & 1u], m);
   }
+}
+
+// logw_i = logpdf(observation(x_i), y): materialises the log-weights that the LG1D step does not store
+__global__ void logw_kernel(Derived dv, double y, int64_t N, const double* __restrict__ x, double* __restrict__ logw) {
+  ModelLG1D mdl;
+  mdl.load(dv.d);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) logw[i] = mdl.logweight(&x[i], y);
 }
 
 // w_i = exp(logw_i - max) / Σe   (normalize, particles.jl:11) — only when the caller fetches w
@@ -1253,7 +1274,15 @@ void SingleFilter::timing(double ms[TK_COUNT], int64_t launches[TK_COUNT]) const
   for (int k = 0; k < TK_COUNT; ++k) { ms[k] = ms_[k]; launches[k] = launches_[k]; }
 }
 
+void SingleFilter::ensure_logw() {
+  if (logw_valid_ || !live()) return;
+  logw_kernel<<<(unsigned)((N_ + 255) / 256), 256, 0, stream_>>>(dv_w_, y_cur_, N_, x_[cur_], logw_[cur_]);
+  SMCB_CUDA_TRY(cudaGetLastError());
+  logw_valid_ = true;
+}
+
 void SingleFilter::launch_init(double y0) {
+  logw_valid_ = true;
   SMCB_CUDA_TRY(cudaMemsetAsync(desc_, 0, sizeof(unsigned long long) * 2 * ntiles_cap_, stream_));
   reset_ctrl_kernel<<<1, 1, 0, stream_>>>(ctrl_);
   launches_[TK_INIT] += 1;
@@ -1275,6 +1304,7 @@ void SingleFilter::launch_scan(int64_t stat_index, bool write_cdf) {
   unsigned long long* dn = desc_ + (size_t)((t_ + 1) & 1u) * ntiles_cap_;
   const int klass = write_cdf ? TK_SCAN : TK_STATS;
   if ((write_cdf || from_w_) && !cdf_) SMCB_CUDA_TRY(cudaMalloc(&cdf_, sizeof(uint64_t) * cap_N_));  // multinomial / utilities only
+  ensure_logw();
   const double* lw = logw_[cur_];
   mark(klass, true);
   StepStats* so = stats_dev_ + stat_index;
@@ -1308,6 +1338,8 @@ void SingleFilter::launch_prop(double y, int resampler) {
   SMCB_CUDA_TRY(cudaGetLastError());
   cur_ ^= 1;
   t_ = t;
+  logw_valid_ = true;
+  y_cur_ = y;
 }
 
 // one bootstrap_filter! step: stats of the current weights (-> stats_dev_[stat_index]) and the move to t_+1
@@ -1338,8 +1370,10 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler) {
   const unsigned nblocks = (unsigned)((N_ + kP2Particles - 1) / kP2Particles);
   const uint32_t t = t_ + 1;
   mark(TK_SCAN, true);
-  SMCB_CUDA_TRY(launch_pdl(sum_kernel, dim3((ix.ntiles + kSumWarps - 1) / kSumWarps), dim3(kSumThreads), stream_, logw_[cur_], cl, N_, S_, ctrl_, ix,
-                           psum_, psum2_, stats_dev_ + stat_index, (int)(t_ & 1u), resampler, R_, key_, stream_id_, t));
+  const int from_x = logw_valid_ ? 0 : 1;  // the previous LG1D step kept its log-weights implicit in x
+  SMCB_CUDA_TRY(launch_pdl(sum_kernel, dim3((ix.ntiles + kSumWarps - 1) / kSumWarps), dim3(kSumThreads), stream_,
+                           from_x ? (const double*)x_[cur_] : (const double*)logw_[cur_], cl, N_, S_, ctrl_, ix, psum_, psum2_,
+                           stats_dev_ + stat_index, (int)(t_ & 1u), resampler, R_, key_, stream_id_, t, from_x, dv_w_, y_cur_));
   mark(TK_SCAN, false);
   SMCB_CUDA_TRY(cudaGetLastError());
   const int nbounds = (int)nblocks + 1;
@@ -1364,16 +1398,22 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler) {
   mark(TK_ANC, false);
   SMCB_CUDA_TRY(cudaGetLastError());
   const unsigned mblocks = (unsigned)((N_ + kMoveThreads * 2 * kMovePairs - 1) / (kMoveThreads * 2 * kMovePairs));
+  // LG1D: the new log-weights are two fma of the new states; they are not stored (sum_kernel and, when a caller asks
+  // for them, logw_kernel recompute them bit for bit).  SV / UCSV weights cost an exp: stored as before.
+  const bool implicit_logw = (kind_ == KIND_LG1D);
   mark(TK_PROP, true);
   dispatch_model(kind_, [&](auto m) {
     using M = decltype(m);
     SMCB_CUDA_TRY(launch_pdl(move_kernel<M>, dim3(mblocks), dim3(kMoveThreads), stream_, dv_, y, (int)N_, ld_, key_, stream_id_, t, anc, x_[cur_],
-                             x_[cur_ ^ 1], logw_[cur_ ^ 1], ctrl_));
+                             x_[cur_ ^ 1], implicit_logw ? (double*)nullptr : logw_[cur_ ^ 1], ctrl_));
   });
   mark(TK_PROP, false);
   SMCB_CUDA_TRY(cudaGetLastError());
   cur_ ^= 1;
   t_ = t;
+  logw_valid_ = !implicit_logw;
+  y_cur_ = y;
+  dv_w_ = dv_;  // the parameters these weights were computed with (step() may be handed new ones)
 }
 
 static void check_args(int kind, int64_t N, int resampler) {
@@ -1453,6 +1493,7 @@ void SingleFilter::fetch(double* x_host, double* w_host, double* logw_host) {
   if (x_host)
     SMCB_CUDA_TRY(cudaMemcpy2DAsync(x_host, sizeof(double) * N_, x_[cur_], sizeof(double) * ld_, sizeof(double) * N_,
                                     d_, cudaMemcpyDeviceToHost, stream_));
+  if (logw_host || w_host) ensure_logw();
   if (logw_host)
     SMCB_CUDA_TRY(cudaMemcpyAsync(logw_host, logw_[cur_], sizeof(double) * N_, cudaMemcpyDeviceToHost, stream_));
   if (w_host) {
@@ -1490,7 +1531,7 @@ void SingleFilter::load_vector(const double* host, int64_t n, bool is_log) {
   }
   kind_ = KIND_LG1D; d_ = 0; N_ = n; ld_ = cap_N_;
   S_ = quant_shift((uint64_t)n); R_ = strata_width((uint64_t)n);
-  t_ = 0; cur_ = 0; anc_rows_ = 0; from_w_ = !is_log;
+  t_ = 0; cur_ = 0; anc_rows_ = 0; from_w_ = !is_log; logw_valid_ = true;
   SMCB_CUDA_TRY(cudaMemsetAsync(desc_, 0, sizeof(unsigned long long) * 2 * ntiles_cap_, stream_));
   reset_ctrl_kernel<<<1, 1, 0, stream_>>>(ctrl_);
   SMCB_CUDA_TRY(cudaMemcpyAsync(logw_[cur_], host, sizeof(double) * n, cudaMemcpyHostToDevice, stream_));

@@ -59,13 +59,14 @@ class SingleFilter {
   uint32_t t() const { return t_; }
   bool live() const { return N_ > 0; }
   const double* dev_x() const { return x_[cur_]; }
-  const double* dev_logw() const { return logw_[cur_]; }
+  const double* dev_logw() { ensure_logw(); return logw_[cur_]; }
 
  private:
   void ensure_capacity(int kind, int64_t N, int64_t anc_rows);
   void load_vector(const double* host, int64_t n, bool is_log);
   void begin_call();
   void end_call();
+  void ensure_logw();  // materialise the log-weights an LG1D step keeps implicit in x
   void launch_init(double y0);
   void launch_prop(double y, int resampler);
   void launch_step(int64_t stat_index, double y, int resampler);  // one bootstrap_filter! step
@@ -103,6 +104,9 @@ class SingleFilter {
   int32_t* bound_arrays_ = nullptr;            // [2][bound_cap_]: ancestor of each propagate CTA's first particle, its tile
   int64_t bound_cap_ = 0;
   int num_sms_ = 0;
+  bool logw_valid_ = true;  // logw_[cur_] holds the current log-weights (false: implicit in x_[cur_] and y_cur_)
+  double y_cur_ = 0.0;      // observation the current weights were computed against
+  Derived dv_w_{};          // ... and the derived parameters they were computed with
   double* psum_ = nullptr;
   double* psum2_ = nullptr;
   StepStats* stats_dev_ = nullptr;
