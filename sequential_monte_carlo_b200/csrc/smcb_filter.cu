@@ -444,18 +444,6 @@ constexpr int kP2Per = 8;
 constexpr int kP2Particles = kP2Threads * kP2Per;      // 1024 particles per CTA
 constexpr int kWinCap = 2048;                          // CDF entries staged per pass (16 KB)
 
-struct StepIndex {
-  unsigned long long* tile_tot;   // [ntiles]
-  unsigned long long* tile_lexcl; // [ntiles] exclusive prefix of the tile inside its sum_kernel CTA (8 tiles)
-  unsigned long long* cta_tot;    // [ntiles / 8] total of each sum_kernel CTA
-  unsigned long long* tile_excl;  // [ntiles] global exclusive prefix of the tile
-  unsigned long long* tile_incl;  // [ntiles]
-  int32_t* bound_pos;             // [nblocks + 1] ancestor of each propagate CTA's first particle (last: of particle N-1)
-  int32_t* bound_tile;            // [nblocks + 1] its tile
-  int ntiles;
-  int chunks_per_tile;
-  int tile_items;
-};
 
 __global__ void __launch_bounds__(kSumThreads, kSumCtasPerSm)
     sum_kernel(const double* __restrict__ logw, unsigned long long* __restrict__ cl, int64_t N, int S, FilterCtrl* ctrl,
@@ -629,7 +617,7 @@ __global__ void __launch_bounds__(kSumThreads, kSumCtasPerSm)
       ctrl->total = Q;
       ctrl->rq_lo = Rw * Q;
       ctrl->rq_hi = mulhi64(Rw, Q);
-      ctrl->sys_off = (resampler == RESAMPLE_SYSTEMATIC) ? mulhi64(uniform64_at(key, 0u, stream, t, PURPOSE_RESAMPLE), Rw) : 0ull;
+      ctrl->sys_off = mulhi64(uniform64_at(key, 0u, stream, t, PURPOSE_RESAMPLE), Rw);  // used by the systematic resampler only
       ctrl->scan_done = 0;
       ctrl->maxslot[slot ^ 1] = encode_ordered(-INFINITY);
     }
@@ -1283,6 +1271,7 @@ void SingleFilter::ensure_logw() {
 
 void SingleFilter::launch_init(double y0) {
   logw_valid_ = true;
+  sum_done_ = false;
   SMCB_CUDA_TRY(cudaMemsetAsync(desc_, 0, sizeof(unsigned long long) * 2 * ntiles_cap_, stream_));
   reset_ctrl_kernel<<<1, 1, 0, stream_>>>(ctrl_);
   launches_[TK_INIT] += 1;
@@ -1340,21 +1329,16 @@ void SingleFilter::launch_prop(double y, int resampler) {
   t_ = t;
   logw_valid_ = true;
   y_cur_ = y;
+  sum_done_ = false;
 }
 
-// one bootstrap_filter! step: stats of the current weights (-> stats_dev_[stat_index]) and the move to t_+1
-void SingleFilter::launch_step(int64_t stat_index, double y, int resampler) {
-  if (resampler == RESAMPLE_MULTINOMIAL) {  // unsorted thresholds: materialised CDF + per-particle global search
-    launch_scan(stat_index, true);
-    launch_prop(y, resampler);
-    return;
-  }
-  // tile geometry: one warp per tile, one full wave of resident warps when N allows, at most kMaxTiles tiles
+// tile geometry of the sorted-resampler step: one warp per tile, one full wave of resident warps when N
+// allows, at most kMaxTiles tiles; returns the tile-local CDF buffer
+unsigned long long* SingleFilter::step_index(StepIndex& ix) {
   const int64_t nchunks = (N_ + kChunk - 1) / kChunk;
   const int64_t resident = (int64_t)num_sms_ * kSumCtasPerSm * kSumWarps;
   int64_t cpt = std::max<int64_t>((nchunks + resident - 1) / resident, (nchunks + kMaxTiles - 1) / kMaxTiles);
   cpt = std::max<int64_t>(cpt, 1);
-  StepIndex ix;
   ix.chunks_per_tile = (int)cpt;
   ix.tile_items = (int)(cpt * kChunk);
   ix.ntiles = (int)((nchunks + cpt - 1) / cpt);
@@ -1366,16 +1350,38 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler) {
   ix.bound_pos = bound_arrays_;
   ix.bound_tile = bound_arrays_ + bound_cap_;
   if (!cdf_) SMCB_CUDA_TRY(cudaMalloc(&cdf_, sizeof(uint64_t) * cap_N_));  // holds the tile-local CDF here (the global CDF on the multinomial path)
-  unsigned long long* cl = reinterpret_cast<unsigned long long*>(cdf_);
-  const unsigned nblocks = (unsigned)((N_ + kP2Particles - 1) / kP2Particles);
+  return reinterpret_cast<unsigned long long*>(cdf_);
+}
+
+// normalize() ingredients of the CURRENT weights (-> stats_dev_[stat_index]) and everything the next
+// sorted-resampler step needs (tile-local CDF, tile index, Q, systematic offset).  A stepping caller
+// runs it right after a step to read logμ / ess; the next step then starts at bounds_kernel.
+void SingleFilter::launch_sum(int64_t stat_index) {
+  StepIndex ix;
+  unsigned long long* cl = step_index(ix);
   const uint32_t t = t_ + 1;
   mark(TK_SCAN, true);
   const int from_x = logw_valid_ ? 0 : 1;  // the previous LG1D step kept its log-weights implicit in x
   SMCB_CUDA_TRY(launch_pdl(sum_kernel, dim3((ix.ntiles + kSumWarps - 1) / kSumWarps), dim3(kSumThreads), stream_,
                            from_x ? (const double*)x_[cur_] : (const double*)logw_[cur_], cl, N_, S_, ctrl_, ix, psum_, psum2_,
-                           stats_dev_ + stat_index, (int)(t_ & 1u), resampler, R_, key_, stream_id_, t, from_x, dv_w_, y_cur_));
+                           stats_dev_ + stat_index, (int)(t_ & 1u), (int)RESAMPLE_SYSTEMATIC, R_, key_, stream_id_, t, from_x, dv_w_, y_cur_));
   mark(TK_SCAN, false);
   SMCB_CUDA_TRY(cudaGetLastError());
+  sum_done_ = true;
+}
+
+// one bootstrap_filter! step: stats of the current weights (-> stats_dev_[stat_index]) and the move to t_+1
+void SingleFilter::launch_step(int64_t stat_index, double y, int resampler) {
+  if (resampler == RESAMPLE_MULTINOMIAL) {  // unsorted thresholds: materialised CDF + per-particle global search
+    launch_scan(stat_index, true);
+    launch_prop(y, resampler);
+    return;
+  }
+  StepIndex ix;
+  unsigned long long* cl = step_index(ix);
+  if (!sum_done_) launch_sum(stat_index);  // (a stepping caller already ran it to read the statistics of the current weights)
+  const unsigned nblocks = (unsigned)((N_ + kP2Particles - 1) / kP2Particles);
+  const uint32_t t = t_ + 1;
   const int nbounds = (int)nblocks + 1;
   mark(TK_BOUNDS, true);
   SMCB_CUDA_TRY(launch_pdl(bounds_kernel, dim3(((nbounds + 1) / 2 + 7) / 8), dim3(256), stream_, ix, cl, ctrl_, (int)N_, resampler, R_, key_,
@@ -1413,7 +1419,8 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler) {
   t_ = t;
   logw_valid_ = !implicit_logw;
   y_cur_ = y;
-  dv_w_ = dv_;  // the parameters these weights were computed with (step() may be handed new ones)
+  dv_w_ = dv_;
+  sum_done_ = false;  // the parameters these weights were computed with (step() may be handed new ones)
 }
 
 static void check_args(int kind, int64_t N, int resampler) {
@@ -1439,7 +1446,7 @@ void SingleFilter::init(int kind, const double* params, int64_t N, double y0, co
   derive_params(kind, params, dv_.d);
   begin_call();
   launch_init(y0);
-  launch_scan(0, false);
+  launch_sum(0);
   SMCB_CUDA_TRY(cudaMemcpyAsync(&last_, stats_dev_, sizeof(StepStats), cudaMemcpyDeviceToHost, stream_));
   end_call();
   if (st) *st = last_;
@@ -1452,8 +1459,9 @@ void SingleFilter::step(const double* params, double y, int resampler, StepStats
   if (params) derive_params(kind_, params, dv_.d);
   if (!record_anc_) anc_rows_ = 0;
   begin_call();
-  launch_step(0, y, resampler);
-  launch_scan(0, false);
+  launch_step(1, y, resampler);  // (the statistics of the old weights, if it has to recompute them, go to slot 1)
+  if (resampler == RESAMPLE_MULTINOMIAL) launch_scan(0, false);
+  else launch_sum(0);            // statistics of the new weights now; the next sorted step reuses everything else
   SMCB_CUDA_TRY(cudaMemcpyAsync(&last_, stats_dev_, sizeof(StepStats), cudaMemcpyDeviceToHost, stream_));
   end_call();
   if (st) *st = last_;
@@ -1480,7 +1488,8 @@ void SingleFilter::run(int kind, const double* params, int64_t N, const double* 
   for (int64_t t = 1; t < T; ++t) {
     launch_step(t - 1, y[t], resampler);  // stats of time t-1, then the step to time t
   }
-  launch_scan(T - 1, false);
+  if (resampler == RESAMPLE_MULTINOMIAL) launch_scan(T - 1, false);
+  else launch_sum(T - 1);
   std::vector<StepStats> tmp;
   SMCB_CUDA_TRY(cudaMemcpyAsync(stats_out, stats_dev_, sizeof(StepStats) * T, cudaMemcpyDeviceToHost, stream_));
   end_call();
@@ -1531,7 +1540,7 @@ void SingleFilter::load_vector(const double* host, int64_t n, bool is_log) {
   }
   kind_ = KIND_LG1D; d_ = 0; N_ = n; ld_ = cap_N_;
   S_ = quant_shift((uint64_t)n); R_ = strata_width((uint64_t)n);
-  t_ = 0; cur_ = 0; anc_rows_ = 0; from_w_ = !is_log; logw_valid_ = true;
+  t_ = 0; cur_ = 0; anc_rows_ = 0; from_w_ = !is_log; logw_valid_ = true; sum_done_ = false;
   SMCB_CUDA_TRY(cudaMemsetAsync(desc_, 0, sizeof(unsigned long long) * 2 * ntiles_cap_, stream_));
   reset_ctrl_kernel<<<1, 1, 0, stream_>>>(ctrl_);
   SMCB_CUDA_TRY(cudaMemcpyAsync(logw_[cur_], host, sizeof(double) * n, cudaMemcpyHostToDevice, stream_));

@@ -21,6 +21,20 @@ struct FilterCtrl {
   unsigned int scan_done;
 };
 
+// index of the sorted-resampler step (device pointers + tile geometry), passed to the kernels by value
+struct StepIndex {
+  unsigned long long* tile_tot;   // [ntiles]
+  unsigned long long* tile_lexcl; // [ntiles] exclusive prefix of the tile inside its sum_kernel CTA (8 tiles)
+  unsigned long long* cta_tot;    // [ntiles / 8] total of each sum_kernel CTA
+  unsigned long long* tile_excl;  // [ntiles] global exclusive prefix of the tile
+  unsigned long long* tile_incl;  // [ntiles]
+  int32_t* bound_pos;             // [nblocks + 1] ancestor of each propagate CTA's first particle (last: of particle N-1)
+  int32_t* bound_tile;            // [nblocks + 1] its tile
+  int ntiles;
+  int chunks_per_tile;
+  int tile_items;
+};
+
 struct StepStats {  // normalize() ingredients for one time step (SPEC §6)
   double mx, sum, sum2;
 };
@@ -71,6 +85,8 @@ class SingleFilter {
   void launch_prop(double y, int resampler);
   void launch_step(int64_t stat_index, double y, int resampler);  // one bootstrap_filter! step
   void launch_scan(int64_t stat_index, bool write_cdf);
+  void launch_sum(int64_t stat_index);
+  unsigned long long* step_index(StepIndex& ix);
   void mark(int klass, bool start);
   void release();
 
@@ -104,6 +120,7 @@ class SingleFilter {
   int32_t* bound_arrays_ = nullptr;            // [2][bound_cap_]: ancestor of each propagate CTA's first particle, its tile
   int64_t bound_cap_ = 0;
   int num_sms_ = 0;
+  bool sum_done_ = false;   // sum_kernel already ran for the current weights (statistics read by a stepping caller)
   bool logw_valid_ = true;  // logw_[cur_] holds the current log-weights (false: implicit in x_[cur_] and y_cur_)
   double y_cur_ = 0.0;      // observation the current weights were computed against
   Derived dv_w_{};          // ... and the derived parameters they were computed with
