@@ -226,3 +226,27 @@ def test_device_detmath_bit_exact(ctx, oracle):
     S = oracle.quant_shift(1 << 24)
     q, _ = ctx.selftest_math(3, x[x <= 0], aux=S)
     np.testing.assert_array_equal(q.view(np.uint64), oracle.det_quant(x[x <= 0], S))
+
+
+def test_stepping_with_mixed_resamplers_and_changing_parameters(ctx, oracle):
+    """The stepping API across every resampler transition and with new model parameters handed to a
+    step: the weights being resampled are those computed under the OLD parameters (the LG1D path keeps
+    them implicit in x), the transition and the new weights use the NEW ones."""
+    kind, N, T = smc.KIND_LG1D, 6000, 13
+    y = _data(oracle, kind, T)
+    seq = [smc.SYSTEMATIC, smc.SYSTEMATIC, smc.MULTINOMIAL, smc.STRATIFIED, smc.SYSTEMATIC, smc.MULTINOMIAL,
+           smc.MULTINOMIAL, smc.STRATIFIED, smc.STRATIFIED, smc.SYSTEMATIC, smc.MULTINOMIAL, smc.SYSTEMATIC]
+    P0, P1 = MODELS[kind], [0.7, 1.0, 0.5, 1.3, 0.0, 1.0]
+    ctx.set_rng(33, 4)
+    ctx.bootstrap_init(kind, P0, N, y[0], stream=1)
+    xo, lwo = oracle.bootstrap_init(kind, P0, N, y[0], 33, 4, 1)
+    for t in range(1, T):
+        P = P1 if t >= 6 else P0
+        lm, es = ctx.bootstrap_step(y[t], seq[t - 1], P)
+        oracle.bootstrap_step(kind, P, xo, lwo, y[t], t, seq[t - 1], 33, 4, 1)
+        lmo, _, eso = oracle.normalize(lwo)
+        assert abs(lm - lmo) <= RTOL * abs(lmo) and abs(es - eso) <= RTOL * eso
+        if t in (3, 6, 12):
+            x, w, lw = ctx.fetch_state(want_logw=True)
+            np.testing.assert_array_equal(x, xo)
+            np.testing.assert_array_equal(lw, lwo)
