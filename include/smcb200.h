@@ -101,6 +101,14 @@ int smcb_log_likelihood(smcb_ctx* ctx, int kind, const double* params, int64_t N
                         int resampler, uint32_t stream, double* logZ, double* logmu_out, double* ess_out);
 /* x [d*N] SoA, w [N] normalised weights, logw [N] unnormalised log-weights; any may be NULL */
 int smcb_fetch_state(smcb_ctx* ctx, double* x, double* w, double* logw);
+/* Summaries of the current cloud computed ON THE DEVICE — what the reference's per-step
+ * `quantile(x, [0.25,0.5,0.75])` (README.md:41,51) and `quantile(x, weights(w), p)` / `var(x, weights(w))`
+ * (examples/inflation_example.jl:39-55) need, without the 16 B/particle read-back.  weighted != 0 uses the
+ * current weights (their fixed-point values, docs/SPEC.md §8), else every particle counts once.
+ * mean [d], var [d] (population variance), quantiles [d][nprobs] (lower empirical quantile: the smallest
+ * x whose cumulative weight exceeds p); any output may be NULL, nprobs <= 16. */
+int smcb_weighted_summary(smcb_ctx* ctx, const double* probs, int nprobs, int weighted, double* mean, double* var,
+                          double* quantiles);
 /* ancestors of steps t = 1 .. T-1 ([T-1][N], row t-1 = step t) if recording was on, else the
  * last step's only when stepping with bootstrap_step (rows = 1); 0 rows when recording is off.
  * rows_cap = rows the buffer can take. */

@@ -85,6 +85,19 @@ function weights(c::Cloud)
     return w
 end
 
+# quantile(x, p) (README.md:41,51) and quantile(x, weights(w), p), var(x, weights(w)) (examples/inflation_example.jl:44-46)
+# of a device-resident cloud, computed on the device: nothing is read back (docs/SPEC.md §8)
+function summary(c::Cloud, p::Vector{Float64}; weighted::Bool=true)
+    m = Vector{Float64}(undef, c.d); v = similar(m); q = Matrix{Float64}(undef, length(p), c.d)   # [np,d] col-major == C [d][np]
+    check(c.ctx, ccall((:smcb_weighted_summary, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                       c.ctx.h, p, length(p), weighted, m, v, q))
+    return m, v, q
+end
+Statistics.quantile(c::Cloud, p::Vector{Float64}) = (q = summary(c, p; weighted=false)[3]; c.d == 1 ? vec(q) : q)
+Statistics.quantile(c::Cloud, ::Cloud, p::Vector{Float64}) = (q = summary(c, p)[3]; c.d == 1 ? vec(q) : q)   # second argument: the weights handle
+Statistics.var(c::Cloud, ::Cloud) = (v = summary(c, Float64[])[2]; c.d == 1 ? v[1] : v)
+Statistics.mean(c::Cloud, ::Cloud) = (m = summary(c, Float64[])[1]; c.d == 1 ? m[1] : m)
+
 function normalize(logw::Vector{Float64}; ctx=context())                                       # :5-15
     w = similar(logw); lm = Ref(0.0); es = Ref(0.0)
     check(ctx, ccall((:smcb_normalize, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Ref{Float64}, Ptr{Float64}, Ref{Float64}),

@@ -230,6 +230,35 @@ def batch_log_likelihood(kind, params, active, n, y, resampler, seed, epoch, str
     return logZ, x, logw
 
 
+def weighted_summary(x, logw, probs, weighted=True):
+    """SPEC §8 restated with numpy: fixed-point weights q_i of the current log-weights (SPEC §5), population mean /
+    variance, and lower empirical quantiles = the smallest x whose cumulative q exceeds r = min(floor(p Q), Q - 1).
+    x: [d, n].  Stands in for quantile(x, weights(w), p) / var(x, weights(w)) of examples/inflation_example.jl:44-46
+    (StatsBase, un-pinned: SURVEY F8) and for quantile(x, p) of README.md:41,51 when weighted=False."""
+    x = np.atleast_2d(np.asarray(x, np.float64))
+    n = x.shape[1]
+    if weighted:
+        lw = np.asarray(logw, np.float64)
+        q = det_quant(lw - lw.max(), quant_shift(n)).astype(object)    # exact Python integers
+    else:
+        q = np.ones(n, dtype=object)
+    Q = int(q.sum())
+    qd = np.array([float(v) for v in q])
+    probs = np.atleast_1d(np.asarray(probs, np.float64))
+    mean, var, quant = np.empty(x.shape[0]), np.empty(x.shape[0]), np.empty((x.shape[0], probs.size))
+    for c in range(x.shape[0]):
+        keep = qd != 0
+        mean[c] = np.sum(qd[keep] * x[c][keep]) / float(Q)
+        var[c] = np.sum(qd[keep] * (x[c][keep] - mean[c]) ** 2) / float(Q)
+        order = np.argsort(x[c], kind="stable")
+        cum = np.cumsum(q[order])                                       # object dtype: exact
+        for j, p in enumerate(probs):
+            r = min(int(np.uint64(np.float64(p) * np.float64(Q))) if p * float(Q) < 1.8e19 else Q - 1, Q - 1)
+            k = next(i for i, cv in enumerate(cum) if cv > r)
+            quant[c, j] = x[c][order][k]
+    return mean, var, quant
+
+
 def num_threads():
     return int(lib().smco_num_threads())
 

@@ -62,6 +62,7 @@ SIGNATURES = {
     "smcb_rng_normals": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int64, C.c_void_p]),
     "smcb_rng_uniforms64": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int64, C.c_void_p]),
     "smcb_simulate": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "smcb_weighted_summary": (C.c_int, [_c_ctx, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "smcb_selftest_math": (C.c_int, [_c_ctx, C.c_int, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p]),
 }
 
@@ -271,6 +272,15 @@ class Context:
         lw = (self.pinned_array("logw", (self._N,)) if big else np.empty(self._N)) if want_logw else None
         self._check(self._lib.smcb_fetch_state(self._h, _ptr(x), _ptr(w), _ptr(lw)))
         return x, w, lw
+
+    def summary(self, probs=(), weighted=True):
+        """(mean [d], var [d], quantiles [d, len(probs)]) of the current cloud, computed on the device."""
+        d = state_dim(self._kind)
+        p = np.ascontiguousarray(probs, np.float64).ravel()
+        mean, var, q = np.empty(d), np.empty(d), np.empty((d, p.size))
+        self._check(self._lib.smcb_weighted_summary(self._h, _ptr(p) if p.size else None, int(p.size), int(bool(weighted)),
+                                                    _ptr(mean), _ptr(var), _ptr(q) if p.size else None))
+        return mean, var, q
 
     def fetch_ancestors(self, rows):
         a = np.empty((max(int(rows), 1), self._N), np.int64)

@@ -225,6 +225,14 @@ int smcb_fetch_state(smcb_ctx* ctx, double* x, double* w, double* logw) {
   return guarded(ctx, [&] { ctx->filter->fetch(x, w, logw); });
 }
 
+int smcb_weighted_summary(smcb_ctx* ctx, const double* probs, int nprobs, int weighted, double* mean, double* var, double* quantiles) {
+  if (!ctx) return SMCB_ERR_BAD_ARG;
+  return guarded(ctx, [&] {
+    need(nprobs == 0 || (probs && quantiles), "weighted_summary: probabilities without an output buffer");
+    ctx->filter->summary(probs, nprobs, weighted != 0, mean, var, quantiles);
+  });
+}
+
 int smcb_fetch_ancestors(smcb_ctx* ctx, int64_t* ancestors, int64_t rows_cap, int64_t* rows_out) {
   if (!ctx) return SMCB_ERR_BAD_ARG;
   return guarded(ctx, [&] {

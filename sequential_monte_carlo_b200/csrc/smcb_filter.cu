@@ -1118,6 +1118,87 @@ __global__ void weights_kernel(const double* __restrict__ logw, double* __restri
   if (i < N) w[i] = det_exp(logw[i] - st.mx) / st.sum;
 }
 
+// ------------------------------------------------------------------------------------------------
+// On-device weighted summaries of the current cloud (docs/SPEC.md §8): the per-step
+// `quantile(x, weights(w), p)` / `var(x, weights(w))` of README.md:41,51 and
+// examples/inflation_example.jl:39-55 without reading 16 B per particle back to the host.
+// Weights are the fixed-point q_i of SPEC §5 (recovered from the tile-local CDF that sum_kernel left
+// behind), so every count is an exact integer and the quantiles are bit-reproducible.
+constexpr int kSumThreadsW = 256;
+constexpr int kMaxProbs = 16;
+
+__device__ __forceinline__ unsigned long long q_of(const unsigned long long* __restrict__ cl, int64_t i, int tile_items, bool weighted) {
+  if (!weighted) return 1ull;
+  const unsigned long long c = cl[i];
+  return (i % tile_items == 0) ? c : c - cl[i - 1];
+}
+
+// mode 0: part[b] = Σ q x ; mode 1: part[b] = Σ q (x - mean)^2   (per-block partials, fixed order)
+__global__ void __launch_bounds__(kSumThreadsW)
+    wmoment_kernel(const double* __restrict__ x, const unsigned long long* __restrict__ cl, int64_t N, int tile_items, int weighted,
+                   int mode, double mean, double* __restrict__ part) {
+  __shared__ double sh[kSumThreadsW / 32];
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * kSumThreadsW + threadIdx.x; i < N; i += (int64_t)gridDim.x * kSumThreadsW) {
+    const double qd = (double)q_of(cl, i, tile_items, weighted != 0);
+    const double v = x[i];
+    if (qd != 0.0) acc += mode == 0 ? qd * v : qd * ((v - mean) * (v - mean));  // q = 0: an infinite state must not poison the sum
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < kSumThreadsW / 32; ++w) t += sh[w];
+    part[blockIdx.x] = t;
+  }
+}
+
+// one radix-select pass (8 bits, most significant first) for np probabilities at once:
+// hist[j][digit] += q_i for the particles whose key agrees with prefix[j] in the digits already fixed
+__global__ void __launch_bounds__(kSumThreadsW)
+    rsel_hist_kernel(const double* __restrict__ x, const unsigned long long* __restrict__ cl, int64_t N, int tile_items, int weighted,
+                     int pass, int np, const unsigned long long* __restrict__ prefix, unsigned long long* __restrict__ hist) {
+  __shared__ unsigned long long s_hist[kMaxProbs * 256];
+  __shared__ unsigned long long s_prefix[kMaxProbs];
+  for (int k = threadIdx.x; k < np * 256; k += kSumThreadsW) s_hist[k] = 0ull;
+  if (threadIdx.x < np) s_prefix[threadIdx.x] = prefix[threadIdx.x];
+  __syncthreads();
+  const int shift = 56 - 8 * pass;
+  for (int64_t i = (int64_t)blockIdx.x * kSumThreadsW + threadIdx.x; i < N; i += (int64_t)gridDim.x * kSumThreadsW) {
+    const unsigned long long q = q_of(cl, i, tile_items, weighted != 0);
+    if (q == 0ull) continue;
+    const unsigned long long key = encode_ordered(x[i]);
+    const unsigned digit = (unsigned)(key >> shift) & 255u;
+    for (int j = 0; j < np; ++j) {
+      const bool match = (pass == 0) || ((key ^ s_prefix[j]) >> (shift + 8)) == 0ull;
+      if (match) atomicAdd(&s_hist[j * 256 + digit], q);
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < np * 256; k += kSumThreadsW)
+    if (s_hist[k]) atomicAdd(&hist[k], s_hist[k]);
+}
+
+// picks the digit holding rank[j] (0-based mass offset inside the current prefix), fixes it, clears the histogram
+__global__ void rsel_pick_kernel(int pass, int np, unsigned long long* __restrict__ prefix, unsigned long long* __restrict__ rank,
+                                 unsigned long long* __restrict__ hist) {
+  const int j = threadIdx.x;
+  if (j < np) {
+    unsigned long long r = rank[j], cum = 0;
+    int d = 255;
+    for (int b = 0; b < 256; ++b) {
+      const unsigned long long h = hist[j * 256 + b];
+      if (cum + h > r) { d = b; break; }
+      cum += h;
+    }
+    rank[j] = r - cum;
+    prefix[j] |= (unsigned long long)d << (56 - 8 * pass);
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < np * 256; k += blockDim.x) hist[k] = 0ull;
+}
+
 // utilities (normalize / resample on caller-supplied vectors; θ-level sizes, not hot)
 __global__ void max_kernel(const double* __restrict__ v, int64_t n, FilterCtrl* ctrl) {
   __shared__ double sh[32];
@@ -1170,8 +1251,8 @@ SingleFilter::~SingleFilter() {
 void SingleFilter::release() {
   cudaFree(x_[0]); cudaFree(x_[1]); cudaFree(logw_[0]); cudaFree(logw_[1]); cudaFree(w_tmp_); cudaFree(cdf_); cudaFree(anc_);
   cudaFree(ctrl_); cudaFree(desc_); cudaFree(psum_); cudaFree(psum2_); cudaFree(stats_dev_);
-  cudaFree(tile_arrays_); cudaFree(bound_arrays_);
-  tile_arrays_ = nullptr; bound_arrays_ = nullptr; bound_cap_ = 0;
+  cudaFree(tile_arrays_); cudaFree(bound_arrays_); cudaFree(summary_dev_);
+  tile_arrays_ = nullptr; bound_arrays_ = nullptr; bound_cap_ = 0; summary_dev_ = nullptr; summary_cap_ = 0;
   x_[0] = x_[1] = logw_[0] = logw_[1] = w_tmp_ = psum_ = psum2_ = nullptr;
   cdf_ = nullptr; anc_ = nullptr; ctrl_ = nullptr; desc_ = nullptr; stats_dev_ = nullptr;
   cap_N_ = cap_d_ = cap_stats_ = cap_anc_rows_ = ntiles_cap_ = 0;
@@ -1494,6 +1575,92 @@ void SingleFilter::run(int kind, const double* params, int64_t N, const double* 
   SMCB_CUDA_TRY(cudaMemcpyAsync(stats_out, stats_dev_, sizeof(StepStats) * T, cudaMemcpyDeviceToHost, stream_));
   end_call();
   last_ = stats_out[T - 1];
+}
+
+// weighted (or plain) mean, variance and quantiles of every state component of the current cloud
+void SingleFilter::summary(const double* probs, int np, bool weighted, double* mean_out, double* var_out, double* q_out) {
+  if (!live()) throw Error{SMCB_ERR_STATE, "no filter state to summarise"};
+  if (np < 0 || np > kMaxProbs) throw Error{SMCB_ERR_BAD_ARG, "at most 16 probabilities per call"};
+  for (int j = 0; j < np; ++j)
+    if (!(probs[j] >= 0.0 && probs[j] <= 1.0)) throw Error{SMCB_ERR_BAD_ARG, "probabilities must lie in [0, 1]"};
+  SMCB_CUDA_TRY(cudaSetDevice(device_));
+  StepIndex ix;
+  unsigned long long* cl = step_index(ix);
+  unsigned long long Q = (unsigned long long)N_;
+  if (weighted) {
+    if (cap_stats_ < 2) {  // slot 1 is scratch for the statistics sum_kernel writes
+      StepStats* nd = nullptr;
+      SMCB_CUDA_TRY(cudaMalloc(&nd, sizeof(StepStats) * 2));
+      if (stats_dev_) SMCB_CUDA_TRY(cudaMemcpyAsync(nd, stats_dev_, sizeof(StepStats) * cap_stats_, cudaMemcpyDeviceToDevice, stream_));
+      SMCB_CUDA_TRY(cudaStreamSynchronize(stream_));
+      cudaFree(stats_dev_);
+      stats_dev_ = nd;
+      cap_stats_ = 2;
+    }
+    if (!sum_done_) launch_sum(1);  // the tile-local CDF of the current weights (and Q)
+    FilterCtrl hc;
+    SMCB_CUDA_TRY(cudaMemcpyAsync(&hc, ctrl_, sizeof(FilterCtrl), cudaMemcpyDeviceToHost, stream_));
+    SMCB_CUDA_TRY(cudaStreamSynchronize(stream_));
+    Q = hc.total;
+  }
+  const int nblk = (int)std::min<int64_t>((N_ + kSumThreadsW - 1) / kSumThreadsW, (int64_t)num_sms_ * 8);
+  const size_t scratch_words = (size_t)nblk + 2 * kMaxProbs + (size_t)kMaxProbs * 256;
+  if (summary_cap_ < scratch_words) {
+    cudaFree(summary_dev_); summary_dev_ = nullptr; summary_cap_ = 0;
+    SMCB_CUDA_TRY(cudaMalloc(&summary_dev_, sizeof(unsigned long long) * scratch_words));
+    summary_cap_ = scratch_words;
+  }
+  double* part = reinterpret_cast<double*>(summary_dev_);
+  unsigned long long* prefix = summary_dev_ + nblk;
+  unsigned long long* rank = prefix + kMaxProbs;
+  unsigned long long* hist = rank + kMaxProbs;
+  std::vector<double> hpart((size_t)nblk);
+  for (int c = 0; c < d_; ++c) {
+    const double* xc = x_[cur_] + (int64_t)c * ld_;
+    double mean = NAN, var = NAN;
+    if (Q != 0 && (mean_out || var_out)) {
+      for (int mode = 0; mode < (var_out ? 2 : 1); ++mode) {
+        wmoment_kernel<<<nblk, kSumThreadsW, 0, stream_>>>(xc, cl, N_, ix.tile_items, weighted ? 1 : 0, mode, mean, part);
+        SMCB_CUDA_TRY(cudaGetLastError());
+        SMCB_CUDA_TRY(cudaMemcpyAsync(hpart.data(), part, sizeof(double) * nblk, cudaMemcpyDeviceToHost, stream_));
+        SMCB_CUDA_TRY(cudaStreamSynchronize(stream_));
+        double t = 0.0;
+        for (int b = 0; b < nblk; ++b) t += hpart[(size_t)b];
+        if (mode == 0) mean = t / (double)Q; else var = t / (double)Q;
+      }
+    }
+    if (mean_out) mean_out[c] = mean;
+    if (var_out) var_out[c] = var;
+    if (np > 0 && q_out) {
+      if (Q == 0) {
+        for (int j = 0; j < np; ++j) q_out[(size_t)c * np + j] = NAN;
+        continue;
+      }
+      unsigned long long hr[kMaxProbs], hp[kMaxProbs];
+      for (int j = 0; j < np; ++j) {  // SPEC §8: r = min(floor(p Q), Q - 1); the quantile is the smallest x with mass(<= x) > r
+        unsigned long long r = (unsigned long long)(probs[j] * (double)Q);
+        hr[j] = r > Q - 1 ? Q - 1 : r;
+        hp[j] = 0ull;
+      }
+      SMCB_CUDA_TRY(cudaMemcpyAsync(rank, hr, sizeof(unsigned long long) * np, cudaMemcpyHostToDevice, stream_));
+      SMCB_CUDA_TRY(cudaMemcpyAsync(prefix, hp, sizeof(unsigned long long) * np, cudaMemcpyHostToDevice, stream_));
+      SMCB_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * kMaxProbs * 256, stream_));
+      for (int pass = 0; pass < 8; ++pass) {
+        rsel_hist_kernel<<<nblk, kSumThreadsW, 0, stream_>>>(xc, cl, N_, ix.tile_items, weighted ? 1 : 0, pass, np, prefix, hist);
+        rsel_pick_kernel<<<1, 256, 0, stream_>>>(pass, np, prefix, rank, hist);
+      }
+      SMCB_CUDA_TRY(cudaGetLastError());
+      SMCB_CUDA_TRY(cudaMemcpyAsync(hp, prefix, sizeof(unsigned long long) * np, cudaMemcpyDeviceToHost, stream_));
+      SMCB_CUDA_TRY(cudaStreamSynchronize(stream_));
+      for (int j = 0; j < np; ++j) {
+        const unsigned long long e = hp[j];
+        const unsigned long long b = (e >> 63) ? (e & 0x7FFFFFFFFFFFFFFFull) : ~e;  // decode_ordered on the host
+        double v;
+        std::memcpy(&v, &b, sizeof v);
+        q_out[(size_t)c * np + j] = v;
+      }
+    }
+  }
 }
 
 void SingleFilter::fetch(double* x_host, double* w_host, double* logw_host) {

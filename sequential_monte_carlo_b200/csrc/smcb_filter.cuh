@@ -61,6 +61,8 @@ class SingleFilter {
                        uint32_t t, uint32_t purpose, int64_t* anc_host);
 
   void fetch(double* x_host, double* w_host, double* logw_host);
+  // weighted mean / variance / quantiles of each state component, computed on the device (SPEC §8)
+  void summary(const double* probs, int np, bool weighted, double* mean_out, double* var_out, double* q_out);
   int64_t fetch_ancestors(int64_t* anc_host, int64_t rows_cap);
 
   void set_record_ancestors(bool on) { record_anc_ = on; }
@@ -117,6 +119,8 @@ class SingleFilter {
   unsigned long long* desc_ = nullptr;  // [2][ntiles_cap]
   // tile index of the sorted-resampler step (sum -> bounds -> prop2)
   unsigned long long* tile_arrays_ = nullptr;  // [5][kMaxTiles]: tot, excl, incl, lexcl, cta_tot
+  unsigned long long* summary_dev_ = nullptr;  // scratch of summary(): block partials, radix-select prefixes / ranks / histograms
+  size_t summary_cap_ = 0;
   int32_t* bound_arrays_ = nullptr;            // [2][bound_cap_]: ancestor of each propagate CTA's first particle, its tile
   int64_t bound_cap_ = 0;
   int num_sms_ = 0;

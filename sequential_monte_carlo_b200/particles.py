@@ -121,6 +121,27 @@ def bootstrap_filter_(states, weights, y, model, *, resampler="multinomial"):
     return logmu, _DeviceArray(ctx, ctx._gen, "w"), ess
 
 
+def quantile(x, w_or_p, p=None):
+    """quantile(x, p) (README.md:41,51: every particle counts once) or quantile(x, weights(w), p)
+    (examples/inflation_example.jl:44) of a cloud that lives on the device — computed there, nothing is
+    read back.  Lower empirical quantile (no interpolation); one row per state component."""
+    weighted = p is not None
+    probs = np.atleast_1d(np.asarray(p if weighted else w_or_p, np.float64))
+    if x._stale():
+        raise RuntimeError("stale particle cloud")
+    q = x._ctx.summary(probs, weighted=weighted)[2]
+    return q[0] if q.shape[0] == 1 else q.T
+
+
+def weighted_mean_var(x, w=None):
+    """(mean, var) of the cloud x under the weights w (mean(x, weights(w)), var(x, weights(w)):
+    examples/inflation_example.jl:46), on the device."""
+    if x._stale():
+        raise RuntimeError("stale particle cloud")
+    m, v, _ = x._ctx.summary((), weighted=w is not None)
+    return (m[0], v[0]) if m.size == 1 else (m, v)
+
+
 def log_likelihood(N, y, model, *, resampler="multinomial", ctx=None, stream=0):
     """x, w, logZ = log_likelihood(N, y, model)  — particles.jl:132-147, one call for the whole series."""
     ctx = ctx or default_context()

@@ -250,3 +250,33 @@ def test_stepping_with_mixed_resamplers_and_changing_parameters(ctx, oracle):
             x, w, lw = ctx.fetch_state(want_logw=True)
             np.testing.assert_array_equal(x, xo)
             np.testing.assert_array_equal(lw, lwo)
+
+
+@pytest.mark.parametrize("kind", [smc.KIND_LG1D, smc.KIND_UCSV])
+def test_on_device_summaries(ctx, oracle, kind):
+    """docs/SPEC.md §8: weighted / plain mean, variance and quantiles of the cloud computed on the device
+    (README.md:41,51; examples/inflation_example.jl:39-55) against the oracle's sort-and-cumulate restatement:
+    quantiles bit-exact, moments at the fp64 tolerance."""
+    N, T = 20011, 9
+    y = _data(oracle, kind, T)
+    probs = [0.0, 0.05, 0.25, 0.5, 0.75, 0.95, 1.0]
+    for resampler in (smc.SYSTEMATIC, smc.MULTINOMIAL):
+        ref = oracle.log_likelihood(kind, MODELS[kind], N, y, resampler, 17, 2, 0)
+        ctx.set_rng(17, 2)
+        ctx.log_likelihood(kind, MODELS[kind], N, y, resampler, 0)
+        for weighted in (True, False):
+            m, v, q = ctx.summary(probs, weighted=weighted)
+            mo, vo, qo = oracle.weighted_summary(ref["x"], ref["logw"], probs, weighted=weighted)
+            np.testing.assert_array_equal(q, qo)
+            np.testing.assert_allclose(m, mo, rtol=RTOL, atol=1e-13)
+            np.testing.assert_allclose(v, vo, rtol=RTOL)
+        assert np.all(np.diff(q, axis=1) >= 0)
+    # the stepping API: summaries after every step, the cloud never leaves the device
+    ctx.set_rng(17, 3)
+    ctx.bootstrap_init(kind, MODELS[kind], N, y[0], 0)
+    xo, lwo = oracle.bootstrap_init(kind, MODELS[kind], N, y[0], 17, 3, 0)
+    for t in range(1, 4):
+        ctx.bootstrap_step(y[t], smc.SYSTEMATIC)
+        oracle.bootstrap_step(kind, MODELS[kind], xo, lwo, y[t], t, oracle.SYSTEMATIC, 17, 3, 0)
+        _, _, q = ctx.summary([0.25, 0.5, 0.75])
+        np.testing.assert_array_equal(q, oracle.weighted_summary(xo, lwo, [0.25, 0.5, 0.75])[2])

@@ -180,3 +180,18 @@ def test_batch_oracle_equals_loop(oracle):
         r = oracle.log_likelihood(0, P[m], N, y, 0, 8, 4, 20 + m)
         assert r["logZ"] == z[m]
         np.testing.assert_array_equal(r["x"], x[m])
+
+
+def test_weighted_summary_restatement(oracle):
+    """SPEC §8 on a case small enough to check by hand, and against numpy on equal weights."""
+    x = np.array([[3.0, -1.0, 2.0, 10.0]])
+    lw = np.log(np.array([0.25, 0.25, 0.5, 1e-300]))
+    m, v, q = oracle.weighted_summary(x, lw, [0.0, 0.2, 0.3, 0.6, 1.0])
+    np.testing.assert_allclose(m, [1.5], rtol=1e-12)
+    np.testing.assert_allclose(v, [0.25 * 2.25 + 0.25 * 6.25 + 0.5 * 0.25], rtol=1e-12)
+    np.testing.assert_array_equal(q, [[-1.0, -1.0, 2.0, 2.0, 3.0]])          # cumulative weights: -1: .25, 2: .75, 3: 1
+    rng = np.random.default_rng(0)
+    z = rng.normal(size=(1, 1001))
+    _, _, q = oracle.weighted_summary(z, None, [0.5, 0.25], weighted=False)
+    s = np.sort(z[0])
+    assert q[0, 0] == s[500] and q[0, 1] == s[250]

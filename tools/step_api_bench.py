@@ -19,3 +19,14 @@ for logn in (20, 24):
         dev += ctx.timing()[0]["total"]
     wall = (time.perf_counter() - t0) / 32
     print(f"N=2^{logn}: bootstrap_filter! {1e6 * wall:.1f} us wall per call, {1e3 * dev / 32:.1f} us device", flush=True)
+    # on-device summaries after a step (docs/SPEC.md §8) against reading the cloud back
+    t0 = time.perf_counter()
+    for _ in range(5):
+        m, v, q = ctx.summary([0.25, 0.5, 0.75])
+    t_dev = (time.perf_counter() - t0) / 5
+    t0 = time.perf_counter()
+    for _ in range(3):
+        x, w, _ = ctx.fetch_state()
+    t_host = (time.perf_counter() - t0) / 3
+    print(f"N=2^{logn}: weighted mean/var/3 quantiles on the device {1e3 * t_dev:.2f} ms; reading x, w back (pinned) {1e3 * t_host:.2f} ms "
+          f"(+ the host-side sort)", flush=True)
