@@ -139,6 +139,9 @@ int smcb_batch_gather(smcb_batch* b, const int32_t* parents);
 int smcb_batch_accept(smcb_batch* current, const smcb_batch* proposal, const uint8_t* accept);
 /* x [M][d][N], w [M][N] normalised, logw [M][N]; any may be NULL */
 int smcb_batch_fetch(smcb_batch* b, double* x, double* w, double* logw);
+/* mean [M][d]: the weighted state mean w[m]' * x[m] of every θ-particle's cloud, computed on the device — what
+ * estimated_trend(smc) and quantile(smc, p) integrate over θ (plotting_utils.jl:116-124,140-157) */
+int smcb_batch_weighted_mean(smcb_batch* b, double* mean);
 /* cross-GPU moves of whole clouds (θ-resample across ranks): pack slot m into / unpack from a
  * device buffer of smcb_batch_cloud_bytes(b) bytes that the caller sends with NCCL / P2P */
 int64_t smcb_batch_cloud_bytes(const smcb_batch* b);

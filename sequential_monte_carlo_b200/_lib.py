@@ -52,6 +52,7 @@ SIGNATURES = {
     "smcb_batch_gather": (C.c_int, [_c_batch, C.c_void_p]),
     "smcb_batch_accept": (C.c_int, [_c_batch, _c_batch, C.c_void_p]),
     "smcb_batch_fetch": (C.c_int, [_c_batch, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "smcb_batch_weighted_mean": (C.c_int, [_c_batch, C.c_void_p]),
     "smcb_batch_cloud_bytes": (C.c_int64, [_c_batch]),
     "smcb_batch_pack": (C.c_int, [_c_batch, C.c_void_p, C.c_int64, C.c_void_p]),
     "smcb_batch_unpack": (C.c_int, [_c_batch, C.c_void_p, C.c_int64, C.c_void_p]),
@@ -388,6 +389,12 @@ class Batch:
         lw = np.empty((self.M, self.N)) if want_logw else None
         self.ctx._check(self._lib.smcb_batch_fetch(self._h, _ptr(x), _ptr(w), _ptr(lw)))
         return x, w, lw
+
+    def weighted_mean(self):
+        """[M, d] weighted state means w[m]' x[m], computed on the device."""
+        out = np.empty((self.M, self.d))
+        self.ctx._check(self._lib.smcb_batch_weighted_mean(self._h, _ptr(out)))
+        return out
 
     def cloud_bytes(self):
         return int(self._lib.smcb_batch_cloud_bytes(self._h))

@@ -358,6 +358,32 @@ __global__ void batch_weights_kernel(const double* __restrict__ logw, const Step
   if (i < N) w[m * N + i] = det_exp(logw[m * ld + i] - st[m].mx) / st[m].sum;
 }
 
+// mean[m][c] = w[m]' x[m][c]  (plotting_utils.jl:116-124,150: the weighted state mean of every θ-particle's cloud);
+// one CTA per (m, c), fixed summation order
+__global__ void __launch_bounds__(256)
+    batch_wmean_kernel(const double* __restrict__ x, const double* __restrict__ logw, const StepStats* __restrict__ st, double* __restrict__ mean,
+                       int64_t N, int64_t ld, int d) {
+  __shared__ double sh[8];
+  const int64_t m = blockIdx.x;
+  const int c = blockIdx.y;
+  const double mx = st[m].mx;
+  const double* xc = x + (m * d + c) * ld;
+  const double* lw = logw + m * ld;
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < N; i += 256) {
+    const double e = det_exp(lw[i] - mx);
+    if (e != 0.0) acc += e * xc[i];
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += sh[w];
+    mean[m * d + c] = t / st[m].sum;
+  }
+}
+
 // scalar Kalman recursion, one thread per model                                 kalman_filter.jl:29-70
 __global__ void kalman_kernel(const double* __restrict__ params, const uint8_t* __restrict__ active, int64_t M,
                               const double* __restrict__ y, int64_t T, int predict_first, double* __restrict__ loglik,
@@ -629,6 +655,17 @@ void BatchFilter::fetch(double* x_host, double* w_host, double* logw_host) {
     SMCB_CUDA_TRY(cudaGetLastError());
     SMCB_CUDA_TRY(cudaMemcpyAsync(w_host, w_tmp_, sizeof(double) * M_ * N_, cudaMemcpyDeviceToHost, stream_));
   }
+  SMCB_CUDA_TRY(cudaStreamSynchronize(stream_));
+}
+
+void BatchFilter::weighted_mean(double* mean_host) {
+  if (!live_) throw Error{SMCB_ERR_STATE, "no batch state to summarise"};
+  SMCB_CUDA_TRY(cudaSetDevice(device_));
+  if (!w_tmp_) SMCB_CUDA_TRY(cudaMalloc(&w_tmp_, sizeof(double) * M_ * N_));  // scratch (>= M*d doubles: N >= d)
+  dim3 grid((unsigned)M_, (unsigned)d_);
+  batch_wmean_kernel<<<grid, 256, 0, stream_>>>(x_[cur_], logw_[cur_], stats_[cur_], w_tmp_, N_, ld_, d_);
+  SMCB_CUDA_TRY(cudaGetLastError());
+  SMCB_CUDA_TRY(cudaMemcpyAsync(mean_host, w_tmp_, sizeof(double) * M_ * d_, cudaMemcpyDeviceToHost, stream_));
   SMCB_CUDA_TRY(cudaStreamSynchronize(stream_));
 }
 

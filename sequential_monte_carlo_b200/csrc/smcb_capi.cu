@@ -319,6 +319,11 @@ int smcb_batch_fetch(smcb_batch* b, double* x, double* w, double* logw) {
   return guarded(b->ctx, [&] { b->impl->fetch(x, w, logw); });
 }
 
+int smcb_batch_weighted_mean(smcb_batch* b, double* mean) {
+  if (!b || !mean) return SMCB_ERR_BAD_ARG;
+  return guarded(b->ctx, [&] { b->impl->weighted_mean(mean); });
+}
+
 int64_t smcb_batch_cloud_bytes(const smcb_batch* b) { return b ? b->impl->cloud_bytes() : 0; }
 
 int smcb_batch_pack(smcb_batch* b, const int32_t* slots, int64_t n, void* buf_dev) {

@@ -227,6 +227,38 @@ def expected_parameters(smc, reference_style=False):
     return (smc.θ * ω[:, None]).sum(axis=0)[:, None]
 
 
+def state_means(smc):
+    """[M, d]: the weighted state mean `smc.w[m]' * smc.x[m]` of every θ-particle's cloud
+    (plotting_utils.jl:120,150), computed on the device(s); the clouds are not read back."""
+    return smc.comm.all_gather(smc._cur.weighted_mean())
+
+
+def _observation_mean_sd(smc):
+    """mean and sd of observation(model(θ_m), x̄_m) for every m (state_space_models.jl:96-103,244-247)."""
+    xm, P = state_means(smc), smc._P
+    if smc.kind == _lib.LG1D:
+        return P[:, 1] * xm[:, 0], np.sqrt(P[:, 3])                    # Normal(B x, sqrt(R))
+    if smc.kind == _lib.SV:
+        return np.zeros(smc.M), np.exp(0.5 * xm[:, 0])                  # Normal(0, exp(x/2))
+    return xm[:, 0], np.exp(0.5 * xm[:, 2])                             # UCSV: Normal(x, exp(lση/2))
+
+
+def estimated_trend(smc):
+    """estimated_trend(smc) (plotting_utils.jl:116-124): Σ_m ω_m mean(observation(model(θ_m), w_m' x_m))."""
+    mu, _ = _observation_mean_sd(smc)
+    return float(np.sum(smc.ω * mu))
+
+
+def quantile_smc(smc, p):
+    """quantile(smc, p) (plotting_utils.jl:140-157): Σ_m ω_m quantile(observation(model(θ_m), w_m' x_m), p),
+    the states integrated out through their weighted means as in the reference."""
+    from statistics import NormalDist
+    p = np.sort(np.atleast_1d(np.asarray(p, np.float64)))             # sort!(p)  :144
+    z = np.array([NormalDist().inv_cdf(float(v)) for v in p])
+    mu, sd = _observation_mean_sd(smc)
+    return (smc.ω[:, None] * (mu[:, None] + sd[:, None] * z[None, :])).sum(axis=0)
+
+
 def resample_(smc):
     """resample!(smc) (smc_samplers.jl:74-84): multinomial ancestors on ω; θ, logZ and the state
     clouds (x AND w: D3; deep copies: D4) follow their parents; ω becomes uniform (D5)."""

@@ -67,6 +67,16 @@ def test_smc2_lg(ctx, oracle, resampler):
     np.testing.assert_array_equal(smc.expected_parameters(g), S.o_expected_parameters(o_) * 1.0) if False else None
     np.testing.assert_allclose(smc.expected_parameters(g), S.o_expected_parameters(o_), rtol=1e-9)
     np.testing.assert_allclose(smc.expected_parameters(g, reference_style=True), S.o_expected_parameters(o_, True), rtol=1e-9)
+    # estimated_trend / quantile(smc, p) (plotting_utils.jl:116-124,140-157): the per-θ weighted state means come
+    # from the device; restated here with numpy on the oracle's clouds
+    xm = smc.state_means(g)
+    xo = np.stack([(oracle.normalize(o_.logw[m])[1] * o_.x[m]).sum(axis=-1) for m in range(M)])
+    np.testing.assert_allclose(xm, xo.reshape(M, -1), rtol=1e-10, atol=1e-13)
+    mu, sd = g._P[:, 1] * xo.reshape(M, -1)[:, 0], np.sqrt(g._P[:, 3])
+    np.testing.assert_allclose(smc.estimated_trend(g), np.sum(g.ω * mu), rtol=1e-10)
+    from statistics import NormalDist
+    z = np.array([NormalDist().inv_cdf(v) for v in (0.05, 0.5, 0.95)])
+    np.testing.assert_allclose(smc.quantile(g, [0.95, 0.05, 0.5]), (g.ω[:, None] * (mu[:, None] + sd[:, None] * z)).sum(axis=0), rtol=1e-10)
     g.close()
 
 
