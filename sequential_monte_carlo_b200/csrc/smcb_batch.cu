@@ -649,7 +649,7 @@ void BatchFilter::fetch(double* x_host, double* w_host, double* logw_host) {
     SMCB_CUDA_TRY(cudaMemcpy2DAsync(logw_host, sizeof(double) * N_, logw_[cur_], sizeof(double) * ld_, sizeof(double) * N_, M_,
                                     cudaMemcpyDeviceToHost, stream_));
   if (w_host) {
-    if (!w_tmp_) SMCB_CUDA_TRY(cudaMalloc(&w_tmp_, sizeof(double) * M_ * N_));
+    if (!w_tmp_) SMCB_CUDA_TRY(cudaMalloc(&w_tmp_, sizeof(double) * M_ * std::max<int64_t>(N_, d_)));
     dim3 grid((unsigned)((N_ + 255) / 256), (unsigned)M_);
     batch_weights_kernel<<<grid, 256, 0, stream_>>>(logw_[cur_], stats_[cur_], w_tmp_, N_, ld_);
     SMCB_CUDA_TRY(cudaGetLastError());
@@ -661,7 +661,7 @@ void BatchFilter::fetch(double* x_host, double* w_host, double* logw_host) {
 void BatchFilter::weighted_mean(double* mean_host) {
   if (!live_) throw Error{SMCB_ERR_STATE, "no batch state to summarise"};
   SMCB_CUDA_TRY(cudaSetDevice(device_));
-  if (!w_tmp_) SMCB_CUDA_TRY(cudaMalloc(&w_tmp_, sizeof(double) * M_ * N_));  // scratch (>= M*d doubles: N >= d)
+  if (!w_tmp_) SMCB_CUDA_TRY(cudaMalloc(&w_tmp_, sizeof(double) * M_ * std::max<int64_t>(N_, d_)));  // scratch (>= M*d doubles: N >= d)
   dim3 grid((unsigned)M_, (unsigned)d_);
   batch_wmean_kernel<<<grid, 256, 0, stream_>>>(x_[cur_], logw_[cur_], stats_[cur_], w_tmp_, N_, ld_, d_);
   SMCB_CUDA_TRY(cudaGetLastError());
