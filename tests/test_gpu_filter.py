@@ -280,3 +280,31 @@ def test_on_device_summaries(ctx, oracle, kind):
         oracle.bootstrap_step(kind, MODELS[kind], xo, lwo, y[t], t, oracle.SYSTEMATIC, 17, 3, 0)
         _, _, q = ctx.summary([0.25, 0.5, 0.75])
         np.testing.assert_array_equal(q, oracle.weighted_summary(xo, lwo, [0.25, 0.5, 0.75])[2])
+
+
+def test_fuzz_sizes_and_weight_profiles(ctx, oracle):
+    """40 seeded random configurations of the sorted-resampler step against the oracle: particle counts
+    around every granularity of the kernels (128-particle chunks, 1024-particle ancestor CTAs, tiles),
+    likelihoods from flat to very sharp (CDF windows from one entry to many passes), both sorted
+    resamplers.  Ancestors of every step, final states and log-weights bit-exact."""
+    rng = np.random.default_rng(20261018)
+    kind, T = smc.KIND_LG1D, 5
+    specials = [127, 128, 129, 1023, 1024, 1025, 2047, 2049, 3583, 3584, 3585, 7168, 28672, 28673, 65535, 65537, 131071]
+    for trial in range(40):
+        N = int(specials[trial]) if trial < len(specials) else int(rng.integers(1, 300000))
+        R = float(10.0 ** rng.uniform(-8, 1))            # observation variance: 1e-8 (degenerate weights) .. 10 (flat)
+        A = float(rng.uniform(-0.95, 0.95))
+        params = [A, 1.0, float(10.0 ** rng.uniform(-2, 0.5)), R, 0.0, 1.0]
+        resampler = smc.SYSTEMATIC if trial % 3 else smc.STRATIFIED
+        _, y = oracle.simulate(kind, [A, 1.0, params[2], max(R, 0.3), 0.0, 1.0], T, 100 + trial)
+        ref = oracle.log_likelihood(kind, params, N, y, resampler, 5, trial, 3, want_anc=True)
+        ctx.set_rng(5, trial)
+        ctx.record_ancestors(True)
+        logZ = ctx.log_likelihood(kind, params, N, y, resampler, 3)
+        anc = ctx.fetch_ancestors(T - 1)
+        x, _, lw = ctx.fetch_state(want_w=False, want_logw=True)
+        ctx.record_ancestors(False)
+        tag = f"trial {trial}: N={N} R={R:.3g} resampler={resampler}"
+        assert np.array_equal(anc, ref["anc"][1:]), tag
+        assert np.array_equal(x, ref["x"]) and np.array_equal(lw, ref["logw"]), tag
+        assert abs(logZ - ref["logZ"]) <= RTOL * abs(ref["logZ"]) or (np.isnan(logZ) and np.isnan(ref["logZ"])), tag
