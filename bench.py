@@ -253,11 +253,12 @@ def main():
     peak, peak_src = measured_peak()
     step_us = {k: (1e3 * kms[k] / kn[k] if kn[k] else None) for k in kms}
     # average duration of one step (its four launches) inside the timed sweeps: CUDA events around the whole sweep on
-    # the library's stream, minus the two launches that are not steps (init at t=1, the final stats-only pass).  The
-    # per-launch events below add ~2.5 us of event overhead to every launch, so their sum is reported but not used.
+    # the library's stream, minus the two launches that are not part of a step (init at t=1, and the T-th sum_kernel
+    # that only produces the statistics of the final weights).  The per-launch events below add ~2.5 us of event
+    # overhead to every launch, so their sum is reported but not used.
     fused_events = sum(v for k, v in step_us.items() if k in ("scan", "bounds", "anc", "prop") and v)
     sweep_us = 1e3 * dev_ms_max / args.steps
-    fused = (sweep_us - (step_us["init"] or 0.0) - (step_us["stats"] or 0.0)) / max(T - 1, 1) if T > 1 else None
+    fused = (sweep_us - (step_us["init"] or 0.0) - (step_us["scan"] or 0.0)) / max(T - 1, 1) if T > 1 else None
     achieved = BYTES_PER_UPDATE * N / (fused * 1e-6) / 1e9 if fused else None
 
     line = {
