@@ -230,10 +230,11 @@ __device__ __forceinline__ void det_exp_quant_stream(double x, int S, double& e,
   const double ev = scale_pow2(p, k);
   e = isnan ? x : ev;
   const int ks = k + S;
+  // SPEC §3 caps q at 2^S.  For x <= 0 the cap never binds: p 2^k <= 1 (k <= -1 gives p 2^k <= 1.4143 / 2; k = 0 means
+  // r = x in (-0.347, 0], where p = 1 + (r + r^2 E) with r + r^2 E <= 0), so the truncation is <= 2^S already — and x is
+  // logw - max(logw) with the EXACT max, never positive.
   const uint64_t v = (uint64_t)scale_pow2(p, ks < 0 ? 0 : ks);
-  const uint64_t cap = (uint64_t)1 << S;
-  const uint64_t vq = v < cap ? v : cap;
-  q = (ks >= 0 && !isnan) ? vq : 0;
+  q = (ks >= 0 && !isnan) ? v : 0;
 }
 #endif
 

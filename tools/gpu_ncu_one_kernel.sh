@@ -1,3 +1,4 @@
+# one `ncu --set full` capture of one kernel of the step: KERNEL=sum_kernel|bounds_kernel|anc_kernel|move_kernel  OUT=name
 mkdir -p gpurun_out
-ncu --set full --clock-control none --import-source on -k regex:'anc_kernel' -s 2 -c 1 -f -o gpurun_out/prof_anc_v13 python tools/prof_step.py > gpurun_out/ncu8.log 2>&1
-tail -2 gpurun_out/ncu8.log
+ncu --set full --clock-control none --import-source on -k regex:"${KERNEL:-anc_kernel}" -s 2 -c 1 -f -o gpurun_out/${OUT:-prof_one} python tools/prof_step.py > gpurun_out/ncu_one.log 2>&1
+tail -2 gpurun_out/ncu_one.log
