@@ -477,29 +477,15 @@ __global__ void __launch_bounds__(kSumThreads, kSumCtasPerSm)
       const int64_t need = (left + kChunk - 1) / kChunk;
       if (need < nch) nch = (int)need;
     }
-    // software pipeline: the next chunk's log-weights are in flight while this one is quantised
-    double nx[4];
-    auto load_chunk = [&](int c, double* out) {
+    // chunks that lie entirely inside [0, N) take a body without any bounds logic; at most one partial chunk follows
+    int nfull = (int)((N - tile0) / kChunk);
+    if (nfull > nch) nfull = nch;
+    auto process = [&](auto full_tag, int c, double (&lw)[4]) {
+      constexpr bool FULL = decltype(full_tag)::value;
       const int64_t base = tile0 + (int64_t)c * kChunk + lane * 4;
-      if (base + 4 <= N) {
-        const double2 a = __ldcs(reinterpret_cast<const double2*>(logw + base));
-        const double2 b = __ldcs(reinterpret_cast<const double2*>(logw + base + 2));
-        out[0] = a.x; out[1] = a.y; out[2] = b.x; out[3] = b.y;
-      } else {
+      if (from_x) {  // (partial chunk: out-of-range items were loaded as -inf and their "weight" must stay -inf)
 #pragma unroll
-        for (int k = 0; k < 4; ++k) out[k] = (base + k < N) ? logw[base + k] : -INFINITY;
-      }
-    };
-    load_chunk(0, nx);
-#pragma unroll 1
-    for (int c = 0; c < nch; ++c) {
-      const int64_t base = tile0 + (int64_t)c * kChunk + lane * 4;
-      double lw[4] = {nx[0], nx[1], nx[2], nx[3]};
-      if (c + 1 < nch) load_chunk(c + 1, nx);
-      if (from_x) {  // out-of-range items were loaded as -inf: their "weight" must stay -inf
-        const bool whole = base + 4 <= N;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) lw[k] = (whole || base + k < N) ? lg_logweight(lw[k]) : -INFINITY;
+        for (int k = 0; k < 4; ++k) lw[k] = (FULL || base + k < N) ? lg_logweight(lw[k]) : -INFINITY;
       }
       unsigned long long q[4];
 #pragma unroll
@@ -516,7 +502,7 @@ __global__ void __launch_bounds__(kSumThreads, kSumCtasPerSm)
       q[3] += q[2];
       const unsigned long long winc = warp_scan_u64(q[3], lane);
       const unsigned long long off = running + (winc - q[3]);
-      if (base + 4 <= N) {
+      if (FULL || base + 4 <= N) {
         *reinterpret_cast<ulonglong2*>(cl + base) = make_ulonglong2(off + q[0], off + q[1]);
         *reinterpret_cast<ulonglong2*>(cl + base + 2) = make_ulonglong2(off + q[2], off + q[3]);
       } else {
@@ -525,6 +511,29 @@ __global__ void __launch_bounds__(kSumThreads, kSumCtasPerSm)
           if (base + k < N) cl[base + k] = off + q[k];
       }
       running += __shfl_sync(kFullMask, winc, 31);
+    };
+    // software pipeline: the next chunk's log-weights are in flight while this one is quantised
+    const double2* src = reinterpret_cast<const double2*>(logw + tile0 + lane * 4);  // chunk c: src[c * 64], src[c * 64 + 1]
+    double2 na = make_double2(0.0, 0.0), nb = na;
+    if (nfull > 0) {
+      na = __ldcs(src);
+      nb = __ldcs(src + 1);
+    }
+#pragma unroll 1
+    for (int c = 0; c < nfull; ++c) {
+      double lw[4] = {na.x, na.y, nb.x, nb.y};
+      if (c + 1 < nfull) {
+        na = __ldcs(src + (c + 1) * (kChunk / 2));
+        nb = __ldcs(src + (c + 1) * (kChunk / 2) + 1);
+      }
+      process(std::true_type{}, c, lw);
+    }
+    if (nfull < nch) {  // the partial chunk at the end of the array
+      const int64_t base = tile0 + (int64_t)nfull * kChunk + lane * 4;
+      double lw[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) lw[k] = (base + k < N) ? logw[base + k] : -INFINITY;
+      process(std::false_type{}, nfull, lw);
     }
     se = warp_sum(se);
     se2 = warp_sum(se2);
