@@ -64,6 +64,7 @@ __global__ void reset_ctrl_kernel(FilterCtrl* ctrl) {
   ctrl->total = 0;
   ctrl->sys_off = 0;
   ctrl->rq_lo = ctrl->rq_hi = 0;
+  ctrl->inv_rq = 0.0;
   ctrl->scan_ticket = 0;
   ctrl->scan_done = 0;
 }
@@ -641,6 +642,7 @@ __global__ void __launch_bounds__(kSumThreads, kSumCtasPerSm)
       ctrl->total = Q;
       ctrl->rq_lo = Rw * Q;
       ctrl->rq_hi = mulhi64(Rw, Q);
+      ctrl->inv_rq = 1.0 / ((double)mulhi64(Rw, Q) + (double)(Rw * Q) * 0x1p-64);
       ctrl->sys_off = mulhi64(uniform64_at(key, 0u, stream, t, PURPOSE_RESAMPLE), Rw);  // used by the systematic resampler only
       ctrl->scan_done = 0;
       ctrl->maxslot[slot ^ 1] = encode_ordered(-INFINITY);
@@ -823,13 +825,50 @@ __device__ __forceinline__ void stage_window(unsigned long long* s_cdf, const St
   }
 }
 
+// Systematic thresholds are an arithmetic progression in 128-bit fixed point: tau_i = hi64(A + i D),
+// A = F_first Q, D = R Q.  So the FIRST particle of the CTA whose threshold reaches a CDF entry C,
+//     o(C) = min{ i >= 0 : tau_i >= C } = ceil((C 2^64 - A) / D),
+// needs no search: a double estimate of the quotient (absolute error < 1e-12 because D / 2^64 >= 1/2:
+// the largest weight is 2^S exactly) decides it unless it falls within 1e-9 of an integer, and then the
+// three candidates are compared exactly.  The ancestor of particle i is a_lo + #{ entries : o <= i }:
+// a histogram of o over the CTA's window followed by a prefix sum — no window in shared memory, no
+// dependent shared-memory chain, work proportional to entries + particles.
+struct SysProgression {
+  unsigned long long a_lo, a_hi, d_lo, d_hi;
+  double a_frac, inv;
+};
+__device__ __forceinline__ uint64_t sys_tau_exact(unsigned long long a_lo, unsigned long long a_hi, unsigned long long d_lo,
+                                                  unsigned long long d_hi, int i) {
+  const unsigned long long m = (unsigned long long)i;
+  const unsigned long long plo = m * d_lo;
+  const unsigned long long phi = m * d_hi + mulhi64(m, d_lo);
+  const unsigned long long slo = a_lo + plo;
+  return a_hi + phi + (slo < plo ? 1ull : 0ull);
+}
+// exact o(C) given that it lies in {n-1, ..., n+2}
+__device__ __noinline__ int sys_first_exact(unsigned long long a_lo, unsigned long long a_hi, unsigned long long d_lo,
+                                            unsigned long long d_hi, unsigned long long C, int n) {
+  int o = n - 1;
+#pragma unroll
+  for (int i = -1; i <= 1; ++i) o += (n + i < 0 || sys_tau_exact(a_lo, a_hi, d_lo, d_hi, n + i) < C) ? 1 : 0;
+  return o;
+}
+// estimate: nearest integer n of the quotient and the signed distance f from it
+__device__ __forceinline__ void sys_estimate(const SysProgression& sp, unsigned long long C, int& n, double& f) {
+  const double r = (__ull2double_rn(C - sp.a_hi) - sp.a_frac) * sp.inv;
+  const double tt = r + 0x1.8p52;
+  n = __double2loint(tt);
+  f = r - (tt - 0x1.8p52);
+}
+constexpr int kStreamCap = 4 * kWinCap;  // widest window the histogram path walks; beyond, the multi-pass path skips dead ranges
+
 // resample (particles.jl:117) for the sorted resamplers: the ancestor of every particle, written as
 // int32.  Model-independent and light in registers, so that many warps hide the dependent
 // shared-memory reads of the search and the walk.  Every thread owns kP2Per CONSECUTIVE particles.
 template <int RESAMPLER>
 __global__ void __launch_bounds__(kP2Threads, 10)  // 48 registers: 12 CTAs/SM spills (79 us), 8 CTAs/SM 72 us, 10 CTAs/SM 68 us at N = 2^24
     anc_kernel(int N, uint64_t Rw, RngKey key, uint32_t stream, uint32_t t, StepIndex ix, const unsigned long long* __restrict__ cl,
-               int32_t* __restrict__ anc_out, const FilterCtrl* __restrict__ ctrl) {
+               int32_t* __restrict__ anc_out, const FilterCtrl* __restrict__ ctrl, double eps) {
   constexpr int NW = kP2Threads / 32;
   __shared__ __align__(16) unsigned long long s_cdf[kWinSlots];
   __shared__ unsigned long long s_min[NW];
@@ -838,22 +877,135 @@ __global__ void __launch_bounds__(kP2Threads, 10)  // 48 registers: 12 CTAs/SM s
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   uint32_t sbase;
   asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"((uint32_t)__cvta_generic_to_shared(s_cdf)));  // opaque: kept in a register, not re-derived
+  int* const s_cnt = reinterpret_cast<int*>(s_cdf);  // histogram of the systematic path (kP2Particles + 4 ints)
+  if (RESAMPLER == RESAMPLE_SYSTEMATIC) {
+    reinterpret_cast<int4*>(s_cnt)[tid] = make_int4(0, 0, 0, 0);
+    reinterpret_cast<int4*>(s_cnt)[tid + kP2Threads] = make_int4(0, 0, 0, 0);
+    if (tid == 0) reinterpret_cast<int4*>(s_cnt)[2 * kP2Threads] = make_int4(0, 0, 0, 0);
+  }
   pdl_launch_dependents();
   pdl_wait();  // the window bounds come from bounds_kernel
+  // everything the CTA needs from the two producer kernels in ONE round trip (no load behind a branch)
   const uint64_t Q = ctrl->total;
+  const int a_lo = __ldg(&ix.bound_pos[blockIdx.x]);
+  const int a_hi = __ldg(&ix.bound_pos[blockIdx.x + 1]);  // ancestor of the next CTA's first particle >= all of mine
+  int T0 = __ldg(&ix.bound_tile[blockIdx.x]);
+  const uint64_t c_off = ctrl->sys_off, c_rq_lo = ctrl->rq_lo, c_rq_hi = ctrl->rq_hi;
+  const double c_inv = ctrl->inv_rq;
   const int i0 = blockIdx.x * kP2Particles + tid * kP2Per;  // first particle of this thread
   const bool full_cta = (int64_t)(blockIdx.x + 1) * kP2Particles <= (int64_t)N;
 
   int anc[kP2Per];
+  auto identity = [&]() {  // Q == 0: every particle is its own ancestor (SPEC §5)
 #pragma unroll
-  for (int k = 0; k < kP2Per; ++k) anc[k] = (i0 + k < N) ? i0 + k : N - 1;  // Q == 0: every particle is its own ancestor (SPEC §5)
+    for (int k = 0; k < kP2Per; ++k) anc[k] = (i0 + k < N) ? i0 + k : N - 1;
+  };
 
+  if (Q == 0) identity();
   if (Q != 0) {
-    const int a_lo = __ldg(&ix.bound_pos[blockIdx.x]);
-    const int a_hi = __ldg(&ix.bound_pos[blockIdx.x + 1]);  // ancestor of the next CTA's first particle >= all of mine
-    int T0 = __ldg(&ix.bound_tile[blockIdx.x]);
     int s0 = a_lo & ~1;
-    if (a_hi - s0 + 1 <= kWinCap) {
+    if (RESAMPLER == RESAMPLE_SYSTEMATIC && a_hi - a_lo <= kStreamCap) {
+      // ---- systematic, common case: histogram of o(C) over the entries [a_lo, a_hi), then a prefix sum
+      SysProgression sp;
+      {
+        const uint64_t F0 = (uint64_t)blockIdx.x * kP2Particles * Rw + c_off;
+        sp.a_lo = F0 * Q;
+        sp.a_hi = mulhi64(F0, Q);
+        sp.d_lo = c_rq_lo;
+        sp.d_hi = c_rq_hi;
+        sp.a_frac = __ull2double_rn(sp.a_lo) * 0x1p-64;
+        sp.inv = c_inv;
+      }
+      __syncthreads();  // the histogram is zero
+      bool near = false;  // an estimate too close to an integer to decide: resolved exactly in a second pass
+      auto sweep = [&](auto exact_pass) {
+        constexpr bool EXACT = decltype(exact_pass)::value;
+        int T = T0, tlo = s0;
+        while (tlo < a_hi) {
+          const int tend_full = (T + 1) * ix.tile_items;
+          const int thi = tend_full < a_hi ? tend_full : a_hi;
+          const unsigned long long base = __ldg(&ix.tile_excl[T]);
+          auto tally = [&](bool valid, unsigned long long C) {
+            int n;
+            double f;
+            sys_estimate(sp, C, n, f);
+            const bool nr = fabs(f) < eps;
+            int o = n + (f > 0.0 ? 1 : 0);
+            if (EXACT) {
+              if (valid && nr) {
+                o = sys_first_exact(sp.a_lo, sp.a_hi, sp.d_lo, sp.d_hi, C, n);
+                if ((unsigned)o < (unsigned)kP2Particles) atomicAdd(&s_cnt[o], 1);
+              }
+            } else {
+              near |= valid && nr;
+              if (valid && !nr && (unsigned)o < (unsigned)kP2Particles) atomicAdd(&s_cnt[o], 1);
+            }
+          };
+          for (int j = tlo + 2 * tid; j < thi; j += 4 * kP2Threads) {  // tlo even, tile_items even; two loads in flight
+            const int j1 = j + 2 * kP2Threads;
+            const bool has1 = j1 < thi;
+            const ulonglong2 v0 = __ldcs(reinterpret_cast<const ulonglong2*>(cl + j));
+            ulonglong2 v1 = make_ulonglong2(0, 0);
+            if (has1) v1 = __ldcs(reinterpret_cast<const ulonglong2*>(cl + j1));
+            tally(j >= a_lo, v0.x + base);
+            tally(j + 1 < thi, v0.y + base);
+            tally(has1, v1.x + base);
+            tally(has1 && j1 + 1 < thi, v1.y + base);
+          }
+          tlo = thi;
+          ++T;
+        }
+      };
+      sweep(std::false_type{});
+      if (__syncthreads_or(near)) {
+        sweep(std::true_type{});
+        __syncthreads();
+      }
+      // two runs of 4 consecutive particles per thread, half a CTA apart: conflict-free 16-byte reads of
+      // the histogram and fully coalesced 16-byte stores of the ancestors
+      constexpr int H = kP2Per / 2;
+      static_assert(H == 4, "the vector accesses below assume 4 particles per run");
+      const int4 cA = reinterpret_cast<const int4*>(s_cnt)[tid], cB = reinterpret_cast<const int4*>(s_cnt)[tid + kP2Threads];
+      int vA[H] = {cA.x, cA.x + cA.y, cA.x + cA.y + cA.z, cA.x + cA.y + cA.z + cA.w};
+      int vB[H] = {cB.x, cB.x + cB.y, cB.x + cB.y + cB.z, cB.x + cB.y + cB.z + cB.w};
+      int inA = vA[H - 1], inB = vB[H - 1];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int uA = __shfl_up_sync(kFullMask, inA, o), uB = __shfl_up_sync(kFullMask, inB, o);
+        if (lane >= o) {
+          inA += uA;
+          inB += uB;
+        }
+      }
+      __shared__ int s_wtot[2][NW];
+      if (lane == 31) {
+        s_wtot[0][warp] = inA;
+        s_wtot[1][warp] = inB;
+      }
+      __syncthreads();
+      int offA = a_lo + inA - vA[H - 1], offB = a_lo + inB - vB[H - 1];
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        const int ta = s_wtot[0][w];
+        if (w < warp) offA += ta;
+        offB += ta;
+        if (w < warp) offB += s_wtot[1][w];
+      }
+      const int iA = blockIdx.x * kP2Particles + tid * H, iB = iA + kP2Particles / 2;
+      if (full_cta) {
+        *reinterpret_cast<int4*>(anc_out + iA) = make_int4(offA + vA[0], offA + vA[1], offA + vA[2], offA + vA[3]);
+        *reinterpret_cast<int4*>(anc_out + iB) = make_int4(offB + vB[0], offB + vB[1], offB + vB[2], offB + vB[3]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < H; ++k) {
+          if (iA + k < N) anc_out[iA + k] = offA + vA[k];
+          if (iB + k < N) anc_out[iB + k] = offB + vB[k];
+        }
+      }
+      return;
+    }
+    identity();
+    if (RESAMPLER != RESAMPLE_SYSTEMATIC && a_hi - s0 + 1 <= kWinCap) {  // (systematic: never reached, kStreamCap > kWinCap)
       // ---- common case: the whole window fits one pass.  C[a_hi] > every tau of this CTA, so the
       // walk below always stops inside the staged entries.
       stage_window(s_cdf, ix, cl, s0, a_hi - s0 + 1, T0, tid);
@@ -1318,6 +1470,7 @@ void SingleFilter::ensure_capacity(int kind, int64_t N, int64_t anc_rows) {
     int v = 0;
     SMCB_CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device_));
     num_sms_ = v > 0 ? v : 148;
+    if (const char* e = std::getenv("SMCB_ANC_FORCE_EXACT")) anc_eps_ = (e[0] && e[0] != '0') ? 2.0 : 1e-9;
   }
   if (anc_rows > cap_anc_rows_ || !anc_) {
     cudaFree(anc_); anc_ = nullptr;
@@ -1502,10 +1655,10 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler) {
   mark(TK_ANC, true);
   if (resampler == RESAMPLE_SYSTEMATIC)
     SMCB_CUDA_TRY(launch_pdl(anc_kernel<RESAMPLE_SYSTEMATIC>, dim3(nblocks), dim3(kP2Threads), stream_, (int)N_, R_, key_, stream_id_, t, ix, cl, anc,
-                             ctrl_));
+                             ctrl_, anc_eps_));
   else
     SMCB_CUDA_TRY(launch_pdl(anc_kernel<RESAMPLE_STRATIFIED>, dim3(nblocks), dim3(kP2Threads), stream_, (int)N_, R_, key_, stream_id_, t, ix, cl, anc,
-                             ctrl_));
+                             ctrl_, anc_eps_));
   mark(TK_ANC, false);
   SMCB_CUDA_TRY(cudaGetLastError());
   const unsigned mblocks = (unsigned)((N_ + kMoveThreads * 2 * kMovePairs - 1) / (kMoveThreads * 2 * kMovePairs));

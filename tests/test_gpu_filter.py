@@ -308,3 +308,28 @@ def test_fuzz_sizes_and_weight_profiles(ctx, oracle):
         assert np.array_equal(anc, ref["anc"][1:]), tag
         assert np.array_equal(x, ref["x"]) and np.array_equal(lw, ref["logw"]), tag
         assert abs(logZ - ref["logZ"]) <= RTOL * abs(ref["logZ"]) or (np.isnan(logZ) and np.isnan(ref["logZ"])), tag
+
+
+def test_systematic_exact_decision_path(oracle, monkeypatch):
+    """anc_kernel decides `first particle whose threshold reaches a CDF entry` from a double estimate and
+    falls back to exact 128-bit comparisons when the estimate is within 1e-9 of an integer — a path
+    random inputs almost never take.  SMCB_ANC_FORCE_EXACT makes every entry take it; the ancestors
+    must not change."""
+    monkeypatch.setenv("SMCB_ANC_FORCE_EXACT", "1")
+    c = smc.Context(0, seed=11)
+    try:
+        kind, T = smc.KIND_LG1D, 4
+        for trial, (N, R) in enumerate([(1000, 0.8), (1024, 1e-6), (5000, 0.05), (70001, 3.0), (262144, 0.8)]):
+            params = [0.7, 1.0, 0.9, R, 0.0, 1.0]
+            _, y = oracle.simulate(kind, [0.7, 1.0, 0.9, 0.8, 0.0, 1.0], T, 40 + trial)
+            ref = oracle.log_likelihood(kind, params, N, y, smc.SYSTEMATIC, 11, trial, 0, want_anc=True)
+            c.set_rng(11, trial)
+            c.record_ancestors(True)
+            c.log_likelihood(kind, params, N, y, smc.SYSTEMATIC, 0)
+            anc = c.fetch_ancestors(T - 1)
+            x, _, _ = c.fetch_state(want_w=False)
+            c.record_ancestors(False)
+            assert np.array_equal(anc, ref["anc"][1:]), (N, R)
+            assert np.array_equal(x, ref["x"]), (N, R)
+    finally:
+        c.close()
