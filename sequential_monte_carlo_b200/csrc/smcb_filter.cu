@@ -715,7 +715,7 @@ __device__ __forceinline__ void warp_count_le2(const unsigned long long* __restr
 // trips are not on the critical path of every ancestor CTA.
 __global__ void __launch_bounds__(256)
     bounds_kernel(StepIndex ix, const unsigned long long* __restrict__ cl, const FilterCtrl* ctrl, int N, int resampler,
-                  uint64_t Rw, RngKey key, uint32_t stream, uint32_t t, int nbounds) {
+                  uint64_t Rw, RngKey key, uint32_t stream, uint32_t t, int nbounds, int block_particles) {
   const int lane = threadIdx.x & 31;
   const int half = (nbounds + 1) >> 1;
   const int b0 = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -729,7 +729,7 @@ __global__ void __launch_bounds__(256)
   uint64_t tau[2];
 #pragma unroll
   for (int s = 0; s < 2; ++s) {
-    int64_t i = (int64_t)(s ? (has1 ? b1 : b0) : b0) * kP2Particles;
+    int64_t i = (int64_t)(s ? (has1 ? b1 : b0) : b0) * block_particles;
     if (i > N - 1) i = N - 1;  // the last boundary is the last particle
     uint64_t u = ctrl->sys_off;
     if (resampler == RESAMPLE_STRATIFIED) u = uniform64_at(key, (uint32_t)i, stream, t, PURPOSE_RESAMPLE);
@@ -860,70 +860,92 @@ __device__ __forceinline__ void sys_estimate(const SysProgression& sp, unsigned 
   n = __double2loint(tt);
   f = r - (tt - 0x1.8p52);
 }
-constexpr int kStreamCap = 4 * kWinCap;  // widest window the histogram path walks; beyond, the multi-pass path skips dead ranges
 
-// resample (particles.jl:117) for the sorted resamplers: the ancestor of every particle, written as
-// int32.  Model-independent and light in registers, so that many warps hide the dependent
-// shared-memory reads of the search and the walk.  Every thread owns kP2Per CONSECUTIVE particles.
-template <int RESAMPLER>
-__global__ void __launch_bounds__(kP2Threads, 10)  // 48 registers: 12 CTAs/SM spills (79 us), 8 CTAs/SM 72 us, 10 CTAs/SM 68 us at N = 2^24
-    anc_kernel(int N, uint64_t Rw, RngKey key, uint32_t stream, uint32_t t, StepIndex ix, const unsigned long long* __restrict__ cl,
-               int32_t* __restrict__ anc_out, const FilterCtrl* __restrict__ ctrl, double eps) {
-  constexpr int NW = kP2Threads / 32;
-  __shared__ __align__(16) unsigned long long s_cdf[kWinSlots];
-  __shared__ unsigned long long s_min[NW];
-  __shared__ int s_next[2];
-
+// ---- the systematic resampler's ancestor kernel (particles.jl:117 with SPEC §5's systematic thresholds).
+// One CTA resolves kSysParticles consecutive particles.  It reads the CDF entries [a_lo, a_hi) between its
+// own first ancestor and the next CTA's (bounds_kernel), adds 1 to hist[o(C)] for each, and the ancestor of
+// local particle i is a_lo + sum_{o <= i} hist[o].  No search, no window in shared memory.
+// Very uneven weights make some windows long and mostly dead (no threshold falls into them).  Whole tiles
+// of such a window are accounted for with ONE add when o(first) == o(last) — read off the tile index,
+// not the entries — so a CTA streams at most the tiles that contain one of its thresholds.
+constexpr int kSysThreads = 128;
+constexpr int kSysPer = 8;                               // particles per thread: kSysPer / 4 runs of 4 consecutive ones
+constexpr int kSysParticles = kSysThreads * kSysPer;
+__global__ void __launch_bounds__(kSysThreads, 12)
+    anc_sys_kernel(int N, uint64_t Rw, StepIndex ix, const unsigned long long* __restrict__ cl, int32_t* __restrict__ anc_out,
+                   const FilterCtrl* __restrict__ ctrl, double eps) {
+  constexpr int NW = kSysThreads / 32, NRUN = kSysPer / 4;
+  __shared__ __align__(16) int s_cnt[kSysParticles + 4];
+  __shared__ int s_wtot[NRUN][NW];
+  __shared__ unsigned s_skip[kMaxTiles / 32];  // wide windows only: tiles already accounted for wholesale
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint32_t sbase;
-  asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"((uint32_t)__cvta_generic_to_shared(s_cdf)));  // opaque: kept in a register, not re-derived
-  int* const s_cnt = reinterpret_cast<int*>(s_cdf);  // histogram of the systematic path (kP2Particles + 4 ints)
-  if (RESAMPLER == RESAMPLE_SYSTEMATIC) {
-    reinterpret_cast<int4*>(s_cnt)[tid] = make_int4(0, 0, 0, 0);
-    reinterpret_cast<int4*>(s_cnt)[tid + kP2Threads] = make_int4(0, 0, 0, 0);
-    if (tid == 0) reinterpret_cast<int4*>(s_cnt)[2 * kP2Threads] = make_int4(0, 0, 0, 0);
-  }
+#pragma unroll
+  for (int r = 0; r < NRUN; ++r) reinterpret_cast<int4*>(s_cnt)[r * kSysThreads + tid] = make_int4(0, 0, 0, 0);
+  if (tid == 0) reinterpret_cast<int4*>(s_cnt)[NRUN * kSysThreads] = make_int4(0, 0, 0, 0);
   pdl_launch_dependents();
   pdl_wait();  // the window bounds come from bounds_kernel
   // everything the CTA needs from the two producer kernels in ONE round trip (no load behind a branch)
   const uint64_t Q = ctrl->total;
   const int a_lo = __ldg(&ix.bound_pos[blockIdx.x]);
   const int a_hi = __ldg(&ix.bound_pos[blockIdx.x + 1]);  // ancestor of the next CTA's first particle >= all of mine
-  int T0 = __ldg(&ix.bound_tile[blockIdx.x]);
+  const int T0 = __ldg(&ix.bound_tile[blockIdx.x]), T1 = __ldg(&ix.bound_tile[blockIdx.x + 1]);
   const uint64_t c_off = ctrl->sys_off, c_rq_lo = ctrl->rq_lo, c_rq_hi = ctrl->rq_hi;
   const double c_inv = ctrl->inv_rq;
-  const int i0 = blockIdx.x * kP2Particles + tid * kP2Per;  // first particle of this thread
-  const bool full_cta = (int64_t)(blockIdx.x + 1) * kP2Particles <= (int64_t)N;
+  const int base_i = blockIdx.x * kSysParticles;
+  const bool full_cta = (int64_t)(blockIdx.x + 1) * kSysParticles <= (int64_t)N;
 
-  int anc[kP2Per];
-  auto identity = [&]() {  // Q == 0: every particle is its own ancestor (SPEC §5)
+  int v[NRUN][4];
+  int off[NRUN];
+  if (Q == 0) {  // every particle is its own ancestor (SPEC §5)
 #pragma unroll
-    for (int k = 0; k < kP2Per; ++k) anc[k] = (i0 + k < N) ? i0 + k : N - 1;
-  };
-
-  if (Q == 0) identity();
-  if (Q != 0) {
-    int s0 = a_lo & ~1;
-    if (RESAMPLER == RESAMPLE_SYSTEMATIC && a_hi - a_lo <= kStreamCap) {
-      // ---- systematic, common case: histogram of o(C) over the entries [a_lo, a_hi), then a prefix sum
-      SysProgression sp;
-      {
-        const uint64_t F0 = (uint64_t)blockIdx.x * kP2Particles * Rw + c_off;
-        sp.a_lo = F0 * Q;
-        sp.a_hi = mulhi64(F0, Q);
-        sp.d_lo = c_rq_lo;
-        sp.d_hi = c_rq_hi;
-        sp.a_frac = __ull2double_rn(sp.a_lo) * 0x1p-64;
-        sp.inv = c_inv;
+    for (int r = 0; r < NRUN; ++r) {
+      off[r] = base_i + r * 4 * kSysThreads + 4 * tid;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[r][k] = k;
+    }
+  } else {
+    SysProgression sp;
+    {
+      const uint64_t F0 = (uint64_t)base_i * Rw + c_off;
+      sp.a_lo = F0 * Q;
+      sp.a_hi = mulhi64(F0, Q);
+      sp.d_lo = c_rq_lo;
+      sp.d_hi = c_rq_hi;
+      sp.a_frac = __ull2double_rn(sp.a_lo) * 0x1p-64;
+      sp.inv = c_inv;
+    }
+    const bool wide = T1 - T0 >= 3;
+    if (wide) {
+      for (int w = tid; w < kMaxTiles / 32; w += kSysThreads) s_skip[w] = 0u;
+    }
+    __syncthreads();  // the histogram (and the bitmap) is zero
+    if (wide) {
+      for (int T = T0 + 1 + tid; T < T1; T += kSysThreads) {  // tiles strictly inside the window: full tiles, all entries in [a_lo, a_hi)
+        int o2[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const unsigned long long C = __ldg(e ? &ix.tile_incl[T] : &ix.tile_excl[T]);  // = CDF of a real entry of the window, both
+          int n;
+          double f;
+          sys_estimate(sp, C, n, f);
+          o2[e] = fabs(f) < eps ? sys_first_exact(sp.a_lo, sp.a_hi, sp.d_lo, sp.d_hi, C, n) : n + (f > 0.0 ? 1 : 0);
+        }
+        if (o2[0] == o2[1]) {
+          if ((unsigned)o2[1] < (unsigned)kSysParticles) atomicAdd(&s_cnt[o2[1]], ix.tile_items);
+          atomicOr(&s_skip[T >> 5], 1u << (T & 31));
+        }
       }
-      __syncthreads();  // the histogram is zero
-      bool near = false;  // an estimate too close to an integer to decide: resolved exactly in a second pass
-      auto sweep = [&](auto exact_pass) {
-        constexpr bool EXACT = decltype(exact_pass)::value;
-        int T = T0, tlo = s0;
-        while (tlo < a_hi) {
-          const int tend_full = (T + 1) * ix.tile_items;
-          const int thi = tend_full < a_hi ? tend_full : a_hi;
+      __syncthreads();
+    }
+    const int s0 = a_lo & ~1;
+    bool near = false;  // an estimate too close to an integer to decide: resolved exactly in a second pass
+    auto sweep = [&](auto exact_pass) {
+      constexpr bool EXACT = decltype(exact_pass)::value;
+      int T = T0, tlo = s0;
+      while (tlo < a_hi) {
+        const int tend_full = (T + 1) * ix.tile_items;
+        const int thi = tend_full < a_hi ? tend_full : a_hi;
+        if (!(wide && ((s_skip[T >> 5] >> (T & 31)) & 1u))) {
           const unsigned long long base = __ldg(&ix.tile_excl[T]);
           auto tally = [&](bool valid, unsigned long long C) {
             int n;
@@ -934,15 +956,15 @@ __global__ void __launch_bounds__(kP2Threads, 10)  // 48 registers: 12 CTAs/SM s
             if (EXACT) {
               if (valid && nr) {
                 o = sys_first_exact(sp.a_lo, sp.a_hi, sp.d_lo, sp.d_hi, C, n);
-                if ((unsigned)o < (unsigned)kP2Particles) atomicAdd(&s_cnt[o], 1);
+                if ((unsigned)o < (unsigned)kSysParticles) atomicAdd(&s_cnt[o], 1);
               }
             } else {
               near |= valid && nr;
-              if (valid && !nr && (unsigned)o < (unsigned)kP2Particles) atomicAdd(&s_cnt[o], 1);
+              if (valid && !nr && (unsigned)o < (unsigned)kSysParticles) atomicAdd(&s_cnt[o], 1);
             }
           };
-          for (int j = tlo + 2 * tid; j < thi; j += 4 * kP2Threads) {  // tlo even, tile_items even; two loads in flight
-            const int j1 = j + 2 * kP2Threads;
+          for (int j = tlo + 2 * tid; j < thi; j += 4 * kSysThreads) {  // tlo even, tile_items even; two loads in flight
+            const int j1 = j + 2 * kSysThreads;
             const bool has1 = j1 < thi;
             const ulonglong2 v0 = __ldcs(reinterpret_cast<const ulonglong2*>(cl + j));
             ulonglong2 v1 = make_ulonglong2(0, 0);
@@ -952,60 +974,97 @@ __global__ void __launch_bounds__(kP2Threads, 10)  // 48 registers: 12 CTAs/SM s
             tally(has1, v1.x + base);
             tally(has1 && j1 + 1 < thi, v1.y + base);
           }
-          tlo = thi;
-          ++T;
         }
-      };
-      sweep(std::false_type{});
-      if (__syncthreads_or(near)) {
-        sweep(std::true_type{});
-        __syncthreads();
+        tlo = thi;
+        ++T;
       }
-      // two runs of 4 consecutive particles per thread, half a CTA apart: conflict-free 16-byte reads of
-      // the histogram and fully coalesced 16-byte stores of the ancestors
-      constexpr int H = kP2Per / 2;
-      static_assert(H == 4, "the vector accesses below assume 4 particles per run");
-      const int4 cA = reinterpret_cast<const int4*>(s_cnt)[tid], cB = reinterpret_cast<const int4*>(s_cnt)[tid + kP2Threads];
-      int vA[H] = {cA.x, cA.x + cA.y, cA.x + cA.y + cA.z, cA.x + cA.y + cA.z + cA.w};
-      int vB[H] = {cB.x, cB.x + cB.y, cB.x + cB.y + cB.z, cB.x + cB.y + cB.z + cB.w};
-      int inA = vA[H - 1], inB = vB[H - 1];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int uA = __shfl_up_sync(kFullMask, inA, o), uB = __shfl_up_sync(kFullMask, inB, o);
-        if (lane >= o) {
-          inA += uA;
-          inB += uB;
-        }
-      }
-      __shared__ int s_wtot[2][NW];
-      if (lane == 31) {
-        s_wtot[0][warp] = inA;
-        s_wtot[1][warp] = inB;
-      }
+    };
+    sweep(std::false_type{});
+    if (__syncthreads_or(near)) {
+      sweep(std::true_type{});
       __syncthreads();
-      int offA = a_lo + inA - vA[H - 1], offB = a_lo + inB - vB[H - 1];
+    }
+    // prefix sums: run r of thread tid covers local particles r * 4 * kSysThreads + 4 tid .. + 3 (conflict-free
+    // 16-byte reads of the histogram, fully coalesced 16-byte stores of the ancestors)
+    int incl[NRUN];
+#pragma unroll
+    for (int r = 0; r < NRUN; ++r) {
+      const int4 c = reinterpret_cast<const int4*>(s_cnt)[r * kSysThreads + tid];
+      v[r][0] = c.x;
+      v[r][1] = c.x + c.y;
+      v[r][2] = c.x + c.y + c.z;
+      v[r][3] = c.x + c.y + c.z + c.w;
+      incl[r] = v[r][3];
+    }
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+      for (int r = 0; r < NRUN; ++r) {
+        const int u = __shfl_up_sync(kFullMask, incl[r], o);
+        if (lane >= o) incl[r] += u;
+      }
+    }
+    if (lane == 31) {
+#pragma unroll
+      for (int r = 0; r < NRUN; ++r) s_wtot[r][warp] = incl[r];
+    }
+    __syncthreads();
+    int run_base = a_lo;
+#pragma unroll
+    for (int r = 0; r < NRUN; ++r) {
+      off[r] = run_base + incl[r] - v[r][3];
 #pragma unroll
       for (int w = 0; w < NW; ++w) {
-        const int ta = s_wtot[0][w];
-        if (w < warp) offA += ta;
-        offB += ta;
-        if (w < warp) offB += s_wtot[1][w];
+        const int tw = s_wtot[r][w];
+        if (w < warp) off[r] += tw;
+        run_base += tw;
       }
-      const int iA = blockIdx.x * kP2Particles + tid * H, iB = iA + kP2Particles / 2;
-      if (full_cta) {
-        *reinterpret_cast<int4*>(anc_out + iA) = make_int4(offA + vA[0], offA + vA[1], offA + vA[2], offA + vA[3]);
-        *reinterpret_cast<int4*>(anc_out + iB) = make_int4(offB + vB[0], offB + vB[1], offB + vB[2], offB + vB[3]);
-      } else {
-#pragma unroll
-        for (int k = 0; k < H; ++k) {
-          if (iA + k < N) anc_out[iA + k] = offA + vA[k];
-          if (iB + k < N) anc_out[iB + k] = offB + vB[k];
-        }
-      }
-      return;
     }
-    identity();
-    if (RESAMPLER != RESAMPLE_SYSTEMATIC && a_hi - s0 + 1 <= kWinCap) {  // (systematic: never reached, kStreamCap > kWinCap)
+  }
+#pragma unroll
+  for (int r = 0; r < NRUN; ++r) {
+    const int i = base_i + r * 4 * kSysThreads + 4 * tid;
+    if (full_cta) {
+      *reinterpret_cast<int4*>(anc_out + i) = make_int4(off[r] + v[r][0], off[r] + v[r][1], off[r] + v[r][2], off[r] + v[r][3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (i + k < N) anc_out[i + k] = off[r] + v[r][k];
+    }
+  }
+}
+
+// resample (particles.jl:117) for the sorted resamplers: the ancestor of every particle, written as
+// int32.  Model-independent and light in registers, so that many warps hide the dependent
+// shared-memory reads of the search and the walk.  Every thread owns kP2Per CONSECUTIVE particles.
+template <int RESAMPLER>
+__global__ void __launch_bounds__(kP2Threads, 10)  // 48 registers: 12 CTAs/SM spills (79 us), 8 CTAs/SM 72 us, 10 CTAs/SM 68 us at N = 2^24
+    anc_kernel(int N, uint64_t Rw, RngKey key, uint32_t stream, uint32_t t, StepIndex ix, const unsigned long long* __restrict__ cl,
+               int32_t* __restrict__ anc_out, const FilterCtrl* __restrict__ ctrl) {
+  constexpr int NW = kP2Threads / 32;
+  __shared__ __align__(16) unsigned long long s_cdf[kWinSlots];
+  __shared__ unsigned long long s_min[NW];
+  __shared__ int s_next[2];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t sbase;
+  asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"((uint32_t)__cvta_generic_to_shared(s_cdf)));  // opaque: kept in a register, not re-derived
+  pdl_launch_dependents();
+  pdl_wait();  // the window bounds come from bounds_kernel
+  const uint64_t Q = ctrl->total;
+  const int i0 = blockIdx.x * kP2Particles + tid * kP2Per;  // first particle of this thread
+  const bool full_cta = (int64_t)(blockIdx.x + 1) * kP2Particles <= (int64_t)N;
+
+  int anc[kP2Per];
+#pragma unroll
+  for (int k = 0; k < kP2Per; ++k) anc[k] = (i0 + k < N) ? i0 + k : N - 1;  // Q == 0: every particle is its own ancestor (SPEC §5)
+
+  if (Q != 0) {
+    const int a_lo = __ldg(&ix.bound_pos[blockIdx.x]);
+    const int a_hi = __ldg(&ix.bound_pos[blockIdx.x + 1]);  // ancestor of the next CTA's first particle >= all of mine
+    int T0 = __ldg(&ix.bound_tile[blockIdx.x]);
+    int s0 = a_lo & ~1;
+    if (a_hi - s0 + 1 <= kWinCap) {
       // ---- common case: the whole window fits one pass.  C[a_hi] > every tau of this CTA, so the
       // walk below always stops inside the staged entries.
       stage_window(s_cdf, ix, cl, s0, a_hi - s0 + 1, T0, tid);
@@ -1638,12 +1697,13 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler) {
   StepIndex ix;
   unsigned long long* cl = step_index(ix);
   if (!sum_done_) launch_sum(stat_index);  // (a stepping caller already ran it to read the statistics of the current weights)
-  const unsigned nblocks = (unsigned)((N_ + kP2Particles - 1) / kP2Particles);
+  const int block_particles = resampler == RESAMPLE_SYSTEMATIC ? kSysParticles : kP2Particles;
+  const unsigned nblocks = (unsigned)((N_ + block_particles - 1) / block_particles);
   const uint32_t t = t_ + 1;
   const int nbounds = (int)nblocks + 1;
   mark(TK_BOUNDS, true);
   SMCB_CUDA_TRY(launch_pdl(bounds_kernel, dim3(((nbounds + 1) / 2 + 7) / 8), dim3(256), stream_, ix, cl, ctrl_, (int)N_, resampler, R_, key_,
-                           stream_id_, t, nbounds));
+                           stream_id_, t, nbounds, block_particles));
   mark(TK_BOUNDS, false);
   SMCB_CUDA_TRY(cudaGetLastError());
   int32_t* anc = anc_;  // row 0 doubles as the scratch ancestor vector when nothing is recorded
@@ -1654,11 +1714,10 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler) {
   }
   mark(TK_ANC, true);
   if (resampler == RESAMPLE_SYSTEMATIC)
-    SMCB_CUDA_TRY(launch_pdl(anc_kernel<RESAMPLE_SYSTEMATIC>, dim3(nblocks), dim3(kP2Threads), stream_, (int)N_, R_, key_, stream_id_, t, ix, cl, anc,
-                             ctrl_, anc_eps_));
+    SMCB_CUDA_TRY(launch_pdl(anc_sys_kernel, dim3(nblocks), dim3(kSysThreads), stream_, (int)N_, R_, ix, cl, anc, ctrl_, anc_eps_));
   else
     SMCB_CUDA_TRY(launch_pdl(anc_kernel<RESAMPLE_STRATIFIED>, dim3(nblocks), dim3(kP2Threads), stream_, (int)N_, R_, key_, stream_id_, t, ix, cl, anc,
-                             ctrl_, anc_eps_));
+                             ctrl_));
   mark(TK_ANC, false);
   SMCB_CUDA_TRY(cudaGetLastError());
   const unsigned mblocks = (unsigned)((N_ + kMoveThreads * 2 * kMovePairs - 1) / (kMoveThreads * 2 * kMovePairs));
