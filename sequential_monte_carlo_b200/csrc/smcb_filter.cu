@@ -869,7 +869,7 @@ __device__ __forceinline__ void sys_estimate(const SysProgression& sp, unsigned 
 // of such a window are accounted for with ONE add when o(first) == o(last) — read off the tile index,
 // not the entries — so a CTA streams at most the tiles that contain one of its thresholds.
 constexpr int kSysThreads = 128;
-constexpr int kSysPer = 8;                               // particles per thread: kSysPer / 4 runs of 4 consecutive ones
+constexpr int kSysPer = 16;                              // particles per thread: kSysPer / 4 runs of 4 consecutive ones
 constexpr int kSysParticles = kSysThreads * kSysPer;
 __global__ void __launch_bounds__(kSysThreads, 12)
     anc_sys_kernel(int N, uint64_t Rw, StepIndex ix, const unsigned long long* __restrict__ cl, int32_t* __restrict__ anc_out,
