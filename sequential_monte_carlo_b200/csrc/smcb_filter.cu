@@ -835,7 +835,7 @@ __device__ __forceinline__ void stage_window(unsigned long long* s_cdf, const St
 // dependent shared-memory chain, work proportional to entries + particles.
 struct SysProgression {
   unsigned long long a_lo, a_hi, d_lo, d_hi;
-  double a_frac, inv;
+  double inv, k;
 };
 __device__ __forceinline__ uint64_t sys_tau_exact(unsigned long long a_lo, unsigned long long a_hi, unsigned long long d_lo,
                                                   unsigned long long d_hi, int i) {
@@ -853,21 +853,20 @@ __device__ __noinline__ int sys_first_exact(unsigned long long a_lo, unsigned lo
   for (int i = -1; i <= 1; ++i) o += (n + i < 0 || sys_tau_exact(a_lo, a_hi, d_lo, d_hi, n + i) < C) ? 1 : 0;
   return o;
 }
-// estimate: nearest integer n of the quotient and the signed distance f from it
-__device__ __forceinline__ void sys_estimate(const SysProgression& sp, unsigned long long C, int& n, double& f) {
-  const double r = (__ull2double_rn(C - sp.a_hi) - sp.a_frac) * sp.inv;
-  const double tt = r + 0x1.8p52;
-  n = __double2loint(tt);
-  f = r - (tt - 0x1.8p52);
+// estimate of o(C) = ceil(quotient): o = round(quotient + 1/2); `near` when the quotient is within eps of an
+// integer (then o may be off by one and sys_first_exact(…, o - 1) decides).  sp.k = 1/2 - a_frac * inv.
+__device__ __forceinline__ int sys_estimate(const SysProgression& sp, unsigned long long C, double near_thr, bool& near) {
+  const double r05 = fma(__ull2double_rn(C - sp.a_hi), sp.inv, sp.k);
+  const double tt = r05 + 0x1.8p52;
+  const double g = r05 - (tt - 0x1.8p52);  // in [-1/2, 1/2]: distance of quotient + 1/2 from its nearest integer
+  near = fabs(g) > near_thr;               // near_thr = 1/2 - eps
+  return __double2loint(tt);
 }
-
-// ---- the systematic resampler's ancestor kernel (particles.jl:117 with SPEC §5's systematic thresholds).
-// One CTA resolves kSysParticles consecutive particles.  It reads the CDF entries [a_lo, a_hi) between its
-// own first ancestor and the next CTA's (bounds_kernel), adds 1 to hist[o(C)] for each, and the ancestor of
-// local particle i is a_lo + sum_{o <= i} hist[o].  No search, no window in shared memory.
-// Very uneven weights make some windows long and mostly dead (no threshold falls into them).  Whole tiles
-// of such a window are accounted for with ONE add when o(first) == o(last) — read off the tile index,
-// not the entries — so a CTA streams at most the tiles that contain one of its thresholds.
+// hist[o] += 1 when pred, as ONE predicated instruction on a shared-space address (an if around atomicAdd
+// compiles to a divergence region per call and re-derives the shared window base each time)
+__device__ __forceinline__ void hist_inc(uint32_t hist_saddr, int o, bool pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], 1;\n\t}" ::"r"(hist_saddr + 4u * (uint32_t)o), "r"((int)pred) : "memory");
+}
 constexpr int kSysThreads = 128;
 constexpr int kSysPer = 16;                              // particles per thread: kSysPer / 4 runs of 4 consecutive ones
 constexpr int kSysParticles = kSysThreads * kSysPer;
@@ -879,6 +878,8 @@ __global__ void __launch_bounds__(kSysThreads, 12)
   __shared__ int s_wtot[NRUN][NW];
   __shared__ unsigned s_skip[kMaxTiles / 32];  // wide windows only: tiles already accounted for wholesale
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t hist;
+  asm volatile("mov.u32 %0, %1;" : "=r"(hist) : "r"((uint32_t)__cvta_generic_to_shared(s_cnt)));  // opaque: kept in a register
 #pragma unroll
   for (int r = 0; r < NRUN; ++r) reinterpret_cast<int4*>(s_cnt)[r * kSysThreads + tid] = make_int4(0, 0, 0, 0);
   if (tid == 0) reinterpret_cast<int4*>(s_cnt)[NRUN * kSysThreads] = make_int4(0, 0, 0, 0);
@@ -911,9 +912,10 @@ __global__ void __launch_bounds__(kSysThreads, 12)
       sp.a_hi = mulhi64(F0, Q);
       sp.d_lo = c_rq_lo;
       sp.d_hi = c_rq_hi;
-      sp.a_frac = __ull2double_rn(sp.a_lo) * 0x1p-64;
       sp.inv = c_inv;
+      sp.k = 0.5 - __ull2double_rn(sp.a_lo) * 0x1p-64 * c_inv;
     }
+    const double near_thr = 0.5 - eps;
     const bool wide = T1 - T0 >= 3;
     if (wide) {
       for (int w = tid; w < kMaxTiles / 32; w += kSysThreads) s_skip[w] = 0u;
@@ -925,10 +927,9 @@ __global__ void __launch_bounds__(kSysThreads, 12)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const unsigned long long C = __ldg(e ? &ix.tile_incl[T] : &ix.tile_excl[T]);  // = CDF of a real entry of the window, both
-          int n;
-          double f;
-          sys_estimate(sp, C, n, f);
-          o2[e] = fabs(f) < eps ? sys_first_exact(sp.a_lo, sp.a_hi, sp.d_lo, sp.d_hi, C, n) : n + (f > 0.0 ? 1 : 0);
+          bool nr;
+          const int o = sys_estimate(sp, C, near_thr, nr);
+          o2[e] = nr ? sys_first_exact(sp.a_lo, sp.a_hi, sp.d_lo, sp.d_hi, C, o - 1) : o;
         }
         if (o2[0] == o2[1]) {
           if ((unsigned)o2[1] < (unsigned)kSysParticles) atomicAdd(&s_cnt[o2[1]], ix.tile_items);
@@ -948,19 +949,16 @@ __global__ void __launch_bounds__(kSysThreads, 12)
         if (!(wide && ((s_skip[T >> 5] >> (T & 31)) & 1u))) {
           const unsigned long long base = __ldg(&ix.tile_excl[T]);
           auto tally = [&](bool valid, unsigned long long C) {
-            int n;
-            double f;
-            sys_estimate(sp, C, n, f);
-            const bool nr = fabs(f) < eps;
-            int o = n + (f > 0.0 ? 1 : 0);
+            bool nr;
+            int o = sys_estimate(sp, C, near_thr, nr);
             if (EXACT) {
               if (valid && nr) {
-                o = sys_first_exact(sp.a_lo, sp.a_hi, sp.d_lo, sp.d_hi, C, n);
+                o = sys_first_exact(sp.a_lo, sp.a_hi, sp.d_lo, sp.d_hi, C, o - 1);
                 if ((unsigned)o < (unsigned)kSysParticles) atomicAdd(&s_cnt[o], 1);
               }
             } else {
               near |= valid && nr;
-              if (valid && !nr && (unsigned)o < (unsigned)kSysParticles) atomicAdd(&s_cnt[o], 1);
+              hist_inc(hist, o, valid && !nr && (unsigned)o < (unsigned)kSysParticles);
             }
           };
           for (int j = tlo + 2 * tid; j < thi; j += 4 * kSysThreads) {  // tlo even, tile_items even; two loads in flight
