@@ -3,7 +3,7 @@
 // One time step of bootstrap_filter! (/root/reference/src/particles.jl:107-129):
 //
 //   sorted resamplers (stratified / systematic) — four launches chained by programmatic dependent
-//   launch, see the block comment further down:   sum_kernel -> bounds_kernel -> anc_kernel -> move_kernel
+//   launch, see the block comment further down:   sum_kernel -> bounds_kernel -> anc_hist_kernel -> move_kernel
 //
 //   multinomial (the reference's i.i.d. law, unsorted thresholds) — two launches:
 //   scan_kernel  normalize() + the CDF of resample():  reads logw, quantises exp(logw - max) to
@@ -424,12 +424,11 @@ __global__ void __launch_bounds__(kPropThreads)
 // every CTA publishes the prefixes of its 8 tiles and one CTA total, the last CTA scans the <= 1024
 // CTA totals (exact integers, so every ancestor equals the one a sequential CDF would give).
 // bounds_kernel finds, for every ancestor CTA, the ancestor of its first particle (32-ary warp
-// searches of the tile index and of one tile).  anc_kernel stages exactly the CDF entries between its
-// own and the next CTA's bound in shared memory (adding the tile offsets; one pad slot per 16
-// entries against bank conflicts) and every thread resolves two runs of 4 CONSECUTIVE particles in
-// lock step: one branch-free binary search per run, then a forward walk that re-reads shared memory
-// only when the ancestor advances; the systematic thresholds tau_i = hi64((i R + u) Q) are advanced
-// by one 128-bit add of R Q.  move_kernel gathers the parents through the sorted int32 ancestor
+// searches of the tile index and of one tile).  anc_hist_kernel reads exactly the CDF entries between
+// its own and the next CTA's bound and turns each into "the first particle whose threshold reaches
+// it" by arithmetic (the thresholds are an arithmetic progression, systematic, or one per stratum,
+// stratified) — a histogram and a prefix sum give the ancestors, no search and no walk (see the block
+// comment at the kernel).  move_kernel gathers the parents through the sorted int32 ancestor
 // vector, draws the transition (Philox + Box-Muller), weights, and feeds the exact max.
 // HBM traffic per particle-update (LG1D fp64): logw 8 R + cl 8 W | cl 8 R + anc 4 W | anc 4 R + x 8 R
 // + x' 8 W + logw' 8 W = 56 B, the algorithmic figure of SURVEY.md §8(d).
@@ -439,11 +438,9 @@ constexpr int kSumWarps = kSumThreads / 32;
 constexpr int kSumCtasPerSm = 4;
 constexpr int kMaxTiles = 8192;                        // tiles of one step (one warp each)
 constexpr int kMaxSumCtas = kMaxTiles / kSumWarps;     // CTA totals scanned by the last CTA of sum_kernel
-constexpr int kP2Threads = 128;
-// consecutive particles per thread (9, an odd stride in the shared window, measured slower than 8)
-constexpr int kP2Per = 8;
-constexpr int kP2Particles = kP2Threads * kP2Per;      // 1024 particles per CTA
-constexpr int kWinCap = 2048;                          // CDF entries staged per pass (16 KB)
+constexpr int kSysThreads = 128;                       // anc_hist_kernel: 128 threads x 16 particles (256 x 16: 45 us, 128 x 8: 45 us, 128 x 16: 39 us)
+constexpr int kSysPer = 16;                            // particles per thread: kSysPer / 4 runs of 4 consecutive ones
+constexpr int kSysParticles = kSysThreads * kSysPer;   // 2048 particles per ancestor CTA
 
 
 __global__ void __launch_bounds__(kSumThreads, kSumCtasPerSm)
@@ -650,38 +647,6 @@ __global__ void __launch_bounds__(kSumThreads, kSumCtasPerSm)
   }
 }
 
-// #{ t in [0,n) : v[t] <= tau } by one warp, 32 probes per round (v sorted ascending)
-__device__ __forceinline__ int warp_count_le(const unsigned long long* __restrict__ v, int n, uint64_t tau, int lane) {
-  int lo = 0, hi = n;
-  while (hi > lo) {
-    const int len = hi - lo;
-    const int step = (len + 31) >> 5;
-    const int p = lo + lane * step + (step - 1);
-    const bool le = (p < hi) && (__ldg(&v[p]) <= tau);
-    const int c = __popc(__ballot_sync(kFullMask, le));
-    lo += c * step;
-    if (c == 32) break;
-    const int nh = lo + step - 1;
-    hi = nh < hi ? nh : hi;
-  }
-  return lo;
-}
-
-// ancestor (global particle index) of threshold tau < Q by one warp: tile index, then the tile's local CDF
-__device__ __forceinline__ int locate_pos(const StepIndex& ix, const unsigned long long* __restrict__ cl, int N, uint64_t tau,
-                                          int lane, int& tile_out) {
-  int T = warp_count_le(ix.tile_incl, ix.ntiles, tau, lane);
-  if (T > ix.ntiles - 1) T = ix.ntiles - 1;
-  const uint64_t rem = tau - __ldg(&ix.tile_excl[T]);
-  const int t0 = T * ix.tile_items;
-  int n = N - t0;
-  if (n > ix.tile_items) n = ix.tile_items;
-  int c = warp_count_le(cl + t0, n, rem, lane);
-  if (c > n - 1) c = n - 1;
-  tile_out = T;
-  return t0 + c;
-}
-
 // two independent searches in lock step (one warp): the dependent round trips of the two overlap
 __device__ __forceinline__ void warp_count_le2(const unsigned long long* __restrict__ v0, const unsigned long long* __restrict__ v1, int n0,
                                                int n1, uint64_t tau0, uint64_t tau1, int lane, int& r0, int& r1) {
@@ -758,73 +723,6 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-__device__ __forceinline__ unsigned long long lds_u64(uint32_t saddr) {
-  unsigned long long v;
-  asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(saddr));
-  return v;
-}
-// The CDF window lives in shared memory with ONE PAD SLOT PER 16 ENTRIES: entry p sits in slot
-// p + (p >> 4).  A binary search probes p = 16 m + 15, 32 m + 31, ... — in a dense array all lanes of a
-// half-warp hit the same bank pair (16-way conflicts); with the pad the slot is 17 m + 15 and the lanes
-// spread over all 16 bank pairs.  The same holds for the walk, where the lanes sit 4 entries apart.
-constexpr int kWinSlots = kWinCap + kWinCap / 16;
-__device__ __forceinline__ uint32_t win_addr(uint32_t sbase, int p) { return sbase + 8u * (uint32_t)(p + (p >> 4)); }
-__device__ __forceinline__ unsigned long long win_load(uint32_t sbase, int p) { return lds_u64(win_addr(sbase, p)); }
-
-// #{ j in [0,len) : cdf[j] <= tau } of a window of len <= kWinCap staged entries; branch-free, and run
-// entirely on SLOT addresses: before the step of size STEP the position is a multiple of 2 STEP, so
-// the probe pos + STEP - 1 sits (STEP-1) + ((STEP-1) >> 4) slots after it and advancing moves
-// STEP + (STEP >> 4) slots — both immediates.  `last` = address of entry len-1, whose value is > tau:
-// a probe past the window reads that entry instead, so nothing beyond the staged entries has to be
-// initialised.  sbase is the window's address in the shared state space (explicit ld.shared: through
-// a generic pointer ptxas re-derives the shared window base on every probe).
-template <int STEP>
-__device__ __forceinline__ uint32_t window_search_slot(uint32_t a, uint32_t last, uint64_t tau) {
-  const uint32_t probe = a + 8u * ((STEP - 1) + ((STEP - 1) >> 4));
-  if (lds_u64(probe < last ? probe : last) <= tau) a += 8u * (STEP + (STEP >> 4));
-  if constexpr (STEP > 1) return window_search_slot<STEP / 2>(a, last, tau);
-  else return a;
-}
-// two independent searches in lock step: both probes of a round are in flight together
-template <int STEP>
-__device__ __forceinline__ void window_search_slot2(uint32_t& a0, uint32_t& a1, uint32_t last, uint64_t tau0, uint64_t tau1) {
-  const uint32_t q0 = a0 + 8u * ((STEP - 1) + ((STEP - 1) >> 4)), q1 = a1 + 8u * ((STEP - 1) + ((STEP - 1) >> 4));
-  const unsigned long long e0 = lds_u64(q0 < last ? q0 : last);
-  const unsigned long long e1 = lds_u64(q1 < last ? q1 : last);
-  if (e0 <= tau0) a0 += 8u * (STEP + (STEP >> 4));
-  if (e1 <= tau1) a1 += 8u * (STEP + (STEP >> 4));
-  if constexpr (STEP > 1) window_search_slot2<STEP / 2>(a0, a1, last, tau0, tau1);
-}
-// entry index of a slot address: slot - slot / 17 (exact for slot < 70000: 61681 / 2^20 ~ 1/17)
-__device__ __forceinline__ int win_entry(uint32_t sbase, uint32_t a) {
-  const uint32_t slot = (a - sbase) >> 3;
-  return (int)(slot - ((slot * 61681u) >> 20));
-}
-__device__ __forceinline__ int window_count_le(uint32_t sbase, int len, uint64_t tau) {
-  return win_entry(sbase, window_search_slot<kWinCap / 2>(sbase, win_addr(sbase, len - 1), tau));
-}
-
-// s_cdf[0..len) <- global CDF entries [s0, s0+len) (tile-local values + tile offsets); s0 even.
-__device__ __forceinline__ void stage_window(unsigned long long* s_cdf, const StepIndex& ix,
-                                            const unsigned long long* __restrict__ cl, int s0, int len, int T, int tid) {
-  const int end = s0 + len;
-  int tlo = s0;
-  while (tlo < end) {
-    const int tend_full = (T + 1) * ix.tile_items;
-    const int thi = tend_full < end ? tend_full : end;
-    const unsigned long long base = __ldg(&ix.tile_excl[T]);
-    for (int j = tlo + 2 * tid; j < thi; j += 2 * kP2Threads) {  // tlo even, tile_items even
-      const ulonglong2 v = __ldcs(reinterpret_cast<const ulonglong2*>(cl + j));
-      const int p = j - s0;  // even: p and p + 1 share a 16-entry row, their slots are adjacent
-      unsigned long long* dst = s_cdf + (p + (p >> 4));
-      dst[0] = v.x + base;
-      dst[1] = v.y + base;  // the odd entry past the window (if any) is never read
-    }
-    tlo = thi;
-    ++T;
-  }
-}
-
 // Systematic thresholds are an arithmetic progression in 128-bit fixed point: tau_i = hi64(A + i D),
 // A = F_first Q, D = R Q.  So the FIRST particle of the CTA whose threshold reaches a CDF entry C,
 //     o(C) = min{ i >= 0 : tau_i >= C } = ceil((C 2^64 - A) / D),
@@ -853,6 +751,24 @@ __device__ __noinline__ int sys_first_exact(unsigned long long a_lo, unsigned lo
   for (int i = -1; i <= 1; ++i) o += (n + i < 0 || sys_tau_exact(a_lo, a_hi, d_lo, d_hi, n + i) < C) ? 1 : 0;
   return o;
 }
+// exact floor((C 2^64 - A) / D) given that it lies in {n-1, n, n+1}: the last i with A + i D <= C 2^64
+__device__ __noinline__ int strat_floor_exact(unsigned long long a_lo, unsigned long long a_hi, unsigned long long d_lo,
+                                              unsigned long long d_hi, unsigned long long C, int n) {
+  int is = n - 2;
+#pragma unroll
+  for (int i = -1; i <= 1; ++i) {
+    bool le = n + i < 0;
+    if (!le) {
+      const unsigned long long m = (unsigned long long)(n + i);
+      const unsigned long long plo = m * d_lo;
+      const unsigned long long slo = a_lo + plo;
+      const unsigned long long shi = a_hi + m * d_hi + mulhi64(m, d_lo) + (slo < plo ? 1ull : 0ull);
+      le = shi < C || (shi == C && slo == 0);
+    }
+    is += le ? 1 : 0;
+  }
+  return is;
+}
 // estimate of o(C) = ceil(quotient): o = round(quotient + 1/2); `near` when the quotient is within eps of an
 // integer (then o may be off by one and sys_first_exact(…, o - 1) decides).  sp.k = 1/2 - a_frac * inv.
 __device__ __forceinline__ int sys_estimate(const SysProgression& sp, unsigned long long C, double near_thr, bool& near) {
@@ -862,17 +778,29 @@ __device__ __forceinline__ int sys_estimate(const SysProgression& sp, unsigned l
   near = fabs(g) > near_thr;               // near_thr = 1/2 - eps
   return __double2loint(tt);
 }
+// ---- the ancestor kernel of the sorted resamplers (particles.jl:117 with SPEC §5's thresholds).
+// One CTA resolves kSysParticles consecutive particles.  It reads the CDF entries [a_lo, a_hi) between its
+// own first ancestor and the next CTA's (bounds_kernel), adds 1 to hist[o(C)] for each, o(C) = the first
+// local particle whose threshold reaches C, and the ancestor of local particle i is
+// a_lo + sum_{o <= i} hist[o].  No search, no window in shared memory.
+//   systematic: o(C) = ceil((C 2^64 - A) / D), A = F_first Q, D = R Q (SysProgression above);
+//   stratified: the thresholds are one per stratum of width R: with s = floor((C 2^64 - A) / D), A = first R Q,
+//               every earlier stratum's threshold is below C, every later one's is not, and stratum s
+//               itself is decided by its own uniform: o(C) = s + [tau_s < C]  (one Philox block per entry).
+// Very uneven weights make some windows long and mostly dead (no threshold falls into them).  Whole tiles
+// of such a window are accounted for with ONE add when o(first) == o(last) — read off the tile index,
+// not the entries — so a CTA streams at most the tiles that contain one of its thresholds.
+//
 // hist[o] += 1 when pred, as ONE predicated instruction on a shared-space address (an if around atomicAdd
 // compiles to a divergence region per call and re-derives the shared window base each time)
 __device__ __forceinline__ void hist_inc(uint32_t hist_saddr, int o, bool pred) {
   asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], 1;\n\t}" ::"r"(hist_saddr + 4u * (uint32_t)o), "r"((int)pred) : "memory");
 }
-constexpr int kSysThreads = 128;
-constexpr int kSysPer = 16;                              // particles per thread: kSysPer / 4 runs of 4 consecutive ones
-constexpr int kSysParticles = kSysThreads * kSysPer;
+template <int RESAMPLER>
 __global__ void __launch_bounds__(kSysThreads, 12)
-    anc_sys_kernel(int N, uint64_t Rw, StepIndex ix, const unsigned long long* __restrict__ cl, int32_t* __restrict__ anc_out,
-                   const FilterCtrl* __restrict__ ctrl, double eps) {
+    anc_hist_kernel(int N, uint64_t Rw, RngKey key, uint32_t stream, uint32_t t, StepIndex ix, const unsigned long long* __restrict__ cl,
+                    int32_t* __restrict__ anc_out, const FilterCtrl* __restrict__ ctrl, double eps) {
+  constexpr bool STRAT = RESAMPLER == RESAMPLE_STRATIFIED;
   constexpr int NW = kSysThreads / 32, NRUN = kSysPer / 4;
   __shared__ __align__(16) int s_cnt[kSysParticles + 4];
   __shared__ int s_wtot[NRUN][NW];
@@ -907,14 +835,31 @@ __global__ void __launch_bounds__(kSysThreads, 12)
   } else {
     SysProgression sp;
     {
-      const uint64_t F0 = (uint64_t)base_i * Rw + c_off;
+      const uint64_t F0 = (uint64_t)base_i * Rw + (STRAT ? 0ull : c_off);
       sp.a_lo = F0 * Q;
       sp.a_hi = mulhi64(F0, Q);
       sp.d_lo = c_rq_lo;
       sp.d_hi = c_rq_hi;
       sp.inv = c_inv;
-      sp.k = 0.5 - __ull2double_rn(sp.a_lo) * 0x1p-64 * c_inv;
+      sp.k = (STRAT ? -0.5 : 0.5) - __ull2double_rn(sp.a_lo) * 0x1p-64 * c_inv;  // round(q - 1/2) = floor, round(q + 1/2) = ceil
     }
+    // o(C) from the estimate e (and, stratified, the stratum's own threshold); valid entries only
+    auto first_reaching = [&](unsigned long long C, int e, bool& in_range) -> int {
+      if (!STRAT) {
+        in_range = (unsigned)e < (unsigned)kSysParticles;
+        return e;
+      }
+      in_range = false;
+      if ((unsigned)e >= (unsigned)kSysParticles || base_i + e >= N) return 0;  // a stratum of a later CTA (or past the last one)
+      const uint64_t i = (uint64_t)(base_i + e);
+      const uint64_t tau = threshold_of(RESAMPLE_STRATIFIED, i, Rw, uniform64_at(key, (uint32_t)i, stream, t, PURPOSE_RESAMPLE), Q);
+      const int o = e + (tau < C ? 1 : 0);
+      in_range = o < kSysParticles;
+      return o;
+    };
+    auto exact = [&](unsigned long long C, int e) -> int {
+      return STRAT ? strat_floor_exact(sp.a_lo, sp.a_hi, sp.d_lo, sp.d_hi, C, e) : sys_first_exact(sp.a_lo, sp.a_hi, sp.d_lo, sp.d_hi, C, e - 1);
+    };
     const double near_thr = 0.5 - eps;
     const bool wide = T1 - T0 >= 3;
     if (wide) {
@@ -927,12 +872,14 @@ __global__ void __launch_bounds__(kSysThreads, 12)
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
           const unsigned long long C = __ldg(e ? &ix.tile_incl[T] : &ix.tile_excl[T]);  // = CDF of a real entry of the window, both
-          bool nr;
-          const int o = sys_estimate(sp, C, near_thr, nr);
-          o2[e] = nr ? sys_first_exact(sp.a_lo, sp.a_hi, sp.d_lo, sp.d_hi, C, o - 1) : o;
+          bool nr, in;
+          int est = sys_estimate(sp, C, near_thr, nr);
+          if (nr) est = exact(C, est);
+          o2[e] = first_reaching(C, est, in);
+          if (!in) o2[e] = kSysParticles;  // (every entry of the window is reached by the next CTA's first particle at the latest)
         }
         if (o2[0] == o2[1]) {
-          if ((unsigned)o2[1] < (unsigned)kSysParticles) atomicAdd(&s_cnt[o2[1]], ix.tile_items);
+          if (o2[1] < kSysParticles) atomicAdd(&s_cnt[o2[1]], ix.tile_items);
           atomicOr(&s_skip[T >> 5], 1u << (T & 31));
         }
       }
@@ -949,16 +896,23 @@ __global__ void __launch_bounds__(kSysThreads, 12)
         if (!(wide && ((s_skip[T >> 5] >> (T & 31)) & 1u))) {
           const unsigned long long base = __ldg(&ix.tile_excl[T]);
           auto tally = [&](bool valid, unsigned long long C) {
-            bool nr;
-            int o = sys_estimate(sp, C, near_thr, nr);
+            bool nr, in;
+            const int est = sys_estimate(sp, C, near_thr, nr);
             if (EXACT) {
               if (valid && nr) {
-                o = sys_first_exact(sp.a_lo, sp.a_hi, sp.d_lo, sp.d_hi, C, o - 1);
-                if ((unsigned)o < (unsigned)kSysParticles) atomicAdd(&s_cnt[o], 1);
+                const int o = first_reaching(C, exact(C, est), in);
+                if (in) atomicAdd(&s_cnt[o], 1);
               }
             } else {
               near |= valid && nr;
-              hist_inc(hist, o, valid && !nr && (unsigned)o < (unsigned)kSysParticles);
+              if (STRAT) {
+                if (valid && !nr) {
+                  const int o = first_reaching(C, est, in);
+                  hist_inc(hist, o, in);
+                }
+              } else {
+                hist_inc(hist, est, valid && !nr && (unsigned)est < (unsigned)kSysParticles);
+              }
             }
           };
           for (int j = tlo + 2 * tid; j < thi; j += 4 * kSysThreads) {  // tlo even, tile_items even; two loads in flight
@@ -1029,219 +983,6 @@ __global__ void __launch_bounds__(kSysThreads, 12)
       for (int k = 0; k < 4; ++k)
         if (i + k < N) anc_out[i + k] = off[r] + v[r][k];
     }
-  }
-}
-
-// resample (particles.jl:117) for the sorted resamplers: the ancestor of every particle, written as
-// int32.  Model-independent and light in registers, so that many warps hide the dependent
-// shared-memory reads of the search and the walk.  Every thread owns kP2Per CONSECUTIVE particles.
-template <int RESAMPLER>
-__global__ void __launch_bounds__(kP2Threads, 10)  // 48 registers: 12 CTAs/SM spills (79 us), 8 CTAs/SM 72 us, 10 CTAs/SM 68 us at N = 2^24
-    anc_kernel(int N, uint64_t Rw, RngKey key, uint32_t stream, uint32_t t, StepIndex ix, const unsigned long long* __restrict__ cl,
-               int32_t* __restrict__ anc_out, const FilterCtrl* __restrict__ ctrl) {
-  constexpr int NW = kP2Threads / 32;
-  __shared__ __align__(16) unsigned long long s_cdf[kWinSlots];
-  __shared__ unsigned long long s_min[NW];
-  __shared__ int s_next[2];
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  uint32_t sbase;
-  asm volatile("mov.u32 %0, %1;" : "=r"(sbase) : "r"((uint32_t)__cvta_generic_to_shared(s_cdf)));  // opaque: kept in a register, not re-derived
-  pdl_launch_dependents();
-  pdl_wait();  // the window bounds come from bounds_kernel
-  const uint64_t Q = ctrl->total;
-  const int i0 = blockIdx.x * kP2Particles + tid * kP2Per;  // first particle of this thread
-  const bool full_cta = (int64_t)(blockIdx.x + 1) * kP2Particles <= (int64_t)N;
-
-  int anc[kP2Per];
-#pragma unroll
-  for (int k = 0; k < kP2Per; ++k) anc[k] = (i0 + k < N) ? i0 + k : N - 1;  // Q == 0: every particle is its own ancestor (SPEC §5)
-
-  if (Q != 0) {
-    const int a_lo = __ldg(&ix.bound_pos[blockIdx.x]);
-    const int a_hi = __ldg(&ix.bound_pos[blockIdx.x + 1]);  // ancestor of the next CTA's first particle >= all of mine
-    int T0 = __ldg(&ix.bound_tile[blockIdx.x]);
-    int s0 = a_lo & ~1;
-    if (a_hi - s0 + 1 <= kWinCap) {
-      // ---- common case: the whole window fits one pass.  C[a_hi] > every tau of this CTA, so the
-      // walk below always stops inside the staged entries.
-      stage_window(s_cdf, ix, cl, s0, a_hi - s0 + 1, T0, tid);
-      const int p_last = a_hi - s0;  // C[a_hi] > every tau of this CTA
-      // thresholds (SPEC §5): tau_i = hi64(F_i Q); systematic: F_{i+1} Q = F_i Q + R Q as a 128-bit value
-      unsigned long long dlo = 0, dhi = 0;
-      if (RESAMPLER == RESAMPLE_SYSTEMATIC) {
-        dlo = ctrl->rq_lo;  // R Q, written by sum_kernel
-        dhi = ctrl->rq_hi;
-      }
-      if (full_cta) {
-        // Full CTA: every thread resolves TWO runs of kP2Per/2 consecutive particles half a CTA apart, in
-        // lock step — two independent ld.shared chains per thread hide each other's latency, a walk
-        // round serves both runs, and the lanes of a warp sit kP2Per/2 entries apart in the window.
-        constexpr int H = kP2Per / 2;
-        const int iA = blockIdx.x * kP2Particles + tid * H, iB = iA + kP2Particles / 2;
-        unsigned long long alo = 0, ahi = 0, blo = 0, bhi = 0;
-        uint64_t tA[H], tB[H];
-        if (RESAMPLER == RESAMPLE_SYSTEMATIC) {
-          const uint64_t FA = (uint64_t)iA * Rw + ctrl->sys_off, FB = (uint64_t)iB * Rw + ctrl->sys_off;
-          alo = FA * Q; ahi = mulhi64(FA, Q);
-          blo = FB * Q; bhi = mulhi64(FB, Q);
-        } else {
-#pragma unroll
-          for (int k = 0; k < H; ++k) {
-            tA[k] = threshold_of(RESAMPLER, (uint64_t)(iA + k), Rw, uniform64_at(key, (uint32_t)(iA + k), stream, t, PURPOSE_RESAMPLE), Q);
-            tB[k] = threshold_of(RESAMPLER, (uint64_t)(iB + k), Rw, uniform64_at(key, (uint32_t)(iB + k), stream, t, PURPOSE_RESAMPLE), Q);
-          }
-        }
-        auto next_tau = [&](int k, unsigned long long& lo, unsigned long long& hi, const uint64_t* tv) -> uint64_t {
-          if (RESAMPLER == RESAMPLE_SYSTEMATIC) {
-            const uint64_t v = hi;
-            asm("add.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, %3;" : "+l"(lo), "+l"(hi) : "l"(dlo), "l"(dhi));
-            return v;
-          }
-          return tv[k];
-        };
-        __syncthreads();
-        int pA, pB;
-        {
-          const uint64_t t0 = next_tau(0, alo, ahi, tA), t1 = next_tau(0, blo, bhi, tB);
-          uint32_t aA = sbase, aB = sbase;
-          window_search_slot2<kWinCap / 2>(aA, aB, win_addr(sbase, p_last), t0, t1);
-          pA = win_entry(sbase, aA);
-          pB = win_entry(sbase, aB);
-        }
-        unsigned long long curA = win_load(sbase, pA), curB = win_load(sbase, pB);
-        int ancA[H], ancB[H];
-        ancA[0] = s0 + pA;
-        ancB[0] = s0 + pB;
-#pragma unroll
-        for (int k = 1; k < H; ++k) {
-          const uint64_t t0 = next_tau(k, alo, ahi, tA), t1 = next_tau(k, blo, bhi, tB);
-          bool mA = curA <= t0, mB = curB <= t1;
-          while (mA || mB) {
-            if (mA) {
-              ++pA;
-              curA = win_load(sbase, pA);
-            }
-            if (mB) {
-              ++pB;
-              curB = win_load(sbase, pB);
-            }
-            mA = curA <= t0;
-            mB = curB <= t1;
-          }
-          ancA[k] = s0 + pA;
-          ancB[k] = s0 + pB;
-        }
-        static_assert(H == 4, "the vector stores below assume 4 particles per run");
-        *reinterpret_cast<int4*>(anc_out + iA) = make_int4(ancA[0], ancA[1], ancA[2], ancA[3]);
-        *reinterpret_cast<int4*>(anc_out + iB) = make_int4(ancB[0], ancB[1], ancB[2], ancB[3]);
-        return;
-      }
-      // the last, partial CTA: 8 consecutive particles per thread with bounds checks
-      unsigned long long plo = 0, phi = 0;
-      uint64_t tau[kP2Per];
-      if (RESAMPLER == RESAMPLE_SYSTEMATIC) {
-        const uint64_t F0 = (uint64_t)i0 * Rw + ctrl->sys_off;
-        plo = F0 * Q;
-        phi = mulhi64(F0, Q);
-      } else {
-#pragma unroll
-        for (int k = 0; k < kP2Per; ++k)
-          tau[k] = threshold_of(RESAMPLER, (uint64_t)(i0 + k), Rw, uniform64_at(key, (uint32_t)(i0 + k), stream, t, PURPOSE_RESAMPLE), Q);
-      }
-      auto tau_at = [&](int k) -> uint64_t {
-        if (RESAMPLER == RESAMPLE_SYSTEMATIC) {
-          const uint64_t v = phi;
-          asm("add.cc.u64 %0, %0, %2;\n\taddc.u64 %1, %1, %3;" : "+l"(plo), "+l"(phi) : "l"(dlo), "l"(dhi));
-          return v;
-        }
-        return tau[k];
-      };
-      __syncthreads();
-      if (i0 < N) {
-        int p = window_count_le(sbase, p_last + 1, tau_at(0));
-        unsigned long long cur = win_load(sbase, p);
-        anc[0] = s0 + p;
-#pragma unroll
-        for (int k = 1; k < kP2Per; ++k) {
-          const uint64_t tk = tau_at(k);
-          if (i0 + k < N) {
-            while (cur <= tk) {
-              ++p;
-              cur = win_load(sbase, p);
-            }
-          }
-          anc[k] = s0 + p;
-        }
-      }
-    } else {
-      // ---- wide window (very uneven weights): pass by pass, each pass starting at the ancestor of
-      // the smallest unresolved threshold; per-particle binary search inside the staged segment
-      uint64_t tau[kP2Per];
-#pragma unroll
-      for (int k = 0; k < kP2Per; ++k) {
-        uint64_t u = ctrl->sys_off;
-        if (RESAMPLER != RESAMPLE_SYSTEMATIC) u = uniform64_at(key, (uint32_t)(i0 + k), stream, t, PURPOSE_RESAMPLE);
-        tau[k] = threshold_of(RESAMPLER, (uint64_t)(i0 + k), Rw, u, Q);
-      }
-      int next = 0;  // first unresolved particle of this thread
-      int nvalid = N - i0;
-      nvalid = nvalid < 0 ? 0 : (nvalid > kP2Per ? kP2Per : nvalid);
-      while (true) {
-        int len = a_hi - s0 + 1;
-        const bool final_seg = len <= kWinCap;
-        if (!final_seg) len = kWinCap;
-        stage_window(s_cdf, ix, cl, s0, len, T0, tid);
-        __syncthreads();
-        const unsigned long long c_end = final_seg ? ~0ull : win_load(sbase, len - 1);
-        unsigned long long my_min = ~0ull;
-#pragma unroll
-        for (int k = 0; k < kP2Per; ++k) {
-          if (k >= next && k < nvalid) {
-            if (tau[k] < c_end) {
-              anc[k] = s0 + window_count_le(sbase, len, tau[k]);
-              next = k + 1;
-            } else if (tau[k] < my_min) {
-              my_min = tau[k];
-            }
-          }
-        }
-        if (__syncthreads_and(next >= nvalid)) break;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const unsigned long long v = __shfl_xor_sync(kFullMask, my_min, o);
-          my_min = v < my_min ? v : my_min;
-        }
-        if (lane == 0) s_min[warp] = my_min;
-        __syncthreads();
-        if (warp == 0) {
-          unsigned long long v = (lane < NW) ? s_min[lane] : ~0ull;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-            const unsigned long long w = __shfl_xor_sync(kFullMask, v, o);
-            v = w < v ? w : v;
-          }
-          int T;
-          const int p = locate_pos(ix, cl, N, v, lane, T);
-          if (lane == 0) {
-            s_next[0] = p;
-            s_next[1] = T;
-          }
-        }
-        __syncthreads();
-        s0 = s_next[0] & ~1;  // rounding down to even never leaves the tile (tile_items even)
-        T0 = s_next[1];
-      }
-    }
-  }
-  if (full_cta) {
-#pragma unroll
-    for (int q = 0; q < kP2Per / 4; ++q)
-      reinterpret_cast<int4*>(anc_out + i0)[q] = make_int4(anc[4 * q], anc[4 * q + 1], anc[4 * q + 2], anc[4 * q + 3]);
-  } else {
-#pragma unroll
-    for (int k = 0; k < kP2Per; ++k)
-      if (i0 + k < N) anc_out[i0 + k] = anc[k];
   }
 }
 
@@ -1319,7 +1060,7 @@ __global__ void __launch_bounds__(kMoveThreads, (Model::D == 1) ? 6 : 3)
   mdl.load(dv.d);
   const int i0 = (blockIdx.x * kMoveThreads + tid) * PER;
   pdl_launch_dependents();
-  pdl_wait();  // the ancestors come from anc_kernel
+  pdl_wait();  // the ancestors come from anc_hist_kernel
   double vmax;
   if ((int64_t)(blockIdx.x + 1) * (kMoveThreads * PER) <= (int64_t)N)
     vmax = move_particles<Model, true>(mdl, y, N, ld, key, stream, t, i0, anc, xprev, xnew, logw);
@@ -1516,7 +1257,7 @@ void SingleFilter::ensure_capacity(int kind, int64_t N, int64_t anc_rows) {
   if (!ctrl_) SMCB_CUDA_TRY(cudaMalloc(&ctrl_, sizeof(FilterCtrl)));
   if (!tile_arrays_) SMCB_CUDA_TRY(cudaMalloc(&tile_arrays_, sizeof(unsigned long long) * 5 * kMaxTiles));
   {
-    const int64_t nb = cap_N_ / kP2Particles + 3;
+    const int64_t nb = cap_N_ / kSysParticles + 3;
     if (nb > bound_cap_) {
       cudaFree(bound_arrays_); bound_arrays_ = nullptr; bound_cap_ = 0;
       SMCB_CUDA_TRY(cudaMalloc(&bound_arrays_, sizeof(int32_t) * 2 * nb));
@@ -1695,7 +1436,7 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler) {
   StepIndex ix;
   unsigned long long* cl = step_index(ix);
   if (!sum_done_) launch_sum(stat_index);  // (a stepping caller already ran it to read the statistics of the current weights)
-  const int block_particles = resampler == RESAMPLE_SYSTEMATIC ? kSysParticles : kP2Particles;
+  const int block_particles = kSysParticles;
   const unsigned nblocks = (unsigned)((N_ + block_particles - 1) / block_particles);
   const uint32_t t = t_ + 1;
   const int nbounds = (int)nblocks + 1;
@@ -1712,10 +1453,11 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler) {
   }
   mark(TK_ANC, true);
   if (resampler == RESAMPLE_SYSTEMATIC)
-    SMCB_CUDA_TRY(launch_pdl(anc_sys_kernel, dim3(nblocks), dim3(kSysThreads), stream_, (int)N_, R_, ix, cl, anc, ctrl_, anc_eps_));
+    SMCB_CUDA_TRY(launch_pdl(anc_hist_kernel<RESAMPLE_SYSTEMATIC>, dim3(nblocks), dim3(kSysThreads), stream_, (int)N_, R_, key_, stream_id_, t, ix, cl,
+                             anc, ctrl_, anc_eps_));
   else
-    SMCB_CUDA_TRY(launch_pdl(anc_kernel<RESAMPLE_STRATIFIED>, dim3(nblocks), dim3(kP2Threads), stream_, (int)N_, R_, key_, stream_id_, t, ix, cl, anc,
-                             ctrl_));
+    SMCB_CUDA_TRY(launch_pdl(anc_hist_kernel<RESAMPLE_STRATIFIED>, dim3(nblocks), dim3(kSysThreads), stream_, (int)N_, R_, key_, stream_id_, t, ix, cl,
+                             anc, ctrl_, anc_eps_));
   mark(TK_ANC, false);
   SMCB_CUDA_TRY(cudaGetLastError());
   const unsigned mblocks = (unsigned)((N_ + kMoveThreads * 2 * kMovePairs - 1) / (kMoveThreads * 2 * kMovePairs));

@@ -17,7 +17,7 @@ struct FilterCtrl {
   unsigned long long total;       // Q = C[N-1] of the last scan
   unsigned long long sys_off;     // mulhi(U(0), R) of the systematic resampler for the coming step
   unsigned long long rq_lo, rq_hi;  // R * Q as a 128-bit value: the increment of (i R + u) Q per particle
-  double inv_rq;                  // 2^64 / (R Q) in double: ESTIMATE of 1 / (threshold spacing), see anc_kernel
+  double inv_rq;                  // 2^64 / (R Q) in double: ESTIMATE of 1 / (threshold spacing), see anc_hist_kernel
   unsigned int scan_ticket;       // dynamic tile ids of the look-back scan
   unsigned int scan_done;
 };
@@ -125,7 +125,7 @@ class SingleFilter {
   int32_t* bound_arrays_ = nullptr;            // [2][bound_cap_]: ancestor of each propagate CTA's first particle, its tile
   int64_t bound_cap_ = 0;
   int num_sms_ = 0;
-  double anc_eps_ = 1e-9;  // anc_kernel: quotient estimates closer than this to an integer are decided exactly (test hook: SMCB_ANC_FORCE_EXACT)
+  double anc_eps_ = 1e-9;  // anc_hist_kernel: quotient estimates closer than this to an integer are decided exactly (test hook: SMCB_ANC_FORCE_EXACT)
   bool sum_done_ = false;   // sum_kernel already ran for the current weights (statistics read by a stepping caller)
   bool logw_valid_ = true;  // logw_[cur_] holds the current log-weights (false: implicit in x_[cur_] and y_cur_)
   double y_cur_ = 0.0;      // observation the current weights were computed against
