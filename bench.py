@@ -98,7 +98,7 @@ class ClockSampler:
 
 # algorithmic bytes per particle-update of each launch of one step (LG1D fp64): they add up to the 56 B of SURVEY §8(d)
 KERNEL_BYTES = {"scan": 16, "bounds": 0, "anc": 12, "prop": 28}
-KERNEL_NAMES = {"scan": "sum_kernel", "bounds": "bounds_kernel", "anc": "anc_kernel", "prop": "move_kernel"}
+KERNEL_NAMES = {"scan": "sum_kernel", "bounds": "bounds_kernel", "anc": "anc_hist_kernel", "prop": "move_kernel"}
 
 
 def cpu_sample(steps, logn_sample=20, T_sample=64):
@@ -272,7 +272,7 @@ def main():
         "wall_ms_per_step_kernel_arm": 1e3 * wall_kernel_max / args.steps,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
                      "traffic": load_traffic(), "peak_source": peak_src,
-                     "kernel": "one filter step = sum_kernel + bounds_kernel + anc_kernel + move_kernel "
+                     "kernel": "one filter step = sum_kernel + bounds_kernel + anc_hist_kernel + move_kernel "
                                "(16 + 0 + 12 + 28 = 56 algorithmic B/particle-update, SURVEY §8d)",
                      "step_us": fused, "step_us_sum_of_per_launch_events": fused_events,
                      "avg_us_per_launch": step_us,

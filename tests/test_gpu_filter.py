@@ -311,7 +311,7 @@ def test_fuzz_sizes_and_weight_profiles(ctx, oracle):
 
 
 def test_systematic_exact_decision_path(oracle, monkeypatch):
-    """anc_kernel decides `first particle whose threshold reaches a CDF entry` from a double estimate and
+    """anc_hist_kernel decides `first particle whose threshold reaches a CDF entry` from a double estimate and
     falls back to exact 128-bit comparisons when the estimate is within 1e-9 of an integer — a path
     random inputs almost never take.  SMCB_ANC_FORCE_EXACT makes every entry take it; the ancestors
     must not change."""
