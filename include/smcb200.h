@@ -66,6 +66,11 @@ int smcb_get_epoch(const smcb_ctx* ctx, uint32_t* next_epoch);
 int smcb_record_ancestors(smcb_ctx* ctx, int enable);
 /* per-kernel CUDA-event timing of the single filter (bench.py roofline); off by default */
 int smcb_set_profiling(smcb_ctx* ctx, int enable);
+/* State storage of the single filter from the next smcb_bootstrap_init / smcb_log_likelihood on:
+ * 0 = binary64 (default), 1 = binary32 states (docs/SPEC.md §9: every state component is rounded to
+ * binary32 where it is stored, arithmetic stays binary64; sorted resamplers only).  The reference has
+ * Float64 only (src/particles.jl:87-147); this is the north star's fp32 tier.  Host-facing arrays stay double. */
+int smcb_set_precision(smcb_ctx* ctx, int precision);
 /* device time of the last sweep / step, and per-kernel-class totals when profiling is on:
  * ms[0] whole call, ms[1] sum/scan (quantise + prefix sums + Σe, Σe²), ms[2] gather+propagate+weight
  * (plus the ancestor search on the multinomial path), ms[3] init, ms[4] stats-only, ms[5] window bounds,

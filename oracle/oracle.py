@@ -180,6 +180,23 @@ def resample_w(w, resampler, seed, epoch, stream, t, purpose=P_RESAMPLE):
     return a
 
 
+class state_f32:
+    """`with oracle.state_f32(): ...` runs the filters in SPEC §9's binary32-state tier (states rounded to
+    binary32 where the device stores them; arithmetic unchanged)."""
+
+    def __init__(self, on=True):
+        self.on = bool(on)
+
+    def __enter__(self):
+        self.prev = lib().smco_get_state_f32()
+        lib().smco_set_state_f32(C.c_int(1 if self.on else 0))
+        return self
+
+    def __exit__(self, *exc):
+        lib().smco_set_state_f32(C.c_int(self.prev))
+        return False
+
+
 # ---------------------------------------------------------------- a3 / a4 / a5
 def bootstrap_init(kind, params, n, y0, seed, epoch=0, stream=0):
     """bootstrap_filter(N, y, model) -> (x [d,n], logw)   particles.jl:87-105 (weights left unnormalised)"""

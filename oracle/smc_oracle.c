@@ -170,6 +170,18 @@ void smco_resample_w(const double *w, int64_t n, int resampler, uint64_t seed, u
   free(q);
 }
 
+/* SPEC §9: the binary32 STATE tier.  When set, every state component is rounded to binary32 right
+ * after it is drawn (initial draw and transition) — it is what the device stores — and everything
+ * downstream (log-weight, quantisation, resampling, the next transition) sees the rounded value,
+ * all arithmetic staying binary64.  Process-global: tests set it, run, and reset it. */
+static int g_state_f32 = 0;
+void smco_set_state_f32(int on) { g_state_f32 = on ? 1 : 0; }
+int smco_get_state_f32(void) { return g_state_f32; }
+static inline void round_state(double *xi, int d) {
+  if (g_state_f32)
+    for (int k = 0; k < d; ++k) xi[k] = (double)(float)xi[k];
+}
+
 /* ------------------------------------------------------------------ a3 bootstrap_filter */
 /* x is SoA [d][n]. */
 void smco_bootstrap_init(int kind, const double *P, int64_t n, double y, uint64_t seed, uint32_t epoch,
@@ -181,6 +193,7 @@ void smco_bootstrap_init(int kind, const double *P, int64_t n, double y, uint64_
     double z[3] = {0, 0, 0}, xi[3];
     for (int k = 0; k < d; ++k) z[k] = o_normal(seed, epoch, (uint32_t)i, stream, 0, P_INIT, (uint32_t)k);
     model_init(kind, D, z, xi);
+    round_state(xi, d);
     for (int k = 0; k < d; ++k) x[(int64_t)k * n + i] = xi[k];
     logw[i] = model_logweight(kind, D, xi, y);
   }
@@ -204,6 +217,7 @@ void smco_bootstrap_step(int kind, const double *P, int64_t n, double y, uint32_
       par[k] = xp[(int64_t)k * n + i];
     }
     model_transition(kind, D, z, par, xi);
+    round_state(xi, d);
     for (int k = 0; k < d; ++k) x[(int64_t)k * n + i] = xi[k];
     logw[i] = model_logweight(kind, D, xi, y);
   }

@@ -30,6 +30,7 @@ SIGNATURES = {
     "smcb_get_epoch": (C.c_int, [_c_ctx, C.POINTER(C.c_uint32)]),
     "smcb_record_ancestors": (C.c_int, [_c_ctx, C.c_int]),
     "smcb_set_profiling": (C.c_int, [_c_ctx, C.c_int]),
+    "smcb_set_precision": (C.c_int, [_c_ctx, C.c_int]),
     "smcb_get_timing": (C.c_int, [_c_ctx, _dp, _i64p]),
     "smcb_synchronize": (C.c_int, [_c_ctx]),
     "smcb_alloc_pinned": (C.c_int, [_c_ctx, C.c_int64, C.POINTER(C.c_void_p)]),
@@ -213,6 +214,12 @@ class Context:
 
     def set_profiling(self, on=True):
         self._check(self._lib.smcb_set_profiling(self._h, int(bool(on))))
+
+    def set_precision(self, precision):
+        """State storage of the single filter from the next bootstrap_init / log_likelihood on: "f64" (default)
+        or "f32" (docs/SPEC.md §9: states rounded to binary32 where stored, arithmetic binary64, sorted resamplers)."""
+        p = {"f64": 0, "f32": 1, 0: 0, 1: 1, "float64": 0, "float32": 1}[precision]
+        self._check(self._lib.smcb_set_precision(self._h, p))
 
     def timing(self):
         ms = (C.c_double * 7)()

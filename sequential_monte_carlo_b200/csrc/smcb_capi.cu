@@ -127,6 +127,12 @@ int smcb_set_profiling(smcb_ctx* ctx, int enable) {
   return SMCB_OK;
 }
 
+int smcb_set_precision(smcb_ctx* ctx, int precision) {
+  if (!ctx || precision < 0 || precision > 1) return SMCB_ERR_BAD_ARG;
+  ctx->filter->set_precision(precision);
+  return SMCB_OK;
+}
+
 int smcb_get_timing(const smcb_ctx* ctx, double ms[7], int64_t launches[7]) {
   if (!ctx || !ms || !launches) return SMCB_ERR_BAD_ARG;
   ctx->filter->timing(ms, launches);

@@ -69,11 +69,24 @@ __global__ void reset_ctrl_kernel(FilterCtrl* ctrl) {
   ctrl->scan_done = 0;
 }
 
+// State storage type XT (docs/SPEC.md §9): double, or float = every state component rounded to
+// binary32 right after it is drawn; all arithmetic stays binary64.
+template <class XT> struct XVec2;
+template <> struct XVec2<double> { using type = double2; static __device__ __forceinline__ double2 make(double a, double b) { return make_double2(a, b); } };
+template <> struct XVec2<float> { using type = float2; static __device__ __forceinline__ float2 make(double a, double b) { return make_float2((float)a, (float)b); } };
+template <class XT, int D>
+__device__ __forceinline__ void round_state(double (&x)[D]) {
+  if (sizeof(XT) == 4) {
+#pragma unroll
+    for (int k = 0; k < D; ++k) x[k] = (double)(float)x[k];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // bootstrap_filter: x_i ~ initial_dist, logw_i = logpdf(observation(x_i), y)   particles.jl:96-99
-template <class Model>
+template <class Model, class XT>
 __global__ void __launch_bounds__(256) init_kernel(Derived dv, double y0, int64_t N, int64_t ld, RngKey key,
-                                                    uint32_t stream, double* __restrict__ x,
+                                                    uint32_t stream, XT* __restrict__ x,
                                                     double* __restrict__ logw, FilterCtrl* ctrl) {
   constexpr int D = Model::D;
   __shared__ double sh[32];
@@ -88,18 +101,20 @@ __global__ void __launch_bounds__(256) init_kernel(Derived dv, double y0, int64_
     for (int k = 0; k < D; ++k) normal_pair_at(key, (uint32_t)p, stream, 0u, PURPOSE_INIT, (uint32_t)k, za[k], zb[k]);
     mdl.init(za, xa);
     mdl.init(zb, xb);
+    round_state<XT>(xa);
+    round_state<XT>(xb);
     const double la = mdl.logweight(xa, y0);
     const double lb = mdl.logweight(xb, y0);
     const int64_t i = 2 * p;
     if (i + 1 < N) {
 #pragma unroll
-      for (int k = 0; k < D; ++k) *reinterpret_cast<double2*>(x + k * ld + i) = make_double2(xa[k], xb[k]);
+      for (int k = 0; k < D; ++k) *reinterpret_cast<typename XVec2<XT>::type*>(x + k * ld + i) = XVec2<XT>::make(xa[k], xb[k]);
       *reinterpret_cast<double2*>(logw + i) = make_double2(la, lb);
       if (la > vmax) vmax = la;  // `>` ignores NaN like the CPU loop
       if (lb > vmax) vmax = lb;
     } else {
 #pragma unroll
-      for (int k = 0; k < D; ++k) x[k * ld + i] = xa[k];
+      for (int k = 0; k < D; ++k) x[k * ld + i] = (XT)xa[k];
       logw[i] = la;
       if (la > vmax) vmax = la;
     }
@@ -443,8 +458,9 @@ constexpr int kSysPer = 16;                            // particles per thread: 
 constexpr int kSysParticles = kSysThreads * kSysPer;   // 2048 particles per ancestor CTA
 
 
+template <class XT>  // XT: the element type behind `logw` — double (log-weights, or binary64 states when from_x) or float (binary32 states, from_x only)
 __global__ void __launch_bounds__(kSumThreads, kSumCtasPerSm)
-    sum_kernel(const double* __restrict__ logw, unsigned long long* __restrict__ cl, int64_t N, int S, FilterCtrl* ctrl,
+    sum_kernel(const XT* __restrict__ logw, unsigned long long* __restrict__ cl, int64_t N, int S, FilterCtrl* ctrl,
                StepIndex ix, double* psum, double* psum2, StepStats* stats_out, int slot, int resampler, uint64_t Rw,
                RngKey key, uint32_t stream, uint32_t t, int from_x, Derived dv, double ycur) {
   // from_x: `logw` points at the LG1D states x and the log-weight logpdf(observation(x), ycur) is
@@ -511,26 +527,38 @@ __global__ void __launch_bounds__(kSumThreads, kSumCtasPerSm)
       running += __shfl_sync(kFullMask, winc, 31);
     };
     // software pipeline: the next chunk's log-weights are in flight while this one is quantised
-    const double2* src = reinterpret_cast<const double2*>(logw + tile0 + lane * 4);  // chunk c: src[c * 64], src[c * 64 + 1]
-    double2 na = make_double2(0.0, 0.0), nb = na;
-    if (nfull > 0) {
-      na = __ldcs(src);
-      nb = __ldcs(src + 1);
-    }
-#pragma unroll 1
-    for (int c = 0; c < nfull; ++c) {
-      double lw[4] = {na.x, na.y, nb.x, nb.y};
-      if (c + 1 < nfull) {
-        na = __ldcs(src + (c + 1) * (kChunk / 2));
-        nb = __ldcs(src + (c + 1) * (kChunk / 2) + 1);
+    if (sizeof(XT) == 8) {
+      const double2* src = reinterpret_cast<const double2*>(logw + tile0 + lane * 4);  // chunk c: src[c * 64], src[c * 64 + 1]
+      double2 na = make_double2(0.0, 0.0), nb = na;
+      if (nfull > 0) {
+        na = __ldcs(src);
+        nb = __ldcs(src + 1);
       }
-      process(std::true_type{}, c, lw);
+#pragma unroll 1
+      for (int c = 0; c < nfull; ++c) {
+        double lw[4] = {na.x, na.y, nb.x, nb.y};
+        if (c + 1 < nfull) {
+          na = __ldcs(src + (c + 1) * (kChunk / 2));
+          nb = __ldcs(src + (c + 1) * (kChunk / 2) + 1);
+        }
+        process(std::true_type{}, c, lw);
+      }
+    } else {  // binary32 states: one 16-byte load per lane and chunk
+      const float4* src = reinterpret_cast<const float4*>(logw + tile0 + lane * 4);  // chunk c: src[c * 32]
+      float4 nf = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (nfull > 0) nf = __ldcs(src);
+#pragma unroll 1
+      for (int c = 0; c < nfull; ++c) {
+        double lw[4] = {(double)nf.x, (double)nf.y, (double)nf.z, (double)nf.w};
+        if (c + 1 < nfull) nf = __ldcs(src + (c + 1) * (kChunk / 4));
+        process(std::true_type{}, c, lw);
+      }
     }
     if (nfull < nch) {  // the partial chunk at the end of the array
       const int64_t base = tile0 + (int64_t)nfull * kChunk + lane * 4;
       double lw[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) lw[k] = (base + k < N) ? logw[base + k] : -INFINITY;
+      for (int k = 0; k < 4; ++k) lw[k] = (base + k < N) ? (double)logw[base + k] : -INFINITY;
       process(std::false_type{}, nfull, lw);
     }
     se = warp_sum(se);
@@ -991,10 +1019,10 @@ __global__ void __launch_bounds__(kSysThreads, 12)
 // chains; parents gathered through the (sorted, hence near-coalesced) ancestor vector.
 constexpr int kMoveThreads = 256;
 constexpr int kMovePairs = 2;
-template <class Model, bool FULL>
+template <class Model, bool FULL, class XT>
 __device__ __forceinline__ double move_particles(const Model& mdl, double y, int N, int64_t ld, const RngKey& key, uint32_t stream, uint32_t t,
-                                                 int i0, const int32_t* __restrict__ anc, const double* __restrict__ xprev,
-                                                 double* __restrict__ xnew, double* __restrict__ logw /* null: not stored */) {
+                                                 int i0, const int32_t* __restrict__ anc, const XT* __restrict__ xprev,
+                                                 XT* __restrict__ xnew, double* __restrict__ logw /* null: not stored */) {
   constexpr int D = Model::D;
   constexpr int PER = 2 * kMovePairs;
   int a[PER];
@@ -1011,7 +1039,7 @@ __device__ __forceinline__ double move_particles(const Model& mdl, double y, int
   double xp[PER][D];
   if (D == 1) {  // all parents requested before the first normal is drawn
 #pragma unroll
-    for (int k = 0; k < PER; ++k) xp[k][0] = __ldg(&xprev[a[k]]);
+    for (int k = 0; k < PER; ++k) xp[k][0] = (double)__ldg(&xprev[a[k]]);
   }
   double vmax = -INFINITY;
 #pragma unroll
@@ -1021,8 +1049,8 @@ __device__ __forceinline__ double move_particles(const Model& mdl, double y, int
     if (D > 1) {
 #pragma unroll
       for (int c = 0; c < D; ++c) {
-        xp[2 * r][c] = __ldg(&xprev[c * ld + a[2 * r]]);
-        xp[2 * r + 1][c] = __ldg(&xprev[c * ld + a[2 * r + 1]]);
+        xp[2 * r][c] = (double)__ldg(&xprev[c * ld + a[2 * r]]);
+        xp[2 * r + 1][c] = (double)__ldg(&xprev[c * ld + a[2 * r + 1]]);
       }
     }
     double za[D], zb[D], xa[D], xb[D];
@@ -1030,17 +1058,19 @@ __device__ __forceinline__ double move_particles(const Model& mdl, double y, int
     for (int c = 0; c < D; ++c) normal_pair_at(key, (uint32_t)(i >> 1), stream, t, PURPOSE_TRANSITION, (uint32_t)c, za[c], zb[c]);
     mdl.transition(za, xp[2 * r], xa);
     mdl.transition(zb, xp[2 * r + 1], xb);
+    round_state<XT>(xa);
+    round_state<XT>(xb);
     const double la = mdl.logweight(xa, y);
     const double lb = mdl.logweight(xb, y);
     if (FULL || i + 1 < N) {
 #pragma unroll
-      for (int c = 0; c < D; ++c) *reinterpret_cast<double2*>(xnew + c * ld + i) = make_double2(xa[c], xb[c]);
+      for (int c = 0; c < D; ++c) *reinterpret_cast<typename XVec2<XT>::type*>(xnew + c * ld + i) = XVec2<XT>::make(xa[c], xb[c]);
       if (logw) *reinterpret_cast<double2*>(logw + i) = make_double2(la, lb);
       if (la > vmax) vmax = la;  // `>` ignores NaN like the CPU loop
       if (lb > vmax) vmax = lb;
     } else {
 #pragma unroll
-      for (int c = 0; c < D; ++c) xnew[c * ld + i] = xa[c];
+      for (int c = 0; c < D; ++c) xnew[c * ld + i] = (XT)xa[c];
       if (logw) logw[i] = la;
       if (la > vmax) vmax = la;
     }
@@ -1048,10 +1078,10 @@ __device__ __forceinline__ double move_particles(const Model& mdl, double y, int
   return vmax;
 }
 
-template <class Model>
+template <class Model, class XT>
 __global__ void __launch_bounds__(kMoveThreads, (Model::D == 1) ? 6 : 3)
     move_kernel(Derived dv, double y, int N, int64_t ld, RngKey key, uint32_t stream, uint32_t t, const int32_t* __restrict__ anc,
-                const double* __restrict__ xprev, double* __restrict__ xnew, double* __restrict__ logw, FilterCtrl* ctrl) {
+                const XT* __restrict__ xprev, XT* __restrict__ xnew, double* __restrict__ logw, FilterCtrl* ctrl) {
   constexpr int PER = 2 * kMovePairs;
   constexpr int NW = kMoveThreads / 32;
   __shared__ unsigned long long s_max[NW];
@@ -1063,9 +1093,9 @@ __global__ void __launch_bounds__(kMoveThreads, (Model::D == 1) ? 6 : 3)
   pdl_wait();  // the ancestors come from anc_hist_kernel
   double vmax;
   if ((int64_t)(blockIdx.x + 1) * (kMoveThreads * PER) <= (int64_t)N)
-    vmax = move_particles<Model, true>(mdl, y, N, ld, key, stream, t, i0, anc, xprev, xnew, logw);
+    vmax = move_particles<Model, true, XT>(mdl, y, N, ld, key, stream, t, i0, anc, xprev, xnew, logw);
   else
-    vmax = move_particles<Model, false>(mdl, y, N, ld, key, stream, t, i0, anc, xprev, xnew, logw);
+    vmax = move_particles<Model, false, XT>(mdl, y, N, ld, key, stream, t, i0, anc, xprev, xnew, logw);
   // exact max(logw) for the next normalize(): ordered encoding, REDUX per warp, one atomic per CTA
   const unsigned long long wm = warp_max_ordered(encode_ordered(vmax));
   if ((tid & 31) == 0) s_max[tid >> 5] = wm;
@@ -1079,11 +1109,20 @@ __global__ void __launch_bounds__(kMoveThreads, (Model::D == 1) ? 6 : 3)
 }
 
 // logw_i = logpdf(observation(x_i), y): materialises the log-weights that the LG1D step does not store
-__global__ void logw_kernel(Derived dv, double y, int64_t N, const double* __restrict__ x, double* __restrict__ logw) {
+template <class XT>
+__global__ void logw_kernel(Derived dv, double y, int64_t N, const XT* __restrict__ x, double* __restrict__ logw) {
   ModelLG1D mdl;
   mdl.load(dv.d);
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < N) logw[i] = mdl.logweight(&x[i], y);
+  if (i < N) {
+    const double xi = (double)x[i];
+    logw[i] = mdl.logweight(&xi, y);
+  }
+}
+// binary32 states -> binary64 for the host-facing fetch
+__global__ void widen_kernel(const float* __restrict__ src, double* __restrict__ dst, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = (double)src[i];
 }
 
 // w_i = exp(logw_i - max) / Σe   (normalize, particles.jl:11) — only when the caller fetches w
@@ -1108,14 +1147,15 @@ __device__ __forceinline__ unsigned long long q_of(const unsigned long long* __r
 }
 
 // mode 0: part[b] = Σ q x ; mode 1: part[b] = Σ q (x - mean)^2   (per-block partials, fixed order)
+template <class XT>
 __global__ void __launch_bounds__(kSumThreadsW)
-    wmoment_kernel(const double* __restrict__ x, const unsigned long long* __restrict__ cl, int64_t N, int tile_items, int weighted,
+    wmoment_kernel(const XT* __restrict__ x, const unsigned long long* __restrict__ cl, int64_t N, int tile_items, int weighted,
                    int mode, double mean, double* __restrict__ part) {
   __shared__ double sh[kSumThreadsW / 32];
   double acc = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * kSumThreadsW + threadIdx.x; i < N; i += (int64_t)gridDim.x * kSumThreadsW) {
     const double qd = (double)q_of(cl, i, tile_items, weighted != 0);
-    const double v = x[i];
+    const double v = (double)x[i];
     if (qd != 0.0) acc += mode == 0 ? qd * v : qd * ((v - mean) * (v - mean));  // q = 0: an infinite state must not poison the sum
   }
   acc = warp_sum(acc);
@@ -1130,8 +1170,9 @@ __global__ void __launch_bounds__(kSumThreadsW)
 
 // one radix-select pass (8 bits, most significant first) for np probabilities at once:
 // hist[j][digit] += q_i for the particles whose key agrees with prefix[j] in the digits already fixed
+template <class XT>
 __global__ void __launch_bounds__(kSumThreadsW)
-    rsel_hist_kernel(const double* __restrict__ x, const unsigned long long* __restrict__ cl, int64_t N, int tile_items, int weighted,
+    rsel_hist_kernel(const XT* __restrict__ x, const unsigned long long* __restrict__ cl, int64_t N, int tile_items, int weighted,
                      int pass, int np, const unsigned long long* __restrict__ prefix, unsigned long long* __restrict__ hist) {
   __shared__ unsigned long long s_hist[kMaxProbs * 256];
   __shared__ unsigned long long s_prefix[kMaxProbs];
@@ -1142,7 +1183,7 @@ __global__ void __launch_bounds__(kSumThreadsW)
   for (int64_t i = (int64_t)blockIdx.x * kSumThreadsW + threadIdx.x; i < N; i += (int64_t)gridDim.x * kSumThreadsW) {
     const unsigned long long q = q_of(cl, i, tile_items, weighted != 0);
     if (q == 0ull) continue;
-    const unsigned long long key = encode_ordered(x[i]);
+    const unsigned long long key = encode_ordered((double)x[i]);
     const unsigned digit = (unsigned)(key >> shift) & 255u;
     for (int j = 0; j < np; ++j) {
       const bool match = (pass == 0) || ((key ^ s_prefix[j]) >> (shift + 8)) == 0ull;
@@ -1202,6 +1243,12 @@ __global__ void ancestor_kernel(const uint64_t* __restrict__ cdf, int64_t N, int
   anc[i] = lower_count(cdf, (int64_t)0, N - 1, tau);
 }
 
+// state storage type of the live filter (SPEC §9)
+template <class F>
+static void dispatch_xt(int prec, F&& f) {
+  if (prec) f(float{});
+  else f(double{});
+}
 template <class F>
 void dispatch_model(int kind, F&& f) {
   switch (kind) {
@@ -1320,7 +1367,10 @@ void SingleFilter::timing(double ms[TK_COUNT], int64_t launches[TK_COUNT]) const
 
 void SingleFilter::ensure_logw() {
   if (logw_valid_ || !live()) return;
-  logw_kernel<<<(unsigned)((N_ + 255) / 256), 256, 0, stream_>>>(dv_w_, y_cur_, N_, x_[cur_], logw_[cur_]);
+  dispatch_xt(prec_, [&](auto tag) {
+    using XT = decltype(tag);
+    logw_kernel<XT><<<(unsigned)((N_ + 255) / 256), 256, 0, stream_>>>(dv_w_, y_cur_, N_, reinterpret_cast<const XT*>(x_[cur_]), logw_[cur_]);
+  });
   SMCB_CUDA_TRY(cudaGetLastError());
   logw_valid_ = true;
 }
@@ -1336,7 +1386,10 @@ void SingleFilter::launch_init(double y0) {
   mark(TK_INIT, true);
   dispatch_model(kind_, [&](auto m) {
     using M = decltype(m);
-    init_kernel<M><<<grid, 256, 0, stream_>>>(dv_, y0, N_, ld_, key_, stream_id_, x_[cur_], logw_[cur_], ctrl_);
+    dispatch_xt(prec_, [&](auto tag) {
+      using XT = decltype(tag);
+      init_kernel<M, XT><<<grid, 256, 0, stream_>>>(dv_, y0, N_, ld_, key_, stream_id_, reinterpret_cast<XT*>(x_[cur_]), logw_[cur_], ctrl_);
+    });
   });
   mark(TK_INIT, false);
   SMCB_CUDA_TRY(cudaGetLastError());
@@ -1418,9 +1471,14 @@ void SingleFilter::launch_sum(int64_t stat_index) {
   const uint32_t t = t_ + 1;
   mark(TK_SCAN, true);
   const int from_x = logw_valid_ ? 0 : 1;  // the previous LG1D step kept its log-weights implicit in x
-  SMCB_CUDA_TRY(launch_pdl(sum_kernel, dim3((ix.ntiles + kSumWarps - 1) / kSumWarps), dim3(kSumThreads), stream_,
-                           from_x ? (const double*)x_[cur_] : (const double*)logw_[cur_], cl, N_, S_, ctrl_, ix, psum_, psum2_,
-                           stats_dev_ + stat_index, (int)(t_ & 1u), (int)RESAMPLE_SYSTEMATIC, R_, key_, stream_id_, t, from_x, dv_w_, y_cur_));
+  if (from_x && prec_)
+    SMCB_CUDA_TRY(launch_pdl(sum_kernel<float>, dim3((ix.ntiles + kSumWarps - 1) / kSumWarps), dim3(kSumThreads), stream_,
+                             reinterpret_cast<const float*>(x_[cur_]), cl, N_, S_, ctrl_, ix, psum_, psum2_, stats_dev_ + stat_index, (int)(t_ & 1u),
+                             (int)RESAMPLE_SYSTEMATIC, R_, key_, stream_id_, t, from_x, dv_w_, y_cur_));
+  else
+    SMCB_CUDA_TRY(launch_pdl(sum_kernel<double>, dim3((ix.ntiles + kSumWarps - 1) / kSumWarps), dim3(kSumThreads), stream_,
+                             from_x ? (const double*)x_[cur_] : (const double*)logw_[cur_], cl, N_, S_, ctrl_, ix, psum_, psum2_,
+                             stats_dev_ + stat_index, (int)(t_ & 1u), (int)RESAMPLE_SYSTEMATIC, R_, key_, stream_id_, t, from_x, dv_w_, y_cur_));
   mark(TK_SCAN, false);
   SMCB_CUDA_TRY(cudaGetLastError());
   sum_done_ = true;
@@ -1467,8 +1525,12 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler) {
   mark(TK_PROP, true);
   dispatch_model(kind_, [&](auto m) {
     using M = decltype(m);
-    SMCB_CUDA_TRY(launch_pdl(move_kernel<M>, dim3(mblocks), dim3(kMoveThreads), stream_, dv_, y, (int)N_, ld_, key_, stream_id_, t, anc, x_[cur_],
-                             x_[cur_ ^ 1], implicit_logw ? (double*)nullptr : logw_[cur_ ^ 1], ctrl_));
+    dispatch_xt(prec_, [&](auto tag) {
+      using XT = decltype(tag);
+      SMCB_CUDA_TRY(launch_pdl(move_kernel<M, XT>, dim3(mblocks), dim3(kMoveThreads), stream_, dv_, y, (int)N_, ld_, key_, stream_id_, t, anc,
+                               reinterpret_cast<const XT*>(x_[cur_]), reinterpret_cast<XT*>(x_[cur_ ^ 1]),
+                               implicit_logw ? (double*)nullptr : logw_[cur_ ^ 1], ctrl_));
+    });
   });
   mark(TK_PROP, false);
   SMCB_CUDA_TRY(cudaGetLastError());
@@ -1497,7 +1559,7 @@ void SingleFilter::init(int kind, const double* params, int64_t N, double y0, co
     SMCB_CUDA_TRY(cudaMalloc(&stats_dev_, sizeof(StepStats) * 2));
     cap_stats_ = 2;
   }
-  kind_ = kind; d_ = state_dim(kind); N_ = N; ld_ = cap_N_;
+  kind_ = kind; d_ = state_dim(kind); N_ = N; ld_ = cap_N_; prec_ = next_prec_;
   S_ = quant_shift((uint64_t)N); R_ = strata_width((uint64_t)N);
   key_ = key; stream_id_ = stream_id; t_ = 0; cur_ = 0; anc_rows_ = 0;
   derive_params(kind, params, dv_.d);
@@ -1512,6 +1574,7 @@ void SingleFilter::init(int kind, const double* params, int64_t N, double y0, co
 void SingleFilter::step(const double* params, double y, int resampler, StepStats* st) {
   if (!live()) throw Error{SMCB_ERR_STATE, "bootstrap_step before bootstrap_init / log_likelihood"};
   check_args(kind_, N_, resampler);
+  if (prec_ && resampler == RESAMPLE_MULTINOMIAL) throw Error{SMCB_ERR_BAD_ARG, "binary32 states: sorted resamplers only (docs/SPEC.md §9)"};
   SMCB_CUDA_TRY(cudaSetDevice(device_));
   if (params) derive_params(kind_, params, dv_.d);
   if (!record_anc_) anc_rows_ = 0;
@@ -1527,6 +1590,7 @@ void SingleFilter::step(const double* params, double y, int resampler, StepStats
 void SingleFilter::run(int kind, const double* params, int64_t N, const double* y, int64_t T, int resampler,
                        const RngKey& key, uint32_t stream_id, StepStats* stats_out) {
   check_args(kind, N, resampler);
+  if (next_prec_ && resampler == RESAMPLE_MULTINOMIAL) throw Error{SMCB_ERR_BAD_ARG, "binary32 states: sorted resamplers only (docs/SPEC.md §9)"};
   if (T < 1) throw Error{SMCB_ERR_BAD_ARG, "T must be >= 1"};
   SMCB_CUDA_TRY(cudaSetDevice(device_));
   N_ = 0;
@@ -1536,7 +1600,7 @@ void SingleFilter::run(int kind, const double* params, int64_t N, const double* 
     SMCB_CUDA_TRY(cudaMalloc(&stats_dev_, sizeof(StepStats) * T));
     cap_stats_ = T;
   }
-  kind_ = kind; d_ = state_dim(kind); N_ = N; ld_ = cap_N_;
+  kind_ = kind; d_ = state_dim(kind); N_ = N; ld_ = cap_N_; prec_ = next_prec_;
   S_ = quant_shift((uint64_t)N); R_ = strata_width((uint64_t)N);
   key_ = key; stream_id_ = stream_id; t_ = 0; cur_ = 0; anc_rows_ = 0;
   derive_params(kind, params, dv_.d);
@@ -1593,10 +1657,12 @@ void SingleFilter::summary(const double* probs, int np, bool weighted, double* m
   std::vector<double> hpart((size_t)nblk);
   for (int c = 0; c < d_; ++c) {
     const double* xc = x_[cur_] + (int64_t)c * ld_;
+    const float* xcf = reinterpret_cast<const float*>(x_[cur_]) + (int64_t)c * ld_;
     double mean = NAN, var = NAN;
     if (Q != 0 && (mean_out || var_out)) {
       for (int mode = 0; mode < (var_out ? 2 : 1); ++mode) {
-        wmoment_kernel<<<nblk, kSumThreadsW, 0, stream_>>>(xc, cl, N_, ix.tile_items, weighted ? 1 : 0, mode, mean, part);
+        if (prec_) wmoment_kernel<float><<<nblk, kSumThreadsW, 0, stream_>>>(xcf, cl, N_, ix.tile_items, weighted ? 1 : 0, mode, mean, part);
+        else wmoment_kernel<double><<<nblk, kSumThreadsW, 0, stream_>>>(xc, cl, N_, ix.tile_items, weighted ? 1 : 0, mode, mean, part);
         SMCB_CUDA_TRY(cudaGetLastError());
         SMCB_CUDA_TRY(cudaMemcpyAsync(hpart.data(), part, sizeof(double) * nblk, cudaMemcpyDeviceToHost, stream_));
         SMCB_CUDA_TRY(cudaStreamSynchronize(stream_));
@@ -1622,7 +1688,8 @@ void SingleFilter::summary(const double* probs, int np, bool weighted, double* m
       SMCB_CUDA_TRY(cudaMemcpyAsync(prefix, hp, sizeof(unsigned long long) * np, cudaMemcpyHostToDevice, stream_));
       SMCB_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(unsigned long long) * kMaxProbs * 256, stream_));
       for (int pass = 0; pass < 8; ++pass) {
-        rsel_hist_kernel<<<nblk, kSumThreadsW, 0, stream_>>>(xc, cl, N_, ix.tile_items, weighted ? 1 : 0, pass, np, prefix, hist);
+        if (prec_) rsel_hist_kernel<float><<<nblk, kSumThreadsW, 0, stream_>>>(xcf, cl, N_, ix.tile_items, weighted ? 1 : 0, pass, np, prefix, hist);
+        else rsel_hist_kernel<double><<<nblk, kSumThreadsW, 0, stream_>>>(xc, cl, N_, ix.tile_items, weighted ? 1 : 0, pass, np, prefix, hist);
         rsel_pick_kernel<<<1, 256, 0, stream_>>>(pass, np, prefix, rank, hist);
       }
       SMCB_CUDA_TRY(cudaGetLastError());
@@ -1642,9 +1709,17 @@ void SingleFilter::summary(const double* probs, int np, bool weighted, double* m
 void SingleFilter::fetch(double* x_host, double* w_host, double* logw_host) {
   if (!live()) throw Error{SMCB_ERR_STATE, "no filter state to fetch"};
   SMCB_CUDA_TRY(cudaSetDevice(device_));
-  if (x_host)
+  if (x_host && !prec_)
     SMCB_CUDA_TRY(cudaMemcpy2DAsync(x_host, sizeof(double) * N_, x_[cur_], sizeof(double) * ld_, sizeof(double) * N_,
                                     d_, cudaMemcpyDeviceToHost, stream_));
+  if (x_host && prec_) {  // binary32 states are widened on the device: the host-facing layout stays [d][N] doubles
+    if (!w_tmp_) SMCB_CUDA_TRY(cudaMalloc(&w_tmp_, sizeof(double) * cap_N_));
+    for (int c = 0; c < d_; ++c) {
+      widen_kernel<<<(unsigned)((N_ + 255) / 256), 256, 0, stream_>>>(reinterpret_cast<const float*>(x_[cur_]) + (int64_t)c * ld_, w_tmp_, N_);
+      SMCB_CUDA_TRY(cudaGetLastError());
+      SMCB_CUDA_TRY(cudaMemcpyAsync(x_host + (int64_t)c * N_, w_tmp_, sizeof(double) * N_, cudaMemcpyDeviceToHost, stream_));
+    }
+  }
   if (logw_host || w_host) ensure_logw();
   if (logw_host)
     SMCB_CUDA_TRY(cudaMemcpyAsync(logw_host, logw_[cur_], sizeof(double) * N_, cudaMemcpyDeviceToHost, stream_));

@@ -68,6 +68,9 @@ class SingleFilter {
 
   void set_record_ancestors(bool on) { record_anc_ = on; }
   void set_profiling(bool on) { profiling_ = on; }
+  // SPEC §9: 0 = binary64 states, 1 = binary32 states (takes effect at the next init / run)
+  void set_precision(int p) { next_prec_ = p ? 1 : 0; }
+  int precision() const { return prec_; }
   void timing(double ms[TK_COUNT], int64_t launches[TK_COUNT]) const;
 
   int64_t N() const { return N_; }
@@ -125,6 +128,7 @@ class SingleFilter {
   int32_t* bound_arrays_ = nullptr;            // [2][bound_cap_]: ancestor of each propagate CTA's first particle, its tile
   int64_t bound_cap_ = 0;
   int num_sms_ = 0;
+  int prec_ = 0, next_prec_ = 0;  // state storage: 0 double, 1 float (the x_ allocations are sized for double either way)
   double anc_eps_ = 1e-9;  // anc_hist_kernel: quotient estimates closer than this to an integer are decided exactly (test hook: SMCB_ANC_FORCE_EXACT)
   bool sum_done_ = false;   // sum_kernel already ran for the current weights (statistics read by a stepping caller)
   bool logw_valid_ = true;  // logw_[cur_] holds the current log-weights (false: implicit in x_[cur_] and y_cur_)

@@ -333,3 +333,58 @@ def test_systematic_exact_decision_path(oracle, monkeypatch):
             assert np.array_equal(x, ref["x"]), (N, R)
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("kind", [smc.KIND_LG1D, smc.KIND_SV, smc.KIND_UCSV])
+def test_f32_state_tier(ctx, oracle, kind):
+    """docs/SPEC.md §9: binary32 states, binary64 arithmetic.  Bit-exact against the oracle run in the same
+    tier (ancestors, states, log-weights), every state representable in binary32, and logZ within the north
+    star's fp32 tolerance (rel 1e-4) of the binary64 tier."""
+    T = 16
+    y = _data(oracle, kind, T)
+    ctx.set_precision("f32")
+    try:
+        for N, resampler in ((1024, smc.SYSTEMATIC), (5001, smc.STRATIFIED), (70001, smc.SYSTEMATIC)):
+            with oracle.state_f32():
+                ref = oracle.log_likelihood(kind, MODELS[kind], N, y, resampler, 13, 2, 1, want_anc=True)
+            ref64 = oracle.log_likelihood(kind, MODELS[kind], N, y, resampler, 13, 2, 1)
+            ctx.set_rng(13, 2)
+            ctx.record_ancestors(True)
+            logZ, logmu, ess = ctx.log_likelihood(kind, MODELS[kind], N, y, resampler, 1, per_step=True)
+            anc = ctx.fetch_ancestors(T - 1)
+            x, w, logw = ctx.fetch_state(want_logw=True)
+            ctx.record_ancestors(False)
+            np.testing.assert_array_equal(anc, ref["anc"][1:])
+            np.testing.assert_array_equal(x, ref["x"])
+            np.testing.assert_array_equal(logw, ref["logw"])
+            assert np.array_equal(x, x.astype(np.float32).astype(np.float64))
+            np.testing.assert_allclose(logmu, ref["logmu"], rtol=RTOL, atol=0)
+            np.testing.assert_allclose(ess, ref["ess"], rtol=RTOL, atol=0)
+            assert abs(logZ - ref["logZ"]) <= RTOL * abs(ref["logZ"])
+            # fp32 tier against the fp64 tier.  Before the first resampling the difference is pure rounding; later
+            # the two runs share ancestors only until the first threshold that falls between the two CDFs, after
+            # which they are two estimates of the same Z (Monte-Carlo error, not rounding error).
+            assert abs(logmu[0] - ref64["logmu"][0]) <= 1e-6 * abs(ref64["logmu"][0])
+            tol = 1e-4 if kind == smc.KIND_LG1D else 5e-3
+            assert abs(logZ - ref64["logZ"]) <= tol * abs(ref64["logZ"])
+            assert not np.array_equal(x, ref64["x"])                            # (it IS a different tier)
+            # on-device summaries read the binary32 states
+            m, v, q = ctx.summary([0.1, 0.5, 0.9])
+            mo, vo, qo = oracle.weighted_summary(ref["x"], ref["logw"], [0.1, 0.5, 0.9])
+            np.testing.assert_allclose(m, mo, rtol=RTOL)
+            np.testing.assert_array_equal(q, qo)
+        # stepping API in the same tier
+        ctx.set_rng(13, 2)
+        ctx.bootstrap_init(kind, MODELS[kind], 70001, y[0], stream=1)
+        for t in range(1, T):
+            ctx.bootstrap_step(y[t], smc.SYSTEMATIC)
+        xs, _, _ = ctx.fetch_state(want_w=False)
+        np.testing.assert_array_equal(xs, ref["x"])
+        with pytest.raises(smc.SMCBError):
+            ctx.bootstrap_step(y[1], smc.MULTINOMIAL)
+        with pytest.raises(smc.SMCBError):
+            ctx.log_likelihood(kind, MODELS[kind], 1024, y, smc.MULTINOMIAL)
+    finally:
+        ctx.set_precision("f64")
+    # and the binary64 tier is untouched afterwards
+    _compare_run(ctx, oracle, kind, 1001, 6, smc.SYSTEMATIC)

@@ -195,3 +195,25 @@ def test_weighted_summary_restatement(oracle):
     _, _, q = oracle.weighted_summary(z, None, [0.5, 0.25], weighted=False)
     s = np.sort(z[0])
     assert q[0, 0] == s[500] and q[0, 1] == s[250]
+
+
+def test_state_f32_tier_restatement():
+    """docs/SPEC.md §9: the binary32-state tier is the binary64 filter with ONE extra rounding of every drawn
+    state; it is a process-global switch of the C oracle that must not leak."""
+    from oracle import oracle as o
+    P = [0.5, 1.0, 0.9, 0.8, 0.0, 1.0]
+    _, y = o.simulate(0, P, 30, 1998)
+    r64 = o.log_likelihood(0, P, 2048, y, 2, 7, 0, 0, want_anc=True)
+    with o.state_f32():
+        r32 = o.log_likelihood(0, P, 2048, y, 2, 7, 0, 0, want_anc=True)
+        # one step restated by hand from the binary64 pieces: round the init draw, weight the rounded state
+        x0, lw0 = o.bootstrap_init(0, P, 64, y[0], 7)
+    x0_64, _ = o.bootstrap_init(0, P, 64, y[0], 7)
+    np.testing.assert_array_equal(x0, x0_64.astype(np.float32).astype(np.float64))
+    v = (y[0] - 1.0 * x0[0]) * (1.0 / np.sqrt(0.8))
+    np.testing.assert_allclose(lw0, -0.5 * v * v - (np.log(np.sqrt(0.8)) + 0.5 * np.log(2 * np.pi)), rtol=1e-13)
+    assert np.array_equal(r32["x"], r32["x"].astype(np.float32).astype(np.float64))
+    assert not np.array_equal(r32["x"], r64["x"])
+    assert abs(r32["logZ"] - r64["logZ"]) <= 1e-4 * abs(r64["logZ"])
+    again = o.log_likelihood(0, P, 2048, y, 2, 7, 0, 0)
+    assert again["logZ"] == r64["logZ"]                      # the switch did not leak

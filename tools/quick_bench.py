@@ -31,6 +31,23 @@ for logn in ([20, 22, 24] if len(sys.argv) < 2 else [int(a) for a in sys.argv[1:
                    init_us=1e3 * msp["init"] / max(npf["init"], 1), logZ=z)
         print(json.dumps(rec), flush=True)
         out.append(rec)
+# the binary32-state tier (docs/SPEC.md §9), systematic only; roofline figure at SURVEY §8d's 40 B per particle-update
+ctx.set_precision("f32")
+for logn in ([20, 22, 24] if len(sys.argv) < 2 else [int(a) for a in sys.argv[1:]]):
+    N, T = 1 << logn, 60
+    y = rng.normal(size=T)
+    ctx.log_likelihood(smc.KIND_LG1D, LG, N, y[:5], smc.SYSTEMATIC)
+    z = ctx.log_likelihood(smc.KIND_LG1D, LG, N, y, smc.SYSTEMATIC)
+    ms, n = ctx.timing()
+    ctx.set_profiling(True)
+    ctx.log_likelihood(smc.KIND_LG1D, LG, N, y, smc.SYSTEMATIC)
+    msp, npf = ctx.timing()
+    ctx.set_profiling(False)
+    pups = N * T / (ms["total"] * 1e-3)
+    print(json.dumps(dict(N=N, T=T, precision="f32 states", resampler="systematic", total_ms=ms["total"], gpups=pups / 1e9,
+                          frac40=pups * 40 / 6551.4e9, **{k + "_us": 1e3 * msp[k] / max(npf[k], 1) for k in ("scan", "bounds", "anc", "prop", "init")},
+                          logZ=z)), flush=True)
+ctx.set_precision("f64")
 # batched: config 3 shape (512 x 1024, T=100), config 4 (1024 x 2048 SV, T=500), config 5 per-GPU (512 x 4096 UCSV, T=241)
 for kind, M, N, T, P in ((smc.KIND_LG1D, 512, 1024, 100, LG), (smc.KIND_SV, 1024, 2048, 500, [-1.0, 0.9, 0.3]),
                          (smc.KIND_UCSV, 512, 4096, 241, [0.2, 0.2, 3.0, 1.0, 1.0]), (smc.KIND_LG1D, 4096, 1024, 100, LG)):
