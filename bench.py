@@ -172,6 +172,7 @@ def main():
     ap.add_argument("--T", type=int, default=1000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-smc2", action="store_true", help="skip the θ-sharded SMC² leg")
+    ap.add_argument("--no-f32", action="store_true", help="skip the binary32-state tier leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -281,6 +282,23 @@ def main():
                                     for k in KERNEL_BYTES}},
         "clocks": clocks,
     }
+    if rank == 0 and world == 1 and not args.no_f32:
+        # the binary32-state tier of the same workload (docs/SPEC.md §9): two sweeps, device time; SURVEY §8d counts
+        # 40 algorithmic B per particle-update for it
+        try:
+            ctx.set_precision("f32")
+            ctx.log_likelihood(smc.KIND_LG1D, LG_PARAMS, N, y, rs, stream=rank)
+            ms32 = 0.0
+            for _ in range(2):
+                ctx.log_likelihood(smc.KIND_LG1D, LG_PARAMS, N, y, rs, stream=rank)
+                ms32 += ctx.timing()[0]["total"]
+            v32 = 2 * N * T / (ms32 * 1e-3)
+            line["f32_states"] = {"value": v32, "unit": "particle-updates/s", "ms_per_step": ms32 / 2, "dtype": "f32 states, f64 arithmetic",
+                                  "algorithmic_bytes_per_update": 40, "roofline_frac": v32 * 40 / (peak * 1e9)}
+        except Exception as e:
+            line["f32_states"] = {"error": repr(e)}
+        finally:
+            ctx.set_precision("f64")
     if rank == 0 and world == 1 and not args.no_cpu:
         v, sample = cpu_sample(2, 20, 64)
         line["cpu_baseline"] = {"value": v, "unit": "particle-updates/s", "cores": 1, "kind": "port", "sample": sample}

@@ -38,6 +38,10 @@ const DEFAULT = Ref{Union{Nothing,Context}}(nothing)
 context() = (DEFAULT[] === nothing && (DEFAULT[] = Context()); DEFAULT[])
 check(ctx, rc) = rc == 0 || error(unsafe_string(ccall((:smcb_last_error, LIB), Cstring, (Ptr{Cvoid},), ctx.h)))
 set_rng!(ctx, seed, epoch) = (ctx.seed = seed; check(ctx, ccall((:smcb_set_rng, LIB), Cint, (Ptr{Cvoid}, UInt64, UInt32), ctx.h, seed, epoch)))
+# state storage of the single filter from the next bootstrap_filter / log_likelihood on: Float64 (default) or Float32
+# (docs/SPEC.md §9: states rounded to binary32 where stored, arithmetic Float64, sorted resamplers only)
+set_precision!(ctx, ::Type{Float64}) = check(ctx, ccall((:smcb_set_precision, LIB), Cint, (Ptr{Cvoid}, Cint), ctx.h, 0))
+set_precision!(ctx, ::Type{Float32}) = check(ctx, ccall((:smcb_set_precision, LIB), Cint, (Ptr{Cvoid}, Cint), ctx.h, 1))
 
 # ---------------------------------------------------------------- models (state_space_models.jl)
 abstract type StateSpaceModel end
