@@ -147,6 +147,10 @@ int smcb_batch_fetch(smcb_batch* b, double* x, double* w, double* logw);
 /* mean [M][d]: the weighted state mean w[m]' * x[m] of every θ-particle's cloud, computed on the device — what
  * estimated_trend(smc) and quantile(smc, p) integrate over θ (plotting_utils.jl:116-124,140-157) */
 int smcb_batch_weighted_mean(smcb_batch* b, double* mean);
+/* quantiles [M][d][nprobs] (nprobs <= 16): the lower empirical quantiles of every θ-particle's cloud under its own
+ * weights (weighted != 0) or counting every particle once, computed on the device (docs/SPEC.md §8) — the per-θ
+ * bands of get_quantiles_uc / get_quantiles_ucsv, examples/inflation_example.jl:39-55,241-253 */
+int smcb_batch_weighted_quantiles(smcb_batch* b, const double* probs, int nprobs, int weighted, double* quantiles);
 /* cross-GPU moves of whole clouds (θ-resample across ranks): pack slot m into / unpack from a
  * device buffer of smcb_batch_cloud_bytes(b) bytes that the caller sends with NCCL / P2P */
 int64_t smcb_batch_cloud_bytes(const smcb_batch* b);

@@ -187,6 +187,14 @@ x(smc::SMC) = (a = Array{Float64}(undef, smc.N, statedim(smc.model(smc.θ[1])), 
 w(smc::SMC) = (a = Matrix{Float64}(undef, smc.N, smc.M);
                check(smc.ctx, ccall((:smcb_batch_fetch, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), smc.cur.h, C_NULL, a, C_NULL)); a)
 
+# quantile(smc.x[i], weights(smc.w[i]), p) for every θ-particle at once (examples/inflation_example.jl:44,250): [np, d, M]
+function state_quantiles(smc::SMC, p::Vector{Float64}; weighted::Bool=true)
+    q = Array{Float64}(undef, length(p), statedim(smc.model(smc.θ[1])), smc.M)
+    check(smc.ctx, ccall((:smcb_batch_weighted_quantiles, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint, Cint, Ptr{Float64}),
+                         smc.cur.h, p, length(p), weighted ? 1 : 0, q))
+    q
+end
+
 expected_parameters(smc::SMC) = sum(reduce(hcat, smc.θ .* smc.ω), dims=2)                      # :61-65 (properly weighted: SURVEY D6)
 
 function random_walk_kernel(θ::Vector{Vector{Float64}})                                        # :94-101

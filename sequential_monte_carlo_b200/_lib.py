@@ -54,6 +54,7 @@ SIGNATURES = {
     "smcb_batch_accept": (C.c_int, [_c_batch, _c_batch, C.c_void_p]),
     "smcb_batch_fetch": (C.c_int, [_c_batch, C.c_void_p, C.c_void_p, C.c_void_p]),
     "smcb_batch_weighted_mean": (C.c_int, [_c_batch, C.c_void_p]),
+    "smcb_batch_weighted_quantiles": (C.c_int, [_c_batch, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "smcb_batch_cloud_bytes": (C.c_int64, [_c_batch]),
     "smcb_batch_pack": (C.c_int, [_c_batch, C.c_void_p, C.c_int64, C.c_void_p]),
     "smcb_batch_unpack": (C.c_int, [_c_batch, C.c_void_p, C.c_int64, C.c_void_p]),
@@ -401,6 +402,14 @@ class Batch:
         """[M, d] weighted state means w[m]' x[m], computed on the device."""
         out = np.empty((self.M, self.d))
         self.ctx._check(self._lib.smcb_batch_weighted_mean(self._h, _ptr(out)))
+        return out
+
+    def weighted_quantiles(self, probs, weighted=True):
+        """[M, d, len(probs)] lower empirical quantiles of every cloud under its own weights (or counting every
+        particle once), computed on the device (docs/SPEC.md §8; examples/inflation_example.jl:39-55)."""
+        p = np.ascontiguousarray(np.atleast_1d(probs), np.float64)
+        out = np.empty((self.M, self.d, p.size))
+        self.ctx._check(self._lib.smcb_batch_weighted_quantiles(self._h, _ptr(p), int(p.size), int(bool(weighted)), _ptr(out)))
         return out
 
     def cloud_bytes(self):

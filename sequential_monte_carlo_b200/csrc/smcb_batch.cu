@@ -384,6 +384,77 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// q[m][c][j] = weighted (or plain) lower empirical quantile p_j of component c of θ-particle m's cloud (SPEC §8):
+// the per-θ bands of get_quantiles_uc / get_quantiles_ucsv (examples/inflation_example.jl:39-55,241-253).  One
+// CTA per (m, c): fixed-point weights q_i (SPEC §5), exact total, then an 8-pass radix select (one byte per
+// pass, most significant first) on the order-preserving bit pattern of x for all np probabilities at once.
+constexpr int kBatchMaxProbs = 16;
+__global__ void __launch_bounds__(256)
+    batch_wquantile_kernel(const double* __restrict__ x, const double* __restrict__ logw, const StepStats* __restrict__ st,
+                           const double* __restrict__ probs, int np, int weighted, int S, double* __restrict__ out, int64_t N, int64_t ld, int d) {
+  __shared__ unsigned long long s_hist[kBatchMaxProbs * 256];
+  __shared__ unsigned long long s_prefix[kBatchMaxProbs], s_rank[kBatchMaxProbs];
+  __shared__ unsigned long long s_red[8];
+  const int64_t m = blockIdx.x;
+  const int c = blockIdx.y, tid = threadIdx.x;
+  const double mx = st[m].mx;
+  const double* xc = x + (m * d + c) * ld;
+  const double* lw = logw + m * ld;
+  auto weight = [&](int64_t i) -> unsigned long long {
+    if (!weighted) return 1ull;
+    double e;
+    uint64_t q;
+    det_exp_quant(lw[i] - mx, S, e, q);
+    return q;
+  };
+  unsigned long long tot = 0;
+  for (int64_t i = tid; i < N; i += 256) tot += weight(i);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(kFullMask, tot, o);
+  if ((tid & 31) == 0) s_red[tid >> 5] = tot;
+  __syncthreads();
+  unsigned long long Q = 0;
+  for (int w = 0; w < 8; ++w) Q += s_red[w];
+  if (Q == 0) {  // no mass (all weights underflowed / NaN): undefined
+    if (tid < np) out[(m * d + c) * np + tid] = NAN;
+    return;
+  }
+  if (tid < np) {
+    unsigned long long r = (unsigned long long)(probs[tid] * (double)Q);  // r = min(floor(p Q), Q - 1)
+    s_rank[tid] = r > Q - 1 ? Q - 1 : r;
+    s_prefix[tid] = 0ull;
+  }
+  for (int pass = 0; pass < 8; ++pass) {
+    for (int k = tid; k < np * 256; k += 256) s_hist[k] = 0ull;
+    __syncthreads();
+    const int shift = 56 - 8 * pass;
+    for (int64_t i = tid; i < N; i += 256) {
+      const unsigned long long q = weight(i);
+      if (q == 0ull) continue;
+      const unsigned long long key = encode_ordered(xc[i]);
+      const unsigned digit = (unsigned)(key >> shift) & 255u;
+      for (int j = 0; j < np; ++j) {
+        const bool match = (pass == 0) || ((key ^ s_prefix[j]) >> (shift + 8)) == 0ull;
+        if (match) atomicAdd(&s_hist[j * 256 + digit], q);
+      }
+    }
+    __syncthreads();
+    if (tid < np) {
+      unsigned long long r = s_rank[tid], cum = 0;
+      int dg = 255;
+      for (int b = 0; b < 256; ++b) {
+        const unsigned long long h = s_hist[tid * 256 + b];
+        if (cum + h > r) { dg = b; break; }
+        cum += h;
+      }
+      s_rank[tid] = r - cum;
+      s_prefix[tid] |= (unsigned long long)dg << shift;
+    }
+    __syncthreads();
+  }
+  if (tid < np) out[(m * d + c) * np + tid] = decode_ordered(s_prefix[tid]);
+}
+
 // scalar Kalman recursion, one thread per model                                 kalman_filter.jl:29-70
 __global__ void kalman_kernel(const double* __restrict__ params, const uint8_t* __restrict__ active, int64_t M,
                               const double* __restrict__ y, int64_t T, int predict_first, double* __restrict__ loglik,
@@ -667,6 +738,29 @@ void BatchFilter::weighted_mean(double* mean_host) {
   SMCB_CUDA_TRY(cudaGetLastError());
   SMCB_CUDA_TRY(cudaMemcpyAsync(mean_host, w_tmp_, sizeof(double) * M_ * d_, cudaMemcpyDeviceToHost, stream_));
   SMCB_CUDA_TRY(cudaStreamSynchronize(stream_));
+}
+
+void BatchFilter::weighted_quantiles(const double* probs, int np, bool weighted, double* q_host) {
+  if (!live_) throw Error{SMCB_ERR_STATE, "no batch state to summarise"};
+  if (np < 1 || np > kBatchMaxProbs || !probs || !q_host) throw Error{SMCB_ERR_BAD_ARG, "batch_weighted_quantiles: 1..16 probabilities"};
+  for (int j = 0; j < np; ++j)
+    if (!(probs[j] >= 0.0 && probs[j] <= 1.0)) throw Error{SMCB_ERR_BAD_ARG, "batch_weighted_quantiles: probabilities must lie in [0, 1]"};
+  SMCB_CUDA_TRY(cudaSetDevice(device_));
+  double* scratch = nullptr;  // probs[np] then out[M][d][np]
+  const size_t words = (size_t)np + (size_t)M_ * d_ * np;
+  SMCB_CUDA_TRY(cudaMalloc(&scratch, sizeof(double) * words));
+  try {
+    SMCB_CUDA_TRY(cudaMemcpyAsync(scratch, probs, sizeof(double) * np, cudaMemcpyHostToDevice, stream_));
+    dim3 grid((unsigned)M_, (unsigned)d_);
+    batch_wquantile_kernel<<<grid, 256, 0, stream_>>>(x_[cur_], logw_[cur_], stats_[cur_], scratch, np, weighted ? 1 : 0, S_, scratch + np, N_, ld_, d_);
+    SMCB_CUDA_TRY(cudaGetLastError());
+    SMCB_CUDA_TRY(cudaMemcpyAsync(q_host, scratch + np, sizeof(double) * M_ * d_ * np, cudaMemcpyDeviceToHost, stream_));
+    SMCB_CUDA_TRY(cudaStreamSynchronize(stream_));
+  } catch (...) {
+    cudaFree(scratch);
+    throw;
+  }
+  cudaFree(scratch);
 }
 
 int64_t BatchFilter::cloud_bytes() const { return (int64_t)sizeof(double) * ((d_ + 1) * ld_ + 4); }

@@ -32,6 +32,8 @@ class BatchFilter {
   void gather(const int32_t* parents);                             // smc_samplers.jl:74-84
   void accept_from(const BatchFilter& prop, const uint8_t* accept);  // smc_samplers.jl:130-133
   void fetch(double* x_host, double* w_host, double* logw_host);
+  // [M][d][np]: lower empirical quantiles of every cloud under its weights (weighted) or counting particles once (SPEC §8)
+  void weighted_quantiles(const double* probs, int np, bool weighted, double* q_host);
   void weighted_mean(double* mean_host);  // [M][d]: w[m]' x[m], computed on the device (plotting_utils.jl:116-124,150)
   int64_t cloud_bytes() const;
   void pack(const int32_t* slots, int64_t n, void* buf_dev, bool to_buffer);

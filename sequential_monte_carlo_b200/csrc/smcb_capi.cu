@@ -325,6 +325,11 @@ int smcb_batch_fetch(smcb_batch* b, double* x, double* w, double* logw) {
   return guarded(b->ctx, [&] { b->impl->fetch(x, w, logw); });
 }
 
+int smcb_batch_weighted_quantiles(smcb_batch* b, const double* probs, int nprobs, int weighted, double* quantiles) {
+  if (!b || !probs || !quantiles) return SMCB_ERR_BAD_ARG;
+  return guarded(b->ctx, [&] { b->impl->weighted_quantiles(probs, nprobs, weighted != 0, quantiles); });
+}
+
 int smcb_batch_weighted_mean(smcb_batch* b, double* mean) {
   if (!b || !mean) return SMCB_ERR_BAD_ARG;
   return guarded(b->ctx, [&] { b->impl->weighted_mean(mean); });

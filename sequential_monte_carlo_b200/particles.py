@@ -121,6 +121,25 @@ def bootstrap_filter_(states, weights, y, model, *, resampler="multinomial"):
     return logmu, _DeviceArray(ctx, ctx._gen, "w"), ess
 
 
+def particle_filter(N, y, model, proposal=None, *, ctx=None, stream=0):
+    """x, w, logμ = particle_filter(N, y[1], model, proposal)  — particles.jl:28-51.  With proposal = nothing
+    (the only form the reference's own example uses, examples/inflation_example.jl:164,178) the initial step IS
+    the bootstrap one: it draws from initial_dist and weights by the observation density.  A guided proposal
+    functor (particles.jl:73-78, inconsistent in the reference: `proposal(model, xp)` vs `proposal(xp)`) is not
+    built: NotImplementedError, never a silent bootstrap run."""
+    if proposal is not None:
+        raise NotImplementedError("guided proposals (particles.jl:73-78) are not built; pass proposal=None for the bootstrap filter")
+    return bootstrap_filter(N, y, model, ctx=ctx, stream=stream)
+
+
+def particle_filter_(states, weights, y, model, proposal=None, *, resampler="multinomial"):
+    """logμ, w, ess = particle_filter!(x, w, y[t], model, proposal)  — particles.jl:53-84; proposal = nothing is
+    bootstrap_filter! (the reference would call `nothing(model, x)` there, particles.jl:73)."""
+    if proposal is not None:
+        raise NotImplementedError("guided proposals (particles.jl:73-78) are not built; pass proposal=None for the bootstrap filter")
+    return bootstrap_filter_(states, weights, y, model, resampler=resampler)
+
+
 def quantile(x, w_or_p, p=None):
     """quantile(x, p) (README.md:41,51: every particle counts once) or quantile(x, weights(w), p)
     (examples/inflation_example.jl:44) of a cloud that lives on the device — computed there, nothing is

@@ -233,6 +233,24 @@ def state_means(smc):
     return smc.comm.all_gather(smc._cur.weighted_mean())
 
 
+def state_quantiles(smc, p, weighted=True):
+    """[M, d, len(p)]: `quantile(smc.x[m], weights(smc.w[m]), p)` (weighted) or `quantile(smc.x[m], p)` of every
+    θ-particle's cloud (examples/inflation_example.jl:44,250), computed on the device(s) by a per-cloud radix
+    select (docs/SPEC.md §8); the clouds are not read back."""
+    return smc.comm.all_gather(smc._cur.weighted_quantiles(np.atleast_1d(np.asarray(p, np.float64)), weighted))
+
+
+def get_quantiles(smc, yt, p=(0.25, 0.5, 0.75), weighted=True, component=0):
+    """get_quantiles_uc / get_quantiles_ucsv (examples/inflation_example.jl:39-55,241-253): the ω-mixture over θ of
+    the per-cloud quantiles of the trend x and of the cycle yt − x.  Returns (xquantiles, cquantiles).
+    The cycle's p-quantile is yt minus the trend's (1 − p)-quantile (lower empirical quantiles on both sides)."""
+    p = np.atleast_1d(np.asarray(p, np.float64))
+    q = state_quantiles(smc, np.concatenate([p, 1.0 - p]), weighted)[:, component, :]
+    xq = (smc.ω[:, None] * q[:, : p.size]).sum(axis=0)
+    cq = (smc.ω[:, None] * (float(yt) - q[:, p.size:])).sum(axis=0)
+    return xq, cq
+
+
 def _observation_mean_sd(smc):
     """mean and sd of observation(model(θ_m), x̄_m) for every m (state_space_models.jl:96-103,244-247)."""
     xm, P = state_means(smc), smc._P

@@ -188,3 +188,27 @@ def test_kalman_batch(ctx, oracle):
     for m in range(M):
         xo, so, lo = oracle.kalman_step(P[m], 0.0, 1.0, y[0])
         assert abs(x1[m] - xo) <= 1e-13 * max(1.0, abs(xo)) and abs(l1[m] - lo) <= 1e-13 * abs(lo)
+
+
+def test_batch_weighted_quantiles(ctx, oracle):
+    """smcb_batch_weighted_quantiles: [M, d, np] per-cloud quantiles (SPEC §8) for a 3-component model, ragged N,
+    against the oracle cloud by cloud; argument errors."""
+    kind, M, N, T = smc.KIND_UCSV, 6, 777, 9
+    P = np.tile(smc._lib.params8([0.2, 0.2, 3.0, 1.0, 1.0]), (M, 1))
+    P[:, 0] = np.linspace(0.1, 0.6, M)
+    _, y = oracle.simulate(kind, [0.2, 0.2, 3.0, 1.0, 1.0], T, 5)
+    b = ctx.batch(kind, M, N)
+    ctx.set_rng(9, 4)
+    b.log_likelihood(P, y, smc.SYSTEMATIC, stream0=2)
+    _, xo, lwo = oracle.batch_log_likelihood(kind, P, None, N, y, smc.SYSTEMATIC, 9, 4, 2)
+    ps = [0.0, 0.05, 0.5, 0.95, 1.0]
+    for weighted in (True, False):
+        q = b.weighted_quantiles(ps, weighted=weighted)
+        assert q.shape == (M, 3, len(ps))
+        for m in range(M):
+            np.testing.assert_array_equal(q[m], oracle.weighted_summary(xo[m], lwo[m], ps, weighted=weighted)[2])
+    with pytest.raises(smc.SMCBError):
+        b.weighted_quantiles([1.5])
+    with pytest.raises(smc.SMCBError):
+        b.weighted_quantiles(np.linspace(0, 1, 17))
+    b.close()

@@ -388,3 +388,37 @@ def test_f32_state_tier(ctx, oracle, kind):
         ctx.set_precision("f64")
     # and the binary64 tier is untouched afterwards
     _compare_run(ctx, oracle, kind, 1001, 6, smc.SYSTEMATIC)
+
+
+def test_readme_loop_through_the_host_mirror(oracle):
+    """The README's online loop (README.md:33-61) spelled with the reference's function names:
+    bootstrap_filter, then bootstrap_filter! and quantile per observation; particle_filter / particle_filter!
+    with proposal = nothing (particles.jl:28-84, examples/inflation_example.jl:164,178) is the same filter."""
+    from sequential_monte_carlo_b200 import particles
+    kind, N, T = smc.KIND_LG1D, 3000, 12
+    y = _data(oracle, kind, T)
+    model = smc.StateSpaceModel(smc.LinearGaussian(0.5, 1.0, 0.9, 0.8, 0.0), (1, 1))
+    c = smc.Context(0, seed=77)
+    particles.set_default_context(c)
+    try:
+        runs = []
+        for init, step in ((smc.bootstrap_filter, smc.bootstrap_filter_),
+                           (lambda n, y0, m: smc.particle_filter(n, y0, m, None), lambda x, w, yt, m, **k: smc.particle_filter_(x, w, yt, m, None, **k))):
+            c.set_rng(77, 0)
+            x, w, logmu = init(N, y[0], model)
+            logZ, qs = logmu, []
+            for t in range(1, T):
+                logmu, w, ess = step(x, w, y[t], model, resampler="systematic")
+                logZ += logmu
+                qs.append(smc.quantile(x, [0.25, 0.5, 0.75]))
+            runs.append((np.array(x.numpy()), np.array(w.numpy()), logZ, np.array(qs)))
+        for a, b in zip(runs[0], runs[1]):
+            np.testing.assert_array_equal(a, b)
+        ref = oracle.log_likelihood(kind, MODELS[kind], N, y, smc.SYSTEMATIC, 77, 0, 0)
+        np.testing.assert_array_equal(runs[0][0].reshape(-1), ref["x"].reshape(-1))
+        assert abs(runs[0][2] - ref["logZ"]) <= RTOL * abs(ref["logZ"])
+        xs = np.sort(ref["x"][0])
+        np.testing.assert_array_equal(runs[0][3][-1], xs[np.minimum((np.array([0.25, 0.5, 0.75]) * N).astype(int), N - 1)])
+    finally:
+        particles.set_default_context(None)
+        c.close()

@@ -157,3 +157,14 @@ def test_model_constructors():
         smc.LinearGaussian(np.eye(2), np.ones((1, 2)), np.eye(2), 1.0)
     x, y = smc.simulate(v, 50, seed=3)
     assert x.shape == (50, 3) and y.shape == (50,)
+
+
+def test_particle_filter_refuses_guided_proposals():
+    """particle_filter / particle_filter! (particles.jl:28-84) exist with the reference's signature; only the
+    proposal = nothing form (≡ bootstrap, the one the reference's example uses) is built, and a guided
+    proposal is refused loudly rather than run as a bootstrap filter."""
+    m = smc.StateSpaceModel(smc.LinearGaussian(0.5, 1.0, 0.9, 0.8, 0.0), (1, 1))
+    with pytest.raises(NotImplementedError):
+        smc.particle_filter(16, 0.1, m, proposal=lambda model, x: None)
+    with pytest.raises(NotImplementedError):
+        smc.particle_filter_(None, None, 0.1, m, proposal=lambda model, x: None)

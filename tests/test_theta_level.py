@@ -77,6 +77,19 @@ def test_smc2_lg(ctx, oracle, resampler):
     from statistics import NormalDist
     z = np.array([NormalDist().inv_cdf(v) for v in (0.05, 0.5, 0.95)])
     np.testing.assert_allclose(smc.quantile(g, [0.95, 0.05, 0.5]), (g.ω[:, None] * (mu[:, None] + sd[:, None] * z)).sum(axis=0), rtol=1e-10)
+    # per-θ quantile bands (get_quantiles_uc, examples/inflation_example.jl:39-55): radix select per cloud on the
+    # device against the oracle's sort + cumulative sum, bit for bit
+    ps = [0.25, 0.5, 0.75]
+    for weighted in (True, False):
+        qg = smc.state_quantiles(g, ps, weighted=weighted)
+        assert qg.shape == (M, 1, 3)
+        for m in range(0, M, 7):
+            np.testing.assert_array_equal(qg[m], oracle.weighted_summary(o_.x[m], o_.logw[m], ps, weighted=weighted)[2])
+    xq, cq = smc.get_quantiles(g, float(y[-1]), ps)
+    qall = smc.state_quantiles(g, [0.25, 0.5, 0.75, 0.75, 0.5, 0.25])[:, 0, :]
+    np.testing.assert_allclose(xq, (g.ω[:, None] * qall[:, :3]).sum(axis=0), rtol=1e-13)
+    np.testing.assert_allclose(cq, (g.ω[:, None] * (float(y[-1]) - qall[:, 3:])).sum(axis=0), rtol=1e-13)
+    assert np.all(np.diff(xq) >= 0) and np.all(np.diff(cq) >= 0)
     g.close()
 
 
