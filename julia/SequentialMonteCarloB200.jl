@@ -206,6 +206,7 @@ end
 function resample!(smc::SMC)                                                                   # :74-84
     set_rng!(smc.ctx, smc.ctx.seed, 0)
     a = resample(smc.ω; ctx=smc.ctx, t=smc.nres, purpose=P_THETA_RESAMPLE); smc.nres += 1
+    sort!(a)                                                                                   # docs/SPEC.md §5b: exchangeable slots, sorted parents stay on their GPU
     smc.θ = smc.θ[a]; smc.logZ = smc.logZ[a]; smc.ω = fill(1 / smc.M, smc.M)
     check(smc.ctx, ccall((:smcb_batch_gather, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}), smc.cur.h, Int32.(a .- 1)))
 end

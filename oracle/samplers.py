@@ -155,6 +155,7 @@ def o_expected_parameters(smc, reference_style=False):
 def o_resample(smc):
     a = o.resample_w(smc.omega, smc.theta_resampler, smc.seed, 0, 0, smc.n_resample, purpose=o.P_THETA_RESAMPLE)   # :75
     smc.n_resample += 1
+    a = np.sort(a)                                         # SPEC §5b: θ-ancestors in ascending order (slots are exchangeable)
     smc.theta = smc.theta[a]                               # :78
     smc.omega = np.full(smc.M, 1.0 / smc.M)                # ω[a], made uniform by rejuvenate! :139
     smc.x = smc.x[a].copy()                                # :82 (deep copy: SURVEY D4)
@@ -312,6 +313,7 @@ class OIBIS:
 def o_ibis_resample(s):
     a = o.resample_w(s.omega, s.theta_resampler, s.seed, 0, 0, s.n_resample, purpose=o.P_THETA_RESAMPLE)   # ibis.jl:75
     s.n_resample += 1
+    a = np.sort(a)                                                                 # SPEC §5b
     s.theta, s.x, s.Sigma, s.logZ = s.theta[a], s.x[a], s.Sigma[a], s.logZ[a]     # ibis.jl:78-84
     s.omega = np.full(s.M, 1.0 / s.M)
     return a

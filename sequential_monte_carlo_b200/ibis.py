@@ -43,6 +43,7 @@ def resample_(ibis):
     ibis.ctx.set_rng(ibis.seed, 0)
     a = ibis.ctx.resample(ibis.ω, ibis.theta_resampler, stream=0, t=ibis._n_resample, purpose=_lib.P_THETA_RESAMPLE)
     ibis._n_resample += 1
+    a = np.sort(a)   # docs/SPEC.md §5b: ascending θ-ancestors (same convention as SMC, where it keeps clouds rank-local)
     ibis.θ, ibis.x, ibis.Σ, ibis.logZ = ibis.θ[a], ibis.x[a], ibis.Σ[a], ibis.logZ[a]
     ibis.ω = np.full(ibis.M, 1.0 / ibis.M)
     return a
