@@ -136,6 +136,18 @@ int smcb_batch_step(smcb_batch* b, const double* params, double y, int resampler
 /* whole series for every θ in ONE launch; the final clouds stay in b */
 int smcb_batch_log_likelihood(smcb_batch* b, const double* params, const uint8_t* active, const double* y,
                               int64_t T, int resampler, uint32_t stream0, double* logZ);
+/* Guided filters — particle_filter / particle_filter! with a proposal      particles.jl:28-84 (docs/SPEC.md §10)
+ * The reference's proposal is a Julia closure (model, xp) -> distribution; the device evaluates the affine-Gaussian
+ * family  x' ~ N(c0 + c1·xp, c2²)  (c2 > 0; a closure over y_t picks the coefficients per step, e.g. the locally
+ * optimal proposal of an LG model), for the one-dimensional models (LG1D, SV).  Every step t >= 1 draws x' from the
+ * proposal and weights by  logpdf(observation(x'), y) + logpdf(transition(xp), x') - logpdf(proposal(xp), x')  (:73-78);
+ * the initial step draws from initial_dist and weights by the observation density (:40-42; the reference's
+ * "+ logpdf(initial_dist, x)" at :44 lacks its "- logpdf(proposal)" partner, commented out at :45 — ruled a defect).
+ * proposal: [M][3] for one step, [T][M][3] for a whole series (row 0 is not read); SMCB_ERR_UNSUPPORTED for UCSV. */
+int smcb_batch_step_guided(smcb_batch* b, const double* params, double y, int resampler, const double* proposal,
+                           double* logmu, double* ess);
+int smcb_batch_log_likelihood_guided(smcb_batch* b, const double* params, const uint8_t* active, const double* y,
+                                     int64_t T, int resampler, uint32_t stream0, const double* proposal, double* logZ);
 /* θ-resample: slot m takes a deep copy of slot parents[m] (x, log-weights, rng identity)
  *   smc_samplers.jl:74-84 (with the w-permutation / aliasing defects D3, D4 fixed) */
 int smcb_batch_gather(smcb_batch* b, const int32_t* parents);
@@ -147,6 +159,9 @@ int smcb_batch_fetch(smcb_batch* b, double* x, double* w, double* logw);
 /* mean [M][d]: the weighted state mean w[m]' * x[m] of every θ-particle's cloud, computed on the device — what
  * estimated_trend(smc) and quantile(smc, p) integrate over θ (plotting_utils.jl:116-124,140-157) */
 int smcb_batch_weighted_mean(smcb_batch* b, double* mean);
+/* mean, var [M][d] (either may be NULL): mean as above and the population variance Σ w_i (x_i - mean)² of every cloud
+ * under its own weights — var(x, weights(w)) per θ-particle (examples/inflation_example.jl:46) */
+int smcb_batch_weighted_moments(smcb_batch* b, double* mean, double* var);
 /* quantiles [M][d][nprobs] (nprobs <= 16): the lower empirical quantiles of every θ-particle's cloud under its own
  * weights (weighted != 0) or counting every particle once, computed on the device (docs/SPEC.md §8) — the per-θ
  * bands of get_quantiles_uc / get_quantiles_ucsv, examples/inflation_example.jl:39-55,241-253 */
@@ -166,6 +181,16 @@ int smcb_kalman_batch_step(smcb_ctx* ctx, const double* params, int64_t M, doubl
 int smcb_kalman_batch_loglik(smcb_ctx* ctx, const double* params, const uint8_t* active, int64_t M,
                              const double* y, int64_t T, int matched_init, double* loglik, double* x,
                              double* sigma);
+
+/* Matrix Kalman filter, M multivariate LinearModels with a scalar observation at once    kalman_filter.jl:3-27,55-70
+ * (MultivariateLinearGaussian, hodrick_prescott: state_space_models.jl:137-202).  State dimension
+ * 1 <= d <= 4.  models [M][3d²+2d+1], row-major: A[d][d], B[d], Q[d][d], R, x0[d], Σ0[d][d].
+ * step: x [M][d], sigma [M][d][d] in/out, loglik [M] out.  loglik: starts from (x0, Σ0) of every model, x / sigma
+ * receive the final filtered moments (may be NULL); matched_init=1 skips the first predict as above. */
+int smcb_kalman_mv_batch_step(smcb_ctx* ctx, int d, const double* models, int64_t M, double y, double* x, double* sigma,
+                              double* loglik);
+int smcb_kalman_mv_batch_loglik(smcb_ctx* ctx, int d, const double* models, const uint8_t* active, int64_t M,
+                                const double* y, int64_t T, int matched_init, double* loglik, double* x, double* sigma);
 
 /* ------------------------------------------------------------------ host-side helpers (no GPU) */
 /* The θ-level samplers draw priors, MH proposals and accept uniforms on the host from the same

@@ -9,14 +9,18 @@
 #   StateSpaceModel, LinearModel, UnivariateLinearGaussian, LinearGaussian, unobserved_components,
 #   UC, UCSV, StochasticVolatility, simulate                                      src/state_space_models.jl
 #   SMC, smc², smc²!, density_tempered, expected_parameters                       src/smc_samplers.jl
-#   kalman_filter, log_likelihood(y, model)                                       src/kalman_filter.jl
+#   kalman_filter, log_likelihood(y, model)  (scalar and matrix methods)          src/kalman_filter.jl
+#   particle_filter, particle_filter!  (guided: affine-Gaussian proposals, docs/SPEC.md §10)   src/particles.jl:28-84
+#   MultivariateLinearGaussian, hodrick_prescott  (Kalman filter only)            src/state_space_models.jl:137-202
 module SequentialMonteCarloB200
 
 using Distributions, LinearAlgebra, Printf, Statistics
 
 export StateSpaceModel, LinearModel, UnivariateLinearGaussian, LinearGaussian, unobserved_components, UC, UCSV,
        StochasticVolatility, simulate, normalize, resample, bootstrap_filter, bootstrap_filter!, log_likelihood,
-       SMC, smc², smc²!, density_tempered, expected_parameters, kalman_filter
+       SMC, smc², smc²!, density_tempered, expected_parameters, kalman_filter,
+       particle_filter, particle_filter!, AffineGaussianProposal, locally_optimal_proposal,
+       MultivariateLinearModel, MultivariateLinearGaussian, hodrick_prescott, state_variances
 
 const LIB = get(ENV, "SMCB200_LIB", joinpath(@__DIR__, "..", "sequential_monte_carlo_b200", "lib", "libsmcb200.so"))
 const MULTINOMIAL, STRATIFIED, SYSTEMATIC = Cint(0), Cint(1), Cint(2)
@@ -156,6 +160,32 @@ function log_likelihood(y::Vector{Float64}, model::LinearModel; ctx=context(), m
     return x[1], s[1], ll[1]
 end
 
+# matrix methods (:3-27) for multivariate LinearModels with a scalar observation, d <= 4
+struct MultivariateLinearModel <: StateSpaceModel                                             # state_space_models.jl:137-154
+    A::Matrix{Float64}; B::Matrix{Float64}; Q::Matrix{Float64}; R::Vector{Float64}; x0::Vector{Float64}; σ0::Matrix{Float64}
+end
+MultivariateLinearGaussian(; A, B, Q, R, X0=zeros(size(A, 1)), Σ0=Matrix(1.0I(size(A, 1)))) =
+    MultivariateLinearModel(Float64.(A), Float64.(reshape(B, 1, :)), Float64.(Q), Float64.(vec(R)), Float64.(X0), Float64.(Matrix(Σ0)))
+hodrick_prescott(; λ, y, init_cov=1000.0) = MultivariateLinearGaussian(                        # :187-202
+    A=[2.0 -1.0; 1.0 0.0], B=[1.0 0.0], Q=[1 / λ 0.0; 0.0 0.0], R=[1.0],
+    X0=[3 * y[1] - 2 * y[2], 2 * y[1] - y[2]], Σ0=Matrix(init_cov * I(2)))
+# row-major block A, B, Q, R, x0, Σ0 (include/smcb200.h); Julia is column-major, hence the transposes
+block(m::MultivariateLinearModel) = vcat(vec(m.A'), vec(m.B), vec(m.Q'), m.R[1:1], m.x0, vec(m.σ0'))
+function kalman_filter(model::MultivariateLinearModel, xt::Vector{Float64}, Σt::Matrix{Float64}, yt::Float64; ctx=context())   # :3-27
+    d = length(xt); x = copy(xt); s = collect(vec(Σt')); ll = [0.0]
+    check(ctx, ccall((:smcb_kalman_mv_batch_step, LIB), Cint,
+                     (Ptr{Cvoid}, Cint, Ptr{Float64}, Int64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                     ctx.h, d, block(model), 1, yt, x, s, ll))
+    return x, collect(reshape(s, d, d)'), ll[1]
+end
+function log_likelihood(y::Vector{Float64}, model::MultivariateLinearModel; ctx=context(), matched_init=false)   # :55-70
+    d = length(model.x0); ll = [0.0]; x = zeros(d); s = zeros(d * d)
+    check(ctx, ccall((:smcb_kalman_mv_batch_loglik, LIB), Cint,
+                     (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{UInt8}, Int64, Ptr{Float64}, Int64, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                     ctx.h, d, block(model), C_NULL, 1, y, length(y), matched_init, ll, x, s))
+    return x, collect(reshape(s, d, d)'), ll[1]
+end
+
 # ---------------------------------------------------------------- smc_samplers.jl
 mutable struct Batch
     h::Ptr{Cvoid}; ctx::Context
@@ -193,6 +223,49 @@ function state_quantiles(smc::SMC, p::Vector{Float64}; weighted::Bool=true)
     check(smc.ctx, ccall((:smcb_batch_weighted_quantiles, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint, Cint, Ptr{Float64}),
                          smc.cur.h, p, length(p), weighted ? 1 : 0, q))
     q
+end
+
+# mean(smc.x[i], weights(smc.w[i])), var(smc.x[i], weights(smc.w[i])) for every θ-particle at once (inflation_example.jl:46): [d, M] each
+function state_variances(smc::SMC)
+    d = statedim(smc.model(smc.θ[1])); mean = Matrix{Float64}(undef, d, smc.M); var = Matrix{Float64}(undef, d, smc.M)
+    check(smc.ctx, ccall((:smcb_batch_weighted_moments, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), smc.cur.h, mean, var))
+    mean, var
+end
+
+# ---------------------------------------------------------------- guided filters (particles.jl:28-84, docs/SPEC.md §10)
+# The device evaluates proposals of the family x' ~ Normal(c0 + c1*xp, c2); a proposal is called as proposal(model, y)
+# and returns (c0, c1, c2) for the step that assimilates y (the closure over y the reference's signature implies).
+struct AffineGaussianProposal
+    c0::Float64; c1::Float64; c2::Float64
+end
+(q::AffineGaussianProposal)(model, y) = (q.c0, q.c1, q.c2)
+function locally_optimal_proposal(model::LinearModel, y::Float64)      # p(x' | xp, y) of a univariate LinearModel
+    s2 = 1 / (1 / model.Q + model.B^2 / model.R)
+    (s2 * model.B * y / model.R, s2 * model.A / model.Q, sqrt(s2))
+end
+mutable struct GuidedCloud                        # a guided filter is a batch of one θ (N <= 8192)
+    b::Batch; N::Int64
+end
+Base.collect(c::GuidedCloud) = (a = Vector{Float64}(undef, c.N);
+    check(c.b.ctx, ccall((:smcb_batch_fetch, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), c.b.h, a, C_NULL, C_NULL)); a)
+weights(c::GuidedCloud) = (a = Vector{Float64}(undef, c.N);
+    check(c.b.ctx, ccall((:smcb_batch_fetch, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), c.b.h, C_NULL, a, C_NULL)); a)
+particle_filter(N::Int64, y::Float64, model::StateSpaceModel, ::Nothing; ctx=context()) = bootstrap_filter(N, y, model; ctx=ctx)   # :28-51
+function particle_filter(N::Int64, y::Float64, model::StateSpaceModel, proposal; ctx=context())
+    b = Batch(ctx, kind(model), 1, N); lm = [0.0]; es = [0.0]
+    check(ctx, ccall((:smcb_batch_init, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{UInt8}, Float64, UInt32, Ptr{Float64}, Ptr{Float64}),
+                     b.h, params8(model), C_NULL, y, 0, lm, es))
+    x = GuidedCloud(b, N)
+    return x, weights(x), lm[1]
+end
+particle_filter!(states::Cloud, w::Vector{Float64}, y::Float64, model::StateSpaceModel, ::Nothing; resampler=MULTINOMIAL) =
+    bootstrap_filter!(states, w, y, model; resampler=resampler)                                # :55-84 with proposal = nothing
+function particle_filter!(states::GuidedCloud, w::Vector{Float64}, y::Float64, model::StateSpaceModel, proposal; resampler=MULTINOMIAL)
+    c = Float64[proposal(model, y)...]; lm = [0.0]; es = [0.0]
+    check(states.b.ctx, ccall((:smcb_batch_step_guided, LIB), Cint,
+                              (Ptr{Cvoid}, Ptr{Float64}, Float64, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                              states.b.h, params8(model), y, resampler, c, lm, es))
+    return lm[1], weights(states), es[1]
 end
 
 expected_parameters(smc::SMC) = sum(reduce(hcat, smc.θ .* smc.ω), dims=2)                      # :61-65 (properly weighted: SURVEY D6)

@@ -41,6 +41,9 @@ def lib():
         L.smco_log_likelihood.restype = C.c_double
         L.smco_kalman_step.restype = C.c_double
         L.smco_kalman_loglik.restype = C.c_double
+        L.smco_guided_log_likelihood.restype = C.c_double
+        L.smco_kalman_mv_step.restype = C.c_double
+        L.smco_kalman_mv_loglik.restype = C.c_double
         _LIB = L
     return _LIB
 
@@ -247,6 +250,56 @@ def batch_log_likelihood(kind, params, active, n, y, resampler, seed, epoch, str
     return logZ, x, logw
 
 
+# ---------------------------------------------------------------- N3 guided filter (SPEC §10)
+def guided_step(kind, params, x, logw, y, t, resampler, prop, seed, epoch=0, stream=0):
+    """particle_filter!(x, w, y, model, proposal) with proposal = Normal(c0 + c1 xp, c2): mutates x [1,n] / logw in
+    place, returns the ancestors.  particles.jl:55-84"""
+    n = logw.size
+    anc = np.empty(n, np.int64)
+    prop = np.ascontiguousarray(prop, np.float64)
+    rc = lib().smco_guided_step(C.c_int(kind), _p(params8(params)), C.c_int64(n), C.c_double(y), C.c_uint32(t),
+                                C.c_int(resampler), C.c_uint64(seed), C.c_uint32(epoch), C.c_uint32(stream), _p(prop),
+                                _p(x), _p(logw), _p(anc))
+    if rc != 0:
+        raise ValueError("guided proposals are defined for the one-dimensional models")
+    return anc
+
+
+def guided_log_likelihood(kind, params, n, y, resampler, prop, seed, epoch=0, stream=0):
+    """bootstrap initial step + guided steps; prop: [T, 3] (row 0 unused).  dict(x, logw, logZ, logmu[T], ess[T])."""
+    y = np.ascontiguousarray(y, np.float64)
+    T = y.size
+    prop = np.ascontiguousarray(prop, np.float64).reshape(T, 3)
+    x, logw = np.empty((1, n)), np.empty(n)
+    logmu, ess = np.empty(T), np.empty(T)
+    logZ = lib().smco_guided_log_likelihood(C.c_int(kind), _p(params8(params)), C.c_int64(n), _p(y), C.c_int64(T),
+                                            C.c_int(resampler), C.c_uint64(seed), C.c_uint32(epoch), C.c_uint32(stream),
+                                            _p(prop), C.c_int64(3), _p(x), _p(logw), _p(logmu), _p(ess))
+    return dict(x=x, logw=logw, logZ=logZ, logmu=logmu, ess=ess)
+
+
+def batch_guided_log_likelihood(kind, params, active, n, y, resampler, prop, seed, epoch, stream0=0):
+    """M guided filters threaded over theta; params [M,8], prop [T,M,3].  Returns (logZ[M], x[M,1,n], logw[M,n])."""
+    params = np.ascontiguousarray(params, np.float64)
+    M = params.shape[0]
+    y = np.ascontiguousarray(y, np.float64)
+    prop = np.ascontiguousarray(prop, np.float64).reshape(y.size, M, 3)
+    logZ, x, logw = np.empty(M), np.empty((M, 1, n)), np.empty((M, n))
+    act = None if active is None else np.ascontiguousarray(active, np.uint8)
+    lib().smco_batch_guided_log_likelihood(C.c_int(kind), _p(params), _p(act), C.c_int64(M), C.c_int64(n), _p(y),
+                                           C.c_int64(y.size), C.c_int(resampler), C.c_uint64(seed), C.c_uint32(epoch),
+                                           C.c_uint32(stream0), _p(prop), _p(logZ), _p(x), _p(logw))
+    return logZ, x, logw
+
+
+def optimal_proposal_lg(params, y):
+    """(c0, c1, c2) of the locally optimal proposal p(x' | xp, y) of an LG1D model (A,B,Q,R,..): precision
+    1/Q + B²/R, mean s²(A xp / Q + B y / R)."""
+    A, B, Q, R = (float(v) for v in np.asarray(params, np.float64)[:4])
+    s2 = 1.0 / (1.0 / Q + B * B / R)
+    return np.array([s2 * B * float(y) / R, s2 * A / Q, np.sqrt(s2)])
+
+
 def weighted_summary(x, logw, probs, weighted=True):
     """SPEC §8 restated with numpy: fixed-point weights q_i of the current log-weights (SPEC §5), population mean /
     variance, and lower empirical quantiles = the smallest x whose cumulative q exceeds r = min(floor(p Q), Q - 1).
@@ -293,6 +346,29 @@ def kalman_loglik(params, y, matched_init=False):
     ll = lib().smco_kalman_loglik(_p(params8(params)), _p(y), C.c_int64(y.size), C.c_int(int(matched_init)),
                                   C.byref(xT), C.byref(ST))
     return xT.value, ST.value, ll
+
+
+def mv_block(A, B, Q, R, x0, S0):
+    """row-major model block A[d][d], B[d], Q[d][d], R, x0[d], Σ0[d][d] of a multivariate LinearModel"""
+    return np.concatenate([np.asarray(A, np.float64).ravel(), np.asarray(B, np.float64).ravel(), np.asarray(Q, np.float64).ravel(),
+                           np.asarray(R, np.float64).ravel()[:1], np.asarray(x0, np.float64).ravel(), np.asarray(S0, np.float64).ravel()])
+
+
+def kalman_mv_step(d, block, x, S, y, predict=True):
+    """kalman_filter(model, xt, Σt, yt) for a multivariate LinearModel   kalman_filter.jl:3-27"""
+    block = np.ascontiguousarray(block, np.float64)
+    x = np.array(x, np.float64).ravel().copy()
+    S = np.array(S, np.float64).reshape(d, d).copy()
+    ll = lib().smco_kalman_mv_step(C.c_int(d), _p(block), _p(x), _p(S), C.c_double(y), C.c_int(int(predict)))
+    return x, S, ll
+
+
+def kalman_mv_loglik(d, block, y, matched_init=False):
+    block = np.ascontiguousarray(block, np.float64)
+    y = np.ascontiguousarray(y, np.float64)
+    x, S = np.empty(d), np.empty((d, d))
+    ll = lib().smco_kalman_mv_loglik(C.c_int(d), _p(block), _p(y), C.c_int64(y.size), C.c_int(int(matched_init)), _p(x), _p(S))
+    return x, S, ll
 
 
 def simulate(kind, params, T, seed):

@@ -14,6 +14,8 @@
  *   smco_batch_log_likelihood <- the Threads.@threads loops /root/reference/src/smc_samplers.jl:112-121,223-229
  *   model_*                 <- LinearModel / UCSV methods /root/reference/src/state_space_models.jl:74-109,215-259
  *   smco_kalman_*           <- kalman_filter / log_likelihood /root/reference/src/kalman_filter.jl:29-70
+ *   smco_guided_*           <- particle_filter / particle_filter! /root/reference/src/particles.jl:28-84 (SPEC §10)
+ *   smco_kalman_mv_*        <- kalman_filter (matrix)       /root/reference/src/kalman_filter.jl:3-27
  *   smco_simulate           <- simulate             /root/reference/src/state_space_models.jl:11-26
  *
  * PARITY UNPINNED: the reference has no tests, fixtures or golden vectors and
@@ -64,9 +66,11 @@ void smco_derive(int kind, const double *P, double *D) {
     D[0] = P[0]; D[1] = P[1]; D[2] = sqrt(P[2]); D[3] = P[4]; D[4] = sqrt(P[5]);
     D[5] = 1.0 / sr;
     D[6] = -(o_log(sr) + O_HALF_LOG_2PI);
+    D[7] = o_log(D[2]);                           /* log sd of the transition: guided weights (SPEC §10) */
   } else if (kind == KIND_SV) {
     D[0] = P[0]; D[1] = P[1]; D[2] = P[2];
     D[3] = P[2] / sqrt(1.0 - P[1] * P[1]);
+    D[4] = o_log(P[2]);                           /* log sd of the transition: guided weights (SPEC §10) */
   } else { /* UCSV: state_space_models.jl:215-259 */
     D[0] = P[0]; D[1] = P[1]; D[2] = P[2]; D[3] = P[3]; D[4] = P[4];
     D[5] = o_exp(0.5 * P[3]);
@@ -226,6 +230,76 @@ void smco_bootstrap_step(int kind, const double *P, int64_t n, double y, uint32_
   free(a);
 }
 
+/* ------------------------------------------------------------------ N3 particle_filter! with a proposal */
+/* particles.jl:55-84 for the one-dimensional models and the affine-Gaussian proposal family of SPEC §10:
+ * prop = (c0, c1, c2), x' ~ Normal(c0 + c1 xp, c2).  Same resampling and the same Philox normal as the
+ * bootstrap step; logw = logpdf(observation(x'), y) + logpdf(transition(xp), x') - logpdf(proposal(xp), x'). */
+int smco_guided_step(int kind, const double *P, int64_t n, double y, uint32_t t, int resampler, uint64_t seed,
+                     uint32_t epoch, uint32_t stream, const double *prop, double *x, double *logw, int64_t *anc_out) {
+  if (kind == KIND_UCSV) return -1;
+  double D[8];
+  smco_derive(kind, P, D);
+  const double c0 = prop[0], c1 = prop[1], c2 = prop[2], lc2 = o_log(prop[2]);
+  const double sdf = D[2], lsdf = (kind == KIND_LG1D) ? D[7] : D[4];
+  int64_t *a = (int64_t *)malloc(sizeof(int64_t) * (size_t)n);              /* a = resample(weights) :66 */
+  smco_ancestors(logw, n, resampler, seed, epoch, stream, t, a);
+  double *xp = (double *)malloc(sizeof(double) * (size_t)n);               /* xp = deepcopy(x[a]) :68 */
+  for (int64_t i = 0; i < n; ++i) xp[i] = x[a[i]];
+  for (int64_t i = 0; i < n; ++i) {                                         /* :72-80 */
+    double z = o_normal(seed, epoch, (uint32_t)i, stream, t, P_TRANS, 0);
+    double mq = fma(c1, xp[i], c0);
+    double xi = fma(c2, z, mq);                                             /* x[i] = rand(proposal(model, xp[i])) :73 */
+    double mf = (kind == KIND_LG1D) ? D[0] * xp[i] : fma(D[1], xp[i] - D[0], D[0]);
+    double zt = (xi - mf) / sdf;
+    double zq = (xi - mq) / c2;
+    double lf = fma(-0.5 * zt, zt, -lsdf);                                  /* logpdf(transition(model, xp[i]), x[i]) :77 */
+    double lq = fma(-0.5 * zq, zq, -lc2);                                   /* logpdf(proposal(xp[i]), x[i]) :78 */
+    x[i] = xi;
+    logw[i] = model_logweight(kind, D, &xi, y) + (lf - lq);                 /* :74 */
+  }
+  if (anc_out) memcpy(anc_out, a, sizeof(int64_t) * (size_t)n);
+  free(xp);
+  free(a);
+  return 0;
+}
+
+/* whole series: bootstrap initial step (particles.jl:40-42; the unmatched "+ logpdf(initial_dist)" of :44 is ruled a
+ * defect, SPEC §10), then guided steps with prop[t] = (c0, c1, c2) of time t (row 0 unused). */
+double smco_guided_log_likelihood(int kind, const double *P, int64_t n, const double *y, int64_t T, int resampler,
+                                  uint64_t seed, uint32_t epoch, uint32_t stream, const double *prop, int64_t prop_stride,
+                                  double *x, double *logw, double *logmu_out, double *ess_out) {
+  double *xl = x ? x : (double *)malloc(sizeof(double) * (size_t)n);
+  double *lw = logw ? logw : (double *)malloc(sizeof(double) * (size_t)n);
+  double logZ = 0.0, lm, es;
+  smco_bootstrap_init(kind, P, n, y[0], seed, epoch, stream, xl, lw);
+  smco_normalize(lw, n, &lm, NULL, &es);
+  logZ = lm;
+  if (logmu_out) logmu_out[0] = lm;
+  if (ess_out) ess_out[0] = es;
+  for (int64_t t = 1; t < T; ++t) {
+    smco_guided_step(kind, P, n, y[t], (uint32_t)t, resampler, seed, epoch, stream, prop + t * prop_stride, xl, lw, NULL);
+    smco_normalize(lw, n, &lm, NULL, &es);
+    logZ += lm;
+    if (logmu_out) logmu_out[t] = lm;
+    if (ess_out) ess_out[t] = es;
+  }
+  if (!x) free(xl);
+  if (!logw) free(lw);
+  return logZ;
+}
+
+/* M guided filters; prop is [T][M][3] */
+void smco_batch_guided_log_likelihood(int kind, const double *P, const uint8_t *active, int64_t M, int64_t n,
+                                      const double *y, int64_t T, int resampler, uint64_t seed, uint32_t epoch,
+                                      uint32_t stream0, const double *prop, double *logZ, double *x, double *logw) {
+#pragma omp parallel for schedule(static)
+  for (int64_t m = 0; m < M; ++m) {
+    if (active && !active[m]) { logZ[m] = -INFINITY; continue; }
+    logZ[m] = smco_guided_log_likelihood(kind, P + 8 * m, n, y, T, resampler, seed, epoch, stream0 + (uint32_t)m,
+                                         prop + 3 * m, 3 * M, x ? x + m * n : NULL, logw ? logw + m * n : NULL, NULL, NULL);
+  }
+}
+
 /* ------------------------------------------------------------------ a5 log_likelihood */
 double smco_log_likelihood(int kind, const double *P, int64_t n, const double *y, int64_t T, int resampler,
                            uint64_t seed, uint32_t epoch, uint32_t stream, double *x, double *logw,
@@ -295,6 +369,61 @@ double smco_kalman_loglik(const double *P, const double *y, int64_t T, int match
   for (int64_t t = 0; t < T; ++t) ll += smco_kalman_step(P, &x, &S, y[t], !(matched_init && t == 0));
   if (xT) *xT = x;
   if (ST) *ST = S;
+  return ll;
+}
+
+/* ------------------------------------------------------------------ N4 Kalman (matrix, scalar observation) */
+/* kalman_filter.jl:3-27.  Model block, row-major: A[d][d], B[d], Q[d][d], R, x0[d], S0[d][d]; d <= 4. */
+double smco_kalman_mv_step(int d, const double *P, double *x, double *S, double yt, int predict) {
+  const double *A = P, *B = P + d * d, *Q = P + d * d + d;
+  const double R = P[2 * d * d + d];
+  double xn[4], AS[16], K[4];
+  if (predict) {
+    for (int i = 0; i < d; ++i) {                      /* xt = A*xt :13 */
+      double acc = 0.0;
+      for (int j = 0; j < d; ++j) acc += A[i * d + j] * x[j];
+      xn[i] = acc;
+      for (int k = 0; k < d; ++k) {
+        double u = 0.0;
+        for (int j = 0; j < d; ++j) u += A[i * d + j] * S[j * d + k];
+        AS[i * d + k] = u;
+      }
+    }
+    for (int i = 0; i < d; ++i) {                      /* St = A*St*A' + Q :14 */
+      x[i] = xn[i];
+      for (int k = 0; k < d; ++k) {
+        double u = 0.0;
+        for (int j = 0; j < d; ++j) u += AS[i * d + j] * A[k * d + j];
+        S[i * d + k] = u + Q[i * d + k];
+      }
+    }
+  }
+  double bx = 0.0, sig = 0.0;
+  for (int i = 0; i < d; ++i) {
+    double u = 0.0;
+    for (int j = 0; j < d; ++j) u += S[i * d + j] * B[j];
+    K[i] = u;
+    bx += B[i] * x[i];
+  }
+  for (int i = 0; i < d; ++i) sig += B[i] * K[i];
+  sig += R;                                            /* :16 */
+  double dy = yt - bx;                                 /* :17 */
+  double inv = 1.0 / sig;
+  for (int i = 0; i < d; ++i) {
+    double g = K[i] * inv;
+    x[i] = x[i] + g * dy;                              /* :20 */
+    for (int j = 0; j < d; ++j) S[i * d + j] = S[i * d + j] - g * K[j];   /* :21 */
+  }
+  return -0.5 * (log(2.0 * M_PI) + log(sig) + (dy * inv * dy));          /* :24-26 */
+}
+/* log_likelihood(y, model) kalman_filter.jl:55-70 */
+double smco_kalman_mv_loglik(int d, const double *P, const double *y, int64_t T, int matched_init, double *xT, double *ST) {
+  double x[4], S[16], ll = 0.0;
+  for (int i = 0; i < d; ++i) x[i] = P[2 * d * d + d + 1 + i];
+  for (int i = 0; i < d * d; ++i) S[i] = P[2 * d * d + 2 * d + 1 + i];
+  for (int64_t t = 0; t < T; ++t) ll += smco_kalman_mv_step(d, P, x, S, y[t], !(matched_init && t == 0));
+  if (xT) for (int i = 0; i < d; ++i) xT[i] = x[i];
+  if (ST) for (int i = 0; i < d * d; ++i) ST[i] = S[i];
   return ll;
 }
 

@@ -50,10 +50,14 @@ SIGNATURES = {
     "smcb_batch_step": (C.c_int, [_c_batch, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]),
     "smcb_batch_log_likelihood": (C.c_int, [_c_batch, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_uint32,
                                             C.c_void_p]),
+    "smcb_batch_step_guided": (C.c_int, [_c_batch, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "smcb_batch_log_likelihood_guided": (C.c_int, [_c_batch, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_uint32,
+                                                   C.c_void_p, C.c_void_p]),
     "smcb_batch_gather": (C.c_int, [_c_batch, C.c_void_p]),
     "smcb_batch_accept": (C.c_int, [_c_batch, _c_batch, C.c_void_p]),
     "smcb_batch_fetch": (C.c_int, [_c_batch, C.c_void_p, C.c_void_p, C.c_void_p]),
     "smcb_batch_weighted_mean": (C.c_int, [_c_batch, C.c_void_p]),
+    "smcb_batch_weighted_moments": (C.c_int, [_c_batch, C.c_void_p, C.c_void_p]),
     "smcb_batch_weighted_quantiles": (C.c_int, [_c_batch, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "smcb_batch_cloud_bytes": (C.c_int64, [_c_batch]),
     "smcb_batch_pack": (C.c_int, [_c_batch, C.c_void_p, C.c_int64, C.c_void_p]),
@@ -62,6 +66,9 @@ SIGNATURES = {
     "smcb_kalman_batch_step": (C.c_int, [_c_ctx, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "smcb_kalman_batch_loglik": (C.c_int, [_c_ctx, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p]),
+    "smcb_kalman_mv_batch_step": (C.c_int, [_c_ctx, C.c_int, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "smcb_kalman_mv_batch_loglik": (C.c_int, [_c_ctx, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int,
+                                              C.c_void_p, C.c_void_p, C.c_void_p]),
     "smcb_rng_normals": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int64, C.c_void_p]),
     "smcb_rng_uniforms64": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int64, C.c_void_p]),
     "smcb_simulate": (C.c_int, [C.c_int, C.c_void_p, C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p]),
@@ -323,6 +330,31 @@ class Context:
                                                        _ptr(ll), _ptr(x), _ptr(s)))
         return ll, x, s
 
+    @staticmethod
+    def _mv_blocks(d, models):
+        stride = 3 * d * d + 2 * d + 1
+        b = np.ascontiguousarray(models, np.float64).reshape(-1, stride)
+        return b, b.shape[0]
+
+    def kalman_mv_step(self, d, models, x, sigma, y):
+        """M × kalman_filter(model, x, Σ, y) for multivariate LinearModels (kalman_filter.jl:3-27); models [M, 3d²+2d+1]
+        = A, B, Q, R, x0, Σ0 row-major.  Returns x [M, d], Σ [M, d, d], step log-likelihoods [M]."""
+        b, M = self._mv_blocks(d, models)
+        x = np.ascontiguousarray(np.broadcast_to(np.asarray(x, np.float64), (M, d))).copy()
+        s = np.ascontiguousarray(np.broadcast_to(np.asarray(sigma, np.float64), (M, d, d))).copy()
+        ll = np.empty(M)
+        self._check(self._lib.smcb_kalman_mv_batch_step(self._h, int(d), _ptr(b), M, float(y), _ptr(x), _ptr(s), _ptr(ll)))
+        return x, s, ll
+
+    def kalman_mv_loglik(self, d, models, y, matched_init=False, active=None):
+        b, M = self._mv_blocks(d, models)
+        y = np.ascontiguousarray(y, np.float64)
+        act = None if active is None else np.ascontiguousarray(active, np.uint8)
+        ll, x, s = np.empty(M), np.empty((M, d)), np.empty((M, d, d))
+        self._check(self._lib.smcb_kalman_mv_batch_loglik(self._h, int(d), _ptr(b), _ptr(act), M, _ptr(y), y.size,
+                                                          int(bool(matched_init)), _ptr(ll), _ptr(x), _ptr(s)))
+        return ll, x, s
+
     def batch(self, kind, M, N):
         return Batch(self, kind, M, N)
 
@@ -367,18 +399,33 @@ class Batch:
         self.ctx._check(self._lib.smcb_batch_init(self._h, _ptr(p), _ptr(act), float(y), int(stream0), _ptr(lm), _ptr(es)))
         return lm, es
 
-    def step(self, y, resampler=MULTINOMIAL, params=None):
+    def _proposal(self, proposal, rows):
+        q = np.ascontiguousarray(np.broadcast_to(np.asarray(proposal, np.float64), (rows, self.M, 3)))
+        return q
+
+    def step(self, y, resampler=MULTINOMIAL, params=None, proposal=None):
+        """one step of every filter; proposal [M, 3] = (c0, c1, c2) makes it the guided step of docs/SPEC.md §10"""
         p = self._params(params)
         lm, es = np.empty(self.M), np.empty(self.M)
-        self.ctx._check(self._lib.smcb_batch_step(self._h, _ptr(p), float(y), int(resampler), _ptr(lm), _ptr(es)))
+        if proposal is None:
+            self.ctx._check(self._lib.smcb_batch_step(self._h, _ptr(p), float(y), int(resampler), _ptr(lm), _ptr(es)))
+        else:
+            q = self._proposal(proposal, 1)
+            self.ctx._check(self._lib.smcb_batch_step_guided(self._h, _ptr(p), float(y), int(resampler), _ptr(q), _ptr(lm), _ptr(es)))
         return lm, es
 
-    def log_likelihood(self, params, y, resampler=MULTINOMIAL, stream0=0, active=None):
+    def log_likelihood(self, params, y, resampler=MULTINOMIAL, stream0=0, active=None, proposal=None):
+        """whole series for every θ in one launch; proposal [T, M, 3] (row 0 unused) runs the guided filter"""
         p, act = self._params(params), self._mask(active)
         y = np.ascontiguousarray(y, np.float64)
         z = np.empty(self.M)
-        self.ctx._check(self._lib.smcb_batch_log_likelihood(self._h, _ptr(p), _ptr(act), _ptr(y), y.size, int(resampler),
-                                                            int(stream0), _ptr(z)))
+        if proposal is None:
+            self.ctx._check(self._lib.smcb_batch_log_likelihood(self._h, _ptr(p), _ptr(act), _ptr(y), y.size, int(resampler),
+                                                                int(stream0), _ptr(z)))
+        else:
+            q = self._proposal(proposal, y.size)
+            self.ctx._check(self._lib.smcb_batch_log_likelihood_guided(self._h, _ptr(p), _ptr(act), _ptr(y), y.size, int(resampler),
+                                                                       int(stream0), _ptr(q), _ptr(z)))
         return z
 
     def gather(self, parents):
@@ -403,6 +450,13 @@ class Batch:
         out = np.empty((self.M, self.d))
         self.ctx._check(self._lib.smcb_batch_weighted_mean(self._h, _ptr(out)))
         return out
+
+    def weighted_moments(self):
+        """([M, d] means, [M, d] population variances) of every cloud under its weights, computed on the device
+        (var(x, weights(w)) per θ-particle, examples/inflation_example.jl:46)."""
+        mean, var = np.empty((self.M, self.d)), np.empty((self.M, self.d))
+        self.ctx._check(self._lib.smcb_batch_weighted_moments(self._h, _ptr(mean), _ptr(var)))
+        return mean, var
 
     def weighted_quantiles(self, probs, weighted=True):
         """[M, d, len(probs)] lower empirical quantiles of every cloud under its own weights (or counting every

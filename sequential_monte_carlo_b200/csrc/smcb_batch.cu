@@ -16,6 +16,7 @@ struct BatchArgs {
   const double* derived;   // [M][8]
   const uint8_t* active;   // [M] or null
   const double* y;         // observations consumed by this launch, y[0] is for time t_begin
+  const double* prop;      // guided kernels only: [t_end - t_begin + 1][M][4] proposal coefficients (SPEC §10), row 0 is for t_begin
   double* x;               // [M][d][ld]
   double* logw;            // [M][ld]
   StepStats* stats;        // [M]
@@ -33,6 +34,14 @@ struct BatchArgs {
   int64_t npad;             // N rounded up to even
 };
 
+// the transition density of the guided kernels; empty for the bootstrap ones
+template <class Model, bool GUIDED>
+struct GuidedDensity : TransDensity<Model> {};
+template <class Model>
+struct GuidedDensity<Model, false> {
+  __device__ __forceinline__ void load(const double*) {}
+};
+
 __device__ __forceinline__ int smem_lower_count(const uint64_t* C, int lo, int hi, uint64_t tau) {
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
@@ -42,9 +51,12 @@ __device__ __forceinline__ int smem_lower_count(const uint64_t* C, int lo, int h
   return lo;
 }
 
-template <class Model, int PAIRS, int MAXT>
+// GUIDED: the move of every step t >= 1 draws from the affine-Gaussian proposal of (t, θ) and the weight carries
+// transition / proposal (particle_filter!, particles.jl:66-80; SPEC §10); D = 1 models only.
+template <class Model, int PAIRS, int MAXT, bool GUIDED>
 __global__ void __launch_bounds__(MAXT) batch_kernel(const BatchArgs a) {
   constexpr int D = Model::D;
+  static_assert(!GUIDED || D == 1, "guided proposals are defined for the one-dimensional models");
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ unsigned long long s_wq[PAIRS][32];
   __shared__ double s_f[3][32];
@@ -70,6 +82,8 @@ __global__ void __launch_bounds__(MAXT) batch_kernel(const BatchArgs a) {
 
   Model mdl;
   mdl.load(a.derived + m * kParamStride);
+  GuidedDensity<Model, GUIDED> fdens;
+  fdens.load(a.derived + m * kParamStride);
   const uint32_t stream = a.stream0 + (uint32_t)m;
   const double logN = log((double)N);
 
@@ -226,6 +240,13 @@ __global__ void __launch_bounds__(MAXT) batch_kernel(const BatchArgs a) {
       }
       __syncthreads();  // C: every parent read before the cloud is overwritten
       // ---- x_i ~ transition(xp_i); logw_i = logpdf(observation(x_i), y)              particles.jl:122-125
+      // (guided: x_i ~ proposal(xp_i); logw_i += logpdf(transition(xp_i), x_i) - logpdf(proposal(xp_i), x_i)   :73-78)
+      double pc[kProposalStride] = {0.0, 0.0, 0.0, 0.0};
+      if constexpr (GUIDED) {
+        const double* g = a.prop + ((int64_t)(t - a.t_begin) * (int64_t)gridDim.x + m) * kProposalStride;
+#pragma unroll
+        for (int k = 0; k < kProposalStride; ++k) pc[k] = g[k];
+      }
 #pragma unroll
       for (int r = 0; r < PAIRS; ++r) {
         const int p = r * nthreads + tid;
@@ -236,13 +257,19 @@ __global__ void __launch_bounds__(MAXT) batch_kernel(const BatchArgs a) {
 #pragma unroll
           for (int k = 0; k < D; ++k)
             normal_pair_at(a.key, (uint32_t)p, stream, t, PURPOSE_TRANSITION, (uint32_t)k, za[k], zb[k]);
-          mdl.transition(za, xpa[r], xa);
-          lw[r][0] = mdl.logweight(xa, y);
+          if constexpr (GUIDED) lw[r][0] = guided_move(mdl, fdens, pc, za[0], xpa[r][0], y, xa);
+          else {
+            mdl.transition(za, xpa[r], xa);
+            lw[r][0] = mdl.logweight(xa, y);
+          }
 #pragma unroll
           for (int k = 0; k < D; ++k) xs[k * ldx + i] = xa[k];
           if (i + 1 < N) {
-            mdl.transition(zb, xpb[r], xb);
-            lw[r][1] = mdl.logweight(xb, y);
+            if constexpr (GUIDED) lw[r][1] = guided_move(mdl, fdens, pc, zb[0], xpb[r][0], y, xb);
+            else {
+              mdl.transition(zb, xpb[r], xb);
+              lw[r][1] = mdl.logweight(xb, y);
+            }
 #pragma unroll
             for (int k = 0; k < D; ++k) xs[k * ldx + i + 1] = xb[k];
           }
@@ -384,6 +411,43 @@ __global__ void __launch_bounds__(256)
   }
 }
 
+// mean[m][c] as above and var[m][c] = Σ_i w_i (x_i − mean)²  (var(x[m], weights(w[m])), the per-θ counterpart of
+// examples/inflation_example.jl:46: population variance, corrected = false); one CTA per (m, c), two passes over
+// the cloud, fixed summation order
+__global__ void __launch_bounds__(256)
+    batch_wmoment_kernel(const double* __restrict__ x, const double* __restrict__ logw, const StepStats* __restrict__ st,
+                         double* __restrict__ mean, double* __restrict__ var, int64_t N, int64_t ld, int d) {
+  __shared__ double sh[8];
+  __shared__ double s_mean;
+  const int64_t m = blockIdx.x;
+  const int c = blockIdx.y;
+  const double mx = st[m].mx;
+  const double* xc = x + (m * d + c) * ld;
+  const double* lw = logw + m * ld;
+  for (int pass = 0; pass < 2; ++pass) {
+    const double mu = pass ? s_mean : 0.0;
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < N; i += 256) {
+      const double e = det_exp(lw[i] - mx);
+      if (e != 0.0) {
+        const double dx = xc[i] - mu;
+        acc += pass ? e * (dx * dx) : e * dx;
+      }
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double t = 0.0;
+      for (int w = 0; w < 8; ++w) t += sh[w];
+      t /= st[m].sum;
+      if (pass) var[m * d + c] = t;
+      else { mean[m * d + c] = t; s_mean = t; }
+    }
+    __syncthreads();
+  }
+}
+
 // q[m][c][j] = weighted (or plain) lower empirical quantile p_j of component c of θ-particle m's cloud (SPEC §8):
 // the per-θ bands of get_quantiles_uc / get_quantiles_ucsv (examples/inflation_example.jl:39-55,241-253).  One
 // CTA per (m, c): fixed-point weights q_i (SPEC §5), exact total, then an 8-pass radix select (one byte per
@@ -487,26 +551,116 @@ __global__ void kalman_kernel(const double* __restrict__ params, const uint8_t* 
   if (sio) sio[m] = S;
 }
 
-template <class Model, int PAIRS, int MAXT>
+// matrix Kalman recursion with a scalar observation, one thread per model          kalman_filter.jl:3-27
+// model block (row-major): A[D][D], B[D], Q[D][D], R, x0[D], Σ0[D][D]  = 3D² + 2D + 1 doubles
+template <int D>
+__global__ void kalman_mv_kernel(const double* __restrict__ models, const uint8_t* __restrict__ active, int64_t M,
+                                 const double* __restrict__ y, int64_t T, int predict_first, double* __restrict__ loglik,
+                                 double* __restrict__ xio, double* __restrict__ sio, int use_state) {
+  const int64_t m = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= M) return;
+  if (active && !active[m]) {
+    loglik[m] = -INFINITY;
+    return;
+  }
+  constexpr int STRIDE = 3 * D * D + 2 * D + 1;
+  const double* P = models + m * STRIDE;
+  double A[D][D], B[D], Q[D][D], x[D], S[D][D];
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    B[i] = P[D * D + i];
+    x[i] = use_state ? xio[m * D + i] : P[2 * D * D + D + 1 + i];
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+      A[i][j] = P[i * D + j];
+      Q[i][j] = P[D * D + D + i * D + j];
+      S[i][j] = use_state ? sio[(m * D + i) * D + j] : P[2 * D * D + 2 * D + 1 + i * D + j];
+    }
+  }
+  const double R = P[2 * D * D + D];
+  double ll = 0.0;
+  for (int64_t t = 0; t < T; ++t) {
+    if (predict_first || t > 0) {
+      double xn[D], AS[D][D];
+#pragma unroll
+      for (int i = 0; i < D; ++i) {  // xt = A*xt                                       :13
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) acc += A[i][j] * x[j];
+        xn[i] = acc;
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          double u = 0.0;
+#pragma unroll
+          for (int j = 0; j < D; ++j) u += A[i][j] * S[j][k];
+          AS[i][k] = u;
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < D; ++i) {  // Σt = A*Σt*A' + Q                                :14
+        x[i] = xn[i];
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+          double u = 0.0;
+#pragma unroll
+          for (int j = 0; j < D; ++j) u += AS[i][j] * A[k][j];
+          S[i][k] = u + Q[i][k];
+        }
+      }
+    }
+    double K[D], bx = 0.0, sig = 0.0;  // K = Σt*B'
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      double u = 0.0;
+#pragma unroll
+      for (int j = 0; j < D; ++j) u += S[i][j] * B[j];
+      K[i] = u;
+      bx += B[i] * x[i];
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) sig += B[i] * K[i];
+    sig += R;                       // σt = B*Σt*B' + R                                  :16
+    const double dy = y[t] - bx;    // Δyt = yt - B*xt                                   :17
+    const double inv = 1.0 / sig;
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      const double g = K[i] * inv;
+      x[i] = x[i] + g * dy;         // xt + (Σt*B')*inv(σt)*Δyt                          :20
+#pragma unroll
+      for (int j = 0; j < D; ++j) S[i][j] = S[i][j] - g * K[j];  // Σt - (Σt*B')*inv(σt)*(B*Σt')  :21
+    }
+    ll += -0.5 * (log(2.0 * M_PI) + log(sig) + (dy * inv * dy));  // :24-26
+  }
+  loglik[m] = ll;
+#pragma unroll
+  for (int i = 0; i < D; ++i) {
+    if (xio) xio[m * D + i] = x[i];
+#pragma unroll
+    for (int j = 0; j < D; ++j)
+      if (sio) sio[(m * D + i) * D + j] = S[i][j];
+  }
+}
+
+template <class Model, int PAIRS, int MAXT, bool GUIDED>
 void launch_batch(const BatchArgs& a, int64_t M, int threads, size_t smem, cudaStream_t stream) {
-  auto kern = batch_kernel<Model, PAIRS, MAXT>;
+  auto kern = batch_kernel<Model, PAIRS, MAXT, GUIDED>;
   SMCB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<(unsigned)M, threads, smem, stream>>>(a);
   SMCB_CUDA_TRY(cudaGetLastError());
 }
 
-template <class Model>
+template <class Model, bool GUIDED = false>
 void launch_batch_model(const BatchArgs& a, int64_t M, int pairs, int threads, size_t smem, cudaStream_t stream) {
   if (pairs == 2) {
-    if (threads <= 256) launch_batch<Model, 2, 256>(a, M, threads, smem, stream);
-    else if (threads <= 512) launch_batch<Model, 2, 512>(a, M, threads, smem, stream);
-    else launch_batch<Model, 2, 1024>(a, M, threads, smem, stream);
+    if (threads <= 256) launch_batch<Model, 2, 256, GUIDED>(a, M, threads, smem, stream);
+    else if (threads <= 512) launch_batch<Model, 2, 512, GUIDED>(a, M, threads, smem, stream);
+    else launch_batch<Model, 2, 1024, GUIDED>(a, M, threads, smem, stream);
   } else if (pairs == 1) {
-    if (threads <= 512) launch_batch<Model, 1, 512>(a, M, threads, smem, stream);
-    else launch_batch<Model, 1, 1024>(a, M, threads, smem, stream);
+    if (threads <= 512) launch_batch<Model, 1, 512, GUIDED>(a, M, threads, smem, stream);
+    else launch_batch<Model, 1, 1024, GUIDED>(a, M, threads, smem, stream);
   } else {
-    if (threads <= 512) launch_batch<Model, 4, 512>(a, M, threads, smem, stream);
-    else launch_batch<Model, 4, 1024>(a, M, threads, smem, stream);
+    if (threads <= 512) launch_batch<Model, 4, 512, GUIDED>(a, M, threads, smem, stream);
+    else launch_batch<Model, 4, 1024, GUIDED>(a, M, threads, smem, stream);
   }
 }
 
@@ -547,6 +701,7 @@ BatchFilter::~BatchFilter() {
     if (ev_[i]) cudaEventDestroy(ev_[i]);
   }
   cudaFree(derived_); cudaFree(active_); cudaFree(y_dev_); cudaFree(out_dev_); cudaFree(w_tmp_); cudaFree(slots_dev_);
+  cudaFree(prop_dev_);
 }
 
 void BatchFilter::begin_call() {
@@ -573,7 +728,34 @@ void BatchFilter::upload_params(const double* params, const uint8_t* active) {
   if (active) SMCB_CUDA_TRY(cudaMemcpyAsync(active_, active, M_, cudaMemcpyHostToDevice, stream_));
 }
 
-void BatchFilter::launch(bool from_init, uint32_t t_begin, uint32_t t_end, int resampler, int64_t) {
+// proposal: [rows][M][3] host coefficients (c0, c1, c2) of x' ~ N(c0 + c1 xp, c2^2); stored as [rows][M][4] with
+// det_log(c2) appended (SPEC §10)
+void BatchFilter::upload_proposal(const double* proposal, int64_t rows) {
+  if (d_ != 1) throw Error{SMCB_ERR_UNSUPPORTED, "guided proposals are defined for the one-dimensional models (LG1D, SV)"};
+  const int64_t n = rows * M_;
+  for (int64_t j = 0; j < n; ++j) {
+    const double c2 = proposal[3 * j + 2];
+    if (!(c2 > 0.0) || !std::isfinite(c2) || !std::isfinite(proposal[3 * j]) || !std::isfinite(proposal[3 * j + 1]))
+      throw Error{SMCB_ERR_BAD_ARG, "proposal: coefficients must be finite and the standard deviation c2 > 0"};
+  }
+  if (prop_cap_ < n) {
+    cudaFree(prop_dev_);
+    prop_dev_ = nullptr;
+    prop_cap_ = 0;
+    SMCB_CUDA_TRY(cudaMalloc(&prop_dev_, sizeof(double) * kProposalStride * n));
+    prop_cap_ = n;
+  }
+  prop_host_.resize((size_t)(kProposalStride * n));
+  for (int64_t j = 0; j < n; ++j) {
+    prop_host_[4 * j + 0] = proposal[3 * j + 0];
+    prop_host_[4 * j + 1] = proposal[3 * j + 1];
+    prop_host_[4 * j + 2] = proposal[3 * j + 2];
+    prop_host_[4 * j + 3] = det_log(proposal[3 * j + 2]);
+  }
+  SMCB_CUDA_TRY(cudaMemcpyAsync(prop_dev_, prop_host_.data(), sizeof(double) * kProposalStride * n, cudaMemcpyHostToDevice, stream_));
+}
+
+void BatchFilter::launch(bool from_init, uint32_t t_begin, uint32_t t_end, int resampler, int64_t, bool guided) {
   const int64_t npairs = (N_ + 1) / 2;
   int pairs = 2;
   if ((npairs + pairs - 1) / pairs > 1024) pairs = 4;
@@ -592,6 +774,7 @@ void BatchFilter::launch(bool from_init, uint32_t t_begin, uint32_t t_end, int r
   a.derived = derived_;
   a.active = use_active_ ? active_ : nullptr;
   a.y = y_dev_;
+  a.prop = guided ? prop_dev_ : nullptr;
   a.x = x_[cur_];
   a.logw = logw_[cur_];
   a.stats = stats_[cur_];
@@ -604,6 +787,13 @@ void BatchFilter::launch(bool from_init, uint32_t t_begin, uint32_t t_end, int r
   a.from_init = from_init ? 1 : 0;
   a.x_in_smem = x_in_smem ? 1 : 0;
   a.npad = npad;
+  if (guided) {
+    if (kind_ == KIND_LG1D) launch_batch_model<ModelLG1D, true>(a, M_, pairs, threads, smem, stream_);
+    else if (kind_ == KIND_SV) launch_batch_model<ModelSV, true>(a, M_, pairs, threads, smem, stream_);
+    else throw Error{SMCB_ERR_UNSUPPORTED, "guided proposals are defined for the one-dimensional models (LG1D, SV)"};
+    ++launches_;
+    return;
+  }
   switch (kind_) {
     case KIND_LG1D: launch_batch_model<ModelLG1D>(a, M_, pairs, threads, smem, stream_); break;
     case KIND_SV: launch_batch_model<ModelSV>(a, M_, pairs, threads, smem, stream_); break;
@@ -636,14 +826,15 @@ void BatchFilter::init(const double* params, const uint8_t* active, double y0, c
   live_ = true;
 }
 
-void BatchFilter::step(const double* params, double y, int resampler, double* logmu, double* ess) {
+void BatchFilter::step(const double* params, double y, int resampler, double* logmu, double* ess, const double* proposal) {
   if (!live_) throw Error{SMCB_ERR_STATE, "batch_step before batch_init / batch_log_likelihood"};
   if (resampler < 0 || resampler > 2) throw Error{SMCB_ERR_BAD_ARG, "unknown resampler"};
   begin_call();
   upload_params(params, nullptr);
   ensure_y(y_dev_, y_cap_, 1);
   SMCB_CUDA_TRY(cudaMemcpyAsync(y_dev_, &y, sizeof(double), cudaMemcpyHostToDevice, stream_));
-  launch(false, t_ + 1, t_ + 1, resampler, 1);
+  if (proposal) upload_proposal(proposal, 1);
+  launch(false, t_ + 1, t_ + 1, resampler, 1, proposal != nullptr);
   t_ += 1;
   if (logmu) SMCB_CUDA_TRY(cudaMemcpyAsync(logmu, out_dev_, sizeof(double) * M_, cudaMemcpyDeviceToHost, stream_));
   if (ess) SMCB_CUDA_TRY(cudaMemcpyAsync(ess, out_dev_ + M_, sizeof(double) * M_, cudaMemcpyDeviceToHost, stream_));
@@ -651,14 +842,15 @@ void BatchFilter::step(const double* params, double y, int resampler, double* lo
 }
 
 void BatchFilter::run(const double* params, const uint8_t* active, const double* y, int64_t T, int resampler,
-                      const RngKey& key, uint32_t stream0, double* logZ) {
+                      const RngKey& key, uint32_t stream0, double* logZ, const double* proposal) {
   if (resampler < 0 || resampler > 2) throw Error{SMCB_ERR_BAD_ARG, "unknown resampler"};
   begin_call();
   upload_params(params, active);
   ensure_y(y_dev_, y_cap_, T);
   SMCB_CUDA_TRY(cudaMemcpyAsync(y_dev_, y, sizeof(double) * T, cudaMemcpyHostToDevice, stream_));
   key_ = key; stream0_ = stream0;
-  launch(true, 0, (uint32_t)(T - 1), resampler, T);
+  if (proposal) upload_proposal(proposal, T);  // row 0 (the initial draw is the bootstrap one) is not read
+  launch(true, 0, (uint32_t)(T - 1), resampler, T, proposal != nullptr);
   t_ = (uint32_t)(T - 1);
   SMCB_CUDA_TRY(cudaMemcpyAsync(logZ, out_dev_, sizeof(double) * M_, cudaMemcpyDeviceToHost, stream_));
   end_call();
@@ -740,6 +932,26 @@ void BatchFilter::weighted_mean(double* mean_host) {
   SMCB_CUDA_TRY(cudaStreamSynchronize(stream_));
 }
 
+void BatchFilter::weighted_moments(double* mean_host, double* var_host) {
+  if (!live_) throw Error{SMCB_ERR_STATE, "no batch state to summarise"};
+  SMCB_CUDA_TRY(cudaSetDevice(device_));
+  double* scratch = nullptr;  // mean[M][d] then var[M][d]
+  const size_t words = (size_t)M_ * d_;
+  SMCB_CUDA_TRY(cudaMalloc(&scratch, sizeof(double) * 2 * words));
+  try {
+    dim3 grid((unsigned)M_, (unsigned)d_);
+    batch_wmoment_kernel<<<grid, 256, 0, stream_>>>(x_[cur_], logw_[cur_], stats_[cur_], scratch, scratch + words, N_, ld_, d_);
+    SMCB_CUDA_TRY(cudaGetLastError());
+    if (mean_host) SMCB_CUDA_TRY(cudaMemcpyAsync(mean_host, scratch, sizeof(double) * words, cudaMemcpyDeviceToHost, stream_));
+    if (var_host) SMCB_CUDA_TRY(cudaMemcpyAsync(var_host, scratch + words, sizeof(double) * words, cudaMemcpyDeviceToHost, stream_));
+    SMCB_CUDA_TRY(cudaStreamSynchronize(stream_));
+  } catch (...) {
+    cudaFree(scratch);
+    throw;
+  }
+  cudaFree(scratch);
+}
+
 void BatchFilter::weighted_quantiles(const double* probs, int np, bool weighted, double* q_host) {
   if (!live_) throw Error{SMCB_ERR_STATE, "no batch state to summarise"};
   if (np < 1 || np > kBatchMaxProbs || !probs || !q_host) throw Error{SMCB_ERR_BAD_ARG, "batch_weighted_quantiles: 1..16 probabilities"};
@@ -811,6 +1023,51 @@ void kalman_batch(int device, cudaStream_t stream, const double* params, const u
     SMCB_CUDA_TRY(cudaMemcpyAsync(loglik, dl, sizeof(double) * M, cudaMemcpyDeviceToHost, stream));
     if (x) SMCB_CUDA_TRY(cudaMemcpyAsync(x, dx, sizeof(double) * M, cudaMemcpyDeviceToHost, stream));
     if (sigma) SMCB_CUDA_TRY(cudaMemcpyAsync(sigma, ds, sizeof(double) * M, cudaMemcpyDeviceToHost, stream));
+    SMCB_CUDA_TRY(cudaStreamSynchronize(stream));
+  } catch (...) {
+    cleanup();
+    throw;
+  }
+  cleanup();
+}
+
+void kalman_mv_batch(int device, cudaStream_t stream, int d, const double* models, const uint8_t* active, int64_t M,
+                     const double* y, int64_t T, bool predict_first, double* loglik, double* x, double* sigma,
+                     bool use_state) {
+  if (d < 1 || d > 4) throw Error{SMCB_ERR_UNSUPPORTED, "matrix Kalman filter: state dimension must be in [1, 4]"};
+  SMCB_CUDA_TRY(cudaSetDevice(device));
+  const int64_t stride = 3 * d * d + 2 * d + 1;
+  double *dp = nullptr, *dy = nullptr, *dl = nullptr, *dx = nullptr, *ds = nullptr;
+  uint8_t* da = nullptr;
+  auto cleanup = [&] { cudaFree(dp); cudaFree(dy); cudaFree(dl); cudaFree(dx); cudaFree(ds); cudaFree(da); };
+  try {
+    SMCB_CUDA_TRY(cudaMalloc(&dp, sizeof(double) * M * stride));
+    SMCB_CUDA_TRY(cudaMalloc(&dy, sizeof(double) * T));
+    SMCB_CUDA_TRY(cudaMalloc(&dl, sizeof(double) * M));
+    SMCB_CUDA_TRY(cudaMalloc(&dx, sizeof(double) * M * d));
+    SMCB_CUDA_TRY(cudaMalloc(&ds, sizeof(double) * M * d * d));
+    SMCB_CUDA_TRY(cudaMemcpyAsync(dp, models, sizeof(double) * M * stride, cudaMemcpyHostToDevice, stream));
+    SMCB_CUDA_TRY(cudaMemcpyAsync(dy, y, sizeof(double) * T, cudaMemcpyHostToDevice, stream));
+    if (active) {
+      SMCB_CUDA_TRY(cudaMalloc(&da, M));
+      SMCB_CUDA_TRY(cudaMemcpyAsync(da, active, M, cudaMemcpyHostToDevice, stream));
+    }
+    if (use_state) {
+      SMCB_CUDA_TRY(cudaMemcpyAsync(dx, x, sizeof(double) * M * d, cudaMemcpyHostToDevice, stream));
+      SMCB_CUDA_TRY(cudaMemcpyAsync(ds, sigma, sizeof(double) * M * d * d, cudaMemcpyHostToDevice, stream));
+    }
+    const unsigned grid = (unsigned)((M + 127) / 128);
+    const int pf = predict_first ? 1 : 0, us = use_state ? 1 : 0;
+    switch (d) {
+      case 1: kalman_mv_kernel<1><<<grid, 128, 0, stream>>>(dp, da, M, dy, T, pf, dl, dx, ds, us); break;
+      case 2: kalman_mv_kernel<2><<<grid, 128, 0, stream>>>(dp, da, M, dy, T, pf, dl, dx, ds, us); break;
+      case 3: kalman_mv_kernel<3><<<grid, 128, 0, stream>>>(dp, da, M, dy, T, pf, dl, dx, ds, us); break;
+      default: kalman_mv_kernel<4><<<grid, 128, 0, stream>>>(dp, da, M, dy, T, pf, dl, dx, ds, us); break;
+    }
+    SMCB_CUDA_TRY(cudaGetLastError());
+    SMCB_CUDA_TRY(cudaMemcpyAsync(loglik, dl, sizeof(double) * M, cudaMemcpyDeviceToHost, stream));
+    if (x) SMCB_CUDA_TRY(cudaMemcpyAsync(x, dx, sizeof(double) * M * d, cudaMemcpyDeviceToHost, stream));
+    if (sigma) SMCB_CUDA_TRY(cudaMemcpyAsync(sigma, ds, sizeof(double) * M * d * d, cudaMemcpyDeviceToHost, stream));
     SMCB_CUDA_TRY(cudaStreamSynchronize(stream));
   } catch (...) {
     cleanup();

@@ -24,10 +24,12 @@ class BatchFilter {
   void init(const double* params, const uint8_t* active, double y0, const RngKey& key, uint32_t stream0,
             double* logmu, double* ess);
   // M × bootstrap_filter!(x[m], w[m], y, model(θ_m))              smc_samplers.jl:325-335
-  void step(const double* params, double y, int resampler, double* logmu, double* ess);
+  // proposal != null: M × particle_filter!(x[m], w[m], y, model(θ_m), proposal_m)  particles.jl:55-84 (SPEC §10);
+  // proposal is [M][3] = (c0, c1, c2) of x' ~ N(c0 + c1 xp, c2²)
+  void step(const double* params, double y, int resampler, double* logmu, double* ess, const double* proposal = nullptr);
   // M × log_likelihood(N, y, model(θ_m))                          smc_samplers.jl:117-121,223-229
   void run(const double* params, const uint8_t* active, const double* y, int64_t T, int resampler,
-           const RngKey& key, uint32_t stream0, double* logZ);
+           const RngKey& key, uint32_t stream0, double* logZ, const double* proposal = nullptr);  // proposal: [T][M][3]
 
   void gather(const int32_t* parents);                             // smc_samplers.jl:74-84
   void accept_from(const BatchFilter& prop, const uint8_t* accept);  // smc_samplers.jl:130-133
@@ -35,6 +37,8 @@ class BatchFilter {
   // [M][d][np]: lower empirical quantiles of every cloud under its weights (weighted) or counting particles once (SPEC §8)
   void weighted_quantiles(const double* probs, int np, bool weighted, double* q_host);
   void weighted_mean(double* mean_host);  // [M][d]: w[m]' x[m], computed on the device (plotting_utils.jl:116-124,150)
+  // [M][d] each: mean and population variance of every cloud under its weights (var(x, weights(w)), inflation_example.jl:46)
+  void weighted_moments(double* mean_host, double* var_host);
   int64_t cloud_bytes() const;
   void pack(const int32_t* slots, int64_t n, void* buf_dev, bool to_buffer);
 
@@ -45,7 +49,8 @@ class BatchFilter {
 
  private:
   void upload_params(const double* params, const uint8_t* active);
-  void launch(bool from_init, uint32_t t_begin, uint32_t t_end, int resampler, int64_t y_count);
+  void launch(bool from_init, uint32_t t_begin, uint32_t t_end, int resampler, int64_t y_count, bool guided = false);
+  void upload_proposal(const double* proposal, int64_t rows);
   void begin_call();
   void end_call();
   void upload_slots(const int32_t* a, const int32_t* b, int64_t n);
@@ -76,6 +81,9 @@ class BatchFilter {
   int32_t* slots_dev_ = nullptr;  // [2][slot_cap_]
   int64_t slot_cap_ = 0;
   std::vector<double> host_tmp_;
+  double* prop_dev_ = nullptr;  // [rows][M][4] proposal coefficients of the guided launches
+  int64_t prop_cap_ = 0;
+  std::vector<double> prop_host_;
 
   cudaEvent_t ev_[2] = {nullptr, nullptr};
   double last_ms_ = 0;
@@ -87,5 +95,13 @@ class BatchFilter {
 void kalman_batch(int device, cudaStream_t stream, const double* params, const uint8_t* active, int64_t M,
                   const double* y, int64_t T, bool predict_first, double* loglik, double* x, double* sigma,
                   bool use_state);
+
+
+// kalman_filter / log_likelihood(y, model) for M multivariate LinearModels with a scalar observation
+// (MultivariateLinearGaussian, hodrick_prescott: state_space_models.jl:137-202; kalman_filter.jl:3-27,55-70).
+// models: [M][3d² + 2d + 1] = A[d][d], B[d], Q[d][d], R, x0[d], Σ0[d][d] row-major; x: [M][d], sigma: [M][d][d].
+void kalman_mv_batch(int device, cudaStream_t stream, int d, const double* models, const uint8_t* active, int64_t M,
+                     const double* y, int64_t T, bool predict_first, double* loglik, double* x, double* sigma,
+                     bool use_state);
 
 }  // namespace smcb

@@ -304,6 +304,26 @@ int smcb_batch_log_likelihood(smcb_batch* b, const double* params, const uint8_t
   });
 }
 
+int smcb_batch_step_guided(smcb_batch* b, const double* params, double y, int resampler, const double* proposal,
+                           double* logmu, double* ess) {
+  if (!b) return SMCB_ERR_BAD_ARG;
+  return guarded(b->ctx, [&] {
+    need(proposal != nullptr, "batch_step_guided: proposal is null (use smcb_batch_step for the bootstrap filter)");
+    b->impl->step(params, y, resampler, logmu, ess, proposal);
+  });
+}
+
+int smcb_batch_log_likelihood_guided(smcb_batch* b, const double* params, const uint8_t* active, const double* y,
+                                     int64_t T, int resampler, uint32_t stream0, const double* proposal, double* logZ) {
+  if (!b) return SMCB_ERR_BAD_ARG;
+  smcb_ctx* ctx = b->ctx;
+  return guarded(ctx, [&] {
+    need(params && y && T >= 1 && logZ && proposal, "batch_log_likelihood_guided: params, y, proposal, logZ must be non-null and T >= 1");
+    b->impl->run(params, active, y, T, resampler, ctx->key(ctx->next_epoch), stream0, logZ, proposal);
+    ctx->next_epoch = (ctx->next_epoch + 1) & 0xFFFFFFu;
+  });
+}
+
 int smcb_batch_gather(smcb_batch* b, const int32_t* parents) {
   if (!b) return SMCB_ERR_BAD_ARG;
   return guarded(b->ctx, [&] {
@@ -333,6 +353,11 @@ int smcb_batch_weighted_quantiles(smcb_batch* b, const double* probs, int nprobs
 int smcb_batch_weighted_mean(smcb_batch* b, double* mean) {
   if (!b || !mean) return SMCB_ERR_BAD_ARG;
   return guarded(b->ctx, [&] { b->impl->weighted_mean(mean); });
+}
+
+int smcb_batch_weighted_moments(smcb_batch* b, double* mean, double* var) {
+  if (!b || (!mean && !var)) return SMCB_ERR_BAD_ARG;
+  return guarded(b->ctx, [&] { b->impl->weighted_moments(mean, var); });
 }
 
 int64_t smcb_batch_cloud_bytes(const smcb_batch* b) { return b ? b->impl->cloud_bytes() : 0; }
@@ -378,6 +403,26 @@ int smcb_kalman_batch_loglik(smcb_ctx* ctx, const double* params, const uint8_t*
     need(params && y && loglik && M >= 1 && T >= 1, "kalman_batch_loglik: bad arguments");
     kalman_batch(ctx->device, ctx->stream, params, active, M, y, T, /*predict_first=*/!matched_init, loglik, x, sigma,
                  /*use_state=*/false);
+  });
+}
+
+int smcb_kalman_mv_batch_step(smcb_ctx* ctx, int d, const double* models, int64_t M, double y, double* x, double* sigma,
+                              double* loglik) {
+  if (!ctx) return SMCB_ERR_BAD_ARG;
+  return guarded(ctx, [&] {
+    need(models && x && sigma && loglik && M >= 1, "kalman_mv_batch_step: bad arguments");
+    kalman_mv_batch(ctx->device, ctx->stream, d, models, nullptr, M, &y, 1, /*predict_first=*/true, loglik, x, sigma,
+                    /*use_state=*/true);
+  });
+}
+
+int smcb_kalman_mv_batch_loglik(smcb_ctx* ctx, int d, const double* models, const uint8_t* active, int64_t M,
+                                const double* y, int64_t T, int matched_init, double* loglik, double* x, double* sigma) {
+  if (!ctx) return SMCB_ERR_BAD_ARG;
+  return guarded(ctx, [&] {
+    need(models && y && loglik && M >= 1 && T >= 1, "kalman_mv_batch_loglik: bad arguments");
+    kalman_mv_batch(ctx->device, ctx->stream, d, models, active, M, y, T, /*predict_first=*/!matched_init, loglik, x, sigma,
+                    /*use_state=*/false);
   });
 }
 

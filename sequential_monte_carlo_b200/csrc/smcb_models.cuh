@@ -34,11 +34,13 @@ SMCB_HD void derive_params(int kind, const double* P, double* D) {
     D[4] = sqrt(P[5]);
     D[5] = 1.0 / sr;
     D[6] = -(det_log(sr) + SMCB_HALF_LOG_2PI);
+    D[7] = det_log(D[2]);  // log sd of the transition kernel: guided weights only (SPEC §10)
   } else if (kind == KIND_SV) {
     D[0] = P[0];
     D[1] = P[1];
     D[2] = P[2];
     D[3] = P[2] / sqrt(1.0 - P[1] * P[1]);
+    D[4] = det_log(P[2]);  // log sd of the transition kernel: guided weights only (SPEC §10)
   } else {
     D[0] = P[0];
     D[1] = P[1];
@@ -105,5 +107,39 @@ struct ModelUCSV {
     return fma(-0.5 * (d * d), det_exp(-x[2]), -(fma(0.5, x[2], SMCB_HALF_LOG_2PI)));
   }
 };
+
+// ---- guided particle filter (particle_filter! with a proposal, particles.jl:66-80; SPEC §10) ----------------
+// The transition kernel of the D = 1 models as a density: mean, sd, log sd.  Kept out of the model structs so
+// that the bootstrap kernels carry no extra members.
+template <class Model>
+struct TransDensity;
+template <>
+struct TransDensity<ModelLG1D> {
+  double sd, lsd;
+  SMCB_HD void load(const double* d) { sd = d[2]; lsd = d[7]; }
+  SMCB_HD double mean(const ModelLG1D& m, double xp) const { return m.A * xp; }
+};
+template <>
+struct TransDensity<ModelSV> {
+  double sd, lsd;
+  SMCB_HD void load(const double* d) { sd = d[2]; lsd = d[4]; }
+  SMCB_HD double mean(const ModelSV& m, double xp) const { return fma(m.rho, xp - m.mu, m.mu); }
+};
+
+constexpr int kProposalStride = 4;  // c0, c1, c2, det_log(c2): the proposal x' ~ N(c0 + c1 xp, c2^2) of one (t, θ)
+
+// x' = rand(proposal(xp)); logw = logpdf(observation(x'), y) + logpdf(transition(xp), x') - logpdf(proposal(xp), x')
+// (particles.jl:73-78; the two 0.5 log 2π cancel).  z is the standard normal the bootstrap transition would consume.
+template <class Model>
+SMCB_HD double guided_move(const Model& mdl, const TransDensity<Model>& f, const double* pc, double z, double xp, double y,
+                           double* x) {
+  const double mq = fma(pc[1], xp, pc[0]);
+  x[0] = fma(pc[2], z, mq);
+  const double zt = (x[0] - f.mean(mdl, xp)) / f.sd;
+  const double zq = (x[0] - mq) / pc[2];
+  const double lf = fma(-0.5 * zt, zt, -f.lsd);
+  const double lq = fma(-0.5 * zq, zq, -pc[3]);
+  return mdl.logweight(x, y) + (lf - lq);
+}
 
 }  // namespace smcb

@@ -5,6 +5,8 @@
     bootstrap_filter(N, y, model)      -> (x, w, logμ)          particles.jl:87-105
     bootstrap_filter_(x, w, y, model)  -> (logμ, w, ess)        particles.jl:107-129  (Julia: bootstrap_filter!)
     log_likelihood(N, y, model)        -> (x, w, logZ)          particles.jl:132-147
+    particle_filter(N, y, model, proposal) / particle_filter_(x, w, y, model, proposal)   particles.jl:28-84
+                                       guided filter, affine-Gaussian proposals on the device (docs/SPEC.md §10)
 
 `x` and `w` are handles on the device-resident cloud: they behave like numpy arrays
 (np.asarray, indexing, quantiles) and copy to the host only when read.  All compute is CUDA; there
@@ -121,23 +123,117 @@ def bootstrap_filter_(states, weights, y, model, *, resampler="multinomial"):
     return logmu, _DeviceArray(ctx, ctx._gen, "w"), ess
 
 
+class AffineGaussianProposal:
+    """The proposal family the device evaluates (docs/SPEC.md §10): x' ~ N(c0 + c1·xp, c2²), c2 > 0.  Stands in for the
+    reference's closure `proposal(model, xp) -> distribution` (particles.jl:73,78).  Called as proposal(model, y) it
+    returns the coefficients (c0, c1, c2) of the step that assimilates y; subclass or pass any callable with that
+    signature for a proposal that looks at the observation."""
+
+    def __init__(self, c0, c1, c2):
+        self.c0, self.c1, self.c2 = float(c0), float(c1), float(c2)
+
+    def __call__(self, model, y):
+        return self.c0, self.c1, self.c2
+
+
+def locally_optimal_proposal(model, y):
+    """p(x' | xp, y) of a univariate LinearModel, the variance-optimal proposal: precision 1/Q + B²/R, mean
+    s²(A·xp/Q + B·y/R).  Use as `particle_filter_(x, w, y, model, locally_optimal_proposal)`."""
+    A, B, Q, R = (float(v) for v in np.asarray(model.params(), np.float64).ravel()[:4])
+    s2 = 1.0 / (1.0 / Q + B * B / R)
+    return s2 * B * float(y) / R, s2 * A / Q, float(np.sqrt(s2))
+
+
+class _GuidedCloud:
+    """x or w of a guided filter: the cloud lives in a one-θ batch on the device (guided filters run on the batched
+    engine, N <= 8192) and is copied to the host only when read."""
+
+    def __init__(self, batch, which):
+        self._batch, self._which, self._host, self._host_t = batch, which, None, -1
+
+    def numpy(self):
+        t = getattr(self._batch, "_t", 0)
+        if self._host is None or self._host_t != t:
+            x, w, _ = self._batch.fetch(want_x=self._which == "x", want_w=self._which == "w")
+            self._host = x[0, 0] if self._which == "x" else w[0]
+            self._host_t = t
+        return self._host
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.numpy()
+        return a if dtype is None else a.astype(dtype)
+
+    def __getitem__(self, i):
+        return self.numpy()[i]
+
+    def __len__(self):
+        return self._batch.N
+
+    @property
+    def shape(self):
+        return (self._batch.N,)
+
+
+def _proposal_coefficients(proposal, model, y):
+    c = proposal(model, y) if callable(proposal) else proposal
+    c = np.asarray(c, np.float64).ravel()
+    if c.size != 3:
+        raise TypeError("proposal must be an AffineGaussianProposal or a callable (model, y) -> (c0, c1, c2) "
+                        "describing x' ~ N(c0 + c1·xp, c2²) (docs/SPEC.md §10); arbitrary closures cannot run on the device")
+    return c
+
+
 def particle_filter(N, y, model, proposal=None, *, ctx=None, stream=0):
     """x, w, logμ = particle_filter(N, y[1], model, proposal)  — particles.jl:28-51.  With proposal = nothing
-    (the only form the reference's own example uses, examples/inflation_example.jl:164,178) the initial step IS
-    the bootstrap one: it draws from initial_dist and weights by the observation density.  A guided proposal
-    functor (particles.jl:73-78, inconsistent in the reference: `proposal(model, xp)` vs `proposal(xp)`) is not
-    built: NotImplementedError, never a silent bootstrap run."""
-    if proposal is not None:
-        raise NotImplementedError("guided proposals (particles.jl:73-78) are not built; pass proposal=None for the bootstrap filter")
-    return bootstrap_filter(N, y, model, ctx=ctx, stream=stream)
+    (the form the reference's own example uses, examples/inflation_example.jl:164,178) this is bootstrap_filter.
+    With a proposal the initial step is STILL the bootstrap one — it draws from initial_dist and weights by the
+    observation density (:40-42; the "+ logpdf(initial_dist, x)" of :44 has lost its "- logpdf(proposal)" partner,
+    commented out at :45, and is ruled a defect, docs/SPEC.md §10) — but the cloud is placed on the batched engine
+    so that particle_filter_ can continue it with guided moves (one-dimensional models, N <= 8192)."""
+    if proposal is None:
+        return bootstrap_filter(N, y, model, ctx=ctx, stream=stream)
+    ctx = ctx or default_context()
+    if model.kind not in (_lib.LG1D, _lib.SV):
+        raise NotImplementedError("guided proposals are built for the one-dimensional models (LinearModel, StochasticVolatility)")
+    b = ctx.batch(model.kind, 1, int(N))
+    logmu, _ = b.init(np.asarray(model.params(), np.float64).reshape(1, -1), float(y), stream0=stream)
+    b._t = 0
+    return _GuidedCloud(b, "x"), _GuidedCloud(b, "w"), float(logmu[0])
 
 
 def particle_filter_(states, weights, y, model, proposal=None, *, resampler="multinomial"):
-    """logμ, w, ess = particle_filter!(x, w, y[t], model, proposal)  — particles.jl:53-84; proposal = nothing is
-    bootstrap_filter! (the reference would call `nothing(model, x)` there, particles.jl:73)."""
-    if proposal is not None:
-        raise NotImplementedError("guided proposals (particles.jl:73-78) are not built; pass proposal=None for the bootstrap filter")
-    return bootstrap_filter_(states, weights, y, model, resampler=resampler)
+    """logμ, w, ess = particle_filter!(x, w, y[t], model, proposal)  — particles.jl:53-84.  proposal = nothing is
+    bootstrap_filter! (the reference would call `nothing(model, x)` there, :73).  Otherwise x' ~ proposal and
+    logw = logpdf(observation(x'), y) + logpdf(transition(xp), x') - logpdf(proposal(xp), x')  (:73-78), evaluated on the
+    device for the affine-Gaussian family (AffineGaussianProposal, locally_optimal_proposal)."""
+    if proposal is None:
+        if isinstance(states, _GuidedCloud):
+            b = states._batch
+            lm, es = b.step(float(y), resampler_id(resampler), np.asarray(model.params(), np.float64).reshape(1, -1))
+            b._t += 1
+            return float(lm[0]), _GuidedCloud(b, "w"), float(es[0])
+        return bootstrap_filter_(states, weights, y, model, resampler=resampler)
+    if not isinstance(states, _GuidedCloud):
+        raise RuntimeError("guided steps continue a cloud created by particle_filter(N, y, model, proposal)")
+    b = states._batch
+    c = _proposal_coefficients(proposal, model, y)
+    lm, es = b.step(float(y), resampler_id(resampler), np.asarray(model.params(), np.float64).reshape(1, -1), proposal=c.reshape(1, 3))
+    b._t += 1
+    return float(lm[0]), _GuidedCloud(b, "w"), float(es[0])
+
+
+def guided_log_likelihood(N, y, model, proposal, *, resampler="multinomial", ctx=None, stream=0):
+    """x, w, logZ of the guided filter over the whole series in ONE launch (the loop of
+    examples/inflation_example.jl:164-171 with a proposal): bootstrap initial step, guided steps for t >= 2."""
+    ctx = ctx or default_context()
+    y = np.asarray(y, np.float64)
+    if model.kind not in (_lib.LG1D, _lib.SV):
+        raise NotImplementedError("guided proposals are built for the one-dimensional models (LinearModel, StochasticVolatility)")
+    prop = np.stack([_proposal_coefficients(proposal, model, yt) for yt in y]).reshape(y.size, 1, 3)
+    b = ctx.batch(model.kind, 1, int(N))
+    z = b.log_likelihood(np.asarray(model.params(), np.float64).reshape(1, -1), y, resampler_id(resampler), stream0=stream, proposal=prop)
+    b._t = y.size - 1
+    return _GuidedCloud(b, "x"), _GuidedCloud(b, "w"), float(z[0])
 
 
 def quantile(x, w_or_p, p=None):

@@ -233,6 +233,14 @@ def state_means(smc):
     return smc.comm.all_gather(smc._cur.weighted_mean())
 
 
+def state_variances(smc):
+    """([M, d] means, [M, d] variances): `mean(smc.x[m], weights(smc.w[m]))`, `var(smc.x[m], weights(smc.w[m]))` of every
+    θ-particle's cloud (the per-θ counterpart of examples/inflation_example.jl:46; population variance), computed on the
+    device(s); the clouds are not read back."""
+    mean, var = smc._cur.weighted_moments()
+    return smc.comm.all_gather(mean), smc.comm.all_gather(var)
+
+
 def state_quantiles(smc, p, weighted=True):
     """[M, d, len(p)]: `quantile(smc.x[m], weights(smc.w[m]), p)` (weighted) or `quantile(smc.x[m], p)` of every
     θ-particle's cloud (examples/inflation_example.jl:44,250), computed on the device(s) by a per-cloud radix

@@ -101,6 +101,49 @@ def unobserved_components(σε=None, ση=None, x0=0.0, **kw):
 UC = unobserved_components  # examples/inflation_example.jl:28-31
 
 
+class MultivariateLinearModel(StateSpaceModel):
+    """LinearModel with a vector state and a scalar observation (state_space_models.jl:137-186):
+    x[t] ~ N(A x[t-1], Q), y[t] ~ N(B x[t], R), x[0] ~ N(X0, Σ0).  Served by the matrix Kalman filter on the device
+    (kalman_filter.kalman_filter / log_likelihood, kalman_filter.jl:3-27,55-70; state dimension <= 4).  It has no
+    particle-filter functor: `kind` is None, so the particle filters refuse it (the reference's own PF cannot run the
+    one multivariate model it ships either — hodrick_prescott's Q is singular and MvNormal(A*x, Q) throws)."""
+    kind = None
+
+    def __init__(self, A, B, Q, R, X0=None, Σ0=None):
+        self.A = np.atleast_2d(np.asarray(A, np.float64))
+        d = self.A.shape[0]
+        if self.A.shape != (d, d) or not 1 <= d <= 4:
+            raise ValueError("A must be square with 1 <= d <= 4")
+        self.B = np.asarray(B, np.float64).reshape(1, d)
+        self.Q = np.asarray(Q, np.float64).reshape(d, d)
+        self.R = np.asarray(R, np.float64).reshape(1)
+        self.x0 = np.zeros(d) if X0 is None else np.asarray(X0, np.float64).reshape(d)
+        self.σ0 = np.eye(d) if Σ0 is None else np.asarray(Σ0, np.float64).reshape(d, d)
+        self.state_dim = d
+
+    def block(self):
+        """[3d² + 2d + 1] row-major block A, B, Q, R, x0, Σ0 (include/smcb200.h, smcb_kalman_mv_batch_*)"""
+        return np.concatenate([self.A.ravel(), self.B.ravel(), self.Q.ravel(), self.R, self.x0, self.σ0.ravel()])
+
+    def params(self):
+        raise NotImplementedError("multivariate linear models are served by the Kalman filter only (no particle-filter functor)")
+
+    def __repr__(self):
+        return f"MultivariateLinearModel(d={self.state_dim})"
+
+
+def MultivariateLinearGaussian(*, A, B, Q, R, X0=None, Σ0=None):
+    """state_space_models.jl:137-154"""
+    return MultivariateLinearModel(A, B, Q, R, X0, Σ0)
+
+
+def hodrick_prescott(*, λ, y, init_cov=1000.0):
+    """Hodrick–Prescott trend model (state_space_models.jl:187-202): x[t] ~ N(2x[t-1] - x[t-2], 1/λ), y[t] ~ N(x[t], 1)"""
+    y = np.asarray(y, np.float64)
+    return MultivariateLinearGaussian(A=[[2.0, -1.0], [1.0, 0.0]], B=[1.0, 0.0], Q=[[1.0 / float(λ), 0.0], [0.0, 0.0]], R=[1.0],
+                                      X0=[3 * y[0] - 2 * y[1], 2 * y[0] - y[1]], Σ0=float(init_cov) * np.eye(2))
+
+
 class UCSV(StateSpaceModel):
     """struct UCSV (state_space_models.jl:215-259): state (x, log σε, log ση).
     `UCSV(γ, x0, (log_σε, log_ση))`; a scalar γ is used for both volatilities (example spelling,

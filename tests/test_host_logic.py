@@ -159,12 +159,17 @@ def test_model_constructors():
     assert x.shape == (50, 3) and y.shape == (50,)
 
 
-def test_particle_filter_refuses_guided_proposals():
-    """particle_filter / particle_filter! (particles.jl:28-84) exist with the reference's signature; only the
-    proposal = nothing form (≡ bootstrap, the one the reference's example uses) is built, and a guided
-    proposal is refused loudly rather than run as a bootstrap filter."""
+def test_particle_filter_refuses_what_it_cannot_run_on_the_device():
+    """particle_filter / particle_filter! (particles.jl:28-84) exist with the reference's signature.  Guided moves are
+    built for the affine-Gaussian family on the one-dimensional models (docs/SPEC.md §10); anything else is refused
+    loudly rather than run as a bootstrap filter — before any device work."""
+    ucsv = smc.UCSV(0.2, 3.0, (1.0, 1.0))
+    with pytest.raises(NotImplementedError):
+        smc.particle_filter(16, 0.1, ucsv, proposal=smc.AffineGaussianProposal(0.0, 1.0, 1.0), ctx=object())
     m = smc.StateSpaceModel(smc.LinearGaussian(0.5, 1.0, 0.9, 0.8, 0.0), (1, 1))
-    with pytest.raises(NotImplementedError):
-        smc.particle_filter(16, 0.1, m, proposal=lambda model, x: None)
-    with pytest.raises(NotImplementedError):
-        smc.particle_filter_(None, None, 0.1, m, proposal=lambda model, x: None)
+    with pytest.raises(RuntimeError):      # a guided step continues a cloud made by particle_filter(..., proposal)
+        smc.particle_filter_(None, None, 0.1, m, proposal=smc.locally_optimal_proposal)
+    from sequential_monte_carlo_b200.particles import _proposal_coefficients
+    with pytest.raises(TypeError):         # an arbitrary closure returning a distribution cannot run on the device
+        _proposal_coefficients(lambda model, y: (0.0, 1.0), m, 0.1)
+    np.testing.assert_allclose(_proposal_coefficients(smc.AffineGaussianProposal(1, 2, 3), m, 0.1), [1, 2, 3])

@@ -1,0 +1,287 @@
+"""SURVEY §8(f) rows N3 / N4 and the per-θ variances:
+
+  * guided particle filter (particle_filter / particle_filter! with a proposal, /root/reference/src/particles.jl:28-84;
+    docs/SPEC.md §10) — the oracle's restatement pinned on the CPU (a proposal equal to the transition IS the
+    bootstrap filter; the locally optimal proposal targets the matched-init Kalman likelihood with a smaller
+    variance), the CUDA path bit-exact against it on the GPU through the C ABI;
+  * matrix Kalman filter (MultivariateLinearGaussian / hodrick_prescott, state_space_models.jl:137-202;
+    kalman_filter.jl:3-27,55-70) — oracle against a numpy restatement on the CPU, CUDA against the oracle on the GPU;
+  * per-θ weighted means / variances of the clouds (var(x, weights(w)), examples/inflation_example.jl:46).
+
+This file sorts last on purpose: these kernels were added after the round's last full GPU run.
+"""
+import numpy as np
+import pytest
+
+import sequential_monte_carlo_b200 as smc
+
+LG = [0.5, 1.0, 0.9, 0.8, 0.0, 1.0]
+SVP = [-1.0, 0.9, 0.3]
+RTOL = 1e-10
+
+
+def _lg_thetas(M, rng):
+    return np.stack([rng.uniform(-0.9, 0.9, M), np.ones(M), rng.uniform(0.3, 2, M), rng.uniform(0.3, 2, M), np.zeros(M), np.ones(M)], 1)
+
+
+def _sv_thetas(M, rng):
+    return np.stack([rng.normal(-1, 0.5, M), rng.uniform(0.5, 0.98, M), rng.uniform(0.1, 0.6, M)], 1)
+
+
+def _stable(rng, d):
+    A = rng.standard_normal((d, d))
+    return 0.9 * A / np.linalg.norm(A, 2)          # spectral norm 0.9: a stable transition
+
+
+def _numpy_kalman(A, B, Q, R, x, S, y, matched_init=False):
+    A, B, Q = np.asarray(A, float), np.asarray(B, float).reshape(1, -1), np.asarray(Q, float)
+    x, S, ll = np.asarray(x, float).copy(), np.asarray(S, float).copy(), 0.0
+    for t, yt in enumerate(y):
+        if not (matched_init and t == 0):
+            x, S = A @ x, A @ S @ A.T + Q
+        sig = (B @ S @ B.T)[0, 0] + R
+        dy = yt - (B @ x)[0]
+        K = (S @ B.T)[:, 0]
+        x, S = x + K / sig * dy, S - np.outer(K, K) / sig
+        ll += -0.5 * (np.log(2 * np.pi) + np.log(sig) + dy * dy / sig)
+    return x, S, ll
+
+
+# ------------------------------------------------------------------------------------------------ CPU: oracle pinned
+def test_oracle_guided_with_transition_proposal_is_bootstrap(oracle):
+    """q = f: same draws, same states, and transition − proposal cancels exactly (SPEC §10)"""
+    for kind, th, coef in ((oracle.KIND_LG1D, LG, [0.0, 0.5, np.sqrt(0.9)]), (oracle.KIND_SV, SVP, [-1.0 * (1 - 0.9), 0.9, 0.3])):
+        _, y = oracle.simulate(kind, th, 40, 11)
+        prop = np.tile(coef, (y.size, 1))
+        g = oracle.guided_log_likelihood(kind, th, 600, y, oracle.SYSTEMATIC, prop, 3, 1, 2)
+        b = oracle.log_likelihood(kind, th, 600, y, oracle.SYSTEMATIC, 3, 1, 2)
+        if kind == oracle.KIND_LG1D:
+            np.testing.assert_array_equal(g["x"], b["x"])
+            assert g["logZ"] == b["logZ"]
+        else:  # SV: μ + ρ(xp − μ) and c0 + c1 xp round differently; the clouds agree to rounding until a resample splits them
+            np.testing.assert_allclose(g["logmu"][:3], b["logmu"][:3], rtol=1e-9)
+
+
+def test_oracle_guided_optimal_proposal_targets_kalman(oracle):
+    """E[Ẑ] = Z for any proposal; the locally optimal one has a much smaller variance than the bootstrap filter"""
+    _, y = oracle.simulate(oracle.KIND_LG1D, LG, 100, 1998)
+    prop = np.array([oracle.optimal_proposal_lg(LG, yt) for yt in y])
+    _, _, kll = oracle.kalman_loglik(LG, y, matched_init=True)
+    g = np.array([oracle.guided_log_likelihood(0, LG, 1024, y, oracle.SYSTEMATIC, prop, s)["logZ"] for s in range(24)])
+    b = np.array([oracle.log_likelihood(0, LG, 1024, y, oracle.SYSTEMATIC, s)["logZ"] for s in range(24)])
+    assert g.std() < 0.5 * b.std()
+    lme = np.log(np.mean(np.exp(g - g.max()))) + g.max()          # log-mean-exp of the unbiased estimates
+    assert abs(lme - kll) < 4 * g.std() / np.sqrt(g.size) + 0.02
+    with pytest.raises(ValueError):
+        oracle.guided_step(oracle.KIND_UCSV, [0.2, 0.2, 3, 1, 1], np.zeros((3, 8)), np.zeros(8), 0.0, 1, 0, [0, 1, 1], 1)
+
+
+def test_oracle_matrix_kalman(oracle):
+    """smco_kalman_mv_* against numpy matrix algebra; d = 1 reproduces the scalar recursion; Hodrick–Prescott block"""
+    _, y = oracle.simulate(oracle.KIND_LG1D, LG, 80, 5)
+    blk = oracle.mv_block([[0.5]], [1.0], [[0.9]], [0.8], [0.0], [[1.0]])
+    for matched in (False, True):
+        assert oracle.kalman_mv_loglik(1, blk, y, matched)[2] == pytest.approx(oracle.kalman_loglik(LG, y, matched)[2], rel=1e-13)
+    rng = np.random.default_rng(0)
+    for d in (2, 3, 4):
+        A = _stable(rng, d)
+        G = rng.standard_normal((d, d))
+        Q, S0 = G @ G.T + 0.1 * np.eye(d), np.eye(d) * 2.0
+        B, R, x0 = rng.standard_normal(d), 0.7, rng.standard_normal(d)
+        blk = oracle.mv_block(A, B, Q, [R], x0, S0)
+        for matched in (False, True):
+            x, S, ll = oracle.kalman_mv_loglik(d, blk, y, matched)
+            xn, Sn, lln = _numpy_kalman(A, B, Q, R, x0, S0, y, matched)
+            assert ll == pytest.approx(lln, rel=1e-11)
+            np.testing.assert_allclose(x, xn, rtol=1e-9, atol=1e-12)
+            np.testing.assert_allclose(S, Sn, rtol=1e-9, atol=1e-12)
+    hp = smc.hodrick_prescott(λ=1600.0, y=y)
+    x, S, ll = oracle.kalman_mv_loglik(2, hp.block(), y)
+    xn, Sn, lln = _numpy_kalman(hp.A, hp.B, hp.Q, hp.R[0], hp.x0, hp.σ0, y)
+    assert ll == pytest.approx(lln, rel=1e-11)
+    np.testing.assert_allclose(x, xn, rtol=1e-8)
+
+
+def test_host_mirror_of_the_new_models_and_proposals():
+    y = np.arange(6.0) ** 1.5
+    hp = smc.hodrick_prescott(λ=1600.0, y=y)
+    assert hp.state_dim == 2 and hp.block().shape == (17,)
+    np.testing.assert_array_equal(hp.A, [[2.0, -1.0], [1.0, 0.0]])                 # state_space_models.jl:195
+    np.testing.assert_array_equal(hp.x0, [3 * y[0] - 2 * y[1], 2 * y[0] - y[1]])    # :199
+    assert hp.Q[0, 0] == 1 / 1600.0 and hp.σ0[1, 1] == 1000.0
+    m = smc.MultivariateLinearGaussian(A=np.eye(3), B=[1, 0, 0], Q=np.eye(3), R=[2.0])
+    np.testing.assert_array_equal(m.x0, np.zeros(3))                               # X0 = zeros, Σ0 = I  :137
+    np.testing.assert_array_equal(m.σ0, np.eye(3))
+    with pytest.raises(NotImplementedError):
+        m.params()
+    lg = smc.LinearGaussian(0.5, 1.0, 0.9, 0.8)
+    c0, c1, c2 = smc.locally_optimal_proposal(lg, 0.3)
+    s2 = 1 / (1 / 0.9 + 1 / 0.8)
+    assert (c0, c1, c2) == pytest.approx((s2 * 0.3 / 0.8, s2 * 0.5 / 0.9, np.sqrt(s2)))
+    assert smc.AffineGaussianProposal(1, 2, 3)(lg, 9.0) == (1.0, 2.0, 3.0)
+
+
+# ------------------------------------------------------------------------------------------------ GPU: parity
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,N", [(smc.KIND_LG1D, 1024), (smc.KIND_LG1D, 777), (smc.KIND_SV, 2048), (smc.KIND_LG1D, 8192), (smc.KIND_SV, 5)])
+def test_guided_batch_bit_exact(ctx, oracle, kind, N):
+    """M guided filters, whole series in one launch: clouds and log-weights bit-exact against the oracle, logZ to 1e-10"""
+    M, T = 9, 25 if N <= 4096 else 6
+    rng = np.random.default_rng(N)
+    true = LG if kind == smc.KIND_LG1D else SVP
+    _, y = oracle.simulate(kind, true, T, 1998)
+    th = _lg_thetas(M, rng) if kind == smc.KIND_LG1D else _sv_thetas(M, rng)
+    P = smc._lib.params8(th)
+    if kind == smc.KIND_LG1D:   # every θ's own locally optimal proposal, per step
+        prop = np.array([[oracle.optimal_proposal_lg(th[m], yt) for m in range(M)] for yt in y])
+    else:                       # SV: a damped, widened version of the transition that leans on |y|
+        prop = np.array([[[th[m, 0] * (1 - 0.8 * th[m, 1]) + 0.05 * np.log(yt * yt + 1e-3), 0.8 * th[m, 1], 1.3 * th[m, 2]]
+                          for m in range(M)] for yt in y])
+    active = np.ones(M, np.uint8)
+    active[4] = 0
+    for resampler in (smc.MULTINOMIAL, smc.STRATIFIED, smc.SYSTEMATIC):
+        seed, epoch, stream0 = 77, 3 + resampler, 40
+        zo, xo, lwo = oracle.batch_guided_log_likelihood(kind, P, active, N, y, resampler, prop, seed, epoch, stream0)
+        b = ctx.batch(kind, M, N)
+        ctx.set_rng(seed, epoch)
+        z = b.log_likelihood(P, y, resampler, stream0, active, proposal=prop)
+        x, _, lw = b.fetch(want_w=False, want_logw=True)
+        on = active.astype(bool)
+        assert np.all(np.isneginf(z[~on]))
+        np.testing.assert_array_equal(x[on], xo[on])
+        np.testing.assert_array_equal(lw[on], lwo[on])
+        np.testing.assert_allclose(z[on], zo[on], rtol=RTOL, atol=0)
+        b.close()
+
+
+@pytest.mark.gpu
+def test_guided_stepping_api_and_python_mirror(ctx, oracle):
+    """particle_filter / particle_filter! with a proposal (particles.jl:28-84) one observation per call == the oracle's
+    step-by-step run; guided_log_likelihood == the same series in one launch; proposal=None continues as bootstrap"""
+    N, T = 1500, 20
+    lg = smc.LinearGaussian(0.5, 1.0, 0.9, 0.8)
+    _, y = oracle.simulate(0, LG, T, 21)
+    ctx.set_rng(13, 5)
+    x, w, logmu = smc.particle_filter(N, y[0], lg, smc.locally_optimal_proposal, ctx=ctx, stream=6)
+    xo, lwo = oracle.bootstrap_init(0, LG, N, y[0], 13, 5, 6)
+    lmo, _, _ = oracle.normalize(lwo)
+    assert abs(logmu - lmo) <= RTOL * abs(lmo)
+    logZ = logmu
+    for t in range(1, T):
+        logmu, w, ess = smc.particle_filter_(x, w, y[t], lg, smc.locally_optimal_proposal, resampler="systematic")
+        oracle.guided_step(0, LG, xo, lwo, y[t], t, oracle.SYSTEMATIC, oracle.optimal_proposal_lg(LG, y[t]), 13, 5, 6)
+        lmo, wo, esso = oracle.normalize(lwo)
+        assert abs(logmu - lmo) <= RTOL * abs(lmo) and abs(ess - esso) <= 1e-9 * esso
+        logZ += logmu
+    np.testing.assert_array_equal(np.asarray(x), xo[0])
+    np.testing.assert_allclose(np.asarray(w), wo, rtol=RTOL)
+    ctx.set_rng(13, 5)
+    x2, _, logZ2 = smc.guided_log_likelihood(N, y, lg, smc.locally_optimal_proposal, resampler="systematic", ctx=ctx, stream=6)
+    np.testing.assert_array_equal(np.asarray(x2), xo[0])
+    assert abs(logZ2 - logZ) <= RTOL * abs(logZ)
+    # a bootstrap step on the same cloud (proposal=None) == the oracle's bootstrap step
+    logmu, w, _ = smc.particle_filter_(x, w, 0.25, lg, None, resampler="systematic")
+    oracle.bootstrap_step(0, LG, xo, lwo, 0.25, T, oracle.SYSTEMATIC, 13, 5, 6)
+    np.testing.assert_array_equal(np.asarray(x), xo[0])
+    # errors: UCSV has no guided kernel; a non-positive proposal sd is refused; coefficients must be three numbers
+    b = ctx.batch(smc.KIND_UCSV, 2, 64)
+    b.init(np.tile(smc._lib.params8([0.2, 0.2, 3.0, 1.0, 1.0]), (2, 1)), 1.0)
+    with pytest.raises(smc.SMCBError):
+        b.step(1.0, smc.SYSTEMATIC, proposal=np.tile([0.0, 1.0, 1.0], (2, 1)))
+    b.close()
+    b = ctx.batch(smc.KIND_LG1D, 2, 64)
+    b.init(np.tile(smc._lib.params8(LG), (2, 1)), 1.0)
+    with pytest.raises(smc.SMCBError):
+        b.step(1.0, smc.SYSTEMATIC, proposal=np.tile([0.0, 1.0, 0.0], (2, 1)))
+    b.close()
+    with pytest.raises(TypeError):
+        smc.particle_filter_(x, w, 0.1, lg, lambda model, yt: (1.0, 2.0))
+
+
+@pytest.mark.gpu
+def test_guided_variance_reduction_on_device(ctx, oracle):
+    """the point of a proposal: at equal N the locally optimal proposal's logZ scatters far less around the matched-init
+    Kalman likelihood than the bootstrap filter's (LG1D, N = 512, 32 independent streams in one batch each)"""
+    M, N, T = 32, 512, 100
+    _, y = oracle.simulate(0, LG, T, 1998)
+    P = np.tile(smc._lib.params8(LG), (M, 1))
+    prop = np.array([[oracle.optimal_proposal_lg(LG, yt)] * M for yt in y])
+    b = ctx.batch(smc.KIND_LG1D, M, N)
+    ctx.set_rng(5, 1)
+    zg = b.log_likelihood(P, y, smc.SYSTEMATIC, 0, proposal=prop)
+    ctx.set_rng(5, 1)
+    zb = b.log_likelihood(P, y, smc.SYSTEMATIC, 0)
+    b.close()
+    kll = ctx.kalman_loglik(LG, y, matched_init=True)[0][0]
+    assert zg.std() < 0.5 * zb.std()
+    assert abs(np.log(np.mean(np.exp(zg - zg.max()))) + zg.max() - kll) < 4 * zg.std() / np.sqrt(M) + 0.02
+
+
+@pytest.mark.gpu
+def test_kalman_mv_batch(ctx, oracle):
+    """smcb_kalman_mv_batch_loglik / _step, d = 1..4, against the oracle model by model; the Python mirror on
+    hodrick_prescott; d = 1 equals the scalar kernel"""
+    rng = np.random.default_rng(1)
+    _, y = oracle.simulate(0, LG, 70, 9)
+    for d in (1, 2, 3, 4):
+        M = 21
+        blocks = []
+        for m in range(M):
+            A = _stable(rng, d)
+            G = rng.standard_normal((d, d))
+            blocks.append(oracle.mv_block(A, rng.standard_normal(d), G @ G.T + 0.1 * np.eye(d), [rng.uniform(0.3, 2)],
+                                          rng.standard_normal(d), 2.0 * np.eye(d)))
+        blocks = np.stack(blocks)
+        act = np.ones(M, np.uint8)
+        act[3] = 0
+        for matched in (False, True):
+            ll, x, S = ctx.kalman_mv_loglik(d, blocks, y, matched, act)
+            for m in range(M):
+                if not act[m]:
+                    assert np.isneginf(ll[m])
+                    continue
+                xo, So, lo = oracle.kalman_mv_loglik(d, blocks[m], y, matched)
+                assert abs(ll[m] - lo) <= 1e-12 * abs(lo)
+                np.testing.assert_allclose(x[m], xo, rtol=1e-11, atol=1e-13)
+                np.testing.assert_allclose(S[m], So, rtol=1e-11, atol=1e-13)
+        x1, S1, l1 = ctx.kalman_mv_step(d, blocks, np.zeros((M, d)), np.broadcast_to(np.eye(d), (M, d, d)), y[0])
+        for m in range(M):
+            xo, So, lo = oracle.kalman_mv_step(d, blocks[m], np.zeros(d), np.eye(d), y[0])
+            assert abs(l1[m] - lo) <= 1e-12 * abs(lo)
+            np.testing.assert_allclose(x1[m], xo, rtol=1e-12, atol=1e-14)
+            np.testing.assert_allclose(S1[m], So, rtol=1e-12, atol=1e-14)
+    blk = oracle.mv_block([[0.5]], [1.0], [[0.9]], [0.8], [0.0], [[1.0]])
+    assert ctx.kalman_mv_loglik(1, blk, y)[0][0] == pytest.approx(ctx.kalman_loglik(LG, y)[0][0], rel=1e-13)
+    hp = smc.hodrick_prescott(λ=1600.0, y=y)
+    ll = smc.kalman_filter.log_likelihood(y, hp, ctx=ctx)
+    assert ll == pytest.approx(oracle.kalman_mv_loglik(2, hp.block(), y)[2], rel=1e-12)
+    xT, ST, ll2 = smc.kalman_filter.filtered_moments(y, hp, ctx=ctx)
+    assert ll2 == ll and xT.shape == (2,) and ST.shape == (2, 2)
+    x1, S1, l1 = smc.kalman_filter.kalman_filter(hp, hp.x0, hp.σ0, y[0], ctx=ctx)
+    xo, So, lo = oracle.kalman_mv_step(2, hp.block(), hp.x0, hp.σ0, y[0])
+    np.testing.assert_allclose(x1, xo, rtol=1e-12)
+    assert l1 == pytest.approx(lo, rel=1e-12)
+    with pytest.raises(smc.SMCBError):
+        ctx.kalman_mv_loglik(5, np.zeros((1, 86)), y)
+
+
+@pytest.mark.gpu
+def test_batch_weighted_moments(ctx, oracle):
+    """smcb_batch_weighted_moments: per-θ mean and population variance of the clouds under their weights"""
+    kind, M, N, T = smc.KIND_UCSV, 7, 1001, 8
+    P = np.tile(smc._lib.params8([0.2, 0.2, 3.0, 1.0, 1.0]), (M, 1))
+    P[:, 0] = np.linspace(0.1, 0.6, M)
+    _, y = oracle.simulate(kind, [0.2, 0.2, 3.0, 1.0, 1.0], T, 5)
+    b = ctx.batch(kind, M, N)
+    ctx.set_rng(9, 4)
+    b.log_likelihood(P, y, smc.SYSTEMATIC, stream0=2)
+    _, xo, lwo = oracle.batch_log_likelihood(kind, P, None, N, y, smc.SYSTEMATIC, 9, 4, 2)
+    mean, var = b.weighted_moments()
+    np.testing.assert_allclose(mean, b.weighted_mean(), rtol=1e-13)
+    for m in range(M):
+        _, w, _ = oracle.normalize(lwo[m])
+        mo = xo[m] @ w
+        vo = ((xo[m] - mo[:, None]) ** 2) @ w
+        np.testing.assert_allclose(mean[m], mo, rtol=1e-10)
+        np.testing.assert_allclose(var[m], vo, rtol=1e-9)
+    b.close()
