@@ -30,6 +30,38 @@ def test_library_exports_every_declared_symbol():
     assert lib.smcb_state_dim(smc.KIND_UCSV) == 3 and lib.smcb_state_dim(smc.KIND_LG1D) == 1 and lib.smcb_state_dim(9) == -1
 
 
+def build_c_client():
+    """tests/abi_client.c compiled as plain C against include/smcb200.h (what an FFI binding sees); returns the binary"""
+    import subprocess
+    out_dir = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out_dir, exist_ok=True)
+    exe, src = os.path.join(out_dir, "abi_client"), os.path.join(ROOT, "tests", "abi_client.c")
+    deps = [src, os.path.join(ROOT, "include", "smcb200.h")]
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.check_call(["gcc", "-std=gnu11", "-O1", "-Wall", "-Wextra", "-Werror", "-ffp-contract=off", src, "-o", exe, "-ldl", "-lm"])
+    return exe
+
+
+def run_c_client(*args):
+    import subprocess
+    _lib.load()
+    out = subprocess.run([build_c_client(), _lib.library_path(), *args], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    return dict(line.split(None, 1) for line in out.stdout.strip().splitlines())
+
+
+def test_header_is_plain_c_and_a_c_client_resolves_every_symbol(oracle):
+    """the drop-in boundary from C: the header compiles as C11 with -Wall -Wextra -Werror, dlopen + dlsym find every
+    declared entry point, and the host-side helpers give the oracle's numbers"""
+    names = _declared()
+    assert run_c_client("symbols", *names)["resolved"] == str(len(names))
+    got = run_c_client("host")
+    assert got["version"] == "100" and got["dims"] == "1 1 3 -1"
+    _, yo = oracle.simulate(0, [0.5, 1.0, 0.9, 0.8, 0.0, 1.0], 40, 1998)
+    for t in range(3):
+        assert float(got[f"y{t}"]) == yo[t]
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():

@@ -285,3 +285,28 @@ def test_batch_weighted_moments(ctx, oracle):
         np.testing.assert_allclose(mean[m], mo, rtol=1e-10)
         np.testing.assert_allclose(var[m], vo, rtol=1e-9)
     b.close()
+
+
+@pytest.mark.gpu
+def test_plain_c_client_runs_the_path(oracle):
+    """tests/abi_client.c (plain C, dlopen): one bootstrap filter, three guided filters with per-θ moments and the
+    Kalman entry points, checked against the oracle — the boundary works without Python or C++ on the caller's side"""
+    from tests.test_abi import run_c_client
+    got = {k: float(v) for k, v in run_c_client("gpu").items()}
+    _, y = oracle.simulate(0, LG, 40, 1998)
+    ref = oracle.log_likelihood(0, LG, 2048, y, oracle.SYSTEMATIC, 7, 1, 0)
+    assert abs(got["pf_logZ"] - ref["logZ"]) <= RTOL * abs(ref["logZ"])
+    assert got["pf_x0"] == ref["x"][0, 0] and got["pf_xlast"] == ref["x"][0, -1]
+    # the C client derives the coefficients with its own arithmetic; feed the oracle the very same numbers
+    s2 = 1.0 / (1.0 / LG[2] + LG[1] * LG[1] / LG[3])
+    prop = np.array([[[s2 * LG[1] * yt / LG[3], s2 * LG[0] / LG[2], np.sqrt(s2)]] * 3 for yt in y])
+    P = np.tile(smc._lib.params8(LG), (3, 1))
+    zo, xo, lwo = oracle.batch_guided_log_likelihood(0, P, None, 512, y, oracle.SYSTEMATIC, prop, 7, 2, 10)
+    for m in range(3):
+        assert abs(got[f"guided_logZ{m}"] - zo[m]) <= RTOL * abs(zo[m])
+        _, w, _ = oracle.normalize(lwo[m])
+        mo = float(xo[m, 0] @ w)
+        assert abs(got[f"guided_mean{m}"] - mo) <= 1e-10 * max(1.0, abs(mo))
+        assert abs(got[f"guided_var{m}"] - float(((xo[m, 0] - mo) ** 2) @ w)) <= 1e-9
+    lo = oracle.kalman_loglik(LG, y)[2]
+    assert abs(got["kalman_mv"] - lo) <= 1e-12 * abs(lo) and abs(got["kalman_scalar"] - lo) <= 1e-12 * abs(lo)
