@@ -20,7 +20,8 @@ configs[1] at its largest size (N = 2^24, T = 1000) — through the C ABI of lib
 
 N > 1 GPUs: a single filter does not shard (global scan + gather every step: "replicas only",
 DESIGN.md §5) — every rank runs its own filter on its own Philox stream (weak scaling).  The
-θ-sharded SMC² numbers (the path that does shard) ride along in the "smc2" object.
+θ-sharded SMC² numbers (the path that does shard) ride along in the "smc2" object, and the rows built after
+the hot path (guided filter, matrix Kalman, per-θ moments: SURVEY §8f) in the "widen" object.
 """
 import argparse
 import json
@@ -172,6 +173,7 @@ def main():
     ap.add_argument("--T", type=int, default=1000)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-smc2", action="store_true", help="skip the θ-sharded SMC² leg")
+    ap.add_argument("--no-widen", action="store_true", help="skip the guided-filter / matrix-Kalman leg (SURVEY §8f rows)")
     ap.add_argument("--no-f32", action="store_true", help="skip the binary32-state tier leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -310,10 +312,48 @@ def main():
                 line["smc2"]["cpu_baseline"] = cpu_rejuvenation_sample(1024, 100)
         except Exception as e:  # the headline line must still print
             line["smc2"] = {"error": repr(e)}
+    if rank == 0 and world == 1 and not args.no_widen:
+        try:
+            line["widen"] = widen_leg(ctx)
+        except Exception as e:  # the headline line must still print
+            line["widen"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def widen_leg(ctx, M=512, N=1024, T=100):
+    """SURVEY §8(f) rows built after the hot path (device time of the library's own events, ms): the guided filter
+    (docs/SPEC.md §10) against the bootstrap filter on config 3's inner shape (512 θ × 1024 particles, T = 100, all θ
+    at the true parameters so that the scatter of logZ over θ is the estimator's own), the matrix Kalman filter on 4096
+    Hodrick–Prescott models, and the per-θ moments."""
+    import sequential_monte_carlo_b200 as smc
+    P = np.tile(smc._lib.params8(LG_PARAMS), (M, 1))
+    y = smc._lib.simulate(smc.KIND_LG1D, LG_PARAMS, T, 1998)[1]
+    lg = smc.LinearGaussian(*LG_PARAMS[:5])
+    prop = np.array([[smc.locally_optimal_proposal(lg, yt)] * M for yt in y])
+    b = ctx.batch(smc.KIND_LG1D, M, N)
+    out = {"workload": f"{M} θ × {N} particles, T={T}, LG1D at the true θ, systematic; one launch per sweep"}
+    for name, q in (("bootstrap", None), ("guided", prop)):
+        b.log_likelihood(P, y, smc.SYSTEMATIC, 0, proposal=q)          # warm-up (module load)
+        z = b.log_likelihood(P, y, smc.SYSTEMATIC, 0, proposal=q)
+        ms = b.timing()[0]
+        out[name] = {"ms_per_sweep": ms, "particle_updates_per_s": M * N * T / (ms * 1e-3), "sd_logZ_over_theta": float(np.std(z)),
+                     "mean_logZ": float(np.mean(z))}
+    t0 = time.perf_counter()
+    mean, var = b.weighted_moments()
+    out["per_theta_moments_ms"] = (time.perf_counter() - t0) * 1e3
+    b.close()
+    out["kalman_matched_init_logZ"] = float(ctx.kalman_loglik(LG_PARAMS, y, matched_init=True)[0][0])
+    yhp = smc._lib.simulate(smc.KIND_LG1D, [1.0, 1.0, 0.05, 1.0, 0.0, 1.0], 241, 1998)[1]
+    blocks = np.stack([smc.hodrick_prescott(λ=lam, y=yhp).block() for lam in np.geomspace(1.0, 1e5, 4096)])
+    ctx.kalman_mv_loglik(2, blocks, yhp)
+    t0 = time.perf_counter()
+    ll, _, _ = ctx.kalman_mv_loglik(2, blocks, yhp)
+    out["kalman_mv"] = {"workload": "4096 Hodrick–Prescott models (d = 2), T = 241, one launch, wall incl. H2D/D2H",
+                        "ms": (time.perf_counter() - t0) * 1e3, "best_lambda": float(np.geomspace(1.0, 1e5, 4096)[int(np.argmax(ll))])}
+    return out
 
 
 def load_traffic():
