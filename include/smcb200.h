@@ -104,6 +104,17 @@ int smcb_bootstrap_step(smcb_ctx* ctx, const double* params, double y, int resam
  * one call for the whole series; logmu_out / ess_out (length T) may be NULL. */
 int smcb_log_likelihood(smcb_ctx* ctx, int kind, const double* params, int64_t N, const double* y, int64_t T,
                         int resampler, uint32_t stream, double* logZ, double* logmu_out, double* ess_out);
+/* particle_filter!(states, weights, y, model, proposal) -> (logμ, w, ess)          particles.jl:55-84
+ * and the loop of examples/inflation_example.jl:164-171 with a proposal, for ONE large-N filter (docs/SPEC.md §10):
+ * proposal = (c0, c1, c2) of x' ~ N(c0 + c1·xp, c2²) for this step ([T][3] for a whole series, row 0 not read — the
+ * initial step is smcb_bootstrap_init's).  One-dimensional models (LG1D, SV) and the sorted resamplers; UCSV or
+ * multinomial resampling -> SMCB_ERR_UNSUPPORTED (the batched entry points below take multinomial, N <= 8192).
+ * Both storage tiers of smcb_set_precision. */
+int smcb_guided_step(smcb_ctx* ctx, const double* params, double y, int resampler, const double* proposal, double* logmu,
+                     double* ess);
+int smcb_guided_log_likelihood(smcb_ctx* ctx, int kind, const double* params, int64_t N, const double* y, int64_t T,
+                               int resampler, uint32_t stream, const double* proposal, double* logZ, double* logmu_out,
+                               double* ess_out);
 /* x [d*N] SoA, w [N] normalised weights, logw [N] unnormalised log-weights; any may be NULL */
 int smcb_fetch_state(smcb_ctx* ctx, double* x, double* w, double* logw);
 /* Summaries of the current cloud computed ON THE DEVICE — what the reference's per-step

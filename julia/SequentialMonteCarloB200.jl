@@ -252,6 +252,7 @@ weights(c::GuidedCloud) = (a = Vector{Float64}(undef, c.N);
     check(c.b.ctx, ccall((:smcb_batch_fetch, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), c.b.h, C_NULL, a, C_NULL)); a)
 particle_filter(N::Int64, y::Float64, model::StateSpaceModel, ::Nothing; ctx=context()) = bootstrap_filter(N, y, model; ctx=ctx)   # :28-51
 function particle_filter(N::Int64, y::Float64, model::StateSpaceModel, proposal; ctx=context())
+    N > 8192 && return bootstrap_filter(N, y, model; ctx=ctx)           # large clouds continue on the single filter
     b = Batch(ctx, kind(model), 1, N); lm = [0.0]; es = [0.0]
     check(ctx, ccall((:smcb_batch_init, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{UInt8}, Float64, UInt32, Ptr{Float64}, Ptr{Float64}),
                      b.h, params8(model), C_NULL, y, 0, lm, es))
@@ -260,6 +261,12 @@ function particle_filter(N::Int64, y::Float64, model::StateSpaceModel, proposal;
 end
 particle_filter!(states::Cloud, w::Vector{Float64}, y::Float64, model::StateSpaceModel, ::Nothing; resampler=MULTINOMIAL) =
     bootstrap_filter!(states, w, y, model; resampler=resampler)                                # :55-84 with proposal = nothing
+function particle_filter!(states::Cloud, w::Vector{Float64}, y::Float64, model::StateSpaceModel, proposal; resampler=SYSTEMATIC)
+    c = Float64[proposal(model, y)...]; lm = Ref(0.0); es = Ref(0.0)     # the large-N single filter: sorted resamplers
+    check(states.ctx, ccall((:smcb_guided_step, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Float64, Cint, Ptr{Float64}, Ref{Float64}, Ref{Float64}),
+                            states.ctx.h, params8(model), y, resampler, c, lm, es))
+    return lm[], weights(states), es[]
+end
 function particle_filter!(states::GuidedCloud, w::Vector{Float64}, y::Float64, model::StateSpaceModel, proposal; resampler=MULTINOMIAL)
     c = Float64[proposal(model, y)...]; lm = [0.0]; es = [0.0]
     check(states.b.ctx, ccall((:smcb_batch_step_guided, LIB), Cint,

@@ -249,6 +249,7 @@ int smco_guided_step(int kind, const double *P, int64_t n, double y, uint32_t t,
     double z = o_normal(seed, epoch, (uint32_t)i, stream, t, P_TRANS, 0);
     double mq = fma(c1, xp[i], c0);
     double xi = fma(c2, z, mq);                                             /* x[i] = rand(proposal(model, xp[i])) :73 */
+    round_state(&xi, 1);                                                    /* SPEC §9: the stored state is what every density sees */
     double mf = (kind == KIND_LG1D) ? D[0] * xp[i] : fma(D[1], xp[i] - D[0], D[0]);
     double zt = (xi - mf) / sdf;
     double zq = (xi - mq) / c2;

@@ -41,6 +41,9 @@ SIGNATURES = {
     "smcb_bootstrap_step": (C.c_int, [_c_ctx, C.c_void_p, C.c_double, C.c_int, _dp, _dp]),
     "smcb_log_likelihood": (C.c_int, [_c_ctx, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_uint32,
                                       _dp, C.c_void_p, C.c_void_p]),
+    "smcb_guided_step": (C.c_int, [_c_ctx, C.c_void_p, C.c_double, C.c_int, C.c_void_p, _dp, _dp]),
+    "smcb_guided_log_likelihood": (C.c_int, [_c_ctx, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_uint32,
+                                             C.c_void_p, _dp, C.c_void_p, C.c_void_p]),
     "smcb_fetch_state": (C.c_int, [_c_ctx, C.c_void_p, C.c_void_p, C.c_void_p]),
     "smcb_fetch_ancestors": (C.c_int, [_c_ctx, C.c_void_p, C.c_int64, _i64p]),
     "smcb_device_state": (C.c_int, [_c_ctx, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), _i64p]),
@@ -277,6 +280,29 @@ class Context:
         es = np.empty(T) if per_step else None
         self._check(self._lib.smcb_log_likelihood(self._h, int(kind), _ptr(p), int(N), _ptr(y), T, int(resampler), int(stream),
                                                   C.byref(z), _ptr(lm), _ptr(es)))
+        self._N, self._kind, self._T = int(N), int(kind), T
+        return (z.value, lm, es) if per_step else z.value
+
+    def guided_step(self, y, proposal, resampler=SYSTEMATIC, params=None):
+        """particle_filter! with proposal = (c0, c1, c2) on the single large-N filter (docs/SPEC.md §10; sorted resamplers)"""
+        p = None if params is None else params8(params)
+        q = np.ascontiguousarray(proposal, np.float64).reshape(3)
+        lm, es = C.c_double(), C.c_double()
+        self._check(self._lib.smcb_guided_step(self._h, _ptr(p), float(y), int(resampler), _ptr(q), C.byref(lm), C.byref(es)))
+        self._T += 1
+        return lm.value, es.value
+
+    def guided_log_likelihood(self, kind, params, N, y, proposal, resampler=SYSTEMATIC, stream=0, per_step=False):
+        """whole series of the guided single filter in one call; proposal [T, 3] (row 0 unused)"""
+        p = params8(params)
+        y = np.ascontiguousarray(y, np.float64)
+        T = y.size
+        q = np.ascontiguousarray(proposal, np.float64).reshape(T, 3)
+        z = C.c_double()
+        lm = np.empty(T) if per_step else None
+        es = np.empty(T) if per_step else None
+        self._check(self._lib.smcb_guided_log_likelihood(self._h, int(kind), _ptr(p), int(N), _ptr(y), T, int(resampler), int(stream),
+                                                         _ptr(q), C.byref(z), _ptr(lm), _ptr(es)))
         self._N, self._kind, self._T = int(N), int(kind), T
         return (z.value, lm, es) if per_step else z.value
 

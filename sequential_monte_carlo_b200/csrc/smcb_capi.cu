@@ -226,6 +226,42 @@ int smcb_log_likelihood(smcb_ctx* ctx, int kind, const double* params, int64_t N
   });
 }
 
+int smcb_guided_step(smcb_ctx* ctx, const double* params, double y, int resampler, const double* proposal, double* logmu,
+                     double* ess) {
+  if (!ctx) return SMCB_ERR_BAD_ARG;
+  return guarded(ctx, [&] {
+    need(proposal != nullptr, "guided_step: proposal is null (use smcb_bootstrap_step for the bootstrap filter)");
+    StepStats st;
+    ctx->filter->step(params, y, resampler, &st, proposal);
+    stats_to(st, ctx->filter->N(), logmu, ess);
+  });
+}
+
+int smcb_guided_log_likelihood(smcb_ctx* ctx, int kind, const double* params, int64_t N, const double* y, int64_t T,
+                               int resampler, uint32_t stream, const double* proposal, double* logZ, double* logmu_out,
+                               double* ess_out) {
+  if (!ctx) return SMCB_ERR_BAD_ARG;
+  return guarded(ctx, [&] {
+    need(params && y && proposal && T >= 1, "guided_log_likelihood: params, y, proposal must be non-null and T >= 1");
+    if (kind != KIND_LG1D && kind != KIND_SV)
+      throw Error{SMCB_ERR_UNSUPPORTED, "guided proposals are defined for the one-dimensional models (LG1D, SV)"};
+    if (resampler == RESAMPLE_MULTINOMIAL && T > 1)
+      throw Error{SMCB_ERR_UNSUPPORTED, "guided single filter: stratified or systematic resampling (multinomial guided filters run on the batched engine, N <= 8192)"};
+    ctx->stats.resize((size_t)T);
+    ctx->filter->run(kind, params, N, y, T, resampler, ctx->key(ctx->next_epoch), stream, ctx->stats.data(), proposal);
+    ctx->next_epoch = (ctx->next_epoch + 1) & 0xFFFFFFu;
+    double z = 0.0;
+    for (int64_t t = 0; t < T; ++t) {
+      double lm, es;
+      stats_to(ctx->stats[(size_t)t], N, &lm, &es);
+      z += lm;
+      if (logmu_out) logmu_out[t] = lm;
+      if (ess_out) ess_out[t] = es;
+    }
+    if (logZ) *logZ = z;
+  });
+}
+
 int smcb_fetch_state(smcb_ctx* ctx, double* x, double* w, double* logw) {
   if (!ctx) return SMCB_ERR_BAD_ARG;
   return guarded(ctx, [&] { ctx->filter->fetch(x, w, logw); });

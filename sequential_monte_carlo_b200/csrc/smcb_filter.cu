@@ -1108,6 +1108,88 @@ __global__ void __launch_bounds__(kMoveThreads, (Model::D == 1) ? 6 : 3)
   }
 }
 
+// Guided move (particle_filter!, particles.jl:66-80; docs/SPEC.md §10) of the one-dimensional models: x_i ~ N(c0 + c1 x[a_i], c2²)
+// from the SAME Philox normal, logw_i = logpdf(observation(x_i), y) + logpdf(transition(x[a_i]), x_i) − logpdf(proposal(x[a_i]), x_i),
+// always stored (it is not a function of x_i alone).  Same streaming layout as move_kernel; in the binary32-state tier the
+// drawn state is rounded before any density sees it (SPEC §9).
+template <class Model, bool FULL, class XT>
+__device__ __forceinline__ double guided_move_particles(const Model& mdl, const TransDensity<Model>& f, const ProposalCoef& pc, double y, int N,
+                                                        const RngKey& key, uint32_t stream, uint32_t t, int i0, const int32_t* __restrict__ anc,
+                                                        const XT* __restrict__ xprev, XT* __restrict__ xnew, double* __restrict__ logw) {
+  static_assert(Model::D == 1, "guided proposals are defined for the one-dimensional models");
+  constexpr int PER = 2 * kMovePairs;
+  int a[PER];
+  if (FULL) {
+#pragma unroll
+    for (int q = 0; q < PER / 2; ++q) {
+      const int2 v = __ldcs(reinterpret_cast<const int2*>(anc + i0) + q);
+      a[2 * q] = v.x; a[2 * q + 1] = v.y;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < PER; ++k) a[k] = (i0 + k < N) ? anc[i0 + k] : 0;
+  }
+  double xp[PER];
+#pragma unroll
+  for (int k = 0; k < PER; ++k) xp[k] = (double)__ldg(&xprev[a[k]]);
+  double vmax = -INFINITY;
+#pragma unroll
+  for (int r = 0; r < kMovePairs; ++r) {
+    const int i = i0 + 2 * r;
+    if (!FULL && i >= N) break;
+    double za, zb;
+    normal_pair_at(key, (uint32_t)(i >> 1), stream, t, PURPOSE_TRANSITION, 0u, za, zb);
+    const double mqa = fma(pc.c[1], xp[2 * r], pc.c[0]), mqb = fma(pc.c[1], xp[2 * r + 1], pc.c[0]);
+    double xa[1] = {fma(pc.c[2], za, mqa)}, xb[1] = {fma(pc.c[2], zb, mqb)};
+    round_state<XT>(xa);
+    round_state<XT>(xb);
+    const double la = mdl.logweight(xa, y) + guided_correction(mdl, f, pc.c, mqa, xp[2 * r], xa[0]);
+    const double lb = mdl.logweight(xb, y) + guided_correction(mdl, f, pc.c, mqb, xp[2 * r + 1], xb[0]);
+    if (FULL || i + 1 < N) {
+      *reinterpret_cast<typename XVec2<XT>::type*>(xnew + i) = XVec2<XT>::make(xa[0], xb[0]);
+      *reinterpret_cast<double2*>(logw + i) = make_double2(la, lb);
+      if (la > vmax) vmax = la;
+      if (lb > vmax) vmax = lb;
+    } else {
+      xnew[i] = (XT)xa[0];
+      logw[i] = la;
+      if (la > vmax) vmax = la;
+    }
+  }
+  return vmax;
+}
+
+template <class Model, class XT>
+__global__ void __launch_bounds__(kMoveThreads, 4)
+    guided_move_kernel(Derived dv, ProposalCoef pc, double y, int N, RngKey key, uint32_t stream, uint32_t t, const int32_t* __restrict__ anc,
+                       const XT* __restrict__ xprev, XT* __restrict__ xnew, double* __restrict__ logw, FilterCtrl* ctrl) {
+  constexpr int PER = 2 * kMovePairs;
+  constexpr int NW = kMoveThreads / 32;
+  __shared__ unsigned long long s_max[NW];
+  const int tid = threadIdx.x;
+  Model mdl;
+  mdl.load(dv.d);
+  TransDensity<Model> f;
+  f.load(dv.d);
+  const int i0 = (blockIdx.x * kMoveThreads + tid) * PER;
+  pdl_launch_dependents();
+  pdl_wait();  // the ancestors come from anc_hist_kernel
+  double vmax;
+  if ((int64_t)(blockIdx.x + 1) * (kMoveThreads * PER) <= (int64_t)N)
+    vmax = guided_move_particles<Model, true, XT>(mdl, f, pc, y, N, key, stream, t, i0, anc, xprev, xnew, logw);
+  else
+    vmax = guided_move_particles<Model, false, XT>(mdl, f, pc, y, N, key, stream, t, i0, anc, xprev, xnew, logw);
+  const unsigned long long wm = warp_max_ordered(encode_ordered(vmax));
+  if ((tid & 31) == 0) s_max[tid >> 5] = wm;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long m = s_max[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) m = s_max[w] > m ? s_max[w] : m;
+    atomicMax(&ctrl->maxslot[t & 1u], m);
+  }
+}
+
 // logw_i = logpdf(observation(x_i), y): materialises the log-weights that the LG1D step does not store
 template <class XT>
 __global__ void logw_kernel(Derived dv, double y, int64_t N, const XT* __restrict__ x, double* __restrict__ logw) {
@@ -1485,7 +1567,16 @@ void SingleFilter::launch_sum(int64_t stat_index) {
 }
 
 // one bootstrap_filter! step: stats of the current weights (-> stats_dev_[stat_index]) and the move to t_+1
-void SingleFilter::launch_step(int64_t stat_index, double y, int resampler) {
+void SingleFilter::launch_step(int64_t stat_index, double y, int resampler, const double* proposal) {
+  ProposalCoef pc{};
+  if (proposal) {  // guided step (docs/SPEC.md §10): sorted resamplers, one-dimensional models
+    if (d_ != 1) throw Error{SMCB_ERR_UNSUPPORTED, "guided proposals are defined for the one-dimensional models (LG1D, SV)"};
+    if (resampler == RESAMPLE_MULTINOMIAL)
+      throw Error{SMCB_ERR_UNSUPPORTED, "guided single filter: stratified or systematic resampling (multinomial guided filters run on the batched engine, N <= 8192)"};
+    if (!(proposal[2] > 0.0) || !std::isfinite(proposal[2]) || !std::isfinite(proposal[0]) || !std::isfinite(proposal[1]))
+      throw Error{SMCB_ERR_BAD_ARG, "proposal: coefficients must be finite and the standard deviation c2 > 0"};
+    pc.c[0] = proposal[0]; pc.c[1] = proposal[1]; pc.c[2] = proposal[2]; pc.c[3] = det_log(proposal[2]);
+  }
   if (resampler == RESAMPLE_MULTINOMIAL) {  // unsorted thresholds: materialised CDF + per-particle global search
     launch_scan(stat_index, true);
     launch_prop(y, resampler);
@@ -1521,8 +1612,19 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler) {
   const unsigned mblocks = (unsigned)((N_ + kMoveThreads * 2 * kMovePairs - 1) / (kMoveThreads * 2 * kMovePairs));
   // LG1D: the new log-weights are two fma of the new states; they are not stored (sum_kernel and, when a caller asks
   // for them, logw_kernel recompute them bit for bit).  SV / UCSV weights cost an exp: stored as before.
-  const bool implicit_logw = (kind_ == KIND_LG1D);
+  const bool implicit_logw = (kind_ == KIND_LG1D) && !proposal;
   mark(TK_PROP, true);
+  if (proposal) {
+    dispatch_xt(prec_, [&](auto tag) {
+      using XT = decltype(tag);
+      if (kind_ == KIND_LG1D)
+        SMCB_CUDA_TRY(launch_pdl(guided_move_kernel<ModelLG1D, XT>, dim3(mblocks), dim3(kMoveThreads), stream_, dv_, pc, y, (int)N_, key_, stream_id_, t,
+                                 anc, reinterpret_cast<const XT*>(x_[cur_]), reinterpret_cast<XT*>(x_[cur_ ^ 1]), logw_[cur_ ^ 1], ctrl_));
+      else
+        SMCB_CUDA_TRY(launch_pdl(guided_move_kernel<ModelSV, XT>, dim3(mblocks), dim3(kMoveThreads), stream_, dv_, pc, y, (int)N_, key_, stream_id_, t,
+                                 anc, reinterpret_cast<const XT*>(x_[cur_]), reinterpret_cast<XT*>(x_[cur_ ^ 1]), logw_[cur_ ^ 1], ctrl_));
+    });
+  } else
   dispatch_model(kind_, [&](auto m) {
     using M = decltype(m);
     dispatch_xt(prec_, [&](auto tag) {
@@ -1571,7 +1673,7 @@ void SingleFilter::init(int kind, const double* params, int64_t N, double y0, co
   if (st) *st = last_;
 }
 
-void SingleFilter::step(const double* params, double y, int resampler, StepStats* st) {
+void SingleFilter::step(const double* params, double y, int resampler, StepStats* st, const double* proposal) {
   if (!live()) throw Error{SMCB_ERR_STATE, "bootstrap_step before bootstrap_init / log_likelihood"};
   check_args(kind_, N_, resampler);
   if (prec_ && resampler == RESAMPLE_MULTINOMIAL) throw Error{SMCB_ERR_BAD_ARG, "binary32 states: sorted resamplers only (docs/SPEC.md §9)"};
@@ -1579,7 +1681,7 @@ void SingleFilter::step(const double* params, double y, int resampler, StepStats
   if (params) derive_params(kind_, params, dv_.d);
   if (!record_anc_) anc_rows_ = 0;
   begin_call();
-  launch_step(1, y, resampler);  // (the statistics of the old weights, if it has to recompute them, go to slot 1)
+  launch_step(1, y, resampler, proposal);  // (the statistics of the old weights, if it has to recompute them, go to slot 1)
   if (resampler == RESAMPLE_MULTINOMIAL) launch_scan(0, false);
   else launch_sum(0);            // statistics of the new weights now; the next sorted step reuses everything else
   SMCB_CUDA_TRY(cudaMemcpyAsync(&last_, stats_dev_, sizeof(StepStats), cudaMemcpyDeviceToHost, stream_));
@@ -1588,7 +1690,7 @@ void SingleFilter::step(const double* params, double y, int resampler, StepStats
 }
 
 void SingleFilter::run(int kind, const double* params, int64_t N, const double* y, int64_t T, int resampler,
-                       const RngKey& key, uint32_t stream_id, StepStats* stats_out) {
+                       const RngKey& key, uint32_t stream_id, StepStats* stats_out, const double* proposal) {
   check_args(kind, N, resampler);
   if (next_prec_ && resampler == RESAMPLE_MULTINOMIAL) throw Error{SMCB_ERR_BAD_ARG, "binary32 states: sorted resamplers only (docs/SPEC.md §9)"};
   if (T < 1) throw Error{SMCB_ERR_BAD_ARG, "T must be >= 1"};
@@ -1607,7 +1709,7 @@ void SingleFilter::run(int kind, const double* params, int64_t N, const double* 
   begin_call();
   launch_init(y[0]);
   for (int64_t t = 1; t < T; ++t) {
-    launch_step(t - 1, y[t], resampler);  // stats of time t-1, then the step to time t
+    launch_step(t - 1, y[t], resampler, proposal ? proposal + 3 * t : nullptr);  // stats of time t-1, then the step to time t
   }
   if (resampler == RESAMPLE_MULTINOMIAL) launch_scan(T - 1, false);
   else launch_sum(T - 1);

@@ -51,10 +51,12 @@ class SingleFilter {
   void init(int kind, const double* params, int64_t N, double y0, const RngKey& key, uint32_t stream_id,
             StepStats* st);
   // bootstrap_filter!(x, w, y, model); params may be null (keep)
-  void step(const double* params, double y, int resampler, StepStats* st);
+  // proposal != null: particle_filter!(x, w, y, model, proposal) with proposal = (c0, c1, c2) of x' ~ N(c0 + c1 xp, c2²)
+  // (particles.jl:55-84, docs/SPEC.md §10): one-dimensional models, sorted resamplers
+  void step(const double* params, double y, int resampler, StepStats* st, const double* proposal = nullptr);
   // log_likelihood(N, y, model): init + T-1 steps, one host sync at the end; stats_out[T]
   void run(int kind, const double* params, int64_t N, const double* y, int64_t T, int resampler,
-           const RngKey& key, uint32_t stream_id, StepStats* stats_out);
+           const RngKey& key, uint32_t stream_id, StepStats* stats_out, const double* proposal = nullptr);  // proposal: [T][3], row 0 unused
 
   // normalize(logw) / resample(w) on caller vectors (scratch use of this object; clobbers its state)
   void normalize_vector(const double* logw_host, int64_t n, StepStats* st, double* w_host);
@@ -89,7 +91,7 @@ class SingleFilter {
   void ensure_logw();  // materialise the log-weights an LG1D step keeps implicit in x
   void launch_init(double y0);
   void launch_prop(double y, int resampler);
-  void launch_step(int64_t stat_index, double y, int resampler);  // one bootstrap_filter! step
+  void launch_step(int64_t stat_index, double y, int resampler, const double* proposal = nullptr);  // one bootstrap_filter! / guided step
   void launch_scan(int64_t stat_index, bool write_cdf);
   void launch_sum(int64_t stat_index);
   unsigned long long* step_index(StepIndex& ix);

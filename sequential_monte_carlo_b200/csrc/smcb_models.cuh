@@ -128,18 +128,29 @@ struct TransDensity<ModelSV> {
 
 constexpr int kProposalStride = 4;  // c0, c1, c2, det_log(c2): the proposal x' ~ N(c0 + c1 xp, c2^2) of one (t, θ)
 
+struct ProposalCoef {  // by-value kernel argument of the grid-wide guided step
+  double c[kProposalStride];
+};
+
+// logpdf(transition(xp), x') - logpdf(proposal(xp), x')   (particles.jl:77-78; the two 0.5 log 2π cancel); mq is the
+// proposal mean fma(c1, xp, c0) that produced x'
+template <class Model>
+SMCB_HD double guided_correction(const Model& mdl, const TransDensity<Model>& f, const double* pc, double mq, double xp, double x) {
+  const double zt = (x - f.mean(mdl, xp)) / f.sd;
+  const double zq = (x - mq) / pc[2];
+  const double lf = fma(-0.5 * zt, zt, -f.lsd);
+  const double lq = fma(-0.5 * zq, zq, -pc[3]);
+  return lf - lq;
+}
+
 // x' = rand(proposal(xp)); logw = logpdf(observation(x'), y) + logpdf(transition(xp), x') - logpdf(proposal(xp), x')
-// (particles.jl:73-78; the two 0.5 log 2π cancel).  z is the standard normal the bootstrap transition would consume.
+// (particles.jl:73-78).  z is the standard normal the bootstrap transition would consume.
 template <class Model>
 SMCB_HD double guided_move(const Model& mdl, const TransDensity<Model>& f, const double* pc, double z, double xp, double y,
                            double* x) {
   const double mq = fma(pc[1], xp, pc[0]);
   x[0] = fma(pc[2], z, mq);
-  const double zt = (x[0] - f.mean(mdl, xp)) / f.sd;
-  const double zq = (x[0] - mq) / pc[2];
-  const double lf = fma(-0.5 * zt, zt, -f.lsd);
-  const double lq = fma(-0.5 * zq, zq, -pc[3]);
-  return mdl.logweight(x, y) + (lf - lq);
+  return mdl.logweight(x, y) + guided_correction(mdl, f, pc, mq, xp, x[0]);
 }
 
 }  // namespace smcb

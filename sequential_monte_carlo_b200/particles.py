@@ -144,9 +144,13 @@ def locally_optimal_proposal(model, y):
     return s2 * B * float(y) / R, s2 * A / Q, float(np.sqrt(s2))
 
 
+_GUIDED_BATCH_MAX = 8192   # guided filters up to this size run on the batched engine (any resampler), larger ones on the single filter
+
+
 class _GuidedCloud:
     """x or w of a guided filter: the cloud lives in a one-θ batch on the device (guided filters run on the batched
-    engine, N <= 8192) and is copied to the host only when read."""
+    engine for N <= 8192; larger guided filters use the single filter and its _DeviceArray handles) and is copied to the
+    host only when read."""
 
     def __init__(self, batch, which):
         self._batch, self._which, self._host, self._host_t = batch, which, None, -1
@@ -195,6 +199,8 @@ def particle_filter(N, y, model, proposal=None, *, ctx=None, stream=0):
     ctx = ctx or default_context()
     if model.kind not in (_lib.LG1D, _lib.SV):
         raise NotImplementedError("guided proposals are built for the one-dimensional models (LinearModel, StochasticVolatility)")
+    if int(N) > _GUIDED_BATCH_MAX:      # large clouds: the grid-wide single filter (guided steps need a sorted resampler there)
+        return bootstrap_filter(N, y, model, ctx=ctx, stream=stream)
     b = ctx.batch(model.kind, 1, int(N))
     logmu, _ = b.init(np.asarray(model.params(), np.float64).reshape(1, -1), float(y), stream0=stream)
     b._t = 0
@@ -213,10 +219,16 @@ def particle_filter_(states, weights, y, model, proposal=None, *, resampler="mul
             b._t += 1
             return float(lm[0]), _GuidedCloud(b, "w"), float(es[0])
         return bootstrap_filter_(states, weights, y, model, resampler=resampler)
+    c = _proposal_coefficients(proposal, model, y)
+    if isinstance(states, _DeviceArray):   # the large-N single filter: guided move kernel of the grid-wide path
+        ctx = states._ctx
+        if states._stale():
+            raise RuntimeError("stale particle cloud")
+        logmu, ess = ctx.guided_step(float(y), c, resampler_id(resampler), model.params())
+        return logmu, _DeviceArray(ctx, ctx._gen, "w"), ess
     if not isinstance(states, _GuidedCloud):
         raise RuntimeError("guided steps continue a cloud created by particle_filter(N, y, model, proposal)")
     b = states._batch
-    c = _proposal_coefficients(proposal, model, y)
     lm, es = b.step(float(y), resampler_id(resampler), np.asarray(model.params(), np.float64).reshape(1, -1), proposal=c.reshape(1, 3))
     b._t += 1
     return float(lm[0]), _GuidedCloud(b, "w"), float(es[0])
@@ -230,6 +242,10 @@ def guided_log_likelihood(N, y, model, proposal, *, resampler="multinomial", ctx
     if model.kind not in (_lib.LG1D, _lib.SV):
         raise NotImplementedError("guided proposals are built for the one-dimensional models (LinearModel, StochasticVolatility)")
     prop = np.stack([_proposal_coefficients(proposal, model, yt) for yt in y]).reshape(y.size, 1, 3)
+    if int(N) > _GUIDED_BATCH_MAX:
+        logZ = ctx.guided_log_likelihood(model.kind, model.params(), int(N), y, prop.reshape(-1, 3), resampler_id(resampler), stream)
+        x, w = _handles(ctx)
+        return x, w, logZ
     b = ctx.batch(model.kind, 1, int(N))
     z = b.log_likelihood(np.asarray(model.params(), np.float64).reshape(1, -1), y, resampler_id(resampler), stream0=stream, proposal=prop)
     b._t = y.size - 1

@@ -199,6 +199,82 @@ def test_guided_stepping_api_and_python_mirror(ctx, oracle):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("kind,N,f32", [(smc.KIND_LG1D, 20011, False), (smc.KIND_SV, 9000, False), (smc.KIND_LG1D, 1 << 16, True),
+                                         (smc.KIND_SV, 12345, True), (smc.KIND_LG1D, 7, False)])
+def test_guided_single_filter_bit_exact(ctx, oracle, kind, N, f32):
+    """the grid-wide guided step (guided_move_kernel after the sorted-resampler kernels), whole series and stepping API,
+    binary64 and binary32-state tiers: states and log-weights bit-exact against the oracle, logZ / logμ to 1e-10"""
+    T = 14
+    true = LG if kind == smc.KIND_LG1D else SVP
+    _, y = oracle.simulate(kind, true, T, 3)
+    if kind == smc.KIND_LG1D:
+        prop = np.array([oracle.optimal_proposal_lg(true, yt) for yt in y])
+    else:
+        prop = np.array([[-1.0 * (1 - 0.8 * 0.9) + 0.05 * np.log(yt * yt + 1e-3), 0.8 * 0.9, 1.3 * 0.3] for yt in y])
+    try:
+        ctx.set_precision("f32" if f32 else "f64")
+        for resampler in (smc.STRATIFIED, smc.SYSTEMATIC):
+            seed, epoch, stream = 31, 2 + resampler, 9
+            with oracle.state_f32(f32):
+                ref = oracle.guided_log_likelihood(kind, true, N, y, resampler, prop, seed, epoch, stream)
+            ctx.set_rng(seed, epoch)
+            z, lm, es = ctx.guided_log_likelihood(kind, true, N, y, prop, resampler, stream, per_step=True)
+            x, _, lw = ctx.fetch_state(want_w=False, want_logw=True)
+            np.testing.assert_array_equal(x, ref["x"])
+            np.testing.assert_array_equal(lw, ref["logw"])
+            np.testing.assert_allclose(lm, ref["logmu"], rtol=RTOL, atol=0)
+            np.testing.assert_allclose(es, ref["ess"], rtol=1e-9, atol=0)
+            assert abs(z - ref["logZ"]) <= RTOL * abs(ref["logZ"])
+            # stepping API: bootstrap init, guided steps mixed with one bootstrap step in the middle
+            ctx.set_rng(seed, epoch)
+            ctx.bootstrap_init(kind, true, N, y[0], stream)
+            with oracle.state_f32(f32):
+                xo, lwo = oracle.bootstrap_init(kind, true, N, y[0], seed, epoch, stream)
+                for t in range(1, 6):
+                    if t == 3:
+                        lmu, _ = ctx.bootstrap_step(y[t], resampler)
+                        oracle.bootstrap_step(kind, true, xo, lwo, y[t], t, resampler, seed, epoch, stream)
+                    else:
+                        lmu, _ = ctx.guided_step(y[t], prop[t], resampler)
+                        oracle.guided_step(kind, true, xo, lwo, y[t], t, resampler, prop[t], seed, epoch, stream)
+                    lmo, _, _ = oracle.normalize(lwo)
+                    assert abs(lmu - lmo) <= RTOL * abs(lmo)
+            x, _, lw = ctx.fetch_state(want_w=False, want_logw=True)
+            np.testing.assert_array_equal(x, xo)
+            np.testing.assert_array_equal(lw, lwo)
+    finally:
+        ctx.set_precision("f64")
+
+
+@pytest.mark.gpu
+def test_guided_single_filter_errors_and_python_mirror(ctx, oracle):
+    """UCSV and multinomial resampling are refused on the grid-wide guided path; particle_filter / particle_filter! route
+    clouds above 8192 particles to it"""
+    _, y = oracle.simulate(0, LG, 6, 3)
+    ctx.bootstrap_init(smc.KIND_UCSV, [0.2, 0.2, 3.0, 1.0, 1.0], 4096, 1.0)
+    with pytest.raises(smc.SMCBError):
+        ctx.guided_step(1.0, [0.0, 1.0, 1.0], smc.SYSTEMATIC)
+    ctx.bootstrap_init(smc.KIND_LG1D, LG, 4096, y[0])
+    with pytest.raises(smc.SMCBError):
+        ctx.guided_step(y[1], [0.0, 1.0, 1.0], smc.MULTINOMIAL)
+    with pytest.raises(smc.SMCBError):
+        ctx.guided_step(y[1], [0.0, 1.0, -1.0], smc.SYSTEMATIC)
+    lg, N = smc.LinearGaussian(0.5, 1.0, 0.9, 0.8), 30000
+    ctx.set_rng(4, 4)
+    x, w, logmu = smc.particle_filter(N, y[0], lg, smc.locally_optimal_proposal, ctx=ctx, stream=1)
+    xo, lwo = oracle.bootstrap_init(0, LG, N, y[0], 4, 4, 1)
+    for t in range(1, 6):
+        logmu, w, ess = smc.particle_filter_(x, w, y[t], lg, smc.locally_optimal_proposal, resampler="systematic")
+        oracle.guided_step(0, LG, xo, lwo, y[t], t, oracle.SYSTEMATIC, oracle.optimal_proposal_lg(LG, y[t]), 4, 4, 1)
+    np.testing.assert_array_equal(np.asarray(x), xo[0])
+    _, wo, _ = oracle.normalize(lwo)
+    np.testing.assert_allclose(np.asarray(w), wo, rtol=RTOL)
+    ctx.set_rng(4, 4)
+    x2, _, _ = smc.guided_log_likelihood(N, y, lg, smc.locally_optimal_proposal, resampler="systematic", ctx=ctx, stream=1)
+    np.testing.assert_array_equal(np.asarray(x2), xo[0])
+
+
+@pytest.mark.gpu
 def test_guided_variance_reduction_on_device(ctx, oracle):
     """the point of a proposal: at equal N the locally optimal proposal's logZ scatters far less around the matched-init
     Kalman likelihood than the bootstrap filter's (LG1D, N = 512, 32 independent streams in one batch each)"""
