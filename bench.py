@@ -341,6 +341,14 @@ def widen_leg(ctx, M=512, N=1024, T=100):
         ms = b.timing()[0]
         out[name] = {"ms_per_sweep": ms, "particle_updates_per_s": M * N * T / (ms * 1e-3), "sd_logZ_over_theta": float(np.std(z)),
                      "mean_logZ": float(np.mean(z))}
+    # one large-N guided filter (guided_move_kernel in place of move_kernel, log-weights stored: 56 B per particle-update)
+    Ng, yg = 1 << 24, y[:50]
+    ctx.guided_log_likelihood(smc.KIND_LG1D, LG_PARAMS, Ng, yg, prop[:50, 0], smc.SYSTEMATIC)
+    zg = ctx.guided_log_likelihood(smc.KIND_LG1D, LG_PARAMS, Ng, yg, prop[:50, 0], smc.SYSTEMATIC)
+    msg = ctx.timing()[0]["total"]
+    out["guided_single_filter"] = {"workload": "LG1D N=2^24, T=50, systematic, locally optimal proposal", "ms_per_sweep": msg,
+                                   "particle_updates_per_s": Ng * 50 / (msg * 1e-3), "roofline_frac_56B": Ng * 50 * 56 / (msg * 1e-3) / (measured_peak()[0] * 1e9),
+                                   "logZ": zg}
     t0 = time.perf_counter()
     mean, var = b.weighted_moments()
     out["per_theta_moments_ms"] = (time.perf_counter() - t0) * 1e3
