@@ -291,7 +291,8 @@ def o_smc2_step(smc, y, t):
 # ----------------------------------------------------------------------------- IBIS (ibis.jl)
 class OIBIS:
     """IBIS(M, model, prior, chain, ess_threshold, min_ar)  ibis.jl:26-52: the θ-level machinery of
-    SMC with the Kalman filter as the (exact) inner filter; LG1D only."""
+    SMC with the Kalman filter as the (exact) inner filter.  `model(θ)` returns (kind, params) for a univariate
+    LinearModel or (("mv", d), block) for a multivariate one (block = A, B, Q, R, x0, Σ0 row-major)."""
 
     def __init__(self, M, model, prior, chain, ess_threshold, min_ar=-1.0, seed=1998, theta_resampler=o.MULTINOMIAL):
         self.M, self.chain, self.model, self.prior, self.seed = M, chain, model, prior, seed
@@ -301,13 +302,32 @@ class OIBIS:
         self.logZ = np.zeros(M)
         self.ess, self.ess_min = 1.0 * M, M * ess_threshold
         self.acc_threshold, self.acc_ratio = min_ar, 0.0
+        kind0 = self.model(self.theta[0])[0]
+        self.d = kind0[1] if isinstance(kind0, tuple) else None
         P = self.params(self.theta)
-        self.x = P[:, 4].copy()                            # model(θ).x0   ibis.jl:39
-        self.Sigma = P[:, 5].copy()                        # model(θ).σ0   ibis.jl:40
+        if self.d is None:
+            self.x = P[:, 4].copy()                        # model(θ).x0   ibis.jl:39
+            self.Sigma = P[:, 5].copy()                    # model(θ).σ0   ibis.jl:40
+        else:
+            d = self.d
+            self.x = P[:, 2 * d * d + d + 1: 2 * d * d + 2 * d + 1].copy()
+            self.Sigma = P[:, 2 * d * d + 2 * d + 1:].reshape(M, d, d).copy()
         self.n_resample, self.n_rejuv = 0, 0
 
     def params(self, theta):
+        if self.d is not None:
+            return np.stack([np.asarray(self.model(th)[1], np.float64) for th in theta])
         return np.stack([o.params8(self.model(th)[1]) for th in theta])
+
+    def kalman_loglik(self, Pm, y):
+        if self.d is None:
+            return o.kalman_loglik(Pm, y, matched_init=False)
+        return o.kalman_mv_loglik(self.d, Pm, y, matched_init=False)
+
+    def kalman_step(self, Pm, x, S, y):
+        if self.d is None:
+            return o.kalman_step(Pm, x, S, y)
+        return o.kalman_mv_step(self.d, Pm, x, S, y)
 
 
 def o_ibis_resample(s):
@@ -333,9 +353,9 @@ def o_ibis_rejuvenate(s, y):
         prop = s.theta + ((scales[c] * Sigma[0, 0]) * z if uni else z @ np.linalg.cholesky(scales[c] * Sigma).T)
         ok = np.array([s.prior.insupport(th) for th in prop])
         P = s.params(np.where(ok[:, None], prop, s.theta))
-        zprop, xprop, Sprop = np.full(M, -math.inf), np.zeros(M), np.zeros(M)
+        zprop, xprop, Sprop = np.full(M, -math.inf), np.zeros_like(s.x), np.zeros_like(s.Sigma)
         for m in np.flatnonzero(ok):
-            xprop[m], Sprop[m], zprop[m] = o.kalman_loglik(P[m], y, matched_init=False)   # log_likelihood(y, model(θ_prop))  ibis.jl:100
+            xprop[m], Sprop[m], zprop[m] = s.kalman_loglik(P[m], y)                       # log_likelihood(y, model(θ_prop))  ibis.jl:100
         lp_prop = np.array([s.prior.logpdf(th) if k else -math.inf for th, k in zip(prop, ok)])
         with np.errstate(invalid="ignore", divide="ignore"):
             ratio = (zprop - s.logZ) + (lp_prop - lp_cur)
@@ -343,8 +363,8 @@ def o_ibis_rejuvenate(s, y):
             accept = ok & (zprop + lp_prop > -math.inf) & (np.log(u) < ratio)
         s.logZ = np.where(accept, zprop, s.logZ)
         s.theta = np.where(accept[:, None], prop, s.theta)
-        s.x = np.where(accept, xprop, s.x)
-        s.Sigma = np.where(accept, Sprop, s.Sigma)
+        s.x = np.where(accept.reshape((-1,) + (1,) * (s.x.ndim - 1)), xprop, s.x)
+        s.Sigma = np.where(accept.reshape((-1,) + (1,) * (s.Sigma.ndim - 1)), Sprop, s.Sigma)
         lp_cur = np.where(accept, lp_prop, lp_cur)
         acc |= accept
     s.omega = np.full(M, 1.0 / M)
@@ -357,7 +377,7 @@ def o_ibis_init(s, y):
     P = s.params(s.theta)
     ll = np.empty(s.M)
     for m in range(s.M):
-        s.x[m], s.Sigma[m], ll[m] = o.kalman_step(P[m], s.x[m], s.Sigma[m], y[0])
+        s.x[m], s.Sigma[m], ll[m] = s.kalman_step(P[m], s.x[m], s.Sigma[m], y[0])
     s.logZ = ll.copy()
     _, s.omega, s.ess = o.normalize(ll)
     return s
@@ -374,7 +394,7 @@ def o_ibis_step(s, y, t):
         logw = np.log(s.omega)
     P = s.params(s.theta)
     for m in range(s.M):
-        s.x[m], s.Sigma[m], ll = o.kalman_step(P[m], s.x[m], s.Sigma[m], y[t])     # ibis.jl:172-177
+        s.x[m], s.Sigma[m], ll = s.kalman_step(P[m], s.x[m], s.Sigma[m], y[t])     # ibis.jl:172-177
         logw[m] += ll
         s.logZ[m] += ll
     _, s.omega, s.ess = o.normalize(logw)

@@ -239,8 +239,8 @@ int smco_guided_step(int kind, const double *P, int64_t n, double y, uint32_t t,
   if (kind == KIND_UCSV) return -1;
   double D[8];
   smco_derive(kind, P, D);
-  const double c0 = prop[0], c1 = prop[1], c2 = prop[2], lc2 = o_log(prop[2]);
-  const double sdf = D[2], lsdf = (kind == KIND_LG1D) ? D[7] : D[4];
+  const double c0 = prop[0], c1 = prop[1], c2 = prop[2], lc2 = o_log(prop[2]), ic2 = 1.0 / prop[2];
+  const double isdf = 1.0 / D[2], lsdf = (kind == KIND_LG1D) ? D[7] : D[4];
   int64_t *a = (int64_t *)malloc(sizeof(int64_t) * (size_t)n);              /* a = resample(weights) :66 */
   smco_ancestors(logw, n, resampler, seed, epoch, stream, t, a);
   double *xp = (double *)malloc(sizeof(double) * (size_t)n);               /* xp = deepcopy(x[a]) :68 */
@@ -251,8 +251,8 @@ int smco_guided_step(int kind, const double *P, int64_t n, double y, uint32_t t,
     double xi = fma(c2, z, mq);                                             /* x[i] = rand(proposal(model, xp[i])) :73 */
     round_state(&xi, 1);                                                    /* SPEC §9: the stored state is what every density sees */
     double mf = (kind == KIND_LG1D) ? D[0] * xp[i] : fma(D[1], xp[i] - D[0], D[0]);
-    double zt = (xi - mf) / sdf;
-    double zq = (xi - mq) / c2;
+    double zt = (xi - mf) * isdf;
+    double zq = (xi - mq) * ic2;
     double lf = fma(-0.5 * zt, zt, -lsdf);                                  /* logpdf(transition(model, xp[i]), x[i]) :77 */
     double lq = fma(-0.5 * zq, zq, -lc2);                                   /* logpdf(proposal(xp[i]), x[i]) :78 */
     x[i] = xi;

@@ -16,7 +16,7 @@ struct BatchArgs {
   const double* derived;   // [M][8]
   const uint8_t* active;   // [M] or null
   const double* y;         // observations consumed by this launch, y[0] is for time t_begin
-  const double* prop;      // guided kernels only: [t_end - t_begin + 1][M][4] proposal coefficients (SPEC §10), row 0 is for t_begin
+  const double* prop;      // guided kernels only: [t_end - t_begin + 1][M][5] proposal coefficients (SPEC §10), row 0 is for t_begin
   double* x;               // [M][d][ld]
   double* logw;            // [M][ld]
   StepStats* stats;        // [M]
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(MAXT) batch_kernel(const BatchArgs a) {
       __syncthreads();  // C: every parent read before the cloud is overwritten
       // ---- x_i ~ transition(xp_i); logw_i = logpdf(observation(x_i), y)              particles.jl:122-125
       // (guided: x_i ~ proposal(xp_i); logw_i += logpdf(transition(xp_i), x_i) - logpdf(proposal(xp_i), x_i)   :73-78)
-      double pc[kProposalStride] = {0.0, 0.0, 0.0, 0.0};
+      double pc[kProposalStride] = {0.0, 0.0, 0.0, 0.0, 0.0};
       if constexpr (GUIDED) {
         const double* g = a.prop + ((int64_t)(t - a.t_begin) * (int64_t)gridDim.x + m) * kProposalStride;
 #pragma unroll
@@ -641,6 +641,19 @@ __global__ void kalman_mv_kernel(const double* __restrict__ models, const uint8_
   }
 }
 
+// (c0, c1, c2) -> (c0, c1, c2, det_log(c2), 1 / c2) for every (t, θ) of a guided launch
+__global__ void proposal_prepare_kernel(const double* __restrict__ raw, double* __restrict__ out, int64_t n) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const double c0 = raw[3 * j], c1 = raw[3 * j + 1], c2 = raw[3 * j + 2];
+  double* q = out + kProposalStride * j;
+  q[0] = c0;
+  q[1] = c1;
+  q[2] = c2;
+  q[3] = det_log(c2);
+  q[4] = 1.0 / c2;
+}
+
 template <class Model, int PAIRS, int MAXT, bool GUIDED>
 void launch_batch(const BatchArgs& a, int64_t M, int threads, size_t smem, cudaStream_t stream) {
   auto kern = batch_kernel<Model, PAIRS, MAXT, GUIDED>;
@@ -728,8 +741,8 @@ void BatchFilter::upload_params(const double* params, const uint8_t* active) {
   if (active) SMCB_CUDA_TRY(cudaMemcpyAsync(active_, active, M_, cudaMemcpyHostToDevice, stream_));
 }
 
-// proposal: [rows][M][3] host coefficients (c0, c1, c2) of x' ~ N(c0 + c1 xp, c2^2); stored as [rows][M][4] with
-// det_log(c2) appended (SPEC §10)
+// proposal: [rows][M][3] host coefficients (c0, c1, c2) of x' ~ N(c0 + c1 xp, c2^2); the device block is [rows][M][5] with
+// det_log(c2) and 1 / c2 appended by proposal_prepare_kernel (SPEC §10; the device det_log is the host's bit for bit)
 void BatchFilter::upload_proposal(const double* proposal, int64_t rows) {
   if (d_ != 1) throw Error{SMCB_ERR_UNSUPPORTED, "guided proposals are defined for the one-dimensional models (LG1D, SV)"};
   const int64_t n = rows * M_;
@@ -742,17 +755,14 @@ void BatchFilter::upload_proposal(const double* proposal, int64_t rows) {
     cudaFree(prop_dev_);
     prop_dev_ = nullptr;
     prop_cap_ = 0;
-    SMCB_CUDA_TRY(cudaMalloc(&prop_dev_, sizeof(double) * kProposalStride * n));
+    SMCB_CUDA_TRY(cudaMalloc(&prop_dev_, sizeof(double) * (kProposalStride + 3) * n));  // derived block, then the raw copy
     prop_cap_ = n;
   }
-  prop_host_.resize((size_t)(kProposalStride * n));
-  for (int64_t j = 0; j < n; ++j) {
-    prop_host_[4 * j + 0] = proposal[3 * j + 0];
-    prop_host_[4 * j + 1] = proposal[3 * j + 1];
-    prop_host_[4 * j + 2] = proposal[3 * j + 2];
-    prop_host_[4 * j + 3] = det_log(proposal[3 * j + 2]);
-  }
-  SMCB_CUDA_TRY(cudaMemcpyAsync(prop_dev_, prop_host_.data(), sizeof(double) * kProposalStride * n, cudaMemcpyHostToDevice, stream_));
+  double* raw = prop_dev_ + kProposalStride * prop_cap_;
+  SMCB_CUDA_TRY(cudaMemcpyAsync(raw, proposal, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, stream_));
+  proposal_prepare_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream_>>>(raw, prop_dev_, n);
+  SMCB_CUDA_TRY(cudaGetLastError());
+  ++launches_;
 }
 
 void BatchFilter::launch(bool from_init, uint32_t t_begin, uint32_t t_end, int resampler, int64_t, bool guided) {

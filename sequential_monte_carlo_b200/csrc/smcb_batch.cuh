@@ -81,9 +81,8 @@ class BatchFilter {
   int32_t* slots_dev_ = nullptr;  // [2][slot_cap_]
   int64_t slot_cap_ = 0;
   std::vector<double> host_tmp_;
-  double* prop_dev_ = nullptr;  // [rows][M][4] proposal coefficients of the guided launches
+  double* prop_dev_ = nullptr;  // [cap][5] proposal coefficients of the guided launches, then [cap][3] raw upload
   int64_t prop_cap_ = 0;
-  std::vector<double> prop_host_;
 
   cudaEvent_t ev_[2] = {nullptr, nullptr};
   double last_ms_ = 0;

@@ -1575,7 +1575,7 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler, cons
       throw Error{SMCB_ERR_UNSUPPORTED, "guided single filter: stratified or systematic resampling (multinomial guided filters run on the batched engine, N <= 8192)"};
     if (!(proposal[2] > 0.0) || !std::isfinite(proposal[2]) || !std::isfinite(proposal[0]) || !std::isfinite(proposal[1]))
       throw Error{SMCB_ERR_BAD_ARG, "proposal: coefficients must be finite and the standard deviation c2 > 0"};
-    pc.c[0] = proposal[0]; pc.c[1] = proposal[1]; pc.c[2] = proposal[2]; pc.c[3] = det_log(proposal[2]);
+    pc.c[0] = proposal[0]; pc.c[1] = proposal[1]; pc.c[2] = proposal[2]; pc.c[3] = det_log(proposal[2]); pc.c[4] = 1.0 / proposal[2];
   }
   if (resampler == RESAMPLE_MULTINOMIAL) {  // unsorted thresholds: materialised CDF + per-particle global search
     launch_scan(stat_index, true);

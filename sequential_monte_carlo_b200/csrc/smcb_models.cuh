@@ -115,18 +115,18 @@ template <class Model>
 struct TransDensity;
 template <>
 struct TransDensity<ModelLG1D> {
-  double sd, lsd;
-  SMCB_HD void load(const double* d) { sd = d[2]; lsd = d[7]; }
+  double isd, lsd;  // 1 / sd (one IEEE division per thread, not per particle), log sd
+  SMCB_HD void load(const double* d) { isd = 1.0 / d[2]; lsd = d[7]; }
   SMCB_HD double mean(const ModelLG1D& m, double xp) const { return m.A * xp; }
 };
 template <>
 struct TransDensity<ModelSV> {
-  double sd, lsd;
-  SMCB_HD void load(const double* d) { sd = d[2]; lsd = d[4]; }
+  double isd, lsd;
+  SMCB_HD void load(const double* d) { isd = 1.0 / d[2]; lsd = d[4]; }
   SMCB_HD double mean(const ModelSV& m, double xp) const { return fma(m.rho, xp - m.mu, m.mu); }
 };
 
-constexpr int kProposalStride = 4;  // c0, c1, c2, det_log(c2): the proposal x' ~ N(c0 + c1 xp, c2^2) of one (t, θ)
+constexpr int kProposalStride = 5;  // c0, c1, c2, det_log(c2), 1 / c2: the proposal x' ~ N(c0 + c1 xp, c2^2) of one (t, θ)
 
 struct ProposalCoef {  // by-value kernel argument of the grid-wide guided step
   double c[kProposalStride];
@@ -136,8 +136,8 @@ struct ProposalCoef {  // by-value kernel argument of the grid-wide guided step
 // proposal mean fma(c1, xp, c0) that produced x'
 template <class Model>
 SMCB_HD double guided_correction(const Model& mdl, const TransDensity<Model>& f, const double* pc, double mq, double xp, double x) {
-  const double zt = (x - f.mean(mdl, xp)) / f.sd;
-  const double zq = (x - mq) / pc[2];
+  const double zt = (x - f.mean(mdl, xp)) * f.isd;
+  const double zq = (x - mq) * pc[4];
   const double lf = fma(-0.5 * zt, zt, -f.lsd);
   const double lq = fma(-0.5 * zq, zq, -pc[3]);
   return lf - lq;

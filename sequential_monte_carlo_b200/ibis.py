@@ -1,6 +1,7 @@
 """IBIS — host mirror of /root/reference/src/ibis.jl: the θ-level sampler of SMC² with the exact
-Kalman filter as inner filter (LG1D only; no state particles).  The M scalar recursions run as one
-device launch (csrc/smcb_batch.cu: kalman_kernel)."""
+Kalman filter as inner filter (no state particles).  The M recursions run as one device launch
+(csrc/smcb_batch.cu): kalman_kernel for univariate LinearModels, kalman_mv_kernel for multivariate ones
+(MultivariateLinearGaussian / hodrick_prescott; the reference's IBIS is generic in the state type XT, ΣT, ibis.jl:3-52)."""
 import math
 import sys
 
@@ -9,6 +10,7 @@ import numpy as np
 from . import _lib
 from .particles import default_context, resampler_id
 from .smc_samplers import _propose, random_walk_kernel
+from .state_space_models import MultivariateLinearModel
 
 
 class IBIS:
@@ -23,9 +25,15 @@ class IBIS:
         self.kernel = random_walk_kernel
         self.θ = prior.sample(self.M, self.seed)                     # :34
         self.ω = np.full(self.M, 1.0 / self.M)                       # :35
+        self.d = None                                                # state dimension of a multivariate model, else None
         P = self._params(self.θ)
-        self.x = P[:, 4].copy()                                      # [mod.x0 for mod in mods]   :38
-        self.Σ = P[:, 5].copy()                                      # [mod.σ0 for mod in mods]   :39
+        if self.d is None:
+            self.x = P[:, 4].copy()                                  # [mod.x0 for mod in mods]   :38
+            self.Σ = P[:, 5].copy()                                  # [mod.σ0 for mod in mods]   :39
+        else:
+            d = self.d
+            self.x = P[:, 2 * d * d + d + 1: 2 * d * d + 2 * d + 1].copy()
+            self.Σ = P[:, 2 * d * d + 2 * d + 1:].reshape(self.M, d, d).copy()
         self.logZ = np.zeros(self.M)
         self.ess, self.ess_min = 1.0 * self.M, self.M * float(ess_threshold)
         self.acc_threshold, self.acc_ratio = float(min_ar), 0.0
@@ -33,9 +41,27 @@ class IBIS:
 
     def _params(self, θ):
         ms = [self.model(th) for th in θ]
+        if ms and isinstance(ms[0], MultivariateLinearModel):
+            self.d = ms[0].state_dim
+            return np.stack([m.block() for m in ms])
         if ms and ms[0].kind != _lib.LG1D:
             raise TypeError("IBIS needs a LinearModel (the inner filter is the Kalman filter, ibis.jl:100,172)")
         return np.stack([m.params8() for m in ms])
+
+    def _kalman_loglik(self, P, y, active):
+        """M × log_likelihood(y, model(θ_m))  (ibis.jl:100) -> (logZ [M], x_T, Σ_T)"""
+        if self.d is None:
+            return self.ctx.kalman_loglik(P, y, matched_init=False, active=active)
+        return self.ctx.kalman_mv_loglik(self.d, P, y, matched_init=False, active=active)
+
+    def _kalman_step(self, P, y):
+        """M × kalman_filter(model(θ_m), x_m, Σ_m, y)  (ibis.jl:172-177) -> (x, Σ, step log-likelihoods)"""
+        if self.d is None:
+            return self.ctx.kalman_step(P, self.x, self.Σ, y)
+        return self.ctx.kalman_mv_step(self.d, P, self.x, self.Σ, y)
+
+    def _where(self, accept, new, old):
+        return np.where(accept.reshape((-1,) + (1,) * (np.ndim(old) - 1)), new, old)
 
 
 def resample_(ibis):
@@ -66,7 +92,7 @@ def rejuvenate_(ibis, y, ξ=1.0, verbose=False):
         θ_prop = _propose(ibis.θ, Σk, univariate, scales[c], z)
         ok = np.array([ibis.prior.insupport(th) for th in θ_prop])
         P = ibis._params(np.where(ok[:, None], θ_prop, ibis.θ))
-        logZ_prop, x_prop, Σ_prop = ibis.ctx.kalman_loglik(P, y, matched_init=False, active=ok.astype(np.uint8))   # :100
+        logZ_prop, x_prop, Σ_prop = ibis._kalman_loglik(P, y, ok.astype(np.uint8))                                   # :100
         lp_prop = np.array([ibis.prior.logpdf(th) if o else -math.inf for th, o in zip(θ_prop, ok)])
         with np.errstate(invalid="ignore", divide="ignore"):
             ratio = ξ * (logZ_prop - ibis.logZ) + (lp_prop - lp_cur)
@@ -74,8 +100,8 @@ def rejuvenate_(ibis, y, ξ=1.0, verbose=False):
             accept = ok & (logZ_prop + lp_prop > -math.inf) & (np.log(u) < ratio)
         ibis.logZ = np.where(accept, logZ_prop, ibis.logZ)
         ibis.θ = np.where(accept[:, None], θ_prop, ibis.θ)
-        ibis.x = np.where(accept, x_prop, ibis.x)
-        ibis.Σ = np.where(accept, Σ_prop, ibis.Σ)
+        ibis.x = ibis._where(accept, x_prop, ibis.x)
+        ibis.Σ = ibis._where(accept, Σ_prop, ibis.Σ)
         lp_cur = np.where(accept, lp_prop, lp_cur)
         acc |= accept
     ibis.ω = np.full(M, 1.0 / M)
@@ -88,7 +114,7 @@ def rejuvenate_(ibis, y, ξ=1.0, verbose=False):
 def smc2(ibis, y):
     """smc²(ibis, y) (ibis.jl:128-147)"""
     y = np.ascontiguousarray(y, np.float64)
-    ibis.x, ibis.Σ, ll = ibis.ctx.kalman_step(ibis._params(ibis.θ), ibis.x, ibis.Σ, y[0])
+    ibis.x, ibis.Σ, ll = ibis._kalman_step(ibis._params(ibis.θ), y[0])
     ibis.logZ = ll.copy()
     _, ibis.ω, ibis.ess = ibis.ctx.normalize(ll)
     return ibis
@@ -106,7 +132,7 @@ def smc2_step(ibis, y, t, verbose=True):
         ibis.rejuvenated = True
     with np.errstate(divide="ignore"):
         logω = np.log(ibis.ω)
-    ibis.x, ibis.Σ, ll = ibis.ctx.kalman_step(ibis._params(ibis.θ), ibis.x, ibis.Σ, y[t])   # :172-177
+    ibis.x, ibis.Σ, ll = ibis._kalman_step(ibis._params(ibis.θ), y[t])                      # :172-177
     logω = logω + ll
     ibis.logZ = ibis.logZ + ll
     _, ibis.ω, ibis.ess = ibis.ctx.normalize(logω)

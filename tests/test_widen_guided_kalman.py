@@ -386,3 +386,31 @@ def test_plain_c_client_runs_the_path(oracle):
         assert abs(got[f"guided_var{m}"] - float(((xo[m, 0] - mo) ** 2) @ w)) <= 1e-9
     lo = oracle.kalman_loglik(LG, y)[2]
     assert abs(got["kalman_mv"] - lo) <= 1e-12 * abs(lo) and abs(got["kalman_scalar"] - lo) <= 1e-12 * abs(lo)
+
+
+@pytest.mark.gpu
+def test_ibis_multivariate_hodrick_prescott(ctx, oracle):
+    """IBIS (ibis.jl:3-189) is generic in the state type: with a multivariate LinearModel the inner filter is the matrix
+    Kalman filter.  Hodrick–Prescott with an unknown λ ~ U(1, 2000): the device sampler against the oracle's, step by step"""
+    from oracle import samplers as S
+    from sequential_monte_carlo_b200 import ibis as ib
+    rng = np.random.default_rng(0)
+    T, M = 80, 96
+    y = np.cumsum(np.cumsum(rng.normal(0, 0.05, T))) + rng.normal(0, 1, T)
+    g = smc.IBIS(M, lambda θ: smc.hodrick_prescott(λ=θ[0], y=y), smc.product_distribution([smc.Uniform(1.0, 2000.0)]), 2, 0.5, seed=3, ctx=ctx)
+    o_ = S.OIBIS(M, lambda th: (("mv", 2), smc.hodrick_prescott(λ=th[0], y=y).block()), S.OProduct([S.OUniform(1.0, 2000.0)]), 2, 0.5, seed=3)
+    assert g.d == 2 and g.x.shape == (M, 2) and g.Σ.shape == (M, 2, 2)
+    ib.smc2(g, y)
+    S.o_ibis_init(o_, y)
+    n = 0
+    for t in range(1, T):
+        ib.smc2_step(g, y, t, verbose=False)
+        S.o_ibis_step(o_, y, t)
+        assert g.rejuvenated == o_.rejuvenated
+        n += g.rejuvenated
+    assert n >= 1
+    np.testing.assert_array_equal(g.θ, o_.theta)
+    np.testing.assert_allclose(g.logZ, o_.logZ, rtol=1e-11)
+    np.testing.assert_allclose(g.x, o_.x, rtol=1e-9, atol=1e-11)
+    np.testing.assert_allclose(g.Σ, o_.Sigma, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(g.ω, o_.omega, rtol=RTOL, atol=1e-300)
