@@ -148,6 +148,13 @@ __global__ void __launch_bounds__(MAXT) batch_kernel(const BatchArgs a) {
         }
       }
     } else {
+      // the proposal of this step is requested first: its L2 / HBM round trip hides behind the normalisation and the search
+      double pc[kProposalStride] = {0.0, 0.0, 0.0, 0.0, 0.0};
+      if constexpr (GUIDED) {
+        const double* g = a.prop + ((int64_t)(t - a.t_begin) * (int64_t)gridDim.x + m) * kProposalStride;
+#pragma unroll
+        for (int k = 0; k < kProposalStride; ++k) pc[k] = __ldg(g + k);
+      }
       // ---- normalize(previous logw) and its fixed-point CDF                         particles.jl:5-15,117
       unsigned long long q0[PAIRS], tq[PAIRS], winc[PAIRS];
       double se = 0.0, se2 = 0.0;
@@ -241,12 +248,6 @@ __global__ void __launch_bounds__(MAXT) batch_kernel(const BatchArgs a) {
       __syncthreads();  // C: every parent read before the cloud is overwritten
       // ---- x_i ~ transition(xp_i); logw_i = logpdf(observation(x_i), y)              particles.jl:122-125
       // (guided: x_i ~ proposal(xp_i); logw_i += logpdf(transition(xp_i), x_i) - logpdf(proposal(xp_i), x_i)   :73-78)
-      double pc[kProposalStride] = {0.0, 0.0, 0.0, 0.0, 0.0};
-      if constexpr (GUIDED) {
-        const double* g = a.prop + ((int64_t)(t - a.t_begin) * (int64_t)gridDim.x + m) * kProposalStride;
-#pragma unroll
-        for (int k = 0; k < kProposalStride; ++k) pc[k] = g[k];
-      }
 #pragma unroll
       for (int r = 0; r < PAIRS; ++r) {
         const int p = r * nthreads + tid;
