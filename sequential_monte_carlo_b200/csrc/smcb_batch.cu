@@ -778,7 +778,17 @@ void BatchFilter::launch(bool from_init, uint32_t t_begin, uint32_t t_end, int r
   const int64_t npad = (N_ + 1) & ~int64_t(1);
   const size_t cdf_bytes = sizeof(uint64_t) * (size_t)npad;
   const size_t x_bytes = sizeof(double) * (size_t)npad * d_;
-  const bool x_in_smem = cdf_bytes + x_bytes <= kSmemBudget;
+  bool x_in_smem = cdf_bytes + x_bytes <= kSmemBudget;
+  // A 3-component cloud of more than ~3600 particles fills more than half an SM's shared memory: one CTA per SM, nothing to
+  // overlap its barriers with.  Keeping only the CDF on chip and the cloud in global memory (the clouds of the resident CTAs
+  // stay in L2) lets two CTAs share an SM: measured on config 5 (UCSV 4096 θ × 4096, T = 100) 294 -> 266 ms of device time,
+  // results bit-identical (profiles/r1_c5_clouds_in_l2_v22.jsonl).  SMCB_BATCH_X_SMEM=0/1 forces either placement.
+  constexpr size_t kHalfSm = 113 * 1024;
+  if (x_in_smem && d_ == 3 && cdf_bytes + x_bytes > kHalfSm && cdf_bytes <= kHalfSm && threads <= 1024) x_in_smem = false;
+  if (const char* e = std::getenv("SMCB_BATCH_X_SMEM")) {
+    if (std::atoi(e) == 0) x_in_smem = false;
+    else x_in_smem = cdf_bytes + x_bytes <= kSmemBudget;
+  }
   const size_t smem = cdf_bytes + (x_in_smem ? x_bytes : 0);
   if (smem > kSmemBudget) throw Error{SMCB_ERR_UNSUPPORTED, "CDF does not fit in shared memory"};
   BatchArgs a;
