@@ -779,10 +779,13 @@ void BatchFilter::launch(bool from_init, uint32_t t_begin, uint32_t t_end, int r
   const size_t cdf_bytes = sizeof(uint64_t) * (size_t)npad;
   const size_t x_bytes = sizeof(double) * (size_t)npad * d_;
   bool x_in_smem = cdf_bytes + x_bytes <= kSmemBudget;
-  // A 3-component cloud of more than ~3600 particles fills more than half an SM's shared memory: one CTA per SM, nothing to
-  // overlap its barriers with.  Keeping only the CDF on chip and the cloud in global memory (the clouds of the resident CTAs
-  // stay in L2) lets two CTAs share an SM: measured on config 5 (UCSV 4096 θ × 4096, T = 100) 294 -> 266 ms of device time,
-  // results bit-identical (profiles/r1_c5_clouds_in_l2_v22.jsonl).  SMCB_BATCH_X_SMEM=0/1 forces either placement.
+  // Placement of the clouds, by measurement (profiles/r1_c5_clouds_in_l2_v22.jsonl, r1_batch_cloud_placement_probe_v22.jsonl):
+  // a 3-component cloud of more than ~3600 particles (UCSV, config 5: 4096 θ × 4096) runs 10 % faster when only the CDF
+  // is in shared memory and the cloud stays in global memory (the resident CTAs' clouds live in L2): 294 -> 266 ms of device
+  // time at T = 100, results bit-identical.  One-component clouds of 8192 particles show no difference (5.96 ms either way)
+  // and keep the shared-memory placement.  The cause was not profiled; the CTAs per SM do not change (1024 threads at 64
+  // registers fill the register file either way), so the candidates are the three strided component gathers hitting the
+  // same banks and the larger L1 carve-out.  SMCB_BATCH_X_SMEM=0/1 forces either placement.
   constexpr size_t kHalfSm = 113 * 1024;
   if (x_in_smem && d_ == 3 && cdf_bytes + x_bytes > kHalfSm && cdf_bytes <= kHalfSm && threads <= 1024) x_in_smem = false;
   if (const char* e = std::getenv("SMCB_BATCH_X_SMEM")) {
