@@ -164,6 +164,23 @@ def test_oracle_regression_vectors(oracle):
         assert int(np.sum(r["anc"][1:] * (np.arange(v["N"]) + 1)) % (2 ** 61 - 1)) == v["anc_checksum"]
 
 
+def test_oracle_regression_vectors_of_the_later_rows(oracle):
+    """guided filter (docs/SPEC.md §10) and matrix Kalman filter: committed bit patterns of the oracle (tools/gen_golden.py)"""
+    for v in json.load(open(os.path.join(GOLD, "widen_vectors.json"))):
+        _, y = oracle.simulate(0 if v["what"] == "kalman_mv" else v["kind"], LG if v["what"] == "kalman_mv" else v["params"], v["T"], v["data_seed"])
+        if v["what"] == "guided":
+            prop = np.array([[float.fromhex(c) for c in row] for row in v["prop_hex"]])
+            r = oracle.guided_log_likelihood(v["kind"], v["params"], v["N"], y, v["resampler"], prop, v["seed"], v["epoch"], v["stream"])
+            assert float(r["logZ"]).hex() == v["logZ_hex"]
+            assert float(np.sum(r["x"])).hex() == v["x_sum_hex"] and float(np.sum(r["logw"])).hex() == v["logw_sum_hex"]
+            assert float(r["x"][0, -1]).hex() == v["x_last_hex"]
+        else:
+            blk = np.array([float.fromhex(c) for c in v["block_hex"]])
+            x, S, ll = oracle.kalman_mv_loglik(v["d"], blk, y, v["matched_init"])
+            assert float(ll).hex() == v["ll_hex"]
+            assert [float(a).hex() for a in x] == v["x_hex"] and [float(a).hex() for a in S.ravel()] == v["S_hex"]
+
+
 def test_batch_oracle_equals_loop(oracle):
     rng = np.random.default_rng(6)
     M, N, T = 5, 100, 12

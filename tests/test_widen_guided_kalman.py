@@ -414,3 +414,54 @@ def test_ibis_multivariate_hodrick_prescott(ctx, oracle):
     np.testing.assert_allclose(g.x, o_.x, rtol=1e-9, atol=1e-11)
     np.testing.assert_allclose(g.Σ, o_.Sigma, rtol=1e-9, atol=1e-12)
     np.testing.assert_allclose(g.ω, o_.omega, rtol=RTOL, atol=1e-300)
+
+
+@pytest.mark.gpu
+def test_cuda_path_against_committed_golden_vectors(ctx):
+    """tests/golden/*.json hold bit patterns written by tools/gen_golden.py from the oracle; here the CUDA path alone (no
+    oracle in the loop) must reproduce them: states and ancestors bit for bit, logZ to 1e-10"""
+    import json
+    import os
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    for v in json.load(open(os.path.join(gold, "oracle_vectors.json"))):
+        _, y = smc._lib.simulate(v["kind"], v["params"], v["T"], v["data_seed"])
+        assert [float(a).hex() for a in y[:4]] == v["y_hex"]
+        ctx.set_rng(v["seed"], v["epoch"])
+        ctx.record_ancestors(True)
+        try:
+            z = ctx.log_likelihood(v["kind"], v["params"], v["N"], y, v["resampler"], v["stream"])
+            x, _, _ = ctx.fetch_state(want_w=False)
+            anc = ctx.fetch_ancestors(v["T"] - 1)
+        finally:
+            ctx.record_ancestors(False)
+        zg = float.fromhex(v["logZ_hex"])
+        assert abs(z - zg) <= RTOL * abs(zg)
+        assert [float(a).hex() for a in x[:, -1]] == v["x_last_hex"] and float(np.sum(x)).hex() == v["x_sum_hex"]
+        assert [int(a) for a in anc[0][:16]] == v["anc_t1_head"]
+        assert int(np.sum(anc * (np.arange(v["N"]) + 1)) % (2 ** 61 - 1)) == v["anc_checksum"]
+    for v in json.load(open(os.path.join(gold, "widen_vectors.json"))):
+        if v["what"] == "guided":
+            _, y = smc._lib.simulate(v["kind"], v["params"], v["T"], v["data_seed"])
+            prop = np.array([[float.fromhex(c) for c in row] for row in v["prop_hex"]])
+            b = ctx.batch(v["kind"], 1, v["N"])
+            ctx.set_rng(v["seed"], v["epoch"])
+            z = b.log_likelihood(smc._lib.params8(v["params"]).reshape(1, -1), y, v["resampler"], v["stream"], proposal=prop[:, None, :])
+            x, _, lw = b.fetch(want_w=False, want_logw=True)
+            b.close()
+            zg = float.fromhex(v["logZ_hex"])
+            assert abs(z[0] - zg) <= RTOL * abs(zg)
+            assert float(np.sum(x[0])).hex() == v["x_sum_hex"] and float(np.sum(lw[0])).hex() == v["logw_sum_hex"]
+            assert float(x[0, 0, -1]).hex() == v["x_last_hex"]
+            if v["resampler"] != smc.MULTINOMIAL:      # the grid-wide guided path takes the sorted resamplers
+                ctx.set_rng(v["seed"], v["epoch"])
+                ctx.guided_log_likelihood(v["kind"], v["params"], v["N"], y, prop, v["resampler"], v["stream"])
+                xs, _, lws = ctx.fetch_state(want_w=False, want_logw=True)
+                assert float(np.sum(xs)).hex() == v["x_sum_hex"] and float(np.sum(lws)).hex() == v["logw_sum_hex"]
+        else:
+            _, y = smc._lib.simulate(0, LG, v["T"], v["data_seed"])
+            blk = np.array([float.fromhex(c) for c in v["block_hex"]])
+            ll, x, S = ctx.kalman_mv_loglik(v["d"], blk, y, v["matched_init"])
+            lg = float.fromhex(v["ll_hex"])
+            assert abs(ll[0] - lg) <= 1e-12 * abs(lg)
+            np.testing.assert_allclose(x[0], [float.fromhex(c) for c in v["x_hex"]], rtol=1e-11, atol=1e-13)
+            np.testing.assert_allclose(S[0].ravel(), [float.fromhex(c) for c in v["S_hex"]], rtol=1e-11, atol=1e-13)

@@ -41,6 +41,28 @@ for kind, P in MODELS.items():
                         anc_checksum=int(np.sum(r["anc"][1:] * (np.arange(257) + 1)) % (2 ** 61 - 1))))
 json.dump(vec, open(os.path.join(G, "oracle_vectors.json"), "w"), indent=1)
 
+# the rows built after the hot path: guided filter (docs/SPEC.md §10) and the matrix Kalman filter
+wid = []
+for kind, P in ((0, MODELS[0]), (1, MODELS[1])):
+    _, y = o.simulate(kind, P, 30, 1998)
+    if kind == 0:
+        prop = np.array([o.optimal_proposal_lg(P, yt) for yt in y])
+    else:
+        prop = np.array([[P[0] * (1 - 0.8 * P[1]) + 0.05 * np.log(yt * yt + 1e-3), 0.8 * P[1], 1.3 * P[2]] for yt in y])
+    for rs in (0, 2):
+        r = o.guided_log_likelihood(kind, P, 257, y, rs, prop, 7, 3, 2)
+        wid.append(dict(what="guided", kind=kind, params=P, N=257, T=30, data_seed=1998, resampler=rs, seed=7, epoch=3, stream=2,
+                        prop_hex=[[float(v).hex() for v in row] for row in prop],
+                        logZ_hex=float(r["logZ"]).hex(), x_sum_hex=float(np.sum(r["x"])).hex(),
+                        logw_sum_hex=float(np.sum(r["logw"])).hex(), x_last_hex=float(r["x"][0, -1]).hex()))
+_, y = o.simulate(0, MODELS[0], 60, 1998)
+hp = o.mv_block([[2, -1], [1, 0]], [1, 0], [[1 / 1600.0, 0], [0, 0]], [1.0], [3 * y[0] - 2 * y[1], 2 * y[0] - y[1]], 1000 * np.eye(2))
+for matched in (0, 1):
+    x, S, ll = o.kalman_mv_loglik(2, hp, y, matched)
+    wid.append(dict(what="kalman_mv", d=2, block_hex=[float(v).hex() for v in hp], T=60, data_seed=1998, matched_init=matched,
+                    ll_hex=float(ll).hex(), x_hex=[float(v).hex() for v in x], S_hex=[float(v).hex() for v in S.ravel()]))
+json.dump(wid, open(os.path.join(G, "widen_vectors.json"), "w"), indent=1)
+
 # det-math spot values (bit patterns) — any change of a coefficient or operation order shows up here
 xs = [-700.0, -37.25, -1.0, -1e-3, 0.0, 0.5, 1.0, 10.125, 700.0]
 us = [2.0 ** -53, 1e-9, 0.1, 0.5, 0.75, 1 - 2.0 ** -53]
