@@ -261,6 +261,8 @@ def quantile(x, w_or_p, p=None):
         return quantile_smc(x, w_or_p)
     weighted = p is not None
     probs = np.atleast_1d(np.asarray(p if weighted else w_or_p, np.float64))
+    if isinstance(x, _GuidedCloud):           # a guided filter's cloud lives in a one-θ batch: per-cloud radix select there
+        return x._batch.weighted_quantiles(probs, weighted=weighted)[0, 0]
     if x._stale():
         raise RuntimeError("stale particle cloud")
     q = x._ctx.summary(probs, weighted=weighted)[2]
@@ -270,6 +272,11 @@ def quantile(x, w_or_p, p=None):
 def weighted_mean_var(x, w=None):
     """(mean, var) of the cloud x under the weights w (mean(x, weights(w)), var(x, weights(w)):
     examples/inflation_example.jl:46), on the device."""
+    if isinstance(x, _GuidedCloud):
+        if w is None:
+            raise NotImplementedError("unweighted moments of a guided filter's cloud: pass its weights (the resampled cloud is weighted)")
+        m, v = x._batch.weighted_moments()
+        return m[0, 0], v[0, 0]
     if x._stale():
         raise RuntimeError("stale particle cloud")
     m, v, _ = x._ctx.summary((), weighted=w is not None)

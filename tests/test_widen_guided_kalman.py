@@ -175,6 +175,13 @@ def test_guided_stepping_api_and_python_mirror(ctx, oracle):
         logZ += logmu
     np.testing.assert_array_equal(np.asarray(x), xo[0])
     np.testing.assert_allclose(np.asarray(w), wo, rtol=RTOL)
+    # summaries of the guided cloud on the device: quantile(x, weights(w), p), mean / var(x, weights(w))
+    ps = [0.25, 0.5, 0.75]
+    mo, vo, qo = oracle.weighted_summary(xo, lwo, ps, weighted=True)
+    np.testing.assert_array_equal(smc.quantile(x, w, ps), qo[0])
+    np.testing.assert_array_equal(smc.quantile(x, ps), oracle.weighted_summary(xo, lwo, ps, weighted=False)[2][0])
+    m, v = smc.weighted_mean_var(x, w)
+    assert abs(m - float(xo[0] @ wo)) <= 1e-10 * max(1.0, abs(m)) and abs(v - float(((xo[0] - m) ** 2) @ wo)) <= 1e-9 * v
     ctx.set_rng(13, 5)
     x2, _, logZ2 = smc.guided_log_likelihood(N, y, lg, smc.locally_optimal_proposal, resampler="systematic", ctx=ctx, stream=6)
     np.testing.assert_array_equal(np.asarray(x2), xo[0])
