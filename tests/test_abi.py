@@ -97,3 +97,22 @@ def test_simulate_matches_oracle(oracle, kind, params):
     np.testing.assert_array_equal(x, xo)
     np.testing.assert_array_equal(y, yo)
     assert x.shape == (3 if kind == 2 else 1, 500)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver times beside the CUDA arm) prints ONE JSON line with the
+    contract's keys, on the CUDA arm's metric / unit / config, without touching a GPU"""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "particle-updates/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("particle-updates/sec") and d["vs_baseline"] is None and d["dtype"] == "f64"
+    assert d["config"]["N"] == 1 << 24 and d["config"]["T"] == 1000 and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["value"] == d["value"] > 1e5
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
