@@ -140,6 +140,68 @@ def test_sharded_redistribution_over_gloo():
     assert got[0] == 4 and got[1] == 4   # clouds whose parent lives on the other rank
 
 
+def _sampler_worker(rank, world, port, out, algo):
+    """the PRODUCT's θ-sharded sampler logic on CPU ranks (oracle-backed fake device, tests/fake_device.py) against the
+    single-process oracle sampler"""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle as o, samplers as S
+        from tests.fake_device import FakeContext
+        N, M, T, chain = 48, 16, 30, 2
+        _, y = o.simulate(0, [0.5, 1.0, 0.9, 0.8, 0.0, 1.0], T, 1998)
+        pg = smc.product_distribution([smc.TruncatedNormal(0, 1, -1, 1), smc.LogNormal(), smc.LogNormal()])
+        po = S.OProduct([S.OTruncatedNormal(0, 1, -1, 1), S.OLogNormal(), S.OLogNormal()])
+        g = smc.SMC(N, M, lambda θ: smc.StateSpaceModel(smc.LinearGaussian(θ[0], 1.0, θ[1], θ[2], 0.0), (1, 1)), pg, chain, 0.5,
+                    seed=5, ctx=FakeContext(5), comm=ss.TorchComm())
+        ref = S.OSMC(N, M, lambda θ: (0, [θ[0], 1.0, θ[1], θ[2], 0.0, 1.0]), po, chain, 0.5, seed=5)
+        n_rejuv = 0
+        if algo == "smc2":
+            smc.smc2(g, y)
+            S.o_smc2(ref, y)
+            for t in range(1, T):
+                smc.smc2_step(g, y, t, verbose=False)
+                S.o_smc2_step(ref, y, t)
+                assert g.rejuvenated == ref.rejuvenated
+                n_rejuv += g.rejuvenated
+        else:
+            smc.density_tempered(g, y, verbose=False)
+            S.o_density_tempered(ref, y)
+            n_rejuv = len(g.schedule) - 1
+        assert n_rejuv >= 1
+        np.testing.assert_array_equal(g.θ, ref.theta)                       # replicated on every rank
+        np.testing.assert_allclose(g.logZ, ref.logZ, rtol=1e-12, atol=0)
+        np.testing.assert_allclose(g.ω, ref.omega, rtol=1e-10, atol=1e-300)
+        lo, hi = rank * (M // world), (rank + 1) * (M // world)
+        np.testing.assert_array_equal(g._cur.x, ref.x[lo:hi])               # this rank's clouds == the oracle's slots [lo, hi)
+        np.testing.assert_array_equal(g._cur.lw, ref.logw[lo:hi])
+        out.put((rank, int(g.stats["clouds_moved"]), n_rejuv))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("algo", ["smc2", "density_tempered"])
+def test_sharded_sampler_logic_over_gloo(algo, oracle):
+    """world_size 2, gloo: smc² / smc²! and density_tempered of the product run θ-sharded on two CPU ranks over an
+    oracle-backed fake device and land on the single-process oracle sampler bit for bit (θ, clouds) — the sharding by
+    GLOBAL θ index, the replicated control flow and the cloud exchange after every θ-resample"""
+    import torch.multiprocessing as mp
+    ctxm = mp.get_context("spawn")
+    out = ctxm.Queue()
+    port = _free_port()
+    procs = [ctxm.Process(target=_sampler_worker, args=(r, 2, port, out, algo)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(240)
+        assert p.exitcode == 0
+    got = [out.get(timeout=5) for _ in range(2)]
+    assert {g[0] for g in got} == {0, 1} and got[0][2] == got[1][2] >= 1
+    print("clouds received per rank:", sorted(got))
+    assert sum(g[1] for g in got) >= 1        # at least one cloud crossed ranks (sorted θ-ancestors keep most parents local)
+
+
 def test_model_constructors():
     m = smc.StateSpaceModel(smc.LinearGaussian(0.5, 1.0, 0.9, 0.8, 0.0), (1, 1))       # README.md:12-15
     assert m.params() == [0.5, 1.0, 0.9, 0.8, 0.0, 1.0] and m.kind == smc.KIND_LG1D
