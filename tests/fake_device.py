@@ -120,3 +120,42 @@ class FakeContext:
 
     def resample(self, w, resampler=0, stream=0, t=0, purpose=3):
         return o.resample_w(np.asarray(w, np.float64), resampler, self.seed, self.epoch, stream, t, purpose=purpose)
+
+    # -- Kalman entry points (ibis.py)
+    def kalman_step(self, params, x, sigma, y):
+        P = np.asarray(params, np.float64).reshape(-1, 8)
+        M = P.shape[0]
+        x = np.broadcast_to(np.asarray(x, np.float64), (M,)).copy()
+        s = np.broadcast_to(np.asarray(sigma, np.float64), (M,)).copy()
+        ll = np.empty(M)
+        for m in range(M):
+            x[m], s[m], ll[m] = o.kalman_step(P[m], x[m], s[m], float(y))
+        return x, s, ll
+
+    def kalman_loglik(self, params, y, matched_init=False, active=None):
+        P = np.asarray(params, np.float64).reshape(-1, 8)
+        M = P.shape[0]
+        ll, x, s = np.full(M, -np.inf), np.zeros(M), np.zeros(M)
+        for m in range(M):
+            if active is None or active[m]:
+                x[m], s[m], ll[m] = o.kalman_loglik(P[m], y, matched_init)
+        return ll, x, s
+
+    def kalman_mv_step(self, d, models, x, sigma, y):
+        B = np.asarray(models, np.float64).reshape(-1, 3 * d * d + 2 * d + 1)
+        M = B.shape[0]
+        x = np.broadcast_to(np.asarray(x, np.float64), (M, d)).copy()
+        s = np.broadcast_to(np.asarray(sigma, np.float64), (M, d, d)).copy()
+        ll = np.empty(M)
+        for m in range(M):
+            x[m], s[m], ll[m] = o.kalman_mv_step(d, B[m], x[m], s[m], float(y))
+        return x, s, ll
+
+    def kalman_mv_loglik(self, d, models, y, matched_init=False, active=None):
+        B = np.asarray(models, np.float64).reshape(-1, 3 * d * d + 2 * d + 1)
+        M = B.shape[0]
+        ll, x, s = np.full(M, -np.inf), np.zeros((M, d)), np.zeros((M, d, d))
+        for m in range(M):
+            if active is None or active[m]:
+                x[m], s[m], ll[m] = o.kalman_mv_loglik(d, B[m], y, matched_init)
+        return ll, x, s

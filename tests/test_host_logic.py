@@ -202,6 +202,70 @@ def test_sharded_sampler_logic_over_gloo(algo, oracle):
     assert sum(g[1] for g in got) >= 1        # at least one cloud crossed ranks (sorted θ-ancestors keep most parents local)
 
 
+@pytest.mark.parametrize("which", ["lg", "hodrick_prescott"])
+def test_ibis_host_logic_on_the_fake_device(oracle, which):
+    """ibis.py (IBIS constructor, smc², smc²!, resample!, rejuvenate!: ibis.jl:26-189) driven on the CPU over the
+    oracle-backed fake device, scalar and matrix Kalman inner filters, against the oracle's IBIS step by step"""
+    from oracle import samplers as S
+    from sequential_monte_carlo_b200 import ibis as ib
+    from tests.fake_device import FakeContext
+    if which == "lg":
+        T, M = 50, 64
+        _, y = oracle.simulate(0, [0.5, 1.0, 0.9, 0.8, 0.0, 1.0], T, 1998)
+        pg = smc.product_distribution([smc.TruncatedNormal(0, 1, -1, 1), smc.LogNormal(), smc.LogNormal()])
+        po = S.OProduct([S.OTruncatedNormal(0, 1, -1, 1), S.OLogNormal(), S.OLogNormal()])
+        g = smc.IBIS(M, lambda θ: smc.LinearGaussian(θ[0], 1.0, θ[1], θ[2], 0.0), pg, 3, 0.5, seed=4, ctx=FakeContext(4))
+        ref = S.OIBIS(M, lambda θ: (0, [θ[0], 1.0, θ[1], θ[2], 0.0, 1.0]), po, 3, 0.5, seed=4)
+    else:
+        rng = np.random.default_rng(0)
+        T, M = 60, 48
+        y = np.cumsum(np.cumsum(rng.normal(0, 0.05, T))) + rng.normal(0, 1, T)
+        g = smc.IBIS(M, lambda θ: smc.hodrick_prescott(λ=θ[0], y=y), smc.product_distribution([smc.Uniform(1.0, 2000.0)]), 2, 0.5,
+                     seed=3, ctx=FakeContext(3))
+        ref = S.OIBIS(M, lambda th: (("mv", 2), smc.hodrick_prescott(λ=th[0], y=y).block()), S.OProduct([S.OUniform(1.0, 2000.0)]), 2, 0.5, seed=3)
+        assert g.d == 2 and g.x.shape == (M, 2) and g.Σ.shape == (M, 2, 2)
+    ib.smc2(g, y)
+    S.o_ibis_init(ref, y)
+    n = 0
+    for t in range(1, T):
+        ib.smc2_step(g, y, t, verbose=False)
+        S.o_ibis_step(ref, y, t)
+        assert g.rejuvenated == ref.rejuvenated
+        n += g.rejuvenated
+    assert n >= 1
+    np.testing.assert_array_equal(g.θ, ref.theta)
+    np.testing.assert_array_equal(g.logZ, ref.logZ)
+    np.testing.assert_array_equal(g.x, ref.x)
+    np.testing.assert_array_equal(g.Σ, ref.Sigma)
+    np.testing.assert_array_equal(g.ω, ref.omega)
+    np.testing.assert_allclose(ib.expected_parameters(g), (ref.theta * ref.omega[:, None]).sum(axis=0)[:, None], rtol=1e-12)
+
+
+def test_exchange_host_logic_on_the_fake_device(oracle):
+    """exchange! (smc_samplers.jl:163-189) on the CPU stand-in: with min_ar above any acceptance rate N doubles after a
+    rejuvenation, every θ is re-filtered with the doubled cloud and ω ∝ exp(new logZ − logZ)"""
+    from tests.fake_device import FakeContext
+    N, M, T = 32, 16, 30
+    _, y = oracle.simulate(0, [0.5, 1.0, 0.9, 0.8, 0.0, 1.0], T, 1998)
+    pg = smc.product_distribution([smc.TruncatedNormal(0, 1, -1, 1), smc.LogNormal(), smc.LogNormal()])
+    g = smc.SMC(N, M, lambda θ: smc.LinearGaussian(θ[0], 1.0, θ[1], θ[2], 0.0), pg, 1, 0.9, 2.0, seed=2, ctx=FakeContext(2))
+    smc.smc2(g, y)
+    for t in range(1, T):
+        smc.smc2_step(g, y, t, verbose=False)
+        if g.rejuvenated:
+            break
+    assert g.rejuvenated and g.N == 64 and g.x.shape == (M, 1, 64)
+    assert np.isfinite(g.logZ).all() and abs(g.ω.sum() - 1) < 1e-12
+    # the doubled clouds: a fresh 64-particle filter over y[:t] on the new batch's Philox identity, then this call's own step to y[t]
+    _, x, lw = oracle.batch_log_likelihood(0, g._P, None, 64, y[:t], 0, g._cur.seed, g._cur.epoch, 0)
+    for m in range(M):
+        oracle.bootstrap_step(0, g._P[m], x[m], lw[m], y[t], t, 0, g._cur.seed, g._cur.epoch, m)
+    np.testing.assert_array_equal(g._cur.x, x)
+    assert g._cur.t == t
+    smc.smc2_step(g, y, t + 1, verbose=False)
+    assert g._cur.t == t + 1
+
+
 def test_model_constructors():
     m = smc.StateSpaceModel(smc.LinearGaussian(0.5, 1.0, 0.9, 0.8, 0.0), (1, 1))       # README.md:12-15
     assert m.params() == [0.5, 1.0, 0.9, 0.8, 0.0, 1.0] and m.kind == smc.KIND_LG1D
