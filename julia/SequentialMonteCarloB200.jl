@@ -55,7 +55,7 @@ end
 UnivariateLinearGaussian(; A, B, Q, R, x0=0.0, σ0=1.0) = LinearModel(A, B, Q, R, x0, σ0)       # :74-77
 LinearGaussian(A, B, Q, R, x0=0.0, σ0=1.0) = LinearModel(A, B, Q, R, x0, σ0)                    # README.md:12-15
 unobserved_components(; σε, ση, x0) = LinearModel(1.0, 1.0, σε, ση, x0, σε)                     # :119-128
-UC(σε, ση, x0) = unobserved_components(σε=σε, ση=ση, x0=x0)
+UC(x0, σε, ση) = unobserved_components(σε=σε, ση=ση, x0=x0)      # order fixed by the example's prior [Normal(3,2), U(0,4), U(0,4)] (:33-37)
 struct UCSV <: StateSpaceModel                   # :215-222
     γ::Tuple{Float64,Float64}; x0::Float64; log_σ0::Tuple{Float64,Float64}
 end

@@ -98,7 +98,11 @@ def unobserved_components(σε=None, ση=None, x0=0.0, **kw):
     return LinearModel(1.0, 1.0, σε, ση, x0, σε)
 
 
-UC = unobserved_components  # examples/inflation_example.jl:28-31
+def UC(x0, σε, ση):
+    """Example spelling `UC(θ...)` (examples/inflation_example.jl:28-31).  `UC` exists nowhere on disk; its positional order
+    is fixed by the example's prior `[Normal(3,2), Uniform(0,4), Uniform(0,4)]` (:33-37): the level first, then the two
+    variances (a Normal(3,2) draw can be negative, so it cannot be a variance)."""
+    return unobserved_components(σε, ση, x0)
 
 
 class MultivariateLinearModel(StateSpaceModel):

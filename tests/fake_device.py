@@ -96,6 +96,21 @@ class FakeBatch:
         w = np.stack([o.normalize(l)[1] for l in self.lw]) if want_w else None
         return (self.x.copy() if want_x else None), w, (self.lw.copy() if want_logw else None)
 
+    # -- per-cloud summaries (SPEC §8)
+    def weighted_mean(self):
+        return self.weighted_moments()[0]
+
+    def weighted_moments(self):
+        mean, var = np.empty((self.M, self.d)), np.empty((self.M, self.d))
+        for m in range(self.M):
+            w = o.normalize(self.lw[m])[1]
+            mean[m] = self.x[m] @ w
+            var[m] = ((self.x[m] - mean[m][:, None]) ** 2) @ w
+        return mean, var
+
+    def weighted_quantiles(self, probs, weighted=True):
+        return np.stack([o.weighted_summary(self.x[m], self.lw[m], probs, weighted=weighted)[2] for m in range(self.M)])
+
     def timing(self):
         return 0.0, 0
 

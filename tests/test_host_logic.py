@@ -266,6 +266,24 @@ def test_exchange_host_logic_on_the_fake_device(oracle):
     assert g._cur.t == t + 1
 
 
+def test_inflation_example_flow_on_the_fake_device(oracle):
+    """examples/inflation_example.py (the reference's examples/inflation_example.jl on this library): the SMC² loop with
+    per-step quartile bands and variances, UC and UC-SV models, at toy sizes on the CPU stand-in"""
+    import importlib.util
+    from tests.fake_device import FakeContext
+    spec = importlib.util.spec_from_file_location("inflation_example", os.path.join(os.path.dirname(os.path.dirname(__file__)), "examples",
+                                                                                     "inflation_example.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    _, y = oracle.simulate(2, [0.2, 0.2, 3.0, 1.0, 1.0], 25, 1998)
+    for model, prior, dθ in ((ex.uc_mod, ex.uc_prior, 3), (ex.ucsv_mod, ex.ucsv_prior, 4)):
+        s, xqs, cqs, variances = ex.run_smc2(model, prior, y, 64, 24, 2, seed=1998, ctx=FakeContext(1998))
+        assert xqs.shape == (25, 3) and np.all(np.diff(xqs, axis=1) >= 0) and np.all(np.diff(cqs, axis=1) >= 0)
+        assert np.all(variances > 0) and smc.expected_parameters(s).shape == (dθ, 1)
+        np.testing.assert_allclose(xqs[:, 1] + cqs[:, 1], y, atol=np.abs(xqs[:, 2] - xqs[:, 0]).max())   # trend + cycle ≈ y
+        assert abs(s.ω.sum() - 1) < 1e-12 and np.isfinite(s.logZ).all()
+
+
 def test_model_constructors():
     m = smc.StateSpaceModel(smc.LinearGaussian(0.5, 1.0, 0.9, 0.8, 0.0), (1, 1))       # README.md:12-15
     assert m.params() == [0.5, 1.0, 0.9, 0.8, 0.0, 1.0] and m.kind == smc.KIND_LG1D
@@ -273,6 +291,7 @@ def test_model_constructors():
     assert u.params() == m.params()
     uc = smc.unobserved_components(0.3, 0.7, 2.0)                                       # :119-128
     assert uc.params() == [1.0, 1.0, 0.3, 0.7, 2.0, 0.3]
+    assert smc.UC(2.0, 0.3, 0.7).params() == uc.params()                                # UC(θ...): level first (example prior order, :33-37)
     v = smc.StateSpaceModel(smc.UCSV(0.2, 3.0, (1.0, 0.5)), (3, 1))                     # examples/inflation_example.jl:229-232
     assert v.params() == [0.2, 0.2, 3.0, 1.0, 0.5] and v.state_dim == 3
     w = smc.unobserved_components_stochastic_volatility(x0=3.0, γε=0.1, γη=0.2, log_σε=1.0, log_ση=0.5)
