@@ -76,6 +76,30 @@ def test_oracle_guided_optimal_proposal_targets_kalman(oracle):
         oracle.guided_step(oracle.KIND_UCSV, [0.2, 0.2, 3, 1, 1], np.zeros((3, 8)), np.zeros(8), 0.0, 1, 0, [0, 1, 1], 1)
 
 
+def test_oracle_guided_step_against_a_numpy_restatement(oracle):
+    """particle_filter! (particles.jl:66-80) restated with numpy / libm on the oracle's own ancestors and normals:
+    x' = c0 + c1 xp + c2 z, logw = logpdf(obs) + logpdf(N(x'; μf, σf)) − logpdf(N(x'; c0 + c1 xp, c2))"""
+    def lognorm(v, mu, sd):
+        return -0.5 * ((v - mu) / sd) ** 2 - np.log(sd) - 0.5 * np.log(2 * np.pi)
+    n, t, seed, epoch, stream = 500, 3, 9, 2, 4
+    for kind, th, prop in ((oracle.KIND_LG1D, LG, [0.2, 0.3, 0.7]), (oracle.KIND_SV, SVP, [-0.4, 0.6, 0.5])):
+        x, lw = oracle.bootstrap_init(kind, th, n, 0.4, seed, epoch, stream)
+        x0, lw0 = x.copy(), lw.copy()
+        a = oracle.guided_step(kind, th, x, lw, -0.3, t, oracle.SYSTEMATIC, prop, seed, epoch, stream)
+        np.testing.assert_array_equal(a, oracle.ancestors(lw0, oracle.SYSTEMATIC, seed, epoch, stream, t))
+        xp = x0[0][a]
+        z = oracle.normals(seed, epoch, stream, t, oracle.P_TRANS, 0, n)
+        xn = prop[0] + prop[1] * xp + prop[2] * z
+        np.testing.assert_allclose(x[0], xn, rtol=1e-14, atol=1e-15)
+        if kind == oracle.KIND_LG1D:
+            A, B, Q, R = th[:4]
+            lobs, lf = lognorm(-0.3, B * xn, np.sqrt(R)), lognorm(xn, A * xp, np.sqrt(Q))
+        else:
+            mu, rho, sig = th
+            lobs, lf = lognorm(-0.3, 0.0, np.exp(0.5 * xn)), lognorm(xn, mu + rho * (xp - mu), sig)
+        np.testing.assert_allclose(lw, lobs + lf - lognorm(xn, prop[0] + prop[1] * xp, prop[2]), rtol=1e-11, atol=1e-12)
+
+
 def test_oracle_matrix_kalman(oracle):
     """smco_kalman_mv_* against numpy matrix algebra; d = 1 reproduces the scalar recursion; Hodrick–Prescott block"""
     _, y = oracle.simulate(oracle.KIND_LG1D, LG, 80, 5)
