@@ -8,7 +8,8 @@
     kalman_filter.jl:3-27,55-70) — oracle against a numpy restatement on the CPU, CUDA against the oracle on the GPU;
   * per-θ weighted means / variances of the clouds (var(x, weights(w)), examples/inflation_example.jl:46).
 
-This file sorts last on purpose: these kernels were added after the round's last full GPU run.
+Also here: the plain-C client of the ABI on the GPU, IBIS over a multivariate model, and the CUDA path against the
+committed golden bit patterns.  The file sorts last; all of it ran green on a B200 (profiles/r1_pytest_gpu_widen_rows.log).
 """
 import numpy as np
 import pytest
