@@ -63,6 +63,9 @@ class IBIS:
     def _where(self, accept, new, old):
         return np.where(accept.reshape((-1,) + (1,) * (np.ndim(old) - 1)), new, old)
 
+    def __repr__(self):                                              # Base.show(io, ibis)   ibis.jl:66-71
+        return f"ess     = {round(self.ess, 3)}\nmean(θ) = {expected_parameters(self).ravel()}"
+
 
 def resample_(ibis):
     """resample!(ibis) (ibis.jl:72-84) — permutes θ, x, Σ, logZ."""
