@@ -17,7 +17,7 @@ module SequentialMonteCarloB200
 using Distributions, LinearAlgebra, Printf, Statistics
 
 export StateSpaceModel, LinearModel, UnivariateLinearGaussian, LinearGaussian, unobserved_components, UC, UCSV,
-       StochasticVolatility, simulate, normalize, resample, bootstrap_filter, bootstrap_filter!, log_likelihood,
+       StochasticVolatility, simulate, transition, observation, initial_dist, normalize, resample, bootstrap_filter, bootstrap_filter!, log_likelihood,
        SMC, smc², smc²!, density_tempered, expected_parameters, kalman_filter,
        particle_filter, particle_filter!, AffineGaussianProposal, locally_optimal_proposal,
        MultivariateLinearModel, MultivariateLinearGaussian, hodrick_prescott, state_variances
@@ -69,6 +69,17 @@ statedim(m) = m isa UCSV ? 3 : 1
 params8(m::LinearModel) = Float64[m.A, m.B, m.Q, m.R, m.x0, m.σ0, 0, 0]
 params8(m::StochasticVolatility) = Float64[m.μ, m.ρ, m.σ, 0, 0, 0, 0, 0]
 params8(m::UCSV) = Float64[m.γ[1], m.γ[2], m.x0, m.log_σ0[1], m.log_σ0[2], 0, 0, 0]
+
+# the model methods the reference exports (state_space_models.jl:1): host-side descriptions of what the device functors evaluate
+initial_dist(m::LinearModel) = Normal(m.x0, sqrt(m.σ0))                                        # :105-109
+transition(m::LinearModel, x::Float64) = Normal(m.A * x, sqrt(m.Q))                            # :87-94
+observation(m::LinearModel, x::Float64) = Normal(m.B * x, sqrt(m.R))                           # :96-103
+initial_dist(m::StochasticVolatility) = Normal(m.μ, m.σ / sqrt(1 - m.ρ^2))
+transition(m::StochasticVolatility, x::Float64) = Normal(m.μ + m.ρ * (x - m.μ), m.σ)
+observation(m::StochasticVolatility, x::Float64) = Normal(0.0, exp(0.5 * x))
+initial_dist(m::UCSV) = (Normal(m.x0, exp(0.5 * m.log_σ0[1])), Normal(m.log_σ0[1], m.γ[1]), Normal(m.log_σ0[2], m.γ[2]))   # :249-259
+transition(m::UCSV, x::Vector{Float64}) = (Normal(x[1], exp(0.5 * x[2])), Normal(x[2], m.γ[1]), Normal(x[3], m.γ[2]))       # :233-242
+observation(m::UCSV, x::Vector{Float64}) = Normal(x[1], exp(0.5 * x[3]))                       # :244-247
 
 function simulate(model::StateSpaceModel, T::Int64; seed::Integer=1998)                       # :11-28
     d = statedim(model); x = Matrix{Float64}(undef, T, d); y = Vector{Float64}(undef, T)     # column-major [T,d] == C [d][T]

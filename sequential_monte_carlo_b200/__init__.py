@@ -11,7 +11,7 @@ __version__ = "0.1.0"
 
 from .state_space_models import (StateSpaceModel, LinearModel, UnivariateLinearGaussian, LinearGaussian,  # noqa: E402,F401
                                  unobserved_components, UC, UCSV, MultivariateLinearModel, MultivariateLinearGaussian, hodrick_prescott, unobserved_components_stochastic_volatility,
-                                 StochasticVolatility, SV, simulate, preallocate)
+                                 StochasticVolatility, SV, simulate, preallocate, transition, observation, initial_dist, MvNormal)
 from .particles import (normalize, reweight, resample, bootstrap_filter, bootstrap_filter_, particle_filter, particle_filter_, log_likelihood,
                         AffineGaussianProposal, locally_optimal_proposal, guided_log_likelihood,  # noqa: E402,F401
                         quantile, weighted_mean_var, default_context, set_default_context)

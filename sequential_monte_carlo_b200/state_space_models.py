@@ -208,6 +208,69 @@ def params_of(model, θ):
     return np.stack([mm.params8() for mm in ms]), ms[0]
 
 
+# ---- the model methods the reference exports (state_space_models.jl:1: transition, observation, initial_dist) ---------------
+# Host-side descriptions of the densities the device functors of csrc/smcb_models.cuh evaluate: what a user of the
+# reference gets from `transition(model, x)` etc.  Univariate states return a `priors.Normal` (μ, σ with σ a standard
+# deviation, as Distributions.jl's Normal); UCSV returns the tuple of its three independent Normals (the reference's
+# `TupleProduct`, state_space_models.jl:237,254); multivariate linear models return `MvNormal(μ, Σ)`.
+class MvNormal:
+    """mean vector and covariance matrix (Distributions.jl's MvNormal(μ, Σ)) of a multivariate linear model's densities"""
+
+    def __init__(self, μ, Σ):
+        self.μ, self.Σ = np.asarray(μ, np.float64), np.asarray(Σ, np.float64)
+
+    def logpdf(self, x):
+        d = np.asarray(x, np.float64) - self.μ
+        _, logdet = np.linalg.slogdet(self.Σ)
+        return float(-0.5 * (d @ np.linalg.solve(self.Σ, d) + logdet + self.μ.size * np.log(2 * np.pi)))
+
+
+def _scalar_model(model):
+    if isinstance(model.params(), np.ndarray):
+        raise TypeError("transition / observation / initial_dist take ONE model, not a ParamColumn batch")
+
+
+def initial_dist(model):
+    """initial_dist(model)  (state_space_models.jl:105-109, 249-259; SV: the stationary law)"""
+    from .priors import Normal
+    if isinstance(model, MultivariateLinearModel):
+        return MvNormal(model.x0, model.σ0)                                   # :181-185
+    _scalar_model(model)
+    if model.kind == _lib.LG1D:
+        return Normal(model.x0, np.sqrt(model.σ0))
+    if model.kind == _lib.SV:
+        return Normal(model.μ, model.σ / np.sqrt(1.0 - model.ρ ** 2))
+    return (Normal(model.x0, np.exp(0.5 * model.log_σ0[0])), Normal(model.log_σ0[0], model.γ[0]), Normal(model.log_σ0[1], model.γ[1]))
+
+
+def transition(model, x):
+    """transition(model, x)  (state_space_models.jl:87-94, 233-242): the law of x[t] given x[t-1] = x"""
+    from .priors import Normal
+    if isinstance(model, MultivariateLinearModel):
+        return MvNormal(model.A @ np.asarray(x, np.float64), model.Q)          # :163-170
+    _scalar_model(model)
+    if model.kind == _lib.LG1D:
+        return Normal(model.A * float(x), np.sqrt(model.Q))
+    if model.kind == _lib.SV:
+        return Normal(model.μ + model.ρ * (float(x) - model.μ), model.σ)
+    x = np.asarray(x, np.float64)
+    return (Normal(x[0], np.exp(0.5 * x[1])), Normal(x[1], model.γ[0]), Normal(x[2], model.γ[1]))   # previous log σε  :238
+
+
+def observation(model, x):
+    """observation(model, x)  (state_space_models.jl:96-103, 244-247): the law of y[t] given x[t] = x"""
+    from .priors import Normal
+    if isinstance(model, MultivariateLinearModel):
+        return Normal(float((model.B @ np.asarray(x, np.float64))[0]), float(np.sqrt(model.R[0])))   # R a variance, as in the Kalman filter
+    _scalar_model(model)
+    if model.kind == _lib.LG1D:
+        return Normal(model.B * float(x), np.sqrt(model.R))
+    if model.kind == _lib.SV:
+        return Normal(0.0, np.exp(0.5 * float(x)))
+    x = np.asarray(x, np.float64)
+    return Normal(x[0], np.exp(0.5 * x[2]))                                    # current log ση  :246
+
+
 def simulate(model, T, seed=1998):
     """simulate([rng,] model, T) -> (x, y)  (state_space_models.jl:11-28).  The rng argument of the
     reference becomes a Philox seed.  x has shape [T] (or [T, 3] for UCSV, one row per period)."""

@@ -304,6 +304,39 @@ def test_model_constructors():
     assert x.shape == (50, 3) and y.shape == (50,)
 
 
+def test_exported_model_methods_describe_what_the_device_evaluates(oracle):
+    """transition / observation / initial_dist (exported by state_space_models.jl:1) against the oracle's functors: the
+    log-weight of every initial particle is logpdf(observation(model, x_i), y), and one oracle transition step has the
+    mean and standard deviation transition(model, x) states"""
+    y = 0.37
+    models = {0: smc.LinearGaussian(0.5, 1.3, 0.9, 0.8, 0.2, 1.5), 1: smc.SV(-1.0, 0.9, 0.3), 2: smc.UCSV((0.2, 0.3), 3.0, (1.0, 0.5))}
+    for kind, m in models.items():
+        x, lw = oracle.bootstrap_init(kind, m.params(), 64, y, 3, 0, 0)
+        z = np.stack([oracle.normals(3, 0, 0, 0, oracle.P_INIT, k, 64) for k in range(m.state_dim)])
+        i0 = smc.initial_dist(m)
+        i0 = i0 if isinstance(i0, tuple) else (i0,)
+        for k, dist in enumerate(i0):
+            np.testing.assert_allclose(x[k], dist.μ + dist.σ * z[k], rtol=1e-13, atol=1e-15)
+        for i in range(0, 64, 7):
+            xi = x[:, i] if m.state_dim > 1 else x[0, i]
+            assert smc.observation(m, xi).logpdf(y) == pytest.approx(lw[i], rel=1e-12, abs=1e-13)
+        x1, lw1 = x.copy(), lw.copy()
+        a = oracle.bootstrap_step(kind, m.params(), x1, lw1, y, 1, oracle.SYSTEMATIC, 3, 0, 0)
+        zt = np.stack([oracle.normals(3, 0, 0, 1, oracle.P_TRANS, k, 64) for k in range(m.state_dim)])
+        for i in range(0, 64, 9):
+            xp = x[:, a[i]] if m.state_dim > 1 else x[0, a[i]]
+            tr = smc.transition(m, xp)
+            tr = tr if isinstance(tr, tuple) else (tr,)
+            for k, dist in enumerate(tr):
+                assert x1[k, i] == pytest.approx(dist.μ + dist.σ * zt[k, i], rel=1e-12, abs=1e-14)
+    hp = smc.hodrick_prescott(λ=1600.0, y=np.array([1.0, 1.5, 2.5]))
+    tr = smc.transition(hp, [2.0, 1.0])
+    np.testing.assert_array_equal(tr.μ, [3.0, 2.0])                       # (2x[t-1] - x[t-2], x[t-1])
+    assert smc.observation(hp, [2.0, 1.0]).μ == 2.0 and smc.initial_dist(hp).Σ[0, 0] == 1000.0
+    mv = smc.MvNormal([0.0, 0.0], np.eye(2))
+    assert mv.logpdf([0.0, 0.0]) == pytest.approx(-np.log(2 * np.pi))
+
+
 def test_particle_filter_refuses_what_it_cannot_run_on_the_device():
     """particle_filter / particle_filter! (particles.jl:28-84) exist with the reference's signature.  Guided moves are
     built for the affine-Gaussian family on the one-dimensional models (docs/SPEC.md §10); anything else is refused
