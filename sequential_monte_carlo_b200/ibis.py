@@ -151,3 +151,31 @@ def expected_parameters(ibis, reference_style=False):
         e = np.exp(ω - ω.max())
         ω = e / e.sum()
     return (ibis.θ * ω[:, None]).sum(axis=0)[:, None]
+
+
+def observation_dist(ibis):
+    """observation_dist(ibis) (plotting_utils.jl:96-113): the ω-mixture of the predicted measurement B x_m and of its
+    variance B Σ_m B' + R over the θ-particles (filtered moments, no predict step — as the reference)."""
+    P = ibis._params(ibis.θ)
+    if ibis.d is None:
+        ym, Sm = P[:, 1] * ibis.x, (P[:, 1] ** 2) * ibis.Σ + P[:, 3]
+    else:
+        d = ibis.d
+        B, R = P[:, d * d: d * d + d], P[:, 2 * d * d + d]
+        ym = np.einsum("mi,mi->m", B, ibis.x)
+        Sm = np.einsum("mi,mij,mj->m", B, ibis.Σ, B) + R
+    return float(np.sum(ibis.ω * ym)), float(np.sum(ibis.ω * Sm))
+
+
+def estimated_trend(ibis):
+    """estimated_trend(ibis::IBIS) (plotting_utils.jl:114)"""
+    return observation_dist(ibis)[0]
+
+
+def quantile(ibis, p):
+    """quantile(ibis, p) (plotting_utils.jl:126-137): quantiles of Normal(y, sqrt(Σ)) with (y, Σ) = observation_dist(ibis)"""
+    from statistics import NormalDist
+    p = np.sort(np.atleast_1d(np.asarray(p, np.float64)))            # sort!(p)  :130
+    y, S = observation_dist(ibis)
+    return np.array([NormalDist(y, math.sqrt(S)).inv_cdf(float(v)) for v in p])
+

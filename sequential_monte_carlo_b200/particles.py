@@ -256,7 +256,10 @@ def quantile(x, w_or_p, p=None):
     """quantile(x, p) (README.md:41,51: every particle counts once) or quantile(x, weights(w), p)
     (examples/inflation_example.jl:44) of a cloud that lives on the device — computed there, nothing is
     read back.  Lower empirical quantile (no interpolation); one row per state component."""
-    if hasattr(x, "θ"):                      # quantile(smc::SMC, p)  plotting_utils.jl:140-157
+    if hasattr(x, "θ"):                      # quantile(smc::SMC, p) / quantile(ibis::IBIS, p)  plotting_utils.jl:126-157
+        if not hasattr(x, "_cur"):
+            from . import ibis as _ibis
+            return _ibis.quantile(x, w_or_p)
         from .smc_samplers import quantile_smc
         return quantile_smc(x, w_or_p)
     weighted = p is not None

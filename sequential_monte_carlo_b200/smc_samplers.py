@@ -270,7 +270,11 @@ def _observation_mean_sd(smc):
 
 
 def estimated_trend(smc):
-    """estimated_trend(smc) (plotting_utils.jl:116-124): Σ_m ω_m mean(observation(model(θ_m), w_m' x_m))."""
+    """estimated_trend(smc) (plotting_utils.jl:116-124): Σ_m ω_m mean(observation(model(θ_m), w_m' x_m)); for an IBIS sampler
+    the mixture of the Kalman filters' predicted measurements (:114)."""
+    if not hasattr(smc, "_cur"):
+        from . import ibis as _ibis
+        return _ibis.estimated_trend(smc)
     mu, _ = _observation_mean_sd(smc)
     return float(np.sum(smc.ω * mu))
 

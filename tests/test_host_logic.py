@@ -239,6 +239,20 @@ def test_ibis_host_logic_on_the_fake_device(oracle, which):
     np.testing.assert_array_equal(g.Σ, ref.Sigma)
     np.testing.assert_array_equal(g.ω, ref.omega)
     np.testing.assert_allclose(ib.expected_parameters(g), (ref.theta * ref.omega[:, None]).sum(axis=0)[:, None], rtol=1e-12)
+    # observation_dist / estimated_trend / quantile(ibis, p)  (plotting_utils.jl:96-137), restated per θ-particle
+    ymix = Smix = 0.0
+    for m in range(M):
+        mod = g.model(g.θ[m])
+        if which == "lg":
+            ym, Sm = mod.B * g.x[m], mod.B * g.Σ[m] * mod.B + mod.R
+        else:
+            ym, Sm = (mod.B @ g.x[m])[0], (mod.B @ g.Σ[m] @ mod.B.T)[0, 0] + mod.R[0]
+        ymix, Smix = ymix + g.ω[m] * ym, Smix + g.ω[m] * Sm
+    yo, So = ib.observation_dist(g)
+    assert yo == pytest.approx(ymix, rel=1e-12) and So == pytest.approx(Smix, rel=1e-12)
+    assert smc.estimated_trend(g) == yo
+    q = smc.quantile(g, [0.95, 0.5, 0.05])
+    assert q[1] == pytest.approx(yo, abs=1e-12) and q[2] - q[1] == pytest.approx(1.6448536269514722 * np.sqrt(So), rel=1e-9) and q[0] < q[1] < q[2]
 
 
 def test_exchange_host_logic_on_the_fake_device(oracle):
