@@ -271,9 +271,17 @@ def observation(model, x):
     return Normal(x[0], np.exp(0.5 * x[2]))                                    # current log ση  :246
 
 
-def simulate(model, T, seed=1998):
+def simulate(*args, seed=1998):
     """simulate([rng,] model, T) -> (x, y)  (state_space_models.jl:11-28).  The rng argument of the
-    reference becomes a Philox seed.  x has shape [T] (or [T, 3] for UCSV, one row per period)."""
+    reference becomes a Philox seed: an int, or a numpy Generator from which one is drawn.
+    x has shape [T] (or [T, 3] for UCSV, one row per period)."""
+    if len(args) == 3:                                   # simulate(rng, model, T)  :11-26
+        rng, model, T = args
+        seed = int(rng.integers(0, 2 ** 63)) if hasattr(rng, "integers") else int(rng)
+    elif len(args) == 2:                                 # simulate(model, T) = simulate(Random.GLOBAL_RNG, model, T)  :28
+        model, T = args
+    else:
+        raise TypeError("simulate([rng,] model, T)")
     x, y = _lib.simulate(model.kind, model.params(), int(T), int(seed))
     return (x[0] if model.state_dim == 1 else np.ascontiguousarray(x.T)), y
 

@@ -316,6 +316,9 @@ def test_model_constructors():
         smc.LinearGaussian(np.eye(2), np.ones((1, 2)), np.eye(2), 1.0)
     x, y = smc.simulate(v, 50, seed=3)
     assert x.shape == (50, 3) and y.shape == (50,)
+    x2, y2 = smc.simulate(3, v, 50)                                                      # simulate(rng, model, T)  :11
+    np.testing.assert_array_equal(y2, y)
+    assert smc.simulate(np.random.default_rng(0), m, 7)[1].shape == (7,)
 
 
 def test_exported_model_methods_describe_what_the_device_evaluates(oracle):
