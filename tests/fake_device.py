@@ -174,3 +174,51 @@ class FakeContext:
             if active is None or active[m]:
                 x[m], s[m], ll[m] = o.kalman_mv_loglik(d, B[m], y, matched_init)
         return ll, x, s
+
+    # -- the single filter (particles.py): bootstrap_filter / bootstrap_filter! / log_likelihood / guided steps / summaries
+    device = -1
+
+    def _epoch_for_sweep(self):
+        e = self.epoch
+        self.epoch += 1
+        return e
+
+    def bootstrap_init(self, kind, params, N, y, stream=0):
+        self._kind, self._N, self._T, self._P = int(kind), int(N), 1, np.asarray(params, np.float64)
+        self._id = (self.seed, self._epoch_for_sweep(), int(stream))
+        self._x, self._lw = o.bootstrap_init(kind, self._P, N, float(y), *self._id)
+        self._t = 0
+        lm, _, es = o.normalize(self._lw)
+        return lm, es
+
+    def bootstrap_step(self, y, resampler=0, params=None):
+        if params is not None:
+            self._P = np.asarray(params, np.float64)
+        self._t += 1
+        self._T += 1
+        o.bootstrap_step(self._kind, self._P, self._x, self._lw, float(y), self._t, resampler, *self._id)
+        lm, _, es = o.normalize(self._lw)
+        return lm, es
+
+    def guided_step(self, y, proposal, resampler=2, params=None):
+        if params is not None:
+            self._P = np.asarray(params, np.float64)
+        self._t += 1
+        self._T += 1
+        o.guided_step(self._kind, self._P, self._x, self._lw, float(y), self._t, resampler, proposal, *self._id)
+        lm, _, es = o.normalize(self._lw)
+        return lm, es
+
+    def log_likelihood(self, kind, params, N, y, resampler=0, stream=0, per_step=False):
+        y = np.ascontiguousarray(y, np.float64)
+        self._kind, self._N, self._T, self._P = int(kind), int(N), y.size, np.asarray(params, np.float64)
+        self._id = (self.seed, self._epoch_for_sweep(), int(stream))
+        r = o.log_likelihood(kind, self._P, N, y, resampler, *self._id)
+        self._x, self._lw, self._t = r["x"], r["logw"], y.size - 1
+        return (r["logZ"], r["logmu"], r["ess"]) if per_step else r["logZ"]
+
+    def fetch_state(self, want_x=True, want_w=True, want_logw=False):
+        return (self._x.copy() if want_x else None), (o.normalize(self._lw)[1] if want_w else None), (self._lw.copy() if want_logw else None)
+
+    def summary(self, probs=(), weighted=True):
+        return o.weighted_summary(self._x, self._lw, np.asarray(probs, np.float64), weighted=weighted)

@@ -298,6 +298,54 @@ def test_inflation_example_flow_on_the_fake_device(oracle):
         assert abs(s.ω.sum() - 1) < 1e-12 and np.isfinite(s.logZ).all()
 
 
+def test_readme_particle_filter_loop_on_the_fake_device(oracle):
+    """particles.py host logic on the CPU stand-in — the README loop (README.md:33-61): bootstrap_filter, then
+    bootstrap_filter! per observation with quantile(x, p) and logZ += logμ; the device-resident handles (lazy copies,
+    staleness after a re-initialisation); log_likelihood; particle_filter with and without a proposal"""
+    from sequential_monte_carlo_b200 import particles as pt
+    from tests.fake_device import FakeContext
+    ctx = FakeContext(1998)
+    lg_example = smc.StateSpaceModel(smc.LinearGaussian(0.5, 1.0, 0.9, 0.8, 0.0), (1, 1))
+    _, y = smc.simulate(lg_example, 30)
+    ctx.set_rng(1998, 3)
+    x, w, logμ = smc.bootstrap_filter(256, y[0], lg_example, ctx=ctx)
+    xq, logZ = [smc.quantile(x, [0.25, 0.5, 0.75])], logμ
+    for t in range(1, len(y)):
+        logμ, w, ess = smc.bootstrap_filter_(x, w, y[t], lg_example)
+        assert 1.0 <= ess <= 256.0
+        xq.append(smc.quantile(x, [0.25, 0.5, 0.75]))
+        logZ += logμ
+    ref = oracle.log_likelihood(0, lg_example.params(), 256, y, oracle.MULTINOMIAL, 1998, 3, 0)
+    assert logZ == pytest.approx(ref["logZ"], rel=1e-12)
+    np.testing.assert_array_equal(np.asarray(x), ref["x"][0])
+    np.testing.assert_allclose(np.asarray(w), oracle.normalize(ref["logw"])[1], rtol=1e-12)
+    assert len(x) == 256 and x.shape == (256,) and np.all(np.diff(np.array(xq), axis=1) >= 0)
+    m, v = smc.weighted_mean_var(x, w)
+    assert m == pytest.approx(float(ref["x"][0] @ np.asarray(w)), rel=1e-9) and v > 0
+    ctx.set_rng(1998, 3)
+    x2, w2, logZ2 = smc.log_likelihood(256, y, lg_example, ctx=ctx)           # the whole series in one call
+    assert logZ2 == pytest.approx(logZ, rel=1e-12)
+    with pytest.raises(RuntimeError):                                          # the first cloud was replaced on this context ...
+        smc.bootstrap_filter_(x, w, y[0], lg_example)
+    assert np.asarray(x).shape == (256,)                                       # ... its last host copy stays readable
+    np.testing.assert_array_equal(np.asarray(x2), ref["x"][0])
+    # particle_filter: proposal = nothing is the bootstrap filter; a guided cloud above the batched engine's size continues on the single filter
+    pt._GUIDED_BATCH_MAX, keep = 128, pt._GUIDED_BATCH_MAX
+    try:
+        ctx.set_rng(7, 1)
+        xg, wg, _ = smc.particle_filter(256, y[0], lg_example, smc.locally_optimal_proposal, ctx=ctx)
+        xo, lwo = oracle.bootstrap_init(0, lg_example.params(), 256, y[0], 7, 1, 0)
+        for t in range(1, 6):
+            _, wg, _ = smc.particle_filter_(xg, wg, y[t], lg_example, smc.locally_optimal_proposal, resampler="systematic")
+            oracle.guided_step(0, lg_example.params(), xo, lwo, y[t], t, oracle.SYSTEMATIC, smc.locally_optimal_proposal(lg_example, y[t]), 7, 1, 0)
+        np.testing.assert_array_equal(np.asarray(xg), xo[0])
+        _, wg, _ = smc.particle_filter_(xg, wg, y[6], lg_example, None, resampler="systematic")     # bootstrap step on the same cloud
+        oracle.bootstrap_step(0, lg_example.params(), xo, lwo, y[6], 6, oracle.SYSTEMATIC, 7, 1, 0)
+        np.testing.assert_array_equal(np.asarray(xg), xo[0])
+    finally:
+        pt._GUIDED_BATCH_MAX = keep
+
+
 def test_model_constructors():
     m = smc.StateSpaceModel(smc.LinearGaussian(0.5, 1.0, 0.9, 0.8, 0.0), (1, 1))       # README.md:12-15
     assert m.params() == [0.5, 1.0, 0.9, 0.8, 0.0, 1.0] and m.kind == smc.KIND_LG1D
