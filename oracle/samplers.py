@@ -124,8 +124,9 @@ class OSMC:
     `model(θ)` returns (kind, params) for the C oracle."""
 
     def __init__(self, N, M, model, prior, chain, ess_threshold, min_ar=-1.0, seed=1998, resampler=o.MULTINOMIAL,
-                 theta_resampler=o.MULTINOMIAL):
+                 theta_resampler=o.MULTINOMIAL, proposal=None):
         self.N, self.M, self.chain = N, M, chain
+        self.proposal = proposal                           # extension: proposal(P [M,8], y) -> [M,3] guides every inner filter step (SPEC §10)
         self.model, self.prior = model, prior
         self.seed, self.resampler, self.theta_resampler = seed, resampler, theta_resampler
         self.theta = prior.sample(M, seed)                 # θ = map(m -> rand(prior), 1:M)      :38
@@ -143,6 +144,13 @@ class OSMC:
 
     def params(self, theta):
         return np.stack([o.params8(self.model(th)[1]) for th in theta])
+
+    def sweep(self, P, active, y, epoch):
+        """M × log_likelihood(N, y, model(θ_m)) — guided when a proposal is set"""
+        if self.proposal is None:
+            return o.batch_log_likelihood(self.kind, P, active, self.N, y, self.resampler, self.seed, epoch, 0)
+        prop = np.stack([np.asarray(self.proposal(P, float(yt)), np.float64) for yt in y])
+        return o.batch_guided_log_likelihood(self.kind, P, active, self.N, y, self.resampler, prop, self.seed, epoch, 0)
 
 
 def o_expected_parameters(smc, reference_style=False):
@@ -198,8 +206,7 @@ def o_rejuvenate(smc, y, xi=1.0):
         P = smc.params(np.where(ok[:, None], prop, smc.theta))
         epoch = smc.epoch
         smc.epoch += 1
-        zprop, xprop, lwprop = o.batch_log_likelihood(smc.kind, P, ok.astype(np.uint8), smc.N, y, smc.resampler, smc.seed,
-                                                      epoch, 0)      # log_likelihood(N, y, model(θ_prop))  :117-121
+        zprop, xprop, lwprop = smc.sweep(P, ok.astype(np.uint8), y, epoch)   # log_likelihood(N, y, model(θ_prop))  :117-121
         lp_prop = np.array([smc.prior.logpdf(th) if k else -math.inf for th, k in zip(prop, ok)])
         with np.errstate(invalid="ignore", divide="ignore"):
             ratio = xi * (zprop - smc.logZ) + (lp_prop - lp_cur)      # :123-127
@@ -222,8 +229,7 @@ def o_density_tempered(smc, y):
     epoch = smc.epoch
     smc.epoch += 1
     smc.cloud_epoch = epoch
-    smc.logZ, smc.x, smc.logw = o.batch_log_likelihood(smc.kind, smc.params(smc.theta), None, smc.N, y, smc.resampler,
-                                                       smc.seed, epoch, 0)        # :223-229
+    smc.logZ, smc.x, smc.logw = smc.sweep(smc.params(smc.theta), None, y, epoch)   # :223-229
     _, smc.omega, smc.ess = o.normalize(smc.logZ)          # :232
     xi = 0.0
     smc.schedule = []
@@ -279,8 +285,12 @@ def o_smc2_step(smc, y, t):
     with np.errstate(divide="ignore"):
         logw = np.log(smc.omega)                           # :324
     P = smc.params(smc.theta)
+    prop_t = None if smc.proposal is None else np.asarray(smc.proposal(P, float(y[t])), np.float64)
     for m in range(smc.M):                                 # :325-335
-        o.bootstrap_step(smc.kind, P[m], smc.x[m], smc.logw[m], y[t], t, smc.resampler, smc.seed, smc.cloud_epoch, m)
+        if smc.proposal is None:
+            o.bootstrap_step(smc.kind, P[m], smc.x[m], smc.logw[m], y[t], t, smc.resampler, smc.seed, smc.cloud_epoch, m)
+        else:
+            o.guided_step(smc.kind, P[m], smc.x[m], smc.logw[m], y[t], t, smc.resampler, prop_t[m], smc.seed, smc.cloud_epoch, m)
         lm, _, _ = o.normalize(smc.logw[m])
         logw[m] += lm
         smc.logZ[m] += lm

@@ -131,6 +131,15 @@ def _propose(θ, Σ, univariate, scale, z):
     return θ + z @ L.T
 
 
+def lg_optimal_proposals(P, y):
+    """[M, 3] locally optimal proposals p(x' | xp, y) of M univariate LinearModels given their parameter blocks
+    P [M, 8] = (A, B, Q, R, x0, σ0, ·, ·): 1/c2² = 1/Q + B²/R, c1 = c2²·A/Q, c0 = c2²·B·y/R (docs/SPEC.md §10)."""
+    P = np.asarray(P, np.float64)
+    A, B, Q, R = P[:, 0], P[:, 1], P[:, 2], P[:, 3]
+    s2 = 1.0 / (1.0 / Q + B * B / R)
+    return np.stack([s2 * B * float(y) / R, s2 * A / Q, np.sqrt(s2)], axis=1)
+
+
 # ----------------------------------------------------------------------------- the sampler
 class SMC:
     """mutable struct SMC (smc_samplers.jl:5-27) + constructor (:29-59).
@@ -141,11 +150,16 @@ class SMC:
     """
 
     def __init__(self, N, M, model, prior, chain, ess_threshold, min_ar=-1.0, *, seed=1998, resampler="multinomial",
-                 theta_resampler="multinomial", ctx=None, comm=None):
+                 theta_resampler="multinomial", ctx=None, comm=None, proposal=None):
         self.N, self.M, self.chain = int(N), int(M), int(chain)
         self.model, self.prior = model, prior
         self.kernel = random_walk_kernel
         self.acc_threshold, self.acc_ratio = float(min_ar), 0.0
+        # Extension (not in the reference's SMC): guided inner filters.  proposal(P [M, 8], y) -> [M, 3] gives every
+        # θ-particle's affine-Gaussian proposal (c0, c1, c2) for the step that assimilates y (docs/SPEC.md §10), e.g.
+        # lg_optimal_proposals; every inner filter step after the first then runs as particle_filter! instead of
+        # bootstrap_filter!.  None (default) is the reference's algorithm.
+        self.proposal = proposal
         self.seed = int(seed)
         self.resampler = resampler_id(resampler)
         self.theta_resampler = resampler_id(theta_resampler)
@@ -185,6 +199,12 @@ class SMC:
 
     def _local(self, v):
         return v[self.lo: self.lo + self.Mloc]
+
+    def _proposals(self, P_local, y):
+        """None, or the [len(y), Mloc, 3] proposal coefficients of the local θ-particles for every observation of y"""
+        if self.proposal is None:
+            return None
+        return np.stack([np.asarray(self.proposal(P_local, float(yt)), np.float64).reshape(P_local.shape[0], 3) for yt in np.atleast_1d(y)])
 
     def _next_epoch(self):
         e = self._epoch
@@ -369,7 +389,8 @@ def rejuvenate_(smc, y, ξ=1.0, verbose=False):
         params = smc._params(np.where(ok[:, None], θ_prop, smc.θ))
         smc._next_epoch()
         z_loc = smc._prop.log_likelihood(smc._local(params), y, smc.resampler, stream0=smc.lo,
-                                         active=smc._local(ok).astype(np.uint8))     # log_likelihood(N, y, model(θ_prop)) :117-121
+                                         active=smc._local(ok).astype(np.uint8),
+                                         proposal=smc._proposals(smc._local(params), y))   # log_likelihood(N, y, model(θ_prop)) :117-121
         smc._account(smc._prop, y.size)
         logZ_prop = smc.comm.all_gather(z_loc)
         with np.errstate(invalid="ignore"):
@@ -410,7 +431,7 @@ def exchange_(smc, y, verbose=False):
     if oldp is not None:
         oldp.close()
     smc._next_epoch()
-    z_loc = smc._cur.log_likelihood(smc._local(smc._P), y, smc.resampler, stream0=smc.lo)
+    z_loc = smc._cur.log_likelihood(smc._local(smc._P), y, smc.resampler, stream0=smc.lo, proposal=smc._proposals(smc._local(smc._P), y))
     smc._account(smc._cur, y.size)
     new_logZ = smc.comm.all_gather(z_loc)
     _, smc.ω, smc.ess = smc.ctx.normalize(new_logZ - smc.logZ)
@@ -421,7 +442,8 @@ def density_tempered(smc, y, verbose=True):
     """density_tempered(smc, y) (smc_samplers.jl:222-281), Duan & Fulop's density-tempered SMC."""
     y = np.ascontiguousarray(y, np.float64)
     smc._next_epoch()
-    z_loc = smc._cur.log_likelihood(smc._local(smc._P), y, smc.resampler, stream0=smc.lo)   # :223-229
+    z_loc = smc._cur.log_likelihood(smc._local(smc._P), y, smc.resampler, stream0=smc.lo,
+                                    proposal=smc._proposals(smc._local(smc._P), y))          # :223-229
     smc._account(smc._cur, y.size)
     smc.logZ = smc.comm.all_gather(z_loc)
     _, smc.ω, smc.ess = smc.ctx.normalize(smc.logZ)                    # :232
@@ -484,7 +506,9 @@ def smc2_step(smc, y, t, verbose=True):
         smc.rejuvenated = True
     with np.errstate(divide="ignore"):
         logω = np.log(smc.ω)                                            # :324
-    lm_loc, _ = smc._cur.step(y[t], smc.resampler, params=smc._local(smc._P) if smc._params_dirty else None)   # M × bootstrap_filter!  :325-331
+    prop = smc._proposals(smc._local(smc._P), y[t])
+    lm_loc, _ = smc._cur.step(y[t], smc.resampler, params=smc._local(smc._P) if smc._params_dirty else None,
+                              proposal=None if prop is None else prop[0])                  # M × bootstrap_filter! (particle_filter! when guided)  :325-331
     smc._params_dirty = False
     smc._account(smc._cur, 1)
     logmu = smc.comm.all_gather(lm_loc)

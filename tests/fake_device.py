@@ -42,23 +42,30 @@ class FakeBatch:
         return lm, es
 
     def step(self, y, resampler=0, params=None, proposal=None):
-        assert self.live and proposal is None
+        assert self.live
         if params is not None:
             self.P = np.array(params, np.float64)
         self.t += 1
         lm, es = np.empty(self.M), np.empty(self.M)
         for m in range(self.M):
-            o.bootstrap_step(self.kind, self.P[m], self.x[m], self.lw[m], float(y), self.t, resampler, self.seed, self.epoch,
-                             self.stream0 + m)
+            if proposal is None:
+                o.bootstrap_step(self.kind, self.P[m], self.x[m], self.lw[m], float(y), self.t, resampler, self.seed, self.epoch,
+                                 self.stream0 + m)
+            else:
+                o.guided_step(self.kind, self.P[m], self.x[m], self.lw[m], float(y), self.t, resampler, np.asarray(proposal)[m],
+                              self.seed, self.epoch, self.stream0 + m)
             lm[m], _, es[m] = o.normalize(self.lw[m])
         return lm, es
 
     def log_likelihood(self, params, y, resampler=0, stream0=0, active=None, proposal=None):
-        assert proposal is None
         self.P = np.array(params, np.float64)
         self._take_identity(stream0)
         y = np.ascontiguousarray(y, np.float64)
-        z, x, lw = o.batch_log_likelihood(self.kind, self.P, active, self.N, y, resampler, self.seed, self.epoch, self.stream0)
+        if proposal is None:
+            z, x, lw = o.batch_log_likelihood(self.kind, self.P, active, self.N, y, resampler, self.seed, self.epoch, self.stream0)
+        else:
+            z, x, lw = o.batch_guided_log_likelihood(self.kind, self.P, active, self.N, y, resampler, proposal, self.seed, self.epoch,
+                                                     self.stream0)
         on = np.ones(self.M, bool) if active is None else np.asarray(active, bool)
         self.x[on], self.lw[on] = x[on], lw[on]
         self.t, self.live = y.size - 1, True

@@ -153,11 +153,12 @@ def _sampler_worker(rank, world, port, out, algo):
         _, y = o.simulate(0, [0.5, 1.0, 0.9, 0.8, 0.0, 1.0], T, 1998)
         pg = smc.product_distribution([smc.TruncatedNormal(0, 1, -1, 1), smc.LogNormal(), smc.LogNormal()])
         po = S.OProduct([S.OTruncatedNormal(0, 1, -1, 1), S.OLogNormal(), S.OLogNormal()])
+        guided = ss.lg_optimal_proposals if algo.endswith("_guided") else None     # guided inner filters (extension, SPEC §10)
         g = smc.SMC(N, M, lambda θ: smc.StateSpaceModel(smc.LinearGaussian(θ[0], 1.0, θ[1], θ[2], 0.0), (1, 1)), pg, chain, 0.5,
-                    seed=5, ctx=FakeContext(5), comm=ss.TorchComm())
-        ref = S.OSMC(N, M, lambda θ: (0, [θ[0], 1.0, θ[1], θ[2], 0.0, 1.0]), po, chain, 0.5, seed=5)
+                    seed=5, ctx=FakeContext(5), comm=ss.TorchComm(), proposal=guided)
+        ref = S.OSMC(N, M, lambda θ: (0, [θ[0], 1.0, θ[1], θ[2], 0.0, 1.0]), po, chain, 0.5, seed=5, proposal=guided)
         n_rejuv = 0
-        if algo == "smc2":
+        if algo.startswith("smc2"):
             smc.smc2(g, y)
             S.o_smc2(ref, y)
             for t in range(1, T):
@@ -181,7 +182,7 @@ def _sampler_worker(rank, world, port, out, algo):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("algo", ["smc2", "density_tempered"])
+@pytest.mark.parametrize("algo", ["smc2", "density_tempered", "smc2_guided", "density_tempered_guided"])
 def test_sharded_sampler_logic_over_gloo(algo, oracle):
     """world_size 2, gloo: smc² / smc²! and density_tempered of the product run θ-sharded on two CPU ranks over an
     oracle-backed fake device and land on the single-process oracle sampler bit for bit (θ, clouds) — the sharding by

@@ -497,3 +497,33 @@ def test_cuda_path_against_committed_golden_vectors(ctx):
             assert abs(ll[0] - lg) <= 1e-12 * abs(lg)
             np.testing.assert_allclose(x[0], [float.fromhex(c) for c in v["x_hex"]], rtol=1e-11, atol=1e-13)
             np.testing.assert_allclose(S[0].ravel(), [float.fromhex(c) for c in v["S_hex"]], rtol=1e-11, atol=1e-13)
+
+
+@pytest.mark.gpu
+def test_smc2_with_guided_inner_filters(ctx, oracle):
+    """extension of SMC (not in the reference): every inner filter step guided by the θ-particle's own locally optimal
+    proposal (SMC(..., proposal=lg_optimal_proposals)); smc² / smc²! with rejuvenations against the oracle's sampler run
+    the same way — θ and clouds bit for bit.  (Host logic also covered on CPU ranks: test_sharded_sampler_logic_over_gloo.)"""
+    from oracle import samplers as S
+    N, M, T, chain = 64, 48, 40, 2
+    _, y = oracle.simulate(0, LG, T, 1998)
+    pg = smc.product_distribution([smc.TruncatedNormal(0, 1, -1, 1), smc.LogNormal(), smc.LogNormal()])
+    po = S.OProduct([S.OTruncatedNormal(0, 1, -1, 1), S.OLogNormal(), S.OLogNormal()])
+    g = smc.SMC(N, M, lambda θ: smc.StateSpaceModel(smc.LinearGaussian(θ[0], 1.0, θ[1], θ[2], 0.0), (1, 1)), pg, chain, 0.5, seed=11,
+                resampler="systematic", ctx=ctx, proposal=smc.lg_optimal_proposals)
+    ref = S.OSMC(N, M, lambda θ: (0, [θ[0], 1.0, θ[1], θ[2], 0.0, 1.0]), po, chain, 0.5, seed=11, resampler=oracle.SYSTEMATIC,
+                 proposal=smc.lg_optimal_proposals)
+    smc.smc2(g, y)
+    S.o_smc2(ref, y)
+    n = 0
+    for t in range(1, T):
+        smc.smc2_step(g, y, t, verbose=False)
+        S.o_smc2_step(ref, y, t)
+        assert g.rejuvenated == ref.rejuvenated
+        n += g.rejuvenated
+    assert n >= 1
+    np.testing.assert_array_equal(g.θ, ref.theta)
+    np.testing.assert_allclose(g.logZ, ref.logZ, rtol=RTOL, atol=0)
+    np.testing.assert_allclose(g.ω, ref.omega, rtol=1e-9, atol=1e-300)
+    np.testing.assert_array_equal(g.x, ref.x)
+    g.close()
