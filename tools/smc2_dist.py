@@ -49,7 +49,9 @@ else:                # tiny, for the independence check
     y = smc.simulate(lg_mod([0.5, 0.9, 0.8]), T, seed=1998)[1]
 
 resampler = os.environ.get("RESAMPLER", "multinomial")
-s = smc.SMC(N, M, model, prior, chain, 0.5, seed=1998, ctx=ctx, comm=comm, resampler=resampler)
+# GUIDED=1: guided inner filters (locally optimal proposals; LG configs only — SMC(..., proposal=...), docs/SPEC.md §10)
+proposal = smc.lg_optimal_proposals if os.environ.get("GUIDED") == "1" and model is lg_mod else None
+s = smc.SMC(N, M, model, prior, chain, 0.5, seed=1998, ctx=ctx, comm=comm, resampler=resampler, proposal=proposal)
 if world > 1:
     dist.barrier()
 torch.cuda.synchronize()
