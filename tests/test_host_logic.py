@@ -256,14 +256,16 @@ def test_ibis_host_logic_on_the_fake_device(oracle, which):
     assert q[1] == pytest.approx(yo, abs=1e-12) and q[2] - q[1] == pytest.approx(1.6448536269514722 * np.sqrt(So), rel=1e-9) and q[0] < q[1] < q[2]
 
 
-def test_exchange_host_logic_on_the_fake_device(oracle):
+@pytest.mark.parametrize("guided", [False, True])
+def test_exchange_host_logic_on_the_fake_device(oracle, guided):
     """exchange! (smc_samplers.jl:163-189) on the CPU stand-in: with min_ar above any acceptance rate N doubles after a
     rejuvenation, every θ is re-filtered with the doubled cloud and ω ∝ exp(new logZ − logZ)"""
     from tests.fake_device import FakeContext
     N, M, T = 32, 16, 30
     _, y = oracle.simulate(0, [0.5, 1.0, 0.9, 0.8, 0.0, 1.0], T, 1998)
     pg = smc.product_distribution([smc.TruncatedNormal(0, 1, -1, 1), smc.LogNormal(), smc.LogNormal()])
-    g = smc.SMC(N, M, lambda θ: smc.LinearGaussian(θ[0], 1.0, θ[1], θ[2], 0.0), pg, 1, 0.9, 2.0, seed=2, ctx=FakeContext(2))
+    prop = ss.lg_optimal_proposals if guided else None
+    g = smc.SMC(N, M, lambda θ: smc.LinearGaussian(θ[0], 1.0, θ[1], θ[2], 0.0), pg, 1, 0.9, 2.0, seed=2, ctx=FakeContext(2), proposal=prop)
     smc.smc2(g, y)
     for t in range(1, T):
         smc.smc2_step(g, y, t, verbose=False)
@@ -272,9 +274,17 @@ def test_exchange_host_logic_on_the_fake_device(oracle):
     assert g.rejuvenated and g.N == 64 and g.x.shape == (M, 1, 64)
     assert np.isfinite(g.logZ).all() and abs(g.ω.sum() - 1) < 1e-12
     # the doubled clouds: a fresh 64-particle filter over y[:t] on the new batch's Philox identity, then this call's own step to y[t]
-    _, x, lw = oracle.batch_log_likelihood(0, g._P, None, 64, y[:t], 0, g._cur.seed, g._cur.epoch, 0)
+    if guided:
+        pr = np.stack([ss.lg_optimal_proposals(g._P, yt) for yt in y[:t]])
+        _, x, lw = oracle.batch_guided_log_likelihood(0, g._P, None, 64, y[:t], 0, pr, g._cur.seed, g._cur.epoch, 0)
+    else:
+        _, x, lw = oracle.batch_log_likelihood(0, g._P, None, 64, y[:t], 0, g._cur.seed, g._cur.epoch, 0)
+    pt = ss.lg_optimal_proposals(g._P, y[t])
     for m in range(M):
-        oracle.bootstrap_step(0, g._P[m], x[m], lw[m], y[t], t, 0, g._cur.seed, g._cur.epoch, m)
+        if guided:
+            oracle.guided_step(0, g._P[m], x[m], lw[m], y[t], t, 0, pt[m], g._cur.seed, g._cur.epoch, m)
+        else:
+            oracle.bootstrap_step(0, g._P[m], x[m], lw[m], y[t], t, 0, g._cur.seed, g._cur.epoch, m)
     np.testing.assert_array_equal(g._cur.x, x)
     assert g._cur.t == t
     smc.smc2_step(g, y, t + 1, verbose=False)
