@@ -8,7 +8,8 @@ function by function, on top of the C oracle's particle filters (oracle/smc_orac
     o_density_tempered  <- density_tempered                 :222-281
     o_smc2 / o_smc2_step<- smc² / smc²!                     :288-340
     o_expected_parameters <- expected_parameters            :61-65
-    OIBIS, o_ibis_*     <- IBIS + methods                   /root/reference/src/ibis.jl:3-189
+    OIBIS, o_ibis_*     <- IBIS + methods                   /root/reference/src/ibis.jl:3-189 (scalar and matrix Kalman inner filter)
+    OSMC(proposal=...)  <- extension, not in the reference: guided inner filters (docs/SPEC.md §10) in every sweep / step
     priors              <- the Distributions.jl subset used by README.md:81-85 and
                            examples/inflation_example.jl:234-239 (un-vendored, un-pinned: SURVEY F8)
 
