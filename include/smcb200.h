@@ -30,6 +30,7 @@ extern "C" {
 
 typedef struct smcb_ctx smcb_ctx;     /* one GPU, one stream, one single-filter slot */
 typedef struct smcb_batch smcb_batch; /* M independent filters of N particles (θ-level samplers) */
+typedef struct smcb_sampler smcb_sampler; /* a device-resident SMC² / density-tempered sampler (mutable struct SMC) */
 
 typedef enum {
   SMCB_OK = 0,
@@ -37,7 +38,8 @@ typedef enum {
   SMCB_ERR_CUDA = -2,
   SMCB_ERR_OOM = -3,
   SMCB_ERR_STATE = -4, /* e.g. step before init */
-  SMCB_ERR_UNSUPPORTED = -5
+  SMCB_ERR_UNSUPPORTED = -5,
+  SMCB_ERR_NCCL = -6 /* NCCL missing or a collective failed (multi-GPU entry points only) */
 } smcb_status;
 
 /* params[8] per model (unused trailing entries ignored):
@@ -183,6 +185,83 @@ int64_t smcb_batch_cloud_bytes(const smcb_batch* b);
 int smcb_batch_pack(smcb_batch* b, const int32_t* slots, int64_t n, void* buf_dev);
 int smcb_batch_unpack(smcb_batch* b, const int32_t* slots, int64_t n, const void* buf_dev);
 int smcb_batch_get_timing(const smcb_batch* b, double* ms_last_call, int64_t* launches_total);
+
+/* ------------------------------------------------------------------ multi-GPU: one process per GPU, θ sharded
+ * The reference's only parallelism is Threads.@threads over θ (smc_samplers.jl:112,174,223); here rank r of G owns the
+ * θ-particles [r·M/G, (r+1)·M/G) with their whole state clouds.  NCCL is bound at run time (dlopen of libnccl.so.2, or
+ * $SMCB_NCCL_LIB); single-GPU users never need it.  Rank 0 calls smcb_comm_unique_id, the host language carries the 128
+ * bytes to the other ranks (MPI.bcast, a file, torch.distributed ...), then EVERY rank calls smcb_comm_init (collective).
+ * Samplers created from the context afterwards are sharded; their results do not depend on G. */
+int smcb_comm_unique_id(uint8_t id[128]);
+int smcb_comm_init(smcb_ctx* ctx, int rank, int nranks, const uint8_t id[128]);
+int smcb_comm_rank(const smcb_ctx* ctx, int* rank, int* nranks);
+/* all[r·n_local + i] = rank r's local[i] on every rank (host vectors; ncclAllGather on the context's stream) */
+int smcb_comm_all_gather(smcb_ctx* ctx, const double* local, int64_t n_local, double* all);
+int smcb_comm_destroy(smcb_ctx* ctx);
+/* host-only (no GPU): who sends which cloud where after a θ-resample with (sorted) parents[M].  local_parents [M/G]:
+ * rank-local parent slot (the slot itself where the parent is remote); send_* / recv_*: the clouds this rank sends /
+ * receives as (peer rank, local slot), grouped by peer, increasing global slot — both sides enumerate the same order.
+ * send_* / recv_* may be NULL (counts only); capacity M entries for send_* (one cloud may have children in every slot of the
+ * other ranks), M/G for recv_*. */
+int smcb_exchange_plan(const int32_t* parents, int64_t M, int rank, int nranks, int32_t* local_parents, int32_t* send_peer,
+                       int32_t* send_slot, int64_t* n_send, int32_t* recv_peer, int32_t* recv_slot, int64_t* n_recv);
+
+/* ------------------------------------------------------------------ device-resident θ-level samplers
+ * mutable struct SMC + SMC(N, M, model, prior, chain, ess_threshold, min_ar)     smc_samplers.jl:5-59
+ * θ, ω, logZ, the log-prior and the parameter blocks of all M θ-particles live on the GPU (replicated on every rank of
+ * the communicator); the M inner particle filters are sharded.  Per smc²! the host enqueues one batched filter step, one
+ * in-place all-gather of M/G doubles and one single-CTA kernel (logω += logμ, normalise, ESS) and reads back 64 bytes.
+ *   prior: product of d_theta univariate laws, row k = (family, p0, p1, lo, hi, c0, c1, 0):
+ *     0 Normal(μ=p0, σ=p1), c0 = log σ        1 LogNormal(μ=p0, σ=p1), c0 = log σ
+ *     2 Uniform(lo, hi), c0 = -log(hi - lo)    3 TruncatedNormal(μ=p0, σ=p1, lo, hi), c0 = log σ, c1 = log mass of [lo, hi]
+ *   model: θ -> StateSpaceModel as a selection map, params[k] = map_src[k] >= 0 ? θ[map_src[k]] : map_const[k]
+ *     (README.md:75-78 lg_mod: src = {0,-1,1,2,-1,-1,..}, const = {·,1,·,·,0,1}; examples/inflation_example.jl:229-232)
+ *   theta0 [M][d_theta]: the prior draws θ = map(m -> rand(prior), 1:M) (:38), drawn by the host language.
+ * The arithmetic of the θ level (covariance, Cholesky, proposal, accept) is frozen in docs/SPEC.md §11. */
+typedef struct {
+  int32_t kind;            /* smcb_model_kind of model(θ) */
+  int32_t d_theta;         /* 1..8 */
+  int64_t N;               /* state particles per θ (<= 8192; exchange! doubles it) */
+  int64_t M;               /* θ-particles (2..16384, divisible by the number of ranks) */
+  int32_t chain;           /* PMMH moves per rejuvenation */
+  int32_t resampler;       /* smcb_resampler of the inner filters */
+  int32_t theta_resampler; /* smcb_resampler of resample!(smc) */
+  int32_t reserved;
+  double ess_threshold;    /* ess_min = M · ess_threshold                       :46 */
+  double min_ar;           /* acc_threshold of exchange! (-1.0 disables it)     :35 */
+  uint64_t seed;
+  double prior[8][8];
+  int32_t map_src[8];
+  double map_const[8];
+} smcb_sampler_config;
+int smcb_sampler_create(smcb_ctx* ctx, const smcb_sampler_config* cfg, const double* theta0, smcb_sampler** out);
+int smcb_sampler_destroy(smcb_sampler* s);
+/* the observations y[0..T) the following calls refer to (copied to the device once) */
+int smcb_sampler_set_data(smcb_sampler* s, const double* y, int64_t T);
+/* smc²(smc, y)                                                              smc_samplers.jl:288-301 */
+int smcb_sampler_smc2_init(smcb_sampler* s);
+/* smc²!(smc, y, t): assimilates y[t] (0-based; Julia's t is t+1); resample! / rejuvenate! / exchange! first when
+ * ess < ess_min.  ess, rejuvenated may be NULL.                              smc_samplers.jl:308-340 */
+int smcb_sampler_smc2_step(smcb_sampler* s, int64_t t, double* ess, int* rejuvenated);
+/* density_tempered(smc, y); schedule [cap][3] receives (ξ, ess, acceptance ratio of the stage's rejuvenation or -1 when the
+ * stage did not resample) of every stage (may be NULL)                         smc_samplers.jl:222-281 */
+int smcb_sampler_density_tempered(smcb_sampler* s, double* schedule, int cap, int* n_stages);
+/* public fields of the struct: θ [M][d_theta], ω [M], logZ [M], ess, acc_ratio, N; any may be NULL   :5-27 */
+int smcb_sampler_get(smcb_sampler* s, double* theta, double* omega, double* logZ, double* ess, double* acc_ratio, int64_t* N);
+/* smc.x, smc.w: a view of this rank's M/G live clouds for smcb_batch_fetch / _weighted_* (owned by the sampler; valid
+ * until the next call that may run exchange!) */
+int smcb_sampler_clouds(smcb_sampler* s, smcb_batch** clouds);
+/* ms[0..3]: device time in the inner filters / all-gathers / cloud moves (θ-resample exchange + accept copies) / θ-level
+ * kernels (CUDA events, only while profiling is on); counts: whole-series sweeps, smc²! steps, rejuvenations, clouds
+ * received from other ranks, particle-updates of this rank, stream synchronisations, kernel launches, θ-resamples */
+int smcb_sampler_set_profiling(smcb_sampler* s, int enable);
+int smcb_sampler_stats(smcb_sampler* s, double ms[8], int64_t counts[8]);
+/* host-only (no GPU): Σ of random_walk_kernel(θ) for θ [M][d] (d×d row-major; d = 1: the σ the reference uses as a standard
+ * deviation) and the lower Cholesky factor of scale·A — the fixed-order arithmetic of docs/SPEC.md §11, exposed so that a
+ * host-language sampler (arbitrary model / prior closures) proposes exactly what the device sampler proposes.
+ *                                                                           smc_samplers.jl:87-101 */
+int smcb_random_walk_sigma(const double* theta, int64_t M, int d, double* sigma);
+int smcb_cholesky_lower(const double* A, int d, double scale, double* L);
 
 /* Kalman filter for LG1D, M models at once                             kalman_filter.jl:29-70
  * params [M][8]; x, sigma [M] in/out; loglik [M] out (step log-likelihoods) */

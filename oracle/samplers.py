@@ -5,6 +5,7 @@ function by function, on top of the C oracle's particle filters (oracle/smc_orac
     o_resample          <- resample!                        :74-84
     o_random_walk_kernel<- random_walk_kernel               :87-101
     o_rejuvenate        <- rejuvenate!                      :103-148
+    o_exchange          <- exchange!                        :163-189
     o_density_tempered  <- density_tempered                 :222-281
     o_smc2 / o_smc2_step<- smc² / smc²!                     :288-340
     o_expected_parameters <- expected_parameters            :61-65
@@ -173,16 +174,56 @@ def o_resample(smc):
     return a
 
 
+def _seq_sum(v):
+    """left-to-right sum (np.cumsum accumulates sequentially; np.sum is pairwise)"""
+    return np.cumsum(np.ascontiguousarray(v, np.float64))[-1]
+
+
+def o_cholesky(A):
+    """lower Cholesky factor by the plain Cholesky–Banachiewicz recursion (docs/SPEC.md §11: LAPACK's blocked / fused
+    operation order is not reproducible on a device)"""
+    d = A.shape[0]
+    L = np.zeros((d, d))
+    for j in range(d):
+        s = float(A[j, j])
+        for k in range(j):
+            s = s - L[j, k] * L[j, k]
+        if not s > 0.0:
+            raise np.linalg.LinAlgError("Matrix is not positive definite")
+        L[j, j] = math.sqrt(s)
+        for i in range(j + 1, d):
+            v = float(A[i, j])
+            for k in range(j):
+                v = v - L[i, k] * L[j, k]
+            L[i, j] = v / L[j, j]
+    return L
+
+
+def o_propose(theta, L, z):
+    """θ'_j = θ_j + Σ_{k<=j} z_k L[j][k], k ascending (docs/SPEC.md §11)"""
+    out = np.empty_like(theta)
+    for j in range(theta.shape[1]):
+        acc = z[:, 0] * L[j, 0]
+        for k in range(1, j + 1):
+            acc = acc + z[:, k] * L[j, k]
+        out[:, j] = theta[:, j] + acc
+    return out
+
+
 def o_random_walk_kernel(theta):
     M, d = theta.shape
-    c = theta - theta.mean(axis=0)
-    cov = (c.T @ c) / (M - 1)
+    mean = np.array([_seq_sum(theta[:, k]) for k in range(d)]) / M     # cov(Θ'): sums in slot order (docs/SPEC.md §11)
+    c = theta - mean
+    cov = np.empty((d, d))
+    for j in range(d):
+        for k in range(j, d):
+            cov[j, k] = cov[k, j] = _seq_sum(c[:, j] * c[:, k]) / (M - 1)
     if d == 1:                                             # :87-92
-        dth = 2.83 ** 2
+        dth = 2.83 * 2.83
         sig = 1.0e-2 if abs(cov[0, 0]) < 1.0e-8 else dth * cov[0, 0] + 1.0e-10
         return np.array([[sig]]), True
-    dth = 2.83 ** 2 / d                                    # :97
-    if math.sqrt(float(np.sum(cov * cov))) < 1.0e-8:       # norm(cov) < 1e-8                    :98
+    dth = (2.83 * 2.83) / d                                # :97
+    if math.sqrt(float(_seq_sum((cov * cov).ravel()))) < 1.0e-8:       # norm(cov) < 1e-8        :98
         return 1.0e-2 * np.eye(d), False
     return dth * cov + 1.0e-10 * np.eye(d), False
 
@@ -201,8 +242,7 @@ def o_rejuvenate(smc, y, xi=1.0):
         if uni:
             prop = smc.theta + (scales[c] * Sigma[0, 0]) * z
         else:
-            L = np.linalg.cholesky(scales[c] * Sigma)
-            prop = smc.theta + z @ L.T                     # rand(MvNormal(θ[m], scales[c]·Σ))    :114
+            prop = o_propose(smc.theta, o_cholesky(scales[c] * Sigma), z)   # rand(MvNormal(θ[m], scales[c]·Σ))    :114
         ok = np.array([smc.prior.insupport(th) for th in prop])       # :116
         P = smc.params(np.where(ok[:, None], prop, smc.theta))
         epoch = smc.epoch
@@ -223,6 +263,21 @@ def o_rejuvenate(smc, y, xi=1.0):
     smc.omega = np.full(M, 1.0 / M)                        # ω[m] = 1.0                            :139
     smc.acc_ratio = float(acc.sum()) / M                   # :142
     return smc
+
+
+def o_exchange(smc, y):
+    """exchange!(smc, y)  smc_samplers.jl:163-189: double N when the acceptance ratio fell below acc_threshold"""
+    if not (smc.acc_ratio < smc.acc_threshold):            # :164
+        return
+    if smc.N > 4096:                                       # :166,186-187
+        return
+    smc.N *= 2                                             # :167
+    epoch = smc.epoch
+    smc.epoch += 1
+    smc.cloud_epoch = epoch
+    new_logZ, smc.x, smc.logw = smc.sweep(smc.params(smc.theta), None, np.ascontiguousarray(y, np.float64), epoch)   # :174-180
+    _, smc.omega, smc.ess = o.normalize(new_logZ - smc.logZ)   # :183
+    smc.logZ = new_logZ                                    # :184
 
 
 def o_density_tempered(smc, y):
@@ -282,6 +337,7 @@ def o_smc2_step(smc, y, t):
     if smc.ess < smc.ess_min:                              # :312
         o_resample(smc)                                    # :314
         o_rejuvenate(smc, y[:t], 1.0)                      # :317
+        o_exchange(smc, y[:t])                             # :320
         smc.rejuvenated = True
     with np.errstate(divide="ignore"):
         logw = np.log(smc.omega)                           # :324
@@ -361,7 +417,7 @@ def o_ibis_rejuvenate(s, y):
     lp_cur = np.array([s.prior.logpdf(th) for th in s.theta])
     for c in range(s.chain):                               # ibis.jl:95-119
         z = np.stack([o.normals(s.seed, ordinal, k, c, o.P_MH_PROPOSAL, 0, M) for k in range(d)], axis=1)
-        prop = s.theta + ((scales[c] * Sigma[0, 0]) * z if uni else z @ np.linalg.cholesky(scales[c] * Sigma).T)
+        prop = s.theta + (scales[c] * Sigma[0, 0]) * z if uni else o_propose(s.theta, o_cholesky(scales[c] * Sigma), z)
         ok = np.array([s.prior.insupport(th) for th in prop])
         P = s.params(np.where(ok[:, None], prop, s.theta))
         zprop, xprop, Sprop = np.full(M, -math.inf), np.zeros_like(s.x), np.zeros_like(s.Sigma)

@@ -16,6 +16,18 @@ P_PRIOR, P_THETA_RESAMPLE, P_MH_PROPOSAL, P_MH_ACCEPT, P_SIMULATE = 4, 5, 6, 7, 
 
 _c_ctx = C.c_void_p
 _c_batch = C.c_void_p
+_c_sampler = C.c_void_p
+PRIOR_NORMAL, PRIOR_LOGNORMAL, PRIOR_UNIFORM, PRIOR_TRUNCNORMAL = 0, 1, 2, 3
+MAX_THETA_DIM, MAX_THETA_PARTICLES = 8, 16384
+
+
+class SamplerConfig(C.Structure):
+    """smcb_sampler_config (include/smcb200.h)"""
+    _fields_ = [("kind", C.c_int32), ("d_theta", C.c_int32), ("N", C.c_int64), ("M", C.c_int64), ("chain", C.c_int32),
+                ("resampler", C.c_int32), ("theta_resampler", C.c_int32), ("reserved", C.c_int32), ("ess_threshold", C.c_double),
+                ("min_ar", C.c_double), ("seed", C.c_uint64), ("prior", (C.c_double * 8) * 8), ("map_src", C.c_int32 * 8),
+                ("map_const", C.c_double * 8)]
+
 _dp = C.POINTER(C.c_double)
 _i64p = C.POINTER(C.c_int64)
 
@@ -66,6 +78,25 @@ SIGNATURES = {
     "smcb_batch_pack": (C.c_int, [_c_batch, C.c_void_p, C.c_int64, C.c_void_p]),
     "smcb_batch_unpack": (C.c_int, [_c_batch, C.c_void_p, C.c_int64, C.c_void_p]),
     "smcb_batch_get_timing": (C.c_int, [_c_batch, _dp, _i64p]),
+    "smcb_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "smcb_comm_init": (C.c_int, [_c_ctx, C.c_int, C.c_int, C.c_void_p]),
+    "smcb_comm_rank": (C.c_int, [_c_ctx, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "smcb_comm_all_gather": (C.c_int, [_c_ctx, C.c_void_p, C.c_int64, C.c_void_p]),
+    "smcb_comm_destroy": (C.c_int, [_c_ctx]),
+    "smcb_exchange_plan": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, _i64p,
+                                     C.c_void_p, C.c_void_p, _i64p]),
+    "smcb_sampler_create": (C.c_int, [_c_ctx, C.POINTER(SamplerConfig), C.c_void_p, C.POINTER(_c_sampler)]),
+    "smcb_sampler_destroy": (C.c_int, [_c_sampler]),
+    "smcb_sampler_set_data": (C.c_int, [_c_sampler, C.c_void_p, C.c_int64]),
+    "smcb_sampler_smc2_init": (C.c_int, [_c_sampler]),
+    "smcb_sampler_smc2_step": (C.c_int, [_c_sampler, C.c_int64, _dp, C.POINTER(C.c_int)]),
+    "smcb_sampler_density_tempered": (C.c_int, [_c_sampler, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
+    "smcb_sampler_get": (C.c_int, [_c_sampler, C.c_void_p, C.c_void_p, C.c_void_p, _dp, _dp, _i64p]),
+    "smcb_sampler_clouds": (C.c_int, [_c_sampler, C.POINTER(_c_batch)]),
+    "smcb_sampler_set_profiling": (C.c_int, [_c_sampler, C.c_int]),
+    "smcb_sampler_stats": (C.c_int, [_c_sampler, _dp, _i64p]),
+    "smcb_random_walk_sigma": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
+    "smcb_cholesky_lower": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
     "smcb_kalman_batch_step": (C.c_int, [_c_ctx, C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]),
     "smcb_kalman_batch_loglik": (C.c_int, [_c_ctx, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int,
                                            C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -93,12 +124,11 @@ def library_path():
 
 
 def load():
-    """dlopen libsmcb200.so (building it first if the sources are newer) and bind every symbol."""
+    """dlopen libsmcb200.so (rebuilding it first when a source or header is newer than the binary: a stale
+    library would silently break the bit-for-bit agreement of host, device and oracle) and bind every symbol."""
     global _LIB
     if _LIB is None:
-        path = _build.LIB_PATH
-        if not os.path.exists(path):
-            path = _build.build_library()
+        path = _build.build_library()   # returns at once when the binary is up to date
         lib = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(lib, name)  # AttributeError if the library does not export a declared symbol
@@ -146,6 +176,53 @@ def rng_uniforms64(seed, epoch, stream, t, purpose, n):
 def rng_uniforms01(seed, epoch, stream, t, purpose, n):
     """(U64 >> 11) * 2^-53 in [0, 1)."""
     return (rng_uniforms64(seed, epoch, stream, t, purpose, n) >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
+
+
+def random_walk_sigma(θ):
+    """Σ of random_walk_kernel(θ) for θ [M, d] in the fixed summation order of docs/SPEC.md §11 (host-only)."""
+    θ = np.ascontiguousarray(θ, np.float64)
+    M, d = θ.shape
+    out = np.zeros((d, d))
+    rc = load().smcb_random_walk_sigma(_ptr(θ), M, d, _ptr(out))
+    if rc != 0:
+        raise SMCBError(rc, "smcb_random_walk_sigma: bad arguments")
+    return out
+
+
+def cholesky_lower(A, scale=1.0):
+    """lower Cholesky factor of scale·A by the plain Cholesky–Banachiewicz recursion (docs/SPEC.md §11, host-only)."""
+    A = np.ascontiguousarray(A, np.float64)
+    d = A.shape[0]
+    L = np.zeros((d, d))
+    rc = load().smcb_cholesky_lower(_ptr(A), d, float(scale), _ptr(L))
+    if rc != 0:
+        raise np.linalg.LinAlgError("Matrix is not positive definite")
+    return L
+
+
+def exchange_plan(parents, rank, world):
+    """smcb_exchange_plan: (local_parents [M/G], [(peer, slot)] to send, [(peer, slot)] to receive) — host-only"""
+    a = np.ascontiguousarray(parents, np.int32)
+    Mloc = a.size // world
+    lp = np.empty(Mloc, np.int32)
+    sp, ss = np.empty(a.size, np.int32), np.empty(a.size, np.int32)   # one cloud may go to every slot of every other rank
+    rp, rs = np.empty(Mloc, np.int32), np.empty(Mloc, np.int32)
+    ns, nr = C.c_int64(), C.c_int64()
+    rc = load().smcb_exchange_plan(_ptr(a), a.size, int(rank), int(world), _ptr(lp), _ptr(sp), _ptr(ss), C.byref(ns), _ptr(rp), _ptr(rs),
+                                   C.byref(nr))
+    if rc != 0:
+        raise SMCBError(rc, "smcb_exchange_plan: bad arguments")
+    return lp, list(zip(sp[: ns.value].tolist(), ss[: ns.value].tolist())), list(zip(rp[: nr.value].tolist(), rs[: nr.value].tolist()))
+
+
+def comm_unique_id():
+    """128 bytes identifying a new NCCL communicator (call on ONE rank, carry to the others, then Context.comm_init)"""
+    buf = (C.c_uint8 * 128)()
+    rc = load().smcb_comm_unique_id(buf)
+    if rc != 0:
+        msg = load().smcb_last_error(None)
+        raise SMCBError(rc, msg.decode() if msg else "smcb_comm_unique_id failed")
+    return bytes(buf)
 
 
 def simulate(kind, params, T, seed):
@@ -384,6 +461,102 @@ class Context:
     def batch(self, kind, M, N):
         return Batch(self, kind, M, N)
 
+    # ---- multi-GPU (one process per GPU)
+    def comm_init(self, rank, nranks, unique_id):
+        """join the NCCL communicator named by unique_id (collective: every rank calls it); samplers created from
+        this context afterwards shard their θ-particles over the ranks"""
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(unique_id))
+        self._check(self._lib.smcb_comm_init(self._h, int(rank), int(nranks), buf))
+
+    def comm_rank(self):
+        r, n = C.c_int(), C.c_int()
+        self._check(self._lib.smcb_comm_rank(self._h, C.byref(r), C.byref(n)))
+        return r.value, n.value
+
+    def comm_all_gather(self, local):
+        local = np.ascontiguousarray(local, np.float64)
+        _, n = self.comm_rank()
+        out = np.empty((n * local.shape[0],) + local.shape[1:])
+        self._check(self._lib.smcb_comm_all_gather(self._h, _ptr(local), local.size, _ptr(out)))
+        return out
+
+    def comm_destroy(self):
+        self._check(self._lib.smcb_comm_destroy(self._h))
+
+    def sampler(self, config, theta0):
+        return Sampler(self, config, theta0)
+
+
+class Sampler:
+    """smcb_sampler: a device-resident SMC² / density-tempered sampler (csrc/smcb_sampler.cu)"""
+
+    def __init__(self, ctx, config, theta0):
+        self.ctx, self._lib = ctx, ctx._lib
+        self.cfg = config
+        self.M, self.d = int(config.M), int(config.d_theta)
+        θ0 = np.ascontiguousarray(theta0, np.float64).reshape(self.M, self.d)
+        self._h = _c_sampler()
+        ctx._check(self._lib.smcb_sampler_create(ctx._h, C.byref(config), _ptr(θ0), C.byref(self._h)))
+        self._rank, self._world = ctx.comm_rank()
+
+    def close(self):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
+            self._lib.smcb_sampler_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_data(self, y):
+        y = np.ascontiguousarray(y, np.float64)
+        self.ctx._check(self._lib.smcb_sampler_set_data(self._h, _ptr(y), y.size))
+
+    def smc2_init(self):
+        self.ctx._check(self._lib.smcb_sampler_smc2_init(self._h))
+
+    def smc2_step(self, t):
+        ess, rj = C.c_double(), C.c_int()
+        self.ctx._check(self._lib.smcb_sampler_smc2_step(self._h, int(t), C.byref(ess), C.byref(rj)))
+        return ess.value, bool(rj.value)
+
+    def density_tempered(self, cap=4096):
+        """[(ξ, ess, acceptance ratio or -1)] of every tempering stage"""
+        sched = np.zeros((cap, 3))
+        n = C.c_int()
+        self.ctx._check(self._lib.smcb_sampler_density_tempered(self._h, _ptr(sched), cap, C.byref(n)))
+        return [(float(a), float(b), float(c)) for a, b, c in sched[: min(n.value, cap)]]
+
+    def get(self, want_theta=True, want_omega=True, want_logZ=True):
+        θ = np.empty((self.M, self.d)) if want_theta else None
+        ω = np.empty(self.M) if want_omega else None
+        z = np.empty(self.M) if want_logZ else None
+        ess, ar, N = C.c_double(), C.c_double(), C.c_int64()
+        self.ctx._check(self._lib.smcb_sampler_get(self._h, _ptr(θ), _ptr(ω), _ptr(z), C.byref(ess), C.byref(ar), C.byref(N)))
+        return θ, ω, z, ess.value, ar.value, N.value
+
+    def clouds(self):
+        """a Batch view of this rank's live clouds (owned by the sampler)"""
+        h = _c_batch()
+        self.ctx._check(self._lib.smcb_sampler_clouds(self._h, C.byref(h)))
+        _, _, _, _, _, N = self.get(False, False, False)
+        return Batch._view(self.ctx, int(self.cfg.kind), self.M // self._world, N, h)
+
+    def set_profiling(self, on=True):
+        self.ctx._check(self._lib.smcb_sampler_set_profiling(self._h, int(bool(on))))
+
+    def stats(self):
+        ms = (C.c_double * 8)()
+        n = (C.c_int64 * 8)()
+        self.ctx._check(self._lib.smcb_sampler_stats(self._h, ms, n))
+        keys_ms = ("filter_ms", "allgather_ms", "exchange_ms", "theta_ms")
+        keys_n = ("sweeps", "steps", "rejuvenations", "clouds_moved", "particle_updates", "syncs", "launches", "theta_resamples")
+        out = {k: float(ms[i]) for i, k in enumerate(keys_ms)}
+        out.update({k: int(n[i]) for i, k in enumerate(keys_n)})
+        return out
+
 
 class Batch:
     """M filters of N particles (smcb_batch): the particle-of-filters of SMC² / PMMH sweeps."""
@@ -394,10 +567,20 @@ class Batch:
         self.kind, self.M, self.N = int(kind), int(M), int(N)
         self.d = state_dim(self.kind)
         self._h = _c_batch()
+        self._owned = True
         ctx._check(self._lib.smcb_batch_create(ctx._h, self.kind, self.M, self.N, C.byref(self._h)))
 
+    @classmethod
+    def _view(cls, ctx, kind, M, N, handle):
+        b = cls.__new__(cls)
+        b.ctx, b._lib = ctx, ctx._lib
+        b.kind, b.M, b.N = int(kind), int(M), int(N)
+        b.d = state_dim(b.kind)
+        b._h, b._owned = handle, False
+        return b
+
     def close(self):
-        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None):
+        if getattr(self, "_h", None) and getattr(self.ctx, "_h", None) and getattr(self, "_owned", True):
             self._lib.smcb_batch_destroy(self._h)
         self._h = None
 

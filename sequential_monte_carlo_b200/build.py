@@ -11,8 +11,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libsmcb200.so")
-SOURCES = ["smcb_filter.cu", "smcb_batch.cu", "smcb_capi.cu"]
-HEADERS = ["smcb_common.cuh", "smcb_detmath.cuh", "smcb_models.cuh", "smcb_filter.cuh", "smcb_batch.cuh",
+SOURCES = ["smcb_filter.cu", "smcb_batch.cu", "smcb_sampler.cu", "smcb_capi.cu"]
+HEADERS = ["smcb_common.cuh", "smcb_detmath.cuh", "smcb_models.cuh", "smcb_filter.cuh", "smcb_batch.cuh", "smcb_sampler.cuh", "smcb_nccl.cuh",
            os.path.join("..", "..", "include", "smcb200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-fmad=false", "-std=c++17",
@@ -54,7 +54,7 @@ def build_library(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode != 0:
             raise RuntimeError("nvcc failed: " + " ".join(cmd))
-    link = [_nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"]
+    link = [_nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC", "-ldl"]
     subprocess.check_call(link)
     return LIB_PATH
 

@@ -766,7 +766,7 @@ void BatchFilter::upload_proposal(const double* proposal, int64_t rows) {
   ++launches_;
 }
 
-void BatchFilter::launch(bool from_init, uint32_t t_begin, uint32_t t_end, int resampler, int64_t, bool guided) {
+void BatchFilter::launch(const IO& io, bool from_init, uint32_t t_begin, uint32_t t_end, int resampler, bool guided) {
   const int64_t npairs = (N_ + 1) / 2;
   int pairs = 2;
   if ((npairs + pairs - 1) / pairs > 1024) pairs = 4;
@@ -795,15 +795,15 @@ void BatchFilter::launch(bool from_init, uint32_t t_begin, uint32_t t_end, int r
   const size_t smem = cdf_bytes + (x_in_smem ? x_bytes : 0);
   if (smem > kSmemBudget) throw Error{SMCB_ERR_UNSUPPORTED, "CDF does not fit in shared memory"};
   BatchArgs a;
-  a.derived = derived_;
-  a.active = use_active_ ? active_ : nullptr;
-  a.y = y_dev_;
+  a.derived = io.derived;
+  a.active = io.active;
+  a.y = io.y;
   a.prop = guided ? prop_dev_ : nullptr;
   a.x = x_[cur_];
   a.logw = logw_[cur_];
   a.stats = stats_[cur_];
-  a.logz_out = out_dev_;
-  a.ess_out = out_dev_ + M_;
+  a.logz_out = io.logz_out;
+  a.ess_out = io.ess_out ? io.ess_out : out_dev_ + M_;
   a.N = N_; a.ld = ld_; a.S = S_; a.R = R_;
   a.key = key_; a.stream0 = stream0_;
   a.t_begin = t_begin; a.t_end = t_end;
@@ -843,7 +843,7 @@ void BatchFilter::init(const double* params, const uint8_t* active, double y0, c
   ensure_y(y_dev_, y_cap_, 1);
   SMCB_CUDA_TRY(cudaMemcpyAsync(y_dev_, &y0, sizeof(double), cudaMemcpyHostToDevice, stream_));
   key_ = key; stream0_ = stream0; t_ = 0;
-  launch(true, 0, 0, RESAMPLE_SYSTEMATIC, 1);
+  launch(own_io(), true, 0, 0, RESAMPLE_SYSTEMATIC);
   if (logmu) SMCB_CUDA_TRY(cudaMemcpyAsync(logmu, out_dev_, sizeof(double) * M_, cudaMemcpyDeviceToHost, stream_));
   if (ess) SMCB_CUDA_TRY(cudaMemcpyAsync(ess, out_dev_ + M_, sizeof(double) * M_, cudaMemcpyDeviceToHost, stream_));
   end_call();
@@ -858,7 +858,7 @@ void BatchFilter::step(const double* params, double y, int resampler, double* lo
   ensure_y(y_dev_, y_cap_, 1);
   SMCB_CUDA_TRY(cudaMemcpyAsync(y_dev_, &y, sizeof(double), cudaMemcpyHostToDevice, stream_));
   if (proposal) upload_proposal(proposal, 1);
-  launch(false, t_ + 1, t_ + 1, resampler, 1, proposal != nullptr);
+  launch(own_io(), false, t_ + 1, t_ + 1, resampler, proposal != nullptr);
   t_ += 1;
   if (logmu) SMCB_CUDA_TRY(cudaMemcpyAsync(logmu, out_dev_, sizeof(double) * M_, cudaMemcpyDeviceToHost, stream_));
   if (ess) SMCB_CUDA_TRY(cudaMemcpyAsync(ess, out_dev_ + M_, sizeof(double) * M_, cudaMemcpyDeviceToHost, stream_));
@@ -874,7 +874,7 @@ void BatchFilter::run(const double* params, const uint8_t* active, const double*
   SMCB_CUDA_TRY(cudaMemcpyAsync(y_dev_, y, sizeof(double) * T, cudaMemcpyHostToDevice, stream_));
   key_ = key; stream0_ = stream0;
   if (proposal) upload_proposal(proposal, T);  // row 0 (the initial draw is the bootstrap one) is not read
-  launch(true, 0, (uint32_t)(T - 1), resampler, T, proposal != nullptr);
+  launch(own_io(), true, 0, (uint32_t)(T - 1), resampler, proposal != nullptr);
   t_ = (uint32_t)(T - 1);
   SMCB_CUDA_TRY(cudaMemcpyAsync(logZ, out_dev_, sizeof(double) * M_, cudaMemcpyDeviceToHost, stream_));
   end_call();
@@ -997,6 +997,72 @@ void BatchFilter::weighted_quantiles(const double* probs, int np, bool weighted,
     throw;
   }
   cudaFree(scratch);
+}
+
+// ---- device-resident variants: enqueue only (no host copies, no synchronisation) --------------------------------
+void BatchFilter::init_dev(const double* derived_dev, const uint8_t* active_dev, const double* y0_dev, const RngKey& key,
+                           uint32_t stream0, double* logmu_dev, double* ess_dev) {
+  SMCB_CUDA_TRY(cudaSetDevice(device_));
+  key_ = key; stream0_ = stream0; t_ = 0;
+  launch(IO{derived_dev, active_dev, y0_dev, logmu_dev, ess_dev}, true, 0, 0, RESAMPLE_SYSTEMATIC);
+  live_ = true;
+}
+
+void BatchFilter::step_dev(const double* derived_dev, const double* y_dev, uint32_t t, int resampler, double* logmu_dev,
+                           double* ess_dev) {
+  if (!live_) throw Error{SMCB_ERR_STATE, "batch step before init / log_likelihood"};
+  if (resampler < 0 || resampler > 2) throw Error{SMCB_ERR_BAD_ARG, "unknown resampler"};
+  SMCB_CUDA_TRY(cudaSetDevice(device_));
+  launch(IO{derived_dev, nullptr, y_dev, logmu_dev, ess_dev}, false, t, t, resampler);
+  t_ = t;
+}
+
+void BatchFilter::run_dev(const double* derived_dev, const uint8_t* active_dev, const double* y_dev, int64_t T, int resampler,
+                          const RngKey& key, uint32_t stream0, double* logz_dev) {
+  if (resampler < 0 || resampler > 2) throw Error{SMCB_ERR_BAD_ARG, "unknown resampler"};
+  SMCB_CUDA_TRY(cudaSetDevice(device_));
+  key_ = key; stream0_ = stream0;
+  launch(IO{derived_dev, active_dev, y_dev, logz_dev, nullptr}, true, 0, (uint32_t)(T - 1), resampler);
+  t_ = (uint32_t)(T - 1);
+  live_ = true;
+}
+
+void BatchFilter::gather_dev(const int32_t* parents_dev) {
+  if (!live_) throw Error{SMCB_ERR_STATE, "batch_gather before any filtering"};
+  SMCB_CUDA_TRY(cudaSetDevice(device_));
+  const int64_t xrow = d_ * ld_, wrow = ld_;
+  dim3 grid((unsigned)M_, (unsigned)std::max<int64_t>(1, std::min<int64_t>(8, xrow / 2 / 256)));
+  copy_clouds_kernel<<<grid, 256, 0, stream_>>>(x_[cur_ ^ 1], x_[cur_], logw_[cur_ ^ 1], logw_[cur_], stats_[cur_ ^ 1],
+                                                stats_[cur_], nullptr, parents_dev, nullptr, xrow, wrow);
+  SMCB_CUDA_TRY(cudaGetLastError());
+  ++launches_;
+  cur_ ^= 1;
+}
+
+void BatchFilter::accept_dev(const BatchFilter& prop, const uint8_t* mask_dev) {
+  if (prop.M_ != M_ || prop.N_ != N_ || prop.kind_ != kind_ || prop.device_ != device_)
+    throw Error{SMCB_ERR_BAD_ARG, "batch_accept: batches differ in shape, model or device"};
+  if (!prop.live_) throw Error{SMCB_ERR_STATE, "batch_accept: proposal batch holds no clouds"};
+  SMCB_CUDA_TRY(cudaSetDevice(device_));
+  const int64_t xrow = d_ * ld_, wrow = ld_;
+  dim3 grid((unsigned)M_, (unsigned)std::max<int64_t>(1, std::min<int64_t>(8, xrow / 2 / 256)));
+  copy_clouds_kernel<<<grid, 256, 0, stream_>>>(x_[cur_], prop.x_[prop.cur_], logw_[cur_], prop.logw_[prop.cur_], stats_[cur_],
+                                                prop.stats_[prop.cur_], nullptr, nullptr, mask_dev, xrow, wrow);
+  SMCB_CUDA_TRY(cudaGetLastError());
+  ++launches_;
+  if (!live_) { t_ = prop.t_; key_ = prop.key_; stream0_ = prop.stream0_; live_ = true; }
+}
+
+void BatchFilter::pack_dev(const int32_t* slots_dev, int64_t n, void* buf_dev, bool to_buffer) {
+  if (n == 0) return;
+  SMCB_CUDA_TRY(cudaSetDevice(device_));
+  const int64_t xrow = d_ * ld_, wrow = ld_;
+  dim3 grid((unsigned)n, (unsigned)std::max<int64_t>(1, std::min<int64_t>(8, xrow / 256)));
+  pack_clouds_kernel<<<grid, 256, 0, stream_>>>(x_[cur_], logw_[cur_], stats_[cur_], slots_dev, static_cast<double*>(buf_dev),
+                                                xrow, wrow, to_buffer ? 1 : 0);
+  SMCB_CUDA_TRY(cudaGetLastError());
+  ++launches_;
+  if (!to_buffer) live_ = true;
 }
 
 int64_t BatchFilter::cloud_bytes() const { return (int64_t)sizeof(double) * ((d_ + 1) * ld_ + 4); }

@@ -42,6 +42,22 @@ class BatchFilter {
   int64_t cloud_bytes() const;
   void pack(const int32_t* slots, int64_t n, void* buf_dev, bool to_buffer);
 
+  // ---- device-resident variants (the θ-level engine, smcb_sampler.cu): every pointer is a DEVICE pointer, nothing is
+  // copied from or to the host and nothing synchronises — the calls only enqueue work on the stream.
+  // derived_dev: [M][8] DERIVED parameter blocks (derive_params); active_dev: [M] or null; y_dev: the observations this
+  // call consumes; logz_dev / logmu_dev / ess_dev: [M] outputs (ess_dev may be null).
+  void init_dev(const double* derived_dev, const uint8_t* active_dev, const double* y0_dev, const RngKey& key, uint32_t stream0,
+                double* logmu_dev, double* ess_dev);
+  void step_dev(const double* derived_dev, const double* y_dev, uint32_t t, int resampler, double* logmu_dev, double* ess_dev);
+  void run_dev(const double* derived_dev, const uint8_t* active_dev, const double* y_dev, int64_t T, int resampler,
+               const RngKey& key, uint32_t stream0, double* logz_dev);
+  void gather_dev(const int32_t* parents_dev);                              // slot m <- slot parents_dev[m]
+  void accept_dev(const BatchFilter& prop, const uint8_t* mask_dev);        // slots with mask_dev[m] != 0 <- prop's slot m
+  void pack_dev(const int32_t* slots_dev, int64_t n, void* buf_dev, bool to_buffer);
+  int kind() const { return kind_; }
+  int state_dim_() const { return d_; }
+  int64_t ld() const { return ld_; }
+
   double last_ms() const { return last_ms_; }
   int64_t launches() const { return launches_; }
   int64_t M() const { return M_; }
@@ -49,7 +65,15 @@ class BatchFilter {
 
  private:
   void upload_params(const double* params, const uint8_t* active);
-  void launch(bool from_init, uint32_t t_begin, uint32_t t_end, int resampler, int64_t y_count, bool guided = false);
+  struct IO {  // device pointers one launch reads its inputs from and writes its per-θ results to
+    const double* derived;
+    const uint8_t* active;
+    const double* y;
+    double* logz_out;
+    double* ess_out;
+  };
+  IO own_io() const { return IO{derived_, use_active_ ? active_ : nullptr, y_dev_, out_dev_, out_dev_ + M_}; }
+  void launch(const IO& io, bool from_init, uint32_t t_begin, uint32_t t_end, int resampler, bool guided = false);
   void upload_proposal(const double* proposal, int64_t rows);
   void begin_call();
   void end_call();

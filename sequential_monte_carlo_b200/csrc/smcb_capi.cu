@@ -10,6 +10,7 @@
 #include "../../include/smcb200.h"
 #include "smcb_batch.cuh"
 #include "smcb_filter.cuh"
+#include "smcb_sampler.cuh"
 
 using namespace smcb;
 
@@ -22,12 +23,23 @@ struct smcb_ctx {
   std::unique_ptr<SingleFilter> filter;
   std::unique_ptr<SingleFilter> scratch;  // normalize / resample utilities
   std::vector<StepStats> stats;
+  Comm comm;                              // θ-sharding across GPUs (smcb_comm_init); nranks == 1 without it
+  double* comm_buf = nullptr;             // device staging of smcb_comm_all_gather
+  int64_t comm_buf_cap = 0;
   RngKey key(uint32_t epoch) const { return make_rng_key((uint32_t)seed, (uint32_t)(seed >> 32), epoch & 0xFFFFFFu); }
 };
 
 struct smcb_batch {
   smcb_ctx* ctx = nullptr;
-  std::unique_ptr<BatchFilter> impl;
+  BatchFilter* impl = nullptr;
+  bool owned = true;   // false: a view of a sampler's live clouds (smcb_sampler_clouds)
+  ~smcb_batch() { if (owned) delete impl; }
+};
+
+struct smcb_sampler {
+  smcb_ctx* ctx = nullptr;
+  std::unique_ptr<ThetaSampler> impl;
+  smcb_batch view;     // borrowed handle of impl->clouds()
 };
 
 namespace {
@@ -93,6 +105,7 @@ int smcb_create(int device, uint64_t seed, smcb_ctx** out) {
 int smcb_destroy(smcb_ctx* ctx) {
   if (!ctx) return SMCB_OK;
   cudaSetDevice(ctx->device);
+  smcb_comm_destroy(ctx);
   ctx->filter.reset();
   ctx->scratch.reset();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -301,13 +314,13 @@ int smcb_batch_create(smcb_ctx* ctx, int kind, int64_t M, int64_t N, smcb_batch*
   return guarded(ctx, [&] {
     std::unique_ptr<smcb_batch> b(new smcb_batch);
     b->ctx = ctx;
-    b->impl.reset(new BatchFilter(ctx->device, ctx->stream, kind, M, N));
+    b->impl = new BatchFilter(ctx->device, ctx->stream, kind, M, N);
     *out = b.release();
   });
 }
 
 int smcb_batch_destroy(smcb_batch* b) {
-  if (!b) return SMCB_OK;
+  if (!b || !b->owned) return SMCB_OK;  // a sampler's view dies with the sampler
   cudaSetDevice(b->ctx->device);
   delete b;
   return SMCB_OK;
@@ -419,6 +432,188 @@ int smcb_batch_get_timing(const smcb_batch* b, double* ms_last_call, int64_t* la
   if (ms_last_call) *ms_last_call = b->impl->last_ms();
   if (launches_total) *launches_total = b->impl->launches();
   return SMCB_OK;
+}
+
+// ------------------------------------------------------------------ multi-GPU (one process per GPU)
+int smcb_comm_unique_id(uint8_t id[128]) {
+  if (!id) return SMCB_ERR_BAD_ARG;
+  return guarded(nullptr, [&] {
+    NcclUniqueId u;
+    SMCB_NCCL_TRY(nccl_api().GetUniqueId(&u));
+    std::memcpy(id, u.internal, 128);
+  });
+}
+
+int smcb_comm_init(smcb_ctx* ctx, int rank, int nranks, const uint8_t id[128]) {
+  if (!ctx) return SMCB_ERR_BAD_ARG;
+  return guarded(ctx, [&] {
+    need(nranks >= 1 && rank >= 0 && rank < nranks, "comm_init: rank must be in [0, nranks)");
+    if (ctx->comm.comm) throw Error{SMCB_ERR_STATE, "comm_init: the context already has a communicator"};
+    if (nranks == 1) { ctx->comm.rank = 0; ctx->comm.nranks = 1; return; }
+    need(id != nullptr, "comm_init: id is null");
+    SMCB_CUDA_TRY(cudaSetDevice(ctx->device));
+    NcclUniqueId u;
+    std::memcpy(u.internal, id, 128);
+    NcclComm c = nullptr;
+    SMCB_NCCL_TRY(nccl_api().CommInitRank(&c, nranks, u, rank));
+    ctx->comm.comm = c;
+    ctx->comm.rank = rank;
+    ctx->comm.nranks = nranks;
+    // build the rings / channels now, outside anybody's timed region
+    double* tmp = nullptr;
+    SMCB_CUDA_TRY(cudaMalloc(&tmp, sizeof(double) * nranks));
+    cudaError_t e = cudaMemsetAsync(tmp, 0, sizeof(double) * nranks, ctx->stream);
+    int r = nccl_api().AllGather(tmp + rank, tmp, 1, kNcclFloat64, c, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(tmp);
+    SMCB_CUDA_TRY(e);
+    SMCB_NCCL_TRY(r);
+  });
+}
+
+int smcb_comm_rank(const smcb_ctx* ctx, int* rank, int* nranks) {
+  if (!ctx) return SMCB_ERR_BAD_ARG;
+  if (rank) *rank = ctx->comm.rank;
+  if (nranks) *nranks = ctx->comm.nranks;
+  return SMCB_OK;
+}
+
+int smcb_comm_all_gather(smcb_ctx* ctx, const double* local, int64_t n_local, double* all) {
+  if (!ctx) return SMCB_ERR_BAD_ARG;
+  return guarded(ctx, [&] {
+    need(local && all && n_local >= 1, "comm_all_gather: bad arguments");
+    const int G = ctx->comm.nranks;
+    if (G == 1) { std::memcpy(all, local, sizeof(double) * n_local); return; }
+    SMCB_CUDA_TRY(cudaSetDevice(ctx->device));
+    if (ctx->comm_buf_cap < n_local * G) {
+      cudaFree(ctx->comm_buf);
+      ctx->comm_buf = nullptr;
+      ctx->comm_buf_cap = 0;
+      SMCB_CUDA_TRY(cudaMalloc(&ctx->comm_buf, sizeof(double) * n_local * G));
+      ctx->comm_buf_cap = n_local * G;
+    }
+    double* mine = ctx->comm_buf + (int64_t)ctx->comm.rank * n_local;
+    SMCB_CUDA_TRY(cudaMemcpyAsync(mine, local, sizeof(double) * n_local, cudaMemcpyHostToDevice, ctx->stream));
+    SMCB_NCCL_TRY(nccl_api().AllGather(mine, ctx->comm_buf, (size_t)n_local, kNcclFloat64, ctx->comm.comm, ctx->stream));
+    SMCB_CUDA_TRY(cudaMemcpyAsync(all, ctx->comm_buf, sizeof(double) * n_local * G, cudaMemcpyDeviceToHost, ctx->stream));
+    SMCB_CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+  });
+}
+
+int smcb_comm_destroy(smcb_ctx* ctx) {
+  if (!ctx) return SMCB_ERR_BAD_ARG;
+  if (ctx->comm.comm) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    nccl_api().CommDestroy(ctx->comm.comm);
+  }
+  cudaFree(ctx->comm_buf);
+  ctx->comm_buf = nullptr;
+  ctx->comm_buf_cap = 0;
+  ctx->comm = Comm{};
+  return SMCB_OK;
+}
+
+int smcb_exchange_plan(const int32_t* parents, int64_t M, int rank, int nranks, int32_t* local_parents, int32_t* send_peer,
+                       int32_t* send_slot, int64_t* n_send, int32_t* recv_peer, int32_t* recv_slot, int64_t* n_recv) {
+  if (!parents || M < 1 || nranks < 1 || rank < 0 || rank >= nranks || M % nranks || !local_parents || !n_send || !n_recv)
+    return SMCB_ERR_BAD_ARG;
+  for (int64_t m = 0; m < M; ++m)
+    if (parents[m] < 0 || parents[m] >= M) return SMCB_ERR_BAD_ARG;
+  return guarded(nullptr, [&] {
+    ExchangePlan plan;
+    make_exchange_plan(parents, M, rank, nranks, plan);
+    std::memcpy(local_parents, plan.local_parents.data(), sizeof(int32_t) * plan.local_parents.size());
+    *n_send = (int64_t)plan.send_slot.size();
+    *n_recv = (int64_t)plan.recv_slot.size();
+    for (size_t i = 0; i < plan.send_slot.size(); ++i) {
+      if (send_peer) send_peer[i] = plan.send_peer[i];
+      if (send_slot) send_slot[i] = plan.send_slot[i];
+    }
+    for (size_t i = 0; i < plan.recv_slot.size(); ++i) {
+      if (recv_peer) recv_peer[i] = plan.recv_peer[i];
+      if (recv_slot) recv_slot[i] = plan.recv_slot[i];
+    }
+  });
+}
+
+int smcb_random_walk_sigma(const double* theta, int64_t M, int d, double* sigma) {
+  if (!theta || !sigma || M < 2 || d < 1 || d > kMaxThetaDim) return SMCB_ERR_BAD_ARG;
+  random_walk_sigma(theta, M, d, sigma);
+  return SMCB_OK;
+}
+
+int smcb_cholesky_lower(const double* A, int d, double scale, double* L) {
+  if (!A || !L || d < 1 || d > kMaxThetaDim) return SMCB_ERR_BAD_ARG;
+  return cholesky_lower(A, d, scale, L) ? SMCB_OK : SMCB_ERR_STATE;
+}
+
+// ------------------------------------------------------------------ device-resident θ-level samplers
+int smcb_sampler_create(smcb_ctx* ctx, const smcb_sampler_config* cfg, const double* theta0, smcb_sampler** out) {
+  if (!ctx || !out) return SMCB_ERR_BAD_ARG;
+  *out = nullptr;
+  return guarded(ctx, [&] {
+    need(cfg && theta0, "sampler_create: cfg, theta0 must be non-null");
+    std::unique_ptr<smcb_sampler> s(new smcb_sampler);
+    s->ctx = ctx;
+    s->impl.reset(new ThetaSampler(ctx->device, ctx->stream, ctx->comm, *cfg, theta0));
+    s->view.ctx = ctx;
+    s->view.owned = false;
+    *out = s.release();
+  });
+}
+
+int smcb_sampler_destroy(smcb_sampler* s) {
+  if (!s) return SMCB_OK;
+  cudaSetDevice(s->ctx->device);
+  delete s;
+  return SMCB_OK;
+}
+
+int smcb_sampler_set_data(smcb_sampler* s, const double* y, int64_t T) {
+  if (!s) return SMCB_ERR_BAD_ARG;
+  return guarded(s->ctx, [&] { s->impl->set_data(y, T); });
+}
+
+int smcb_sampler_smc2_init(smcb_sampler* s) {
+  if (!s) return SMCB_ERR_BAD_ARG;
+  return guarded(s->ctx, [&] { s->impl->smc2_init(); });
+}
+
+int smcb_sampler_smc2_step(smcb_sampler* s, int64_t t, double* ess, int* rejuvenated) {
+  if (!s) return SMCB_ERR_BAD_ARG;
+  return guarded(s->ctx, [&] { s->impl->smc2_step(t, ess, rejuvenated); });
+}
+
+int smcb_sampler_density_tempered(smcb_sampler* s, double* schedule, int cap, int* n_stages) {
+  if (!s) return SMCB_ERR_BAD_ARG;
+  return guarded(s->ctx, [&] {
+    const int n = s->impl->density_tempered(schedule, cap);
+    if (n_stages) *n_stages = n;
+  });
+}
+
+int smcb_sampler_get(smcb_sampler* s, double* theta, double* omega, double* logZ, double* ess, double* acc_ratio, int64_t* N) {
+  if (!s) return SMCB_ERR_BAD_ARG;
+  return guarded(s->ctx, [&] { s->impl->get(theta, omega, logZ, ess, acc_ratio, N); });
+}
+
+int smcb_sampler_clouds(smcb_sampler* s, smcb_batch** clouds) {
+  if (!s || !clouds) return SMCB_ERR_BAD_ARG;
+  s->view.impl = s->impl->clouds();
+  *clouds = &s->view;
+  return SMCB_OK;
+}
+
+int smcb_sampler_set_profiling(smcb_sampler* s, int enable) {
+  if (!s) return SMCB_ERR_BAD_ARG;
+  s->impl->set_profiling(enable != 0);
+  return SMCB_OK;
+}
+
+int smcb_sampler_stats(smcb_sampler* s, double ms[8], int64_t counts[8]) {
+  if (!s || !ms || !counts) return SMCB_ERR_BAD_ARG;
+  return guarded(s->ctx, [&] { s->impl->stats(ms, counts); });
 }
 
 // ------------------------------------------------------------------ Kalman

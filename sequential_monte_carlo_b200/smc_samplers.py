@@ -83,6 +83,86 @@ class TorchComm:
         return recv
 
 
+class NcclComm:
+    """θ-sharding over the library's own NCCL communicator (smcb_comm_init, include/smcb200.h): one process per GPU,
+    rank r owns θ-particles [r·M/G, (r+1)·M/G).  The host language only carries the 128-byte NCCL id from rank 0 to the
+    other ranks — here through torch.distributed (any backend), in Julia through MPI or a file; every M-length vector
+    then stays on the GPUs (all-gathers and cloud moves are issued by the library on its own stream)."""
+
+    def __init__(self, ctx, rank, world, unique_id):
+        self.ctx, self.rank, self.world = ctx, int(rank), int(world)
+        if ctx.comm_rank()[1] == 1 and self.world > 1:
+            ctx.comm_init(self.rank, self.world, unique_id)
+
+    @classmethod
+    def from_torch(cls, ctx):
+        import torch.distributed as dist
+        rank, world = dist.get_rank(), dist.get_world_size()
+        if ctx.comm_rank()[1] > 1 or world == 1:
+            return cls(ctx, rank, world, None)
+        box = [_lib.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        return cls(ctx, rank, world, box[0])
+
+    def all_gather(self, local):
+        return self.ctx.comm_all_gather(local)
+
+
+_PRIOR_FAMILIES = None
+
+
+def prior_descriptor(prior):
+    """[d, 8] rows (family, p0, p1, lo, hi, c0, c1, 0) of a product of univariate priors for smcb_sampler_config, or None when
+    a component is not one of the device families (Normal, LogNormal, Uniform, TruncatedNormal)"""
+    from . import priors as pr
+    comps = getattr(prior, "components", None)
+    if comps is None:
+        comps = [prior] if isinstance(prior, pr.Distribution) else None
+    if not comps or len(comps) > _lib.MAX_THETA_DIM:
+        return None
+    rows = np.zeros((len(comps), 8))
+    for k, c in enumerate(comps):
+        if type(c) is pr.Normal:
+            rows[k, :6] = (_lib.PRIOR_NORMAL, c.μ, c.σ, 0.0, 0.0, math.log(c.σ))
+        elif type(c) is pr.LogNormal:
+            rows[k, :6] = (_lib.PRIOR_LOGNORMAL, c.μ, c.σ, 0.0, 0.0, math.log(c.σ))
+        elif type(c) is pr.Uniform:
+            rows[k, :6] = (_lib.PRIOR_UNIFORM, 0.0, 0.0, c.a, c.b, -math.log(c.b - c.a))
+        elif type(c) is pr.TruncatedNormal:
+            rows[k, :7] = (_lib.PRIOR_TRUNCNORMAL, c.μ, c.σ, c.lo, c.hi, math.log(c.σ), c._logmass)
+        else:
+            return None
+    return rows
+
+
+def parameter_map(model, prior, d):
+    """(kind, src [8], const [8]) when model(θ) only SELECTS components of θ and constants into the model's parameter block
+    (every model closure of the reference's README and example: lg_mod, uc_mod, ucsv_mod), found by probing the closure on
+    prior draws; None for anything else (the host-language sampler then runs the control flow)."""
+    try:
+        θ = np.asarray(prior.sample(6, 0xC0FFEE), np.float64).reshape(6, d)
+        P, m0 = params_of(model, θ)
+    except Exception:
+        return None
+    src, cst = np.full(8, -1, np.int32), np.zeros(8)
+    for k in range(8):
+        col = P[:, k]
+        if np.all(col == col[0]):
+            hits = [j for j in range(d) if np.all(θ[:, j] == col)]
+            if hits:
+                src[k] = hits[0]
+            else:
+                cst[k] = col[0]
+            continue
+        hits = [j for j in range(d) if np.array_equal(θ[:, j], col)]
+        if not hits:
+            return None
+        src[k] = hits[0]
+    if not hasattr(m0, "kind") or m0.kind not in (_lib.LG1D, _lib.SV, _lib.UCSV):
+        return None
+    return int(m0.kind), src, cst
+
+
 def exchange_plan(parents, rank, world):
     """Who sends which cloud where after a θ-resample (replicated, deterministic).
     Returns (local_parents[Mloc] int32, send {dst: [src local slots]}, recv {src: [dst local slots]})."""
@@ -110,25 +190,25 @@ def random_walk_kernel(θ):
     """smc_samplers.jl:87-101.  θ: [M, d].  Returns Σ (d×d) such that proposals are
     MvNormal(x, scale·Σ); for d = 1 the reference uses σ = 2.83²·var + 1e-10 as a standard
     deviation (Normal(x, scale·σ)) — kept, and encoded as Σ = σ² with scale applied to σ."""
-    θ = np.asarray(θ, np.float64)
-    M, d = θ.shape
-    c = θ - θ.mean(axis=0)
-    cov = (c.T @ c) / (M - 1)
-    if d == 1:
-        dθ = 2.83 ** 2
-        σ = 1.0e-2 if abs(cov[0, 0]) < 1.0e-8 else dθ * cov[0, 0] + 1.0e-10
-        return np.array([[σ]]), True
-    dθ = 2.83 ** 2 / d
-    if math.sqrt(float(np.sum(cov * cov))) < 1.0e-8:
-        return 1.0e-2 * np.eye(d), False
-    return dθ * cov + 1.0e-10 * np.eye(d), False
+    θ = np.ascontiguousarray(θ, np.float64)
+    # the sums run in slot order and the 2.83²/d scaling, the 1e-10 jitter and the small-covariance branch are applied
+    # by the library's host routine (docs/SPEC.md §11), the one the device-resident sampler uses: both propose the same θ'
+    return _lib.random_walk_sigma(θ), θ.shape[1] == 1
 
 
 def _propose(θ, Σ, univariate, scale, z):
+    """rand(MvNormal(θ_m, scale·Σ)) for every m: θ'_j = θ_j + Σ_{k<=j} z_k L[j][k] with L the plain lower Cholesky factor
+    of scale·Σ and k ascending (docs/SPEC.md §11; LAPACK / BLAS operation orders are not reproducible on a device)"""
     if univariate:
         return θ + (scale * Σ[0, 0]) * z
-    L = np.linalg.cholesky(scale * Σ)
-    return θ + z @ L.T
+    L = _lib.cholesky_lower(Σ, scale)
+    out = np.empty_like(θ)
+    for j in range(θ.shape[1]):
+        acc = z[:, 0] * L[j, 0]
+        for k in range(1, j + 1):
+            acc = acc + z[:, k] * L[j, k]
+        out[:, j] = θ[:, j] + acc
+    return out
 
 
 def lg_optimal_proposals(P, y):
@@ -150,7 +230,11 @@ class SMC:
     """
 
     def __init__(self, N, M, model, prior, chain, ess_threshold, min_ar=-1.0, *, seed=1998, resampler="multinomial",
-                 theta_resampler="multinomial", ctx=None, comm=None, proposal=None):
+                 theta_resampler="multinomial", ctx=None, comm=None, proposal=None, engine="auto"):
+        """engine: "device" keeps θ, ω, logZ and the whole control flow on the GPU(s) (smcb_sampler_*, csrc/smcb_sampler.cu) —
+        possible when the prior is a product of the device families and model(θ) selects components of θ into the parameter
+        block; "host" runs the control flow below in numpy with one batched launch per loop over θ (any closures, guided
+        inner filters); "auto" picks "device" whenever it is possible."""
         self.N, self.M, self.chain = int(N), int(M), int(chain)
         self.model, self.prior = model, prior
         self.kernel = random_walk_kernel
@@ -169,20 +253,84 @@ class SMC:
         self.Mloc = self.M // self.comm.world
         self.lo = self.comm.rank * self.Mloc
         self.ctx = ctx or default_context()
-        self.θ = prior.sample(self.M, self.seed)                       # θ = map(m -> rand(prior), 1:M)      :38
-        self.ω = np.full(self.M, 1.0 / self.M)                         # :39
-        self.logZ = np.zeros(self.M)                                   # :44
+        self._θ = prior.sample(self.M, self.seed)                      # θ = map(m -> rand(prior), 1:M)      :38
+        self._ω = np.full(self.M, 1.0 / self.M)                        # :39
+        self._logZ = np.zeros(self.M)                                  # :44
         self.ess = 1.0 * self.M                                        # :45
         self.ess_min = self.M * float(ess_threshold)                   # :46
-        self._P, m0 = params_of(model, self.θ)      # [M, 8] parameter blocks, kept in step with θ
+        self._P, m0 = params_of(model, self._θ)     # [M, 8] parameter blocks, kept in step with θ
         self.kind, self.d = m0.kind, m0.state_dim
-        self._cur = self.ctx.batch(self.kind, self.Mloc, self.N)
+        self._eng, self._stale, self._y_dev = None, False, None
+        if engine not in ("auto", "device", "host"):
+            raise ValueError("engine must be 'auto', 'device' or 'host'")
+        if engine != "host":
+            why = self._try_device_engine(ess_threshold)
+            if why and engine == "device":
+                raise ValueError("engine='device' is not possible here: " + why)
+        self.engine = "device" if self._eng is not None else "host"
+        self._cur = self.ctx.batch(self.kind, self.Mloc, self.N) if self._eng is None else None
         self._prop = None
         self._epoch = 1          # ordinal of the next batched sweep (device Philox epoch)
         self._n_resample = 0     # ordinal of the next θ-resample
         self._n_rejuv = 0        # ordinal of the next rejuvenation (host Philox epoch)
         self._params_dirty = True  # device copy of the parameter blocks is stale
         self.stats = {"sweeps": 0, "particle_updates": 0, "device_ms": 0.0, "clouds_moved": 0}
+
+    # -- the device-resident engine
+    def _try_device_engine(self, ess_threshold):
+        """create the smcb_sampler; returns None on success, else the reason the host path is used"""
+        if not isinstance(self.ctx, _lib.Context):
+            return "the context is not a CUDA context"
+        if self.proposal is not None:
+            return "guided inner filters run on the host-language path"
+        if not (2 <= self.M <= _lib.MAX_THETA_PARTICLES) or self.N > 8192:
+            return "M or N out of the device sampler's range"
+        d = self._θ.shape[1]
+        rows = prior_descriptor(self.prior)
+        if rows is None or rows.shape[0] != d:
+            return "the prior is not a product of Normal / LogNormal / Uniform / TruncatedNormal"
+        pm = parameter_map(self.model, self.prior, d)
+        if pm is None or pm[0] != self.kind:
+            return "model(θ) is not a selection of θ components and constants"
+        if isinstance(self.comm, TorchComm):
+            if self.comm.world > 1 and self.comm.device.type != "cuda":
+                return "the communicator is not on CUDA devices"
+            self.comm = NcclComm.from_torch(self.ctx)
+        elif not isinstance(self.comm, (LocalComm, NcclComm)):
+            return "unknown communicator type"
+        cfg = _lib.SamplerConfig()
+        cfg.kind, cfg.d_theta, cfg.N, cfg.M, cfg.chain = int(self.kind), d, self.N, self.M, self.chain
+        cfg.resampler, cfg.theta_resampler = int(self.resampler), int(self.theta_resampler)
+        cfg.ess_threshold, cfg.min_ar, cfg.seed = float(ess_threshold), float(self.acc_threshold), self.seed & (2 ** 64 - 1)
+        for k in range(d):
+            for j in range(8):
+                cfg.prior[k][j] = float(rows[k, j])
+        for k in range(8):
+            cfg.map_src[k], cfg.map_const[k] = int(pm[1][k]), float(pm[2][k])
+        self._eng = self.ctx.sampler(cfg, self._θ)
+        return None
+
+    def _engine_data(self, y):
+        """the observations the engine's calls refer to live on the device; re-sent only when they change"""
+        y = np.ascontiguousarray(y, np.float64)
+        if self._y_dev is None or self._y_dev.shape != y.shape or not np.array_equal(self._y_dev, y):
+            self._eng.set_data(y)
+            self._y_dev = y.copy()
+
+    def _refresh(self):
+        if self._eng is not None and self._stale:
+            self._θ, self._ω, self._logZ, self.ess, self.acc_ratio, self.N = self._eng.get()
+            self._P = self._params(self._θ)
+            self._stale = False
+
+    # θ, ω, logZ: public fields of the reference's struct (smc_samplers.jl:5-27); with the device engine they are read
+    # back from the GPU when somebody looks at them
+    θ = property(lambda self: (self._refresh(), self._θ)[1], lambda self, v: setattr(self, "_θ", v))
+    ω = property(lambda self: (self._refresh(), self._ω)[1], lambda self, v: setattr(self, "_ω", v))
+    logZ = property(lambda self: (self._refresh(), self._logZ)[1], lambda self, v: setattr(self, "_logZ", v))
+
+    def _clouds(self):
+        return self._cur if self._eng is None else self._eng.clouds()
 
     # -- helpers
     def _params(self, θ):
@@ -220,17 +368,21 @@ class SMC:
 
     @property
     def x(self):
-        return self._cur.fetch(want_x=True, want_w=False)[0]
+        return self._clouds().fetch(want_x=True, want_w=False)[0]
 
     @property
     def w(self):
-        return self._cur.fetch(want_x=False, want_w=True)[1]
+        return self._clouds().fetch(want_x=False, want_w=True)[1]
 
     def close(self):
         for b in (self._cur, self._prop):
             if b is not None:
                 b.close()
         self._cur = self._prop = None
+        if self._eng is not None:
+            self._refresh()
+            self._eng.close()
+            self._eng = None
 
     def __repr__(self):
         return f"ess     = {round(self.ess, 3)}\nmean(θ) = {expected_parameters(self).ravel()}"
@@ -250,14 +402,14 @@ def expected_parameters(smc, reference_style=False):
 def state_means(smc):
     """[M, d]: the weighted state mean `smc.w[m]' * smc.x[m]` of every θ-particle's cloud
     (plotting_utils.jl:120,150), computed on the device(s); the clouds are not read back."""
-    return smc.comm.all_gather(smc._cur.weighted_mean())
+    return smc.comm.all_gather(smc._clouds().weighted_mean())
 
 
 def state_variances(smc):
     """([M, d] means, [M, d] variances): `mean(smc.x[m], weights(smc.w[m]))`, `var(smc.x[m], weights(smc.w[m]))` of every
     θ-particle's cloud (the per-θ counterpart of examples/inflation_example.jl:46; population variance), computed on the
     device(s); the clouds are not read back."""
-    mean, var = smc._cur.weighted_moments()
+    mean, var = smc._clouds().weighted_moments()
     return smc.comm.all_gather(mean), smc.comm.all_gather(var)
 
 
@@ -265,7 +417,7 @@ def state_quantiles(smc, p, weighted=True):
     """[M, d, len(p)]: `quantile(smc.x[m], weights(smc.w[m]), p)` (weighted) or `quantile(smc.x[m], p)` of every
     θ-particle's cloud (examples/inflation_example.jl:44,250), computed on the device(s) by a per-cloud radix
     select (docs/SPEC.md §8); the clouds are not read back."""
-    return smc.comm.all_gather(smc._cur.weighted_quantiles(np.atleast_1d(np.asarray(p, np.float64)), weighted))
+    return smc.comm.all_gather(smc._clouds().weighted_quantiles(np.atleast_1d(np.asarray(p, np.float64)), weighted))
 
 
 def get_quantiles(smc, yt, p=(0.25, 0.5, 0.75), weighted=True, component=0):
@@ -281,7 +433,7 @@ def get_quantiles(smc, yt, p=(0.25, 0.5, 0.75), weighted=True, component=0):
 
 def _observation_mean_sd(smc):
     """mean and sd of observation(model(θ_m), x̄_m) for every m (state_space_models.jl:96-103,244-247)."""
-    xm, P = state_means(smc), smc._P
+    xm, P = state_means(smc), (smc._refresh(), smc._P)[1]
     if smc.kind == _lib.LG1D:
         return P[:, 1] * xm[:, 0], np.sqrt(P[:, 3])                    # Normal(B x, sqrt(R))
     if smc.kind == _lib.SV:
@@ -441,6 +593,16 @@ def exchange_(smc, y, verbose=False):
 def density_tempered(smc, y, verbose=True):
     """density_tempered(smc, y) (smc_samplers.jl:222-281), Duan & Fulop's density-tempered SMC."""
     y = np.ascontiguousarray(y, np.float64)
+    if smc._eng is not None:                                            # the whole loop below, on the device(s)
+        smc._engine_data(y)
+        stages = smc._eng.density_tempered()
+        smc.schedule = [(ξ, ess) for ξ, ess, _ in stages]
+        smc._stale = True
+        smc._refresh()
+        if verbose:                                                     # the trace format of smc_samplers.jl:207-214
+            for ξ, ess, ar in stages:
+                sys.stdout.write("ξ = %1.5f\tess = %4.3f" % (ξ, ess) + ("\t[rejuvenating]\tacc_rate: %1.5f\n" % ar if ar >= 0.0 else "\n"))
+        return smc
     smc._next_epoch()
     z_loc = smc._cur.log_likelihood(smc._local(smc._P), y, smc.resampler, stream0=smc.lo,
                                     proposal=smc._proposals(smc._local(smc._P), y))          # :223-229
@@ -484,6 +646,11 @@ def density_tempered(smc, y, verbose=True):
 def smc2(smc, y):
     """smc²(smc, y) (smc_samplers.jl:288-301): M bootstrap filters at the first observation."""
     y = np.ascontiguousarray(y, np.float64)
+    if smc._eng is not None:
+        smc._engine_data(y)
+        smc._eng.smc2_init()
+        smc._stale = True
+        return smc
     smc._next_epoch()
     lm_loc, _ = smc._cur.init(smc._local(smc._P), y[0], stream0=smc.lo)
     smc._account(smc._cur, 1)
@@ -495,6 +662,19 @@ def smc2(smc, y):
 
 def smc2_step(smc, y, t, verbose=True):
     """smc²!(smc, y, t) (smc_samplers.jl:308-340); t is the 0-based index of the new observation."""
+    if smc._eng is not None:                                            # one call: (resample!, rejuvenate!, exchange!,) M filter steps, reweight
+        smc._engine_data(y)
+        if verbose:
+            sys.stdout.write("t = %4d\tess = %4.3f" % (t, smc.ess))
+        smc.ess, smc.rejuvenated = smc._eng.smc2_step(t)
+        smc._stale = True
+        if smc.rejuvenated:
+            _, _, _, _, smc.acc_ratio, smc.N = smc._eng.get(False, False, False)
+            if verbose:
+                sys.stdout.write("\t[rejuvenating]\tacc_rate: %1.5f" % smc.acc_ratio)
+        if verbose:
+            sys.stdout.write("\n")
+        return smc
     y = np.ascontiguousarray(y, np.float64)
     if verbose:
         sys.stdout.write("t = %4d\tess = %4.3f" % (t, smc.ess))

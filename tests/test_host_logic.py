@@ -427,3 +427,77 @@ def test_particle_filter_refuses_what_it_cannot_run_on_the_device():
     with pytest.raises(TypeError):         # an arbitrary closure returning a distribution cannot run on the device
         _proposal_coefficients(lambda model, y: (0.0, 1.0), m, 0.1)
     np.testing.assert_allclose(_proposal_coefficients(smc.AffineGaussianProposal(1, 2, 3), m, 0.1), [1, 2, 3])
+
+
+def test_exchange_plan_of_the_library_equals_the_python_plan():
+    """smcb_exchange_plan (host-only C ABI entry, used by the device-resident sampler) against exchange_plan above"""
+    from sequential_monte_carlo_b200 import _lib
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        G, Mloc = int(rng.choice([1, 2, 4, 8])), int(rng.integers(1, 9))
+        M = G * Mloc
+        a = np.sort(rng.integers(0, M, M))
+        for r in range(G):
+            lp, send, recv = ss.exchange_plan(a, r, G)
+            lp2, s2, r2 = _lib.exchange_plan(a, r, G)
+            local = a[r * Mloc:(r + 1) * Mloc] // Mloc == r
+            np.testing.assert_array_equal(lp[local], lp2[local])
+            np.testing.assert_array_equal(lp2[~local], np.arange(Mloc)[~local])       # remote parents: the slot itself (overwritten by the unpack)
+            assert [(d, sl) for d in sorted(send) for sl in send[d]] == s2
+            assert [(d, sl) for d in sorted(recv) for sl in recv[d]] == r2
+    # every cloud that crosses ranks is sent exactly once and received exactly once, in matching order
+    a = np.sort(rng.integers(0, 64, 64))
+    sent = {(r, d): [] for r in range(4) for d in range(4)}
+    for r in range(4):
+        _, s2, r2 = _lib.exchange_plan(a, r, 4)
+        for d, sl in s2:
+            sent[(r, d)].append(sl + r * 16)
+    for r in range(4):
+        _, _, r2 = _lib.exchange_plan(a, r, 4)
+        got = {}
+        for src, sl in r2:
+            got.setdefault(src, []).append(sl)
+        for src, slots in got.items():
+            assert [int(a[r * 16 + sl]) for sl in slots] == sent[(src, r)]
+
+
+def test_device_sampler_descriptors():
+    """prior_descriptor / parameter_map: what decides between the device-resident sampler and the host-language control flow"""
+    pg = smc.product_distribution([smc.TruncatedNormal(0, 1, -1, 1), smc.LogNormal(0.5, 2.0), smc.Uniform(-1, 3), smc.Normal(3, 2)])
+    rows = ss.prior_descriptor(pg)
+    assert rows.shape == (4, 8) and list(rows[:, 0]) == [3, 1, 2, 0]
+    assert rows[0, 6] == pg.components[0]._logmass and rows[1, 5] == np.log(2.0) and rows[2, 5] == -np.log(4.0) and rows[3, 1] == 3.0
+
+    class Odd(smc.Normal):
+        pass
+    assert ss.prior_descriptor(smc.product_distribution([Odd(0, 1)])) is None          # unknown family -> host path
+    pl = smc.product_distribution([smc.TruncatedNormal(0, 1, -1, 1), smc.LogNormal(), smc.LogNormal()])
+    kind, src, cst = ss.parameter_map(lambda θ: smc.StateSpaceModel(smc.LinearGaussian(θ[0], 1.0, θ[1], θ[2], 0.0), (1, 1)), pl, 3)
+    assert kind == 0 and list(src[:6]) == [0, -1, 1, 2, -1, -1] and list(cst[:6]) == [0, 1, 0, 0, 0, 1]
+    pu = smc.product_distribution([smc.Uniform(0, 1), smc.Normal(3, 2), smc.Uniform(0, 2), smc.Uniform(0, 2)])
+    kind, src, cst = ss.parameter_map(lambda θ: smc.StateSpaceModel(smc.UCSV(θ[0], θ[1], (θ[2], θ[3])), (3, 1)), pu, 4)
+    assert kind == 2 and list(src[:5]) == [0, 0, 1, 2, 3]
+    # a closure that transforms θ is not a selection: host path
+    assert ss.parameter_map(lambda θ: smc.LinearGaussian(θ[0], 1.0, θ[1] * 2.0, θ[2], 0.0), pl, 3) is None
+
+
+def test_proposal_arithmetic_is_the_frozen_one(oracle):
+    """docs/SPEC.md §11: the library's host routines (used by both product samplers) against the oracle's numpy restatement,
+    bit for bit, and against LAPACK / numpy to rounding"""
+    from oracle import samplers as S
+    from sequential_monte_carlo_b200 import _lib
+    rng = np.random.default_rng(3)
+    for d in (2, 3, 4, 5):
+        th = rng.normal(size=(300, d)) * rng.uniform(0.1, 3.0, d) + rng.normal(size=d)
+        Sg, So = _lib.random_walk_sigma(th), S.o_random_walk_kernel(th)[0]
+        np.testing.assert_array_equal(Sg, So)
+        np.testing.assert_allclose(Sg, (2.83 * 2.83 / d) * np.cov(th.T) + 1e-10 * np.eye(d), rtol=1e-11)
+        for scale in (1.5, 1.0, 0.5):
+            L = _lib.cholesky_lower(Sg, scale)
+            np.testing.assert_array_equal(L, S.o_cholesky(scale * So))
+            np.testing.assert_allclose(L, np.linalg.cholesky(scale * Sg), rtol=1e-12, atol=1e-15)
+            z = rng.normal(size=(300, d))
+            np.testing.assert_array_equal(ss._propose(th, Sg, False, scale, z), S.o_propose(th, S.o_cholesky(scale * So), z))
+            np.testing.assert_allclose(ss._propose(th, Sg, False, scale, z), th + z @ np.linalg.cholesky(scale * Sg).T, rtol=1e-12, atol=1e-14)
+    with pytest.raises(np.linalg.LinAlgError):
+        _lib.cholesky_lower(np.array([[1.0, 2.0], [2.0, 1.0]]))

@@ -42,14 +42,19 @@ def _check_same(g, o_, oracle, clouds=True):
             np.testing.assert_allclose(w[m], wo, rtol=1e-10, atol=0)
 
 
+ENGINES = ["device", "host"]   # the device-resident sampler (smcb_sampler_*) and the host-language control flow
+
+
+@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("resampler", ["multinomial", "systematic"])
-def test_smc2_lg(ctx, oracle, resampler):
+def test_smc2_lg(ctx, oracle, resampler, engine):
     """BASELINE config 3 shape, scaled down: SMC(N, M, lg_mod, lg_prior, 3, 0.5), smc² then smc²! for t = 2..T."""
     from oracle import samplers as S
     N, M, T, chain = 128, 64, 40, 3
     _, y = oracle.simulate(0, LG_TRUE, T, 1998)
     pg, po = lg_priors()
-    g = smc.SMC(N, M, lg_mod, pg, chain, 0.5, seed=11, resampler=resampler, ctx=ctx)
+    g = smc.SMC(N, M, lg_mod, pg, chain, 0.5, seed=11, resampler=resampler, ctx=ctx, engine=engine)
+    assert g.engine == engine
     o_ = S.OSMC(N, M, lg_mod_o, po, chain, 0.5, seed=11, resampler=ss.resampler_id(resampler))
     smc.smc2(g, y)
     S.o_smc2(o_, y)
@@ -93,14 +98,17 @@ def test_smc2_lg(ctx, oracle, resampler):
     g.close()
 
 
-def test_smc2_ucsv(ctx, oracle):
+@pytest.mark.parametrize("engine", ENGINES)
+def test_smc2_ucsv(ctx, oracle, engine):
     """BASELINE config 5 shape, scaled down: the 4-parameter UCSV of examples/inflation_example.jl:229-239."""
     from oracle import samplers as S
     N, M, T, chain = 96, 32, 24, 2
     _, y = oracle.simulate(2, [0.2, 0.2, 3.0, 1.0, 1.0], T, 1998)
     pg = smc.product_distribution([smc.Uniform(0, 1), smc.Normal(3, 2), smc.Uniform(0, 2), smc.Uniform(0, 2)])
     po = S.OProduct([S.OUniform(0, 1), S.ONormal(3, 2), S.OUniform(0, 2), S.OUniform(0, 2)])
-    g = smc.SMC(N, M, lambda θ: smc.StateSpaceModel(smc.UCSV(θ[0], θ[1], (θ[2], θ[3])), (3, 1)), pg, chain, 0.5, seed=3, ctx=ctx)
+    g = smc.SMC(N, M, lambda θ: smc.StateSpaceModel(smc.UCSV(θ[0], θ[1], (θ[2], θ[3])), (3, 1)), pg, chain, 0.5, seed=3, ctx=ctx,
+                engine=engine)
+    assert g.engine == engine
     o_ = S.OSMC(N, M, lambda θ: (2, [θ[0], θ[0], θ[1], θ[2], θ[3]]), po, chain, 0.5, seed=3)
     smc.smc2(g, y)
     S.o_smc2(o_, y)
@@ -112,13 +120,14 @@ def test_smc2_ucsv(ctx, oracle):
     g.close()
 
 
-def test_density_tempered_lg(ctx, oracle, capsys):
+@pytest.mark.parametrize("engine", ENGINES)
+def test_density_tempered_lg(ctx, oracle, capsys, engine):
     """BASELINE config 4 algorithm on the README's LG example, scaled down."""
     from oracle import samplers as S
     N, M, T, chain = 128, 96, 50, 3
     _, y = oracle.simulate(0, LG_TRUE, T, 1998)
     pg, po = lg_priors()
-    g = smc.SMC(N, M, lg_mod, pg, chain, 0.5, seed=5, ctx=ctx)
+    g = smc.SMC(N, M, lg_mod, pg, chain, 0.5, seed=5, ctx=ctx, engine=engine)
     o_ = S.OSMC(N, M, lg_mod_o, po, chain, 0.5, seed=5)
     smc.density_tempered(g, y, verbose=True)
     S.o_density_tempered(o_, y)
@@ -133,14 +142,15 @@ def test_density_tempered_lg(ctx, oracle, capsys):
     g.close()
 
 
-def test_density_tempered_sv(ctx, oracle):
+@pytest.mark.parametrize("engine", ENGINES)
+def test_density_tempered_sv(ctx, oracle, engine):
     """BASELINE config 4 model: stochastic volatility, θ = (μ, ρ, σ)."""
     from oracle import samplers as S
     N, M, T = 128, 48, 60
     _, y = oracle.simulate(1, [-1.0, 0.9, 0.3], T, 1998)
     pg = smc.product_distribution([smc.Normal(0, 2), smc.Uniform(-1, 1), smc.LogNormal(-1, 1)])
     po = S.OProduct([S.ONormal(0, 2), S.OUniform(-1, 1), S.OLogNormal(-1, 1)])
-    g = smc.SMC(N, M, lambda θ: smc.SV(θ[0], θ[1], θ[2]), pg, 2, 0.5, seed=8, resampler="stratified", ctx=ctx)
+    g = smc.SMC(N, M, lambda θ: smc.SV(θ[0], θ[1], θ[2]), pg, 2, 0.5, seed=8, resampler="stratified", ctx=ctx, engine=engine)
     o_ = S.OSMC(N, M, lambda θ: (1, [θ[0], θ[1], θ[2]]), po, 2, 0.5, seed=8, resampler=1)
     smc.density_tempered(g, y, verbose=False)
     S.o_density_tempered(o_, y)
@@ -149,21 +159,160 @@ def test_density_tempered_sv(ctx, oracle):
     g.close()
 
 
-def test_exchange_doubles_state_particles(ctx, oracle):
-    """exchange! (smc_samplers.jl:163-189): with min_ar above any acceptance rate N doubles after a rejuvenation."""
+@pytest.mark.parametrize("engine", ENGINES)
+def test_exchange_doubles_state_particles(ctx, oracle, engine):
+    """exchange! (smc_samplers.jl:163-189): with min_ar above any acceptance rate N doubles after a rejuvenation, every θ is
+    re-filtered with the doubled cloud and ω ∝ exp(new logZ − logZ) — θ, the doubled clouds, ω and logZ against the oracle's
+    restatement (o_exchange) at the doubling step and one step later."""
+    from oracle import samplers as S
     N, M, T = 64, 32, 30
     _, y = oracle.simulate(0, LG_TRUE, T, 1998)
-    pg, _ = lg_priors()
-    g = smc.SMC(N, M, lg_mod, pg, 1, 0.9, 2.0, seed=2, ctx=ctx)
+    pg, po = lg_priors()
+    g = smc.SMC(N, M, lg_mod, pg, 1, 0.9, 2.0, seed=2, ctx=ctx, engine=engine)
+    o_ = S.OSMC(N, M, lg_mod_o, po, 1, 0.9, 2.0, seed=2)
     smc.smc2(g, y)
+    S.o_smc2(o_, y)
     for t in range(1, T):
         smc.smc2_step(g, y, t, verbose=False)
+        S.o_smc2_step(o_, y, t)
+        assert g.rejuvenated == o_.rejuvenated
         if g.rejuvenated:
             break
-    assert g.rejuvenated and g.N == 128 and g.x.shape == (M, 1, 128)
+    assert g.rejuvenated and g.N == 128 == o_.N and g.x.shape == (M, 1, 128)
+    _check_same(g, o_, oracle)
     assert np.isfinite(g.logZ).all() and abs(g.ω.sum() - 1) < 1e-12
     smc.smc2_step(g, y, t + 1, verbose=False)
+    S.o_smc2_step(o_, y, t + 1)
+    _check_same(g, o_, oracle)
     g.close()
+
+
+def test_smc2_config3_shape_against_the_oracle(ctx, oracle):
+    """BASELINE config 3 at its own shape: SMC(1024, 512, lg_mod, lg_prior, 3, 0.5), T = 100 (README.md:88-103), the device
+    sampler against the OpenMP oracle: same rejuvenation times, θ and clouds bit for bit, logZ to 1e-10."""
+    from oracle import samplers as S
+    N, M, T, chain = 1024, 512, 100, 3
+    _, y = oracle.simulate(0, LG_TRUE, T, 1998)
+    pg, po = lg_priors()
+    g = smc.SMC(N, M, lg_mod, pg, chain, 0.5, seed=1998, resampler="systematic", ctx=ctx, engine="device")
+    o_ = S.OSMC(N, M, lg_mod_o, po, chain, 0.5, seed=1998, resampler=2)
+    smc.smc2(g, y)
+    S.o_smc2(o_, y)
+    n = 0
+    for t in range(1, T):
+        smc.smc2_step(g, y, t, verbose=False)
+        S.o_smc2_step(o_, y, t)
+        assert g.rejuvenated == o_.rejuvenated, t
+        n += g.rejuvenated
+    assert n >= 3
+    _check_same(g, o_, oracle)
+    m = smc.expected_parameters(g).ravel()
+    assert abs(m[0] - 0.5) < 0.25 and 0.4 < m[1] < 1.8 and 0.3 < m[2] < 1.6
+    g.close()
+
+
+def test_density_tempered_config4_shape_reduced_T(ctx, oracle):
+    """BASELINE config 4 at its own M × N (1024 θ × 2048 state particles, SV) with T cut to 40 so that the oracle finishes
+    in seconds: schedule, θ and clouds against the oracle."""
+    from oracle import samplers as S
+    N, M, T = 2048, 1024, 40
+    _, y = oracle.simulate(1, [-1.0, 0.9, 0.3], T, 1998)
+    pg = smc.product_distribution([smc.Normal(0, 2), smc.Uniform(-1, 1), smc.LogNormal(-1, 1)])
+    po = S.OProduct([S.ONormal(0, 2), S.OUniform(-1, 1), S.OLogNormal(-1, 1)])
+    g = smc.SMC(N, M, lambda θ: smc.SV(θ[0], θ[1], θ[2]), pg, 3, 0.5, seed=4, resampler="systematic", ctx=ctx, engine="device")
+    o_ = S.OSMC(N, M, lambda θ: (1, [θ[0], θ[1], θ[2]]), po, 3, 0.5, seed=4, resampler=2)
+    smc.density_tempered(g, y, verbose=False)
+    S.o_density_tempered(o_, y)
+    assert len(g.schedule) == len(o_.schedule) >= 2
+    for (xg, eg), (xo, eo) in zip(g.schedule, o_.schedule):
+        assert abs(xg - xo) <= 1e-12 and abs(eg - eo) <= RTOL * eo
+    _check_same(g, o_, oracle, clouds=False)
+    x = g.x
+    for m in range(0, M, 97):
+        np.testing.assert_array_equal(x[m], o_.x[m])
+    g.close()
+
+
+def test_smc2_config5_shape_reduced_T(ctx, oracle):
+    """BASELINE config 5's inner shape (UCSV, 4096 state particles per θ) with M = 256 θ-particles and T = 12: the large
+    clouds take the L2 placement of batch_kernel; θ, logZ and sampled clouds against the oracle."""
+    from oracle import samplers as S
+    N, M, T, chain = 4096, 256, 12, 2
+    _, y = oracle.simulate(2, [0.2, 0.2, 3.0, 1.0, 1.0], T, 1998)
+    pg = smc.product_distribution([smc.Uniform(0, 1), smc.Normal(3, 2), smc.Uniform(0, 2), smc.Uniform(0, 2)])
+    po = S.OProduct([S.OUniform(0, 1), S.ONormal(3, 2), S.OUniform(0, 2), S.OUniform(0, 2)])
+    g = smc.SMC(N, M, lambda θ: smc.StateSpaceModel(smc.UCSV(θ[0], θ[1], (θ[2], θ[3])), (3, 1)), pg, chain, 0.5, seed=3,
+                resampler="systematic", ctx=ctx, engine="device")
+    o_ = S.OSMC(N, M, lambda θ: (2, [θ[0], θ[0], θ[1], θ[2], θ[3]]), po, chain, 0.5, seed=3, resampler=2)
+    smc.smc2(g, y)
+    S.o_smc2(o_, y)
+    n = 0
+    for t in range(1, T):
+        smc.smc2_step(g, y, t, verbose=False)
+        S.o_smc2_step(o_, y, t)
+        assert g.rejuvenated == o_.rejuvenated, t
+        n += g.rejuvenated
+    assert n >= 1
+    _check_same(g, o_, oracle, clouds=False)
+    x = g.x
+    for m in range(0, M, 37):
+        np.testing.assert_array_equal(x[m], o_.x[m])
+    g.close()
+
+
+def test_device_sampler_through_ctypes_only(ctx, oracle):
+    """the new entry points called directly (no Python sampler class in between): smcb_sampler_create / set_data / smc2_init /
+    smc2_step / get / stats / clouds, on a single-rank communicator set up through smcb_comm_init"""
+    import ctypes as C
+    from oracle import samplers as S
+    lib = smc._lib.load()
+    r, n = C.c_int(-1), C.c_int(-1)
+    assert lib.smcb_comm_rank(ctx._h, C.byref(r), C.byref(n)) == 0 and (r.value, n.value) == (0, 1)
+    N, M, T = 64, 32, 30
+    _, y = oracle.simulate(0, LG_TRUE, T, 1998)
+    pg, po = lg_priors()
+    cfg = smc._lib.SamplerConfig()
+    cfg.kind, cfg.d_theta, cfg.N, cfg.M, cfg.chain, cfg.resampler, cfg.theta_resampler = 0, 3, N, M, 2, 0, 0
+    cfg.ess_threshold, cfg.min_ar, cfg.seed = 0.5, -1.0, 21
+    rows = ss.prior_descriptor(pg)
+    for k in range(3):
+        for j in range(8):
+            cfg.prior[k][j] = rows[k, j]
+    for k, (src, cst) in enumerate([(0, 0.0), (-1, 1.0), (1, 0.0), (2, 0.0), (-1, 0.0), (-1, 1.0), (-1, 0.0), (-1, 0.0)]):
+        cfg.map_src[k], cfg.map_const[k] = src, cst
+    θ0 = np.ascontiguousarray(pg.sample(M, 21))
+    h = C.c_void_p()
+    assert lib.smcb_sampler_create(ctx._h, C.byref(cfg), θ0.ctypes.data_as(C.c_void_p), C.byref(h)) == 0, lib.smcb_last_error(ctx._h)
+    assert lib.smcb_sampler_smc2_init(h) == smc._lib.SMCBError(-4, "").code            # no data yet: SMCB_ERR_STATE
+    assert lib.smcb_sampler_set_data(h, y.ctypes.data_as(C.c_void_p), T) == 0
+    assert lib.smcb_sampler_smc2_init(h) == 0
+    o_ = S.OSMC(N, M, lg_mod_o, po, 2, 0.5, seed=21)
+    S.o_smc2(o_, y)
+    ess, rj, nrj = C.c_double(), C.c_int(), 0
+    for t in range(1, T):
+        assert lib.smcb_sampler_smc2_step(h, t, C.byref(ess), C.byref(rj)) == 0, lib.smcb_last_error(ctx._h)
+        S.o_smc2_step(o_, y, t)
+        assert bool(rj.value) == o_.rejuvenated and abs(ess.value - o_.ess) <= RTOL * o_.ess
+        nrj += rj.value
+    assert nrj >= 1
+    assert lib.smcb_sampler_smc2_step(h, T, None, None) == -1                           # t out of range: SMCB_ERR_BAD_ARG
+    θ, ω, z = np.empty((M, 3)), np.empty(M), np.empty(M)
+    ar, Nn = C.c_double(), C.c_int64()
+    assert lib.smcb_sampler_get(h, θ.ctypes.data_as(C.c_void_p), ω.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p), C.byref(ess),
+                                C.byref(ar), C.byref(Nn)) == 0
+    np.testing.assert_array_equal(θ, o_.theta)
+    np.testing.assert_allclose(z, o_.logZ, rtol=1e-10)
+    np.testing.assert_allclose(ω, o_.omega, rtol=RTOL, atol=1e-300)
+    assert ar.value == o_.acc_ratio and Nn.value == N
+    b = C.c_void_p()
+    assert lib.smcb_sampler_clouds(h, C.byref(b)) == 0
+    x = np.empty((M, 1, N))
+    assert lib.smcb_batch_fetch(b, x.ctypes.data_as(C.c_void_p), None, None) == 0
+    np.testing.assert_array_equal(x, o_.x)
+    ms, cnt = (C.c_double * 8)(), (C.c_int64 * 8)()
+    assert lib.smcb_sampler_stats(h, ms, cnt) == 0
+    assert cnt[1] == T - 1 and cnt[2] == nrj and cnt[0] == 2 * nrj and cnt[4] > 0
+    assert lib.smcb_sampler_destroy(h) == 0
 
 
 def test_posterior_is_plausible(ctx, oracle):
