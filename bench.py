@@ -18,10 +18,16 @@ configs[1] at its largest size (N = 2^24, T = 1000) — through the C ABI of lib
   cpu_baseline  the CPU oracle (a port of the Julia reference; Julia is not in this image) timed on
          the host cores on a bounded sample
 
-N > 1 GPUs: a single filter does not shard (global scan + gather every step: "replicas only",
-DESIGN.md §5) — every rank runs its own filter on its own Philox stream (weak scaling).  The
-θ-sharded SMC² numbers (the path that does shard) ride along in the "smc2" object, and the rows built after
-the hot path (guided filter, matrix Kalman, per-θ moments: SURVEY §8f) in the "widen" object.
+N = 1 GPU: the workload above (it fits one GPU; a single filter does not shard: global scan + gather every step,
+"replicas only").  The θ-level configurations (BASELINE configs[2..4]) ride along in the "smc2" object,
+the rows built after the hot path (guided filter, matrix Kalman, per-θ moments: SURVEY §8f) in "widen".
+
+N > 1 GPUs: the path that shards — BASELINE configs[4], smc² on the 4-parameter UCSV model with 4096 θ ×
+4096 state particles, T = 241, θ sharded over the ranks through the library's own NCCL communicator (smcb_comm_init):
+STRONG scaling, one "step" = one whole smc² run, value = particle-updates of the whole job / device time (max over
+ranks), with the breakdown of where the time went, the same workload on ONE GPU of the same box beside it
+("single_gpu_same_workload"), configs[2] and configs[3] sharded the same way ("smc2"), and the replicated
+single-filter headline as an extra ("replicas").
 """
 import argparse
 import json
@@ -138,22 +144,75 @@ def cpu_rejuvenation_sample(N=1024, T=100, seconds=8.0):
             "sample": f"one rejuvenation sweep: {M} theta x {N} particles x T={T}, multinomial, oracle/smc_oracle.c OpenMP over theta"}
 
 
+def cpu_sharded_sample(seconds=10.0):
+    """The CPU arm of the N > 1 workload (configs[4]): the reference spends >95 % of smc² in rejuvenate!'s `Threads.@threads for m`
+    loop of full particle filters (smc_samplers.jl:112-121) — one such sweep of UCSV filters with 4096 particles each over
+    T = 60 observations by the CPU oracle, OpenMP over θ with every host thread, multinomial like the reference."""
+    from oracle import oracle as o
+    o.build()
+    threads = o.num_threads()
+    P = o.params8([0.2, 0.2, 3.0, 1.0, 1.0])
+    N, T = 4096, 60
+    _, y = o.simulate(2, P, T, DATA_SEED)
+    M, t1 = threads, 0.0
+    while True:
+        Pm = np.tile(P[None, :], (M, 1))
+        t0 = time.perf_counter()
+        o.batch_log_likelihood(2, Pm, None, N, y, o.MULTINOMIAL, DATA_SEED, 0, 0, want_state=False)
+        t1 = time.perf_counter() - t0
+        if t1 > seconds / 4 or M >= 4096:
+            break
+        M *= 4
+    return M * N * T / t1, threads, f"one rejuvenation sweep of configs[4]'s inner filters: {M} theta x {N} particles x T={T}, UCSV, multinomial, " \
+                                    f"oracle/smc_oracle.c OpenMP over theta ({threads} threads)"
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
-    v, sample = cpu_sample(max(args.steps, 1) + 0, 20, 32)
+    note = ("Julia is not installed in this image and the reference module does not load as shipped (SURVEY F2/F7): the "
+            "reference arm is the C port of its algorithm (oracle/smc_oracle.c)")
+    if args.gpus > 1:
+        # the arm of the sharded workload: every host thread, like Threads.@threads over θ
+        vals = [cpu_sharded_sample() for _ in range(max(1, min(args.steps, 2)))]
+        v, threads, sample = float(np.mean([a[0] for a in vals])), vals[0][1], vals[0][2]
+        from sequential_monte_carlo_b200 import bench_smc2
+        line = {
+            "impl": "reference", "metric": "particle-updates/sec (N×T) bootstrap PF", "value": v, "unit": "particle-updates/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": sharded_config(args.gpus),
+            "extrapolated": True, "measured_on": sample,
+            "cpu_baseline": {"value": v, "unit": "particle-updates/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": note + "; the value is the throughput of the sampled sweep, the whole 4096 θ × 4096 × T=241 run was not executed on the CPU",
+        }
+        print(json.dumps(line), flush=True)
+        return
+    sample_logn, sample_T = 20, 32
+    v, sample = cpu_sample(max(args.steps, 1), sample_logn, sample_T)
     N, T = 1 << args.logn, args.T
     line = {
         "impl": "reference", "metric": "particle-updates/sec (N×T) bootstrap PF", "value": v, "unit": "particle-updates/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * N * T / v,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * (1 << sample_logn) * sample_T / v,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(N, T),
+        "extrapolated": True, "sample_N": 1 << sample_logn, "sample_T": sample_T,
+        "ms_per_step_note": f"ms_per_step is the measured time of one sampled sweep (N=2^{sample_logn}, T={sample_T}); the value (particle-updates/s) "
+                            "is linear in N·T for a per-particle loop, the full N=2^24 × T=1000 sweep (≈ 2000 s on one core) was not run",
         "cpu_baseline": {"value": v, "unit": "particle-updates/s", "cores": 1, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "Julia is not installed in this image and the reference module does not load as shipped (SURVEY F2/F7): the "
-                "reference arm is the C port of its algorithm; the reference PF is single-threaded (particles.jl:122)",
+        "note": note + "; the reference PF is single-threaded (particles.jl:122), so one core is all it can use; systematic resampling "
+                       "like the GPU arm (the reference's multinomial draw is timed in the 'multinomial' leg of the GPU arm's line)",
     }
     print(json.dumps(line), flush=True)
+
+
+def sharded_config(world):
+    return {"workload": "smc² + smc²! t=2..241 on the 4-parameter UCSV model (examples/inflation_example.jl shape), 4096 θ × 4096 state "
+                        f"particles, chain 3, ESS 0.5 (BASELINE.json configs[4]), θ sharded over {world} GPUs",
+            "N": 4096, "M": 4096, "T": 241, "chain": 3, "resampler": "systematic", "model": None,
+            "l2": "state clouds 4096 θ × 4096 × 4 × 8 B = 0.5 GB per copy (larger than L2 at 1-2 GPUs); every sweep redraws all clouds",
+            "parallelism": f"theta-sharded x{world} (ncclAllGather of M/G log-likelihoods per step, ncclSend/Recv of resampled clouds)"}
 
 
 def workload_config(N, T):
@@ -199,6 +258,11 @@ def main():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    if world > 1:
+        main_sharded(args, rank, world, local, barrier)
+        dist.destroy_process_group()
+        return
 
     N, T = 1 << args.logn, args.T
     _, y = smc._lib.simulate(smc.KIND_LG1D, LG_PARAMS, T, DATA_SEED)
@@ -306,12 +370,15 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": "particle-updates/s", "cores": 1, "kind": "port", "sample": sample}
     if not args.no_smc2:
         try:
-            from sequential_monte_carlo_b200 import bench_smc2
-            line["smc2"] = bench_smc2.run(local, rank, world)
-            if rank == 0 and world == 1 and not args.no_cpu:
+            line["smc2"] = smc2_legs(ctx, None, 0, 1, None, ("c3", "c4", "c5"))
+            if not args.no_cpu:
                 line["smc2"]["cpu_baseline"] = cpu_rejuvenation_sample(1024, 100)
         except Exception as e:  # the headline line must still print
             line["smc2"] = {"error": repr(e)}
+    try:
+        line["config1_latency"] = config1_latency(ctx)
+    except Exception as e:
+        line["config1_latency"] = {"error": repr(e)}
     if rank == 0 and world == 1 and not args.no_widen:
         try:
             line["widen"] = widen_leg(ctx)
@@ -321,6 +388,133 @@ def main():
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _reducers(world):
+    if world == 1:
+        return (lambda v: float(v)), (lambda v: float(v))
+    import torch
+    import torch.distributed as dist
+
+    def red(op):
+        def f(v):
+            t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=op)
+            return float(t.item())
+        return f
+    return red(dist.ReduceOp.MAX), red(dist.ReduceOp.SUM)
+
+
+def smc2_legs(ctx, comm, rank, world, barrier, names, steps=1, warmup=1):
+    """the θ-level configurations through the public sampler API on the device-resident engine"""
+    from sequential_monte_carlo_b200 import bench_smc2
+    rmax, rsum = _reducers(world)
+    out = {}
+    for name in names:
+        try:
+            out[name] = bench_smc2.finish(bench_smc2.run_config(name, ctx, comm, rank, world, steps=steps, warmup=warmup, barrier=barrier),
+                                          world, rmax, rsum)
+        except Exception as e:
+            out[name] = {"error": repr(e)}
+    return out
+
+
+def config1_latency(ctx, reps=20):
+    """BASELINE configs[0]: log_likelihood(1024, y, lg_mod([0.5,0.9,0.8])), T = 100 — wall clock of ONE public call with host
+    buffers (H2D of y, the whole series in one launch on the batched engine, D2H of x, w, logZ), checked against kalman_filter."""
+    import sequential_monte_carlo_b200 as smc
+    from sequential_monte_carlo_b200 import particles, state_space_models as ssm
+    model = ssm.LinearGaussian(LG_THETA[0], 1.0, LG_THETA[1], LG_THETA[2], 0.0)
+    y = smc._lib.simulate(smc.KIND_LG1D, LG_PARAMS, 100, DATA_SEED)[1]
+    particles.log_likelihood(1024, y, model)
+    ts, zs = [], []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        x, w, z = particles.log_likelihood(1024, y, model)
+        _ = float(z) + float(np.asarray(w)[0])
+        ts.append(time.perf_counter() - t0)
+        zs.append(float(z))
+    kal = float(ctx.kalman_loglik(LG_PARAMS, y, matched_init=True)[0][0])
+    return {"workload": "log_likelihood(1024, y, lg_mod([0.5,0.9,0.8])), T=100, multinomial (the API default), one public call incl. H2D/D2H "
+                        "(BASELINE.json configs[0])", "wall_ms_median": 1e3 * statistics.median(ts), "wall_ms_min": 1e3 * min(ts),
+            "particle_updates_per_s": 1024 * 100 / statistics.median(ts), "logZ_mean": float(np.mean(zs)), "logZ_sd": float(np.std(zs)),
+            "kalman_matched_init_logZ": kal}
+
+
+def main_sharded(args, rank, world, local, barrier):
+    """N > 1: BASELINE configs[4] θ-sharded over the ranks (strong scaling), see the module docstring"""
+    import torch
+    import torch.distributed as dist
+    import sequential_monte_carlo_b200 as smc
+    from sequential_monte_carlo_b200 import bench_smc2, smc_samplers as ss
+    ctx = smc.Context(local, seed=DATA_SEED)
+    comm = ss.NcclComm.from_torch(ctx)
+    rmax, rsum = _reducers(world)
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    head = bench_smc2.run_config("c5", ctx, comm, rank, world, steps=args.steps, warmup=max(1, min(args.warmup, 3)), barrier=barrier)
+    barrier()
+    clocks = sampler.stop()
+    head = bench_smc2.finish(head, world, rmax, rsum)
+    peak, peak_src = measured_peak()
+    units = head["particle_updates"]
+    value = units / head["device_span_s"]
+    filt_s = 1e-3 * head["breakdown_ms"]["filter_ms"]
+    line = {
+        "metric": "particle-updates/sec (N×T) bootstrap PF", "value": value, "unit": "particle-updates/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(1, min(args.warmup, 3)), "ms_per_step": 1e3 * head["device_span_s"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic (simulate(), Philox seed 1998)",
+        "config": sharded_config(world),
+        "e2e": {"value": units / head["wall_s"], "unit": "particle-updates/s", "h2d_bytes_per_step": 8 * 241,
+                "d2h_bytes_per_step": 64 * (241 + 3 * head["rejuvenations"]) + 8 * 4096 * 6, "ms_per_step": 1e3 * head["wall_s"],
+                "note": "wall clock of smc²(smc, y) + smc²!(smc, y, t) for t = 2..T through the public sampler API: y from host memory, ess read back "
+                        "every step, θ / ω / logZ read back at the end; the sampler object is created outside"},
+        "gpu_launches": int(head["kernel_launches"] * args.steps),
+        "breakdown_ms_per_step": head["breakdown_ms"],
+        "run": {k: head[k] for k in ("theta_sha", "logZ_sum", "final_ess", "posterior_mean", "rejuvenations", "sweeps", "clouds_received_all_ranks",
+                                     "s_per_plain_step", "s_per_rejuvenation_step", "stream_syncs", "wall_s", "device_span_s", "particle_updates")},
+        "roofline": {"bound": "hbm", "achieved": 88 * (units / world) / filt_s / 1e9 if filt_s > 0 else None, "peak": peak, "unit": "GB/s",
+                     "frac": (88 * (units / world) / filt_s / 1e9 / peak) if filt_s > 0 else None, "traffic": None, "peak_source": peak_src,
+                     "kernel": "batch_kernel<ModelUCSV> (one CTA per θ, whole series in one launch): 88 algorithmic B per particle-update "
+                               "(SURVEY §8d, UCSV fp64) × this rank's particle-updates ÷ its device time in the inner filters; the clouds are "
+                               "block-resident, so the kernel is bound by fp64 issue / barrier latency, not HBM (SURVEY §8d, DESIGN.md §4)"},
+        "clocks": clocks,
+    }
+    # the same workload on ONE GPU of this box, same build, same run (rank 0 alone; the other ranks wait at the barrier)
+    if not args.no_smc2:
+        if rank == 0:
+            try:
+                ctx1 = smc.Context(local, seed=DATA_SEED)
+                one = bench_smc2.finish(bench_smc2.run_config("c5", ctx1, None, 0, 1, steps=1, warmup=1), 1, float, float)
+                line["single_gpu_same_workload"] = {k: one[k] for k in ("wall_s", "device_span_s", "particle_updates", "particle_updates_per_s", "theta_sha",
+                                                                          "breakdown_ms", "rejuvenations", "s_per_plain_step", "s_per_rejuvenation_step")}
+                line["single_gpu_same_workload"]["value"] = one["particle_updates"] / one["device_span_s"]
+                ctx1.close()
+            except Exception as e:
+                line["single_gpu_same_workload"] = {"error": repr(e)}
+        barrier()
+        line["smc2"] = smc2_legs(ctx, comm, rank, world, barrier, ("c3", "c4"), steps=2, warmup=1)
+    # the single-filter headline as N independent replicas (weak scaling, no collective): a single filter does not shard
+    try:
+        Nr, Tr = 1 << args.logn, 200
+        yr = smc._lib.simulate(smc.KIND_LG1D, LG_PARAMS, Tr, DATA_SEED)[1]
+        rctx = smc.Context(local, seed=DATA_SEED + rank)
+        rctx.log_likelihood(smc.KIND_LG1D, LG_PARAMS, Nr, yr, smc.SYSTEMATIC, stream=rank)
+        barrier()
+        ms = 0.0
+        for _ in range(2):
+            rctx.log_likelihood(smc.KIND_LG1D, LG_PARAMS, Nr, yr, smc.SYSTEMATIC, stream=rank)
+            ms += rctx.timing()[0]["total"]
+        barrier()
+        rctx.close()
+        line["replicas"] = {"workload": f"log_likelihood LG1D N=2^{args.logn}, T={Tr}, systematic: one independent filter per GPU (weak scaling)",
+                            "value": 2 * Nr * Tr * world / (rmax(ms) * 1e-3), "unit": "particle-updates/s", "ms_per_sweep": rmax(ms) / 2}
+    except Exception as e:
+        line["replicas"] = {"error": repr(e)}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    ctx.close()
 
 
 def widen_leg(ctx, M=512, N=1024, T=100):

@@ -252,7 +252,8 @@ int smcb_sampler_get(smcb_sampler* s, double* theta, double* omega, double* logZ
  * until the next call that may run exchange!) */
 int smcb_sampler_clouds(smcb_sampler* s, smcb_batch** clouds);
 /* ms[0..3]: device time in the inner filters / all-gathers / cloud moves (θ-resample exchange + accept copies) / θ-level
- * kernels (CUDA events, only while profiling is on); counts: whole-series sweeps, smc²! steps, rejuvenations, clouds
+ * kernels (CUDA events, only while profiling is on); ms[4]: CUDA-event time on the context's stream from the start of the
+ * last smc² / density_tempered call to the last completed step (always measured); counts: whole-series sweeps, smc²! steps, rejuvenations, clouds
  * received from other ranks, particle-updates of this rank, stream synchronisations, kernel launches, θ-resamples */
 int smcb_sampler_set_profiling(smcb_sampler* s, int enable);
 int smcb_sampler_stats(smcb_sampler* s, double ms[8], int64_t counts[8]);

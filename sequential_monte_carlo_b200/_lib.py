@@ -551,7 +551,7 @@ class Sampler:
         ms = (C.c_double * 8)()
         n = (C.c_int64 * 8)()
         self.ctx._check(self._lib.smcb_sampler_stats(self._h, ms, n))
-        keys_ms = ("filter_ms", "allgather_ms", "exchange_ms", "theta_ms")
+        keys_ms = ("filter_ms", "allgather_ms", "exchange_ms", "theta_ms", "span_ms")
         keys_n = ("sweeps", "steps", "rejuvenations", "clouds_moved", "particle_updates", "syncs", "launches", "theta_resamples")
         out = {k: float(ms[i]) for i, k in enumerate(keys_ms)}
         out.update({k: int(n[i]) for i, k in enumerate(keys_n)})

@@ -1,51 +1,114 @@
-"""SMC² timing leg of bench.py (BASELINE.json metric part 2: "SMC² 512×1024 s/step at 1–8 GPUs").
+"""θ-level legs of bench.py: the BASELINE.json configurations that shard over θ, run through the public
+sampler API on the device-resident engine (smcb_sampler_*, csrc/smcb_sampler.cu):
 
-Config 3: SMC(1024, 512, lg_mod, lg_prior, 3, 0.5) on T=100 observations of lg_mod([0.5,0.9,0.8]).
-θ-particles are sharded across the ranks (strong scaling: total work fixed); reports seconds per
-smc²! call split into plain propagation steps and steps that rejuvenated, plus the whole-run wall.
+  c3  SMC(1024, 512, lg_mod, lg_prior, 3, 0.5), smc² + smc²! over T = 100            (BASELINE configs[2], README.md:88-103)
+  c4  density_tempered, stochastic volatility, 1024 θ × 2048 state particles, T = 500  (configs[3])
+  c5  smc², 4-parameter UCSV (examples/inflation_example.jl:229-256 shape), 4096 θ × 4096, T = 241  (configs[4])
+
+θ-particles are sharded over the ranks (strong scaling: the job is fixed).  One "step" = one whole run of the sampler over
+its series.  Every run reports wall time, particle-updates/s of the whole job, where the time went (device time in the inner
+filters, in the all-gathers, in cloud moves, in the θ-level kernels — CUDA events on the library's stream — and the
+remainder: host control + launch gaps), and a hash of θ that must not depend on the number of GPUs.
 """
+import hashlib
 import time
 
 import numpy as np
 
+CONFIGS = {
+    "c3": dict(kind="lg", N=1024, M=512, T=100, chain=3, algo="smc2", bytes_per_update=56,
+               name="smc² + smc²! t=2..100: SMC(1024, 512, lg_mod, lg_prior, 3, 0.5) (BASELINE.json configs[2])"),
+    "c4": dict(kind="sv", N=2048, M=1024, T=500, chain=3, algo="dt", bytes_per_update=56,
+               name="density_tempered, stochastic volatility, 1024 θ × 2048 state particles, T=500 (BASELINE.json configs[3])"),
+    "c5": dict(kind="ucsv", N=4096, M=4096, T=241, chain=3, algo="smc2", bytes_per_update=88,
+               name="smc² + smc²! t=2..241: UCSV (inflation example shape), 4096 θ × 4096 state particles, chain 3 (BASELINE.json configs[4])"),
+}
 
-def run(local, rank, world, N=1024, M=512, T=100, chain=3):
-    import torch
-    import torch.distributed as dist
+
+def _setup(smc, kind):
+    if kind == "lg":
+        model = lambda θ: smc.StateSpaceModel(smc.LinearGaussian(θ[0], 1.0, θ[1], θ[2], 0.0), (1, 1))   # README.md:75-78
+        prior = smc.product_distribution([smc.TruncatedNormal(0, 1, -1, 1), smc.LogNormal(), smc.LogNormal()])   # README.md:81-85
+        truth = [0.5, 0.9, 0.8]
+    elif kind == "sv":
+        model = lambda θ: smc.SV(θ[0], θ[1], θ[2])
+        prior = smc.product_distribution([smc.Normal(0, 2), smc.Uniform(-1, 1), smc.LogNormal(-1, 1)])
+        truth = [-1.0, 0.9, 0.3]
+    else:
+        model = lambda θ: smc.StateSpaceModel(smc.UCSV(θ[0], θ[1], (θ[2], θ[3])), (3, 1))              # inflation_example.jl:229-232
+        prior = smc.product_distribution([smc.Uniform(0, 1), smc.Normal(3, 2), smc.Uniform(0, 2), smc.Uniform(0, 2)])   # :234-239
+        truth = [0.2, 3.0, 1.0, 1.0]
+    return model, prior, truth
+
+
+def run_config(name, ctx, comm, rank, world, steps=1, warmup=1, resampler="systematic", barrier=None, T=None, M=None):
+    """`warmup` untimed runs, then `steps` timed runs of configuration `name`, θ sharded over `world` ranks.  Returns the
+    per-run averages (max over ranks is taken by the caller through `reduce_max`)."""
     import sequential_monte_carlo_b200 as smc
-
-    def lg_mod(θ):
-        return smc.StateSpaceModel(smc.LinearGaussian(θ[0], 1.0, θ[1], θ[2], 0.0), (1, 1))
-
-    prior = smc.product_distribution([smc.TruncatedNormal(0, 1, -1, 1), smc.LogNormal(), smc.LogNormal()])
-    y = smc.simulate(lg_mod([0.5, 0.9, 0.8]), T, seed=1998)[1]
-    comm = smc.TorchComm() if world > 1 else None
-    ctx = smc.default_context()
-    out = {}
-    for rep in range(2):   # rep 0 warms up (module load, allocations)
-        s = smc.SMC(N, M, lg_mod, prior, chain, 0.5, seed=1998, ctx=ctx, comm=comm)
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    cfg = dict(CONFIGS[name])
+    if T:
+        cfg["T"] = int(T)
+    if M:
+        cfg["M"] = int(M)
+    model, prior, truth = _setup(smc, cfg["kind"])
+    y = smc.simulate(model(truth), cfg["T"], seed=1998)[1]
+    walls, spans, plains, rejuvs, stats_sum, out = [], [], [], [], None, {}
+    for rep in range(warmup + steps):
+        s = smc.SMC(cfg["N"], cfg["M"], model, prior, cfg["chain"], 0.5, seed=1998, ctx=ctx, comm=comm, resampler=resampler, engine="device")
+        s._eng.set_profiling(True)
+        if barrier:
+            barrier()
+        ctx.synchronize()
         t0 = time.perf_counter()
-        smc.smc2(s, y)
         plain, rejuv = [], []
-        for t in range(1, T):
-            t1 = time.perf_counter()
-            smc.smc2_step(s, y, t, verbose=False)
-            (rejuv if s.rejuvenated else plain).append(time.perf_counter() - t1)
-        torch.cuda.synchronize()
+        if cfg["algo"] == "smc2":
+            smc.smc2(s, y)
+            for t in range(1, cfg["T"]):
+                t1 = time.perf_counter()
+                smc.smc2_step(s, y, t, verbose=False)
+                (rejuv if s.rejuvenated else plain).append(time.perf_counter() - t1)
+        else:
+            smc.density_tempered(s, y, verbose=False)
+        θ = s.θ                       # the D2H read of the result (θ, ω, logZ) is inside the timed region
+        ctx.synchronize()
         wall = time.perf_counter() - t0
-        tm = torch.tensor([wall, sum(plain), sum(rejuv)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        wall, tp, tr = (float(v) for v in tm.tolist())
-        pu = s.stats["particle_updates"] * world
-        out = {"workload": f"smc² + smc²! t=2..{T}: SMC({N},{M},lg_mod,lg_prior,{chain},0.5), θ sharded over {world} GPU(s), multinomial",
-               "scaling": "strong", "wall_s": wall, "s_per_step_mean": wall / T,
-               "s_per_plain_step": tp / max(len(plain), 1), "s_per_rejuvenation_step": tr / max(len(rejuv), 1),
-               "rejuvenations": len(rejuv), "particle_updates": pu, "particle_updates_per_s": pu / wall,
-               "device_ms_in_filters": s.stats["device_ms"], "sweeps": s.stats["sweeps"], "clouds_moved_rank0": s.stats["clouds_moved"],
-               "posterior_mean": [float(v) for v in smc.expected_parameters(s).ravel()], "final_ess": float(s.ess)}
+        st = s._eng.stats()
+        if rep >= warmup:
+            walls.append(wall)
+            spans.append(st["span_ms"])
+            plains += plain
+            rejuvs += rejuv
+            st = {k: v for k, v in st.items() if k != "span_ms"}
+            stats_sum = st if stats_sum is None else {k: stats_sum[k] + st[k] for k in st}
+        out = {"theta_sha": hashlib.sha256(np.ascontiguousarray(θ).tobytes()).hexdigest()[:16], "logZ_sum": float(np.sum(s.logZ)),
+               "final_ess": float(s.ess), "posterior_mean": [float(v) for v in smc.expected_parameters(s).ravel()],
+               "stages": len(getattr(s, "schedule", [])), "final_N": int(s.N)}
         s.close()
+    n = len(walls)
+    pu_local = stats_sum["particle_updates"] / n
+    dev = {k: stats_sum[k] / n for k in ("filter_ms", "allgather_ms", "exchange_ms", "theta_ms")}
+    wall = float(np.mean(walls))
+    out.update({
+        "workload": cfg["name"] + f", {resampler} inner resampling, θ sharded over {world} GPU(s)", "config": name, "algo": cfg["algo"],
+        "N": cfg["N"], "M": cfg["M"], "T": cfg["T"], "scaling": "strong", "runs_timed": n, "wall_s": wall, "device_span_s": 1e-3 * float(np.mean(spans)),
+        "particle_updates_local": pu_local, "bytes_per_update": cfg["bytes_per_update"],
+        "s_per_plain_step": float(np.mean(plains)) if plains else None, "s_per_rejuvenation_step": float(np.mean(rejuvs)) if rejuvs else None,
+        "rejuvenations": stats_sum["rejuvenations"] // n, "sweeps": stats_sum["sweeps"] // n, "clouds_received_this_rank": stats_sum["clouds_moved"] // n,
+        "stream_syncs": stats_sum["syncs"] // n, "kernel_launches": stats_sum["launches"] // n,
+        "breakdown_ms": dict(dev, host_control_and_gaps=1e3 * wall - sum(dev.values())),
+    })
+    return out
+
+
+def finish(out, world, reduce_max, reduce_sum):
+    """max over ranks of the times, sum over ranks of the work; whole-job particle-updates/s"""
+    out["wall_s"] = reduce_max(out["wall_s"])
+    out["device_span_s"] = reduce_max(out["device_span_s"])
+    out["particle_updates"] = reduce_sum(out.pop("particle_updates_local"))
+    out["particle_updates_per_s"] = out["particle_updates"] / out["wall_s"]
+    for k in ("s_per_plain_step", "s_per_rejuvenation_step"):
+        if out[k] is not None:
+            out[k] = reduce_max(out[k])
+    out["breakdown_ms"] = {k: reduce_max(v) for k, v in out["breakdown_ms"].items()}
+    out["clouds_received_all_ranks"] = int(reduce_sum(float(out.pop("clouds_received_this_rank"))))
     return out

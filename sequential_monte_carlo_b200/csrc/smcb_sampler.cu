@@ -481,8 +481,10 @@ ThetaSampler::ThetaSampler(int device, cudaStream_t stream, const Comm& comm, co
   SMCB_CUDA_TRY(cudaMemsetAsync(logz_[0], 0, sizeof(double) * M, stream_));  // :44
   theta_prepare_kernel<<<(unsigned)((M_ + 127) / 128), 128, 0, stream_>>>(theta_[0], (int)M_, d_, kind_, prior_, map_, lp_[0], derived_[0]);
   SMCB_CUDA_TRY(cudaGetLastError());
+  ++n_theta_launches_;
   theta_finish_kernel<<<1, kTB, 0, stream_>>>((int)M_, accept_, omega_, scal_dev_);  // ω = 1/M   :39 (the count it writes is not read)
   SMCB_CUDA_TRY(cudaGetLastError());
+  ++n_theta_launches_;
   SMCB_CUDA_TRY(cudaStreamSynchronize(stream_));
   SMCB_CUDA_TRY(cudaFuncSetAttribute(theta_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kMaxThetaParticles)));
   SMCB_CUDA_TRY(cudaFuncSetAttribute(theta_bisect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(double) * kMaxThetaParticles)));
@@ -500,6 +502,8 @@ ThetaSampler::~ThetaSampler() {
   cudaFreeHost(scal_host_); cudaFreeHost(anc_host_); cudaFreeHost(slots_host_); cudaFreeHost(theta_host_);
   for (auto& m : marks_) { cudaEventDestroy(m.e0); cudaEventDestroy(m.e1); }
   for (auto e : ev_free_) cudaEventDestroy(e);
+  for (auto e : span_)
+    if (e) cudaEventDestroy(e);
 }
 
 void ThetaSampler::mark(int klass, bool start) {
@@ -554,14 +558,28 @@ void ThetaSampler::all_gather(double* all) {
 
 void ThetaSampler::read_scalars() {
   SMCB_CUDA_TRY(cudaMemcpyAsync(scal_host_, scal_dev_, sizeof(ThetaScalars), cudaMemcpyDeviceToHost, stream_));
+  if (span_open_) SMCB_CUDA_TRY(cudaEventRecord(span_[1], stream_));
   SMCB_CUDA_TRY(cudaStreamSynchronize(stream_));
   ++n_syncs_;
+  if (span_open_) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, span_[0], span_[1]) == cudaSuccess) span_ms_ = ms;
+  }
   resolve_marks();
+}
+
+void ThetaSampler::open_span() {  // device-timeline span of a run: from its first enqueued operation to its last completed one
+  for (int i = 0; i < 2; ++i)
+    if (!span_[i]) SMCB_CUDA_TRY(cudaEventCreate(&span_[i]));
+  SMCB_CUDA_TRY(cudaEventRecord(span_[0], stream_));
+  span_open_ = true;
+  span_ms_ = 0.0;
 }
 
 void ThetaSampler::smc2_init() {
   if (T_ < 1) throw Error{SMCB_ERR_STATE, "sampler: set_data before smc2_init"};
   SMCB_CUDA_TRY(cudaSetDevice(device_));
+  open_span();
   const uint32_t e = next_epoch();
   mark(SK_FILTER, true);
   cur_->init_dev(derived_[tcur_] + lo_ * kParamStride, nullptr, y_dev_, key(e), (uint32_t)lo_, logmu_ + lo_, nullptr);
@@ -571,6 +589,7 @@ void ThetaSampler::smc2_init() {
   mark(SK_THETA, true);
   theta_step_kernel<<<1, kTB, sizeof(double) * M_, stream_>>>(logmu_, omega_, logz_[tcur_], scal_dev_, (int)M_, 0);
   SMCB_CUDA_TRY(cudaGetLastError());
+  ++n_theta_launches_;
   mark(SK_THETA, false);
   read_scalars();
   ess_ = scal_host_->ess;
@@ -597,6 +616,7 @@ void ThetaSampler::smc2_step(int64_t t, double* ess, int* rejuvenated) {
   mark(SK_THETA, true);
   theta_step_kernel<<<1, kTB, sizeof(double) * M_, stream_>>>(logmu_, omega_, logz_[tcur_], scal_dev_, (int)M_, 1);  // :333-338
   SMCB_CUDA_TRY(cudaGetLastError());
+  ++n_theta_launches_;
   mark(SK_THETA, false);
   read_scalars();
   ess_ = scal_host_->ess;
@@ -609,10 +629,12 @@ void ThetaSampler::resample() {
   mark(SK_THETA, true);
   theta_resample_kernel<<<1, kTB, 12 * (size_t)M_, stream_>>>(omega_, (int)M_, theta_resampler_, key(0u), n_resample_, anc_);
   SMCB_CUDA_TRY(cudaGetLastError());
+  ++n_theta_launches_;
   ++n_resample_;
   theta_gather_kernel<<<(unsigned)((M_ + 127) / 128), 128, 0, stream_>>>(anc_, (int)M_, d_, theta_[tcur_], theta_[o], logz_[tcur_], logz_[o],
                                                                          lp_[tcur_], lp_[o], derived_[tcur_], derived_[o], omega_);
   SMCB_CUDA_TRY(cudaGetLastError());
+  ++n_theta_launches_;
   mark(SK_THETA, false);
   tcur_ = o;
   SMCB_CUDA_TRY(cudaMemcpyAsync(theta_host_, theta_[tcur_], sizeof(double) * M_ * d_, cudaMemcpyDeviceToHost, stream_));
@@ -690,6 +712,7 @@ void ThetaSampler::rejuvenate(int64_t t_len, double xi) {
     theta_propose_kernel<<<grid, 128, 0, stream_>>>(theta_[tcur_], (int)M_, d_, kind_, L, hkey, (uint32_t)c, prior_, map_, theta_prop_, lp_prop_,
                                                    ok_, derived_prop_);
     SMCB_CUDA_TRY(cudaGetLastError());
+  ++n_theta_launches_;
     mark(SK_THETA, false);
     const uint32_t e = next_epoch();
     mark(SK_FILTER, true);
@@ -702,6 +725,7 @@ void ThetaSampler::rejuvenate(int64_t t_len, double xi) {
     theta_accept_kernel<<<grid, 128, 0, stream_>>>((int)M_, d_, xi, hkey, (uint32_t)c, theta_prop_, lp_prop_, ok_, logz_prop_, derived_prop_,
                                                   theta_[tcur_], lp_[tcur_], logz_[tcur_], derived_[tcur_], accept_, acc_any_);
     SMCB_CUDA_TRY(cudaGetLastError());
+  ++n_theta_launches_;
     mark(SK_THETA, false);
     mark(SK_EXCHANGE, true);
     cur_->accept_dev(*prop_, accept_ + lo_);  // :130-133
@@ -710,6 +734,7 @@ void ThetaSampler::rejuvenate(int64_t t_len, double xi) {
   mark(SK_THETA, true);
   theta_finish_kernel<<<1, kTB, 0, stream_>>>((int)M_, acc_any_, omega_, scal_dev_);
   SMCB_CUDA_TRY(cudaGetLastError());
+  ++n_theta_launches_;
   mark(SK_THETA, false);
   SMCB_CUDA_TRY(cudaMemcpyAsync(theta_host_, theta_[tcur_], sizeof(double) * M_ * d_, cudaMemcpyDeviceToHost, stream_));
   read_scalars();
@@ -722,6 +747,7 @@ void ThetaSampler::exchange(int64_t t_len) {
   if (N_ > 4096) return;                       // "[cannot exceed max state particles]"   :187
   N_ *= 2;                                     // :167
   SMCB_CUDA_TRY(cudaStreamSynchronize(stream_));
+  n_batch_launches_retired_ += cur_->launches() + (prop_ ? prop_->launches() : 0);
   prop_.reset();
   cur_.reset(new BatchFilter(device_, stream_, kind_, Mloc_, N_));
   const uint32_t e = next_epoch();
@@ -734,6 +760,7 @@ void ThetaSampler::exchange(int64_t t_len) {
   mark(SK_THETA, true);
   theta_step_kernel<<<1, kTB, sizeof(double) * M_, stream_>>>(logmu_, omega_, logz_[tcur_], scal_dev_, (int)M_, 2);  // :183-185
   SMCB_CUDA_TRY(cudaGetLastError());
+  ++n_theta_launches_;
   mark(SK_THETA, false);
   read_scalars();
   ess_ = scal_host_->ess;
@@ -742,6 +769,7 @@ void ThetaSampler::exchange(int64_t t_len) {
 int ThetaSampler::density_tempered(double* schedule, int cap) {
   if (T_ < 1) throw Error{SMCB_ERR_STATE, "sampler: set_data before density_tempered"};
   SMCB_CUDA_TRY(cudaSetDevice(device_));
+  open_span();
   const uint32_t e = next_epoch();
   mark(SK_FILTER, true);
   cur_->run_dev(derived_[tcur_] + lo_ * kParamStride, nullptr, y_dev_, T_, resampler_, key(e), (uint32_t)lo_, logz_[tcur_] + lo_);  // :223-229
@@ -755,6 +783,7 @@ int ThetaSampler::density_tempered(double* schedule, int cap) {
     mark(SK_THETA, true);
     theta_bisect_kernel<<<1, kTB, sizeof(double) * M_, stream_>>>(logz_[tcur_], omega_, scal_dev_, (int)M_, xi, ess_min_);  // :237-266
     SMCB_CUDA_TRY(cudaGetLastError());
+  ++n_theta_launches_;
     mark(SK_THETA, false);
     read_scalars();
     xi = scal_host_->xi;
@@ -791,13 +820,14 @@ void ThetaSampler::get(double* theta, double* omega, double* logZ, double* ess, 
 void ThetaSampler::stats(double ms[8], int64_t counts[8]) {
   for (int i = 0; i < 8; ++i) { ms[i] = 0.0; counts[i] = 0; }
   for (int i = 0; i < SK_COUNT; ++i) ms[i] = ms_[i];
+  ms[4] = span_ms_;
   counts[0] = n_sweeps_;
   counts[1] = n_steps_;
   counts[2] = n_rejuv_done_;
   counts[3] = n_clouds_moved_;
   counts[4] = n_particle_updates_;
   counts[5] = n_syncs_;
-  counts[6] = cur_ ? cur_->launches() + (prop_ ? prop_->launches() : 0) : 0;
+  counts[6] = n_theta_launches_ + n_batch_launches_retired_ + (cur_ ? cur_->launches() : 0) + (prop_ ? prop_->launches() : 0);
   counts[7] = n_resample_;
 }
 

@@ -98,6 +98,7 @@ class ThetaSampler {
   void exchange(int64_t t_len);          // exchange!(smc, y[1:t_len])
   void mark(int klass, bool start);
   void resolve_marks();
+  void open_span();
 
   int device_;
   cudaStream_t stream_;
@@ -152,7 +153,11 @@ class ThetaSampler {
   std::vector<Mark> marks_;
   std::vector<cudaEvent_t> ev_free_;
   double ms_[SK_COUNT] = {0, 0, 0, 0};
-  int64_t n_sweeps_ = 0, n_steps_ = 0, n_rejuv_done_ = 0, n_clouds_moved_ = 0, n_particle_updates_ = 0, n_syncs_ = 0;
+  cudaEvent_t span_[2] = {nullptr, nullptr};
+  bool span_open_ = false;
+  double span_ms_ = 0.0;   // CUDA-event time from the start of smc² / density_tempered to the last completed step
+  int64_t n_sweeps_ = 0, n_steps_ = 0, n_rejuv_done_ = 0, n_clouds_moved_ = 0, n_particle_updates_ = 0, n_syncs_ = 0, n_theta_launches_ = 0,
+          n_batch_launches_retired_ = 0;
 };
 
 }  // namespace smcb

@@ -19,6 +19,7 @@ from . import _lib
 _RESAMPLERS = {"multinomial": _lib.MULTINOMIAL, "stratified": _lib.STRATIFIED, "systematic": _lib.SYSTEMATIC,
                _lib.MULTINOMIAL: _lib.MULTINOMIAL, _lib.STRATIFIED: _lib.STRATIFIED, _lib.SYSTEMATIC: _lib.SYSTEMATIC}
 _DEFAULT = None
+_SMALL_N_MAX = 8192     # clouds up to this size run block-resident (csrc/smcb_batch.cu) when a whole series is filtered in one call
 
 
 def resampler_id(r):
@@ -159,7 +160,10 @@ class _GuidedCloud:
         t = getattr(self._batch, "_t", 0)
         if self._host is None or self._host_t != t:
             x, w, _ = self._batch.fetch(want_x=self._which == "x", want_w=self._which == "w")
-            self._host = x[0, 0] if self._which == "x" else w[0]
+            if self._which == "x":
+                self._host = x[0, 0] if x.shape[1] == 1 else np.ascontiguousarray(x[0].T)   # UCSV: N rows of 3
+            else:
+                self._host = w[0]
             self._host_t = t
         return self._host
 
@@ -175,7 +179,7 @@ class _GuidedCloud:
 
     @property
     def shape(self):
-        return (self._batch.N,)
+        return (self._batch.N,) if self._which == "w" or self._batch.d == 1 else (self._batch.N, self._batch.d)
 
 
 def _proposal_coefficients(proposal, model, y):
@@ -289,6 +293,15 @@ def weighted_mean_var(x, w=None):
 def log_likelihood(N, y, model, *, resampler="multinomial", ctx=None, stream=0):
     """x, w, logZ = log_likelihood(N, y, model)  — particles.jl:132-147, one call for the whole series."""
     ctx = ctx or default_context()
-    logZ = ctx.log_likelihood(model.kind, model.params(), int(N), np.asarray(y, np.float64), resampler_id(resampler), stream)
+    y = np.asarray(y, np.float64)
+    if int(N) <= _SMALL_N_MAX and y.size > 1:
+        # a small cloud (BASELINE configs[0]: N = 1024, T = 100) lives in one CTA for the whole series: ONE launch of the
+        # block-resident engine instead of two to four grid-wide launches per observation (same arithmetic, same x, w, logZ)
+        b = ctx.batch(model.kind, 1, int(N))
+        z = b.log_likelihood(np.asarray(model.params(), np.float64).reshape(1, -1), y, resampler_id(resampler), stream0=stream)
+        b._t = y.size - 1
+        ctx._gen = getattr(ctx, "_gen", 0) + 1          # as on the single filter: earlier handles of this context go stale
+        return _GuidedCloud(b, "x"), _GuidedCloud(b, "w"), float(z[0])
+    logZ = ctx.log_likelihood(model.kind, model.params(), int(N), y, resampler_id(resampler), stream)
     x, w = _handles(ctx)
     return x, w, logZ

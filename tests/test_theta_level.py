@@ -237,13 +237,13 @@ def test_smc2_config5_shape_reduced_T(ctx, oracle):
     """BASELINE config 5's inner shape (UCSV, 4096 state particles per θ) with M = 256 θ-particles and T = 12: the large
     clouds take the L2 placement of batch_kernel; θ, logZ and sampled clouds against the oracle."""
     from oracle import samplers as S
-    N, M, T, chain = 4096, 256, 12, 2
+    N, M, T, chain = 4096, 256, 14, 2
     _, y = oracle.simulate(2, [0.2, 0.2, 3.0, 1.0, 1.0], T, 1998)
     pg = smc.product_distribution([smc.Uniform(0, 1), smc.Normal(3, 2), smc.Uniform(0, 2), smc.Uniform(0, 2)])
     po = S.OProduct([S.OUniform(0, 1), S.ONormal(3, 2), S.OUniform(0, 2), S.OUniform(0, 2)])
-    g = smc.SMC(N, M, lambda θ: smc.StateSpaceModel(smc.UCSV(θ[0], θ[1], (θ[2], θ[3])), (3, 1)), pg, chain, 0.5, seed=3,
+    g = smc.SMC(N, M, lambda θ: smc.StateSpaceModel(smc.UCSV(θ[0], θ[1], (θ[2], θ[3])), (3, 1)), pg, chain, 0.9, seed=3,
                 resampler="systematic", ctx=ctx, engine="device")
-    o_ = S.OSMC(N, M, lambda θ: (2, [θ[0], θ[0], θ[1], θ[2], θ[3]]), po, chain, 0.5, seed=3, resampler=2)
+    o_ = S.OSMC(N, M, lambda θ: (2, [θ[0], θ[0], θ[1], θ[2], θ[3]]), po, chain, 0.9, seed=3, resampler=2)
     smc.smc2(g, y)
     S.o_smc2(o_, y)
     n = 0
