@@ -1461,6 +1461,7 @@ void SingleFilter::launch_init(double y0) {
   logw_valid_ = true;
   sum_done_ = false;
   SMCB_CUDA_TRY(cudaMemsetAsync(desc_, 0, sizeof(unsigned long long) * 2 * ntiles_cap_, stream_));
+  desc_clean_t_ = 0;
   reset_ctrl_kernel<<<1, 1, 0, stream_>>>(ctrl_);
   launches_[TK_INIT] += 1;
   const int64_t npairs = (N_ + 1) / 2;
@@ -1484,6 +1485,13 @@ void SingleFilter::launch_scan(int64_t stat_index, bool write_cdf) {
   unsigned long long* dn = desc_ + (size_t)((t_ + 1) & 1u) * ntiles_cap_;
   const int klass = write_cdf ? TK_SCAN : TK_STATS;
   if ((write_cdf || from_w_) && !cdf_) SMCB_CUDA_TRY(cudaMalloc(&cdf_, sizeof(uint64_t) * cap_N_));  // multinomial / utilities only
+  if (write_cdf || from_w_) {
+    // The look-back descriptors of this scan must start cleared.  A WRITE_CDF scan at time t clears the half the scan at
+    // t + 1 will use — but sorted-resampler steps advance t_ without scanning, so a multinomial step after them would find
+    // the descriptors of an older scan of the same parity, still flagged inclusive, and could accept a stale prefix.
+    if (desc_clean_t_ != (int64_t)t_) SMCB_CUDA_TRY(cudaMemsetAsync(dc, 0, sizeof(unsigned long long) * ntiles, stream_));
+    desc_clean_t_ = (int64_t)t_ + 1;  // this launch clears dn
+  }
   ensure_logw();
   const double* lw = logw_[cur_];
   mark(klass, true);
@@ -1862,6 +1870,7 @@ void SingleFilter::load_vector(const double* host, int64_t n, bool is_log) {
   S_ = quant_shift((uint64_t)n); R_ = strata_width((uint64_t)n);
   t_ = 0; cur_ = 0; anc_rows_ = 0; from_w_ = !is_log; logw_valid_ = true; sum_done_ = false;
   SMCB_CUDA_TRY(cudaMemsetAsync(desc_, 0, sizeof(unsigned long long) * 2 * ntiles_cap_, stream_));
+  desc_clean_t_ = 0;
   reset_ctrl_kernel<<<1, 1, 0, stream_>>>(ctrl_);
   SMCB_CUDA_TRY(cudaMemcpyAsync(logw_[cur_], host, sizeof(double) * n, cudaMemcpyHostToDevice, stream_));
   const unsigned grid = (unsigned)std::min<int64_t>((n + 255) / 256, 1184);

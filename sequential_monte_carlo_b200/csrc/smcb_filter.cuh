@@ -123,6 +123,7 @@ class SingleFilter {
   int32_t* anc_ = nullptr;
   FilterCtrl* ctrl_ = nullptr;
   unsigned long long* desc_ = nullptr;  // [2][ntiles_cap]
+  int64_t desc_clean_t_ = -1;           // the descriptor half of time index desc_clean_t_ is known to be cleared (launch_scan)
   // tile index of the sorted-resampler step (sum -> bounds -> prop2)
   unsigned long long* tile_arrays_ = nullptr;  // [5][kMaxTiles]: tot, excl, incl, lexcl, cta_tot
   unsigned long long* summary_dev_ = nullptr;  // scratch of summary(): block partials, radix-select prefixes / ranks / histograms

@@ -252,6 +252,28 @@ def test_stepping_with_mixed_resamplers_and_changing_parameters(ctx, oracle):
             np.testing.assert_array_equal(lw, lwo)
 
 
+def test_multinomial_after_sorted_steps_at_many_tiles(ctx, oracle):
+    """A multinomial step that follows sorted-resampler steps must not see the look-back descriptors of an older scan of
+    the same parity (they are flagged "inclusive" with stale prefixes; the sorted steps advance t without scanning).  Many
+    tiles (N = 2^19 + 77: 257 scan tiles), multinomial at t = 1, 5, 9, 11 with systematic / stratified in between; states
+    and log-weights bit for bit against the oracle after every multinomial step."""
+    kind, N, T = smc.KIND_SV, (1 << 19) + 77, 12
+    y = _data(oracle, kind, T)
+    seq = [smc.MULTINOMIAL, smc.SYSTEMATIC, smc.STRATIFIED, smc.SYSTEMATIC, smc.MULTINOMIAL, smc.SYSTEMATIC, smc.SYSTEMATIC,
+           smc.STRATIFIED, smc.MULTINOMIAL, smc.SYSTEMATIC, smc.MULTINOMIAL]
+    for rep in range(3):            # the hazard is a race: repeat it
+        ctx.set_rng(91 + rep, 2)
+        ctx.bootstrap_init(kind, MODELS[kind], N, y[0], stream=0)
+        xo, lwo = oracle.bootstrap_init(kind, MODELS[kind], N, y[0], 91 + rep, 2, 0)
+        for t in range(1, T):
+            ctx.bootstrap_step(y[t], seq[t - 1])
+            oracle.bootstrap_step(kind, MODELS[kind], xo, lwo, y[t], t, seq[t - 1], 91 + rep, 2, 0)
+            if seq[t - 1] == smc.MULTINOMIAL:
+                x, _, lw = ctx.fetch_state(want_w=False, want_logw=True)
+                np.testing.assert_array_equal(x, xo)
+                np.testing.assert_array_equal(lw, lwo)
+
+
 @pytest.mark.parametrize("kind", [smc.KIND_LG1D, smc.KIND_UCSV])
 def test_on_device_summaries(ctx, oracle, kind):
     """docs/SPEC.md §8: weighted / plain mean, variance and quantiles of the cloud computed on the device
