@@ -368,6 +368,37 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         v, sample = cpu_sample(2, 20, 64)
         line["cpu_baseline"] = {"value": v, "unit": "particle-updates/s", "cores": 1, "kind": "port", "sample": sample}
+    # the reference's own resampling law (multinomial: particles.jl:17-19, the API default) on the same workload: two-level
+    # draw of docs/SPEC.md §5c (sum -> mn_prep -> mn_count -> mn_cell -> move), against the same 56 B roofline
+    try:
+        Tm = min(T, 100)
+        ctx.log_likelihood(smc.KIND_LG1D, LG_PARAMS, N, y[:Tm], smc.MULTINOMIAL, stream=rank)
+        msm = 0.0
+        ctx.set_profiling(True)
+        km = {}
+        for _ in range(2):
+            ctx.log_likelihood(smc.KIND_LG1D, LG_PARAMS, N, y[:Tm], smc.MULTINOMIAL, stream=rank)
+            ms_, n_ = ctx.timing()
+            for k in ("scan", "bounds", "anc", "prop"):
+                km[k] = km.get(k, 0.0) + 1e3 * ms_[k] / max(n_[k], 1) / 2
+        ctx.set_profiling(False)
+        for _ in range(2):
+            ctx.log_likelihood(smc.KIND_LG1D, LG_PARAMS, N, y[:Tm], smc.MULTINOMIAL, stream=rank)
+            msm += ctx.timing()[0]["total"]
+        vm = 2 * N * Tm / (msm * 1e-3)
+        line["multinomial"] = {"workload": f"the headline workload with multinomial resampling (the reference's law and the API default), T={Tm}",
+                               "value": vm, "unit": "particle-updates/s", "us_per_step": 1e3 * msm / 2 / Tm, "roofline_frac_56B": vm * BYTES_PER_UPDATE / (peak * 1e9),
+                               "vs_systematic": vm / value,
+                               "avg_us_per_launch": {"sum_kernel": km.get("scan"), "mn_prep+mn_count": km.get("bounds"), "mn_cell_kernel": km.get("anc"),
+                                                     "move_kernel": km.get("prop")}}
+        if not args.no_cpu:
+            from oracle import oracle as o
+            t0 = time.perf_counter()
+            o.log_likelihood(0, LG_PARAMS, 1 << 20, y[:16], o.MULTINOMIAL, seed=DATA_SEED, epoch=0)
+            line["multinomial"]["cpu_baseline"] = {"value": (1 << 20) * 16 / (time.perf_counter() - t0), "unit": "particle-updates/s", "cores": 1, "kind": "port",
+                                                   "sample": "LG1D N=2^20, T=16, multinomial (SPEC §5c two-level draw), oracle/smc_oracle.c"}
+    except Exception as e:
+        line["multinomial"] = {"error": repr(e)}
     if not args.no_smc2:
         try:
             line["smc2"] = smc2_legs(ctx, None, 0, 1, None, ("c3", "c4", "c5"))

@@ -16,6 +16,8 @@ _LIB = None
 KIND_LG1D, KIND_SV, KIND_UCSV = 0, 1, 2
 MULTINOMIAL, STRATIFIED, SYSTEMATIC = 0, 1, 2
 P_INIT, P_TRANS, P_RESAMPLE, P_PRIOR, P_THETA_RESAMPLE, P_MH_PROPOSAL, P_MH_ACCEPT, P_SIMULATE = 1, 2, 3, 4, 5, 6, 7, 8
+P_RESAMPLE_CELL = 9   # in-cell thresholds of the two-level multinomial resampler (docs/SPEC.md §5c)
+MN_CELL, MN_CHUNK, MN_LEGACY_MAX = 4096, 8192, 8192
 
 _dp = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
 _u64p = np.ctypeslib.ndpointer(np.uint64, flags="C_CONTIGUOUS")
@@ -160,6 +162,26 @@ def ancestors_numpy(logw, resampler, seed, epoch, stream, t):
     R = (2 ** 64 - 1) // n
     U = [int(v) for v in uniforms64(seed, epoch, stream, t, P_RESAMPLE, n)]
     out = np.empty(n, np.int64)
+    if resampler == MULTINOMIAL and n > MN_LEGACY_MAX and Q != 0:
+        # SPEC §5c, vectorised differently from the C oracle: level-1 cells by one searchsorted, level-2 per cell
+        ncells = (n + MN_CELL - 1) // MN_CELL
+        last = np.minimum((np.arange(ncells) + 1) * MN_CELL - 1, n - 1)
+        cellC = Cs[last]
+        tau1 = np.array([(u * Q) >> 64 for u in U], dtype=np.uint64)
+        K = np.bincount(np.searchsorted(cellC, tau1, side="right"), minlength=ncells)
+        V = [int(v) for v in uniforms64(seed, epoch, stream, t, P_RESAMPLE_CELL, n)]
+        O = 0
+        for c in range(ncells):
+            j0, j1 = c * MN_CELL, min((c + 1) * MN_CELL, n)
+            base = int(cellC[c - 1]) if c else 0
+            W = int(cellC[c]) - base
+            loc = Cs[j0:j1] - np.uint64(base)
+            for g0 in range(O, O + int(K[c]), MN_CHUNK):
+                g1 = min(g0 + MN_CHUNK, O + int(K[c]))
+                tau2 = np.array([(V[g] * W) >> 64 for g in range(g0, g1)], dtype=np.uint64)
+                out[g0:g1] = np.sort(j0 + np.searchsorted(loc, tau2, side="right"))
+            O += int(K[c])
+        return out
     for i in range(n):
         if Q == 0:
             out[i] = i

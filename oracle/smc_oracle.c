@@ -32,7 +32,7 @@
 
 enum { KIND_LG1D = 0, KIND_SV = 1, KIND_UCSV = 2 };
 enum { RS_MULTINOMIAL = 0, RS_STRATIFIED = 1, RS_SYSTEMATIC = 2 };
-enum { P_INIT = 1, P_TRANS = 2, P_RESAMPLE = 3, P_SIMULATE = 8 };
+enum { P_INIT = 1, P_TRANS = 2, P_RESAMPLE = 3, P_SIMULATE = 8, P_RESAMPLE_CELL = 9 };
 
 int smco_state_dim(int kind) { return kind == KIND_UCSV ? 3 : 1; }
 
@@ -150,6 +150,63 @@ static void ancestors_from_q(const uint64_t *q, int64_t n, int resampler, uint64
   free(C);
 }
 
+/* SPEC §5c: multinomial resampling of a LARGE cloud (n > 8192) in two levels.  The reference draws n i.i.d. categorical
+ * indices (particles.jl:18); their offspring counts are multinomial and the resampled particles exchangeable, so
+ *   level 1: the n thresholds tau_i = mulhi(U(i), Q) are counted per cell of 4096 consecutive particles -> K_c;
+ *   level 2: output position g of cell c (positions O_c .. O_c + K_c - 1, O = exclusive prefix of K) draws V(g) from a second
+ *            Philox purpose and takes the in-cell ancestor  c*4096 + #{ j in cell : Cloc_j <= mulhi(V(g), W_c) };
+ *   order:   every chunk of 8192 consecutive output positions of a cell is written in ascending ancestor order. */
+#define MN_CELL 4096
+#define MN_CHUNK 8192
+#define MN_LEGACY_MAX 8192
+static int cmp_i64(const void *a, const void *b) {
+  int64_t x = *(const int64_t *)a, y = *(const int64_t *)b;
+  return (x > y) - (x < y);
+}
+static void ancestors_two_level(const uint64_t *q, int64_t n, uint64_t seed, uint32_t epoch, uint32_t stream, uint32_t t,
+                                int64_t *anc) {
+  int64_t ncells = (n + MN_CELL - 1) / MN_CELL;
+  uint64_t *C = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)n);
+  uint64_t *cellC = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)ncells);
+  int64_t *K = (int64_t *)calloc((size_t)ncells, sizeof(int64_t));
+  uint64_t run = 0;
+  for (int64_t j = 0; j < n; ++j) { run += q[j]; C[j] = run; }
+  uint64_t Q = run;
+  if (Q == 0) {
+    for (int64_t i = 0; i < n; ++i) anc[i] = i;
+    free(C); free(cellC); free(K);
+    return;
+  }
+  for (int64_t c = 0; c < ncells; ++c) {
+    int64_t last = (c + 1) * MN_CELL - 1;
+    if (last > n - 1) last = n - 1;
+    cellC[c] = C[last];
+  }
+  for (int64_t i = 0; i < n; ++i) {                      /* level 1 */
+    uint64_t tau = o_mulhi(o_uniform64(seed, epoch, (uint32_t)i, stream, t, P_RESAMPLE), Q);
+    int64_t lo = 0, hi = ncells;                         /* c = #{c : cellC_c <= tau} */
+    while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (cellC[mid] <= tau) lo = mid + 1; else hi = mid; }
+    K[lo] += 1;
+  }
+  int64_t O = 0;
+  for (int64_t c = 0; c < ncells; ++c) {                 /* level 2 */
+    int64_t j0 = c * MN_CELL, len = (n - j0 < MN_CELL) ? n - j0 : MN_CELL;
+    uint64_t base = c ? cellC[c - 1] : 0, W = cellC[c] - base;
+    for (int64_t g0 = O; g0 < O + K[c]; g0 += MN_CHUNK) {
+      int64_t g1 = (g0 + MN_CHUNK < O + K[c]) ? g0 + MN_CHUNK : O + K[c];
+      for (int64_t g = g0; g < g1; ++g) {
+        uint64_t tau = o_mulhi(o_uniform64(seed, epoch, (uint32_t)g, stream, t, P_RESAMPLE_CELL), W);
+        int64_t lo = 0, hi = len;                        /* #{ j in cell : C_j - base <= tau } */
+        while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (C[j0 + mid] - base <= tau) lo = mid + 1; else hi = mid; }
+        anc[g] = j0 + lo;
+      }
+      qsort(anc + g0, (size_t)(g1 - g0), sizeof(int64_t), cmp_i64);
+    }
+    O += K[c];
+  }
+  free(C); free(cellC); free(K);
+}
+
 void smco_ancestors(const double *logw, int64_t n, int resampler, uint64_t seed, uint32_t epoch, uint32_t stream,
                     uint32_t t, int64_t *anc) {
   int S = smco_quant_shift(n);
@@ -157,7 +214,8 @@ void smco_ancestors(const double *logw, int64_t n, int resampler, uint64_t seed,
   for (int64_t i = 0; i < n; ++i) if (logw[i] > mx) mx = logw[i];
   uint64_t *q = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)n);
   for (int64_t i = 0; i < n; ++i) q[i] = o_quant(logw[i] - mx, S);
-  ancestors_from_q(q, n, resampler, seed, epoch, stream, t, P_RESAMPLE, anc);
+  if (resampler == RS_MULTINOMIAL && n > MN_LEGACY_MAX) ancestors_two_level(q, n, seed, epoch, stream, t, anc);
+  else ancestors_from_q(q, n, resampler, seed, epoch, stream, t, P_RESAMPLE, anc);
   free(q);
 }
 

@@ -95,6 +95,7 @@ enum : uint32_t {
   PURPOSE_MH_PROPOSAL = 6,
   PURPOSE_MH_ACCEPT = 7,
   PURPOSE_SIMULATE = 8,
+  PURPOSE_RESAMPLE_CELL = 9,  // in-cell thresholds of the two-level multinomial resampler (SPEC §5c)
 };
 
 struct RngKey {

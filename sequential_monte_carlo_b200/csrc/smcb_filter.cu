@@ -1014,6 +1014,269 @@ __global__ void __launch_bounds__(kSysThreads, 12)
   }
 }
 
+// ================================================================================================
+// Multinomial resampling of a large cloud (N > kMnLegacyMax) — the reference's law, `sample(1:n, Weights(w), n)`
+// (particles.jl:17-19), without N random walks through a CDF that does not fit the L2 (docs/SPEC.md §5c).
+// The offspring counts of i.i.d. thresholds are multinomial whatever order the thresholds are looked at in, and
+// the particles of a resampled cloud are exchangeable, so the draw is organised in two levels:
+//   level 1  the N thresholds tau_i = mulhi(U(i), Q) are only COUNTED per cell of kMnCell consecutive particles
+//            (mn_count_kernel: an interpolation guess + a short gallop in the <= 32 KB cell index, a shared-memory
+//            histogram per CTA) -> K_c, and their prefix O_c;
+//   level 2  given K_c, the thresholds that fell into cell c are i.i.d. uniform on the cell's mass: output
+//            position g in [O_c, O_c + K_c) draws its own V(g) (a second Philox purpose), searches the cell-local
+//            CDF held in shared memory, and every chunk of kMnChunk consecutive output positions of a cell is
+//            written in ascending ancestor order (mn_cell_kernel: histogram + prefix sum, no sort).
+// The ancestor vector is piecewise sorted (cells in order), so move_kernel's gather is as coalesced as for the
+// systematic resampler; every step is defined by particle / output indices only, not by the launch geometry, so the
+// oracle reproduces the ancestors bit for bit.  sum_kernel (tile-local CDF, Q, normalize statistics) is shared
+// with the sorted resamplers:  sum -> mn_prep -> mn_count -> mn_cell -> move.
+constexpr int kMnCell = 4096;
+constexpr int kMnChunk = 8192;
+constexpr int kMnLegacyMax = 8192;      // N <= this: per-particle search of the materialised CDF, unsorted ancestors (SPEC §5 row 0)
+constexpr int kMnCountThreads = 256;
+constexpr int kMnSmemCells = 8192;      // cells whose counters fit a CTA's shared memory (N <= 2^25)
+constexpr int kMnCellThreads = 512;
+
+struct MnIndex {
+  unsigned long long* cellC;  // [ncells] global CDF at the last particle of every cell
+  int32_t* K;                 // [ncells] thresholds that fell into the cell
+  int32_t* O;                 // [ncells] exclusive prefix of K: first output position of the cell
+  int32_t* part_start;        // [ncells + 1] exclusive prefix of max(1, ceil(K_c / kMnChunk)): first work item of the cell
+  unsigned int* ticket;       // last-CTA-out counter of mn_count_kernel
+  int ncells;
+};
+
+// cellC[c] = C at the last particle of cell c, from the tile-local CDF and the tile offsets; K[c] = 0
+__global__ void mn_prep_kernel(MnIndex mn, StepIndex ix, const unsigned long long* __restrict__ cl, int N) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();  // the tile-local CDF and the tile offsets come from sum_kernel
+  if (c >= mn.ncells) return;
+  int64_t last = (int64_t)(c + 1) * kMnCell - 1;
+  if (last > N - 1) last = N - 1;
+  const int T = (int)(last / ix.tile_items);
+  mn.cellC[c] = __ldg(&ix.tile_excl[T]) + __ldg(&cl[last]);
+  mn.K[c] = 0;
+}
+
+// #{ c : cellC[c] <= tau } starting from the interpolation guess g (cell masses are nearly equal unless the weights
+// are very uneven, so the answer is almost always within a cell or two of g); cellC[ncells - 1] = Q > tau
+__device__ __forceinline__ int mn_cell_of(const unsigned long long* __restrict__ cellC, int ncells, uint64_t tau, int g) {
+  int lo, hi;
+  if (__ldg(&cellC[g]) <= tau) {
+    lo = g + 1;
+    hi = g + 1;
+    int s = 1;
+    while (hi < ncells - 1 && __ldg(&cellC[hi]) <= tau) {
+      lo = hi + 1;
+      s <<= 1;
+      hi = hi + s < ncells - 1 ? hi + s : ncells - 1;
+    }
+  } else {
+    hi = g;
+    lo = g;
+    int s = 1;
+    while (lo > 0 && __ldg(&cellC[lo - 1]) > tau) {
+      hi = lo - 1;
+      s <<= 1;
+      lo = lo - s > 0 ? lo - s : 0;
+    }
+  }
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (__ldg(&cellC[mid]) <= tau) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+// level 1: K[c] = #{ i : tau_i in cell c }; the last CTA out turns K into output offsets and work items
+__global__ void __launch_bounds__(kMnCountThreads)
+    mn_count_kernel(MnIndex mn, const FilterCtrl* __restrict__ ctrl, int N, RngKey key, uint32_t stream, uint32_t t) {
+  extern __shared__ int s_hist[];  // [ncells] when ncells <= kMnSmemCells
+  __shared__ bool s_last;
+  __shared__ int s_wtot[kMnCountThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int ncells = mn.ncells;
+  const bool in_smem = ncells <= kMnSmemCells;
+  if (in_smem)
+    for (int c = tid; c < ncells; c += kMnCountThreads) s_hist[c] = 0;
+  pdl_launch_dependents();
+  pdl_wait();  // cellC, K = 0 come from mn_prep_kernel, Q from sum_kernel
+  const uint64_t Q = ctrl->total;
+  __syncthreads();
+  const int npairs = (N + 1) >> 1;
+  for (int p = blockIdx.x * kMnCountThreads + tid; p < npairs; p += gridDim.x * kMnCountThreads) {
+    const Philox4 b = philox4x32_10((uint32_t)p, stream, t, purpose_word(PURPOSE_RESAMPLE, 0, key.epoch), key);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = 2 * p + h;
+      if (i >= N) break;
+      int c;
+      if (Q != 0) {
+        const uint64_t U = uniform64_of(b, (uint32_t)h);
+        int g = (int)mulhi64(U, (uint64_t)ncells);
+        g = g < ncells - 1 ? g : ncells - 1;
+        c = mn_cell_of(mn.cellC, ncells, mulhi64(U, Q), g);
+      } else {
+        c = i / kMnCell;  // no mass at all: every particle is its own ancestor (SPEC §5)
+      }
+      if (in_smem) atomicAdd(&s_hist[c], 1);
+      else atomicAdd(&mn.K[c], 1);
+    }
+  }
+  __syncthreads();
+  if (in_smem)
+    for (int c = tid; c < ncells; c += kMnCountThreads) {
+      const int v = s_hist[c];
+      if (v) atomicAdd(&mn.K[c], v);
+    }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(mn.ticket, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  // ---- last CTA out: O = exclusive prefix of K, part_start = exclusive prefix of the work items per cell
+  __threadfence();
+  int run_k = 0, run_p = 0;
+  for (int c0 = 0; c0 < ncells; c0 += kMnCountThreads) {
+    const int c = c0 + tid;
+    const int k = c < ncells ? __ldcg(&mn.K[c]) : 0;
+    const int np = c < ncells ? (k > kMnChunk ? (k + kMnChunk - 1) / kMnChunk : 1) : 0;
+    int ik = k, ip = np;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int uk = __shfl_up_sync(kFullMask, ik, o), up = __shfl_up_sync(kFullMask, ip, o);
+      if (lane >= o) { ik += uk; ip += up; }
+    }
+    __syncthreads();
+    if (lane == 31) { s_wtot[warp] = ik; s_hist[warp] = ip; }  // (s_hist is free again; 8 entries always fit)
+    __syncthreads();
+    int wk = 0, wp = 0, tk = 0, tp = 0;
+#pragma unroll
+    for (int w = 0; w < kMnCountThreads / 32; ++w) {
+      const int a = s_wtot[w], b2 = s_hist[w];
+      if (w < warp) { wk += a; wp += b2; }
+      tk += a; tp += b2;
+    }
+    if (c < ncells) {
+      mn.O[c] = run_k + wk + ik - k;
+      mn.part_start[c] = run_p + wp + ip - np;
+    }
+    run_k += tk;
+    run_p += tp;
+  }
+  if (tid == 0) {
+    mn.part_start[ncells] = run_p;
+    *mn.ticket = 0u;
+  }
+}
+
+// level 2: one CTA per (cell, chunk of kMnChunk output positions)
+__global__ void __launch_bounds__(kMnCellThreads, 4)
+    mn_cell_kernel(MnIndex mn, StepIndex ix, const unsigned long long* __restrict__ cl, const FilterCtrl* __restrict__ ctrl, int N, RngKey key,
+                   uint32_t stream, uint32_t t, int32_t* __restrict__ anc) {
+  extern __shared__ __align__(16) unsigned char mn_smem[];
+  unsigned long long* s_c = reinterpret_cast<unsigned long long*>(mn_smem);     // [kMnCell] cell-local inclusive CDF
+  int* s_h = reinterpret_cast<int*>(mn_smem + sizeof(unsigned long long) * kMnCell);  // [kMnCell] offspring counts, then their inclusive prefix
+  __shared__ int s_w[kMnCellThreads / 32];
+  __shared__ int s_item[2];
+  constexpr int PER = kMnCell / kMnCellThreads;  // 8 consecutive particles per thread
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_launch_dependents();
+  pdl_wait();  // K, O, part_start come from mn_count_kernel
+  const int ncells = mn.ncells;
+  const int item = blockIdx.x;
+  if (item >= __ldg(&mn.part_start[ncells])) return;
+  if (tid == 0) {  // cell of this work item: the last c with part_start[c] <= item
+    int lo = 0, hi = ncells - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (__ldg(&mn.part_start[mid]) <= item) lo = mid;
+      else hi = mid - 1;
+    }
+    s_item[0] = lo;
+    s_item[1] = item - __ldg(&mn.part_start[lo]);
+  }
+  __syncthreads();
+  const int c = s_item[0], part = s_item[1];
+  const int Kc = __ldg(&mn.K[c]), Oc = __ldg(&mn.O[c]);
+  const int g0 = Oc + part * kMnChunk;
+  const int g1 = (Oc + Kc < g0 + kMnChunk) ? Oc + Kc : g0 + kMnChunk;
+  const int n_out = g1 - g0;
+  if (n_out <= 0) return;
+  const int j0 = c * kMnCell;
+  const int len = (N - j0 < kMnCell) ? N - j0 : kMnCell;
+  const uint64_t Q = ctrl->total;
+  if (Q == 0) {  // identity ancestors
+    for (int r = tid; r < n_out; r += kMnCellThreads) anc[g0 + r] = j0 + part * kMnChunk + r;
+    return;
+  }
+  const unsigned long long base = c ? __ldg(&mn.cellC[c - 1]) : 0ull;
+  const unsigned long long W = __ldg(&mn.cellC[c]) - base;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    const int j = k * kMnCellThreads + tid;
+    if (j < len) {
+      const int idx = j0 + j;
+      s_c[j] = __ldg(&ix.tile_excl[idx / ix.tile_items]) + __ldcs(&cl[idx]) - base;
+    }
+    s_h[j] = 0;
+  }
+  __syncthreads();
+  // in-cell thresholds: output position g draws V(g); pairs (2p, 2p+1) share one Philox block
+  for (int p = (g0 >> 1) + tid; 2 * p < g1; p += kMnCellThreads) {
+    const Philox4 b = philox4x32_10((uint32_t)p, stream, t, purpose_word(PURPOSE_RESAMPLE_CELL, 0, key.epoch), key);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int g = 2 * p + h;
+      if (g < g0 || g >= g1) continue;
+      const uint64_t tau = mulhi64(uniform64_of(b, (uint32_t)h), W);
+      int lo = 0, hi = len - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (s_c[mid] <= tau) lo = mid + 1;
+        else hi = mid;
+      }
+      atomicAdd(&s_h[lo], 1);
+    }
+  }
+  __syncthreads();
+  // inclusive prefix of the offspring counts (8 consecutive cells per thread, warp scan, warp totals)
+  int v[PER], tot = 0;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) {
+    tot += s_h[tid * PER + k];
+    v[k] = tot;
+  }
+  int inc = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int u = __shfl_up_sync(kFullMask, inc, o);
+    if (lane >= o) inc += u;
+  }
+  if (lane == 31) s_w[warp] = inc;
+  __syncthreads();
+  int woff = 0;
+#pragma unroll
+  for (int w = 0; w < kMnCellThreads / 32; ++w)
+    if (w < warp) woff += s_w[w];
+  const int off = woff + inc - tot;
+#pragma unroll
+  for (int k = 0; k < PER; ++k) s_h[tid * PER + k] = off + v[k];
+  __syncthreads();
+  // ancestors in ascending order: output r belongs to the first particle whose inclusive count exceeds r
+  for (int r = tid; r < n_out; r += kMnCellThreads) {
+    int lo = 0, hi = len - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (s_h[mid] <= r) lo = mid + 1;
+      else hi = mid;
+    }
+    anc[g0 + r] = j0 + lo;
+  }
+}
+
 // x_i ~ transition(x[a_i]); logw_i = logpdf(observation(x_i), y)   (particles.jl:119-125): a streaming
 // pass, kMovePairs pairs (4 consecutive particles) per thread for two independent Philox / Box-Muller
 // chains; parents gathered through the (sorted, hence near-coalesced) ancestor vector.
@@ -1354,8 +1617,8 @@ SingleFilter::~SingleFilter() {
 void SingleFilter::release() {
   cudaFree(x_[0]); cudaFree(x_[1]); cudaFree(logw_[0]); cudaFree(logw_[1]); cudaFree(w_tmp_); cudaFree(cdf_); cudaFree(anc_);
   cudaFree(ctrl_); cudaFree(desc_); cudaFree(psum_); cudaFree(psum2_); cudaFree(stats_dev_);
-  cudaFree(tile_arrays_); cudaFree(bound_arrays_); cudaFree(summary_dev_);
-  tile_arrays_ = nullptr; bound_arrays_ = nullptr; bound_cap_ = 0; summary_dev_ = nullptr; summary_cap_ = 0;
+  cudaFree(tile_arrays_); cudaFree(bound_arrays_); cudaFree(summary_dev_); cudaFree(mn_arrays_);
+  tile_arrays_ = nullptr; bound_arrays_ = nullptr; bound_cap_ = 0; summary_dev_ = nullptr; summary_cap_ = 0; mn_arrays_ = nullptr; mn_cap_ = 0;
   x_[0] = x_[1] = logw_[0] = logw_[1] = w_tmp_ = psum_ = psum2_ = nullptr;
   cdf_ = nullptr; anc_ = nullptr; ctrl_ = nullptr; desc_ = nullptr; stats_dev_ = nullptr;
   cap_N_ = cap_d_ = cap_stats_ = cap_anc_rows_ = ntiles_cap_ = 0;
@@ -1391,6 +1654,15 @@ void SingleFilter::ensure_capacity(int kind, int64_t N, int64_t anc_rows) {
       cudaFree(bound_arrays_); bound_arrays_ = nullptr; bound_cap_ = 0;
       SMCB_CUDA_TRY(cudaMalloc(&bound_arrays_, sizeof(int32_t) * 2 * nb));
       bound_cap_ = nb;
+    }
+  }
+  {
+    const int64_t nc = (cap_N_ + kMnCell - 1) / kMnCell + 1;
+    if (nc > mn_cap_) {  // cell index of the two-level multinomial resampler (allocated with the rest: 20 B per 4096 particles)
+      cudaFree(mn_arrays_); mn_arrays_ = nullptr; mn_cap_ = 0;
+      SMCB_CUDA_TRY(cudaMalloc(&mn_arrays_, (size_t)(sizeof(unsigned long long) * nc + sizeof(int32_t) * (3 * nc + 4))));
+      SMCB_CUDA_TRY(cudaMemsetAsync(mn_arrays_, 0, (size_t)(sizeof(unsigned long long) * nc + sizeof(int32_t) * (3 * nc + 4)), stream_));
+      mn_cap_ = nc;
     }
   }
   if (num_sms_ == 0) {
@@ -1579,13 +1851,13 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler, cons
   ProposalCoef pc{};
   if (proposal) {  // guided step (docs/SPEC.md §10): sorted resamplers, one-dimensional models
     if (d_ != 1) throw Error{SMCB_ERR_UNSUPPORTED, "guided proposals are defined for the one-dimensional models (LG1D, SV)"};
-    if (resampler == RESAMPLE_MULTINOMIAL)
-      throw Error{SMCB_ERR_UNSUPPORTED, "guided single filter: stratified or systematic resampling (multinomial guided filters run on the batched engine, N <= 8192)"};
+    if (legacy_multinomial(resampler))
+      throw Error{SMCB_ERR_UNSUPPORTED, "guided single filter with N <= 8192: stratified or systematic resampling (multinomial guided filters of that size run on the batched engine)"};
     if (!(proposal[2] > 0.0) || !std::isfinite(proposal[2]) || !std::isfinite(proposal[0]) || !std::isfinite(proposal[1]))
       throw Error{SMCB_ERR_BAD_ARG, "proposal: coefficients must be finite and the standard deviation c2 > 0"};
     pc.c[0] = proposal[0]; pc.c[1] = proposal[1]; pc.c[2] = proposal[2]; pc.c[3] = det_log(proposal[2]); pc.c[4] = 1.0 / proposal[2];
   }
-  if (resampler == RESAMPLE_MULTINOMIAL) {  // unsorted thresholds: materialised CDF + per-particle global search
+  if (legacy_multinomial(resampler)) {  // a small cloud: materialised CDF + per-particle search, unsorted ancestors (SPEC §5 row 0)
     launch_scan(stat_index, true);
     launch_prop(y, resampler);
     return;
@@ -1597,17 +1869,46 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler, cons
   const unsigned nblocks = (unsigned)((N_ + block_particles - 1) / block_particles);
   const uint32_t t = t_ + 1;
   const int nbounds = (int)nblocks + 1;
-  mark(TK_BOUNDS, true);
-  SMCB_CUDA_TRY(launch_pdl(bounds_kernel, dim3(((nbounds + 1) / 2 + 7) / 8), dim3(256), stream_, ix, cl, ctrl_, (int)N_, resampler, R_, key_,
-                           stream_id_, t, nbounds, block_particles));
-  mark(TK_BOUNDS, false);
-  SMCB_CUDA_TRY(cudaGetLastError());
   int32_t* anc = anc_;  // row 0 doubles as the scratch ancestor vector when nothing is recorded
   if (record_anc_) {
     const int64_t row = std::min<int64_t>(anc_rows_, cap_anc_rows_ - 1);
     anc = anc_ + row * cap_N_;
     anc_rows_ = row + 1;
   }
+  if (resampler == RESAMPLE_MULTINOMIAL) {  // large cloud: two-level multinomial draw (SPEC §5c), three launches
+    MnIndex mn;
+    mn.ncells = (int)((N_ + kMnCell - 1) / kMnCell);
+    mn.cellC = reinterpret_cast<unsigned long long*>(mn_arrays_);
+    mn.K = reinterpret_cast<int32_t*>(mn.cellC + mn_cap_);
+    mn.O = mn.K + mn_cap_;
+    mn.part_start = mn.O + mn_cap_;
+    mn.ticket = reinterpret_cast<unsigned int*>(mn.part_start + mn_cap_ + 1);
+    mark(TK_BOUNDS, true);
+    SMCB_CUDA_TRY(launch_pdl(mn_prep_kernel, dim3((mn.ncells + 255) / 256), dim3(256), stream_, mn, ix, cl, (int)N_));
+    const int64_t want = (N_ / 2 + kMnCountThreads * 8 - 1) / (kMnCountThreads * 8);  // >= 16 thresholds per thread
+    const unsigned cgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)num_sms_ * 4));
+    const size_t csmem = sizeof(int) * (size_t)std::max(mn.ncells <= kMnSmemCells ? mn.ncells : 0, 32);
+    SMCB_CUDA_TRY(launch_pdl_smem(mn_count_kernel, dim3(cgrid), dim3(kMnCountThreads), csmem, stream_, mn, (const FilterCtrl*)ctrl_, (int)N_, key_,
+                                  stream_id_, t));
+    mark(TK_BOUNDS, false);
+    SMCB_CUDA_TRY(cudaGetLastError());
+    const unsigned items = (unsigned)(mn.ncells + (N_ + kMnChunk - 1) / kMnChunk + 1);  // >= Σ_c max(1, ceil(K_c / kMnChunk))
+    mark(TK_ANC, true);
+    constexpr size_t kCellSmem = (sizeof(unsigned long long) + sizeof(int)) * kMnCell;  // 48 KB
+    if (!mn_attr_set_) {
+      SMCB_CUDA_TRY(cudaFuncSetAttribute(mn_cell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCellSmem));
+      mn_attr_set_ = true;
+    }
+    SMCB_CUDA_TRY(launch_pdl_smem(mn_cell_kernel, dim3(items), dim3(kMnCellThreads), kCellSmem, stream_, mn, ix, (const unsigned long long*)cl,
+                                  (const FilterCtrl*)ctrl_, (int)N_, key_, stream_id_, t, anc));
+    mark(TK_ANC, false);
+    SMCB_CUDA_TRY(cudaGetLastError());
+  } else {
+  mark(TK_BOUNDS, true);
+  SMCB_CUDA_TRY(launch_pdl(bounds_kernel, dim3(((nbounds + 1) / 2 + 7) / 8), dim3(256), stream_, ix, cl, ctrl_, (int)N_, resampler, R_, key_,
+                           stream_id_, t, nbounds, block_particles));
+  mark(TK_BOUNDS, false);
+  SMCB_CUDA_TRY(cudaGetLastError());
   mark(TK_ANC, true);
   if (resampler == RESAMPLE_SYSTEMATIC)
     SMCB_CUDA_TRY(launch_pdl(anc_hist_kernel<RESAMPLE_SYSTEMATIC>, dim3(nblocks), dim3(kSysThreads), stream_, (int)N_, R_, key_, stream_id_, t, ix, cl,
@@ -1617,6 +1918,7 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler, cons
                              anc, ctrl_, anc_eps_));
   mark(TK_ANC, false);
   SMCB_CUDA_TRY(cudaGetLastError());
+  }
   const unsigned mblocks = (unsigned)((N_ + kMoveThreads * 2 * kMovePairs - 1) / (kMoveThreads * 2 * kMovePairs));
   // LG1D: the new log-weights are two fma of the new states; they are not stored (sum_kernel and, when a caller asks
   // for them, logw_kernel recompute them bit for bit).  SV / UCSV weights cost an exp: stored as before.
@@ -1652,6 +1954,8 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler, cons
   sum_done_ = false;  // the parameters these weights were computed with (step() may be handed new ones)
 }
 
+bool SingleFilter::legacy_multinomial(int resampler) const { return resampler == RESAMPLE_MULTINOMIAL && N_ <= kMnLegacyMax; }
+
 static void check_args(int kind, int64_t N, int resampler) {
   if (kind < 0 || kind >= KIND_COUNT) throw Error{SMCB_ERR_BAD_ARG, "unknown model kind"};
   if (N < 1 || N > (int64_t(1) << 31) - 64) throw Error{SMCB_ERR_BAD_ARG, "N must be in [1, 2^31-64]"};
@@ -1684,13 +1988,13 @@ void SingleFilter::init(int kind, const double* params, int64_t N, double y0, co
 void SingleFilter::step(const double* params, double y, int resampler, StepStats* st, const double* proposal) {
   if (!live()) throw Error{SMCB_ERR_STATE, "bootstrap_step before bootstrap_init / log_likelihood"};
   check_args(kind_, N_, resampler);
-  if (prec_ && resampler == RESAMPLE_MULTINOMIAL) throw Error{SMCB_ERR_BAD_ARG, "binary32 states: sorted resamplers only (docs/SPEC.md §9)"};
+  if (prec_ && legacy_multinomial(resampler)) throw Error{SMCB_ERR_BAD_ARG, "binary32 states with N <= 8192: sorted resamplers only (docs/SPEC.md §9)"};
   SMCB_CUDA_TRY(cudaSetDevice(device_));
   if (params) derive_params(kind_, params, dv_.d);
   if (!record_anc_) anc_rows_ = 0;
   begin_call();
   launch_step(1, y, resampler, proposal);  // (the statistics of the old weights, if it has to recompute them, go to slot 1)
-  if (resampler == RESAMPLE_MULTINOMIAL) launch_scan(0, false);
+  if (legacy_multinomial(resampler)) launch_scan(0, false);
   else launch_sum(0);            // statistics of the new weights now; the next sorted step reuses everything else
   SMCB_CUDA_TRY(cudaMemcpyAsync(&last_, stats_dev_, sizeof(StepStats), cudaMemcpyDeviceToHost, stream_));
   end_call();
@@ -1700,7 +2004,7 @@ void SingleFilter::step(const double* params, double y, int resampler, StepStats
 void SingleFilter::run(int kind, const double* params, int64_t N, const double* y, int64_t T, int resampler,
                        const RngKey& key, uint32_t stream_id, StepStats* stats_out, const double* proposal) {
   check_args(kind, N, resampler);
-  if (next_prec_ && resampler == RESAMPLE_MULTINOMIAL) throw Error{SMCB_ERR_BAD_ARG, "binary32 states: sorted resamplers only (docs/SPEC.md §9)"};
+  if (next_prec_ && resampler == RESAMPLE_MULTINOMIAL && N <= kMnLegacyMax) throw Error{SMCB_ERR_BAD_ARG, "binary32 states with N <= 8192: sorted resamplers only (docs/SPEC.md §9)"};
   if (T < 1) throw Error{SMCB_ERR_BAD_ARG, "T must be >= 1"};
   SMCB_CUDA_TRY(cudaSetDevice(device_));
   N_ = 0;
@@ -1719,7 +2023,7 @@ void SingleFilter::run(int kind, const double* params, int64_t N, const double* 
   for (int64_t t = 1; t < T; ++t) {
     launch_step(t - 1, y[t], resampler, proposal ? proposal + 3 * t : nullptr);  // stats of time t-1, then the step to time t
   }
-  if (resampler == RESAMPLE_MULTINOMIAL) launch_scan(T - 1, false);
+  if (legacy_multinomial(resampler)) launch_scan(T - 1, false);
   else launch_sum(T - 1);
   std::vector<StepStats> tmp;
   SMCB_CUDA_TRY(cudaMemcpyAsync(stats_out, stats_dev_, sizeof(StepStats) * T, cudaMemcpyDeviceToHost, stream_));

@@ -95,6 +95,7 @@ class SingleFilter {
   void launch_scan(int64_t stat_index, bool write_cdf);
   void launch_sum(int64_t stat_index);
   unsigned long long* step_index(StepIndex& ix);
+  bool legacy_multinomial(int resampler) const;  // small clouds keep the per-particle search with unsorted ancestors (SPEC §5 row 0 vs §5c)
   void mark(int klass, bool start);
   void release();
 
@@ -128,6 +129,9 @@ class SingleFilter {
   unsigned long long* tile_arrays_ = nullptr;  // [5][kMaxTiles]: tot, excl, incl, lexcl, cta_tot
   unsigned long long* summary_dev_ = nullptr;  // scratch of summary(): block partials, radix-select prefixes / ranks / histograms
   size_t summary_cap_ = 0;
+  void* mn_arrays_ = nullptr;                  // cell index of the two-level multinomial resampler: cellC u64[cap], K, O i32[cap], part_start i32[cap + 1], ticket
+  int64_t mn_cap_ = 0;
+  bool mn_attr_set_ = false;
   int32_t* bound_arrays_ = nullptr;            // [2][bound_cap_]: ancestor of each propagate CTA's first particle, its tile
   int64_t bound_cap_ = 0;
   int num_sms_ = 0;

@@ -82,6 +82,47 @@ def test_above_2_pow_24_multi_trip_tiles(ctx, oracle):
     _compare_run(ctx, oracle, smc.KIND_LG1D, (1 << 24) + 4097, 3, smc.SYSTEMATIC)
 
 
+@pytest.mark.parametrize("kind,N,T", [(smc.KIND_LG1D, 8193, 6), (smc.KIND_SV, 12289 + 4096 * 3 + 17, 5), (smc.KIND_UCSV, (1 << 16) + 5, 4),
+                                      (smc.KIND_LG1D, (1 << 20) + 3, 4)])
+def test_two_level_multinomial_bit_exact(ctx, oracle, kind, N, T):
+    """SPEC §5c: the reference's multinomial law for clouds above 8192 particles (counts per 4096-particle cell, in-cell
+    thresholds, ascending chunks): ancestors of every step, states and log-weights bit for bit against the oracle."""
+    _compare_run(ctx, oracle, kind, N, T, smc.MULTINOMIAL, seed=17, epoch=N % 89)
+
+
+def test_two_level_multinomial_degenerate_weights(ctx, oracle):
+    """A sharp likelihood puts nearly all the mass on a few particles: a few cells receive almost every output (many chunks
+    per cell, most cells empty) — and the all-(-inf) cloud is its own ancestor."""
+    kind, N, T = smc.KIND_LG1D, (1 << 17) + 99, 5
+    y = _data(oracle, kind, T)
+    for R in (1e-6, 1e-10):
+        params = [0.5, 1.0, 0.9, R, 0.0, 1.0]
+        ref = oracle.log_likelihood(kind, params, N, y, smc.MULTINOMIAL, 3, 0, 0, want_anc=True)
+        ctx.set_rng(3, 0)
+        ctx.record_ancestors(True)
+        logZ, logmu, ess = ctx.log_likelihood(kind, params, N, y, smc.MULTINOMIAL, 0, per_step=True)
+        anc = ctx.fetch_ancestors(T - 1)
+        x, _, _ = ctx.fetch_state(want_w=False)
+        ctx.record_ancestors(False)
+        np.testing.assert_array_equal(anc, ref["anc"][1:])
+        np.testing.assert_array_equal(x, ref["x"])
+        np.testing.assert_allclose(logmu, ref["logmu"], rtol=RTOL)
+        assert ess.min() < 500
+    # the stepping API: multinomial steps between sorted ones at a size above the legacy limit, statistics after every step
+    N = 50000
+    ctx.set_rng(21, 1)
+    ctx.bootstrap_init(kind, MODELS[kind], N, y[0], stream=2)
+    xo, lwo = oracle.bootstrap_init(kind, MODELS[kind], N, y[0], 21, 1, 2)
+    for t, rs in zip(range(1, T), (smc.MULTINOMIAL, smc.SYSTEMATIC, smc.MULTINOMIAL, smc.MULTINOMIAL)):
+        lm, es = ctx.bootstrap_step(y[t], rs)
+        oracle.bootstrap_step(kind, MODELS[kind], xo, lwo, y[t], t, rs, 21, 1, 2)
+        lmo, _, eso = oracle.normalize(lwo)
+        assert abs(lm - lmo) <= RTOL * abs(lmo) and abs(es - eso) <= RTOL * eso
+    x, _, lw = ctx.fetch_state(want_w=False, want_logw=True)
+    np.testing.assert_array_equal(x, xo)
+    np.testing.assert_array_equal(lw, lwo)
+
+
 def test_degenerate_weights_window_fallback(ctx, oracle):
     """A sharp likelihood (tiny R) concentrates the weight on few particles, so some CTAs see CDF
     windows wider than the staging buffer and take the global-search path."""

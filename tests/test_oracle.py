@@ -109,6 +109,61 @@ def test_ancestors_c_vs_numpy(oracle, resampler):
     assert np.all(oracle.ancestors(lw, resampler, 1, 0, 0, 1) == 40)
 
 
+def test_two_level_multinomial_restatements_agree(oracle):
+    """SPEC §5c (multinomial for n > 8192): the C oracle against the independent numpy restatement, ragged sizes, a dead
+    stretch of weights (empty cells), one dominant particle (one cell takes almost every output: many chunks), no mass."""
+    rng = np.random.default_rng(7)
+    for n in (8193, 12289, 40000):
+        lw = rng.normal(size=n) * 2.0
+        if n == 12289:
+            lw[100:9000] = -800.0
+        if n == 40000:
+            lw[23456] = 25.0
+        a = oracle.ancestors(lw, 0, 5, 2, 1, 7)
+        np.testing.assert_array_equal(a, oracle.ancestors_numpy(lw, 0, 5, 2, 1, 7))
+        assert a.min() >= 0 and a.max() < n
+        cells = a // oracle.MN_CELL
+        assert np.all(np.diff(cells) >= 0)                              # cells in order
+        if n == 40000:
+            assert np.mean(a == 23456) > 0.9
+    lw = np.full(9000, -np.inf)
+    np.testing.assert_array_equal(oracle.ancestors(lw, 0, 1, 0, 0, 1), np.arange(9000))          # Q = 0
+    # n <= 8192 keeps SPEC §5 row 0 (unsorted, one search per particle)
+    a = oracle.ancestors(rng.normal(size=8192), 0, 5, 2, 1, 7)
+    assert np.any(np.diff(a) < 0)
+
+
+def test_two_level_multinomial_has_the_multinomial_law(oracle):
+    """The offspring counts of the two-level draw (SPEC §5c) are Multinomial(n, w) like those of the one-level draw (§5 row 0,
+    StatsBase `sample(1:n, Weights(w), n)`, particles.jl:18): z-scores and χ² of the pooled counts of the heaviest
+    particles against n·w, the count VARIANCE of single particles against n·w·(1 − w) (a low-variance scheme would fail
+    it), and a two-sample comparison with the one-level draw on the same weights."""
+    rng = np.random.default_rng(8)
+    n, reps = 10000, 60
+    lw = rng.normal(size=n) * 1.2
+    w = np.exp(lw - lw.max())
+    w /= w.sum()
+    top = np.argsort(w)[-200:]
+    c2 = np.stack([np.bincount(oracle.ancestors(lw, 0, 123, r, 0, 1), minlength=n)[top] for r in range(reps)])          # two-level
+    lw_pad = lw[:8192]                                                                                                   # one-level law on the largest legacy size
+    w_pad = np.exp(lw_pad - lw_pad.max())
+    w_pad /= w_pad.sum()
+    top1 = np.argsort(w_pad)[-200:]
+    c1 = np.stack([np.bincount(oracle.ancestors(lw_pad, 0, 123, r, 0, 1), minlength=8192)[top1] for r in range(reps)])
+    for c, ww, nn in ((c2, w[top], n), (c1, w_pad[top1], 8192)):
+        mean, var = nn * ww, nn * ww * (1 - ww)
+        z = (c.sum(axis=0) - reps * mean) / np.sqrt(reps * var)
+        assert np.abs(z).max() < 4.5 and abs(z.mean()) < 0.35
+        chi2 = float(np.sum(z * z))
+        assert 120 < chi2 < 290                                          # χ²(200): mean 200, sd 20
+        ratio = c.var(axis=0, ddof=1) / var                              # multinomial: ≈ 1 for every particle
+        assert 0.8 < ratio.mean() < 1.2
+    # two-sample: standardised counts of the two schemes have the same spread
+    s2 = ((c2 - n * w[top]) / np.sqrt(n * w[top] * (1 - w[top]))).ravel()
+    s1 = ((c1 - 8192 * w_pad[top1]) / np.sqrt(8192 * w_pad[top1] * (1 - w_pad[top1]))).ravel()
+    assert abs(s2.std() - s1.std()) < 0.05 and abs(s2.mean() - s1.mean()) < 0.05
+
+
 def test_resampler_is_unbiased(oracle):
     rng = np.random.default_rng(4)
     n = 256
