@@ -118,6 +118,18 @@ def uniforms64(seed, epoch, stream, t, kind, n):
     return out
 
 
+def uniforms32(seed, epoch, stream, t, kind, n):
+    """32-bit uniforms of docs/SPEC.md §5c: element i is word (i & 3) of the Philox block at index i >> 2.  Built on the 64-bit
+    stream: U64 of index 2q is (r0 << 32) | r1 of block q, of index 2q + 1 is (r2 << 32) | r3."""
+    u64 = uniforms64(seed, epoch, stream, t, kind, 2 * ((n + 3) // 4))
+    out = np.empty(4 * ((n + 3) // 4), np.uint32)
+    out[0::4] = (u64[0::2] >> np.uint64(32)).astype(np.uint32)
+    out[1::4] = (u64[0::2] & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    out[2::4] = (u64[1::2] >> np.uint64(32)).astype(np.uint32)
+    out[3::4] = (u64[1::2] & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    return out[:n]
+
+
 def uniforms01(seed, epoch, stream, t, kind, n):
     """(U64 >> 11) * 2^-53 in [0,1) — used by the host-level MH accept draw."""
     return (uniforms64(seed, epoch, stream, t, kind, n) >> np.uint64(11)).astype(np.float64) * 2.0 ** -53
@@ -167,9 +179,10 @@ def ancestors_numpy(logw, resampler, seed, epoch, stream, t):
         ncells = (n + MN_CELL - 1) // MN_CELL
         last = np.minimum((np.arange(ncells) + 1) * MN_CELL - 1, n - 1)
         cellC = Cs[last]
-        tau1 = np.array([(u * Q) >> 64 for u in U], dtype=np.uint64)
+        U32 = uniforms32(seed, epoch, stream, t, P_RESAMPLE, n)         # word (i & 3) of the Philox block at index i >> 2
+        tau1 = np.array([(int(u) * Q) >> 32 for u in U32], dtype=np.uint64)
         K = np.bincount(np.searchsorted(cellC, tau1, side="right"), minlength=ncells)
-        V = [int(v) for v in uniforms64(seed, epoch, stream, t, P_RESAMPLE_CELL, n)]
+        V = [int(v) for v in uniforms32(seed, epoch, stream, t, P_RESAMPLE_CELL, n)]
         O = 0
         for c in range(ncells):
             j0, j1 = c * MN_CELL, min((c + 1) * MN_CELL, n)
@@ -178,7 +191,7 @@ def ancestors_numpy(logw, resampler, seed, epoch, stream, t):
             loc = Cs[j0:j1] - np.uint64(base)
             for g0 in range(O, O + int(K[c]), MN_CHUNK):
                 g1 = min(g0 + MN_CHUNK, O + int(K[c]))
-                tau2 = np.array([(V[g] * W) >> 64 for g in range(g0, g1)], dtype=np.uint64)
+                tau2 = np.array([(V[g] * W) >> 32 for g in range(g0, g1)], dtype=np.uint64)
                 out[g0:g1] = np.sort(j0 + np.searchsorted(loc, tau2, side="right"))
             O += int(K[c])
         return out

@@ -152,13 +152,23 @@ static void ancestors_from_q(const uint64_t *q, int64_t n, int resampler, uint64
 
 /* SPEC §5c: multinomial resampling of a LARGE cloud (n > 8192) in two levels.  The reference draws n i.i.d. categorical
  * indices (particles.jl:18); their offspring counts are multinomial and the resampled particles exchangeable, so
- *   level 1: the n thresholds tau_i = mulhi(U(i), Q) are counted per cell of 4096 consecutive particles -> K_c;
- *   level 2: output position g of cell c (positions O_c .. O_c + K_c - 1, O = exclusive prefix of K) draws V(g) from a second
- *            Philox purpose and takes the in-cell ancestor  c*4096 + #{ j in cell : Cloc_j <= mulhi(V(g), W_c) };
+ *   level 1: the n thresholds tau_i = floor(U32(i) Q / 2^32) are counted per cell of 4096 consecutive particles -> K_c;
+ *   level 2: output position g of cell c (positions O_c .. O_c + K_c - 1, O = exclusive prefix of K) draws V32(g) from a second
+ *            Philox purpose and takes the in-cell ancestor  c*4096 + #{ j in cell : Cloc_j <= floor(V32(g) W_c / 2^32) };
+ *   (32-bit uniforms, four per Philox block: a threshold only has to pick one of 4096 cells / one of 4096 particles)
  *   order:   every chunk of 8192 consecutive output positions of a cell is written in ascending ancestor order. */
 #define MN_CELL 4096
 #define MN_CHUNK 8192
 #define MN_LEGACY_MAX 8192
+/* 32-bit uniform of SPEC §5c: word (i & 3) of the Philox block at index i >> 2; tau = floor(u * v / 2^32) */
+static uint32_t o_uniform32(uint64_t seed, uint32_t epoch, uint32_t i, uint32_t stream, uint32_t t, uint32_t purpose) {
+  uint32_t r[4];
+  uint32_t ctr[4] = {i >> 2, stream, t, (purpose << 24) | (epoch & 0xFFFFFFu)};
+  uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  o_philox(ctr, key, r);
+  return r[i & 3];
+}
+static uint64_t o_mul32(uint32_t u, uint64_t v) { return (uint64_t)(((unsigned __int128)u * v) >> 32); }
 static int cmp_i64(const void *a, const void *b) {
   int64_t x = *(const int64_t *)a, y = *(const int64_t *)b;
   return (x > y) - (x < y);
@@ -183,7 +193,7 @@ static void ancestors_two_level(const uint64_t *q, int64_t n, uint64_t seed, uin
     cellC[c] = C[last];
   }
   for (int64_t i = 0; i < n; ++i) {                      /* level 1 */
-    uint64_t tau = o_mulhi(o_uniform64(seed, epoch, (uint32_t)i, stream, t, P_RESAMPLE), Q);
+    uint64_t tau = o_mul32(o_uniform32(seed, epoch, (uint32_t)i, stream, t, P_RESAMPLE), Q);
     int64_t lo = 0, hi = ncells;                         /* c = #{c : cellC_c <= tau} */
     while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (cellC[mid] <= tau) lo = mid + 1; else hi = mid; }
     K[lo] += 1;
@@ -195,7 +205,7 @@ static void ancestors_two_level(const uint64_t *q, int64_t n, uint64_t seed, uin
     for (int64_t g0 = O; g0 < O + K[c]; g0 += MN_CHUNK) {
       int64_t g1 = (g0 + MN_CHUNK < O + K[c]) ? g0 + MN_CHUNK : O + K[c];
       for (int64_t g = g0; g < g1; ++g) {
-        uint64_t tau = o_mulhi(o_uniform64(seed, epoch, (uint32_t)g, stream, t, P_RESAMPLE_CELL), W);
+        uint64_t tau = o_mul32(o_uniform32(seed, epoch, (uint32_t)g, stream, t, P_RESAMPLE_CELL), W);
         int64_t lo = 0, hi = len;                        /* #{ j in cell : C_j - base <= tau } */
         while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (C[j0 + mid] - base <= tau) lo = mid + 1; else hi = mid; }
         anc[g] = j0 + lo;

@@ -770,6 +770,16 @@ void BatchFilter::launch(const IO& io, bool from_init, uint32_t t_begin, uint32_
   const int64_t npairs = (N_ + 1) / 2;
   int pairs = 2;
   if ((npairs + pairs - 1) / pairs > 1024) pairs = 4;
+  // Few θ-particles on this GPU (θ sharded over many GPUs: 512 θ / 8 GPUs = 64 CTAs on 148 SMs): every CTA has an SM to itself
+  // and the sweep time is the per-step dependent chain of ONE cloud — one pair per thread shortens it (N = 1024, T = 100:
+  // 4.25 against 5.77 µs per step for M <= 128, 6.7 against 7.1 at M = 256; from M = 512 on two pairs per thread win on
+  // throughput: profiles/r2_batch_occupancy_lg1024.jsonl).
+  if (num_sms_ == 0) {
+    int v = 0;
+    SMCB_CUDA_TRY(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device_));
+    num_sms_ = v > 0 ? v : 148;
+  }
+  if (pairs == 2 && npairs <= 1024 && M_ <= 2 * (int64_t)num_sms_) pairs = 1;
   if (const char* e = std::getenv("SMCB_BATCH_PAIRS")) {
     const int v = std::atoi(e);
     if ((v == 1 || v == 2 || v == 4) && (npairs + v - 1) / v <= 1024) pairs = v;

@@ -82,6 +82,7 @@ class BatchFilter {
   int device_;
   cudaStream_t stream_;
   int kind_, d_;
+  int num_sms_ = 0;
   int64_t M_, N_, ld_;
   int S_;
   uint64_t R_;

@@ -1033,7 +1033,7 @@ __global__ void __launch_bounds__(kSysThreads, 12)
 constexpr int kMnCell = 4096;
 constexpr int kMnChunk = 8192;
 constexpr int kMnLegacyMax = 8192;      // N <= this: per-particle search of the materialised CDF, unsorted ancestors (SPEC §5 row 0)
-constexpr int kMnCountThreads = 256;
+constexpr int kMnCountThreads = 512;
 constexpr int kMnSmemCells = 8192;      // cells whose counters fit a CTA's shared memory (N <= 2^25)
 constexpr int kMnCellThreads = 512;
 
@@ -1042,82 +1042,108 @@ struct MnIndex {
   int32_t* K;                 // [ncells] thresholds that fell into the cell
   int32_t* O;                 // [ncells] exclusive prefix of K: first output position of the cell
   int32_t* part_start;        // [ncells + 1] exclusive prefix of max(1, ceil(K_c / kMnChunk)): first work item of the cell
+  int32_t* lut;               // [kMnLutMax + 1] bucket of a threshold (its top bits) -> first cell whose boundary is not below the bucket
   unsigned int* ticket;       // last-CTA-out counter of mn_count_kernel
   int ncells;
 };
+constexpr int kMnLutBits = 13;
+constexpr int kMnLutMax = 1 << kMnLutBits;  // buckets of the level-1 lookup table
+constexpr int kMnHeavySpan = 24;  // lookup-table ranges at least this long are filled by the whole CTA
+constexpr int kMnHeavyCap = 96;
+constexpr int kMnSubBits = 12;
+constexpr int kMnSub = 1 << kMnSubBits;     // outputs per sub-pass of mn_cell_kernel = buckets of its counting sort
 
-// cellC[c] = C at the last particle of cell c, from the tile-local CDF and the tile offsets; K[c] = 0
-__global__ void mn_prep_kernel(MnIndex mn, StepIndex ix, const unsigned long long* __restrict__ cl, int N) {
+// floor(u * v / 2^32) for a 32-bit uniform u and v < 2^61 (exact: the two partial products fit 64 bits)
+__device__ __forceinline__ uint64_t mulhi32_64(uint32_t u, uint64_t v) {
+  return (uint64_t)u * (v >> 32) + (((uint64_t)u * (v & 0xFFFFFFFFull)) >> 32);
+}
+
+// number of low bits dropped so that (v >> shift) < 2^bits for every v <= vmax
+__device__ __forceinline__ int mn_shift(unsigned long long vmax, int bits) {
+  const int len = 64 - __clzll((long long)(vmax | 1ull));
+  return len > bits ? len - bits : 0;
+}
+
+// cellC[c] = C at the last particle of cell c (tile-local CDF + tile offset); K[c] = 0; and the level-1 lookup table:
+// lut[b] = #{ c : (cellC_c >> s) < b } — every one of those cells ends below any threshold of bucket b
+__global__ void mn_prep_kernel(MnIndex mn, StepIndex ix, const unsigned long long* __restrict__ cl, const FilterCtrl* __restrict__ ctrl, int N) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   pdl_launch_dependents();
-  pdl_wait();  // the tile-local CDF and the tile offsets come from sum_kernel
+  pdl_wait();  // the tile-local CDF, the tile offsets and Q come from sum_kernel
   if (c >= mn.ncells) return;
-  int64_t last = (int64_t)(c + 1) * kMnCell - 1;
-  if (last > N - 1) last = N - 1;
-  const int T = (int)(last / ix.tile_items);
-  mn.cellC[c] = __ldg(&ix.tile_excl[T]) + __ldg(&cl[last]);
+  auto cell_cdf = [&](int cc) -> unsigned long long {
+    int64_t last = (int64_t)(cc + 1) * kMnCell - 1;
+    if (last > N - 1) last = N - 1;
+    return __ldg(&ix.tile_excl[(int)(last / ix.tile_items)]) + __ldg(&cl[last]);
+  };
+  const unsigned long long C = cell_cdf(c);
+  mn.cellC[c] = C;
   mn.K[c] = 0;
+  const unsigned long long Q = ctrl->total;
+  if (Q == 0) return;
+  const int s = mn_shift(Q, kMnLutBits);
+  const int b_hi = (int)(C >> s);
+  const int b_lo = c ? (int)(cell_cdf(c - 1) >> s) + 1 : 0;
+  for (int b = b_lo; b <= b_hi; ++b) mn.lut[b] = c;
 }
 
-// #{ c : cellC[c] <= tau } starting from the interpolation guess g (cell masses are nearly equal unless the weights
-// are very uneven, so the answer is almost always within a cell or two of g); cellC[ncells - 1] = Q > tau
-__device__ __forceinline__ int mn_cell_of(const unsigned long long* __restrict__ cellC, int ncells, uint64_t tau, int g) {
-  int lo, hi;
-  if (__ldg(&cellC[g]) <= tau) {
-    lo = g + 1;
-    hi = g + 1;
-    int s = 1;
-    while (hi < ncells - 1 && __ldg(&cellC[hi]) <= tau) {
-      lo = hi + 1;
-      s <<= 1;
-      hi = hi + s < ncells - 1 ? hi + s : ncells - 1;
-    }
-  } else {
-    hi = g;
-    lo = g;
-    int s = 1;
-    while (lo > 0 && __ldg(&cellC[lo - 1]) > tau) {
-      hi = lo - 1;
-      s <<= 1;
-      lo = lo - s > 0 ? lo - s : 0;
-    }
-  }
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (__ldg(&cellC[mid]) <= tau) lo = mid + 1;
-    else hi = mid;
-  }
-  return lo;
+// idx / tile_items without an integer division: tile_items = 128 cpt, so the quotient is (idx >> 7) / cpt, estimated in binary32
+// (idx >> 7 < 2^24 is exact in a float) and corrected by at most one
+__device__ __forceinline__ int mn_tile_of(int idx, int cpt, float inv_cpt) {
+  const int x = idx >> 7;
+  int q = (int)((float)x * inv_cpt);
+  const int r = x - q * cpt;
+  q += (r >= cpt) ? 1 : 0;
+  q -= (r < 0) ? 1 : 0;
+  return q;
 }
 
-// level 1: K[c] = #{ i : tau_i in cell c }; the last CTA out turns K into output offsets and work items
+// level 1: K[c] = #{ i : tau_i in cell c }; the last CTA out turns K into output offsets and work items.
+// A threshold's cell is read off a lookup table indexed by its top bits (about two buckets per cell) and fixed by at most a step or
+// two through the cell boundaries; table, boundaries and counters all live in shared memory.
 __global__ void __launch_bounds__(kMnCountThreads)
     mn_count_kernel(MnIndex mn, const FilterCtrl* __restrict__ ctrl, int N, RngKey key, uint32_t stream, uint32_t t) {
-  extern __shared__ int s_hist[];  // [ncells] when ncells <= kMnSmemCells
-  __shared__ bool s_last;
-  __shared__ int s_wtot[kMnCountThreads / 32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  extern __shared__ __align__(16) unsigned char mn_cnt_smem[];
+  unsigned long long* s_cell = reinterpret_cast<unsigned long long*>(mn_cnt_smem);   // [ncells] when ncells <= kMnSmemCells
   const int ncells = mn.ncells;
   const bool in_smem = ncells <= kMnSmemCells;
+  int* s_lut = reinterpret_cast<int*>(mn_cnt_smem + (in_smem ? sizeof(unsigned long long) * (size_t)ncells : 0));  // [kMnLutMax + 1]
+  int* s_hist = s_lut + kMnLutMax + 1;                                                // [ncells] when ncells <= kMnSmemCells
+  __shared__ bool s_last;
+  __shared__ int s_wtot[2][kMnCountThreads / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (in_smem)
     for (int c = tid; c < ncells; c += kMnCountThreads) s_hist[c] = 0;
   pdl_launch_dependents();
-  pdl_wait();  // cellC, K = 0 come from mn_prep_kernel, Q from sum_kernel
+  pdl_wait();  // cellC, the lookup table and K = 0 come from mn_prep_kernel, Q from sum_kernel
   const uint64_t Q = ctrl->total;
+  const int s = mn_shift(Q, kMnLutBits);
+  if (Q != 0) {
+    const int nb = (int)(Q >> s) + 1;
+    for (int b = tid; b < nb; b += kMnCountThreads) s_lut[b] = __ldg(&mn.lut[b]);
+    if (in_smem)
+      for (int c = tid; c < ncells; c += kMnCountThreads) s_cell[c] = __ldg(&mn.cellC[c]);
+  }
   __syncthreads();
-  const int npairs = (N + 1) >> 1;
-  for (int p = blockIdx.x * kMnCountThreads + tid; p < npairs; p += gridDim.x * kMnCountThreads) {
+  const int nquads = (N + 3) >> 2;
+  for (int p = blockIdx.x * kMnCountThreads + tid; p < nquads; p += gridDim.x * kMnCountThreads) {
+    // SPEC §5c level 1: threshold i uses word (i & 3) of the Philox block at index i >> 2 (a 32-bit uniform is ample for a count per cell)
     const Philox4 b = philox4x32_10((uint32_t)p, stream, t, purpose_word(PURPOSE_RESAMPLE, 0, key.epoch), key);
+    const uint32_t u4[4] = {b.r0, b.r1, b.r2, b.r3};
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int i = 2 * p + h;
+    for (int h = 0; h < 4; ++h) {
+      const int i = 4 * p + h;
       if (i >= N) break;
       int c;
       if (Q != 0) {
-        const uint64_t U = uniform64_of(b, (uint32_t)h);
-        int g = (int)mulhi64(U, (uint64_t)ncells);
-        g = g < ncells - 1 ? g : ncells - 1;
-        c = mn_cell_of(mn.cellC, ncells, mulhi64(U, Q), g);
+        const uint64_t tau = mulhi32_64(u4[h], Q);
+        c = s_lut[(int)(tau >> s)];
+        // cells whose boundary shares the threshold's bucket (cellC[ncells - 1] = Q > tau ends the walk)
+        if (in_smem) {
+          while (s_cell[c] <= tau) ++c;
+        } else {
+          while (__ldg(&mn.cellC[c]) <= tau) ++c;
+        }
       } else {
         c = i / kMnCell;  // no mass at all: every particle is its own ancestor (SPEC §5)
       }
@@ -1126,11 +1152,16 @@ __global__ void __launch_bounds__(kMnCountThreads)
     }
   }
   __syncthreads();
-  if (in_smem)
-    for (int c = tid; c < ncells; c += kMnCountThreads) {
+  if (in_smem) {
+    // every CTA starts its flush at a different cell so that the CTAs do not queue up on the same counters
+    const int rot = (int)(((unsigned)blockIdx.x * 2654435761u) % (unsigned)ncells);
+    for (int k = tid; k < ncells; k += kMnCountThreads) {
+      int c = k + rot;
+      c -= (c >= ncells) ? ncells : 0;
       const int v = s_hist[c];
       if (v) atomicAdd(&mn.K[c], v);
     }
+  }
   __threadfence();
   __syncthreads();
   if (tid == 0) s_last = (atomicAdd(mn.ticket, 1u) == gridDim.x - 1);
@@ -1150,12 +1181,12 @@ __global__ void __launch_bounds__(kMnCountThreads)
       if (lane >= o) { ik += uk; ip += up; }
     }
     __syncthreads();
-    if (lane == 31) { s_wtot[warp] = ik; s_hist[warp] = ip; }  // (s_hist is free again; 8 entries always fit)
+    if (lane == 31) { s_wtot[0][warp] = ik; s_wtot[1][warp] = ip; }
     __syncthreads();
     int wk = 0, wp = 0, tk = 0, tp = 0;
 #pragma unroll
     for (int w = 0; w < kMnCountThreads / 32; ++w) {
-      const int a = s_wtot[w], b2 = s_hist[w];
+      const int a = s_wtot[0][w], b2 = s_wtot[1][w];
       if (w < warp) { wk += a; wp += b2; }
       tk += a; tp += b2;
     }
@@ -1172,34 +1203,49 @@ __global__ void __launch_bounds__(kMnCountThreads)
   }
 }
 
-// level 2: one CTA per (cell, chunk of kMnChunk output positions)
-__global__ void __launch_bounds__(kMnCellThreads, 4)
+// level 2: one CTA per (cell, chunk of kMnChunk output positions).  The cell-local CDF sits in shared memory together with a
+// lookup table over its top bits (about one bucket per particle): a threshold finds its particle with one table read and a step
+// or two along the CDF — no binary search — and bumps the particle's offspring counter.  The inclusive prefix R_j of the counters
+// then says that outputs R_{j-1} .. R_j - 1 belong to particle j: head flags + a max-scan write the chunk in ascending order.
+// Thread `tid` owns the 8 consecutive particles 8 tid .. 8 tid + 7 throughout.
+__global__ void __launch_bounds__(kMnCellThreads, 3)
     mn_cell_kernel(MnIndex mn, StepIndex ix, const unsigned long long* __restrict__ cl, const FilterCtrl* __restrict__ ctrl, int N, RngKey key,
                    uint32_t stream, uint32_t t, int32_t* __restrict__ anc) {
   extern __shared__ __align__(16) unsigned char mn_smem[];
-  unsigned long long* s_c = reinterpret_cast<unsigned long long*>(mn_smem);     // [kMnCell] cell-local inclusive CDF
-  int* s_h = reinterpret_cast<int*>(mn_smem + sizeof(unsigned long long) * kMnCell);  // [kMnCell] offspring counts, then their inclusive prefix
+  unsigned long long* s_c = reinterpret_cast<unsigned long long*>(mn_smem);             // [kMnCell] cell-local inclusive CDF
+  int* s_head = reinterpret_cast<int*>(mn_smem);                                        // [kMnChunk] (after the counting) head flags
+  int* s_lut = reinterpret_cast<int*>(mn_smem + sizeof(unsigned long long) * kMnCell);  // [kMnSub + 1]
+  int* s_hist = s_lut + kMnSub + 4;                                                     // [kMnCell] offspring counts (16-byte aligned)
   __shared__ int s_w[kMnCellThreads / 32];
   __shared__ int s_item[2];
-  constexpr int PER = kMnCell / kMnCellThreads;  // 8 consecutive particles per thread
+  __shared__ int s_nheavy;
+  __shared__ int s_heavy[kMnHeavyCap][3];
+  constexpr int PER = kMnCell / kMnCellThreads;  // 8 particles per thread
+  constexpr int NW = kMnCellThreads / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   pdl_launch_dependents();
   pdl_wait();  // K, O, part_start come from mn_count_kernel
   const int ncells = mn.ncells;
   const int item = blockIdx.x;
-  if (item >= __ldg(&mn.part_start[ncells])) return;
-  if (tid == 0) {  // cell of this work item: the last c with part_start[c] <= item
-    int lo = 0, hi = ncells - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi + 1) >> 1;
-      if (__ldg(&mn.part_start[mid]) <= item) lo = mid;
-      else hi = mid - 1;
+  int c = item, part = 0;
+  if (item >= ncells) {  // work items beyond the first chunk of every cell exist only when some K_c > kMnChunk
+    const int total = __ldg(&mn.part_start[ncells]);
+    if (item >= total) return;
+    const int want = item - ncells;  // the want-th extra chunk: cell c, part >= 1 with (part_start[c] - c) + part - 1 = want
+    if (tid == 0) {
+      int lo = 0, hi = ncells - 1;  // last c with (part_start[c] - c) <= want
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(&mn.part_start[mid]) - mid <= want) lo = mid;
+        else hi = mid - 1;
+      }
+      s_item[0] = lo;
+      s_item[1] = want - (__ldg(&mn.part_start[lo]) - lo) + 1;
     }
-    s_item[0] = lo;
-    s_item[1] = item - __ldg(&mn.part_start[lo]);
+    __syncthreads();
+    c = s_item[0];
+    part = s_item[1];
   }
-  __syncthreads();
-  const int c = s_item[0], part = s_item[1];
   const int Kc = __ldg(&mn.K[c]), Oc = __ldg(&mn.O[c]);
   const int g0 = Oc + part * kMnChunk;
   const int g1 = (Oc + Kc < g0 + kMnChunk) ? Oc + Kc : g0 + kMnChunk;
@@ -1214,66 +1260,162 @@ __global__ void __launch_bounds__(kMnCellThreads, 4)
   }
   const unsigned long long base = c ? __ldg(&mn.cellC[c - 1]) : 0ull;
   const unsigned long long W = __ldg(&mn.cellC[c]) - base;
+  const int s = mn_shift(W, kMnSubBits);
+  // ---- the cell-local CDF of this thread's 8 particles (past the end of a ragged cell: W, so that they own no threshold)
+  const int jf = tid * PER;
+  unsigned long long C[PER];
+  {
+    const int i_first = j0 + jf;                     // multiple of 8: the 8 entries never straddle more than one tile boundary
+    const int cpt = ix.tile_items >> 7;
+    const int T0 = mn_tile_of(i_first < N ? i_first : N - 1, cpt, 1.0f / (float)cpt);
+    const int tile_end = (T0 + 1) * ix.tile_items;
+    const unsigned long long e0 = __ldg(&ix.tile_excl[T0]) - base;
+    const unsigned long long e1 = (tile_end < i_first + PER && tile_end < N) ? __ldg(&ix.tile_excl[T0 + 1]) - base : e0;
+    if (jf + PER <= len) {
 #pragma unroll
-  for (int k = 0; k < PER; ++k) {
-    const int j = k * kMnCellThreads + tid;
-    if (j < len) {
-      const int idx = j0 + j;
-      s_c[j] = __ldg(&ix.tile_excl[idx / ix.tile_items]) + __ldcs(&cl[idx]) - base;
-    }
-    s_h[j] = 0;
-  }
-  __syncthreads();
-  // in-cell thresholds: output position g draws V(g); pairs (2p, 2p+1) share one Philox block
-  for (int p = (g0 >> 1) + tid; 2 * p < g1; p += kMnCellThreads) {
-    const Philox4 b = philox4x32_10((uint32_t)p, stream, t, purpose_word(PURPOSE_RESAMPLE_CELL, 0, key.epoch), key);
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int g = 2 * p + h;
-      if (g < g0 || g >= g1) continue;
-      const uint64_t tau = mulhi64(uniform64_of(b, (uint32_t)h), W);
-      int lo = 0, hi = len - 1;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (s_c[mid] <= tau) lo = mid + 1;
-        else hi = mid;
+      for (int k = 0; k < PER; k += 2) {
+        const ulonglong2 v = __ldcs(reinterpret_cast<const ulonglong2*>(cl + i_first + k));
+        C[k] = v.x + (i_first + k < tile_end ? e0 : e1);
+        C[k + 1] = v.y + (i_first + k + 1 < tile_end ? e0 : e1);
       }
-      atomicAdd(&s_h[lo], 1);
+    } else {
+#pragma unroll
+      for (int k = 0; k < PER; ++k) C[k] = (jf + k < len) ? __ldcs(&cl[i_first + k]) + (i_first + k < tile_end ? e0 : e1) : W;
+    }
+#pragma unroll
+    for (int k = 0; k < PER; k += 2) reinterpret_cast<ulonglong2*>(s_c)[(jf + k) >> 1] = make_ulonglong2(C[k], C[k + 1]);
+    reinterpret_cast<int4*>(s_hist)[2 * tid] = make_int4(0, 0, 0, 0);
+    reinterpret_cast<int4*>(s_hist)[2 * tid + 1] = make_int4(0, 0, 0, 0);
+  }
+  __syncthreads();
+  // ---- lookup table: lut[b] = #{ j : (C_j >> s) < b }; particle j writes the buckets (C_{j-1} >> s, C_j >> s] — about one each.
+  // A particle that holds a large share of the cell's mass spans many buckets: those ranges go to a short list that the
+  // whole CTA fills together, so that very uneven weights do not serialise the CTA behind one thread.
+  if (tid == 0) s_nheavy = 0;
+  __syncthreads();
+  if (jf < len) {
+    int b = jf ? (int)(s_c[jf - 1] >> s) + 1 : 0;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      if (jf + k < len) {
+        const int b_hi = (int)(C[k] >> s);
+        if (b_hi - b >= kMnHeavySpan) {
+          const int slot = atomicAdd(&s_nheavy, 1);
+          if (slot < kMnHeavyCap) {
+            s_heavy[slot][0] = b;
+            s_heavy[slot][1] = b_hi;
+            s_heavy[slot][2] = jf + k;
+            b = b_hi + 1;
+          }
+        }
+        for (; b <= b_hi; ++b) s_lut[b] = jf + k;
+      }
     }
   }
   __syncthreads();
-  // inclusive prefix of the offspring counts (8 consecutive cells per thread, warp scan, warp totals)
-  int v[PER], tot = 0;
-#pragma unroll
-  for (int k = 0; k < PER; ++k) {
-    tot += s_h[tid * PER + k];
-    v[k] = tot;
-  }
-  int inc = tot;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int u = __shfl_up_sync(kFullMask, inc, o);
-    if (lane >= o) inc += u;
-  }
-  if (lane == 31) s_w[warp] = inc;
-  __syncthreads();
-  int woff = 0;
-#pragma unroll
-  for (int w = 0; w < kMnCellThreads / 32; ++w)
-    if (w < warp) woff += s_w[w];
-  const int off = woff + inc - tot;
-#pragma unroll
-  for (int k = 0; k < PER; ++k) s_h[tid * PER + k] = off + v[k];
-  __syncthreads();
-  // ancestors in ascending order: output r belongs to the first particle whose inclusive count exceeds r
-  for (int r = tid; r < n_out; r += kMnCellThreads) {
-    int lo = 0, hi = len - 1;
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (s_h[mid] <= r) lo = mid + 1;
-      else hi = mid;
+  {
+    const int nh = s_nheavy < kMnHeavyCap ? s_nheavy : kMnHeavyCap;
+    for (int e = 0; e < nh; ++e) {
+      const int b_hi = s_heavy[e][1], j = s_heavy[e][2];
+      for (int b = s_heavy[e][0] + tid; b <= b_hi; b += kMnCellThreads) s_lut[b] = j;
     }
-    anc[g0 + r] = j0 + lo;
+    if (nh) __syncthreads();
+  }
+  // ---- in-cell thresholds (SPEC §5c level 2): output position g uses word (g & 3) of the Philox block at index g >> 2
+  for (int p = (g0 >> 2) + tid; 4 * p < g1; p += kMnCellThreads) {
+    const Philox4 blk = philox4x32_10((uint32_t)p, stream, t, purpose_word(PURPOSE_RESAMPLE_CELL, 0, key.epoch), key);
+    const uint32_t v4[4] = {blk.r0, blk.r1, blk.r2, blk.r3};
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      const int g = 4 * p + h;
+      if (g >= g0 && g < g1) {
+        const uint64_t tau = mulhi32_64(v4[h], W);
+        int j = s_lut[(int)(tau >> s)];
+        while (s_c[j] <= tau) ++j;  // (C of the cell's last particle = W > tau ends the walk)
+        atomicAdd(&s_hist[j], 1);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- R_j = inclusive prefix of the offspring counts
+  int R[PER], Rm1;
+  {
+    const int4 h0 = reinterpret_cast<const int4*>(s_hist)[2 * tid], h1 = reinterpret_cast<const int4*>(s_hist)[2 * tid + 1];
+    R[0] = h0.x; R[1] = R[0] + h0.y; R[2] = R[1] + h0.z; R[3] = R[2] + h0.w;
+    R[4] = R[3] + h1.x; R[5] = R[4] + h1.y; R[6] = R[5] + h1.z; R[7] = R[6] + h1.w;
+    int inc = R[7];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(kFullMask, inc, o);
+      if (lane >= o) inc += u;
+    }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    int woff = 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+      if (w < warp) woff += s_w[w];
+    Rm1 = woff + inc - R[7];
+#pragma unroll
+    for (int k = 0; k < PER; ++k) R[k] += Rm1;
+  }
+  // ---- head flags (they reuse the CDF's shared memory: every thread is past the counting) and the max-scan
+  for (int r = tid; r < n_out; r += kMnCellThreads) s_head[r] = 0;
+  __syncthreads();
+  {
+    int prev = Rm1;
+#pragma unroll
+    for (int k = 0; k < PER; ++k) {
+      if (R[k] > prev) s_head[prev] = jf + k;
+      prev = R[k];
+    }
+  }
+  __syncthreads();
+  {
+    constexpr int OUT = kMnChunk / kMnCellThreads;  // 16 consecutive outputs per thread
+    const int r0 = tid * OUT;
+    int v[OUT], run = 0;
+    if (r0 < n_out) {
+#pragma unroll
+      for (int q = 0; q < OUT / 4; ++q) {
+        const int4 hv = reinterpret_cast<const int4*>(s_head)[tid * (OUT / 4) + q];  // (entries past n_out may hold stale CDF bits: masked)
+        const int e[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int val = (r0 + 4 * q + k < n_out) ? e[k] : 0;
+          run = val > run ? val : run;
+          v[4 * q + k] = run;
+        }
+      }
+    }
+    int inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(kFullMask, inc, o);
+      if (lane >= o) inc = u > inc ? u : inc;
+    }
+    const int wprev = __shfl_up_sync(kFullMask, inc, 1);
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    int carry = lane ? wprev : 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+      if (w < warp) carry = s_w[w] > carry ? s_w[w] : carry;
+    if (r0 + OUT <= n_out && ((g0 + r0) & 3) == 0) {
+#pragma unroll
+      for (int q = 0; q < OUT / 4; ++q) {
+        int4 o4;
+        o4.x = j0 + (v[4 * q] > carry ? v[4 * q] : carry);
+        o4.y = j0 + (v[4 * q + 1] > carry ? v[4 * q + 1] : carry);
+        o4.z = j0 + (v[4 * q + 2] > carry ? v[4 * q + 2] : carry);
+        o4.w = j0 + (v[4 * q + 3] > carry ? v[4 * q + 3] : carry);
+        *reinterpret_cast<int4*>(anc + g0 + r0 + 4 * q) = o4;
+      }
+    } else if (r0 < n_out) {
+#pragma unroll
+      for (int k = 0; k < OUT; ++k)
+        if (r0 + k < n_out) anc[g0 + r0 + k] = j0 + (v[k] > carry ? v[k] : carry);
+    }
   }
 }
 
@@ -1660,8 +1802,9 @@ void SingleFilter::ensure_capacity(int kind, int64_t N, int64_t anc_rows) {
     const int64_t nc = (cap_N_ + kMnCell - 1) / kMnCell + 1;
     if (nc > mn_cap_) {  // cell index of the two-level multinomial resampler (allocated with the rest: 20 B per 4096 particles)
       cudaFree(mn_arrays_); mn_arrays_ = nullptr; mn_cap_ = 0;
-      SMCB_CUDA_TRY(cudaMalloc(&mn_arrays_, (size_t)(sizeof(unsigned long long) * nc + sizeof(int32_t) * (3 * nc + 4))));
-      SMCB_CUDA_TRY(cudaMemsetAsync(mn_arrays_, 0, (size_t)(sizeof(unsigned long long) * nc + sizeof(int32_t) * (3 * nc + 4)), stream_));
+      const size_t bytes = (size_t)(sizeof(unsigned long long) * nc + sizeof(int32_t) * (3 * nc + 8 + (1 << 13) + 1));
+      SMCB_CUDA_TRY(cudaMalloc(&mn_arrays_, bytes));
+      SMCB_CUDA_TRY(cudaMemsetAsync(mn_arrays_, 0, bytes, stream_));
       mn_cap_ = nc;
     }
   }
@@ -1882,19 +2025,24 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler, cons
     mn.K = reinterpret_cast<int32_t*>(mn.cellC + mn_cap_);
     mn.O = mn.K + mn_cap_;
     mn.part_start = mn.O + mn_cap_;
-    mn.ticket = reinterpret_cast<unsigned int*>(mn.part_start + mn_cap_ + 1);
+    mn.lut = mn.part_start + mn_cap_ + 1;
+    mn.ticket = reinterpret_cast<unsigned int*>(mn.lut + kMnLutMax + 1);
     mark(TK_BOUNDS, true);
-    SMCB_CUDA_TRY(launch_pdl(mn_prep_kernel, dim3((mn.ncells + 255) / 256), dim3(256), stream_, mn, ix, cl, (int)N_));
-    const int64_t want = (N_ / 2 + kMnCountThreads * 8 - 1) / (kMnCountThreads * 8);  // >= 16 thresholds per thread
-    const unsigned cgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)num_sms_ * 4));
-    const size_t csmem = sizeof(int) * (size_t)std::max(mn.ncells <= kMnSmemCells ? mn.ncells : 0, 32);
+    SMCB_CUDA_TRY(launch_pdl(mn_prep_kernel, dim3((mn.ncells + 255) / 256), dim3(256), stream_, mn, ix, (const unsigned long long*)cl,
+                             (const FilterCtrl*)ctrl_, (int)N_));
+    const int64_t want = (N_ / 4 + kMnCountThreads * 4 - 1) / (kMnCountThreads * 4);  // >= 16 thresholds per thread
+    const unsigned cgrid = (unsigned)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)num_sms_ * 2));
+    const size_t csmem = sizeof(int) * (size_t)(kMnLutMax + 1) + (mn.ncells <= kMnSmemCells ? (sizeof(int) + sizeof(unsigned long long)) * (size_t)mn.ncells : 0);
+    if (!mn_attr_set_)
+      SMCB_CUDA_TRY(cudaFuncSetAttribute(mn_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)(sizeof(int) * (kMnLutMax + 1) + (sizeof(int) + sizeof(unsigned long long)) * kMnSmemCells)));
     SMCB_CUDA_TRY(launch_pdl_smem(mn_count_kernel, dim3(cgrid), dim3(kMnCountThreads), csmem, stream_, mn, (const FilterCtrl*)ctrl_, (int)N_, key_,
                                   stream_id_, t));
     mark(TK_BOUNDS, false);
     SMCB_CUDA_TRY(cudaGetLastError());
     const unsigned items = (unsigned)(mn.ncells + (N_ + kMnChunk - 1) / kMnChunk + 1);  // >= Σ_c max(1, ceil(K_c / kMnChunk))
     mark(TK_ANC, true);
-    constexpr size_t kCellSmem = (sizeof(unsigned long long) + sizeof(int)) * kMnCell;  // 48 KB
+    constexpr size_t kCellSmem = sizeof(unsigned long long) * kMnCell + sizeof(int) * (kMnSub + 4 + kMnCell);  // 64 KB: CDF (later the head flags) + table + counters
     if (!mn_attr_set_) {
       SMCB_CUDA_TRY(cudaFuncSetAttribute(mn_cell_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kCellSmem));
       mn_attr_set_ = true;

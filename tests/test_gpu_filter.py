@@ -443,8 +443,14 @@ def test_f32_state_tier(ctx, oracle, kind):
             ctx.bootstrap_step(y[t], smc.SYSTEMATIC)
         xs, _, _ = ctx.fetch_state(want_w=False)
         np.testing.assert_array_equal(xs, ref["x"])
-        with pytest.raises(smc.SMCBError):
-            ctx.bootstrap_step(y[1], smc.MULTINOMIAL)
+        # multinomial in this tier: the two-level draw of SPEC §5c (N > 8192) shares the sorted path's kernels and works; the
+        # per-particle search of small clouds does not exist in binary32 and is refused
+        with oracle.state_f32():
+            refm = oracle.log_likelihood(kind, MODELS[kind], 70001, y, smc.MULTINOMIAL, 13, 3, 1)
+        ctx.set_rng(13, 3)
+        ctx.log_likelihood(kind, MODELS[kind], 70001, y, smc.MULTINOMIAL, stream=1)
+        xm, _, _ = ctx.fetch_state(want_w=False)
+        np.testing.assert_array_equal(xm, refm["x"])
         with pytest.raises(smc.SMCBError):
             ctx.log_likelihood(kind, MODELS[kind], 1024, y, smc.MULTINOMIAL)
     finally:

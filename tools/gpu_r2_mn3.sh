@@ -1,0 +1,27 @@
+#!/bin/bash
+set -x
+python -m pytest tests/test_gpu_filter.py -m gpu -x -q -k "two_level or ragged or medium or mixed or after_sorted or f32" 2>&1 | tail -8
+python - <<'PY'
+import json, numpy as np, sequential_monte_carlo_b200 as smc
+ctx = smc.Context(0, 1998)
+P = [0.5, 1.0, 0.9, 0.8, 0.0, 1.0]
+y = smc._lib.simulate(0, P, 60, 1998)[1]
+for logn in (20, 22, 24):
+    N = 1 << logn
+    for rs, name in ((smc.SYSTEMATIC, "systematic"), (smc.MULTINOMIAL, "multinomial")):
+        ctx.log_likelihood(0, P, N, y, rs)
+        ctx.set_profiling(True)
+        ctx.log_likelihood(0, P, N, y, rs)
+        ms, n = ctx.timing()
+        ctx.set_profiling(False)
+        ctx.log_likelihood(0, P, N, y, rs)
+        tot = ctx.timing()[0]["total"]
+        print(json.dumps({"logn": logn, "resampler": name, "us_per_step": 1e3 * tot / 60, "Gpups": N * 60 / tot / 1e6,
+                          "per_launch_us": {k: round(1e3 * ms[k] / max(n[k], 1), 1) for k in ("scan", "bounds", "anc", "prop")}}), flush=True)
+# degenerate weights: sharp likelihood
+for R in (1e-4, 1e-8):
+    Pd = [0.5, 1.0, 0.9, R, 0.0, 1.0]
+    ctx.log_likelihood(0, Pd, 1 << 24, y[:20], smc.MULTINOMIAL)
+    z, lm, es = ctx.log_likelihood(0, Pd, 1 << 24, y[:20], smc.MULTINOMIAL, per_step=True)
+    print(json.dumps({"R": R, "multinomial_us_per_step": 1e3 * ctx.timing()[0]["total"] / 20, "ess_min": float(es.min())}))
+PY
