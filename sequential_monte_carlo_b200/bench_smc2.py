@@ -93,7 +93,7 @@ def run_config(name, ctx, comm, rank, world, steps=1, warmup=1, resampler="syste
     wall = float(np.mean(walls))
     out.update({
         "workload": cfg["name"] + f", {resampler} inner resampling, θ sharded over {world} GPU(s)", "config": name, "algo": cfg["algo"],
-        "N": cfg["N"], "M": cfg["M"], "T": cfg["T"], "scaling": "strong", "runs_timed": n, "wall_s": wall, "device_span_s": 1e-3 * float(np.mean(spans)),
+        "N": cfg["N"], "M": cfg["M"], "T": cfg["T"], "scaling": "strong", "runs_timed": n, "wall_s": wall, "wall_s_min": float(np.min(walls)), "device_span_s": 1e-3 * float(np.mean(spans)),
         "particle_updates_local": pu_local, "bytes_per_update": cfg["bytes_per_update"],
         "s_per_plain_step": float(np.mean(plains)) if plains else None, "s_per_rejuvenation_step": float(np.mean(rejuvs)) if rejuvs else None,
         "rejuvenations": stats_sum["rejuvenations"] // n, "sweeps": stats_sum["sweeps"] // n, "clouds_received_this_rank": stats_sum["clouds_moved"] // n,
