@@ -8,7 +8,9 @@
 #   normalize, resample, bootstrap_filter, bootstrap_filter!, log_likelihood      src/particles.jl
 #   StateSpaceModel, LinearModel, UnivariateLinearGaussian, LinearGaussian, unobserved_components,
 #   UC, UCSV, StochasticVolatility, simulate                                      src/state_space_models.jl
-#   SMC, smc², smc²!, density_tempered, expected_parameters                       src/smc_samplers.jl
+#   SMC, smc², smc²!, density_tempered, expected_parameters (exchange! included;   src/smc_samplers.jl
+#     the whole θ level runs on the GPU(s) behind smcb_sampler_*; comm_init! shards θ over one process per GPU)
+#   IBIS + smc², smc²!                                                            src/ibis.jl
 #   kalman_filter, log_likelihood(y, model)  (scalar and matrix methods)          src/kalman_filter.jl
 #   particle_filter, particle_filter!  (guided: affine-Gaussian proposals, docs/SPEC.md §10)   src/particles.jl:28-84
 #   MultivariateLinearGaussian, hodrick_prescott  (Kalman filter only)            src/state_space_models.jl:137-202
@@ -18,7 +20,7 @@ using Distributions, LinearAlgebra, Printf, Statistics
 
 export StateSpaceModel, LinearModel, UnivariateLinearGaussian, LinearGaussian, unobserved_components, UC, UCSV,
        StochasticVolatility, simulate, transition, observation, initial_dist, normalize, resample, bootstrap_filter, bootstrap_filter!, log_likelihood,
-       SMC, smc², smc²!, density_tempered, expected_parameters, kalman_filter,
+       SMC, IBIS, smc², smc²!, density_tempered, expected_parameters, kalman_filter, comm_unique_id, comm_init!,
        particle_filter, particle_filter!, AffineGaussianProposal, locally_optimal_proposal,
        MultivariateLinearModel, MultivariateLinearGaussian, hodrick_prescott, state_variances
 
@@ -198,50 +200,114 @@ function log_likelihood(y::Vector{Float64}, model::MultivariateLinearModel; ctx=
 end
 
 # ---------------------------------------------------------------- smc_samplers.jl
-mutable struct Batch
-    h::Ptr{Cvoid}; ctx::Context
-    function Batch(ctx, kind, M, N)
-        ref = Ref{Ptr{Cvoid}}(C_NULL)
-        check(ctx, ccall((:smcb_batch_create, LIB), Cint, (Ptr{Cvoid}, Cint, Int64, Int64, Ref{Ptr{Cvoid}}), ctx.h, kind, M, N, ref))
-        b = new(ref[], ctx); finalizer(b -> ccall((:smcb_batch_destroy, LIB), Cint, (Ptr{Cvoid},), b.h), b)
+# The sampler lives on the GPU(s): θ, ω, logZ, the log-prior and the parameter blocks of all M θ-particles are device arrays
+# behind ONE handle (smcb_sampler, include/smcb200.h); smc², smc²!, density_tempered are one ccall each and the public fields of
+# the reference's struct (θ, ω, logZ, ess, N, acc_ratio, x, w  — smc_samplers.jl:5-27) are read back when somebody looks at them.
+mutable struct Batch                  # M filters of N particles; also the view of a sampler's live clouds
+    h::Ptr{Cvoid}; ctx::Context; owned::Bool
+end
+function Batch(ctx::Context, kind, M, N)
+    ref = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ctx, ccall((:smcb_batch_create, LIB), Cint, (Ptr{Cvoid}, Cint, Int64, Int64, Ref{Ptr{Cvoid}}), ctx.h, kind, M, N, ref))
+    finalizer(b -> b.owned && ccall((:smcb_batch_destroy, LIB), Cint, (Ptr{Cvoid},), b.h), Batch(ref[], ctx, true))
+end
+
+# smcb_sampler_config (include/smcb200.h); isbits, passed by reference
+struct SamplerConfig
+    kind::Int32; d_theta::Int32; N::Int64; M::Int64; chain::Int32; resampler::Int32; theta_resampler::Int32; reserved::Int32
+    ess_threshold::Float64; min_ar::Float64; seed::UInt64
+    prior::NTuple{64,Float64}; map_src::NTuple{8,Int32}; map_const::NTuple{8,Float64}
+end
+
+# product of univariate priors -> rows (family, p0, p1, lo, hi, c0, c1, 0) of the device prior table (README.md:81-85)
+prior_row(d::Normal) = (0.0, d.μ, d.σ, 0.0, 0.0, log(d.σ), 0.0, 0.0)
+prior_row(d::LogNormal) = (1.0, d.μ, d.σ, 0.0, 0.0, log(d.σ), 0.0, 0.0)
+prior_row(d::Uniform) = (2.0, 0.0, 0.0, d.a, d.b, -log(d.b - d.a), 0.0, 0.0)
+prior_row(d::Truncated{<:Normal}) = (3.0, d.untruncated.μ, d.untruncated.σ, d.lower, d.upper, log(d.untruncated.σ), d.logtp, 0.0)
+components(p::Product) = p.v
+components(p::UnivariateDistribution) = [p]
+
+# model(θ) as a selection map: params[k] = θ[src[k]] or a constant — found by probing the closure on prior draws; every
+# model closure of the reference's README / example (lg_mod, uc_mod, ucsv_mod) is of this form
+function parameter_map(model, prior)
+    Θ = [collect(rand(prior)) for _ in 1:6]; P = [params8(model(θ)) for θ in Θ]
+    src = fill(Int32(-1), 8); cst = zeros(8)
+    for k in 1:8
+        col = [p[k] for p in P]
+        j = findfirst(j -> all(Θ[i][j] == col[i] for i in 1:6), 1:length(Θ[1]))
+        if j !== nothing; src[k] = j - 1
+        elseif all(==(col[1]), col); cst[k] = col[1]
+        else error("model(θ) must select components of θ and constants into the model's parameters (device-resident sampler)") end
     end
+    return kind(model(Θ[1])), src, cst
 end
 
-mutable struct SMC{SSM,KT}                                                                     # :5-27
-    θ::Vector{Vector{Float64}}; ω::Vector{Float64}
-    ess::Float64; ess_min::Float64; N::Int64; M::Int64; chain::Int64; logZ::Vector{Float64}
-    model::SSM; prior::Sampleable; kernel::KT; acc_threshold::Float64; acc_ratio::Float64
-    ctx::Context; cur::Batch; prop::Union{Nothing,Batch}; epoch::UInt32; nres::UInt32; nrej::UInt32; resampler::Cint
+mutable struct SMC{SSM}                                                                        # :5-27
+    h::Ptr{Cvoid}; ctx::Context; model::SSM; prior::Sampleable; M::Int64; chain::Int64; ess_min::Float64; acc_threshold::Float64
+    d::Int; y::Vector{Float64}; schedule::Vector{Tuple{Float64,Float64}}; kernel::Function
 end
-params(smc, θ) = reduce(hcat, [params8(smc.model(th)) for th in θ])                            # [8,M] col-major == C [M][8]
-next_epoch!(smc) = (set_rng!(smc.ctx, smc.ctx.seed, smc.epoch); smc.epoch += 1)
-
 function SMC(N::Int64, M::Int64, model, prior::Sampleable, chain::Int64, ess_threshold::Float64, min_ar::Float64=-1.0;
-             ctx=context(), resampler=MULTINOMIAL)                                             # :29-59
-    θ = map(m -> collect(rand(prior)), 1:M)
-    cur = Batch(ctx, kind(model(θ[1])), M, N)
-    SMC(θ, fill(1 / M, M), 1.0 * M, M * ess_threshold, N, M, chain, zeros(M), model, prior, random_walk_kernel, min_ar, 0.0,
-        ctx, cur, nothing, UInt32(1), UInt32(0), UInt32(0), resampler)
+             ctx=context(), resampler=MULTINOMIAL, theta_resampler=MULTINOMIAL)                # :29-59
+    θ0 = [collect(rand(prior)) for _ in 1:M]; d = length(θ0[1])                                # θ = map(m -> rand(prior), 1:M)   :38
+    k, src, cst = parameter_map(model, prior)
+    rows = vcat([collect(prior_row(c)) for c in components(prior)]..., zeros(8 * (8 - d)))
+    cfg = SamplerConfig(k, d, N, M, chain, resampler, theta_resampler, 0, ess_threshold, min_ar, ctx.seed, Tuple(rows), Tuple(src), Tuple(cst))
+    ref = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ctx, ccall((:smcb_sampler_create, LIB), Cint, (Ptr{Cvoid}, Ref{SamplerConfig}, Ptr{Float64}, Ref{Ptr{Cvoid}}),
+                     ctx.h, Ref(cfg), reduce(hcat, θ0), ref))                                   # [d,M] col-major == C [M][d]
+    smc = SMC(ref[], ctx, model, prior, M, chain, M * ess_threshold, min_ar, d, Float64[], Tuple{Float64,Float64}[], random_walk_kernel)
+    finalizer(s -> ccall((:smcb_sampler_destroy, LIB), Cint, (Ptr{Cvoid},), s.h), smc)
 end
-x(smc::SMC) = (a = Array{Float64}(undef, smc.N, statedim(smc.model(smc.θ[1])), smc.M);
-               check(smc.ctx, ccall((:smcb_batch_fetch, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), smc.cur.h, a, C_NULL, C_NULL)); a)
-w(smc::SMC) = (a = Matrix{Float64}(undef, smc.N, smc.M);
-               check(smc.ctx, ccall((:smcb_batch_fetch, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), smc.cur.h, C_NULL, a, C_NULL)); a)
+function sampler_get(smc::SMC)
+    θ = Matrix{Float64}(undef, smc.d, smc.M); ω = Vector{Float64}(undef, smc.M); z = similar(ω)
+    ess = Ref(0.0); ar = Ref(0.0); N = Ref{Int64}(0)
+    check(smc.ctx, ccall((:smcb_sampler_get, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ref{Float64}, Ref{Float64}, Ref{Int64}),
+                         smc.h, θ, ω, z, ess, ar, N))
+    return (θ=[θ[:, m] for m in 1:smc.M], ω=ω, logZ=z, ess=ess[], acc_ratio=ar[], N=N[])
+end
+function clouds(smc::SMC)                                                                      # smc.x, smc.w live here
+    ref = Ref{Ptr{Cvoid}}(C_NULL)
+    check(smc.ctx, ccall((:smcb_sampler_clouds, LIB), Cint, (Ptr{Cvoid}, Ref{Ptr{Cvoid}}), smc.h, ref))
+    Batch(ref[], smc.ctx, false)
+end
+function Base.getproperty(smc::SMC, f::Symbol)                                                 # the struct's public fields
+    f in (:θ, :ω, :logZ, :ess, :acc_ratio, :N) && return getfield(sampler_get(smc), f)
+    f === :x && return fetch_x(clouds(smc), smc)
+    f === :w && return fetch_w(clouds(smc), smc)
+    return getfield(smc, f)
+end
+statedim(smc::SMC) = statedim(smc.model(sampler_get(smc).θ[1]))
+fetch_x(b::Batch, smc) = (a = Array{Float64}(undef, sampler_get(smc).N, statedim(smc), smc.M);
+    check(smc.ctx, ccall((:smcb_batch_fetch, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), b.h, a, C_NULL, C_NULL)); a)
+fetch_w(b::Batch, smc) = (a = Matrix{Float64}(undef, sampler_get(smc).N, smc.M);
+    check(smc.ctx, ccall((:smcb_batch_fetch, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), b.h, C_NULL, a, C_NULL)); a)
+function set_data!(smc::SMC, y::Vector{Float64})
+    y == getfield(smc, :y) && return
+    check(smc.ctx, ccall((:smcb_sampler_set_data, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), smc.h, y, length(y)))
+    setfield!(smc, :y, copy(y))
+end
 
 # quantile(smc.x[i], weights(smc.w[i]), p) for every θ-particle at once (examples/inflation_example.jl:44,250): [np, d, M]
 function state_quantiles(smc::SMC, p::Vector{Float64}; weighted::Bool=true)
-    q = Array{Float64}(undef, length(p), statedim(smc.model(smc.θ[1])), smc.M)
+    q = Array{Float64}(undef, length(p), statedim(smc), smc.M)
     check(smc.ctx, ccall((:smcb_batch_weighted_quantiles, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint, Cint, Ptr{Float64}),
-                         smc.cur.h, p, length(p), weighted ? 1 : 0, q))
+                         clouds(smc).h, p, length(p), weighted ? 1 : 0, q))
     q
 end
-
 # mean(smc.x[i], weights(smc.w[i])), var(smc.x[i], weights(smc.w[i])) for every θ-particle at once (inflation_example.jl:46): [d, M] each
 function state_variances(smc::SMC)
-    d = statedim(smc.model(smc.θ[1])); mean = Matrix{Float64}(undef, d, smc.M); var = Matrix{Float64}(undef, d, smc.M)
-    check(smc.ctx, ccall((:smcb_batch_weighted_moments, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), smc.cur.h, mean, var))
+    d = statedim(smc); mean = Matrix{Float64}(undef, d, smc.M); var = Matrix{Float64}(undef, d, smc.M)
+    check(smc.ctx, ccall((:smcb_batch_weighted_moments, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), clouds(smc).h, mean, var))
     mean, var
 end
+
+# ---------------------------------------------------------------- multi-GPU: one Julia process per GPU, θ sharded (SURVEY §8e)
+# rank 0: id = comm_unique_id(); carry the 128 bytes to the other ranks (MPI.bcast, a shared file, Distributed.jl ...); then
+# EVERY rank: comm_init!(ctx, rank, nranks, id).  Samplers created from ctx afterwards shard their θ-particles over the ranks
+# (all-gathers and cloud moves run inside the library over NCCL / NVLink); their results do not depend on the number of GPUs.
+comm_unique_id() = (id = Vector{UInt8}(undef, 128); ccall((:smcb_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id) == 0 || error("NCCL is not available"); id)
+comm_init!(ctx::Context, rank::Integer, nranks::Integer, id::Vector{UInt8}) =
+    check(ctx, ccall((:smcb_comm_init, LIB), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{UInt8}), ctx.h, rank, nranks, id))
 
 # ---------------------------------------------------------------- guided filters (particles.jl:28-84, docs/SPEC.md §10)
 # The device evaluates proposals of the family x' ~ Normal(c0 + c1*xp, c2); a proposal is called as proposal(model, y)
@@ -286,116 +352,115 @@ function particle_filter!(states::GuidedCloud, w::Vector{Float64}, y::Float64, m
     return lm[1], weights(states), es[1]
 end
 
-expected_parameters(smc::SMC) = sum(reduce(hcat, smc.θ .* smc.ω), dims=2)                      # :61-65 (properly weighted: SURVEY D6)
+expected_parameters(smc::SMC) = (g = sampler_get(smc); sum(reduce(hcat, g.θ .* g.ω), dims=2))    # :61-65 (properly weighted: SURVEY D6)
 
-function random_walk_kernel(θ::Vector{Vector{Float64}})                                        # :94-101
-    Θ = hcat(θ...); dθ = 2.83^2 / size(Θ, 1)
-    Σ = norm(cov(Θ')) < 1.e-8 ? 1.e-2I(size(Θ, 1)) : dθ * cov(Θ') + 1.e-10I
-    return Matrix(Σ)
+# Σ of the random-walk proposal in the frozen summation order of docs/SPEC.md §11 (what the device sampler uses)  :87-101
+function random_walk_kernel(θ::Vector{Vector{Float64}})
+    d = length(θ[1]); Σ = Matrix{Float64}(undef, d, d)
+    ccall((:smcb_random_walk_sigma, LIB), Cint, (Ptr{Float64}, Int64, Cint, Ptr{Float64}), reduce(hcat, θ), length(θ), d, Σ)
+    return Matrix(Σ')
 end
 
-function resample!(smc::SMC)                                                                   # :74-84
-    set_rng!(smc.ctx, smc.ctx.seed, 0)
-    a = resample(smc.ω; ctx=smc.ctx, t=smc.nres, purpose=P_THETA_RESAMPLE); smc.nres += 1
-    sort!(a)                                                                                   # docs/SPEC.md §5b: exchangeable slots, sorted parents stay on their GPU
-    smc.θ = smc.θ[a]; smc.logZ = smc.logZ[a]; smc.ω = fill(1 / smc.M, smc.M)
-    check(smc.ctx, ccall((:smcb_batch_gather, LIB), Cint, (Ptr{Cvoid}, Ptr{Int32}), smc.cur.h, Int32.(a .- 1)))
-end
-
-function host_normals(smc, ordinal, k, c, M)
-    z = Vector{Float64}(undef, M)
-    ccall((:smcb_rng_normals, LIB), Cint, (UInt64, UInt32, UInt32, UInt32, UInt32, UInt32, Int64, Ptr{Float64}),
-          smc.ctx.seed, ordinal, k, c, P_MH_PROPOSAL, 0, M, z); z
-end
-function host_uniforms(smc, ordinal, c, M)
-    u = Vector{UInt64}(undef, M)
-    ccall((:smcb_rng_uniforms64, LIB), Cint, (UInt64, UInt32, UInt32, UInt32, UInt32, Int64, Ptr{UInt64}),
-          smc.ctx.seed, ordinal, 0, c, P_MH_ACCEPT, M, u)
-    return Float64.(u .>> 11) .* 2.0^-53
-end
-
-function rejuvenate!(smc::SMC, y::Vector{Float64}, ξ::Float64, verbose::Bool)                  # :103-148
-    M, d = smc.M, length(smc.θ[1]); acc = falses(M)
-    Σ = smc.kernel(smc.θ); scales = 0.5 * reverse(1:smc.chain)
-    verbose && @printf("\t[rejuvenating]")
-    smc.prop === nothing && (smc.prop = Batch(smc.ctx, kind(smc.model(smc.θ[1])), M, smc.N))
-    ordinal = smc.nrej; smc.nrej += 1
-    for c in 1:smc.chain
-        L = cholesky(Symmetric(scales[c] * Σ)).L
-        Z = reduce(hcat, [host_normals(smc, ordinal, k - 1, c - 1, M) for k in 1:d])          # [M,d]
-        θp = [smc.θ[m] + L * Z[m, :] for m in 1:M]
-        ok = [insupport(smc.prior, θp[m]) for m in 1:M]
-        P = params(smc, [ok[m] ? θp[m] : smc.θ[m] for m in 1:M]); zp = Vector{Float64}(undef, M)
-        next_epoch!(smc)
-        check(smc.ctx, ccall((:smcb_batch_log_likelihood, LIB), Cint,
-                             (Ptr{Cvoid}, Ptr{Float64}, Ptr{UInt8}, Ptr{Float64}, Int64, Cint, UInt32, Ptr{Float64}),
-                             smc.prop.h, P, UInt8.(ok), y, length(y), smc.resampler, 0, zp))   # ONE launch for all θ (:117-121)
-        u = host_uniforms(smc, ordinal, c - 1, M); accept = falses(M)
-        for m in 1:M
-            ok[m] || continue
-            lp = logpdf(smc.prior, θp[m])
-            ratio = ξ * (zp[m] - smc.logZ[m]) + lp - logpdf(smc.prior, smc.θ[m])
-            if zp[m] + lp > -Inf && log(u[m]) < ratio
-                smc.logZ[m] = zp[m]; smc.θ[m] = θp[m]; accept[m] = true; acc[m] = true
-            end
-        end
-        check(smc.ctx, ccall((:smcb_batch_accept, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{UInt8}), smc.cur.h, smc.prop.h, UInt8.(accept)))
-    end
-    smc.ω = fill(1 / M, M); smc.acc_ratio = sum(acc) / M
-    verbose && @printf("\tacc_rate: %1.5f", smc.acc_ratio)
+# smc²(smc, y): M bootstrap filters at y[1], one launch                                        :288-301
+function smc²(smc::SMC, y::Vector{Float64})
+    set_data!(smc, y)
+    check(smc.ctx, ccall((:smcb_sampler_smc2_init, LIB), Cint, (Ptr{Cvoid},), smc.h))
     return smc
 end
 
-function density_tempered(smc::SMC, y::Vector{Float64}, verbose=true)                          # :222-281
-    next_epoch!(smc)
-    check(smc.ctx, ccall((:smcb_batch_log_likelihood, LIB), Cint,
-                         (Ptr{Cvoid}, Ptr{Float64}, Ptr{UInt8}, Ptr{Float64}, Int64, Cint, UInt32, Ptr{Float64}),
-                         smc.cur.h, params(smc, smc.θ), C_NULL, y, length(y), smc.resampler, 0, smc.logZ))
-    _, smc.ω, smc.ess = reweight(smc.logZ; ctx=smc.ctx)
-    ξ = 0.0
-    while ξ < 1.0
-        resample_flag = true; lower_bound = oldξ = ξ; upper_bound = 2.0
-        local newξ, logω
-        while upper_bound - lower_bound > 1.e-6
-            newξ = (upper_bound + lower_bound) / 2.0
-            logω = (newξ - oldξ) * smc.logZ
-            _, smc.ω, smc.ess = reweight(logω; ctx=smc.ctx)
-            if smc.ess == smc.ess_min; break
-            elseif smc.ess < smc.ess_min; upper_bound = newξ
-            else lower_bound = newξ end
-        end
-        if newξ ≥ 1.0
-            resample_flag = false; newξ = 1.0; logω = (newξ - oldξ) * smc.logZ
-            _, smc.ω, smc.ess = reweight(logω; ctx=smc.ctx)
-        end
-        ξ = newξ
-        verbose && @printf("ξ = %1.5f\tess = %4.3f", ξ, smc.ess)
-        if resample_flag
-            resample!(smc); rejuvenate!(smc, y, ξ, verbose)
-        end
-        verbose && print("\n")
-    end
-end
-
-function smc²(smc::SMC, y::Vector{Float64})                                                    # :288-301
-    next_epoch!(smc); lm = Vector{Float64}(undef, smc.M)
-    check(smc.ctx, ccall((:smcb_batch_init, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{UInt8}, Float64, UInt32, Ptr{Float64}, Ptr{Float64}),
-                         smc.cur.h, params(smc, smc.θ), C_NULL, y[1], 0, lm, C_NULL))
-    smc.logZ = copy(lm); _, smc.ω, smc.ess = reweight(lm; ctx=smc.ctx)
-    return smc
-end
-
-function smc²!(smc::SMC, y::Vector{Float64}, t::Int64, verbose::Bool=true)                     # :308-340
+# smc²!(smc, y, t): resample! / rejuvenate! / exchange! when ess < ess_min, then M filter steps at y[t] and the reweighting —
+# all inside the library (θ-level vectors never leave the GPU); t is Julia's 1-based index                   :308-340
+function smc²!(smc::SMC, y::Vector{Float64}, t::Int64, verbose::Bool=true)
+    set_data!(smc, y)
     verbose && @printf("t = %4d\tess = %4.3f", t - 1, smc.ess)
-    if smc.ess < smc.ess_min
-        resample!(smc); rejuvenate!(smc, y[1:(t-1)], 1.0, verbose)
-    end
-    logω = log.(smc.ω); lm = Vector{Float64}(undef, smc.M)
-    check(smc.ctx, ccall((:smcb_batch_step, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Float64, Cint, Ptr{Float64}, Ptr{Float64}),
-                         smc.cur.h, params(smc, smc.θ), y[t], smc.resampler, lm, C_NULL))       # ONE launch (:325-331)
-    logω .+= lm; smc.logZ .+= lm
-    _, smc.ω, smc.ess = reweight(logω; ctx=smc.ctx)
+    ess = Ref(0.0); rj = Ref{Cint}(0)
+    check(smc.ctx, ccall((:smcb_sampler_smc2_step, LIB), Cint, (Ptr{Cvoid}, Int64, Ref{Float64}, Ref{Cint}), smc.h, t - 1, ess, rj))
+    verbose && rj[] != 0 && @printf("\t[rejuvenating]\tacc_rate: %1.5f", smc.acc_ratio)
     verbose && print("\n")
 end
+
+# density_tempered(smc, y): the whole tempering loop (bisection for ξ on the device, resample!, rejuvenate!) in one call   :222-281
+function density_tempered(smc::SMC, y::Vector{Float64}, verbose=true)
+    set_data!(smc, y)
+    sched = Matrix{Float64}(undef, 3, 4096); n = Ref{Cint}(0)
+    check(smc.ctx, ccall((:smcb_sampler_density_tempered, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Cint, Ref{Cint}), smc.h, sched, 4096, n))
+    setfield!(smc, :schedule, [(sched[1, i], sched[2, i]) for i in 1:n[]])
+    if verbose
+        for i in 1:n[]
+            @printf("ξ = %1.5f\tess = %4.3f", sched[1, i], sched[2, i])
+            sched[3, i] >= 0 && @printf("\t[rejuvenating]\tacc_rate: %1.5f", sched[3, i])
+            print("\n")
+        end
+    end
+end
+
+# ---------------------------------------------------------------- ibis.jl: the same θ-level scheme with the Kalman filter as inner filter
+# IBIS(M, model, prior, chain, ess_threshold, min_ar): no state particles — x, Σ are the M filtered means / variances.  The M-wide
+# Kalman recursions are one device call each (smcb_kalman_batch_*); the θ level (M numbers) runs here with the host-level Philox
+# streams and the frozen proposal arithmetic of docs/SPEC.md §11, so a run reproduces the Python host mirror (ibis.py) draw for draw.
+mutable struct IBIS{SSM}                                                                       # ibis.jl:3-24
+    θ::Vector{Vector{Float64}}; ω::Vector{Float64}; x::Vector{Float64}; Σ::Vector{Float64}
+    ess::Float64; ess_min::Float64; M::Int64; chain::Int64; logZ::Vector{Float64}
+    model::SSM; prior::Sampleable; kernel::Function; acc_threshold::Float64; acc_ratio::Float64
+    ctx::Context; nres::UInt32; nrej::UInt32
+end
+function IBIS(M::Int64, model, prior::Sampleable, chain::Int64, ess_threshold::Float64, min_ar::Float64=-1.0; ctx=context())   # ibis.jl:26-52
+    θ = [collect(rand(prior)) for _ in 1:M]; ms = model.(θ)
+    all(m -> m isa LinearModel, ms) || throw(ArgumentError("IBIS needs a univariate LinearModel (its inner filter is kalman_filter)"))
+    IBIS(θ, fill(1 / M, M), [m.x0 for m in ms], [m.σ0 for m in ms], 1.0 * M, M * ess_threshold, M, chain, zeros(M), model, prior,
+         random_walk_kernel, min_ar, 0.0, ctx, UInt32(0), UInt32(0))
+end
+pblock(s::IBIS, θ) = reduce(hcat, [params8(s.model(th)) for th in θ])                          # [8,M] col-major == C [M][8]
+function kalman_all!(s::IBIS, y::Float64)                                                      # M × kalman_filter(model(θ_m), x_m, Σ_m, y)
+    ll = Vector{Float64}(undef, s.M)
+    check(s.ctx, ccall((:smcb_kalman_batch_step, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                       s.ctx.h, pblock(s, s.θ), s.M, y, s.x, s.Σ, ll))
+    ll
+end
+function host_normals(seed, ordinal, k, c, M)
+    z = Vector{Float64}(undef, M)
+    ccall((:smcb_rng_normals, LIB), Cint, (UInt64, UInt32, UInt32, UInt32, UInt32, UInt32, Int64, Ptr{Float64}), seed, ordinal, k, c, P_MH_PROPOSAL, 0, M, z); z
+end
+function host_uniforms(seed, ordinal, c, M)
+    u = Vector{UInt64}(undef, M)
+    ccall((:smcb_rng_uniforms64, LIB), Cint, (UInt64, UInt32, UInt32, UInt32, UInt32, Int64, Ptr{UInt64}), seed, ordinal, 0, c, P_MH_ACCEPT, M, u)
+    Float64.(u .>> 11) .* 2.0^-53
+end
+function smc²(s::IBIS, y::Vector{Float64})                                                     # ibis.jl:128-147
+    ll = kalman_all!(s, y[1]); s.logZ = copy(ll); _, s.ω, s.ess = reweight(ll; ctx=s.ctx); s
+end
+function smc²!(s::IBIS, y::Vector{Float64}, t::Int64, verbose::Bool=true)                      # ibis.jl:154-189
+    if s.ess < s.ess_min
+        set_rng!(s.ctx, s.ctx.seed, 0)
+        a = sort!(resample(s.ω; ctx=s.ctx, t=s.nres, purpose=P_THETA_RESAMPLE)); s.nres += 1  # ibis.jl:72-84 (+ docs/SPEC.md §5b)
+        s.θ, s.x, s.Σ, s.logZ, s.ω = s.θ[a], s.x[a], s.Σ[a], s.logZ[a], fill(1 / s.M, s.M)
+        d = length(s.θ[1]); Σp = s.kernel(s.θ); acc = falses(s.M); ord = s.nrej; s.nrej += 1  # ibis.jl:86-126
+        yy = y[1:t-1]; lp = [logpdf(s.prior, th) for th in s.θ]
+        for c in 1:s.chain
+            L = Matrix{Float64}(undef, d, d); sc = 0.5 * (s.chain - c + 1)
+            d == 1 ? (L[1, 1] = sc * Σp[1, 1]) :
+                ccall((:smcb_cholesky_lower, LIB), Cint, (Ptr{Float64}, Cint, Float64, Ptr{Float64}), Matrix(Σp'), d, sc, L) == 0 || error("proposal covariance not positive definite")
+            d > 1 && (L = Matrix(L'))
+            Z = reduce(hcat, [host_normals(s.ctx.seed, ord, k - 1, c - 1, s.M) for k in 1:d])
+            θp = [s.θ[m] .+ [sum(Z[m, k] * L[j, k] for k in 1:j) for j in 1:d] for m in 1:s.M]
+            ok = [insupport(s.prior, th) for th in θp]
+            P = pblock(s, [ok[m] ? θp[m] : s.θ[m] for m in 1:s.M]); zp = fill(-Inf, s.M); xp = similar(s.x); Sp = similar(s.Σ)
+            check(s.ctx, ccall((:smcb_kalman_batch_loglik, LIB), Cint,
+                               (Ptr{Cvoid}, Ptr{Float64}, Ptr{UInt8}, Int64, Ptr{Float64}, Int64, Cint, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                               s.ctx.h, P, UInt8.(ok), s.M, yy, length(yy), 0, zp, xp, Sp))
+            u = host_uniforms(s.ctx.seed, ord, c - 1, s.M)
+            for m in findall(ok)
+                lpp = logpdf(s.prior, θp[m])
+                if zp[m] + lpp > -Inf && log(u[m]) < (zp[m] - s.logZ[m]) + (lpp - lp[m])
+                    s.logZ[m], s.θ[m], s.x[m], s.Σ[m], lp[m], acc[m] = zp[m], θp[m], xp[m], Sp[m], lpp, true
+                end
+            end
+        end
+        s.acc_ratio = sum(acc) / s.M
+    end
+    ll = kalman_all!(s, y[t]); logω = log.(s.ω) .+ ll; s.logZ .+= ll
+    _, s.ω, s.ess = reweight(logω; ctx=s.ctx)
+end
+expected_parameters(s::IBIS) = sum(reduce(hcat, s.θ .* s.ω), dims=2)
 
 end # module
