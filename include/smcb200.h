@@ -93,6 +93,10 @@ int smcb_normalize(smcb_ctx* ctx, const double* logw, int64_t n, double* logmu, 
 int smcb_resample(smcb_ctx* ctx, const double* w, int64_t n, int resampler, uint32_t stream, uint32_t t,
                   uint32_t purpose, int64_t* ancestors);
 
+/* resample(w, N) with N != length(w): n_out ancestors (0-based indices into w) from the n weights                 particles.jl:17 */
+int smcb_resample_n(smcb_ctx* ctx, const double* w, int64_t n, int64_t n_out, int resampler, uint32_t stream, uint32_t t,
+                    uint32_t purpose, int64_t* ancestors);
+
 /* ------------------------------------------------------------------ one filter (large N) */
 /* bootstrap_filter(N, y, model) -> (x, w, logμ)                        particles.jl:87-105
  * the cloud stays on the device; read it back with smcb_fetch_state. */

@@ -210,8 +210,13 @@ def ancestors_numpy(logw, resampler, seed, epoch, stream, t):
     return out
 
 
-def resample_w(w, resampler, seed, epoch, stream, t, purpose=P_RESAMPLE):
+def resample_w(w, resampler, seed, epoch, stream, t, purpose=P_RESAMPLE, n_out=None):
     w = np.ascontiguousarray(w, np.float64)
+    if n_out is not None and int(n_out) != w.size:            # resample(w, N) with N != length(w)   particles.jl:17
+        a = np.empty(int(n_out), np.int64)
+        lib().smco_resample_w_n(_p(w), C.c_int64(w.size), C.c_int64(int(n_out)), C.c_int(resampler), C.c_uint64(seed), C.c_uint32(epoch),
+                                C.c_uint32(stream), C.c_uint32(t), C.c_uint32(purpose), _p(a))
+        return a
     a = np.empty(w.size, np.int64)
     lib().smco_resample_w(_p(w), C.c_int64(w.size), C.c_int(resampler), C.c_uint64(seed), C.c_uint32(epoch),
                           C.c_uint32(stream), C.c_uint32(t), C.c_uint32(purpose), _p(a))

@@ -128,16 +128,23 @@ void smco_normalize(const double *logw, int64_t n, double *logmu, double *w, dou
 }
 
 /* ------------------------------------------------------------------ a2 resample (SPEC §5) */
+static void ancestors_from_q_n(const uint64_t *q, int64_t n, int64_t n_out, int resampler, uint64_t seed, uint32_t epoch,
+                               uint32_t stream, uint32_t t, uint32_t purpose, int64_t *anc);
 static void ancestors_from_q(const uint64_t *q, int64_t n, int resampler, uint64_t seed, uint32_t epoch,
                              uint32_t stream, uint32_t t, uint32_t purpose, int64_t *anc) {
+  ancestors_from_q_n(q, n, n, resampler, seed, epoch, stream, t, purpose, anc);
+}
+/* n_out draws from n weights (resample(w, N), particles.jl:17): thresholds i = 0 .. n_out-1 with strata of width floor((2^64-1)/n_out) */
+static void ancestors_from_q_n(const uint64_t *q, int64_t n, int64_t n_out, int resampler, uint64_t seed, uint32_t epoch,
+                               uint32_t stream, uint32_t t, uint32_t purpose, int64_t *anc) {
   uint64_t *C = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)n);
   uint64_t run = 0;
   for (int64_t j = 0; j < n; ++j) { run += q[j]; C[j] = run; }
   uint64_t Q = run;
-  uint64_t R = 0xFFFFFFFFFFFFFFFFull / (uint64_t)n;
+  uint64_t R = 0xFFFFFFFFFFFFFFFFull / (uint64_t)n_out;
   uint64_t U0 = o_uniform64(seed, epoch, 0, stream, t, purpose);
-  for (int64_t i = 0; i < n; ++i) {
-    if (Q == 0) { anc[i] = i; continue; }
+  for (int64_t i = 0; i < n_out; ++i) {
+    if (Q == 0) { anc[i] = i < n ? i : n - 1; continue; }
     uint64_t F;
     if (resampler == RS_MULTINOMIAL) F = o_uniform64(seed, epoch, (uint32_t)i, stream, t, purpose);
     else if (resampler == RS_STRATIFIED) F = (uint64_t)i * R + o_mulhi(o_uniform64(seed, epoch, (uint32_t)i, stream, t, purpose), R);
@@ -239,6 +246,18 @@ void smco_resample_w(const double *w, int64_t n, int resampler, uint64_t seed, u
   double scale = o_from_bits((uint64_t)(1023 + S) << 52);
   for (int64_t i = 0; i < n; ++i) q[i] = (mx > 0.0 && w[i] > 0.0) ? (uint64_t)((w[i] / mx) * scale) : 0;
   ancestors_from_q(q, n, resampler, seed, epoch, stream, t, purpose, anc);
+  free(q);
+}
+/* resample(w, N) with N != length(w)   particles.jl:17-19 */
+void smco_resample_w_n(const double *w, int64_t n, int64_t n_out, int resampler, uint64_t seed, uint32_t epoch, uint32_t stream,
+                       uint32_t t, uint32_t purpose, int64_t *anc) {
+  int S = smco_quant_shift(n);
+  double mx = 0.0;
+  for (int64_t i = 0; i < n; ++i) if (w[i] > mx) mx = w[i];
+  uint64_t *q = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)n);
+  double scale = o_from_bits((uint64_t)(1023 + S) << 52);
+  for (int64_t i = 0; i < n; ++i) q[i] = (mx > 0.0 && w[i] > 0.0) ? (uint64_t)((w[i] / mx) * scale) : 0;
+  ancestors_from_q_n(q, n, n_out, resampler, seed, epoch, stream, t, purpose, anc);
   free(q);
 }
 

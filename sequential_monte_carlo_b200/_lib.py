@@ -49,6 +49,7 @@ SIGNATURES = {
     "smcb_free_pinned": (C.c_int, [_c_ctx, C.c_void_p]),
     "smcb_normalize": (C.c_int, [_c_ctx, C.c_void_p, C.c_int64, _dp, C.c_void_p, _dp]),
     "smcb_resample": (C.c_int, [_c_ctx, C.c_void_p, C.c_int64, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "smcb_resample_n": (C.c_int, [_c_ctx, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_void_p]),
     "smcb_bootstrap_init": (C.c_int, [_c_ctx, C.c_int, C.c_void_p, C.c_int64, C.c_double, C.c_uint32, _dp, _dp]),
     "smcb_bootstrap_step": (C.c_int, [_c_ctx, C.c_void_p, C.c_double, C.c_int, _dp, _dp]),
     "smcb_log_likelihood": (C.c_int, [_c_ctx, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_uint32,
@@ -327,8 +328,12 @@ class Context:
         self._check(self._lib.smcb_normalize(self._h, _ptr(logw), logw.size, C.byref(lm), _ptr(w), C.byref(es)))
         return lm.value, w, es.value
 
-    def resample(self, w, resampler=MULTINOMIAL, stream=0, t=0, purpose=3):
+    def resample(self, w, resampler=MULTINOMIAL, stream=0, t=0, purpose=3, n_out=None):
         w = np.ascontiguousarray(w, np.float64)
+        if n_out is not None and int(n_out) != w.size:
+            a = np.empty(int(n_out), np.int64)
+            self._check(self._lib.smcb_resample_n(self._h, _ptr(w), w.size, int(n_out), int(resampler), int(stream), int(t), int(purpose), _ptr(a)))
+            return a
         a = np.empty(w.size, np.int64)
         self._check(self._lib.smcb_resample(self._h, _ptr(w), w.size, int(resampler), int(stream), int(t), int(purpose), _ptr(a)))
         return a

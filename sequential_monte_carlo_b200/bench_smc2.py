@@ -53,9 +53,11 @@ def run_config(name, ctx, comm, rank, world, steps=1, warmup=1, resampler="syste
     model, prior, truth = _setup(smc, cfg["kind"])
     y = smc.simulate(model(truth), cfg["T"], seed=1998)[1]
     walls, spans, plains, rejuvs, stats_sum, out = [], [], [], [], None, {}
+    if world > 1:
+        warmup = max(warmup, 2)        # the first sharded run also builds NCCL's point-to-point channels: never the profiled one
     for rep in range(warmup + steps):
         s = smc.SMC(cfg["N"], cfg["M"], model, prior, cfg["chain"], 0.5, seed=1998, ctx=ctx, comm=comm, resampler=resampler, engine="device")
-        s._eng.set_profiling(rep < warmup)     # the breakdown comes from the (untimed) warm-up runs: the events cost ~10 µs per step
+        s._eng.set_profiling(rep == warmup - 1)     # the breakdown comes from the last (untimed) warm-up run: the events cost ~10 µs per step
         if barrier:
             barrier()
         ctx.synchronize()
@@ -73,10 +75,10 @@ def run_config(name, ctx, comm, rank, world, steps=1, warmup=1, resampler="syste
         ctx.synchronize()
         wall = time.perf_counter() - t0
         st = s._eng.stats()
-        if rep < warmup:
+        if rep == warmup - 1:
             prof = {k: st[k] for k in ("filter_ms", "allgather_ms", "exchange_ms", "theta_ms")}
             prof_wall = wall
-        else:
+        elif rep >= warmup:
             walls.append(wall)
             spans.append(st["span_ms"])
             plains += plain

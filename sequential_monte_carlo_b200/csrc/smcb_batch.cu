@@ -946,7 +946,7 @@ void BatchFilter::fetch(double* x_host, double* w_host, double* logw_host) {
     SMCB_CUDA_TRY(cudaMemcpy2DAsync(logw_host, sizeof(double) * N_, logw_[cur_], sizeof(double) * ld_, sizeof(double) * N_, M_,
                                     cudaMemcpyDeviceToHost, stream_));
   if (w_host) {
-    if (!w_tmp_) SMCB_CUDA_TRY(cudaMalloc(&w_tmp_, sizeof(double) * M_ * std::max<int64_t>(N_, d_)));
+    ensure_scratch((size_t)(M_ * std::max<int64_t>(N_, d_)));
     dim3 grid((unsigned)((N_ + 255) / 256), (unsigned)M_);
     batch_weights_kernel<<<grid, 256, 0, stream_>>>(logw_[cur_], stats_[cur_], w_tmp_, N_, ld_);
     SMCB_CUDA_TRY(cudaGetLastError());
@@ -958,7 +958,7 @@ void BatchFilter::fetch(double* x_host, double* w_host, double* logw_host) {
 void BatchFilter::weighted_mean(double* mean_host) {
   if (!live_) throw Error{SMCB_ERR_STATE, "no batch state to summarise"};
   SMCB_CUDA_TRY(cudaSetDevice(device_));
-  if (!w_tmp_) SMCB_CUDA_TRY(cudaMalloc(&w_tmp_, sizeof(double) * M_ * std::max<int64_t>(N_, d_)));  // scratch (>= M*d doubles: N >= d)
+  ensure_scratch((size_t)(M_ * d_));
   dim3 grid((unsigned)M_, (unsigned)d_);
   batch_wmean_kernel<<<grid, 256, 0, stream_>>>(x_[cur_], logw_[cur_], stats_[cur_], w_tmp_, N_, ld_, d_);
   SMCB_CUDA_TRY(cudaGetLastError());
@@ -969,21 +969,25 @@ void BatchFilter::weighted_mean(double* mean_host) {
 void BatchFilter::weighted_moments(double* mean_host, double* var_host) {
   if (!live_) throw Error{SMCB_ERR_STATE, "no batch state to summarise"};
   SMCB_CUDA_TRY(cudaSetDevice(device_));
-  double* scratch = nullptr;  // mean[M][d] then var[M][d]
   const size_t words = (size_t)M_ * d_;
-  SMCB_CUDA_TRY(cudaMalloc(&scratch, sizeof(double) * 2 * words));
-  try {
-    dim3 grid((unsigned)M_, (unsigned)d_);
-    batch_wmoment_kernel<<<grid, 256, 0, stream_>>>(x_[cur_], logw_[cur_], stats_[cur_], scratch, scratch + words, N_, ld_, d_);
-    SMCB_CUDA_TRY(cudaGetLastError());
-    if (mean_host) SMCB_CUDA_TRY(cudaMemcpyAsync(mean_host, scratch, sizeof(double) * words, cudaMemcpyDeviceToHost, stream_));
-    if (var_host) SMCB_CUDA_TRY(cudaMemcpyAsync(var_host, scratch + words, sizeof(double) * words, cudaMemcpyDeviceToHost, stream_));
-    SMCB_CUDA_TRY(cudaStreamSynchronize(stream_));
-  } catch (...) {
-    cudaFree(scratch);
-    throw;
-  }
-  cudaFree(scratch);
+  ensure_scratch(2 * words);  // mean[M][d] then var[M][d]; the scratch is kept across calls (no cudaMalloc / cudaFree per call)
+  double* scratch = w_tmp_;
+  dim3 grid((unsigned)M_, (unsigned)d_);
+  batch_wmoment_kernel<<<grid, 256, 0, stream_>>>(x_[cur_], logw_[cur_], stats_[cur_], scratch, scratch + words, N_, ld_, d_);
+  SMCB_CUDA_TRY(cudaGetLastError());
+  if (mean_host) SMCB_CUDA_TRY(cudaMemcpyAsync(mean_host, scratch, sizeof(double) * words, cudaMemcpyDeviceToHost, stream_));
+  if (var_host) SMCB_CUDA_TRY(cudaMemcpyAsync(var_host, scratch + words, sizeof(double) * words, cudaMemcpyDeviceToHost, stream_));
+  SMCB_CUDA_TRY(cudaStreamSynchronize(stream_));
+}
+
+void BatchFilter::ensure_scratch(size_t words) {
+  if (w_cap_ >= words) return;
+  SMCB_CUDA_TRY(cudaStreamSynchronize(stream_));
+  cudaFree(w_tmp_);
+  w_tmp_ = nullptr;
+  w_cap_ = 0;
+  SMCB_CUDA_TRY(cudaMalloc(&w_tmp_, sizeof(double) * words));
+  w_cap_ = words;
 }
 
 void BatchFilter::weighted_quantiles(const double* probs, int np, bool weighted, double* q_host) {
@@ -992,21 +996,16 @@ void BatchFilter::weighted_quantiles(const double* probs, int np, bool weighted,
   for (int j = 0; j < np; ++j)
     if (!(probs[j] >= 0.0 && probs[j] <= 1.0)) throw Error{SMCB_ERR_BAD_ARG, "batch_weighted_quantiles: probabilities must lie in [0, 1]"};
   SMCB_CUDA_TRY(cudaSetDevice(device_));
-  double* scratch = nullptr;  // probs[np] then out[M][d][np]
-  const size_t words = (size_t)np + (size_t)M_ * d_ * np;
-  SMCB_CUDA_TRY(cudaMalloc(&scratch, sizeof(double) * words));
-  try {
-    SMCB_CUDA_TRY(cudaMemcpyAsync(scratch, probs, sizeof(double) * np, cudaMemcpyHostToDevice, stream_));
-    dim3 grid((unsigned)M_, (unsigned)d_);
-    batch_wquantile_kernel<<<grid, 256, 0, stream_>>>(x_[cur_], logw_[cur_], stats_[cur_], scratch, np, weighted ? 1 : 0, S_, scratch + np, N_, ld_, d_);
-    SMCB_CUDA_TRY(cudaGetLastError());
-    SMCB_CUDA_TRY(cudaMemcpyAsync(q_host, scratch + np, sizeof(double) * M_ * d_ * np, cudaMemcpyDeviceToHost, stream_));
-    SMCB_CUDA_TRY(cudaStreamSynchronize(stream_));
-  } catch (...) {
-    cudaFree(scratch);
-    throw;
-  }
-  cudaFree(scratch);
+  const size_t words = (size_t)np + (size_t)M_ * d_ * np;  // probs[np] then out[M][d][np]
+  ensure_scratch(words);
+  double* scratch = w_tmp_;
+  SMCB_CUDA_TRY(cudaMemcpyAsync(scratch, probs, sizeof(double) * np, cudaMemcpyHostToDevice, stream_));
+  SMCB_CUDA_TRY(cudaStreamSynchronize(stream_));  // the caller's probs buffer is not retained
+  dim3 grid((unsigned)M_, (unsigned)d_);
+  batch_wquantile_kernel<<<grid, 256, 0, stream_>>>(x_[cur_], logw_[cur_], stats_[cur_], scratch, np, weighted ? 1 : 0, S_, scratch + np, N_, ld_, d_);
+  SMCB_CUDA_TRY(cudaGetLastError());
+  SMCB_CUDA_TRY(cudaMemcpyAsync(q_host, scratch + np, sizeof(double) * M_ * d_ * np, cudaMemcpyDeviceToHost, stream_));
+  SMCB_CUDA_TRY(cudaStreamSynchronize(stream_));
 }
 
 // ---- device-resident variants: enqueue only (no host copies, no synchronisation) --------------------------------

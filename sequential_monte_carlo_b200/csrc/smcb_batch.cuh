@@ -78,6 +78,7 @@ class BatchFilter {
   void begin_call();
   void end_call();
   void upload_slots(const int32_t* a, const int32_t* b, int64_t n);
+  void ensure_scratch(size_t words);
 
   int device_;
   cudaStream_t stream_;
@@ -102,7 +103,8 @@ class BatchFilter {
   double* y_dev_ = nullptr;
   int64_t y_cap_ = 0;
   double* out_dev_ = nullptr;  // [2][M]: Σ logμ, ess
-  double* w_tmp_ = nullptr;
+  double* w_tmp_ = nullptr;    // scratch of fetch / the summaries, grown on demand and kept
+  size_t w_cap_ = 0;
   int32_t* slots_dev_ = nullptr;  // [2][slot_cap_]
   int64_t slot_cap_ = 0;
   std::vector<double> host_tmp_;

@@ -197,6 +197,16 @@ int smcb_resample(smcb_ctx* ctx, const double* w, int64_t n, int resampler, uint
   });
 }
 
+int smcb_resample_n(smcb_ctx* ctx, const double* w, int64_t n, int64_t n_out, int resampler, uint32_t stream, uint32_t t,
+                    uint32_t purpose, int64_t* ancestors) {
+  if (!ctx) return SMCB_ERR_BAD_ARG;
+  return guarded(ctx, [&] {
+    need(w && ancestors && n >= 1 && n_out >= 1, "resample_n: w, ancestors must be non-null and n, n_out >= 1");
+    need(purpose >= 1 && purpose <= 15, "resample_n: purpose must be in [1, 15]");
+    ctx->scratch->resample_vector(w, n, resampler, ctx->key(ctx->next_epoch), stream, t, purpose, ancestors, n_out);
+  });
+}
+
 // ------------------------------------------------------------------ one filter
 int smcb_bootstrap_init(smcb_ctx* ctx, int kind, const double* params, int64_t N, double y, uint32_t stream,
                         double* logmu, double* ess) {

@@ -1713,14 +1713,14 @@ __global__ void max_kernel(const double* __restrict__ v, int64_t n, FilterCtrl* 
   if (threadIdx.x == 0) atomicMax(&ctrl->maxslot[0], encode_ordered(m));
 }
 
-__global__ void ancestor_kernel(const uint64_t* __restrict__ cdf, int64_t N, int resampler, uint64_t Rw, RngKey key,
+__global__ void ancestor_kernel(const uint64_t* __restrict__ cdf, int64_t N, int64_t n_out, int resampler, uint64_t Rw, RngKey key,
                                 uint32_t stream, uint32_t t, uint32_t purpose, const FilterCtrl* ctrl,
                                 int64_t* __restrict__ anc) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
+  if (i >= n_out) return;
   const uint64_t Q = ctrl->total;
   if (Q == 0) {
-    anc[i] = i;
+    anc[i] = i < N ? i : N - 1;
     return;
   }
   uint64_t u;
@@ -1759,7 +1759,8 @@ SingleFilter::~SingleFilter() {
 void SingleFilter::release() {
   cudaFree(x_[0]); cudaFree(x_[1]); cudaFree(logw_[0]); cudaFree(logw_[1]); cudaFree(w_tmp_); cudaFree(cdf_); cudaFree(anc_);
   cudaFree(ctrl_); cudaFree(desc_); cudaFree(psum_); cudaFree(psum2_); cudaFree(stats_dev_);
-  cudaFree(tile_arrays_); cudaFree(bound_arrays_); cudaFree(summary_dev_); cudaFree(mn_arrays_);
+  cudaFree(tile_arrays_); cudaFree(bound_arrays_); cudaFree(summary_dev_); cudaFree(mn_arrays_); cudaFree(util_anc_);
+  util_anc_ = nullptr; util_cap_ = 0;
   tile_arrays_ = nullptr; bound_arrays_ = nullptr; bound_cap_ = 0; summary_dev_ = nullptr; summary_cap_ = 0; mn_arrays_ = nullptr; mn_cap_ = 0;
   x_[0] = x_[1] = logw_[0] = logw_[1] = w_tmp_ = psum_ = psum2_ = nullptr;
   cdf_ = nullptr; anc_ = nullptr; ctrl_ = nullptr; desc_ = nullptr; stats_dev_ = nullptr;
@@ -2342,20 +2343,26 @@ void SingleFilter::normalize_vector(const double* logw_host, int64_t n, StepStat
 }
 
 void SingleFilter::resample_vector(const double* w_host, int64_t n, int resampler, const RngKey& key, uint32_t stream_id,
-                                   uint32_t t, uint32_t purpose, int64_t* anc_host) {
+                                   uint32_t t, uint32_t purpose, int64_t* anc_host, int64_t n_out) {
   if (resampler < 0 || resampler > 2) throw Error{SMCB_ERR_BAD_ARG, "unknown resampler"};
+  if (n_out <= 0) n_out = n;
   load_vector(w_host, n, false);
   begin_call();
   launch_scan(0, true);
   from_w_ = false;
-  int64_t* anc_dev = nullptr;
-  SMCB_CUDA_TRY(cudaMalloc(&anc_dev, sizeof(int64_t) * n));
-  ancestor_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream_>>>(cdf_, n, resampler, R_, key, stream_id, t, purpose,
-                                                                    ctrl_, anc_dev);
+  if (util_cap_ < n_out) {  // scratch of the utility: kept across calls (a cudaMalloc / cudaFree pair per call cost more than the kernels)
+    cudaFree(util_anc_);
+    util_anc_ = nullptr;
+    util_cap_ = 0;
+    SMCB_CUDA_TRY(cudaMalloc(&util_anc_, sizeof(int64_t) * n_out));
+    util_cap_ = n_out;
+  }
+  int64_t* anc_dev = util_anc_;
+  ancestor_kernel<<<(unsigned)((n_out + 255) / 256), 256, 0, stream_>>>(cdf_, n, n_out, resampler, strata_width((uint64_t)n_out), key, stream_id, t,
+                                                                        purpose, ctrl_, anc_dev);
   cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaMemcpyAsync(anc_host, anc_dev, sizeof(int64_t) * n, cudaMemcpyDeviceToHost, stream_);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(anc_host, anc_dev, sizeof(int64_t) * n_out, cudaMemcpyDeviceToHost, stream_);
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream_);
-  cudaFree(anc_dev);
   N_ = 0;
   SMCB_CUDA_TRY(e);
   end_call();

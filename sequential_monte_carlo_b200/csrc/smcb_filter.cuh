@@ -60,8 +60,9 @@ class SingleFilter {
 
   // normalize(logw) / resample(w) on caller vectors (scratch use of this object; clobbers its state)
   void normalize_vector(const double* logw_host, int64_t n, StepStats* st, double* w_host);
+  // n_out > 0: draw n_out ancestors from the n weights (resample(w, N), particles.jl:17)
   void resample_vector(const double* w_host, int64_t n, int resampler, const RngKey& key, uint32_t stream_id,
-                       uint32_t t, uint32_t purpose, int64_t* anc_host);
+                       uint32_t t, uint32_t purpose, int64_t* anc_host, int64_t n_out = 0);
 
   void fetch(double* x_host, double* w_host, double* logw_host);
   // weighted mean / variance / quantiles of each state component, computed on the device (SPEC §8)
@@ -129,6 +130,8 @@ class SingleFilter {
   unsigned long long* tile_arrays_ = nullptr;  // [5][kMaxTiles]: tot, excl, incl, lexcl, cta_tot
   unsigned long long* summary_dev_ = nullptr;  // scratch of summary(): block partials, radix-select prefixes / ranks / histograms
   size_t summary_cap_ = 0;
+  int64_t* util_anc_ = nullptr;                // scratch of resample_vector, kept across calls
+  int64_t util_cap_ = 0;
   void* mn_arrays_ = nullptr;                  // cell index of the two-level multinomial resampler: cellC u64[cap], K, O i32[cap], part_start i32[cap + 1], ticket
   int64_t mn_cap_ = 0;
   bool mn_attr_set_ = false;

@@ -47,6 +47,7 @@ class _DeviceArray:
 
     def __init__(self, ctx, gen, which):
         self._ctx, self._gen, self._which, self._host, self._host_t = ctx, gen, which, None, -1
+        self._T0 = getattr(ctx, "_T", 0)    # the step a weights handle belongs to (bootstrap_filter! returns a NEW w every step)
 
     def _stale(self):
         return getattr(self._ctx, "_gen", 0) != self._gen
@@ -56,6 +57,11 @@ class _DeviceArray:
             return self._host
         if self._stale():
             raise RuntimeError("this particle cloud was replaced by a later bootstrap_filter / log_likelihood on the same context")
+        if self._which == "w" and self._ctx._T != self._T0:
+            if self._host is not None:
+                return self._host          # the weights of its own step, read while they were current
+            raise RuntimeError("these weights belong to an earlier step of the filter and were not read while they were current: "
+                               "use the w returned by the latest bootstrap_filter! / particle_filter!")
         if self._which == "x":
             x, _, _ = self._ctx.fetch_state(want_x=True, want_w=False)
             self._host = x[0] if x.shape[0] == 1 else np.ascontiguousarray(x.T)   # UCSV: N rows of 3 (state_space_models.jl:229-231)
@@ -101,9 +107,7 @@ def resample(w, N=None, *, resampler="multinomial", ctx=None, stream=0, t=0, pur
     """ancestors = resample(w)  — particles.jl:17-19.  0-based indices (Julia's are 1-based)."""
     ctx = ctx or default_context()
     w = np.asarray(w, np.float64)
-    if N is not None and int(N) != w.size:
-        raise NotImplementedError("resample(w, N) with N != length(w) is not used anywhere on the reference's path")
-    return ctx.resample(w, resampler_id(resampler), stream=stream, t=t, purpose=purpose)
+    return ctx.resample(w, resampler_id(resampler), stream=stream, t=t, purpose=purpose, n_out=N)
 
 
 def bootstrap_filter(N, y, model, *, ctx=None, stream=0):

@@ -208,6 +208,34 @@ def test_pf_vs_kalman(ctx, oracle):
     assert abs(xT[0] - xo) <= 1e-12 * abs(xo) and abs(sT[0] - so) <= 1e-12 * so
 
 
+def test_resample_with_a_different_output_size(ctx, oracle):
+    """resample(w, N) with N != length(w) (particles.jl:17-19): N ancestors drawn from length(w) weights"""
+    rng = np.random.default_rng(5)
+    w = rng.random(3000)
+    w /= w.sum()
+    for rs in (smc.MULTINOMIAL, smc.STRATIFIED, smc.SYSTEMATIC):
+        for n_out in (1, 77, 3000, 10001):
+            ctx.set_rng(9, 4)
+            a = smc.resample(w, n_out, resampler=rs, ctx=ctx, stream=2, t=3)
+            np.testing.assert_array_equal(a, oracle.resample_w(w, rs, 9, 4, 2, 3, n_out=n_out))
+            assert a.shape == (n_out,) and a.min() >= 0 and a.max() < w.size
+
+
+def test_stale_weights_handle(ctx, oracle):
+    """bootstrap_filter! returns a NEW w every step (particles.jl:128): a handle of an earlier step keeps its own values when
+    they were read in time, and refuses to hand out a later step's weights otherwise"""
+    lg = smc.LinearGaussian(0.5, 1.0, 0.9, 0.8, 0.0)
+    y = _data(oracle, smc.KIND_LG1D, 4)
+    x, w0, _ = smc.bootstrap_filter(20000, y[0], lg, ctx=ctx)
+    first = np.array(w0)
+    _, w1, _ = smc.bootstrap_filter_(x, w0, y[1], lg, resampler="systematic")
+    np.testing.assert_array_equal(np.asarray(w0), first)            # read in time: keeps its values
+    _, w2, _ = smc.bootstrap_filter_(x, w1, y[2], lg, resampler="systematic")
+    with pytest.raises(RuntimeError):
+        np.asarray(w1)                                              # never read while current
+    assert abs(np.asarray(w2).sum() - 1.0) < 1e-12
+
+
 def test_normalize_utility(ctx, oracle):
     rng = np.random.default_rng(0)
     for n in (1, 2, 1000, 2048, 100003):
