@@ -17,6 +17,6 @@ from .particles import (normalize, reweight, resample, bootstrap_filter, bootstr
                         quantile, weighted_mean_var, default_context, set_default_context)
 from .priors import Normal, LogNormal, Uniform, TruncatedNormal, product_distribution  # noqa: E402,F401
 from .smc_samplers import (SMC, smc2, smc2_step, density_tempered, expected_parameters, random_walk_kernel,  # noqa: E402,F401
-                           lg_optimal_proposals, estimated_trend, state_means, state_variances, state_quantiles, get_quantiles, LocalComm, TorchComm)
+                           lg_optimal_proposals, estimated_trend, state_means, state_variances, state_quantiles, get_quantiles, LocalComm, TorchComm, NcclComm)
 from .ibis import IBIS  # noqa: E402,F401
 from . import kalman_filter, ibis, smc_samplers, particles, state_space_models, priors  # noqa: E402,F401
