@@ -365,6 +365,27 @@ def main():
             line["f32_states"] = {"error": repr(e)}
         finally:
             ctx.set_precision("f64")
+        # the binary32-ARITHMETIC tier (docs/SPEC.md §9b: float normals four per Philox block, float4 loads / stores): same workload
+        try:
+            ctx.set_precision("f32_arith")
+            ctx.log_likelihood(smc.KIND_LG1D, LG_PARAMS, N, y, rs, stream=rank)
+            msa, za = 0.0, 0.0
+            for _ in range(2):
+                za = ctx.log_likelihood(smc.KIND_LG1D, LG_PARAMS, N, y, rs, stream=rank)
+                msa += ctx.timing()[0]["total"]
+            ctx.set_profiling(True)
+            ctx.log_likelihood(smc.KIND_LG1D, LG_PARAMS, N, y, rs, stream=rank)
+            ms_, n_ = ctx.timing()
+            ctx.set_profiling(False)
+            va = 2 * N * T / (msa * 1e-3)
+            line["f32_arithmetic"] = {"value": va, "unit": "particle-updates/s", "ms_per_step": msa / 2, "us_per_filter_step": 1e3 * msa / 2 / T,
+                                      "dtype": "f32 normals / model arithmetic / log-weights, u64 CDF", "algorithmic_bytes_per_update": 40,
+                                      "roofline_frac": va * 40 / (peak * 1e9), "logZ": za,
+                                      "avg_us_per_launch": {KERNEL_NAMES[k]: 1e3 * ms_[k] / max(n_[k], 1) for k in KERNEL_NAMES}}
+        except Exception as e:
+            line["f32_arithmetic"] = {"error": repr(e)}
+        finally:
+            ctx.set_precision("f64")
     if rank == 0 and world == 1 and not args.no_cpu:
         v, sample = cpu_sample(2, 20, 64)
         line["cpu_baseline"] = {"value": v, "unit": "particle-updates/s", "cores": 1, "kind": "port", "sample": sample}

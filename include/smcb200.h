@@ -70,8 +70,10 @@ int smcb_record_ancestors(smcb_ctx* ctx, int enable);
 int smcb_set_profiling(smcb_ctx* ctx, int enable);
 /* State storage of the single filter from the next smcb_bootstrap_init / smcb_log_likelihood on:
  * 0 = binary64 (default), 1 = binary32 states (docs/SPEC.md §9: every state component is rounded to
- * binary32 where it is stored, arithmetic stays binary64; sorted resamplers only).  The reference has
- * Float64 only (src/particles.jl:87-147); this is the north star's fp32 tier.  Host-facing arrays stay double. */
+ * binary32 where it is stored, arithmetic stays binary64), 2 = binary32 ARITHMETIC (docs/SPEC.md §9b: float Philox
+ * normals four per block, float model arithmetic and log-weights, float4 loads / stores; the CDF stays uint64).
+ * Tiers 1 and 2: sorted resamplers at any N, multinomial for N > 8192; tier 2 has no guided step.  The reference is
+ * Float64 only (src/particles.jl:87-147); these are the north star's fp32 tier.  Host-facing arrays stay double. */
 int smcb_set_precision(smcb_ctx* ctx, int precision);
 /* device time of the last sweep / step, and per-kernel-class totals when profiling is on:
  * ms[0] whole call, ms[1] sum/scan (quantise + prefix sums + Σe, Σe²), ms[2] gather+propagate+weight
@@ -298,7 +300,8 @@ int smcb_rng_uniforms64(uint64_t seed, uint32_t epoch, uint32_t stream, uint32_t
 /* simulate(model, T) -> (x [d][T], y [T])                               state_space_models.jl:11-28 */
 int smcb_simulate(int kind, const double* params, int64_t T, uint64_t seed, double* x, double* y);
 /* device self-test of the deterministic math (parity tests): fn 0 exp, 1 log, 2 sincos2pi (out0=sin,
- * out1=cos), 3 quantise with shift S = (int)aux -> out0 holds uint64 bit patterns */
+ * out1=cos), 3 quantise with shift S = (int)aux -> out0 holds uint64 bit patterns; 4-7 the same four in the binary32
+ * arithmetic of docs/SPEC.md §9b (inputs rounded to binary32 first, outputs widened exactly) */
 int smcb_selftest_math(smcb_ctx* ctx, int fn, const double* in, int64_t n, double aux, double* out0, double* out1);
 
 #ifdef __cplusplus

@@ -174,4 +174,99 @@ static inline uint64_t o_uniform64(uint64_t seed, uint32_t epoch, uint32_t i, ui
   return (i & 1) ? (((uint64_t)r[2] << 32) | r[3]) : (((uint64_t)r[0] << 32) | r[1]);
 }
 
+
+/* ---- SPEC §9b: the binary32 ARITHMETIC tier (every operation below is an IEEE binary32 operation; only fmaf fuses) ---- */
+static const float OF_MAGIC = 0x1.8p23f;
+static const float OF_LN2_HI = 0x1.62e4p-1f;
+static const float OF_LN2_LO = 0x1.7f7d1cp-20f;
+static const float OF_LOG2E = 0x1.715476p+0f;
+static const float OF_HALF_LOG_2PI = 0x1.d67f1cp-1f;
+static const float OF_SQRT2 = 0x1.6a09e6p+0f;
+/* lowest degree first */
+static const float OF_EXP_E[5] = {0x1.0p-1f, 0x1.5554dcp-3f, 0x1.55551ap-5f, 0x1.120b6ep-7f, 0x1.6d110ap-10f};
+static const float OF_LOG_R[3] = {0x1.55555cp-1f, 0x1.997c2ep-2f, 0x1.2ee656p-2f};
+static const float OF_SINQ_S[4] = {0x1.921fb6p+0f, -0x1.4abbbap-1f, 0x1.465ec2p-4f, -0x1.2d9b1ep-8f};
+static const float OF_COSQ_C[4] = {0x1.0p+0f, -0x1.3bd392p+0f, 0x1.03af58p-2f, -0x1.4e5dd4p-6f};
+
+static inline float of_horner(const float *c, int n, float z) {
+  float acc = c[n - 1];
+  for (int k = n - 2; k >= 0; --k) acc = fmaf(acc, z, c[k]);
+  return acc;
+}
+static inline float of_from_bits(uint32_t b) { float f; memcpy(&f, &b, sizeof f); return f; }
+static inline uint32_t of_to_bits(float f) { uint32_t b; memcpy(&b, &f, sizeof b); return b; }
+static inline void of_exp_parts(float x, float *p, int *k) {
+  float kf = (x * OF_LOG2E + OF_MAGIC) - OF_MAGIC;
+  float r = fmaf(-kf, OF_LN2_HI, x);
+  r = fmaf(-kf, OF_LN2_LO, r);
+  float E = of_horner(OF_EXP_E, 5, r);
+  *p = 1.0f + fmaf(r * r, E, r);
+  *k = (int)kf;
+}
+static inline float of_exp(float x) {
+  if (x < -86.0f) return 0.0f;
+  if (x > 87.0f) return INFINITY;
+  float p;
+  int k;
+  of_exp_parts(x, &p, &k);
+  return of_from_bits(of_to_bits(p) + ((uint32_t)k << 23));
+}
+/* q = min(trunc(exp(x) 2^S), 2^S), x <= 0: exact integer value of p 2^(k+S) for the 24-bit mantissa of p */
+static inline uint64_t of_quant(float x, int S) {
+  if (!(x >= -86.0f)) return 0;
+  float p;
+  int k;
+  of_exp_parts(x, &p, &k);
+  int ep;
+  float fr = frexpf(p, &ep);                       /* p = fr 2^ep, fr in [1/2, 1) */
+  uint64_t M = (uint64_t)ldexpf(fr, 24);           /* 24-bit integer mantissa */
+  int sh = ep - 24 + k + S;
+  uint64_t v = sh >= 0 ? (M << sh) : (sh > -64 ? (M >> (-sh)) : 0);
+  uint64_t cap = (uint64_t)1 << S;
+  return v < cap ? v : cap;
+}
+static inline float of_log(float u) {
+  uint32_t b = of_to_bits(u);
+  int e = (int)((b >> 23) & 0xFF) - 127;
+  float m = of_from_bits((b & 0x007FFFFFu) | 0x3F800000u);
+  if (m > OF_SQRT2) {
+    m = m * 0.5f;
+    e = e + 1;
+  }
+  float f = m - 1.0f;
+  float s = f / (2.0f + f);
+  float z = s * s;
+  float lm = fmaf(s * z, of_horner(OF_LOG_R, 3, z), s + s);
+  return fmaf((float)e, OF_LN2_HI, fmaf((float)e, OF_LN2_LO, lm));
+}
+static inline void of_sincos2pi(float u, float *sn, float *cs) {
+  float a = 4.0f * u;
+  float nf = (a + OF_MAGIC) - OF_MAGIC;
+  float r = a - nf;
+  int n = ((int)nf) & 3;
+  float z = r * r;
+  float sr = r * of_horner(OF_SINQ_S, 4, z);
+  float cr = of_horner(OF_COSQ_C, 4, z);
+  switch (n) {
+    case 0: *sn = sr; *cs = cr; break;
+    case 1: *sn = cr; *cs = -sr; break;
+    case 2: *sn = -sr; *cs = -cr; break;
+    default: *sn = -cr; *cs = sr; break;
+  }
+}
+/* particle i uses the Philox block at index i >> 2: words (r0, r1) -> the Box-Muller pair of particles 4q, 4q+1, (r2, r3) -> 4q+2, 4q+3 */
+static inline float of_normal(uint64_t seed, uint32_t epoch, uint32_t i, uint32_t stream, uint32_t t, uint32_t kind, uint32_t comp) {
+  uint32_t ctr[4] = {i >> 2, stream, t, o_purpose(kind, comp, epoch)};
+  uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  uint32_t r[4];
+  o_philox(ctr, key, r);
+  int h = (i >> 1) & 1;
+  float u1 = (float)(2u * (r[2 * h] >> 9) + 1u) * 0x1p-24f;
+  float u2 = (float)(2u * (r[2 * h + 1] >> 9) + 1u) * 0x1p-24f;
+  float rho = sqrtf(-2.0f * of_log(u1));
+  float sn, cs;
+  of_sincos2pi(u2, &sn, &cs);
+  return (i & 1) ? rho * sn : rho * cs;
+}
+
 #endif

@@ -223,6 +223,48 @@ def resample_w(w, resampler, seed, epoch, stream, t, purpose=P_RESAMPLE, n_out=N
     return a
 
 
+def detf(fn, x, S=0):
+    """the binary32 functions of docs/SPEC.md §9b on values rounded to binary32: fn in 'exp', 'log', 'sincos', 'quant'"""
+    x = np.ascontiguousarray(x, np.float64)
+    if fn == "sincos":
+        s, c = np.empty_like(x), np.empty_like(x)
+        lib().smco_sincos2pif(_p(x), _p(s), _p(c), C.c_int64(x.size))
+        return s, c
+    if fn == "quant":
+        q = np.empty(x.size, np.uint64)
+        lib().smco_quantf(_p(x), C.c_int(S), _p(q), C.c_int64(x.size))
+        return q
+    out = np.empty_like(x)
+    getattr(lib(), "smco_expf" if fn == "exp" else "smco_logf")(_p(x), _p(out), C.c_int64(x.size))
+    return out
+
+
+class arith_f32:
+    """`with oracle.arith_f32(): ...` runs the filters in SPEC §9b's binary32-ARITHMETIC tier (float normals four per Philox block,
+    float model arithmetic, float exponential behind the fixed-point weights); states / log-weights come back as binary32 values."""
+
+    def __init__(self, on=True):
+        self.on = bool(on)
+
+    def __enter__(self):
+        self.prev = lib().smco_get_arith_f32()
+        lib().smco_set_arith_f32(C.c_int(1 if self.on else 0))
+        return self
+
+    def __exit__(self, *exc):
+        lib().smco_set_arith_f32(C.c_int(self.prev))
+        return False
+
+
+def normalize_f32(logw):
+    """normalize() of the binary32-arithmetic tier: expf in binary32, sums in binary64"""
+    logw = np.ascontiguousarray(logw, np.float64)
+    w = np.empty_like(logw)
+    lm, es = C.c_double(), C.c_double()
+    lib().smco_normalize_f32(_p(logw), C.c_int64(logw.size), C.byref(lm), _p(w), C.byref(es))
+    return lm.value, w, es.value
+
+
 class state_f32:
     """`with oracle.state_f32(): ...` runs the filters in SPEC §9's binary32-state tier (states rounded to
     binary32 where the device stores them; arithmetic unchanged)."""

@@ -32,6 +32,7 @@
 
 enum { KIND_LG1D = 0, KIND_SV = 1, KIND_UCSV = 2 };
 enum { RS_MULTINOMIAL = 0, RS_STRATIFIED = 1, RS_SYSTEMATIC = 2 };
+static int g_arith_f32 = 0;   /* SPEC §9b tier switch (set by smco_set_arith_f32 below) */
 enum { P_INIT = 1, P_TRANS = 2, P_RESAMPLE = 3, P_SIMULATE = 8, P_RESAMPLE_CELL = 9 };
 
 int smco_state_dim(int kind) { return kind == KIND_UCSV ? 3 : 1; }
@@ -40,6 +41,12 @@ int smco_state_dim(int kind) { return kind == KIND_UCSV ? 3 : 1; }
 void smco_philox(const uint32_t *ctr, const uint32_t *key, uint32_t *out) { o_philox(ctr, key, out); }
 void smco_exp(const double *x, double *y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = o_exp(x[i]); }
 void smco_log(const double *x, double *y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = o_log(x[i]); }
+void smco_expf(const double *x, double *y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = (double)of_exp((float)x[i]); }
+void smco_logf(const double *x, double *y, int64_t n) { for (int64_t i = 0; i < n; ++i) y[i] = (double)of_log((float)x[i]); }
+void smco_sincos2pif(const double *u, double *s, double *c, int64_t n) {
+  for (int64_t i = 0; i < n; ++i) { float a, b; of_sincos2pi((float)u[i], &a, &b); s[i] = (double)a; c[i] = (double)b; }
+}
+void smco_quantf(const double *x, int S, uint64_t *q, int64_t n) { for (int64_t i = 0; i < n; ++i) q[i] = of_quant((float)x[i], S); }
 void smco_sincos2pi(const double *u, double *s, double *c, int64_t n) {
   for (int64_t i = 0; i < n; ++i) o_sincos2pi(u[i], &s[i], &c[i]);
 }
@@ -230,7 +237,11 @@ void smco_ancestors(const double *logw, int64_t n, int resampler, uint64_t seed,
   double mx = -INFINITY;
   for (int64_t i = 0; i < n; ++i) if (logw[i] > mx) mx = logw[i];
   uint64_t *q = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)n);
-  for (int64_t i = 0; i < n; ++i) q[i] = o_quant(logw[i] - mx, S);
+  if (g_arith_f32) {
+    for (int64_t i = 0; i < n; ++i) q[i] = of_quant((float)logw[i] - (float)mx, S);
+  } else {
+    for (int64_t i = 0; i < n; ++i) q[i] = o_quant(logw[i] - mx, S);
+  }
   if (resampler == RS_MULTINOMIAL && n > MN_LEGACY_MAX) ancestors_two_level(q, n, seed, epoch, stream, t, anc);
   else ancestors_from_q(q, n, resampler, seed, epoch, stream, t, P_RESAMPLE, anc);
   free(q);
@@ -273,6 +284,53 @@ static inline void round_state(double *xi, int d) {
     for (int k = 0; k < d; ++k) xi[k] = (double)(float)xi[k];
 }
 
+/* SPEC §9b: the binary32 ARITHMETIC tier.  When set, the normals (four per Philox block), the model arithmetic, the log-weights
+ * and the exponential behind the fixed-point weights are binary32; states and log-weights are binary32 values (held in the
+ * double arrays of this interface), the CDF / thresholds / ancestors machinery is unchanged.  Process-global like the state tier. */
+void smco_set_arith_f32(int on) { g_arith_f32 = on ? 1 : 0; }
+int smco_get_arith_f32(void) { return g_arith_f32; }
+static void modelf_init(int kind, const float *D, const float *z, float *x) {
+  if (kind == KIND_LG1D) x[0] = fmaf(D[4], z[0], D[3]);
+  else if (kind == KIND_SV) x[0] = fmaf(D[3], z[0], D[0]);
+  else { x[0] = fmaf(D[5], z[0], D[2]); x[1] = fmaf(D[0], z[1], D[3]); x[2] = fmaf(D[1], z[2], D[4]); }
+}
+static void modelf_transition(int kind, const float *D, const float *z, const float *xp, float *x) {
+  if (kind == KIND_LG1D) x[0] = fmaf(D[2], z[0], D[0] * xp[0]);
+  else if (kind == KIND_SV) x[0] = fmaf(D[2], z[0], fmaf(D[1], xp[0] - D[0], D[0]));
+  else {
+    float sd = of_exp(0.5f * xp[1]);
+    x[0] = fmaf(sd, z[0], xp[0]);
+    x[1] = fmaf(D[0], z[1], xp[1]);
+    x[2] = fmaf(D[1], z[2], xp[2]);
+  }
+}
+static float modelf_logweight(int kind, const float *D, const float *x, float y) {
+  if (kind == KIND_LG1D) {
+    float v = (y - D[1] * x[0]) * D[5];
+    return fmaf(-0.5f * v, v, D[6]);
+  } else if (kind == KIND_SV) {
+    return fmaf(-0.5f * (y * y), of_exp(-x[0]), -(fmaf(0.5f, x[0], OF_HALF_LOG_2PI)));
+  } else {
+    float d = y - x[0];
+    return fmaf(-0.5f * (d * d), of_exp(-x[2]), -(fmaf(0.5f, x[2], OF_HALF_LOG_2PI)));
+  }
+}
+static void derive_f(int kind, const double *P, float *Df) {   /* the binary64 derived block rounded once to binary32 */
+  double D[8];
+  smco_derive(kind, P, D);
+  for (int i = 0; i < 8; ++i) Df[i] = (float)D[i];
+}
+/* normalize() in the tier: e_i = expf(logw_i - max) in binary32, the sums in binary64 */
+void smco_normalize_f32(const double *logw, int64_t n, double *logmu, double *w, double *ess) {
+  float maxw = -INFINITY;
+  for (int64_t i = 0; i < n; ++i) if ((float)logw[i] > maxw) maxw = (float)logw[i];
+  double sumw = 0.0, sum2 = 0.0;
+  for (int64_t i = 0; i < n; ++i) { double e = (double)of_exp((float)logw[i] - maxw); sumw += e; sum2 += e * e; }
+  *logmu = (double)maxw + log(sumw) - log((double)n);
+  *ess = (sumw * sumw) / sum2;
+  if (w) for (int64_t i = 0; i < n; ++i) w[i] = (double)of_exp((float)logw[i] - maxw) / sumw;
+}
+
 /* ------------------------------------------------------------------ a3 bootstrap_filter */
 /* x is SoA [d][n]. */
 void smco_bootstrap_init(int kind, const double *P, int64_t n, double y, uint64_t seed, uint32_t epoch,
@@ -280,6 +338,18 @@ void smco_bootstrap_init(int kind, const double *P, int64_t n, double y, uint64_
   double D[8];
   smco_derive(kind, P, D);
   int d = smco_state_dim(kind);
+  if (g_arith_f32) {
+    float Df[8];
+    derive_f(kind, P, Df);
+    for (int64_t i = 0; i < n; ++i) {
+      float z[3] = {0, 0, 0}, xi[3];
+      for (int k = 0; k < d; ++k) z[k] = of_normal(seed, epoch, (uint32_t)i, stream, 0, P_INIT, (uint32_t)k);
+      modelf_init(kind, Df, z, xi);
+      for (int k = 0; k < d; ++k) x[(int64_t)k * n + i] = (double)xi[k];
+      logw[i] = (double)modelf_logweight(kind, Df, xi, (float)y);
+    }
+    return;
+  }
   for (int64_t i = 0; i < n; ++i) {                                         /* :96-99 */
     double z[3] = {0, 0, 0}, xi[3];
     for (int k = 0; k < d; ++k) z[k] = o_normal(seed, epoch, (uint32_t)i, stream, 0, P_INIT, (uint32_t)k);
@@ -301,6 +371,24 @@ void smco_bootstrap_step(int kind, const double *P, int64_t n, double y, uint32_
   double *xp = (double *)malloc(sizeof(double) * (size_t)(n * d));         /* xp = deepcopy(x[a]) :119 */
   for (int k = 0; k < d; ++k)
     for (int64_t i = 0; i < n; ++i) xp[(int64_t)k * n + i] = x[(int64_t)k * n + a[i]];
+  if (g_arith_f32) {
+    float Df[8];
+    derive_f(kind, P, Df);
+    for (int64_t i = 0; i < n; ++i) {
+      float z[3] = {0, 0, 0}, par[3] = {0, 0, 0}, xi[3];
+      for (int k = 0; k < d; ++k) {
+        z[k] = of_normal(seed, epoch, (uint32_t)i, stream, t, P_TRANS, (uint32_t)k);
+        par[k] = (float)xp[(int64_t)k * n + i];
+      }
+      modelf_transition(kind, Df, z, par, xi);
+      for (int k = 0; k < d; ++k) x[(int64_t)k * n + i] = (double)xi[k];
+      logw[i] = (double)modelf_logweight(kind, Df, xi, (float)y);
+    }
+    if (anc_out) memcpy(anc_out, a, sizeof(int64_t) * (size_t)n);
+    free(xp);
+    free(a);
+    return;
+  }
   for (int64_t i = 0; i < n; ++i) {                                         /* :122-125 */
     double z[3] = {0, 0, 0}, par[3] = {0, 0, 0}, xi[3];
     for (int k = 0; k < d; ++k) {
@@ -397,14 +485,14 @@ double smco_log_likelihood(int kind, const double *P, int64_t n, const double *y
   double *lw = logw ? logw : (double *)malloc(sizeof(double) * (size_t)n);
   double logZ = 0.0, lm, es;
   smco_bootstrap_init(kind, P, n, y[0], seed, epoch, stream, xl, lw);       /* :139 */
-  smco_normalize(lw, n, &lm, NULL, &es);
+  (g_arith_f32 ? smco_normalize_f32 : smco_normalize)(lw, n, &lm, NULL, &es);
   logZ = lm;
   if (logmu_out) logmu_out[0] = lm;
   if (ess_out) ess_out[0] = es;
   for (int64_t t = 1; t < T; ++t) {                                         /* :141-144 */
     smco_bootstrap_step(kind, P, n, y[t], (uint32_t)t, resampler, seed, epoch, stream, xl, lw,
                         anc_out ? anc_out + t * n : NULL);
-    smco_normalize(lw, n, &lm, NULL, &es);
+    (g_arith_f32 ? smco_normalize_f32 : smco_normalize)(lw, n, &lm, NULL, &es);
     logZ += lm;
     if (logmu_out) logmu_out[t] = lm;
     if (ess_out) ess_out[t] = es;

@@ -307,7 +307,7 @@ class Context:
     def set_precision(self, precision):
         """State storage of the single filter from the next bootstrap_init / log_likelihood on: "f64" (default)
         or "f32" (docs/SPEC.md §9: states rounded to binary32 where stored, arithmetic binary64, sorted resamplers)."""
-        p = {"f64": 0, "f32": 1, 0: 0, 1: 1, "float64": 0, "float32": 1}[precision]
+        p = {"f64": 0, "f32": 1, 0: 0, 1: 1, 2: 2, "float64": 0, "float32": 1, "f32_states": 1, "f32_arith": 2, "f32_arithmetic": 2}[precision]
         self._check(self._lib.smcb_set_precision(self._h, p))
 
     def timing(self):

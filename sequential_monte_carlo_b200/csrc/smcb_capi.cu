@@ -11,6 +11,7 @@
 #include "smcb_batch.cuh"
 #include "smcb_filter.cuh"
 #include "smcb_sampler.cuh"
+#include "smcb_detmathf.cuh"
 
 using namespace smcb;
 
@@ -141,7 +142,7 @@ int smcb_set_profiling(smcb_ctx* ctx, int enable) {
 }
 
 int smcb_set_precision(smcb_ctx* ctx, int precision) {
-  if (!ctx || precision < 0 || precision > 1) return SMCB_ERR_BAD_ARG;
+  if (!ctx || precision < 0 || precision > 2) return SMCB_ERR_BAD_ARG;
   ctx->filter->set_precision(precision);
   return SMCB_OK;
 }
@@ -726,7 +727,12 @@ __global__ void selftest_kernel(int fn, const double* in, int64_t n, double aux,
   if (fn == 0) o0[i] = det_exp(v);
   else if (fn == 1) o0[i] = det_log(v);
   else if (fn == 2) { double s, c; det_sincos2pi(v, s, c); o0[i] = s; o1[i] = c; }
-  else { double e; uint64_t q; det_exp_quant(v, (int)aux, e, q); o0[i] = u64_as_double(q); o1[i] = e; }
+  else if (fn == 3) { double e; uint64_t q; det_exp_quant(v, (int)aux, e, q); o0[i] = u64_as_double(q); o1[i] = e; }
+  // the binary32 functions of SPEC §9b (inputs are rounded to binary32 first, outputs widened exactly)
+  else if (fn == 4) o0[i] = (double)det_expf((float)v);
+  else if (fn == 5) o0[i] = (double)det_logf((float)v);
+  else if (fn == 6) { float s, c; det_sincos2pif((float)v, s, c); o0[i] = (double)s; o1[i] = (double)c; }
+  else { float e; uint64_t q; det_exp_quantf((float)v, (int)aux, e, q); o0[i] = u64_as_double(q); o1[i] = (double)e; }
 }
 }  // namespace
 
@@ -745,7 +751,7 @@ int smcb_simulate(int kind, const double* params, int64_t T, uint64_t seed, doub
 int smcb_selftest_math(smcb_ctx* ctx, int fn, const double* in, int64_t n, double aux, double* out0, double* out1) {
   if (!ctx) return SMCB_ERR_BAD_ARG;
   return guarded(ctx, [&] {
-    need(in && out0 && n >= 1 && fn >= 0 && fn <= 3, "selftest_math: bad arguments");
+    need(in && out0 && n >= 1 && fn >= 0 && fn <= 7, "selftest_math: bad arguments");
     SMCB_CUDA_TRY(cudaSetDevice(ctx->device));
     double *di = nullptr, *d0 = nullptr, *d1 = nullptr;
     cudaError_t e = cudaMalloc(&di, sizeof(double) * n);
@@ -757,7 +763,7 @@ int smcb_selftest_math(smcb_ctx* ctx, int fn, const double* in, int64_t n, doubl
       e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaMemcpyAsync(out0, d0, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess && out1 && fn >= 2) e = cudaMemcpyAsync(out1, d1, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess && out1 && (fn == 2 || fn == 3 || fn >= 6)) e = cudaMemcpyAsync(out1, d1, sizeof(double) * n, cudaMemcpyDeviceToHost, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     cudaFree(di); cudaFree(d0); cudaFree(d1);
     SMCB_CUDA_TRY(e);

@@ -21,6 +21,7 @@
 #include <type_traits>
 
 #include "smcb_filter.cuh"
+#include "smcb_detmathf.cuh"
 
 namespace smcb {
 
@@ -458,7 +459,8 @@ constexpr int kSysPer = 16;                            // particles per thread: 
 constexpr int kSysParticles = kSysThreads * kSysPer;   // 2048 particles per ancestor CTA
 
 
-template <class XT>  // XT: the element type behind `logw` — double (log-weights, or binary64 states when from_x) or float (binary32 states, from_x only)
+// AT: arithmetic of the weights — double, or float = the binary32-arithmetic tier of SPEC §9b (the elements are then binary32 too)
+template <class XT, class AT = double>  // XT: the element type behind `logw` — double (log-weights, or binary64 states when from_x) or float (binary32 states / log-weights)
 __global__ void __launch_bounds__(kSumThreads, kSumCtasPerSm)
     sum_kernel(const XT* __restrict__ logw, unsigned long long* __restrict__ cl, int64_t N, int S, FilterCtrl* ctrl,
                StepIndex ix, double* psum, double* psum2, StepStats* stats_out, int slot, int resampler, uint64_t Rw,
@@ -497,19 +499,40 @@ __global__ void __launch_bounds__(kSumThreads, kSumCtasPerSm)
     auto process = [&](auto full_tag, int c, double (&lw)[4]) {
       constexpr bool FULL = decltype(full_tag)::value;
       const int64_t base = tile0 + (int64_t)c * kChunk + lane * 4;
-      if (from_x) {  // (partial chunk: out-of-range items were loaded as -inf and their "weight" must stay -inf)
-#pragma unroll
-        for (int k = 0; k < 4; ++k) lw[k] = (FULL || base + k < N) ? lg_logweight(lw[k]) : -INFINITY;
-      }
       unsigned long long q[4];
+      if constexpr (std::is_same<AT, float>::value) {
+        // binary32 arithmetic (SPEC §9b): the elements are binary32 values (carried here as doubles, exactly); the log-weight
+        // of an LG1D state, the shift by the max and the exponential are binary32 operations, the two sums binary64
+        const float fB = (float)dv.d[1], fir = (float)dv.d[5], fc = (float)dv.d[6], fy = (float)ycur, fmx = (float)mx;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {  // out-of-range items carry logw = -inf: e = 0, q = 0
-        double e;
-        uint64_t qq;
-        det_exp_quant_stream(lw[k] - mx, S, e, qq);
-        se += e;
-        se2 += e * e;
-        q[k] = qq;
+        for (int k = 0; k < 4; ++k) {
+          float lf = (float)lw[k];
+          if (from_x) {
+            const float v = (fy - fB * lf) * fir;
+            lf = (FULL || base + k < N) ? fmaf(-0.5f * v, v, fc) : -INFINITY;
+          }
+          float ef;
+          uint64_t qq;
+          det_exp_quantf(lf - fmx, S, ef, qq);
+          const double e = (double)ef;
+          se += e;
+          se2 += e * e;
+          q[k] = qq;
+        }
+      } else {
+        if (from_x) {  // (partial chunk: out-of-range items were loaded as -inf and their "weight" must stay -inf)
+#pragma unroll
+          for (int k = 0; k < 4; ++k) lw[k] = (FULL || base + k < N) ? lg_logweight(lw[k]) : -INFINITY;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {  // out-of-range items carry logw = -inf: e = 0, q = 0
+          double e;
+          uint64_t qq;
+          det_exp_quant_stream(lw[k] - mx, S, e, qq);
+          se += e;
+          se2 += e * e;
+          q[k] = qq;
+        }
       }
       q[1] += q[0];
       q[2] += q[1];
@@ -1595,6 +1618,142 @@ __global__ void __launch_bounds__(kMoveThreads, 4)
   }
 }
 
+// ================================================================================================
+// The binary32-ARITHMETIC tier (docs/SPEC.md §9b): four particles per thread = one Philox block per state component, float
+// Box-Muller / model arithmetic / log-weights, 16-byte float4 loads and stores.  Everything between the weights and the
+// ancestors (sum_kernel<float, float> -> bounds / anc_hist or the two-level multinomial kernels) is shared with the other tiers.
+template <class ModelF>
+__global__ void __launch_bounds__(256) init_kernel_f(DerivedF dv, float y0, int64_t N, int64_t ld, RngKey key, uint32_t stream,
+                                                      float* __restrict__ x, float* __restrict__ logw, FilterCtrl* ctrl) {
+  constexpr int D = ModelF::D;
+  __shared__ double sh[32];
+  ModelF mdl;
+  mdl.load(dv.d);
+  const int64_t nquads = (N + 3) >> 2;
+  const int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  double vmax = -INFINITY;
+  if (q < nquads) {
+    float z[D][4];
+#pragma unroll
+    for (int k = 0; k < D; ++k) normal_quadf_at(key, (uint32_t)q, stream, 0u, PURPOSE_INIT, (uint32_t)k, z[k]);
+    float xo[D][4], lw[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      float zi[D], xi[D];
+#pragma unroll
+      for (int k = 0; k < D; ++k) zi[k] = z[k][h];
+      mdl.init(zi, xi);
+      lw[h] = mdl.logweight(xi, y0);
+#pragma unroll
+      for (int k = 0; k < D; ++k) xo[k][h] = xi[k];
+    }
+    const int64_t i = 4 * q;
+    if (i + 3 < N) {
+#pragma unroll
+      for (int k = 0; k < D; ++k) *reinterpret_cast<float4*>(x + k * ld + i) = make_float4(xo[k][0], xo[k][1], xo[k][2], xo[k][3]);
+      *reinterpret_cast<float4*>(logw + i) = make_float4(lw[0], lw[1], lw[2], lw[3]);
+#pragma unroll
+      for (int h = 0; h < 4; ++h)
+        if ((double)lw[h] > vmax) vmax = (double)lw[h];
+    } else {
+      for (int h = 0; h < 4 && i + h < N; ++h) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) x[k * ld + i + h] = xo[k][h];
+        logw[i + h] = lw[h];
+        if ((double)lw[h] > vmax) vmax = (double)lw[h];
+      }
+    }
+  }
+  const double bm = block_max(vmax, sh);
+  if (threadIdx.x == 0) atomicMax(&ctrl->maxslot[0], encode_ordered(bm));
+}
+
+template <class ModelF>
+__global__ void __launch_bounds__(kMoveThreads, (ModelF::D == 1) ? 6 : 3)
+    move_kernel_f(DerivedF dv, float y, int N, int64_t ld, RngKey key, uint32_t stream, uint32_t t, const int32_t* __restrict__ anc,
+                  const float* __restrict__ xprev, float* __restrict__ xnew, float* __restrict__ logw /* null: not stored */, FilterCtrl* ctrl) {
+  constexpr int D = ModelF::D;
+  constexpr int NW = kMoveThreads / 32;
+  __shared__ unsigned long long s_max[NW];
+  const int tid = threadIdx.x;
+  ModelF mdl;
+  mdl.load(dv.d);
+  const int q = blockIdx.x * kMoveThreads + tid;
+  const int i0 = 4 * q;
+  pdl_launch_dependents();
+  pdl_wait();  // the ancestors come from anc_hist_kernel / mn_cell_kernel
+  double vmax = -INFINITY;
+  if (i0 < N) {
+    const bool full = i0 + 3 < N;
+    int a[4];
+    if (full) {
+      const int4 v = __ldcs(reinterpret_cast<const int4*>(anc + i0));
+      a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w;
+    } else {
+#pragma unroll
+      for (int h = 0; h < 4; ++h) a[h] = (i0 + h < N) ? anc[i0 + h] : 0;
+    }
+    float xp[D][4];
+#pragma unroll
+    for (int k = 0; k < D; ++k)
+#pragma unroll
+      for (int h = 0; h < 4; ++h) xp[k][h] = __ldg(&xprev[k * ld + a[h]]);
+    float z[D][4];
+#pragma unroll
+    for (int k = 0; k < D; ++k) normal_quadf_at(key, (uint32_t)q, stream, t, PURPOSE_TRANSITION, (uint32_t)k, z[k]);
+    float xo[D][4], lw[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      float zi[D], pi[D], xi[D];
+#pragma unroll
+      for (int k = 0; k < D; ++k) { zi[k] = z[k][h]; pi[k] = xp[k][h]; }
+      mdl.transition(zi, pi, xi);
+      lw[h] = mdl.logweight(xi, y);
+#pragma unroll
+      for (int k = 0; k < D; ++k) xo[k][h] = xi[k];
+    }
+    if (full) {
+#pragma unroll
+      for (int k = 0; k < D; ++k) *reinterpret_cast<float4*>(xnew + k * ld + i0) = make_float4(xo[k][0], xo[k][1], xo[k][2], xo[k][3]);
+      if (logw) *reinterpret_cast<float4*>(logw + i0) = make_float4(lw[0], lw[1], lw[2], lw[3]);
+#pragma unroll
+      for (int h = 0; h < 4; ++h)
+        if ((double)lw[h] > vmax) vmax = (double)lw[h];  // `>` ignores NaN like the CPU loop
+    } else {
+      for (int h = 0; h < 4 && i0 + h < N; ++h) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) xnew[k * ld + i0 + h] = xo[k][h];
+        if (logw) logw[i0 + h] = lw[h];
+        if ((double)lw[h] > vmax) vmax = (double)lw[h];
+      }
+    }
+  }
+  const unsigned long long wm = warp_max_ordered(encode_ordered(vmax));
+  if ((tid & 31) == 0) s_max[tid >> 5] = wm;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long m = s_max[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) m = s_max[w] > m ? s_max[w] : m;
+    atomicMax(&ctrl->maxslot[t & 1u], m);
+  }
+}
+
+// LG1D log-weights of the tier, materialised when a caller fetches them; and w_i = expf(logw_i - max) / Σe
+__global__ void logw_kernel_f(DerivedF dv, float y, int64_t N, const float* __restrict__ x, float* __restrict__ logw) {
+  ModelLG1Df mdl;
+  mdl.load(dv.d);
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) {
+    const float xi = x[i];
+    logw[i] = mdl.logweight(&xi, y);
+  }
+}
+__global__ void weights_kernel_f(const float* __restrict__ logw, double* __restrict__ w, int64_t N, StepStats st) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) w[i] = (double)det_expf(logw[i] - (float)st.mx) / st.sum;
+}
+
 // logw_i = logpdf(observation(x_i), y): materialises the log-weights that the LG1D step does not store
 template <class XT>
 __global__ void logw_kernel(Derived dv, double y, int64_t N, const XT* __restrict__ x, double* __restrict__ logw) {
@@ -1748,6 +1907,21 @@ void dispatch_model(int kind, F&& f) {
 
 }  // namespace
 
+static DerivedF to_float(const Derived& d) {
+  DerivedF f;
+  for (int i = 0; i < kParamStride; ++i) f.d[i] = (float)d.d[i];
+  return f;
+}
+template <class F>
+static void dispatch_model_f(int kind, F&& f) {
+  switch (kind) {
+    case KIND_LG1D: f(ModelLG1Df{}); break;
+    case KIND_SV: f(ModelSVf{}); break;
+    case KIND_UCSV: f(ModelUCSVf{}); break;
+    default: throw Error{SMCB_ERR_BAD_ARG, "unknown model kind"};
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 SingleFilter::~SingleFilter() {
   release();
@@ -1865,6 +2039,13 @@ void SingleFilter::timing(double ms[TK_COUNT], int64_t launches[TK_COUNT]) const
 
 void SingleFilter::ensure_logw() {
   if (logw_valid_ || !live()) return;
+  if (prec_ == 2) {
+    logw_kernel_f<<<(unsigned)((N_ + 255) / 256), 256, 0, stream_>>>(to_float(dv_w_), (float)y_cur_, N_, reinterpret_cast<const float*>(x_[cur_]),
+                                                                   reinterpret_cast<float*>(logw_[cur_]));
+    SMCB_CUDA_TRY(cudaGetLastError());
+    logw_valid_ = true;
+    return;
+  }
   dispatch_xt(prec_, [&](auto tag) {
     using XT = decltype(tag);
     logw_kernel<XT><<<(unsigned)((N_ + 255) / 256), 256, 0, stream_>>>(dv_w_, y_cur_, N_, reinterpret_cast<const XT*>(x_[cur_]), logw_[cur_]);
@@ -1883,6 +2064,14 @@ void SingleFilter::launch_init(double y0) {
   const int64_t npairs = (N_ + 1) / 2;
   const unsigned grid = (unsigned)((npairs + 255) / 256);
   mark(TK_INIT, true);
+  if (prec_ == 2) {
+    const unsigned qgrid = (unsigned)(((N_ + 3) / 4 + 255) / 256);
+    dispatch_model_f(kind_, [&](auto m) {
+      using M = decltype(m);
+      init_kernel_f<M><<<qgrid, 256, 0, stream_>>>(to_float(dv_), (float)y0, N_, ld_, key_, stream_id_, reinterpret_cast<float*>(x_[cur_]),
+                                                  reinterpret_cast<float*>(logw_[cur_]), ctrl_);
+    });
+  } else
   dispatch_model(kind_, [&](auto m) {
     using M = decltype(m);
     dispatch_xt(prec_, [&](auto tag) {
@@ -1977,7 +2166,11 @@ void SingleFilter::launch_sum(int64_t stat_index) {
   const uint32_t t = t_ + 1;
   mark(TK_SCAN, true);
   const int from_x = logw_valid_ ? 0 : 1;  // the previous LG1D step kept its log-weights implicit in x
-  if (from_x && prec_)
+  if (prec_ == 2)  // binary32 arithmetic: the states AND the stored log-weights are binary32
+    SMCB_CUDA_TRY(launch_pdl(sum_kernel<float, float>, dim3((ix.ntiles + kSumWarps - 1) / kSumWarps), dim3(kSumThreads), stream_,
+                             from_x ? reinterpret_cast<const float*>(x_[cur_]) : reinterpret_cast<const float*>(logw_[cur_]), cl, N_, S_, ctrl_, ix, psum_,
+                             psum2_, stats_dev_ + stat_index, (int)(t_ & 1u), (int)RESAMPLE_SYSTEMATIC, R_, key_, stream_id_, t, from_x, dv_w_, y_cur_));
+  else if (from_x && prec_)
     SMCB_CUDA_TRY(launch_pdl(sum_kernel<float>, dim3((ix.ntiles + kSumWarps - 1) / kSumWarps), dim3(kSumThreads), stream_,
                              reinterpret_cast<const float*>(x_[cur_]), cl, N_, S_, ctrl_, ix, psum_, psum2_, stats_dev_ + stat_index, (int)(t_ & 1u),
                              (int)RESAMPLE_SYSTEMATIC, R_, key_, stream_id_, t, from_x, dv_w_, y_cur_));
@@ -1994,6 +2187,7 @@ void SingleFilter::launch_sum(int64_t stat_index) {
 void SingleFilter::launch_step(int64_t stat_index, double y, int resampler, const double* proposal) {
   ProposalCoef pc{};
   if (proposal) {  // guided step (docs/SPEC.md §10): sorted resamplers, one-dimensional models
+    if (prec_ == 2) throw Error{SMCB_ERR_UNSUPPORTED, "guided proposals are not built for the binary32-arithmetic tier (docs/SPEC.md §9b)"};
     if (d_ != 1) throw Error{SMCB_ERR_UNSUPPORTED, "guided proposals are defined for the one-dimensional models (LG1D, SV)"};
     if (legacy_multinomial(resampler))
       throw Error{SMCB_ERR_UNSUPPORTED, "guided single filter with N <= 8192: stratified or systematic resampling (multinomial guided filters of that size run on the batched engine)"};
@@ -2082,6 +2276,14 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler, cons
       else
         SMCB_CUDA_TRY(launch_pdl(guided_move_kernel<ModelSV, XT>, dim3(mblocks), dim3(kMoveThreads), stream_, dv_, pc, y, (int)N_, key_, stream_id_, t,
                                  anc, reinterpret_cast<const XT*>(x_[cur_]), reinterpret_cast<XT*>(x_[cur_ ^ 1]), logw_[cur_ ^ 1], ctrl_));
+    });
+  } else if (prec_ == 2) {
+    const unsigned qblocks = (unsigned)(((N_ + 3) / 4 + kMoveThreads - 1) / kMoveThreads);
+    dispatch_model_f(kind_, [&](auto m) {
+      using M = decltype(m);
+      SMCB_CUDA_TRY(launch_pdl(move_kernel_f<M>, dim3(qblocks), dim3(kMoveThreads), stream_, to_float(dv_), (float)y, (int)N_, ld_, key_, stream_id_, t,
+                               (const int32_t*)anc, reinterpret_cast<const float*>(x_[cur_]), reinterpret_cast<float*>(x_[cur_ ^ 1]),
+                               implicit_logw ? (float*)nullptr : reinterpret_cast<float*>(logw_[cur_ ^ 1]), ctrl_));
     });
   } else
   dispatch_model(kind_, [&](auto m) {
@@ -2284,10 +2486,17 @@ void SingleFilter::fetch(double* x_host, double* w_host, double* logw_host) {
     }
   }
   if (logw_host || w_host) ensure_logw();
-  if (logw_host)
+  if (logw_host && prec_ == 2) {  // binary32 log-weights, widened like the states
+    if (!w_tmp_) SMCB_CUDA_TRY(cudaMalloc(&w_tmp_, sizeof(double) * cap_N_));
+    widen_kernel<<<(unsigned)((N_ + 255) / 256), 256, 0, stream_>>>(reinterpret_cast<const float*>(logw_[cur_]), w_tmp_, N_);
+    SMCB_CUDA_TRY(cudaGetLastError());
+    SMCB_CUDA_TRY(cudaMemcpyAsync(logw_host, w_tmp_, sizeof(double) * N_, cudaMemcpyDeviceToHost, stream_));
+  } else if (logw_host)
     SMCB_CUDA_TRY(cudaMemcpyAsync(logw_host, logw_[cur_], sizeof(double) * N_, cudaMemcpyDeviceToHost, stream_));
   if (w_host) {
     if (!w_tmp_) SMCB_CUDA_TRY(cudaMalloc(&w_tmp_, sizeof(double) * cap_N_));
+    if (prec_ == 2) weights_kernel_f<<<(unsigned)((N_ + 255) / 256), 256, 0, stream_>>>(reinterpret_cast<const float*>(logw_[cur_]), w_tmp_, N_, last_);
+    else
     weights_kernel<<<(unsigned)((N_ + 255) / 256), 256, 0, stream_>>>(logw_[cur_], w_tmp_, N_, last_);
     SMCB_CUDA_TRY(cudaGetLastError());
     SMCB_CUDA_TRY(cudaMemcpyAsync(w_host, w_tmp_, sizeof(double) * N_, cudaMemcpyDeviceToHost, stream_));

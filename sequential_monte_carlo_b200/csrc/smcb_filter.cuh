@@ -71,8 +71,8 @@ class SingleFilter {
 
   void set_record_ancestors(bool on) { record_anc_ = on; }
   void set_profiling(bool on) { profiling_ = on; }
-  // SPEC §9: 0 = binary64 states, 1 = binary32 states (takes effect at the next init / run)
-  void set_precision(int p) { next_prec_ = p ? 1 : 0; }
+  // SPEC §9: 0 = binary64, 1 = binary32 STATES (binary64 arithmetic), 2 = binary32 ARITHMETIC (§9b); takes effect at the next init / run
+  void set_precision(int p) { next_prec_ = p; }
   int precision() const { return prec_; }
   void timing(double ms[TK_COUNT], int64_t launches[TK_COUNT]) const;
 

@@ -487,6 +487,90 @@ def test_f32_state_tier(ctx, oracle, kind):
     _compare_run(ctx, oracle, kind, 1001, 6, smc.SYSTEMATIC)
 
 
+def test_f32_arithmetic_math_bit_exact(ctx, oracle):
+    """docs/SPEC.md §9b: the device's binary32 exp / log / sincos2pi / quantiser against the oracle's independent restatement,
+    bit for bit (the ancestors of the tier depend on every bit of the exponential)"""
+    rng = np.random.default_rng(11)
+    x = np.concatenate([rng.uniform(-90, 3, 100000), [-0.0, 0.0, -86.0, -86.000001, -1e-9, -np.inf]]).astype(np.float32).astype(np.float64)
+    np.testing.assert_array_equal(ctx.selftest_math(4, x)[0], oracle.detf("exp", x))
+    u = np.concatenate([(2 * rng.integers(0, 1 << 23, 100000) + 1) * 2.0 ** -24, [2.0 ** -24, 1 - 2.0 ** -24, 0.5, 0.70710677, 0.7071068]])
+    np.testing.assert_array_equal(ctx.selftest_math(5, u)[0], oracle.detf("log", u))
+    s, c = ctx.selftest_math(6, u)
+    so, co = oracle.detf("sincos", u)
+    np.testing.assert_array_equal(s, so)
+    np.testing.assert_array_equal(c, co)
+    for S in (37, 47, 51):
+        xq = x[x <= 0]
+        q, _ = ctx.selftest_math(7, xq, aux=S)
+        np.testing.assert_array_equal(q.view(np.uint64), oracle.detf("quant", xq, S))
+
+
+@pytest.mark.parametrize("kind", [smc.KIND_LG1D, smc.KIND_SV, smc.KIND_UCSV])
+def test_f32_arithmetic_tier(ctx, oracle, kind):
+    """docs/SPEC.md §9b: binary32 ARITHMETIC (float Philox normals four per block, float model arithmetic and log-weights, the
+    uint64 CDF kept).  Ancestors, states and log-weights bit-exact against the oracle run in the same tier for the sorted
+    resamplers and the two-level multinomial draw; logμ / ess at 1e-10 (the sums are binary64 in both)."""
+    T = 12
+    y = _data(oracle, kind, T)
+    ctx.set_precision("f32_arith")
+    try:
+        for N, resampler in ((1024, smc.SYSTEMATIC), (5003, smc.STRATIFIED), (70001, smc.SYSTEMATIC), (40002, smc.MULTINOMIAL)):
+            with oracle.arith_f32():
+                ref = oracle.log_likelihood(kind, MODELS[kind], N, y, resampler, 13, 2, 1, want_anc=True)
+            ctx.set_rng(13, 2)
+            ctx.record_ancestors(True)
+            logZ, logmu, ess = ctx.log_likelihood(kind, MODELS[kind], N, y, resampler, 1, per_step=True)
+            anc = ctx.fetch_ancestors(T - 1)
+            x, w, logw = ctx.fetch_state(want_logw=True)
+            ctx.record_ancestors(False)
+            np.testing.assert_array_equal(anc, ref["anc"][1:])
+            np.testing.assert_array_equal(x, ref["x"])
+            np.testing.assert_array_equal(logw, ref["logw"])
+            assert np.array_equal(x, x.astype(np.float32).astype(np.float64)) and np.array_equal(logw, logw.astype(np.float32).astype(np.float64))
+            np.testing.assert_allclose(logmu, ref["logmu"], rtol=RTOL, atol=0)
+            np.testing.assert_allclose(ess, ref["ess"], rtol=RTOL, atol=0)
+            with oracle.arith_f32():
+                np.testing.assert_allclose(w, oracle.normalize_f32(ref["logw"])[1], rtol=RTOL, atol=0)
+            if kind == smc.KIND_LG1D and N == 70001:   # summaries read binary32 states and the uint64 weights: bit-exact as in the other tiers
+                m, v, q = ctx.summary([0.1, 0.5, 0.9])
+                mo, vo, qo = oracle.weighted_summary(ref["x"], ref["logw"], [0.1, 0.5, 0.9])
+                np.testing.assert_allclose(m, mo, rtol=1e-6)     # (the oracle's summary quantises the weights in binary64)
+        # the stepping API in the tier
+        ctx.set_rng(13, 2)
+        ctx.bootstrap_init(kind, MODELS[kind], 70001, y[0], stream=1)
+        for t in range(1, T):
+            ctx.bootstrap_step(y[t], smc.SYSTEMATIC)
+        with oracle.arith_f32():
+            ref = oracle.log_likelihood(kind, MODELS[kind], 70001, y, smc.SYSTEMATIC, 13, 2, 1)
+        np.testing.assert_array_equal(ctx.fetch_state(want_w=False)[0], ref["x"])
+        with pytest.raises(smc.SMCBError):
+            ctx.log_likelihood(kind, MODELS[kind], 1024, y, smc.MULTINOMIAL)          # small-cloud multinomial: binary64 only
+        if kind != smc.KIND_UCSV:
+            with pytest.raises(smc.SMCBError):
+                ctx.guided_log_likelihood(kind, MODELS[kind], 20000, y, np.tile([0.0, 0.5, 1.0], (T, 1)), smc.SYSTEMATIC)
+    finally:
+        ctx.set_precision("f64")
+
+
+def test_f32_arithmetic_tier_agrees_with_binary64(ctx, oracle):
+    """BASELINE.json north star: logZ of the fp32 tier within rel 1e-4 of fp64.  The tier draws its normals four per Philox block,
+    so it is another Monte-Carlo run of the same filter: at N = 2^22 the two estimates of log Z agree to the north star's
+    tolerance, and both agree with the matched-init Kalman likelihood (the exact value)."""
+    N, T = 1 << 22, 100
+    y = _data(oracle, smc.KIND_LG1D, T)
+    z64 = ctx.log_likelihood(smc.KIND_LG1D, MODELS[smc.KIND_LG1D], N, y, smc.SYSTEMATIC)
+    ctx.set_precision("f32_arith")
+    try:
+        z32 = ctx.log_likelihood(smc.KIND_LG1D, MODELS[smc.KIND_LG1D], N, y, smc.SYSTEMATIC)
+        z32m = ctx.log_likelihood(smc.KIND_LG1D, MODELS[smc.KIND_LG1D], N, y, smc.MULTINOMIAL)
+    finally:
+        ctx.set_precision("f64")
+    kal = float(ctx.kalman_loglik(MODELS[smc.KIND_LG1D], y, matched_init=True)[0][0])
+    assert abs(z32 - z64) <= 1e-4 * abs(z64), (z32, z64)
+    assert abs(z32m - z64) <= 1e-4 * abs(z64), (z32m, z64)
+    assert abs(z32 - kal) <= 1e-4 * abs(kal) and abs(z64 - kal) <= 1e-4 * abs(kal), (z32, z64, kal)
+
+
 def test_readme_loop_through_the_host_mirror(oracle):
     """The README's online loop (README.md:33-61) spelled with the reference's function names:
     bootstrap_filter, then bootstrap_filter! and quantile per observation; particle_filter / particle_filter!

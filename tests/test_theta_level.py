@@ -372,7 +372,8 @@ def test_reference_docstring_trace_is_a_plausible_draw(ctx):
     for seed in range(24):
         y = smc.simulate(lg_mod([0.5, 0.9, 0.8]), 100, seed=1000 + seed)[1]
         g = smc.SMC(1024, 512, lg_mod, pg, 3, 0.5, seed=seed, ctx=ctx, engine="device")         # on-disk argument order: N, M
-        st = g._eng.density_tempered()
+        g._engine_data(y)
+        st = g._eng.density_tempered()                              # [(ξ, ess, acceptance ratio or -1)] per stage
         g._stale = True
         stages.append(len(st))
         for k, (xi, ess, acc) in enumerate(st):
