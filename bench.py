@@ -422,8 +422,8 @@ def main():
         line["multinomial"] = {"error": repr(e)}
     if not args.no_smc2:
         try:
-            line["smc2"] = smc2_legs(ctx, None, 0, 1, None, ("c3", "c4"), steps=3, warmup=1)
-            line["smc2"].update(smc2_legs(ctx, None, 0, 1, None, ("c5",), steps=1, warmup=1))
+            line["smc2"] = smc2_legs(ctx, None, 0, 1, None, ("c3", "c4", "c3_multinomial"), steps=3, warmup=1)
+            line["smc2"].update(smc2_legs(ctx, None, 0, 1, None, ("c5", "c5_multinomial"), steps=1, warmup=1))
             if not args.no_cpu:
                 line["smc2"]["cpu_baseline"] = cpu_rejuvenation_sample(1024, 100)
         except Exception as e:  # the headline line must still print
@@ -547,7 +547,7 @@ def main_sharded(args, rank, world, local, barrier):
             except Exception as e:
                 line["single_gpu_same_workload"] = {"error": repr(e)}
         barrier()
-        line["smc2"] = smc2_legs(ctx, comm, rank, world, barrier, ("c3", "c4"), steps=2, warmup=1)
+        line["smc2"] = smc2_legs(ctx, comm, rank, world, barrier, ("c3", "c4", "c5_multinomial"), steps=2, warmup=1)
     # the single-filter headline as N independent replicas (weak scaling, no collective): a single filter does not shard
     try:
         Nr, Tr = 1 << args.logn, 200

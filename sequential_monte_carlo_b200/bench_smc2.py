@@ -45,6 +45,8 @@ def run_config(name, ctx, comm, rank, world, steps=1, warmup=1, resampler="syste
     """`warmup` untimed runs, then `steps` timed runs of configuration `name`, θ sharded over `world` ranks.  Returns the
     per-run averages (max over ranks is taken by the caller through `reduce_max`)."""
     import sequential_monte_carlo_b200 as smc
+    if name.endswith("_multinomial"):        # the same configuration with the reference's own inner resampling law (particles.jl:117)
+        name, resampler = name[: -len("_multinomial")], "multinomial"
     cfg = dict(CONFIGS[name])
     if T:
         cfg["T"] = int(T)

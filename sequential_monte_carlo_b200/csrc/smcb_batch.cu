@@ -50,6 +50,19 @@ __device__ __forceinline__ int smem_lower_count(const uint64_t* C, int lo, int h
   }
   return lo;
 }
+// the same count for a threshold known to be >= the one that gave `lo` (sorted resamplers: the second particle of a pair):
+// its ancestor is lo or a few entries further, so gallop from lo instead of bisecting [lo, hi) from scratch
+__device__ __forceinline__ int smem_lower_count_from(const uint64_t* C, int lo, int hi, uint64_t tau) {
+  int step = 1, top = lo;
+  while (top < hi && C[top] <= tau) {
+    lo = top + 1;
+    top = lo + step - 1;
+    step <<= 1;
+    if (top > hi) top = hi;
+  }
+  // invariant: every entry below lo is <= tau; C[top] > tau or top == hi
+  return smem_lower_count(C, lo, top, tau);
+}
 
 // GUIDED: the move of every step t >= 1 draws from the affine-Gaussian proposal of (t, θ) and the weight carries
 // transition / proposal (particle_filter!, particles.jl:66-80; SPEC §10); D = 1 models only.
@@ -236,7 +249,7 @@ __global__ void __launch_bounds__(MAXT) batch_kernel(const BatchArgs a) {
             }
             const uint64_t t0 = mulhi64(F0, Q), t1 = mulhi64(F1, Q);
             a0 = smem_lower_count(s_cdf, 0, N - 1, t0);
-            a1 = smem_lower_count(s_cdf, (a.resampler == RESAMPLE_MULTINOMIAL) ? 0 : a0, N - 1, t1);
+            a1 = (a.resampler == RESAMPLE_MULTINOMIAL) ? smem_lower_count(s_cdf, 0, N - 1, t1) : smem_lower_count_from(s_cdf, a0, N - 1, t1);
           }
 #pragma unroll
           for (int k = 0; k < D; ++k) {
