@@ -47,7 +47,13 @@ typedef enum {
  *         unobserved_components(σε,ση,x0) is LG1D(1,1,σε,ση,x0,σε)              :119-128
  *   SV    μ, ρ, σ              x1~N(μ,σ²/(1-ρ²)), x'~N(μ+ρ(x-μ),σ), y~N(0,exp(x/2))  (absent upstream)
  *   UCSV  γε, γη, x0, logσε0, logση0                       state_space_models.jl:215-259 */
-typedef enum { SMCB_LG1D = 0, SMCB_SV = 1, SMCB_UCSV = 2 } smcb_model_kind;
+typedef enum { SMCB_LG1D = 0, SMCB_SV = 1, SMCB_UCSV = 2, SMCB_MVLG2 = 3, SMCB_MVLG3 = 4, SMCB_MVLG4 = 5 } smcb_model_kind;
+/* SMCB_MVLG2..4: MultivariateLinearGaussian with a d = 2, 3, 4 dimensional state and a scalar observation
+ *   x' ~ MvNormal(A x, Q), y ~ Normal(B x, R), x1 ~ MvNormal(x0, Σ0)        state_space_models.jl:137-189, hodrick_prescott :193-202
+ * `params` is then the block of smcb_kalman_mv_* below (3d² + 2d + 1 doubles, row-major: A, B, Q, R, x0, Σ0), NOT 8 doubles.  Q and Σ0
+ * may be positive SEMI-definite (hodrick_prescott's Q has a zero pivot); R is a variance as in kalman_filter.jl:16.  Engine: the large-N
+ * single filter (smcb_bootstrap_init / _step, smcb_log_likelihood, smcb_fetch_state, smcb_weighted_summary, smcb_simulate), binary64
+ * arithmetic; the batched / θ-level entry points answer SMCB_ERR_UNSUPPORTED (IBIS over the matrix Kalman filter covers them). */
 
 /* MULTINOMIAL is the reference's distribution (i.i.d., unsorted; particles.jl:17-19);
  * STRATIFIED / SYSTEMATIC give sorted ancestors and are the bandwidth-optimal modes. */

@@ -55,14 +55,17 @@ def _p(a):
 
 
 def params8(p):
-    out = np.zeros(8)
+    """8-double parameter block of the univariate kinds / UCSV; a multivariate LG block (3d² + 2d + 1 doubles) passes through"""
     p = np.asarray(p, dtype=np.float64).ravel()
+    if p.size > 8:
+        return np.ascontiguousarray(p)
+    out = np.zeros(8)
     out[: p.size] = p
     return out
 
 
 def state_dim(kind):
-    return 3 if kind == KIND_UCSV else 1
+    return kind - 1 if kind >= 3 else (3 if kind == KIND_UCSV else 1)   # kinds 3..5: multivariate LG, d = 2..4
 
 
 def quant_shift(n):

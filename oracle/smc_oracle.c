@@ -35,7 +35,7 @@ enum { RS_MULTINOMIAL = 0, RS_STRATIFIED = 1, RS_SYSTEMATIC = 2 };
 static int g_arith_f32 = 0;   /* SPEC §9b tier switch (set by smco_set_arith_f32 below) */
 enum { P_INIT = 1, P_TRANS = 2, P_RESAMPLE = 3, P_SIMULATE = 8, P_RESAMPLE_CELL = 9 };
 
-int smco_state_dim(int kind) { return kind == KIND_UCSV ? 3 : 1; }
+int smco_state_dim(int kind) { return kind >= 3 ? kind - 1 : (kind == KIND_UCSV ? 3 : 1); }   /* kinds 3..5: multivariate LG, d = 2..4 */
 
 /* ------------------------------------------------------------------ vector math for the tests */
 void smco_philox(const uint32_t *ctr, const uint32_t *key, uint32_t *out) { o_philox(ctr, key, out); }
@@ -66,8 +66,36 @@ int smco_quant_shift(int64_t n) {
 }
 
 /* ------------------------------------------------------------------ models (SPEC §4) */
+/* lower Cholesky factor of a positive SEMI-definite matrix (SPEC §4b): a non-positive pivot gives a zero column */
+static void chol_psd(const double *A, int d, double *L) {
+  for (int i = 0; i < d * d; ++i) L[i] = 0.0;
+  for (int j = 0; j < d; ++j) {
+    double s = A[j * d + j];
+    for (int k = 0; k < j; ++k) s = s - L[j * d + k] * L[j * d + k];
+    if (!(s > 0.0)) continue;
+    L[j * d + j] = sqrt(s);
+    for (int i = j + 1; i < d; ++i) {
+      double v = A[i * d + j];
+      for (int k = 0; k < j; ++k) v = v - L[i * d + k] * L[j * d + k];
+      L[i * d + j] = v / L[j * d + j];
+    }
+  }
+}
+/* D holds 64 doubles; multivariate LG (state_space_models.jl:137-189): block A, B, Q, R, x0, Σ0 -> A | B | chol(Q) | 1/sqrt(R) | c | x0 | chol(Σ0) */
 void smco_derive(int kind, const double *P, double *D) {
-  for (int i = 0; i < 8; ++i) D[i] = 0.0;
+  for (int i = 0; i < 64; ++i) D[i] = 0.0;
+  if (kind >= 3) {
+    int d = kind - 1;
+    const double *A = P, *B = P + d * d, *Q = B + d, *x0 = Q + d * d + 1, *S0 = x0 + d;
+    double R = Q[d * d], sr = sqrt(R), *o = D;
+    memcpy(o, A, sizeof(double) * d * d); o += d * d;
+    memcpy(o, B, sizeof(double) * d); o += d;
+    chol_psd(Q, d, o); o += d * d;
+    o[0] = 1.0 / sr; o[1] = -(o_log(sr) + O_HALF_LOG_2PI); o += 2;
+    memcpy(o, x0, sizeof(double) * d); o += d;
+    chol_psd(S0, d, o);
+    return;
+  }
   if (kind == KIND_LG1D) { /* A,B,Q,R,x0,s0 : state_space_models.jl:74-109 */
     double sr = sqrt(P[3]);
     D[0] = P[0]; D[1] = P[1]; D[2] = sqrt(P[2]); D[3] = P[4]; D[4] = sqrt(P[5]);
@@ -86,6 +114,16 @@ void smco_derive(int kind, const double *P, double *D) {
 
 /* x: the d state components of one particle; z: d standard normals */
 static void model_init(int kind, const double *D, const double *z, double *x) {
+  if (kind >= 3) {                                /* MvNormal(x0, Σ0) :185-189 */
+    int d = kind - 1;
+    const double *x0 = D + 2 * d * d + d + 2, *L0 = x0 + d;
+    for (int i = 0; i < d; ++i) {
+      double acc = x0[i];
+      for (int j = 0; j <= i; ++j) acc = fma(L0[i * d + j], z[j], acc);
+      x[i] = acc;
+    }
+    return;
+  }
   if (kind == KIND_LG1D) {
     x[0] = fma(D[4], z[0], D[3]);                 /* Normal(x0, sqrt(s0)) :105-109 */
   } else if (kind == KIND_SV) {
@@ -97,6 +135,17 @@ static void model_init(int kind, const double *D, const double *z, double *x) {
   }
 }
 static void model_transition(int kind, const double *D, const double *z, const double *xp, double *x) {
+  if (kind >= 3) {                                /* MvNormal(A x, Q) :163-171 */
+    int d = kind - 1;
+    const double *A = D, *LQ = D + d * d + d;
+    for (int i = 0; i < d; ++i) {
+      double acc = A[i * d] * xp[0];
+      for (int j = 1; j < d; ++j) acc = fma(A[i * d + j], xp[j], acc);
+      for (int j = 0; j <= i; ++j) acc = fma(LQ[i * d + j], z[j], acc);
+      x[i] = acc;
+    }
+    return;
+  }
   if (kind == KIND_LG1D) {
     x[0] = fma(D[2], z[0], D[0] * xp[0]);         /* Normal(A x, sqrt(Q)) :87-94 */
   } else if (kind == KIND_SV) {
@@ -109,6 +158,14 @@ static void model_transition(int kind, const double *D, const double *z, const d
   }
 }
 static double model_logweight(int kind, const double *D, const double *x, double y) {
+  if (kind >= 3) {                                /* Normal(B x, sqrt(R)) — R a variance as in kalman_filter.jl:16 (D9) */
+    int d = kind - 1;
+    const double *B = D + d * d, *tail = D + 2 * d * d + d;
+    double m = B[0] * x[0];
+    for (int j = 1; j < d; ++j) m = fma(B[j], x[j], m);
+    double v = (y - m) * tail[0];
+    return fma(-0.5 * v, v, tail[1]);
+  }
   if (kind == KIND_LG1D) {                        /* logpdf(Normal(B x, sqrt(R)), y) :96-103 */
     double v = (y - D[1] * x[0]) * D[5];
     return fma(-0.5 * v, v, D[6]);
@@ -316,7 +373,7 @@ static float modelf_logweight(int kind, const float *D, const float *x, float y)
   }
 }
 static void derive_f(int kind, const double *P, float *Df) {   /* the binary64 derived block rounded once to binary32 */
-  double D[8];
+  double D[64];
   smco_derive(kind, P, D);
   for (int i = 0; i < 8; ++i) Df[i] = (float)D[i];
 }
@@ -335,14 +392,14 @@ void smco_normalize_f32(const double *logw, int64_t n, double *logmu, double *w,
 /* x is SoA [d][n]. */
 void smco_bootstrap_init(int kind, const double *P, int64_t n, double y, uint64_t seed, uint32_t epoch,
                          uint32_t stream, double *x, double *logw) {
-  double D[8];
+  double D[64];
   smco_derive(kind, P, D);
   int d = smco_state_dim(kind);
   if (g_arith_f32) {
     float Df[8];
     derive_f(kind, P, Df);
     for (int64_t i = 0; i < n; ++i) {
-      float z[3] = {0, 0, 0}, xi[3];
+      float z[4] = {0, 0, 0, 0}, xi[4];
       for (int k = 0; k < d; ++k) z[k] = of_normal(seed, epoch, (uint32_t)i, stream, 0, P_INIT, (uint32_t)k);
       modelf_init(kind, Df, z, xi);
       for (int k = 0; k < d; ++k) x[(int64_t)k * n + i] = (double)xi[k];
@@ -351,7 +408,7 @@ void smco_bootstrap_init(int kind, const double *P, int64_t n, double y, uint64_
     return;
   }
   for (int64_t i = 0; i < n; ++i) {                                         /* :96-99 */
-    double z[3] = {0, 0, 0}, xi[3];
+    double z[4] = {0, 0, 0, 0}, xi[4];
     for (int k = 0; k < d; ++k) z[k] = o_normal(seed, epoch, (uint32_t)i, stream, 0, P_INIT, (uint32_t)k);
     model_init(kind, D, z, xi);
     round_state(xi, d);
@@ -363,7 +420,7 @@ void smco_bootstrap_init(int kind, const double *P, int64_t n, double y, uint64_
 /* ------------------------------------------------------------------ a4 bootstrap_filter! */
 void smco_bootstrap_step(int kind, const double *P, int64_t n, double y, uint32_t t, int resampler, uint64_t seed,
                          uint32_t epoch, uint32_t stream, double *x, double *logw, int64_t *anc_out) {
-  double D[8];
+  double D[64];
   smco_derive(kind, P, D);
   int d = smco_state_dim(kind);
   int64_t *a = (int64_t *)malloc(sizeof(int64_t) * (size_t)n);              /* a = resample(weights) :117 */
@@ -375,7 +432,7 @@ void smco_bootstrap_step(int kind, const double *P, int64_t n, double y, uint32_
     float Df[8];
     derive_f(kind, P, Df);
     for (int64_t i = 0; i < n; ++i) {
-      float z[3] = {0, 0, 0}, par[3] = {0, 0, 0}, xi[3];
+      float z[4] = {0, 0, 0, 0}, par[4] = {0, 0, 0, 0}, xi[4];
       for (int k = 0; k < d; ++k) {
         z[k] = of_normal(seed, epoch, (uint32_t)i, stream, t, P_TRANS, (uint32_t)k);
         par[k] = (float)xp[(int64_t)k * n + i];
@@ -390,7 +447,7 @@ void smco_bootstrap_step(int kind, const double *P, int64_t n, double y, uint32_
     return;
   }
   for (int64_t i = 0; i < n; ++i) {                                         /* :122-125 */
-    double z[3] = {0, 0, 0}, par[3] = {0, 0, 0}, xi[3];
+    double z[4] = {0, 0, 0, 0}, par[4] = {0, 0, 0, 0}, xi[4];
     for (int k = 0; k < d; ++k) {
       z[k] = o_normal(seed, epoch, (uint32_t)i, stream, t, P_TRANS, (uint32_t)k);
       par[k] = xp[(int64_t)k * n + i];
@@ -412,7 +469,7 @@ void smco_bootstrap_step(int kind, const double *P, int64_t n, double y, uint32_
 int smco_guided_step(int kind, const double *P, int64_t n, double y, uint32_t t, int resampler, uint64_t seed,
                      uint32_t epoch, uint32_t stream, const double *prop, double *x, double *logw, int64_t *anc_out) {
   if (kind == KIND_UCSV) return -1;
-  double D[8];
+  double D[64];
   smco_derive(kind, P, D);
   const double c0 = prop[0], c1 = prop[1], c2 = prop[2], lc2 = o_log(prop[2]), ic2 = 1.0 / prop[2];
   const double isdf = 1.0 / D[2], lsdf = (kind == KIND_LG1D) ? D[7] : D[4];
@@ -607,18 +664,24 @@ double smco_kalman_mv_loglik(int d, const double *P, const double *y, int64_t T,
 /* state_space_models.jl:11-26 with Philox purpose 8: stream 0 = state noise, stream 1 = obs noise.
  * The observation draw inverts the model's weight function: y = mean + sd * z. */
 void smco_simulate(int kind, const double *P, int64_t T, uint64_t seed, double *x, double *y) {
-  double D[8];
+  double D[64];
   smco_derive(kind, P, D);
   int d = smco_state_dim(kind);
-  double cur[3] = {0, 0, 0}, nxt[3];
+  double cur[4] = {0, 0, 0, 0}, nxt[4];
   for (int64_t t = 0; t < T; ++t) {
-    double z[3] = {0, 0, 0};
+    double z[4] = {0, 0, 0, 0};
     for (int k = 0; k < d; ++k) z[k] = o_normal(seed, 0, (uint32_t)t, 0, 0, P_SIMULATE, (uint32_t)k);
     if (t == 0) model_init(kind, D, z, nxt); else model_transition(kind, D, z, cur, nxt);
     for (int k = 0; k < d; ++k) { cur[k] = nxt[k]; x[(int64_t)k * T + t] = cur[k]; }
     double zo = o_normal(seed, 0, (uint32_t)t, 1, 0, P_SIMULATE, 0);
     double mean, sd;
-    if (kind == KIND_LG1D) { mean = D[1] * cur[0]; sd = sqrt(P[3]); }
+    if (kind >= 3) {
+      const double *B = D + d * d;
+      mean = B[0] * cur[0];
+      for (int j = 1; j < d; ++j) mean = fma(B[j], cur[j], mean);
+      sd = sqrt(P[2 * d * d + d]);
+    }
+    else if (kind == KIND_LG1D) { mean = D[1] * cur[0]; sd = sqrt(P[3]); }
     else if (kind == KIND_SV) { mean = 0.0; sd = o_exp(0.5 * cur[0]); }
     else { mean = cur[0]; sd = o_exp(0.5 * cur[2]); }
     y[t] = fma(sd, zo, mean);

@@ -9,6 +9,7 @@ import numpy as np
 from . import build as _build
 
 LG1D, SV, UCSV = 0, 1, 2
+MVLG2, MVLG3, MVLG4 = 3, 4, 5     # MultivariateLinearGaussian, d = 2..4 (single filter only); params = the A, B, Q, R, x0, Σ0 block
 MULTINOMIAL, STRATIFIED, SYSTEMATIC = 0, 1, 2
 PARAM_STRIDE = 8
 # Philox purposes of the host-level streams (docs/SPEC.md §2)
@@ -144,15 +145,17 @@ def _ptr(a):
 
 
 def params8(p):
-    """[..., k<=8] -> contiguous [..., 8] float64 parameter block(s)."""
+    """[..., k<=8] -> contiguous [..., 8] float64 parameter block(s); a multivariate LG block (more than 8 doubles) passes through."""
     p = np.asarray(p, dtype=np.float64)
+    if p.shape[-1] > PARAM_STRIDE:
+        return np.ascontiguousarray(p)
     out = np.zeros(p.shape[:-1] + (PARAM_STRIDE,), dtype=np.float64)
     out[..., : p.shape[-1]] = p
     return np.ascontiguousarray(out)
 
 
 def state_dim(kind):
-    return 3 if kind == UCSV else 1
+    return kind - 1 if kind >= MVLG2 else (3 if kind == UCSV else 1)
 
 
 def rng_normals(seed, epoch, stream, t, purpose, comp, n):
@@ -228,7 +231,7 @@ def comm_unique_id():
 
 def simulate(kind, params, T, seed):
     """simulate(model, T) -> (x [d, T], y [T])   /root/reference/src/state_space_models.jl:11-28; CPU only."""
-    p = params8(params)
+    p = params8(np.asarray(params, np.float64).ravel())
     x = np.empty((state_dim(kind), int(T)))
     y = np.empty(int(T))
     rc = load().smcb_simulate(int(kind), _ptr(p), int(T), C.c_uint64(int(seed) & (2 ** 64 - 1)), _ptr(x), _ptr(y))

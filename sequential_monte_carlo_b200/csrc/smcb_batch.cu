@@ -698,6 +698,7 @@ constexpr size_t kSmemBudget = 227 * 1024 - 2048;  // dynamic part; static scrat
 // ------------------------------------------------------------------------------------------------
 BatchFilter::BatchFilter(int device, cudaStream_t stream, int kind, int64_t M, int64_t N)
     : device_(device), stream_(stream), kind_(kind), d_(0), M_(M), N_(N) {
+  if (is_mv_kind(kind)) throw Error{SMCB_ERR_UNSUPPORTED, "multivariate linear models run on the single filter (smcb_bootstrap_* / smcb_log_likelihood), not on the batched engine"};
   if (kind < 0 || kind >= KIND_COUNT) throw Error{SMCB_ERR_BAD_ARG, "unknown model kind"};
   if (M < 1 || M > (1 << 24)) throw Error{SMCB_ERR_BAD_ARG, "M must be in [1, 2^24]"};
   if (N < 1 || N > 8192) throw Error{SMCB_ERR_UNSUPPORTED, "batched filters support N in [1, 8192] (use the single filter above)"};

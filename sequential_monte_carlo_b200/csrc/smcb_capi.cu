@@ -80,7 +80,7 @@ extern "C" {
 
 int smcb_version(void) { return 100; }
 
-int smcb_state_dim(int kind) { return (kind >= 0 && kind < KIND_COUNT) ? state_dim(kind) : SMCB_ERR_BAD_ARG; }
+int smcb_state_dim(int kind) { return (kind >= 0 && kind < KIND_ALL) ? state_dim(kind) : SMCB_ERR_BAD_ARG; }
 
 int smcb_create(int device, uint64_t seed, smcb_ctx** out) {
   if (!out) return SMCB_ERR_BAD_ARG;
@@ -713,7 +713,13 @@ void simulate_model(const double* D, const double* P, int64_t T, uint64_t seed, 
     normal_pair_at(key, (uint32_t)(t >> 1), 1u, 0u, PURPOSE_SIMULATE, 0u, z0, z1);
     const double zo = (t & 1) ? z1 : z0;
     double mean, sd;
-    if (Model::KIND == KIND_LG1D) { mean = D[1] * cur[0]; sd = sqrt(P[3]); }
+    if (Model::KIND >= KIND_MVLG2) {
+      const double* B = D + DIM * DIM;
+      mean = B[0] * cur[0];
+      for (int j = 1; j < DIM; ++j) mean = fma(B[j], cur[j], mean);
+      sd = sqrt(P[2 * DIM * DIM + DIM]);
+    }
+    else if (Model::KIND == KIND_LG1D) { mean = D[1] * cur[0]; sd = sqrt(P[3]); }
     else if (Model::KIND == KIND_SV) { mean = 0.0; sd = det_exp(0.5 * cur[0]); }
     else { mean = cur[0]; sd = det_exp(0.5 * cur[DIM - 1]); }
     y[t] = fma(sd, zo, mean);
@@ -739,8 +745,15 @@ __global__ void selftest_kernel(int fn, const double* in, int64_t n, double aux,
 extern "C" {
 
 int smcb_simulate(int kind, const double* params, int64_t T, uint64_t seed, double* x, double* y) {
-  if (!params || !x || !y || T < 1 || kind < 0 || kind >= KIND_COUNT) return SMCB_ERR_BAD_ARG;
-  double D[kParamStride];
+  if (!params || !x || !y || T < 1 || kind < 0 || kind >= KIND_ALL) return SMCB_ERR_BAD_ARG;
+  double D[kMvStride];
+  if (is_mv_kind(kind)) {
+    derive_params_mv(state_dim(kind), params, D);
+    if (kind == KIND_MVLG2) simulate_model<ModelMVLG<2>>(D, params, T, seed, x, y);
+    else if (kind == KIND_MVLG3) simulate_model<ModelMVLG<3>>(D, params, T, seed, x, y);
+    else simulate_model<ModelMVLG<4>>(D, params, T, seed, x, y);
+    return SMCB_OK;
+  }
   derive_params(kind, params, D);
   if (kind == KIND_LG1D) simulate_model<ModelLG1D>(D, params, T, seed, x, y);
   else if (kind == KIND_SV) simulate_model<ModelSV>(D, params, T, seed, x, y);

@@ -86,7 +86,7 @@ __device__ __forceinline__ void round_state(double (&x)[D]) {
 // ------------------------------------------------------------------------------------------------
 // bootstrap_filter: x_i ~ initial_dist, logw_i = logpdf(observation(x_i), y)   particles.jl:96-99
 template <class Model, class XT>
-__global__ void __launch_bounds__(256) init_kernel(Derived dv, double y0, int64_t N, int64_t ld, RngKey key,
+__global__ void __launch_bounds__(256) init_kernel(typename Model::DV dv, double y0, int64_t N, int64_t ld, RngKey key,
                                                     uint32_t stream, XT* __restrict__ x,
                                                     double* __restrict__ logw, FilterCtrl* ctrl) {
   constexpr int D = Model::D;
@@ -307,7 +307,7 @@ __device__ __forceinline__ uint64_t threshold_of(int resampler, uint64_t i, uint
 // bootstrap_filter!: a = resample(w); x_i ~ transition(x[a_i]); logw_i = logpdf(observation(x_i), y)
 template <class Model>
 __global__ void __launch_bounds__(kPropThreads)
-    prop_kernel(Derived dv, double y, int64_t N, int64_t ld, int resampler, uint64_t Rw, RngKey key,
+    prop_kernel(typename Model::DV dv, double y, int64_t N, int64_t ld, int resampler, uint64_t Rw, RngKey key,
                 uint32_t stream, uint32_t t, const uint64_t* __restrict__ cdf, const double* __restrict__ xprev,
                 double* __restrict__ xnew, double* __restrict__ logw, int32_t* __restrict__ anc_out,
                 FilterCtrl* ctrl) {
@@ -1508,7 +1508,7 @@ __device__ __forceinline__ double move_particles(const Model& mdl, double y, int
 
 template <class Model, class XT>
 __global__ void __launch_bounds__(kMoveThreads, (Model::D == 1) ? 6 : 3)
-    move_kernel(Derived dv, double y, int N, int64_t ld, RngKey key, uint32_t stream, uint32_t t, const int32_t* __restrict__ anc,
+    move_kernel(typename Model::DV dv, double y, int N, int64_t ld, RngKey key, uint32_t stream, uint32_t t, const int32_t* __restrict__ anc,
                 const XT* __restrict__ xprev, XT* __restrict__ xnew, double* __restrict__ logw, FilterCtrl* ctrl) {
   constexpr int PER = 2 * kMovePairs;
   constexpr int NW = kMoveThreads / 32;
@@ -1901,11 +1901,19 @@ void dispatch_model(int kind, F&& f) {
     case KIND_LG1D: f(ModelLG1D{}); break;
     case KIND_SV: f(ModelSV{}); break;
     case KIND_UCSV: f(ModelUCSV{}); break;
+    case KIND_MVLG2: f(ModelMVLG<2>{}); break;
+    case KIND_MVLG3: f(ModelMVLG<3>{}); break;
+    case KIND_MVLG4: f(ModelMVLG<4>{}); break;
     default: throw Error{SMCB_ERR_BAD_ARG, "unknown model kind"};
   }
 }
 
 }  // namespace
+
+// the derived block a model's kernels take by value: 8 doubles for the univariate kinds, 64 for the multivariate ones
+static inline const Derived& pick_dv(const Derived& a, const DerivedMV&, const Derived*) { return a; }
+static inline const DerivedMV& pick_dv(const Derived&, const DerivedMV& b, const DerivedMV*) { return b; }
+#define SMCB_DV(M) pick_dv(dv_, dvmv_, (const typename M::DV*)nullptr)
 
 static DerivedF to_float(const Derived& d) {
   DerivedF f;
@@ -2064,6 +2072,7 @@ void SingleFilter::launch_init(double y0) {
   const int64_t npairs = (N_ + 1) / 2;
   const unsigned grid = (unsigned)((npairs + 255) / 256);
   mark(TK_INIT, true);
+  if (prec_ == 2 && is_mv_kind(kind_)) throw Error{SMCB_ERR_UNSUPPORTED, "the binary32-arithmetic tier is built for the univariate kinds and UCSV (docs/SPEC.md §9b)"};
   if (prec_ == 2) {
     const unsigned qgrid = (unsigned)(((N_ + 3) / 4 + 255) / 256);
     dispatch_model_f(kind_, [&](auto m) {
@@ -2076,7 +2085,7 @@ void SingleFilter::launch_init(double y0) {
     using M = decltype(m);
     dispatch_xt(prec_, [&](auto tag) {
       using XT = decltype(tag);
-      init_kernel<M, XT><<<grid, 256, 0, stream_>>>(dv_, y0, N_, ld_, key_, stream_id_, reinterpret_cast<XT*>(x_[cur_]), logw_[cur_], ctrl_);
+      init_kernel<M, XT><<<grid, 256, 0, stream_>>>(SMCB_DV(M), y0, N_, ld_, key_, stream_id_, reinterpret_cast<XT*>(x_[cur_]), logw_[cur_], ctrl_);
     });
   });
   mark(TK_INIT, false);
@@ -2124,7 +2133,7 @@ void SingleFilter::launch_prop(double y, int resampler) {
   mark(TK_PROP, true);
   dispatch_model(kind_, [&](auto m) {
     using M = decltype(m);
-    prop_kernel<M><<<grid, kPropThreads, 0, stream_>>>(dv_, y, N_, ld_, resampler, R_, key_, stream_id_, t, cdf_,
+    prop_kernel<M><<<grid, kPropThreads, 0, stream_>>>(SMCB_DV(M), y, N_, ld_, resampler, R_, key_, stream_id_, t, cdf_,
                                                        x_[cur_], x_[cur_ ^ 1], logw_[cur_ ^ 1], anc, ctrl_);
   });
   mark(TK_PROP, false);
@@ -2290,7 +2299,7 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler, cons
     using M = decltype(m);
     dispatch_xt(prec_, [&](auto tag) {
       using XT = decltype(tag);
-      SMCB_CUDA_TRY(launch_pdl(move_kernel<M, XT>, dim3(mblocks), dim3(kMoveThreads), stream_, dv_, y, (int)N_, ld_, key_, stream_id_, t, anc,
+      SMCB_CUDA_TRY(launch_pdl(move_kernel<M, XT>, dim3(mblocks), dim3(kMoveThreads), stream_, SMCB_DV(M), y, (int)N_, ld_, key_, stream_id_, t, anc,
                                reinterpret_cast<const XT*>(x_[cur_]), reinterpret_cast<XT*>(x_[cur_ ^ 1]),
                                implicit_logw ? (double*)nullptr : logw_[cur_ ^ 1], ctrl_));
     });
@@ -2307,8 +2316,19 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler, cons
 
 bool SingleFilter::legacy_multinomial(int resampler) const { return resampler == RESAMPLE_MULTINOMIAL && N_ <= kMnLegacyMax; }
 
+void SingleFilter::set_params(int kind, const double* params) {
+  if (is_mv_kind(kind)) {
+    const int d = state_dim(kind);
+    const double R = params[2 * d * d + d];
+    if (!(R > 0.0) || !std::isfinite(R)) throw Error{SMCB_ERR_BAD_ARG, "multivariate linear model: the observation variance R must be positive"};
+    derive_params_mv(d, params, dvmv_.d);
+  } else {
+    derive_params(kind, params, dv_.d);
+  }
+}
+
 static void check_args(int kind, int64_t N, int resampler) {
-  if (kind < 0 || kind >= KIND_COUNT) throw Error{SMCB_ERR_BAD_ARG, "unknown model kind"};
+  if (kind < 0 || kind >= KIND_ALL) throw Error{SMCB_ERR_BAD_ARG, "unknown model kind"};
   if (N < 1 || N > (int64_t(1) << 31) - 64) throw Error{SMCB_ERR_BAD_ARG, "N must be in [1, 2^31-64]"};
   if (resampler < 0 || resampler > 2) throw Error{SMCB_ERR_BAD_ARG, "unknown resampler"};
 }
@@ -2327,7 +2347,7 @@ void SingleFilter::init(int kind, const double* params, int64_t N, double y0, co
   kind_ = kind; d_ = state_dim(kind); N_ = N; ld_ = cap_N_; prec_ = next_prec_;
   S_ = quant_shift((uint64_t)N); R_ = strata_width((uint64_t)N);
   key_ = key; stream_id_ = stream_id; t_ = 0; cur_ = 0; anc_rows_ = 0;
-  derive_params(kind, params, dv_.d);
+  set_params(kind, params);
   begin_call();
   launch_init(y0);
   launch_sum(0);
@@ -2341,7 +2361,7 @@ void SingleFilter::step(const double* params, double y, int resampler, StepStats
   check_args(kind_, N_, resampler);
   if (prec_ && legacy_multinomial(resampler)) throw Error{SMCB_ERR_BAD_ARG, "binary32 states with N <= 8192: sorted resamplers only (docs/SPEC.md §9)"};
   SMCB_CUDA_TRY(cudaSetDevice(device_));
-  if (params) derive_params(kind_, params, dv_.d);
+  if (params) set_params(kind_, params);
   if (!record_anc_) anc_rows_ = 0;
   begin_call();
   launch_step(1, y, resampler, proposal);  // (the statistics of the old weights, if it has to recompute them, go to slot 1)
@@ -2368,7 +2388,7 @@ void SingleFilter::run(int kind, const double* params, int64_t N, const double* 
   kind_ = kind; d_ = state_dim(kind); N_ = N; ld_ = cap_N_; prec_ = next_prec_;
   S_ = quant_shift((uint64_t)N); R_ = strata_width((uint64_t)N);
   key_ = key; stream_id_ = stream_id; t_ = 0; cur_ = 0; anc_rows_ = 0;
-  derive_params(kind, params, dv_.d);
+  set_params(kind, params);
   begin_call();
   launch_init(y[0]);
   for (int64_t t = 1; t < T; ++t) {

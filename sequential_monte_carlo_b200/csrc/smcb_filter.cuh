@@ -86,6 +86,7 @@ class SingleFilter {
 
  private:
   void ensure_capacity(int kind, int64_t N, int64_t anc_rows);
+  void set_params(int kind, const double* params);  // derive_params / derive_params_mv into dv_ / dvmv_
   void load_vector(const double* host, int64_t n, bool is_log);
   void begin_call();
   void end_call();
@@ -111,6 +112,7 @@ class SingleFilter {
   uint32_t stream_id_ = 0;
   RngKey key_{};
   Derived dv_{};
+  DerivedMV dvmv_{};   // derived block of the multivariate kinds (KIND_MVLG2..4)
   bool record_anc_ = false;
   bool profiling_ = false;
   bool from_w_ = false;

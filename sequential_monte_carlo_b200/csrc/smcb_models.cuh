@@ -13,14 +13,70 @@
 
 namespace smcb {
 
-enum : int { KIND_LG1D = 0, KIND_SV = 1, KIND_UCSV = 2, KIND_COUNT = 3 };
+// kinds 0..2 run on every engine; kinds 3..5 = MultivariateLinearGaussian with a d = 2, 3, 4 dimensional state and a scalar
+// observation (state_space_models.jl:137-189, hodrick_prescott :193-202): the large-N single filter only
+enum : int { KIND_LG1D = 0, KIND_SV = 1, KIND_UCSV = 2, KIND_COUNT = 3, KIND_MVLG2 = 3, KIND_MVLG3 = 4, KIND_MVLG4 = 5, KIND_ALL = 6 };
 constexpr int kParamStride = 8;  // doubles per θ in both the raw and the derived block
 
 struct Derived {
   double d[kParamStride];
 };
 
-SMCB_HD int state_dim(int kind) { return kind == KIND_UCSV ? 3 : 1; }
+struct DerivedMV {  // by-value kernel argument of the multivariate kinds
+  double d[64];
+};
+constexpr int kMvStride = 64;
+
+SMCB_HD int state_dim(int kind) { return kind >= KIND_MVLG2 ? kind - 1 : (kind == KIND_UCSV ? 3 : 1); }
+SMCB_HD bool is_mv_kind(int kind) { return kind >= KIND_MVLG2 && kind < KIND_ALL; }
+
+// lower Cholesky factor (row-major d×d) of a symmetric positive SEMI-definite matrix by the plain Cholesky–Banachiewicz recursion:
+// a pivot that is not positive gives a zero column (hodrick_prescott's Q = diag(1/λ, 0), state_space_models.jl:197: the reference's
+// MvNormal(A x, Q) would throw PosDefException there; a deterministic second component is what the model means)
+SMCB_HD void chol_psd(const double* A, int d, double* L) {
+  for (int i = 0; i < d * d; ++i) L[i] = 0.0;
+  for (int j = 0; j < d; ++j) {
+    double s = A[j * d + j];
+    for (int k = 0; k < j; ++k) s = s - L[j * d + k] * L[j * d + k];
+    if (!(s > 0.0)) continue;
+    const double ljj = sqrt(s);
+    L[j * d + j] = ljj;
+    for (int i = j + 1; i < d; ++i) {
+      double v = A[i * d + j];
+      for (int k = 0; k < j; ++k) v = v - L[i * d + k] * L[j * d + k];
+      L[i * d + j] = v / ljj;
+    }
+  }
+}
+
+// block (include/smcb200.h, the layout of smcb_kalman_mv_*): A[d][d], B[d], Q[d][d], R, x0[d], Σ0[d][d] row-major  ->
+// derived: A[d²] | B[d] | LQ[d²] | ir = 1/sqrt(R) | c = -(det_log(sqrt(R)) + ½ log 2π) | x0[d] | L0[d²]
+// R is a VARIANCE as in kalman_filter.jl:16 and in the univariate methods (:102); the multivariate `observation` passes it to Normal
+// un-square-rooted (:178), an inconsistency of the reference ruled a defect — the filter then targets the
+// likelihood the reference's own Kalman filter computes.
+SMCB_HD void derive_params_mv(int d, const double* P, double* D) {
+  for (int i = 0; i < kMvStride; ++i) D[i] = 0.0;
+  const double* A = P;
+  const double* B = P + d * d;
+  const double* Q = B + d;
+  const double R = Q[d * d];
+  const double* x0 = Q + d * d + 1;
+  const double* S0 = x0 + d;
+  double* o = D;
+  for (int i = 0; i < d * d; ++i) o[i] = A[i];
+  o += d * d;
+  for (int i = 0; i < d; ++i) o[i] = B[i];
+  o += d;
+  chol_psd(Q, d, o);
+  o += d * d;
+  const double sr = sqrt(R);
+  o[0] = 1.0 / sr;
+  o[1] = -(det_log(sr) + SMCB_HALF_LOG_2PI);
+  o += 2;
+  for (int i = 0; i < d; ++i) o[i] = x0[i];
+  o += d;
+  chol_psd(S0, d, o);
+}
 
 // host + device so that the same derived block is produced wherever it is computed
 SMCB_HD void derive_params(int kind, const double* P, double* D) {
@@ -52,6 +108,7 @@ SMCB_HD void derive_params(int kind, const double* P, double* D) {
 }
 
 struct ModelLG1D {
+  using DV = Derived;
   static constexpr int KIND = KIND_LG1D;
   static constexpr int D = 1;
   double A, B, sq, x0, s0, ir, c;
@@ -69,6 +126,7 @@ struct ModelLG1D {
 };
 
 struct ModelSV {
+  using DV = Derived;
   static constexpr int KIND = KIND_SV;
   static constexpr int D = 1;
   double mu, rho, sigma, s0;
@@ -85,6 +143,7 @@ struct ModelSV {
 };
 
 struct ModelUCSV {
+  using DV = Derived;
   static constexpr int KIND = KIND_UCSV;
   static constexpr int D = 3;
   double ge, gn, x0, lse0, lsn0, e0;
@@ -105,6 +164,61 @@ struct ModelUCSV {
   SMCB_HD double logweight(const double* x, double y) const {
     double d = y - x[0];
     return fma(-0.5 * (d * d), det_exp(-x[2]), -(fma(0.5, x[2], SMCB_HALF_LOG_2PI)));
+  }
+};
+
+// MultivariateLinearGaussian (state_space_models.jl:137-189): x' ~ MvNormal(A x, Q), y ~ Normal(B x, R), x1 ~ MvNormal(x0, Σ0).
+// docs/SPEC.md §4b: x'_i = fma-chain of A[i][·] x then of LQ[i][0..i] z; log-weight from v = (y − B x') / sqrt(R).
+template <int DIM>
+struct ModelMVLG {
+  using DV = DerivedMV;
+  static constexpr int KIND = KIND_MVLG2 + DIM - 2;
+  static constexpr int D = DIM;
+  double A[DIM][DIM], B[DIM], LQ[DIM][DIM], ir, c, x0[DIM], L0[DIM][DIM];
+  SMCB_HD void load(const double* d) {
+    const double* o = d;
+    for (int i = 0; i < DIM; ++i)
+      for (int j = 0; j < DIM; ++j) A[i][j] = o[i * DIM + j];
+    o += DIM * DIM;
+    for (int i = 0; i < DIM; ++i) B[i] = o[i];
+    o += DIM;
+    for (int i = 0; i < DIM; ++i)
+      for (int j = 0; j < DIM; ++j) LQ[i][j] = o[i * DIM + j];
+    o += DIM * DIM;
+    ir = o[0];
+    c = o[1];
+    o += 2;
+    for (int i = 0; i < DIM; ++i) x0[i] = o[i];
+    o += DIM;
+    for (int i = 0; i < DIM; ++i)
+      for (int j = 0; j < DIM; ++j) L0[i][j] = o[i * DIM + j];
+  }
+  SMCB_HD void init(const double* z, double* x) const {
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) {
+      double acc = x0[i];
+#pragma unroll
+      for (int j = 0; j <= i; ++j) acc = fma(L0[i][j], z[j], acc);
+      x[i] = acc;
+    }
+  }
+  SMCB_HD void transition(const double* z, const double* xp, double* x) const {
+#pragma unroll
+    for (int i = 0; i < DIM; ++i) {
+      double acc = A[i][0] * xp[0];
+#pragma unroll
+      for (int j = 1; j < DIM; ++j) acc = fma(A[i][j], xp[j], acc);
+#pragma unroll
+      for (int j = 0; j <= i; ++j) acc = fma(LQ[i][j], z[j], acc);
+      x[i] = acc;
+    }
+  }
+  SMCB_HD double logweight(const double* x, double y) const {
+    double m = B[0] * x[0];
+#pragma unroll
+    for (int j = 1; j < DIM; ++j) m = fma(B[j], x[j], m);
+    const double v = (y - m) * ir;
+    return fma(-0.5 * v, v, c);
   }
 };
 

@@ -298,7 +298,7 @@ def log_likelihood(N, y, model, *, resampler="multinomial", ctx=None, stream=0):
     """x, w, logZ = log_likelihood(N, y, model)  — particles.jl:132-147, one call for the whole series."""
     ctx = ctx or default_context()
     y = np.asarray(y, np.float64)
-    if int(N) <= _SMALL_N_MAX and y.size > 1:
+    if int(N) <= _SMALL_N_MAX and y.size > 1 and model.kind <= _lib.UCSV:    # (multivariate linear models run on the single filter)
         # a small cloud (BASELINE configs[0]: N = 1024, T = 100) lives in one CTA for the whole series: ONE launch of the
         # block-resident engine instead of two to four grid-wide launches per observation (same arithmetic, same x, w, logZ)
         b = ctx.batch(model.kind, 1, int(N))

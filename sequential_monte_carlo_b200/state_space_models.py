@@ -108,10 +108,10 @@ def UC(x0, σε, ση):
 class MultivariateLinearModel(StateSpaceModel):
     """LinearModel with a vector state and a scalar observation (state_space_models.jl:137-186):
     x[t] ~ N(A x[t-1], Q), y[t] ~ N(B x[t], R), x[0] ~ N(X0, Σ0).  Served by the matrix Kalman filter on the device
-    (kalman_filter.kalman_filter / log_likelihood, kalman_filter.jl:3-27,55-70; state dimension <= 4).  It has no
-    particle-filter functor: `kind` is None, so the particle filters refuse it (the reference's own PF cannot run the
-    one multivariate model it ships either — hodrick_prescott's Q is singular and MvNormal(A*x, Q) throws)."""
-    kind = None
+    (kalman_filter.kalman_filter / log_likelihood, kalman_filter.jl:3-27,55-70; state dimension <= 4) and, for d = 2..4, by the
+    particle filters of the large-N single filter (bootstrap_filter / bootstrap_filter! / log_likelihood: device functor
+    ModelMVLG<d>, csrc/smcb_models.cuh; docs/SPEC.md §4b).  Q and Σ0 may be positive semi-definite (hodrick_prescott's Q has a
+    zero pivot, where the reference's own MvNormal(A*x, Q) throws); R is a variance, as in the reference's Kalman filter."""
 
     def __init__(self, A, B, Q, R, X0=None, Σ0=None):
         self.A = np.atleast_2d(np.asarray(A, np.float64))
@@ -124,13 +124,17 @@ class MultivariateLinearModel(StateSpaceModel):
         self.x0 = np.zeros(d) if X0 is None else np.asarray(X0, np.float64).reshape(d)
         self.σ0 = np.eye(d) if Σ0 is None else np.asarray(Σ0, np.float64).reshape(d, d)
         self.state_dim = d
+        self.kind = (None, None, _lib.MVLG2, _lib.MVLG3, _lib.MVLG4)[d]    # d = 1: use LinearGaussian (the univariate kind)
 
     def block(self):
         """[3d² + 2d + 1] row-major block A, B, Q, R, x0, Σ0 (include/smcb200.h, smcb_kalman_mv_batch_*)"""
         return np.concatenate([self.A.ravel(), self.B.ravel(), self.Q.ravel(), self.R, self.x0, self.σ0.ravel()])
 
     def params(self):
-        raise NotImplementedError("multivariate linear models are served by the Kalman filter only (no particle-filter functor)")
+        """the parameter block the particle filters take for the multivariate kinds (include/smcb200.h: SMCB_MVLG2..4)"""
+        if self.kind is None:
+            raise NotImplementedError("a one-dimensional multivariate model: use LinearGaussian(A, B, Q, R, x0, σ0)")
+        return self.block()
 
     def __repr__(self):
         return f"MultivariateLinearModel(d={self.state_dim})"

@@ -571,6 +571,75 @@ def test_f32_arithmetic_tier_agrees_with_binary64(ctx, oracle):
     assert abs(z32 - kal) <= 1e-4 * abs(kal) and abs(z64 - kal) <= 1e-4 * abs(kal), (z32, z64, kal)
 
 
+def _mv_model(d, rng):
+    """a stable d-dimensional MultivariateLinearGaussian with a full-rank Q (state_space_models.jl:137-154)"""
+    A = 0.7 * np.eye(d) + 0.1 * rng.normal(size=(d, d)) / d
+    G = rng.normal(size=(d, d))
+    S0 = rng.normal(size=(d, d))
+    return smc.MultivariateLinearGaussian(A=A, B=rng.normal(size=d), Q=0.3 * (G @ G.T) / d + 0.05 * np.eye(d), R=[0.6],
+                                          X0=0.3 * rng.normal(size=d), Σ0=(S0 @ S0.T) / d + 0.2 * np.eye(d))
+
+
+@pytest.mark.parametrize("d", [2, 3, 4])
+def test_multivariate_linear_gaussian_particle_filter(ctx, oracle, d):
+    """the particle-filter functor of MultivariateLinearGaussian (state_space_models.jl:156-189; MvNormal(A x, Q)
+    transition through the Cholesky factor of Q, scalar observation): ancestors, states, log-weights bit-exact against the oracle
+    for every resampler incl. the two-level multinomial draw, and the likelihood against the reference's own exact filter —
+    the matrix Kalman filter (kalman_filter.jl:3-27), on the device and in the oracle."""
+    rng = np.random.default_rng(40 + d)
+    m = _mv_model(d, rng)
+    T = 10
+    x_sim, y = smc.simulate(m, T, seed=5)
+    xo, yo = oracle.simulate(m.kind, m.block(), T, 5)
+    np.testing.assert_array_equal(y, yo)
+    np.testing.assert_array_equal(x_sim, xo.T)
+    for N, rs in ((1024, smc.SYSTEMATIC), (5001, smc.MULTINOMIAL), (20011, smc.STRATIFIED), (30000, smc.MULTINOMIAL)):
+        ref = oracle.log_likelihood(m.kind, m.block(), N, y, rs, 21, 1, 0, want_anc=True)
+        ctx.set_rng(21, 1)
+        ctx.record_ancestors(True)
+        logZ, logmu, ess = ctx.log_likelihood(m.kind, m.block(), N, y, rs, 0, per_step=True)
+        anc = ctx.fetch_ancestors(T - 1)
+        x, w, logw = ctx.fetch_state(want_logw=True)
+        ctx.record_ancestors(False)
+        assert x.shape == (d, N)
+        np.testing.assert_array_equal(anc, ref["anc"][1:])
+        np.testing.assert_array_equal(x, ref["x"])
+        np.testing.assert_array_equal(logw, ref["logw"])
+        np.testing.assert_allclose(logmu, ref["logmu"], rtol=RTOL, atol=0)
+        assert abs(logZ - ref["logZ"]) <= RTOL * abs(ref["logZ"])
+    # the public API and the exact answer: PF log-mean-exp over seeds against the matched-init matrix Kalman filter
+    kal = float(ctx.kalman_mv_loglik(d, m.block(), y, matched_init=True)[0][0])
+    zs = []
+    for seed in range(6):
+        ctx.set_rng(100 + seed, 0)
+        xh, wh, z = smc.log_likelihood(1 << 17, y, m, resampler="systematic", ctx=ctx)
+        zs.append(z)
+    assert np.asarray(xh).shape == (1 << 17, d) and abs(np.asarray(wh).sum() - 1) < 1e-12
+    zs = np.array(zs)
+    lme = zs.max() + np.log(np.mean(np.exp(zs - zs.max())))
+    assert abs(lme - kal) < 4 * max(zs.std(), 1e-3) / np.sqrt(len(zs)) + 5e-3, (lme, kal, zs.std())
+    mean, var, q = ctx.summary([0.5])
+    assert mean.shape == (d,) and q.shape == (d, 1)
+    with pytest.raises(smc.SMCBError):
+        ctx.batch(m.kind, 4, 128)                              # batched / θ-level engines: univariate kinds and UCSV only
+
+
+def test_hodrick_prescott_particle_filter(ctx, oracle):
+    """hodrick_prescott (state_space_models.jl:193-202): Q = diag(1/λ, 0) is singular — the reference's MvNormal(A x, Q) throws —
+    and the second state component is the lagged first; the functor's semi-definite Cholesky makes that exact."""
+    y = smc.simulate(smc.LinearGaussian(0.9, 1.0, 0.3, 1.0, 2.0), 40, seed=3)[1]
+    hp = smc.hodrick_prescott(λ=50.0, y=y, init_cov=4.0)
+    N = 50000
+    ref = oracle.log_likelihood(hp.kind, hp.block(), N, y, smc.SYSTEMATIC, 8, 0, 0)
+    ctx.set_rng(8, 0)
+    z = ctx.log_likelihood(hp.kind, hp.block(), N, y, smc.SYSTEMATIC)
+    x, _, _ = ctx.fetch_state(want_w=False)
+    np.testing.assert_array_equal(x, ref["x"])
+    assert abs(z - ref["logZ"]) <= RTOL * abs(ref["logZ"])
+    kal = float(ctx.kalman_mv_loglik(2, hp.block(), y, matched_init=True)[0][0])
+    assert abs(z - kal) < 0.5, (z, kal)
+
+
 def test_readme_loop_through_the_host_mirror(oracle):
     """The README's online loop (README.md:33-61) spelled with the reference's function names:
     bootstrap_filter, then bootstrap_filter! and quantile per observation; particle_filter / particle_filter!

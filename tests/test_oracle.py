@@ -206,6 +206,30 @@ def test_particle_filter_targets_kalman_likelihood(oracle):
     assert 0 < abs(kf - kf_ref) < 0.3
 
 
+def test_multivariate_lg_particle_filter_targets_the_matrix_kalman_likelihood(oracle):
+    """SPEC §4b: the oracle's multivariate-LG particle filter (state_space_models.jl:156-189) is unbiased for the likelihood of the
+    reference's own exact filter, the matrix Kalman recursion (kalman_filter.jl:3-27, matched initial condition: SURVEY D1) — for a
+    full-rank model and for hodrick_prescott's singular Q."""
+    rng = np.random.default_rng(2)
+    A = np.array([[0.8, 0.1], [0.0, 0.5]])
+    blk = np.concatenate([A.ravel(), [1.0, 0.5], [0.5, 0.1, 0.1, 0.3], [0.7], [0.5, -0.2], [1.0, 0.2, 0.2, 0.5]])
+    _, y = oracle.simulate(3, blk, 40, 7)
+    _, _, kal = oracle.kalman_mv_loglik(2, blk, y, matched_init=True)
+    zs = np.array([oracle.log_likelihood(3, blk, 3000, y, 2, s, 0, 0)["logZ"] for s in range(12)])
+    lme = zs.max() + np.log(np.mean(np.exp(zs - zs.max())))
+    assert abs(lme - kal) < 4 * zs.std() / np.sqrt(12) + 0.02, (lme, kal, zs.std())
+    hp = np.concatenate([[2.0, -1.0, 1.0, 0.0], [1.0, 0.0], [1 / 50.0, 0.0, 0.0, 0.0], [1.0], [3 * y[0] - 2 * y[1], 2 * y[0] - y[1]], [4.0, 0.0, 0.0, 4.0]])
+    _, _, kalhp = oracle.kalman_mv_loglik(2, hp, y, matched_init=True)
+    r = oracle.log_likelihood(3, hp, 20000, y, 2, 1, 0, 0)
+    assert abs(r["logZ"] - kalhp) < 0.6, (r["logZ"], kalhp)
+    # a 4-dimensional state uses all of z[4]: states are finite, the filter runs
+    A4 = 0.6 * np.eye(4)
+    blk4 = np.concatenate([A4.ravel(), np.ones(4), (0.2 * np.eye(4)).ravel(), [0.5], np.zeros(4), np.eye(4).ravel()])
+    _, y4 = oracle.simulate(5, blk4, 20, 3)
+    r4 = oracle.log_likelihood(5, blk4, 2000, y4, 0, 1, 0, 0)
+    assert r4["x"].shape == (4, 2000) and np.isfinite(r4["logZ"])
+
+
 def test_oracle_regression_vectors(oracle):
     for v in json.load(open(os.path.join(GOLD, "oracle_vectors.json"))):
         _, y = oracle.simulate(v["kind"], v["params"], v["T"], v["data_seed"])

@@ -137,8 +137,9 @@ def test_host_mirror_of_the_new_models_and_proposals():
     m = smc.MultivariateLinearGaussian(A=np.eye(3), B=[1, 0, 0], Q=np.eye(3), R=[2.0])
     np.testing.assert_array_equal(m.x0, np.zeros(3))                               # X0 = zeros, Σ0 = I  :137
     np.testing.assert_array_equal(m.σ0, np.eye(3))
+    assert m.kind == smc._lib.MVLG3 and np.array_equal(m.params(), m.block())          # the particle-filter functor's block (SPEC §4b)
     with pytest.raises(NotImplementedError):
-        m.params()
+        smc.MultivariateLinearGaussian(A=[[0.5]], B=[1.0], Q=[[1.0]], R=[1.0]).params()  # d = 1: LinearGaussian is the univariate kind
     lg = smc.LinearGaussian(0.5, 1.0, 0.9, 0.8)
     c0, c1, c2 = smc.locally_optimal_proposal(lg, 0.3)
     s2 = 1 / (1 / 0.9 + 1 / 0.8)
