@@ -104,7 +104,10 @@ class ClockSampler:
 
 
 # algorithmic bytes per particle-update of each launch of one step (LG1D fp64): they add up to the 56 B of SURVEY §8(d)
-KERNEL_BYTES = {"scan": 16, "bounds": 0, "anc": 12, "prop": 28}
+KERNEL_BYTES = {"scan": 16, "bounds": 0, "anc": 12, "prop": 28}   # SURVEY §8d's algorithmic split of the 56 B
+# what the LG1D launches really move: the log-weight is two fma of x', so move_kernel does not store it (−8 B) and sum_kernel
+# reads x' instead of logw (same 8 B): 48 B per particle-update
+KERNEL_BYTES_MOVED_LG1D = {"scan": 16, "bounds": 0, "anc": 12, "prop": 20}
 KERNEL_NAMES = {"scan": "sum_kernel", "bounds": "bounds_kernel", "anc": "anc_hist_kernel", "prop": "move_kernel"}
 
 
@@ -343,8 +346,9 @@ def main():
                                "(16 + 0 + 12 + 28 = 56 algorithmic B/particle-update, SURVEY §8d)",
                      "step_us": fused, "step_us_sum_of_per_launch_events": fused_events,
                      "avg_us_per_launch": step_us,
-                     "per_kernel": {KERNEL_NAMES[k]: {"bytes_per_update": KERNEL_BYTES[k], "us": step_us[k],
-                                                      "GB/s": (KERNEL_BYTES[k] * N / (step_us[k] * 1e-6) / 1e9) if step_us[k] else None}
+                     "per_kernel": {KERNEL_NAMES[k]: {"bytes_per_update": KERNEL_BYTES[k], "bytes_moved_per_update": KERNEL_BYTES_MOVED_LG1D[k],
+                                                      "us": step_us[k],
+                                                      "GB/s": (KERNEL_BYTES_MOVED_LG1D[k] * N / (step_us[k] * 1e-6) / 1e9) if step_us[k] else None}
                                     for k in KERNEL_BYTES}},
         "clocks": clocks,
     }

@@ -121,9 +121,10 @@ int smcb_log_likelihood(smcb_ctx* ctx, int kind, const double* params, int64_t N
 /* particle_filter!(states, weights, y, model, proposal) -> (logμ, w, ess)          particles.jl:55-84
  * and the loop of examples/inflation_example.jl:164-171 with a proposal, for ONE large-N filter (docs/SPEC.md §10):
  * proposal = (c0, c1, c2) of x' ~ N(c0 + c1·xp, c2²) for this step ([T][3] for a whole series, row 0 not read — the
- * initial step is smcb_bootstrap_init's).  One-dimensional models (LG1D, SV) and the sorted resamplers; UCSV or
- * multinomial resampling -> SMCB_ERR_UNSUPPORTED (the batched entry points below take multinomial, N <= 8192).
- * Both storage tiers of smcb_set_precision. */
+ * initial step is smcb_bootstrap_init's).  LG1D, SV: both storage tiers of smcb_set_precision.  UCSV (docs/SPEC.md §10b): the triple
+ * is (kappa, 0, 1), kappa in [0, 1] tempers the conditionally optimal move of the trend (0 = bootstrap, 1 = p(x' | x, le, ln', y));
+ * the log-volatilities move by the transition; binary64 states.  Sorted resamplers; multinomial resampling ->
+ * SMCB_ERR_UNSUPPORTED (the batched entry points below take multinomial, N <= 8192). */
 int smcb_guided_step(smcb_ctx* ctx, const double* params, double y, int resampler, const double* proposal, double* logmu,
                      double* ess);
 int smcb_guided_log_likelihood(smcb_ctx* ctx, int kind, const double* params, int64_t N, const double* y, int64_t T,
@@ -164,11 +165,12 @@ int smcb_batch_log_likelihood(smcb_batch* b, const double* params, const uint8_t
 /* Guided filters — particle_filter / particle_filter! with a proposal      particles.jl:28-84 (docs/SPEC.md §10)
  * The reference's proposal is a Julia closure (model, xp) -> distribution; the device evaluates the affine-Gaussian
  * family  x' ~ N(c0 + c1·xp, c2²)  (c2 > 0; a closure over y_t picks the coefficients per step, e.g. the locally
- * optimal proposal of an LG model), for the one-dimensional models (LG1D, SV).  Every step t >= 1 draws x' from the
+ * optimal proposal of an LG model), for the one-dimensional models (LG1D, SV); for UCSV the triple is (kappa, 0, 1), the tempered
+ * optimal trend move of docs/SPEC.md §10b.  Every step t >= 1 draws x' from the
  * proposal and weights by  logpdf(observation(x'), y) + logpdf(transition(xp), x') - logpdf(proposal(xp), x')  (:73-78);
  * the initial step draws from initial_dist and weights by the observation density (:40-42; the reference's
  * "+ logpdf(initial_dist, x)" at :44 lacks its "- logpdf(proposal)" partner, commented out at :45 — ruled a defect).
- * proposal: [M][3] for one step, [T][M][3] for a whole series (row 0 is not read); SMCB_ERR_UNSUPPORTED for UCSV. */
+ * proposal: [M][3] for one step, [T][M][3] for a whole series (row 0 is not read). */
 int smcb_batch_step_guided(smcb_batch* b, const double* params, double y, int resampler, const double* proposal,
                            double* logmu, double* ess);
 int smcb_batch_log_likelihood_guided(smcb_batch* b, const double* params, const uint8_t* active, const double* y,

@@ -346,16 +346,16 @@ def guided_step(kind, params, x, logw, y, t, resampler, prop, seed, epoch=0, str
                                 C.c_int(resampler), C.c_uint64(seed), C.c_uint32(epoch), C.c_uint32(stream), _p(prop),
                                 _p(x), _p(logw), _p(anc))
     if rc != 0:
-        raise ValueError("guided proposals are defined for the one-dimensional models")
+        raise ValueError("guided proposals are defined for LG1D, SV (affine-Gaussian, SPEC §10) and UCSV (tempered optimal trend move, §10b)")
     return anc
 
 
 def guided_log_likelihood(kind, params, n, y, resampler, prop, seed, epoch=0, stream=0):
-    """bootstrap initial step + guided steps; prop: [T, 3] (row 0 unused).  dict(x, logw, logZ, logmu[T], ess[T])."""
+    """bootstrap initial step + guided steps; prop: [T, 3] (row 0 unused; UCSV: (κ, ·, ·), SPEC §10b).  dict(x, logw, logZ, logmu[T], ess[T])."""
     y = np.ascontiguousarray(y, np.float64)
     T = y.size
     prop = np.ascontiguousarray(prop, np.float64).reshape(T, 3)
-    x, logw = np.empty((1, n)), np.empty(n)
+    x, logw = np.empty((state_dim(kind), n)), np.empty(n)
     logmu, ess = np.empty(T), np.empty(T)
     logZ = lib().smco_guided_log_likelihood(C.c_int(kind), _p(params8(params)), C.c_int64(n), _p(y), C.c_int64(T),
                                             C.c_int(resampler), C.c_uint64(seed), C.c_uint32(epoch), C.c_uint32(stream),
@@ -369,7 +369,7 @@ def batch_guided_log_likelihood(kind, params, active, n, y, resampler, prop, see
     M = params.shape[0]
     y = np.ascontiguousarray(y, np.float64)
     prop = np.ascontiguousarray(prop, np.float64).reshape(y.size, M, 3)
-    logZ, x, logw = np.empty(M), np.empty((M, 1, n)), np.empty((M, n))
+    logZ, x, logw = np.empty(M), np.empty((M, state_dim(kind), n)), np.empty((M, n))
     act = None if active is None else np.ascontiguousarray(active, np.uint8)
     lib().smco_batch_guided_log_likelihood(C.c_int(kind), _p(params), _p(act), C.c_int64(M), C.c_int64(n), _p(y),
                                            C.c_int64(y.size), C.c_int(resampler), C.c_uint64(seed), C.c_uint32(epoch),

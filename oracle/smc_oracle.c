@@ -466,15 +466,53 @@ void smco_bootstrap_step(int kind, const double *P, int64_t n, double y, uint32_
 /* particles.jl:55-84 for the one-dimensional models and the affine-Gaussian proposal family of SPEC §10:
  * prop = (c0, c1, c2), x' ~ Normal(c0 + c1 xp, c2).  Same resampling and the same Philox normal as the
  * bootstrap step; logw = logpdf(observation(x'), y) + logpdf(transition(xp), x') - logpdf(proposal(xp), x'). */
+/* UCSV (SPEC §10b): the two log-volatilities move by the transition, the trend by the conditionally optimal Gaussian tempered by
+ * κ = prop[0] in [0, 1]:  r = σε²/ση'² with σε = exp(le/2) (previous, state_space_models.jl:238) and ση'² = exp(ln') (current, :246);
+ * g = κ r/(1 + r); x' ~ Normal(x + g (y − x), (1 − g) σε²); κ = 0 is the bootstrap move, κ = 1 the locally optimal one. */
+static void guided_step_ucsv(const double *D, int64_t n, double y, uint32_t t, uint64_t seed, uint32_t epoch, uint32_t stream,
+                             const double *prop, const int64_t *a, double *x, double *logw) {
+  const double kappa = prop[0];
+  double *xp = (double *)malloc(sizeof(double) * (size_t)(3 * n));
+  for (int k = 0; k < 3; ++k)
+    for (int64_t i = 0; i < n; ++i) xp[(int64_t)k * n + i] = x[(int64_t)k * n + a[i]];
+  for (int64_t i = 0; i < n; ++i) {
+    double z[3], par[3], xi[3];
+    for (int k = 0; k < 3; ++k) {
+      z[k] = o_normal(seed, epoch, (uint32_t)i, stream, t, P_TRANS, (uint32_t)k);
+      par[k] = xp[(int64_t)k * n + i];
+    }
+    xi[1] = fma(D[0], z[1], par[1]);
+    xi[2] = fma(D[1], z[2], par[2]);
+    double sd = o_exp(0.5 * par[1]);
+    double r = (sd * sd) * o_exp(-xi[2]);
+    double g = kappa * (r / (1.0 + r));
+    double omg = 1.0 - g;
+    double mq = fma(g, y - par[0], par[0]);
+    double c2 = sd * sqrt(omg);
+    xi[0] = fma(c2, z[0], mq);                                              /* x[i] = rand(proposal(model, xp[i])) :73 */
+    double zt = (xi[0] - par[0]) / sd;
+    double corr = fma(-0.5 * zt, zt, 0.5 * (z[0] * z[0])) + 0.5 * o_log(omg);  /* logpdf(transition) − logpdf(proposal) :77-78 */
+    for (int k = 0; k < 3; ++k) x[(int64_t)k * n + i] = xi[k];
+    logw[i] = model_logweight(KIND_UCSV, D, xi, y) + corr;                  /* :74 */
+  }
+  free(xp);
+}
+
 int smco_guided_step(int kind, const double *P, int64_t n, double y, uint32_t t, int resampler, uint64_t seed,
                      uint32_t epoch, uint32_t stream, const double *prop, double *x, double *logw, int64_t *anc_out) {
-  if (kind == KIND_UCSV) return -1;
+  if (kind > KIND_UCSV) return -1;
   double D[64];
   smco_derive(kind, P, D);
-  const double c0 = prop[0], c1 = prop[1], c2 = prop[2], lc2 = o_log(prop[2]), ic2 = 1.0 / prop[2];
-  const double isdf = 1.0 / D[2], lsdf = (kind == KIND_LG1D) ? D[7] : D[4];
   int64_t *a = (int64_t *)malloc(sizeof(int64_t) * (size_t)n);              /* a = resample(weights) :66 */
   smco_ancestors(logw, n, resampler, seed, epoch, stream, t, a);
+  if (kind == KIND_UCSV) {
+    guided_step_ucsv(D, n, y, t, seed, epoch, stream, prop, a, x, logw);
+    if (anc_out) memcpy(anc_out, a, sizeof(int64_t) * (size_t)n);
+    free(a);
+    return 0;
+  }
+  const double c0 = prop[0], c1 = prop[1], c2 = prop[2], lc2 = o_log(prop[2]), ic2 = 1.0 / prop[2];
+  const double isdf = 1.0 / D[2], lsdf = (kind == KIND_LG1D) ? D[7] : D[4];
   double *xp = (double *)malloc(sizeof(double) * (size_t)n);               /* xp = deepcopy(x[a]) :68 */
   for (int64_t i = 0; i < n; ++i) xp[i] = x[a[i]];
   for (int64_t i = 0; i < n; ++i) {                                         /* :72-80 */
@@ -501,7 +539,7 @@ int smco_guided_step(int kind, const double *P, int64_t n, double y, uint32_t t,
 double smco_guided_log_likelihood(int kind, const double *P, int64_t n, const double *y, int64_t T, int resampler,
                                   uint64_t seed, uint32_t epoch, uint32_t stream, const double *prop, int64_t prop_stride,
                                   double *x, double *logw, double *logmu_out, double *ess_out) {
-  double *xl = x ? x : (double *)malloc(sizeof(double) * (size_t)n);
+  double *xl = x ? x : (double *)malloc(sizeof(double) * (size_t)(n * smco_state_dim(kind)));
   double *lw = logw ? logw : (double *)malloc(sizeof(double) * (size_t)n);
   double logZ = 0.0, lm, es;
   smco_bootstrap_init(kind, P, n, y[0], seed, epoch, stream, xl, lw);
@@ -529,7 +567,7 @@ void smco_batch_guided_log_likelihood(int kind, const double *P, const uint8_t *
   for (int64_t m = 0; m < M; ++m) {
     if (active && !active[m]) { logZ[m] = -INFINITY; continue; }
     logZ[m] = smco_guided_log_likelihood(kind, P + 8 * m, n, y, T, resampler, seed, epoch, stream0 + (uint32_t)m,
-                                         prop + 3 * m, 3 * M, x ? x + m * n : NULL, logw ? logw + m * n : NULL, NULL, NULL);
+                                         prop + 3 * m, 3 * M, x ? x + m * n * smco_state_dim(kind) : NULL, logw ? logw + m * n : NULL, NULL, NULL);
   }
 }
 

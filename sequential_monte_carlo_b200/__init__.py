@@ -13,7 +13,7 @@ from .state_space_models import (StateSpaceModel, LinearModel, UnivariateLinearG
                                  unobserved_components, UC, UCSV, MultivariateLinearModel, MultivariateLinearGaussian, hodrick_prescott, unobserved_components_stochastic_volatility,
                                  StochasticVolatility, SV, simulate, preallocate, transition, observation, initial_dist, MvNormal)
 from .particles import (normalize, reweight, resample, bootstrap_filter, bootstrap_filter_, particle_filter, particle_filter_, log_likelihood,
-                        AffineGaussianProposal, locally_optimal_proposal, guided_log_likelihood,  # noqa: E402,F401
+                        AffineGaussianProposal, UCSVTrendProposal, locally_optimal_proposal, guided_log_likelihood,  # noqa: E402,F401
                         quantile, weighted_mean_var, default_context, set_default_context)
 from .priors import Normal, LogNormal, Uniform, TruncatedNormal, product_distribution  # noqa: E402,F401
 from .smc_samplers import (SMC, smc2, smc2_step, density_tempered, expected_parameters, random_walk_kernel,  # noqa: E402,F401

@@ -32,7 +32,21 @@ struct BatchArgs {
   int from_init;            // t_begin == 0 draws the cloud; else continue from (x, logw, stats)
   int x_in_smem;
   int64_t npad;             // N rounded up to even
+  int64_t M;                // θ-particles of this launch (the grid of the static kernel)
+  // dynamic (θ, chunk) scheduling (DYN kernels): the series is cut into nchunks chunks of `chunk` steps, the resident CTAs claim
+  // units u = c·M + m from sched[0] in order, and sched[1 + m] counts the finished chunks of θ-particle m
+  unsigned* sched;
+  uint32_t chunk, nchunks;
 };
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // the transition density of the guided kernels; empty for the bootstrap ones
 template <class Model, bool GUIDED>
@@ -66,17 +80,17 @@ __device__ __forceinline__ int smem_lower_count_from(const uint64_t* C, int lo, 
 
 // GUIDED: the move of every step t >= 1 draws from the affine-Gaussian proposal of (t, θ) and the weight carries
 // transition / proposal (particle_filter!, particles.jl:66-80; SPEC §10); D = 1 models only.
-template <class Model, int PAIRS, int MAXT, bool GUIDED>
-__global__ void __launch_bounds__(MAXT) batch_kernel(const BatchArgs a) {
+// One unit of work: θ-particle m, observations tb..te (the whole launch for the static kernel, one chunk for the dynamic one).
+// from_init: tb == 0 draws the cloud; else the unit continues from (x, logw, stats) in global memory, and with `carry` also
+// from the running Σ logμ in logz_out[m] — the sum is continued in the same order, so a chunked series gives the bits of an
+// unchunked one.
+template <class Model, int PAIRS, bool GUIDED>
+__device__ __forceinline__ void batch_unit(const BatchArgs& a, const int64_t m, const uint32_t tb, const uint32_t te, const bool from_init,
+                                           const bool carry, unsigned char* smem_raw, unsigned long long (*s_wq)[32], double (*s_f)[32]) {
   constexpr int D = Model::D;
-  static_assert(!GUIDED || D == 1, "guided proposals are defined for the one-dimensional models");
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ unsigned long long s_wq[PAIRS][32];
-  __shared__ double s_f[3][32];
-
+  static_assert(!GUIDED || D == 1 || Model::KIND == KIND_UCSV, "guided proposals: affine-Gaussian for D = 1 (SPEC §10), the tempered trend move for UCSV (§10b)");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nthreads = blockDim.x, nwarps = nthreads >> 5;
-  const int64_t m = blockIdx.x;
   if (a.active && !a.active[m]) {
     if (tid == 0) {
       a.logz_out[m] = -INFINITY;
@@ -102,7 +116,7 @@ __global__ void __launch_bounds__(MAXT) batch_kernel(const BatchArgs a) {
 
   double lw[PAIRS][2];
   double mx = -INFINITY;
-  double logz = 0.0;
+  double logz = carry ? __ldcg(a.logz_out + m) : 0.0;
   bool account = true;
 
   // block-uniform max of the thread-local log-weights (exact, order-independent)
@@ -114,30 +128,30 @@ __global__ void __launch_bounds__(MAXT) batch_kernel(const BatchArgs a) {
     return warp_max(r);
   };
 
-  if (!a.from_init) {
-    // continue from the stored cloud
+  if (!from_init) {
+    // continue from the stored cloud (L2 loads: under dynamic scheduling another SM may have written it)
 #pragma unroll
     for (int r = 0; r < PAIRS; ++r) {
       const int p = r * nthreads + tid;
       const int i = 2 * p;
-      lw[r][0] = (i < N) ? glw[i] : -INFINITY;
-      lw[r][1] = (i + 1 < N) ? glw[i + 1] : -INFINITY;
+      lw[r][0] = (i < N) ? __ldcg(glw + i) : -INFINITY;
+      lw[r][1] = (i + 1 < N) ? __ldcg(glw + i + 1) : -INFINITY;
       if (a.x_in_smem && p < npairs) {
 #pragma unroll
         for (int k = 0; k < D; ++k) {
-          xs[k * ldx + i] = gx[k * ld + i];
-          if (i + 1 < N) xs[k * ldx + i + 1] = gx[k * ld + i + 1];
+          xs[k * ldx + i] = __ldcg(gx + k * ld + i);
+          if (i + 1 < N) xs[k * ldx + i + 1] = __ldcg(gx + k * ld + i + 1);
         }
       }
     }
-    mx = a.stats[m].mx;
+    mx = __ldcg(&a.stats[m].mx);
     account = false;  // the stored weights' logμ was reported by the launch that produced them
     __syncthreads();
   }
 
-  for (uint32_t t = a.t_begin; t <= a.t_end; ++t) {
+  for (uint32_t t = tb; t <= te; ++t) {
     const double y = a.y[t - a.t_begin];
-    if (t == 0 && a.from_init) {
+    if (t == 0 && from_init) {
       // bootstrap_filter: x_i ~ initial_dist; logw_i = logpdf(observation(x_i), y1)   particles.jl:96-99
 #pragma unroll
       for (int r = 0; r < PAIRS; ++r) {
@@ -164,7 +178,7 @@ __global__ void __launch_bounds__(MAXT) batch_kernel(const BatchArgs a) {
       // the proposal of this step is requested first: its L2 / HBM round trip hides behind the normalisation and the search
       double pc[kProposalStride] = {0.0, 0.0, 0.0, 0.0, 0.0};
       if constexpr (GUIDED) {
-        const double* g = a.prop + ((int64_t)(t - a.t_begin) * (int64_t)gridDim.x + m) * kProposalStride;
+        const double* g = a.prop + ((int64_t)(t - a.t_begin) * a.M + m) * kProposalStride;
 #pragma unroll
         for (int k = 0; k < kProposalStride; ++k) pc[k] = __ldg(g + k);
       }
@@ -271,7 +285,8 @@ __global__ void __launch_bounds__(MAXT) batch_kernel(const BatchArgs a) {
 #pragma unroll
           for (int k = 0; k < D; ++k)
             normal_pair_at(a.key, (uint32_t)p, stream, t, PURPOSE_TRANSITION, (uint32_t)k, za[k], zb[k]);
-          if constexpr (GUIDED) lw[r][0] = guided_move(mdl, fdens, pc, za[0], xpa[r][0], y, xa);
+          if constexpr (GUIDED && D == 1) lw[r][0] = guided_move(mdl, fdens, pc, za[0], xpa[r][0], y, xa);
+          else if constexpr (GUIDED) lw[r][0] = guided_move_ucsv(mdl, pc[0], za, xpa[r], y, xa);
           else {
             mdl.transition(za, xpa[r], xa);
             lw[r][0] = mdl.logweight(xa, y);
@@ -279,7 +294,8 @@ __global__ void __launch_bounds__(MAXT) batch_kernel(const BatchArgs a) {
 #pragma unroll
           for (int k = 0; k < D; ++k) xs[k * ldx + i] = xa[k];
           if (i + 1 < N) {
-            if constexpr (GUIDED) lw[r][1] = guided_move(mdl, fdens, pc, zb[0], xpb[r][0], y, xb);
+            if constexpr (GUIDED && D == 1) lw[r][1] = guided_move(mdl, fdens, pc, zb[0], xpb[r][0], y, xb);
+            else if constexpr (GUIDED) lw[r][1] = guided_move_ucsv(mdl, pc[0], zb, xpb[r], y, xb);
             else {
               mdl.transition(zb, xpb[r], xb);
               lw[r][1] = mdl.logweight(xb, y);
@@ -347,6 +363,48 @@ __global__ void __launch_bounds__(MAXT) batch_kernel(const BatchArgs a) {
           for (int k = 0; k < D; ++k) gx[k * ld + i] = xs[k * ldx + i];
         }
       }
+    }
+  }
+}
+
+// Static kernel: one CTA per θ-particle, the whole series.  DYN: a persistent grid (one wave of resident CTAs) claims
+// (chunk, θ) units in order — 512 θ on 148 one-CTA SMs are 3.46 waves of whole series (4 with one CTA per θ, 13.5 % of the
+// launch idle: the θ-sharded config 5 on 8 GPUs), but 3.46·C waves of chunks.  Unit (c, m) needs unit (c − 1, m), which was
+// claimed M units earlier by a CTA that is running: waiting on it cannot deadlock.
+// (the scheduling loop of the small-CTA kernels of the one-component models must not cost them a resident CTA: same register cap as
+// the static kernels, which fit 1024 / MAXT CTAs of 64-register threads)
+template <class Model, int PAIRS, int MAXT, bool GUIDED, bool DYN>
+__global__ void __launch_bounds__(MAXT, (DYN && Model::D == 1 && PAIRS <= 2 && !GUIDED) ? 1024 / MAXT : 1) batch_kernel(const BatchArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ unsigned long long s_wq[PAIRS][32];
+  __shared__ double s_f[3][32];
+  if constexpr (!DYN) {
+    batch_unit<Model, PAIRS, GUIDED>(a, (int64_t)blockIdx.x, a.t_begin, a.t_end, a.from_init != 0, false, smem_raw, s_wq, s_f);
+  } else {
+    __shared__ unsigned s_unit;
+    const unsigned M = (unsigned)a.M, nunits = M * a.nchunks;
+    for (;;) {
+      if (threadIdx.x == 0) s_unit = atomicAdd(a.sched, 1u);
+      __syncthreads();
+      const unsigned u = s_unit;
+      if (u >= nunits) break;
+      const unsigned c = u / M, m = u - c * M;
+      const bool act = !(a.active && !a.active[m]);
+      if (act && c > 0) {
+        if (threadIdx.x == 0) {
+          while (ld_acquire_u32(a.sched + 1 + m) < c) __nanosleep(100);
+          __threadfence();
+        }
+        __syncthreads();  // the acquire above orders every thread's reads of the cloud after the producer's writes
+      }
+      if (act || c == 0) {
+        const uint32_t tb = a.t_begin + c * a.chunk;
+        const uint32_t te = (tb + a.chunk - 1 < a.t_end) ? tb + a.chunk - 1 : a.t_end;
+        batch_unit<Model, PAIRS, GUIDED>(a, (int64_t)m, tb, te, a.from_init != 0 && c == 0, c > 0, smem_raw, s_wq, s_f);
+      }
+      __threadfence();
+      __syncthreads();  // also: everybody has read s_unit and is done with the shared scratch
+      if (act && threadIdx.x == 0) st_release_u32(a.sched + 1 + m, c + 1);
     }
   }
 }
@@ -668,26 +726,68 @@ __global__ void proposal_prepare_kernel(const double* __restrict__ raw, double* 
   q[4] = 1.0 / c2;
 }
 
+struct DynPlan {   // host side of the dynamic scheduling
+  unsigned* sched;  // [1 + M]
+  int num_sms;
+  int force_chunk;  // SMCB_BATCH_CHUNK: -1 automatic, 0 never, K > 0 chunks of K steps
+};
+
 template <class Model, int PAIRS, int MAXT, bool GUIDED>
-void launch_batch(const BatchArgs& a, int64_t M, int threads, size_t smem, cudaStream_t stream) {
-  auto kern = batch_kernel<Model, PAIRS, MAXT, GUIDED>;
-  SMCB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<(unsigned)M, threads, smem, stream>>>(a);
+void launch_batch(BatchArgs a, int64_t M, int threads, size_t smem, cudaStream_t stream, const DynPlan& dp) {
+  auto kern = batch_kernel<Model, PAIRS, MAXT, GUIDED, false>;
+  auto kdyn = batch_kernel<Model, PAIRS, MAXT, GUIDED, true>;
+  const int64_t steps = (int64_t)a.t_end - (int64_t)a.t_begin + 1;
+  int64_t chunk = 0, slots = 0;
+  if (dp.force_chunk != 0 && steps >= 2 && dp.sched) {
+    SMCB_CUDA_TRY(cudaFuncSetAttribute(kdyn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int occ = 0;
+    SMCB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kdyn, threads, smem));
+    slots = (int64_t)std::max(occ, 1) * dp.num_sms;
+    if (dp.force_chunk > 0) chunk = dp.force_chunk;
+    else if (M > dp.num_sms) {
+      // Whole series, one CTA per θ, waste two ways (measured: profiles/r2_chunk_*.jsonl).  More θ than resident CTAs: ceil(M / slots)
+      // waves for M / slots waves of work (UCSV 4096: 512 θ on 148 slots, SV 2048: 1024 θ on 296 slots — 3.46 waves run as 4).
+      // All resident but unevenly spread over SMs whose warps are saturated: the SMs that hold ceil(M / SMs) CTAs finish last
+      // (LG1D 1024: 512 CTAs of 256 threads on 148 SMs).  Chunks pay when either wastes more than 3 %; a chunk boundary costs
+      // 5-7 µs (publish, acquire, reload), so chunks are at least 8 steps of a cloud of >= 1024 particles.
+      const double waves = (double)M / (double)slots, load = (double)M / (double)dp.num_sms;
+      double eff = 1.0;
+      if (M > slots) eff = waves / std::ceil(waves);
+      else if ((int64_t)threads * (int64_t)std::ceil(load) >= 1024) eff = load / std::ceil(load);
+      const int64_t min_chunk = std::max<int64_t>(8, 8192 / std::max<int64_t>(a.N, 1));
+      if (eff < 0.97 && steps >= 2 * min_chunk) {
+        const int64_t want = (33 * slots + M - 1) / M;              // chunks per θ for >= 33 waves of units
+        const int64_t nch = std::max<int64_t>(1, std::min<int64_t>(want, steps / min_chunk));
+        chunk = (steps + nch - 1) / nch;
+      }
+    }
+    if (chunk >= steps) chunk = 0;
+  }
+  if (chunk > 0) {
+    a.sched = dp.sched;
+    a.chunk = (uint32_t)chunk;
+    a.nchunks = (uint32_t)((steps + chunk - 1) / chunk);
+    SMCB_CUDA_TRY(cudaMemsetAsync(dp.sched, 0, sizeof(unsigned) * (size_t)(M + 1), stream));
+    kdyn<<<(unsigned)std::min<int64_t>(M, slots), threads, smem, stream>>>(a);
+  } else {
+    SMCB_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<(unsigned)M, threads, smem, stream>>>(a);
+  }
   SMCB_CUDA_TRY(cudaGetLastError());
 }
 
 template <class Model, bool GUIDED = false>
-void launch_batch_model(const BatchArgs& a, int64_t M, int pairs, int threads, size_t smem, cudaStream_t stream) {
+void launch_batch_model(const BatchArgs& a, int64_t M, int pairs, int threads, size_t smem, cudaStream_t stream, const DynPlan& dp) {
   if (pairs == 2) {
-    if (threads <= 256) launch_batch<Model, 2, 256, GUIDED>(a, M, threads, smem, stream);
-    else if (threads <= 512) launch_batch<Model, 2, 512, GUIDED>(a, M, threads, smem, stream);
-    else launch_batch<Model, 2, 1024, GUIDED>(a, M, threads, smem, stream);
+    if (threads <= 256) launch_batch<Model, 2, 256, GUIDED>(a, M, threads, smem, stream, dp);
+    else if (threads <= 512) launch_batch<Model, 2, 512, GUIDED>(a, M, threads, smem, stream, dp);
+    else launch_batch<Model, 2, 1024, GUIDED>(a, M, threads, smem, stream, dp);
   } else if (pairs == 1) {
-    if (threads <= 512) launch_batch<Model, 1, 512, GUIDED>(a, M, threads, smem, stream);
-    else launch_batch<Model, 1, 1024, GUIDED>(a, M, threads, smem, stream);
+    if (threads <= 512) launch_batch<Model, 1, 512, GUIDED>(a, M, threads, smem, stream, dp);
+    else launch_batch<Model, 1, 1024, GUIDED>(a, M, threads, smem, stream, dp);
   } else {
-    if (threads <= 512) launch_batch<Model, 4, 512, GUIDED>(a, M, threads, smem, stream);
-    else launch_batch<Model, 4, 1024, GUIDED>(a, M, threads, smem, stream);
+    if (threads <= 512) launch_batch<Model, 4, 512, GUIDED>(a, M, threads, smem, stream, dp);
+    else launch_batch<Model, 4, 1024, GUIDED>(a, M, threads, smem, stream, dp);
   }
 }
 
@@ -719,6 +819,7 @@ BatchFilter::BatchFilter(int device, cudaStream_t stream, int kind, int64_t M, i
   SMCB_CUDA_TRY(cudaMalloc(&derived_, sizeof(double) * M * kParamStride));
   SMCB_CUDA_TRY(cudaMalloc(&active_, M));
   SMCB_CUDA_TRY(cudaMalloc(&out_dev_, sizeof(double) * 2 * M));
+  SMCB_CUDA_TRY(cudaMalloc(&sched_, sizeof(unsigned) * (size_t)(M + 1)));
   host_tmp_.resize((size_t)(M * kParamStride));
 }
 
@@ -730,6 +831,7 @@ BatchFilter::~BatchFilter() {
   }
   cudaFree(derived_); cudaFree(active_); cudaFree(y_dev_); cudaFree(out_dev_); cudaFree(w_tmp_); cudaFree(slots_dev_);
   cudaFree(prop_dev_);
+  cudaFree(sched_);
 }
 
 void BatchFilter::begin_call() {
@@ -759,12 +861,13 @@ void BatchFilter::upload_params(const double* params, const uint8_t* active) {
 // proposal: [rows][M][3] host coefficients (c0, c1, c2) of x' ~ N(c0 + c1 xp, c2^2); the device block is [rows][M][5] with
 // det_log(c2) and 1 / c2 appended by proposal_prepare_kernel (SPEC §10; the device det_log is the host's bit for bit)
 void BatchFilter::upload_proposal(const double* proposal, int64_t rows) {
-  if (d_ != 1) throw Error{SMCB_ERR_UNSUPPORTED, "guided proposals are defined for the one-dimensional models (LG1D, SV)"};
   const int64_t n = rows * M_;
   for (int64_t j = 0; j < n; ++j) {
     const double c2 = proposal[3 * j + 2];
     if (!(c2 > 0.0) || !std::isfinite(c2) || !std::isfinite(proposal[3 * j]) || !std::isfinite(proposal[3 * j + 1]))
       throw Error{SMCB_ERR_BAD_ARG, "proposal: coefficients must be finite and the standard deviation c2 > 0"};
+    if (kind_ == KIND_UCSV && !(proposal[3 * j] >= 0.0 && proposal[3 * j] <= 1.0))
+      throw Error{SMCB_ERR_BAD_ARG, "proposal (UCSV, docs/SPEC.md §10b): the triple is (kappa, 0, 1) with kappa in [0, 1]"};
   }
   if (prop_cap_ < n) {
     cudaFree(prop_dev_);
@@ -835,17 +938,23 @@ void BatchFilter::launch(const IO& io, bool from_init, uint32_t t_begin, uint32_
   a.from_init = from_init ? 1 : 0;
   a.x_in_smem = x_in_smem ? 1 : 0;
   a.npad = npad;
+  a.M = M_;
+  a.sched = nullptr;
+  a.chunk = 0;
+  a.nchunks = 1;
+  DynPlan dp{sched_, num_sms_, -1};
+  if (const char* e = std::getenv("SMCB_BATCH_CHUNK")) dp.force_chunk = std::atoi(e);
   if (guided) {
-    if (kind_ == KIND_LG1D) launch_batch_model<ModelLG1D, true>(a, M_, pairs, threads, smem, stream_);
-    else if (kind_ == KIND_SV) launch_batch_model<ModelSV, true>(a, M_, pairs, threads, smem, stream_);
-    else throw Error{SMCB_ERR_UNSUPPORTED, "guided proposals are defined for the one-dimensional models (LG1D, SV)"};
+    if (kind_ == KIND_LG1D) launch_batch_model<ModelLG1D, true>(a, M_, pairs, threads, smem, stream_, dp);
+    else if (kind_ == KIND_SV) launch_batch_model<ModelSV, true>(a, M_, pairs, threads, smem, stream_, dp);
+    else launch_batch_model<ModelUCSV, true>(a, M_, pairs, threads, smem, stream_, dp);
     ++launches_;
     return;
   }
   switch (kind_) {
-    case KIND_LG1D: launch_batch_model<ModelLG1D>(a, M_, pairs, threads, smem, stream_); break;
-    case KIND_SV: launch_batch_model<ModelSV>(a, M_, pairs, threads, smem, stream_); break;
-    default: launch_batch_model<ModelUCSV>(a, M_, pairs, threads, smem, stream_); break;
+    case KIND_LG1D: launch_batch_model<ModelLG1D>(a, M_, pairs, threads, smem, stream_, dp); break;
+    case KIND_SV: launch_batch_model<ModelSV>(a, M_, pairs, threads, smem, stream_, dp); break;
+    default: launch_batch_model<ModelUCSV>(a, M_, pairs, threads, smem, stream_, dp); break;
   }
   ++launches_;
 }

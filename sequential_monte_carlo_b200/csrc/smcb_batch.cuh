@@ -110,6 +110,7 @@ class BatchFilter {
   std::vector<double> host_tmp_;
   double* prop_dev_ = nullptr;  // [cap][5] proposal coefficients of the guided launches, then [cap][3] raw upload
   int64_t prop_cap_ = 0;
+  unsigned* sched_ = nullptr;   // [1 + M]: unit counter and per-θ chunk counters of the dynamically scheduled launches
 
   cudaEvent_t ev_[2] = {nullptr, nullptr};
   double last_ms_ = 0;

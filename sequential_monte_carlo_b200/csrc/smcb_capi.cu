@@ -267,8 +267,8 @@ int smcb_guided_log_likelihood(smcb_ctx* ctx, int kind, const double* params, in
   if (!ctx) return SMCB_ERR_BAD_ARG;
   return guarded(ctx, [&] {
     need(params && y && proposal && T >= 1, "guided_log_likelihood: params, y, proposal must be non-null and T >= 1");
-    if (kind != KIND_LG1D && kind != KIND_SV)
-      throw Error{SMCB_ERR_UNSUPPORTED, "guided proposals are defined for the one-dimensional models (LG1D, SV)"};
+    if (kind != KIND_LG1D && kind != KIND_SV && kind != KIND_UCSV)
+      throw Error{SMCB_ERR_UNSUPPORTED, "guided proposals are defined for LG1D, SV (docs/SPEC.md §10) and UCSV (§10b)"};
     if (resampler == RESAMPLE_MULTINOMIAL && T > 1)
       throw Error{SMCB_ERR_UNSUPPORTED, "guided single filter: stratified or systematic resampling (multinomial guided filters run on the batched engine, N <= 8192)"};
     ctx->stats.resize((size_t)T);

@@ -1618,6 +1618,55 @@ __global__ void __launch_bounds__(kMoveThreads, 4)
   }
 }
 
+// The guided move of UCSV (docs/SPEC.md §10b; guided_move_ucsv in smcb_models.cuh): one pair of particles per thread, three
+// component gathers through the sorted ancestor vector, binary64 storage, log-weights stored.
+__global__ void __launch_bounds__(kMoveThreads, 3)
+    guided_move_ucsv_kernel(Derived dv, double kappa, double y, int N, int64_t ld, RngKey key, uint32_t stream, uint32_t t, const int32_t* __restrict__ anc,
+                            const double* __restrict__ xprev, double* __restrict__ xnew, double* __restrict__ logw, FilterCtrl* ctrl) {
+  constexpr int NW = kMoveThreads / 32;
+  __shared__ unsigned long long s_max[NW];
+  const int tid = threadIdx.x;
+  ModelUCSV mdl;
+  mdl.load(dv.d);
+  const int p = blockIdx.x * kMoveThreads + tid;
+  const int i = 2 * p;
+  pdl_launch_dependents();
+  pdl_wait();  // the ancestors come from anc_hist_kernel
+  double vmax = -INFINITY;
+  if (i < N) {
+    const bool two = i + 1 < N;
+    const int a0 = anc[i], a1 = two ? anc[i + 1] : a0;
+    double xpa[3], xpb[3], za[3], zb[3], xa[3], xb[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      xpa[k] = __ldg(&xprev[k * ld + a0]);
+      xpb[k] = __ldg(&xprev[k * ld + a1]);
+      normal_pair_at(key, (uint32_t)p, stream, t, PURPOSE_TRANSITION, (uint32_t)k, za[k], zb[k]);
+    }
+    const double la = guided_move_ucsv(mdl, kappa, za, xpa, y, xa);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) xnew[k * ld + i] = xa[k];
+    logw[i] = la;
+    vmax = la;
+    if (two) {
+      const double lb = guided_move_ucsv(mdl, kappa, zb, xpb, y, xb);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) xnew[k * ld + i + 1] = xb[k];
+      logw[i + 1] = lb;
+      if (lb > vmax) vmax = lb;
+    }
+  }
+  const unsigned long long wm = warp_max_ordered(encode_ordered(vmax));
+  if ((tid & 31) == 0) s_max[tid >> 5] = wm;
+  __syncthreads();
+  if (tid == 0) {
+    unsigned long long m = s_max[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) m = s_max[w] > m ? s_max[w] : m;
+    atomicMax(&ctrl->maxslot[t & 1u], m);
+  }
+}
+
 // ================================================================================================
 // The binary32-ARITHMETIC tier (docs/SPEC.md §9b): four particles per thread = one Philox block per state component, float
 // Box-Muller / model arithmetic / log-weights, 16-byte float4 loads and stores.  Everything between the weights and the
@@ -2197,7 +2246,10 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler, cons
   ProposalCoef pc{};
   if (proposal) {  // guided step (docs/SPEC.md §10): sorted resamplers, one-dimensional models
     if (prec_ == 2) throw Error{SMCB_ERR_UNSUPPORTED, "guided proposals are not built for the binary32-arithmetic tier (docs/SPEC.md §9b)"};
-    if (d_ != 1) throw Error{SMCB_ERR_UNSUPPORTED, "guided proposals are defined for the one-dimensional models (LG1D, SV)"};
+    if (kind_ > KIND_UCSV) throw Error{SMCB_ERR_UNSUPPORTED, "guided proposals are defined for LG1D, SV (docs/SPEC.md §10) and UCSV (§10b)"};
+    if (kind_ == KIND_UCSV && prec_ != 0) throw Error{SMCB_ERR_UNSUPPORTED, "the guided UCSV move keeps binary64 states (docs/SPEC.md §10b)"};
+    if (kind_ == KIND_UCSV && !(proposal[0] >= 0.0 && proposal[0] <= 1.0))
+      throw Error{SMCB_ERR_BAD_ARG, "proposal (UCSV, docs/SPEC.md §10b): the triple is (kappa, 0, 1) with kappa in [0, 1]"};
     if (legacy_multinomial(resampler))
       throw Error{SMCB_ERR_UNSUPPORTED, "guided single filter with N <= 8192: stratified or systematic resampling (multinomial guided filters of that size run on the batched engine)"};
     if (!(proposal[2] > 0.0) || !std::isfinite(proposal[2]) || !std::isfinite(proposal[0]) || !std::isfinite(proposal[1]))
@@ -2276,7 +2328,11 @@ void SingleFilter::launch_step(int64_t stat_index, double y, int resampler, cons
   // for them, logw_kernel recompute them bit for bit).  SV / UCSV weights cost an exp: stored as before.
   const bool implicit_logw = (kind_ == KIND_LG1D) && !proposal;
   mark(TK_PROP, true);
-  if (proposal) {
+  if (proposal && kind_ == KIND_UCSV) {
+    const unsigned ublocks = (unsigned)(((N_ + 1) / 2 + kMoveThreads - 1) / kMoveThreads);
+    SMCB_CUDA_TRY(launch_pdl(guided_move_ucsv_kernel, dim3(ublocks), dim3(kMoveThreads), stream_, dv_, pc.c[0], y, (int)N_, ld_, key_, stream_id_, t,
+                             (const int32_t*)anc, (const double*)x_[cur_], (double*)x_[cur_ ^ 1], logw_[cur_ ^ 1], ctrl_));
+  } else if (proposal) {
     dispatch_xt(prec_, [&](auto tag) {
       using XT = decltype(tag);
       if (kind_ == KIND_LG1D)

@@ -240,6 +240,11 @@ struct TransDensity<ModelSV> {
   SMCB_HD double mean(const ModelSV& m, double xp) const { return fma(m.rho, xp - m.mu, m.mu); }
 };
 
+template <>
+struct TransDensity<ModelUCSV> {  // (the UCSV move of SPEC §10b derives its densities from the state: nothing per θ)
+  SMCB_HD void load(const double*) {}
+};
+
 constexpr int kProposalStride = 5;  // c0, c1, c2, det_log(c2), 1 / c2: the proposal x' ~ N(c0 + c1 xp, c2^2) of one (t, θ)
 
 struct ProposalCoef {  // by-value kernel argument of the grid-wide guided step
@@ -265,6 +270,25 @@ SMCB_HD double guided_move(const Model& mdl, const TransDensity<Model>& f, const
   const double mq = fma(pc[1], xp, pc[0]);
   x[0] = fma(pc[2], z, mq);
   return mdl.logweight(x, y) + guided_correction(mdl, f, pc, mq, xp, x[0]);
+}
+
+// UCSV (docs/SPEC.md §10b): the log-volatilities move by the transition, the trend by the conditionally optimal Gaussian move
+// tempered by κ in [0, 1]: with σε = exp(le/2) of the PARENT (state_space_models.jl:238) and ση'² = exp(ln') of the NEW state (:246),
+// r = σε²/ση'², g = κ r/(1 + r): x' ~ N(x + g (y − x), (1 − g) σε²).  κ = 0 is the bootstrap move, κ = 1 p(x' | x, le, ln', y).
+// logw = logpdf(observation(x'), y) + logpdf(transition(xp), x') − logpdf(proposal(xp), x')   (particles.jl:73-78)
+SMCB_HD double guided_move_ucsv(const ModelUCSV& mdl, double kappa, const double* z, const double* xp, double y, double* x) {
+  x[1] = fma(mdl.ge, z[1], xp[1]);
+  x[2] = fma(mdl.gn, z[2], xp[2]);
+  const double sd = det_exp(0.5 * xp[1]);
+  const double r = (sd * sd) * det_exp(-x[2]);
+  const double g = kappa * (r / (1.0 + r));
+  const double omg = 1.0 - g;
+  const double mq = fma(g, y - xp[0], xp[0]);
+  const double c2 = sd * sqrt(omg);
+  x[0] = fma(c2, z[0], mq);
+  const double zt = (x[0] - xp[0]) / sd;
+  const double corr = fma(-0.5 * zt, zt, 0.5 * (z[0] * z[0])) + 0.5 * det_log(omg);
+  return mdl.logweight(x, y) + corr;
 }
 
 }  // namespace smcb

@@ -149,6 +149,23 @@ def locally_optimal_proposal(model, y):
     return s2 * B * float(y) / R, s2 * A / Q, float(np.sqrt(s2))
 
 
+class UCSVTrendProposal:
+    """The guided move of the UCSV model (docs/SPEC.md §10b): the two log-volatilities move by the transition and the trend by
+    the conditionally optimal Gaussian move, tempered by κ in [0, 1] — x' ~ N(x + g·(y − x), (1 − g)·σε²) with
+    g = κ·σε²/(σε² + ση'²), σε = exp(le/2) of the parent, ση'² = exp(ln') of the new state.  κ = 0 is the bootstrap move,
+    κ = 1 is p(x' | x, le, ln', y), after which the weight no longer depends on x'.  Use as
+    `particle_filter_(x, w, y, model, UCSVTrendProposal(1.0))`."""
+
+    def __init__(self, kappa=1.0):
+        if not 0.0 <= float(kappa) <= 1.0:
+            raise ValueError("kappa must lie in [0, 1]")
+        self.kappa = float(kappa)
+
+    def __call__(self, model, y):
+        return self.kappa, 0.0, 1.0
+
+
+_GUIDED_KINDS = (_lib.LG1D, _lib.SV, _lib.UCSV)
 _GUIDED_BATCH_MAX = 8192   # guided filters up to this size run on the batched engine (any resampler), larger ones on the single filter
 
 
@@ -186,6 +203,15 @@ class _GuidedCloud:
         return (self._batch.N,) if self._which == "w" or self._batch.d == 1 else (self._batch.N, self._batch.d)
 
 
+def _check_family(model, proposal):
+    """the device evaluates one proposal family per model: affine-Gaussian for the one-dimensional models (docs/SPEC.md §10), the
+    tempered optimal trend move for UCSV (§10b); anything else is refused, never run as a bootstrap filter"""
+    if model.kind not in _GUIDED_KINDS:
+        raise NotImplementedError("guided proposals are built for LinearModel, StochasticVolatility (affine-Gaussian) and UCSV (UCSVTrendProposal)")
+    if (model.kind == _lib.UCSV) != isinstance(proposal, UCSVTrendProposal):
+        raise NotImplementedError("UCSV takes a UCSVTrendProposal (docs/SPEC.md §10b); the one-dimensional models take the affine-Gaussian family (§10)")
+
+
 def _proposal_coefficients(proposal, model, y):
     c = proposal(model, y) if callable(proposal) else proposal
     c = np.asarray(c, np.float64).ravel()
@@ -205,8 +231,7 @@ def particle_filter(N, y, model, proposal=None, *, ctx=None, stream=0):
     if proposal is None:
         return bootstrap_filter(N, y, model, ctx=ctx, stream=stream)
     ctx = ctx or default_context()
-    if model.kind not in (_lib.LG1D, _lib.SV):
-        raise NotImplementedError("guided proposals are built for the one-dimensional models (LinearModel, StochasticVolatility)")
+    _check_family(model, proposal)
     if int(N) > _GUIDED_BATCH_MAX:      # large clouds: the grid-wide single filter (guided steps need a sorted resampler there)
         return bootstrap_filter(N, y, model, ctx=ctx, stream=stream)
     b = ctx.batch(model.kind, 1, int(N))
@@ -227,6 +252,8 @@ def particle_filter_(states, weights, y, model, proposal=None, *, resampler="mul
             b._t += 1
             return float(lm[0]), _GuidedCloud(b, "w"), float(es[0])
         return bootstrap_filter_(states, weights, y, model, resampler=resampler)
+    if isinstance(states, (_DeviceArray, _GuidedCloud)):
+        _check_family(model, proposal)
     c = _proposal_coefficients(proposal, model, y)
     if isinstance(states, _DeviceArray):   # the large-N single filter: guided move kernel of the grid-wide path
         ctx = states._ctx
@@ -247,8 +274,7 @@ def guided_log_likelihood(N, y, model, proposal, *, resampler="multinomial", ctx
     examples/inflation_example.jl:164-171 with a proposal): bootstrap initial step, guided steps for t >= 2."""
     ctx = ctx or default_context()
     y = np.asarray(y, np.float64)
-    if model.kind not in (_lib.LG1D, _lib.SV):
-        raise NotImplementedError("guided proposals are built for the one-dimensional models (LinearModel, StochasticVolatility)")
+    _check_family(model, proposal)
     prop = np.stack([_proposal_coefficients(proposal, model, yt) for yt in y]).reshape(y.size, 1, 3)
     if int(N) > _GUIDED_BATCH_MAX:
         logZ = ctx.guided_log_likelihood(model.kind, model.params(), int(N), y, prop.reshape(-1, 3), resampler_id(resampler), stream)

@@ -597,6 +597,7 @@ def density_tempered(smc, y, verbose=True):
         smc._engine_data(y)
         stages = smc._eng.density_tempered()
         smc.schedule = [(ξ, ess) for ξ, ess, _ in stages]
+        smc.acceptance = [ar for _, _, ar in stages if ar >= 0.0]     # acc_rate of every rejuvenation, as the reference prints it
         smc._stale = True
         smc._refresh()
         if verbose:                                                     # the trace format of smc_samplers.jl:207-214
@@ -610,7 +611,7 @@ def density_tempered(smc, y, verbose=True):
     smc.logZ = smc.comm.all_gather(z_loc)
     _, smc.ω, smc.ess = smc.ctx.normalize(smc.logZ)                    # :232
     ξ = 0.0
-    smc.schedule = []
+    smc.schedule, smc.acceptance = [], []
     while ξ < 1.0:
         resample_flag = True
         lower = oldξ = ξ
@@ -638,6 +639,7 @@ def density_tempered(smc, y, verbose=True):
         if resample_flag:
             resample_(smc)                                              # :272
             rejuvenate_(smc, y, ξ, verbose)                             # :275
+            smc.acceptance.append(smc.acc_ratio)
         if verbose:
             sys.stdout.write("\n")
     return smc

@@ -73,8 +73,6 @@ def test_oracle_guided_optimal_proposal_targets_kalman(oracle):
     assert g.std() < 0.5 * b.std()
     lme = np.log(np.mean(np.exp(g - g.max()))) + g.max()          # log-mean-exp of the unbiased estimates
     assert abs(lme - kll) < 4 * g.std() / np.sqrt(g.size) + 0.02
-    with pytest.raises(ValueError):
-        oracle.guided_step(oracle.KIND_UCSV, [0.2, 0.2, 3, 1, 1], np.zeros((3, 8)), np.zeros(8), 0.0, 1, 0, [0, 1, 1], 1)
 
 
 def test_oracle_guided_step_against_a_numpy_restatement(oracle):
@@ -147,7 +145,102 @@ def test_host_mirror_of_the_new_models_and_proposals():
     assert smc.AffineGaussianProposal(1, 2, 3)(lg, 9.0) == (1.0, 2.0, 3.0)
 
 
+UCSVP = [0.2, 0.2, 3.0, 1.0, 1.0]
+
+
+def test_oracle_guided_ucsv_move(oracle):
+    """SPEC §10b: κ = 0 IS the bootstrap filter (same states; the weight correction −½zt² + ½z² vanishes to rounding), κ = 1 is
+    the conditionally optimal trend move: logZ estimates the same likelihood with a much smaller scatter"""
+    N, T = 512, 60
+    _, y = oracle.simulate(2, UCSVP, T, 5)
+    z0, z1, zb = [], [], []
+    for seed in range(24):
+        b = oracle.log_likelihood(2, UCSVP, N, y, oracle.SYSTEMATIC, seed, 0, 0)
+        g0 = oracle.guided_log_likelihood(2, UCSVP, N, y, oracle.SYSTEMATIC, np.tile([0.0, 0.0, 1.0], (T, 1)), seed)
+        g1 = oracle.guided_log_likelihood(2, UCSVP, N, y, oracle.SYSTEMATIC, np.tile([1.0, 0.0, 1.0], (T, 1)), seed)
+        if seed == 0:
+            np.testing.assert_array_equal(g0["x"], b["x"])
+            np.testing.assert_allclose(g0["logw"], b["logw"], rtol=0, atol=1e-12)
+            assert g1["x"].shape == (3, N) and np.all(np.isfinite(g1["logw"]))
+        zb.append(b["logZ"]); z0.append(g0["logZ"]); z1.append(g1["logZ"])
+    np.testing.assert_allclose(z0, zb, rtol=1e-12)
+    assert np.std(z1) < 0.6 * np.std(zb)
+    lme = lambda z: np.log(np.mean(np.exp(np.array(z) - np.max(z)))) + np.max(z)      # noqa: E731
+    assert abs(lme(z1) - lme(zb)) < 3 * np.std(zb) / np.sqrt(24) + 0.1
+
+
 # ------------------------------------------------------------------------------------------------ GPU: parity
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [1024, 777, 4096, 6])
+def test_guided_ucsv_batch_bit_exact(ctx, oracle, N):
+    """the tempered optimal trend move of UCSV (SPEC §10b) in the batched engine (clouds in shared memory, and in global memory at
+    N = 4096), κ per (t, θ): clouds and log-weights bit-exact against the oracle, logZ to 1e-10"""
+    M, T = 5, 12 if N <= 1024 else 5
+    rng = np.random.default_rng(N)
+    _, y = oracle.simulate(2, UCSVP, T, 1998)
+    th = np.stack([rng.uniform(0.1, 0.4, M), rng.uniform(0.1, 0.4, M), rng.normal(3, 0.3, M), rng.normal(1, 0.2, M), rng.normal(1, 0.2, M)], 1)
+    P = smc._lib.params8(th)
+    prop = np.zeros((T, M, 3))
+    prop[:, :, 0] = rng.uniform(0, 1, (T, M))
+    prop[:, 0, 0], prop[:, 1, 0] = 1.0, 0.0
+    prop[:, :, 2] = 1.0
+    active = np.ones(M, np.uint8)
+    active[3] = 0
+    for resampler in (smc.MULTINOMIAL, smc.STRATIFIED, smc.SYSTEMATIC):
+        seed, epoch, stream0 = 78, 3 + resampler, 41
+        zo, xo, lwo = oracle.batch_guided_log_likelihood(2, P, active, N, y, resampler, prop, seed, epoch, stream0)
+        b = ctx.batch(smc.KIND_UCSV, M, N)
+        ctx.set_rng(seed, epoch)
+        z = b.log_likelihood(P, y, resampler, stream0, active, proposal=prop)
+        x, _, lw = b.fetch(want_w=False, want_logw=True)
+        on = active.astype(bool)
+        assert np.all(np.isneginf(z[~on]))
+        np.testing.assert_array_equal(x[on], xo[on])
+        np.testing.assert_array_equal(lw[on], lwo[on])
+        np.testing.assert_allclose(z[on], zo[on], rtol=RTOL, atol=0)
+        b.close()
+    b = ctx.batch(smc.KIND_UCSV, M, N)
+    bad = prop.copy()
+    bad[1, 2, 0] = 1.2
+    with pytest.raises(smc.SMCBError):
+        b.log_likelihood(P, y, smc.SYSTEMATIC, 0, proposal=bad)
+    b.close()
+
+
+@pytest.mark.gpu
+def test_guided_ucsv_single_filter_and_python_mirror(ctx, oracle):
+    """the same move on the grid-wide path (guided_move_ucsv_kernel) for one large cloud, whole series and stepping API, and through
+    particle_filter / particle_filter! with UCSVTrendProposal (small cloud: batched engine; large: single filter)"""
+    N, T = 20011, 10
+    _, y = oracle.simulate(2, UCSVP, T, 3)
+    prop = np.tile([1.0, 0.0, 1.0], (T, 1))
+    prop[::2, 0] = 0.6
+    for resampler in (smc.STRATIFIED, smc.SYSTEMATIC):
+        seed, epoch, stream = 32, 2 + resampler, 8
+        ref = oracle.guided_log_likelihood(2, UCSVP, N, y, resampler, prop, seed, epoch, stream)
+        ctx.set_rng(seed, epoch)
+        z, lm, es = ctx.guided_log_likelihood(smc.KIND_UCSV, UCSVP, N, y, prop, resampler, stream, per_step=True)
+        x, _, lw = ctx.fetch_state(want_w=False, want_logw=True)
+        np.testing.assert_array_equal(x, ref["x"])
+        np.testing.assert_array_equal(lw, ref["logw"])
+        np.testing.assert_allclose(lm, ref["logmu"], rtol=RTOL, atol=0)
+        assert abs(z - ref["logZ"]) <= RTOL * abs(ref["logZ"])
+    ucsv = smc.UCSV((UCSVP[0], UCSVP[1]), UCSVP[2], (UCSVP[3], UCSVP[4]))
+    for n in (1500, 30000):
+        ctx.set_rng(13, 5)
+        xs, w, logmu = smc.particle_filter(n, y[0], ucsv, smc.UCSVTrendProposal(1.0), ctx=ctx, stream=6)
+        xo, lwo = oracle.bootstrap_init(2, UCSVP, n, y[0], 13, 5, 6)
+        for t in range(1, 6):
+            logmu, w, ess = smc.particle_filter_(xs, w, y[t], ucsv, smc.UCSVTrendProposal(1.0), resampler="systematic")
+            oracle.guided_step(2, UCSVP, xo, lwo, y[t], t, oracle.SYSTEMATIC, [1.0, 0.0, 1.0], 13, 5, 6)
+            lmo, wo, esso = oracle.normalize(lwo)
+            assert abs(logmu - lmo) <= RTOL * abs(lmo) and abs(ess - esso) <= 1e-9 * esso
+        np.testing.assert_array_equal(np.asarray(xs), xo.T)
+        np.testing.assert_allclose(np.asarray(w), wo, rtol=RTOL)
+    with pytest.raises(ValueError):
+        smc.UCSVTrendProposal(1.5)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind,N", [(smc.KIND_LG1D, 1024), (smc.KIND_LG1D, 777), (smc.KIND_SV, 2048), (smc.KIND_LG1D, 8192), (smc.KIND_SV, 5)])
 def test_guided_batch_bit_exact(ctx, oracle, kind, N):
@@ -281,12 +374,12 @@ def test_guided_single_filter_bit_exact(ctx, oracle, kind, N, f32):
 
 @pytest.mark.gpu
 def test_guided_single_filter_errors_and_python_mirror(ctx, oracle):
-    """UCSV and multinomial resampling are refused on the grid-wide guided path; particle_filter / particle_filter! route
+    """bad coefficients and multinomial resampling are refused on the grid-wide guided path; particle_filter / particle_filter! route
     clouds above 8192 particles to it"""
     _, y = oracle.simulate(0, LG, 6, 3)
     ctx.bootstrap_init(smc.KIND_UCSV, [0.2, 0.2, 3.0, 1.0, 1.0], 4096, 1.0)
     with pytest.raises(smc.SMCBError):
-        ctx.guided_step(1.0, [0.0, 1.0, 1.0], smc.SYSTEMATIC)
+        ctx.guided_step(1.0, [1.5, 0.0, 1.0], smc.SYSTEMATIC)      # UCSV (SPEC §10b): κ outside [0, 1]
     ctx.bootstrap_init(smc.KIND_LG1D, LG, 4096, y[0])
     with pytest.raises(smc.SMCBError):
         ctx.guided_step(y[1], [0.0, 1.0, 1.0], smc.MULTINOMIAL)
