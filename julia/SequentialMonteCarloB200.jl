@@ -12,7 +12,7 @@
 #     the whole θ level runs on the GPU(s) behind smcb_sampler_*; comm_init! shards θ over one process per GPU)
 #   IBIS + smc², smc²!                                                            src/ibis.jl
 #   kalman_filter, log_likelihood(y, model)  (scalar and matrix methods)          src/kalman_filter.jl
-#   particle_filter, particle_filter!  (guided: affine-Gaussian proposals, docs/SPEC.md §10)   src/particles.jl:28-84
+#   particle_filter, particle_filter!  (guided: affine-Gaussian proposals, docs/SPEC.md §10; UCSV trend move, §10b)   src/particles.jl:28-84
 #   MultivariateLinearGaussian, hodrick_prescott  (Kalman filter only)            src/state_space_models.jl:137-202
 module SequentialMonteCarloB200
 
@@ -21,7 +21,7 @@ using Distributions, LinearAlgebra, Printf, Statistics
 export StateSpaceModel, LinearModel, UnivariateLinearGaussian, LinearGaussian, unobserved_components, UC, UCSV,
        StochasticVolatility, simulate, transition, observation, initial_dist, normalize, resample, bootstrap_filter, bootstrap_filter!, log_likelihood,
        SMC, IBIS, smc², smc²!, density_tempered, expected_parameters, kalman_filter, comm_unique_id, comm_init!,
-       particle_filter, particle_filter!, AffineGaussianProposal, locally_optimal_proposal,
+       particle_filter, particle_filter!, AffineGaussianProposal, UCSVTrendProposal, locally_optimal_proposal,
        MultivariateLinearModel, MultivariateLinearGaussian, hodrick_prescott, state_variances
 
 const LIB = get(ENV, "SMCB200_LIB", joinpath(@__DIR__, "..", "sequential_monte_carlo_b200", "lib", "libsmcb200.so"))
@@ -316,15 +316,23 @@ struct AffineGaussianProposal
     c0::Float64; c1::Float64; c2::Float64
 end
 (q::AffineGaussianProposal)(model, y) = (q.c0, q.c1, q.c2)
+# UCSV (docs/SPEC.md §10b): the log-volatilities move by the transition, the trend by the conditionally optimal Gaussian move
+# tempered by κ in [0, 1] (0 = bootstrap, 1 = p(x' | x, le, ln', y)); the device takes the triple (κ, 0, 1)
+struct UCSVTrendProposal
+    κ::Float64
+    UCSVTrendProposal(κ=1.0) = (0.0 <= κ <= 1.0 || error("κ must lie in [0, 1]"); new(κ))
+end
+(q::UCSVTrendProposal)(model, y) = (q.κ, 0.0, 1.0)
 function locally_optimal_proposal(model::LinearModel, y::Float64)      # p(x' | xp, y) of a univariate LinearModel
     s2 = 1 / (1 / model.Q + model.B^2 / model.R)
     (s2 * model.B * y / model.R, s2 * model.A / model.Q, sqrt(s2))
 end
 mutable struct GuidedCloud                        # a guided filter is a batch of one θ (N <= 8192)
-    b::Batch; N::Int64
+    b::Batch; N::Int64; d::Int64                  # d state components (UCSV: 3), fetched as [d][N]
 end
-Base.collect(c::GuidedCloud) = (a = Vector{Float64}(undef, c.N);
-    check(c.b.ctx, ccall((:smcb_batch_fetch, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), c.b.h, a, C_NULL, C_NULL)); a)
+Base.collect(c::GuidedCloud) = (a = Vector{Float64}(undef, c.d * c.N);
+    check(c.b.ctx, ccall((:smcb_batch_fetch, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), c.b.h, a, C_NULL, C_NULL));
+    c.d == 1 ? a : [a[(k - 1) * c.N + i] for i in 1:c.N, k in 1:c.d])
 weights(c::GuidedCloud) = (a = Vector{Float64}(undef, c.N);
     check(c.b.ctx, ccall((:smcb_batch_fetch, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), c.b.h, C_NULL, a, C_NULL)); a)
 particle_filter(N::Int64, y::Float64, model::StateSpaceModel, ::Nothing; ctx=context()) = bootstrap_filter(N, y, model; ctx=ctx)   # :28-51
@@ -333,7 +341,7 @@ function particle_filter(N::Int64, y::Float64, model::StateSpaceModel, proposal;
     b = Batch(ctx, kind(model), 1, N); lm = [0.0]; es = [0.0]
     check(ctx, ccall((:smcb_batch_init, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{UInt8}, Float64, UInt32, Ptr{Float64}, Ptr{Float64}),
                      b.h, params8(model), C_NULL, y, 0, lm, es))
-    x = GuidedCloud(b, N)
+    x = GuidedCloud(b, N, kind(model) == 2 ? 3 : 1)
     return x, weights(x), lm[1]
 end
 particle_filter!(states::Cloud, w::Vector{Float64}, y::Float64, model::StateSpaceModel, ::Nothing; resampler=MULTINOMIAL) =

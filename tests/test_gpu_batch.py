@@ -212,3 +212,56 @@ def test_batch_weighted_quantiles(ctx, oracle):
     with pytest.raises(smc.SMCBError):
         b.weighted_quantiles(np.linspace(0, 1, 17))
     b.close()
+
+
+@pytest.mark.parametrize("kind,N,M", [(smc.KIND_LG1D, 1024, 333), (smc.KIND_UCSV, 4096, 170), (smc.KIND_SV, 2048, 301), (smc.KIND_UCSV, 640, 200)])
+def test_dynamic_chunk_scheduling_is_bit_identical(ctx, oracle, kind, N, M, monkeypatch):
+    """the persistent-grid launch that claims (chunk, θ) units dynamically (smcb_batch.cu, DYN kernels) carries the cloud, the
+    statistics and the running Σ logμ through global memory between chunks: logZ, states and log-weights have to be the bits of
+    the one-CTA-per-θ launch — forced chunk lengths (ragged last chunk, chunk = 1), the automatic choice, some θ inactive,
+    all three resamplers, and the oracle on a few θ"""
+    T = 29
+    rng = np.random.default_rng(N + M)
+    _, y = oracle.simulate(kind, TRUE[kind], T, 1998)
+    P = smc._lib.params8(_thetas(kind, M, rng))
+    active = np.ones(M, np.uint8)
+    active[rng.integers(0, M, 9)] = 0
+    b = ctx.batch(kind, M, N)
+    for resampler in (smc.MULTINOMIAL, smc.STRATIFIED, smc.SYSTEMATIC):
+        out = {}
+        for chunk in ("0", "1", "5", "8", None):
+            if chunk is None:
+                monkeypatch.delenv("SMCB_BATCH_CHUNK", raising=False)
+            else:
+                monkeypatch.setenv("SMCB_BATCH_CHUNK", chunk)
+            ctx.set_rng(9, 20 + resampler)
+            z = b.log_likelihood(P, y, resampler, 7, active)
+            x, _, lw = b.fetch(want_w=False, want_logw=True)
+            out[chunk] = (z.copy(), x.copy(), lw.copy())
+        on = active.astype(bool)
+        for chunk in ("1", "5", "8", None):
+            for ref, got in zip(out["0"], out[chunk]):
+                np.testing.assert_array_equal(got[on], ref[on])
+            assert np.all(np.isneginf(out[chunk][0][~on]))
+        sel = np.flatnonzero(on)[[0, len(np.flatnonzero(on)) // 2, -1]]
+        for m in sel:                                        # (the oracle numbers its streams from stream0 by position)
+            zo1, xo1, lwo1 = oracle.batch_log_likelihood(kind, P[m:m + 1], None, N, y, resampler, 9, 20 + resampler, 7 + int(m))
+            np.testing.assert_array_equal(out["5"][1][m], xo1[0])
+            np.testing.assert_array_equal(out["5"][2][m], lwo1[0])
+            assert abs(out["5"][0][m] - zo1[0]) <= RTOL * abs(zo1[0])
+    monkeypatch.delenv("SMCB_BATCH_CHUNK", raising=False)
+    # the stepping calls after a chunked sweep continue from its stored state
+    ctx.set_rng(9, 31)
+    monkeypatch.setenv("SMCB_BATCH_CHUNK", "4")
+    b.log_likelihood(P, y[:20], smc.SYSTEMATIC, 7)
+    monkeypatch.delenv("SMCB_BATCH_CHUNK", raising=False)
+    lm1, _ = b.step(float(y[20]), smc.SYSTEMATIC)
+    x1, _, _ = b.fetch(want_w=False)
+    ctx.set_rng(9, 31)
+    monkeypatch.setenv("SMCB_BATCH_CHUNK", "0")
+    b.log_likelihood(P, y[:20], smc.SYSTEMATIC, 7)
+    lm0, _ = b.step(float(y[20]), smc.SYSTEMATIC)
+    x0, _, _ = b.fetch(want_w=False)
+    np.testing.assert_array_equal(x1, x0)
+    np.testing.assert_array_equal(lm1, lm0)
+    b.close()
