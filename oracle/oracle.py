@@ -17,7 +17,6 @@ KIND_LG1D, KIND_SV, KIND_UCSV = 0, 1, 2
 MULTINOMIAL, STRATIFIED, SYSTEMATIC = 0, 1, 2
 P_INIT, P_TRANS, P_RESAMPLE, P_PRIOR, P_THETA_RESAMPLE, P_MH_PROPOSAL, P_MH_ACCEPT, P_SIMULATE = 1, 2, 3, 4, 5, 6, 7, 8
 P_RESAMPLE_CELL = 9   # in-cell thresholds of the two-level multinomial resampler (docs/SPEC.md §5c)
-P_RESAMPLE_CLOSE = 10  # the closing exponential spacing of a cell (docs/SPEC.md §5c level 2)
 MN_CELL, MN_CHUNK, MN_LEGACY_MAX = 4096, 8192, 8192
 
 _dp = np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")
@@ -193,18 +192,6 @@ def ancestors_numpy(logw, resampler, seed, epoch, stream, t):
             base = int(cellC[c - 1]) if c else 0
             W = int(cellC[c]) - base
             loc = Cs[j0:j1] - np.uint64(base)
-            Kc = int(K[c])
-            if 0 < Kc <= MN_CHUNK - 4:
-                # sorted thresholds from normalised cumulative exponential spacings (integer sums, one reciprocal per cell)
-                u = np.array(V[O:O + Kc] + [int(uniforms32(seed, epoch, stream, t, P_RESAMPLE_CLOSE, c + 1)[c])], dtype=np.uint64)
-                e = (-det_log((2 * u + 1).astype(np.float64) * 2.0 ** -33) * 2.0 ** 26).astype(np.uint64)
-                Sj = np.cumsum(e[:-1], dtype=np.uint64)
-                Stot = int(Sj[-1]) + int(e[-1]) + 1
-                r = 1.0 / float(Stot)
-                tau2 = np.minimum(((Sj.astype(np.float64) * r) * float(W)).astype(np.uint64), np.uint64(W - 1))
-                out[O:O + Kc] = j0 + np.searchsorted(loc, tau2, side="right")
-                O += Kc
-                continue
             for g0 in range(O, O + int(K[c]), MN_CHUNK):
                 g1 = min(g0 + MN_CHUNK, O + int(K[c]))
                 tau2 = np.array([(V[g] * W) >> 32 for g in range(g0, g1)], dtype=np.uint64)

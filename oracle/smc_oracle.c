@@ -33,7 +33,7 @@
 enum { KIND_LG1D = 0, KIND_SV = 1, KIND_UCSV = 2 };
 enum { RS_MULTINOMIAL = 0, RS_STRATIFIED = 1, RS_SYSTEMATIC = 2 };
 static int g_arith_f32 = 0;   /* SPEC §9b tier switch (set by smco_set_arith_f32 below) */
-enum { P_INIT = 1, P_TRANS = 2, P_RESAMPLE = 3, P_SIMULATE = 8, P_RESAMPLE_CELL = 9, P_RESAMPLE_CLOSE = 10 };
+enum { P_INIT = 1, P_TRANS = 2, P_RESAMPLE = 3, P_SIMULATE = 8, P_RESAMPLE_CELL = 9 };
 
 int smco_state_dim(int kind) { return kind >= 3 ? kind - 1 : (kind == KIND_UCSV ? 3 : 1); }   /* kinds 3..5: multivariate LG, d = 2..4 */
 
@@ -240,12 +240,6 @@ static uint32_t o_uniform32(uint64_t seed, uint32_t epoch, uint32_t i, uint32_t 
   return r[i & 3];
 }
 static uint64_t o_mul32(uint32_t u, uint64_t v) { return (uint64_t)(((unsigned __int128)u * v) >> 32); }
-/* exponential spacing of SPEC §5c level 2: E = trunc(-log((2u + 1) 2^-33) 2^26)  (0 <= E < 2^31) */
-static uint64_t o_expo32(uint32_t u) {
-  double x = (double)(2 * (uint64_t)u + 1) * 0x1p-33;
-  return (uint64_t)(-o_log(x) * 0x1p26);
-}
-#define MN_SORTED_MAX (MN_CHUNK - 4)   /* cells with at most this many outputs draw their thresholds already sorted */
 static int cmp_i64(const void *a, const void *b) {
   int64_t x = *(const int64_t *)a, y = *(const int64_t *)b;
   return (x > y) - (x < y);
@@ -279,25 +273,6 @@ static void ancestors_two_level(const uint64_t *q, int64_t n, uint64_t seed, uin
   for (int64_t c = 0; c < ncells; ++c) {                 /* level 2 */
     int64_t j0 = c * MN_CELL, len = (n - j0 < MN_CELL) ? n - j0 : MN_CELL;
     uint64_t base = c ? cellC[c - 1] : 0, W = cellC[c] - base;
-    if (K[c] > 0 && K[c] <= MN_SORTED_MAX) {
-      /* the K_c in-cell thresholds, i.i.d. uniform on [0, W), drawn SORTED: normalised cumulative exponential spacings
-       * U_(j) = S_j / S_{K+1}, S_j = E_1 + .. + E_j (integers: exact in any order) */
-      uint64_t S = 0, *Sj = (uint64_t *)malloc(sizeof(uint64_t) * (size_t)K[c]);
-      for (int64_t j = 0; j < K[c]; ++j) {
-        S += o_expo32(o_uniform32(seed, epoch, (uint32_t)(O + j), stream, t, P_RESAMPLE_CELL));
-        Sj[j] = S;
-      }
-      uint64_t Stot = S + o_expo32(o_uniform32(seed, epoch, (uint32_t)c, stream, t, P_RESAMPLE_CLOSE)) + 1;
-      double r = 1.0 / (double)Stot, Wd = (double)W;
-      for (int64_t j = 0; j < K[c]; ++j) {
-        uint64_t tau = (uint64_t)(((double)Sj[j] * r) * Wd);
-        if (tau > W - 1) tau = W - 1;
-        int64_t lo = 0, hi = len;                        /* #{ j in cell : C_j - base <= tau } */
-        while (lo < hi) { int64_t mid = (lo + hi) >> 1; if (C[j0 + mid] - base <= tau) lo = mid + 1; else hi = mid; }
-        anc[O + j] = j0 + lo;
-      }
-      free(Sj);
-    } else
     for (int64_t g0 = O; g0 < O + K[c]; g0 += MN_CHUNK) {
       int64_t g1 = (g0 + MN_CHUNK < O + K[c]) ? g0 + MN_CHUNK : O + K[c];
       for (int64_t g = g0; g < g1; ++g) {

@@ -96,7 +96,6 @@ enum : uint32_t {
   PURPOSE_MH_ACCEPT = 7,
   PURPOSE_SIMULATE = 8,
   PURPOSE_RESAMPLE_CELL = 9,  // in-cell thresholds of the two-level multinomial resampler (SPEC §5c)
-  PURPOSE_RESAMPLE_CLOSE = 10,  // the closing exponential spacing of a cell (SPEC §5c level 2)
 };
 
 struct RngKey {

@@ -1081,13 +1081,6 @@ __device__ __forceinline__ uint64_t mulhi32_64(uint32_t u, uint64_t v) {
   return (uint64_t)u * (v >> 32) + (((uint64_t)u * (v & 0xFFFFFFFFull)) >> 32);
 }
 
-// exponential spacing of SPEC §5c level 2: E = trunc(-log((2u + 1) 2^-33) 2^26), 0 <= E < 2^31
-__device__ __forceinline__ uint32_t mn_expo32(uint32_t u) {
-  const double x = (double)(2ull * (unsigned long long)u + 1ull) * 0x1p-33;
-  return (uint32_t)__double2ull_rz(-det_log(x) * 0x1p26);
-}
-constexpr int kMnSortedMax = kMnChunk - 4;  // cells with at most this many outputs draw their thresholds already sorted
-
 // number of low bits dropped so that (v >> shift) < 2^bits for every v <= vmax
 __device__ __forceinline__ int mn_shift(unsigned long long vmax, int bits) {
   const int len = 64 - __clzll((long long)(vmax | 1ull));
@@ -1318,88 +1311,6 @@ __global__ void __launch_bounds__(kMnCellThreads, 3)
     reinterpret_cast<int4*>(s_hist)[2 * tid + 1] = make_int4(0, 0, 0, 0);
   }
   __syncthreads();
-  if (Kc <= kMnSortedMax) {
-    // ---- the usual case (SPEC §5c level 2): the K_c thresholds of the cell are drawn SORTED, as normalised cumulative exponential
-    // spacings U_(j) = S_j / S_{K+1} — one Philox word and one log per output, an integer block scan, and a merge with the CDF in
-    // shared memory: no lookup table, no atomics, no second scan.  Thread `tid` owns the 16 output positions 4 (pa + 4 tid) ..
-    // + 15 (four whole Philox blocks, pa = g0 >> 2), of which those inside [g0, g1) exist.
-    constexpr int OUT = 16;
-    __shared__ unsigned long long s_ws[NW];
-    __shared__ unsigned long long s_close;
-    const int gbase = 4 * ((g0 >> 2) + 4 * tid);
-    uint32_t E[OUT];
-    unsigned long long tot = 0;
-#pragma unroll
-    for (int q = 0; q < OUT / 4; ++q) {
-      const int p = (gbase >> 2) + q;
-      uint32_t v4[4] = {0u, 0u, 0u, 0u};
-      if (4 * p < g1) {
-        const Philox4 blk = philox4x32_10((uint32_t)p, stream, t, purpose_word(PURPOSE_RESAMPLE_CELL, 0, key.epoch), key);
-        v4[0] = blk.r0; v4[1] = blk.r1; v4[2] = blk.r2; v4[3] = blk.r3;
-      }
-#pragma unroll
-      for (int h = 0; h < 4; ++h) {
-        const int g = 4 * p + h;
-        E[4 * q + h] = (g >= g0 && g < g1) ? mn_expo32(v4[h]) : 0u;
-        tot += E[4 * q + h];
-      }
-    }
-    if (tid == 0) {
-      const Philox4 blk = philox4x32_10((uint32_t)c >> 2, stream, t, purpose_word(PURPOSE_RESAMPLE_CLOSE, 0, key.epoch), key);
-      const uint32_t w4[4] = {blk.r0, blk.r1, blk.r2, blk.r3};
-      s_close = (unsigned long long)mn_expo32(w4[c & 3]) + 1ull;
-    }
-    const unsigned long long winc = warp_scan_u64(tot, lane);
-    if (lane == 31) s_ws[warp] = winc;
-    __syncthreads();
-    unsigned long long S = winc - tot, Stot = s_close;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) {
-      const unsigned long long v = s_ws[w];
-      if (w < warp) S += v;
-      Stot += v;
-    }
-    const double rinv = 1.0 / (double)Stot, Wd = (double)W;
-    int j = -1;  // ancestors found so far lie at or before j; -1: this thread has not searched yet
-    int outv[OUT];
-#pragma unroll
-    for (int k = 0; k < OUT; ++k) {
-      const int g = gbase + k;
-      outv[k] = 0;
-      if (g >= g0 && g < g1) {
-        S += E[k];
-        unsigned long long tau = __double2ull_rz(((double)S * rinv) * Wd);
-        if (tau > W - 1) tau = W - 1;
-        // #{ j' in cell : C_j' <= tau }: the first one by bisection, the next ones gallop forward from their predecessor
-        int lo, hi;
-        if (j < 0) { lo = 0; hi = len; }
-        else {
-          lo = j;
-          int step = 1, top = lo;
-          while (top < len && s_c[top] <= tau) { lo = top + 1; top = lo + step - 1; step <<= 1; if (top > len) top = len; }
-          hi = top;
-        }
-        while (lo < hi) {
-          const int mid = (lo + hi) >> 1;
-          if (s_c[mid] <= tau) lo = mid + 1;
-          else hi = mid;
-        }
-        j = lo;
-        outv[k] = j0 + j;
-      }
-    }
-    if (gbase >= g0 && gbase + OUT <= g1) {
-#pragma unroll
-      for (int q = 0; q < OUT / 4; ++q)
-        *reinterpret_cast<int4*>(anc + gbase + 4 * q) = make_int4(outv[4 * q], outv[4 * q + 1], outv[4 * q + 2], outv[4 * q + 3]);
-    } else {
-#pragma unroll
-      for (int k = 0; k < OUT; ++k)
-        if (gbase + k >= g0 && gbase + k < g1) anc[gbase + k] = outv[k];
-    }
-    return;
-  }
-  // ---- cells that drew more than kMnSortedMax outputs (very uneven weights): unsorted in-cell uniforms, counted per particle
   // ---- lookup table: lut[b] = #{ j : (C_j >> s) < b }; particle j writes the buckets (C_{j-1} >> s, C_j >> s] — about one each.
   // A particle that holds a large share of the cell's mass spans many buckets: those ranges go to a short list that the
   // whole CTA fills together, so that very uneven weights do not serialise the CTA behind one thread.

@@ -260,6 +260,30 @@ def test_oracle_regression_vectors_of_the_later_rows(oracle):
             assert [float(a).hex() for a in x] == v["x_hex"] and [float(a).hex() for a in S.ravel()] == v["S_hex"]
 
 
+def test_oracle_regression_vectors_of_round_2(oracle):
+    """two-level multinomial draw (SPEC §5c), guided UCSV move (§10b), multivariate LG particle filter (§4b): committed bit patterns"""
+    for v in json.load(open(os.path.join(GOLD, "round2_vectors.json"))):
+        if v["what"] == "two_level_multinomial":
+            _, y = oracle.simulate(v["kind"], v["params"], v["T"], v["data_seed"])
+            r = oracle.log_likelihood(v["kind"], v["params"], v["N"], y, v["resampler"], v["seed"], v["epoch"], v["stream"], want_anc=True)
+            assert float(r["logZ"]).hex() == v["logZ_hex"] and float(np.sum(r["x"])).hex() == v["x_sum_hex"]
+            assert [int(a) for a in r["anc"][1][:16]] == v["anc_t1_head"]
+            assert int(np.sum(r["anc"][1:] * (np.arange(v["N"]) + 1)) % (2 ** 61 - 1)) == v["anc_checksum"]
+        elif v["what"] == "guided_ucsv":
+            _, y = oracle.simulate(v["kind"], v["params"], v["T"], v["data_seed"])
+            kap = np.array([float.fromhex(c) for c in v["kappa_hex"]])
+            prop = np.stack([kap, np.zeros(kap.size), np.ones(kap.size)], 1)
+            r = oracle.guided_log_likelihood(v["kind"], v["params"], v["N"], y, v["resampler"], prop, v["seed"], v["epoch"], v["stream"])
+            assert float(r["logZ"]).hex() == v["logZ_hex"] and float(np.sum(r["x"])).hex() == v["x_sum_hex"]
+            assert float(np.sum(r["logw"])).hex() == v["logw_sum_hex"] and [float(a).hex() for a in r["x"][:, -1]] == v["x_last_hex"]
+        else:
+            _, y = oracle.simulate(0, LG, v["T"], v["data_seed"])
+            blk = np.array([float.fromhex(c) for c in v["block_hex"]])
+            r = oracle.log_likelihood(v["kind"], blk, v["N"], y, v["resampler"], v["seed"], v["epoch"], v["stream"])
+            assert float(r["logZ"]).hex() == v["logZ_hex"] and float(np.sum(r["x"])).hex() == v["x_sum_hex"]
+            assert [float(a).hex() for a in r["x"][:, -1]] == v["x_last_hex"]
+
+
 def test_batch_oracle_equals_loop(oracle):
     rng = np.random.default_rng(6)
     M, N, T = 5, 100, 12

@@ -594,6 +594,52 @@ def test_cuda_path_against_committed_golden_vectors(ctx):
 
 
 @pytest.mark.gpu
+def test_cuda_path_against_committed_golden_vectors_of_round_2(ctx):
+    """tests/golden/round2_vectors.json: the two-level multinomial draw of a large cloud (SPEC §5c), the guided UCSV move on both
+    engines (§10b) and the multivariate LG particle filter (§4b) — the CUDA path alone against the committed bit patterns"""
+    import json
+    import os
+    for v in json.load(open(os.path.join(os.path.dirname(__file__), "golden", "round2_vectors.json"))):
+        zg = float.fromhex(v["logZ_hex"])
+        ctx.set_rng(v["seed"], v["epoch"])
+        if v["what"] == "two_level_multinomial":
+            _, y = smc._lib.simulate(v["kind"], v["params"], v["T"], v["data_seed"])
+            ctx.record_ancestors(True)
+            try:
+                z = ctx.log_likelihood(v["kind"], v["params"], v["N"], y, v["resampler"], v["stream"])
+                x, _, _ = ctx.fetch_state(want_w=False)
+                anc = ctx.fetch_ancestors(v["T"] - 1)
+            finally:
+                ctx.record_ancestors(False)
+            assert abs(z - zg) <= RTOL * abs(zg) and float(np.sum(x)).hex() == v["x_sum_hex"]
+            assert [int(a) for a in anc[0][:16]] == v["anc_t1_head"]
+            assert int(np.sum(anc * (np.arange(v["N"]) + 1)) % (2 ** 61 - 1)) == v["anc_checksum"]
+        elif v["what"] == "guided_ucsv":
+            _, y = smc._lib.simulate(v["kind"], v["params"], v["T"], v["data_seed"])
+            kap = np.array([float.fromhex(c) for c in v["kappa_hex"]])
+            prop = np.stack([kap, np.zeros(kap.size), np.ones(kap.size)], 1)
+            b = ctx.batch(v["kind"], 1, v["N"])
+            z = b.log_likelihood(smc._lib.params8(v["params"]).reshape(1, -1), y, v["resampler"], v["stream"], proposal=prop[:, None, :])
+            x, _, lw = b.fetch(want_w=False, want_logw=True)
+            b.close()
+            assert abs(z[0] - zg) <= RTOL * abs(zg)
+            assert float(np.sum(x[0])).hex() == v["x_sum_hex"] and float(np.sum(lw[0])).hex() == v["logw_sum_hex"]
+            assert [float(a).hex() for a in x[0, :, -1]] == v["x_last_hex"]
+            if v["resampler"] != smc.MULTINOMIAL:
+                ctx.set_rng(v["seed"], v["epoch"])
+                ctx.guided_log_likelihood(v["kind"], v["params"], v["N"], y, prop, v["resampler"], v["stream"])
+                xs, _, lws = ctx.fetch_state(want_w=False, want_logw=True)
+                assert float(np.sum(xs)).hex() == v["x_sum_hex"] and float(np.sum(lws)).hex() == v["logw_sum_hex"]
+        else:
+            _, y = smc._lib.simulate(0, LG, v["T"], v["data_seed"])
+            blk = np.array([float.fromhex(c) for c in v["block_hex"]])
+            z = ctx.log_likelihood(v["kind"], blk, v["N"], y, v["resampler"], v["stream"])
+            x, _, _ = ctx.fetch_state(want_w=False)
+            assert abs(z - zg) <= RTOL * abs(zg) and float(np.sum(x)).hex() == v["x_sum_hex"]
+            assert [float(a).hex() for a in x[:, -1]] == v["x_last_hex"]
+
+
+@pytest.mark.gpu
 def test_smc2_with_guided_inner_filters(ctx, oracle):
     """extension of SMC (not in the reference): every inner filter step guided by the θ-particle's own locally optimal
     proposal (SMC(..., proposal=lg_optimal_proposals)); smc² / smc²! with rejuvenations against the oracle's sampler run

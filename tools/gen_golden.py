@@ -63,6 +63,29 @@ for matched in (0, 1):
                     ll_hex=float(ll).hex(), x_hex=[float(v).hex() for v in x], S_hex=[float(v).hex() for v in S.ravel()]))
 json.dump(wid, open(os.path.join(G, "widen_vectors.json"), "w"), indent=1)
 
+# round 2: the two-level multinomial draw of a large cloud (SPEC §5c, sorted in-cell thresholds), the guided UCSV move (§10b),
+# the particle-filter functor of the multivariate linear models (§4b)
+r2 = []
+_, y = o.simulate(0, MODELS[0], 6, 1998)
+r = o.log_likelihood(0, MODELS[0], 20011, y, 0, seed=7, epoch=3, stream=2, want_anc=True)
+r2.append(dict(what="two_level_multinomial", kind=0, params=MODELS[0], N=20011, T=6, data_seed=1998, resampler=0, seed=7, epoch=3, stream=2,
+               logZ_hex=float(r["logZ"]).hex(), x_sum_hex=float(np.sum(r["x"])).hex(), anc_t1_head=[int(v) for v in r["anc"][1][:16]],
+               anc_checksum=int(np.sum(r["anc"][1:] * (np.arange(20011) + 1)) % (2 ** 61 - 1))))
+_, y = o.simulate(2, MODELS[2], 20, 1998)
+kap = np.linspace(0.0, 1.0, 20)
+prop = np.stack([kap, np.zeros(20), np.ones(20)], 1)
+for rs in (0, 2):
+    r = o.guided_log_likelihood(2, MODELS[2], 257, y, rs, prop, 7, 3, 2)
+    r2.append(dict(what="guided_ucsv", kind=2, params=MODELS[2], N=257, T=20, data_seed=1998, resampler=rs, seed=7, epoch=3, stream=2,
+                   kappa_hex=[float(v).hex() for v in kap], logZ_hex=float(r["logZ"]).hex(), x_sum_hex=float(np.sum(r["x"])).hex(),
+                   logw_sum_hex=float(np.sum(r["logw"])).hex(), x_last_hex=[float(v).hex() for v in r["x"][:, -1]]))
+_, y = o.simulate(0, MODELS[0], 30, 1998)
+blk = o.mv_block([[0.7, 0.2], [-0.1, 0.5]], [1.0, 0.5], [[0.5, 0.1], [0.1, 0.3]], [0.8], [0.0, 0.0], np.eye(2))
+r = o.log_likelihood(3, blk, 9001, y, 2, seed=7, epoch=3, stream=2)
+r2.append(dict(what="mvlg_filter", kind=3, block_hex=[float(v).hex() for v in blk], N=9001, T=30, data_seed=1998, resampler=2, seed=7, epoch=3, stream=2,
+               logZ_hex=float(r["logZ"]).hex(), x_sum_hex=float(np.sum(r["x"])).hex(), x_last_hex=[float(v).hex() for v in r["x"][:, -1]]))
+json.dump(r2, open(os.path.join(G, "round2_vectors.json"), "w"), indent=1)
+
 # det-math spot values (bit patterns) — any change of a coefficient or operation order shows up here
 xs = [-700.0, -37.25, -1.0, -1e-3, 0.0, 0.5, 1.0, 10.125, 700.0]
 us = [2.0 ** -53, 1e-9, 0.1, 0.5, 0.75, 1 - 2.0 ** -53]
