@@ -45,6 +45,7 @@ sys.path.insert(0, ROOT)
 
 LG_THETA = [0.5, 0.9, 0.8]                       # README.md:21  (A, Q, R)
 LG_PARAMS = [0.5, 1.0, 0.9, 0.8, 0.0, 1.0]       # A, B, Q, R, x0, σ0
+UCSV_TRUE = [0.2, 0.2, 3.0, 1.0, 1.0]          # γε, γη, x0, log σε, log ση (docs/SPEC.md §4)
 BYTES_PER_UPDATE = 56
 DATA_SEED = 1998
 
@@ -426,7 +427,8 @@ def main():
         line["multinomial"] = {"error": repr(e)}
     if not args.no_smc2:
         try:
-            line["smc2"] = smc2_legs(ctx, None, 0, 1, None, ("c3", "c4", "c3_multinomial"), steps=3, warmup=1)
+            line["smc2"] = smc2_legs(ctx, None, 0, 1, None, ("c3", "c3_multinomial"), steps=5, warmup=2)   # 16 ms runs: cheap to repeat
+            line["smc2"].update(smc2_legs(ctx, None, 0, 1, None, ("c4",), steps=3, warmup=1))
             line["smc2"].update(smc2_legs(ctx, None, 0, 1, None, ("c5", "c5_multinomial"), steps=1, warmup=1))
             if not args.no_cpu:
                 line["smc2"]["cpu_baseline"] = cpu_rejuvenation_sample(1024, 100)
@@ -606,6 +608,22 @@ def widen_leg(ctx, M=512, N=1024, T=100):
     mean, var = b.weighted_moments()
     out["per_theta_moments_ms"] = (time.perf_counter() - t0) * 1e3
     b.close()
+    # the guided move of UCSV (docs/SPEC.md §10b: tempered optimal trend proposal) on config 5's inner shape: 296 independent
+    # filters of 4096 particles at the true θ, κ = 1 against the bootstrap filter — device time and the scatter of logZ
+    Mu, Nu, Tu = 296, 4096, 100
+    Pu = np.tile(smc._lib.params8(UCSV_TRUE), (Mu, 1))
+    yu = smc._lib.simulate(smc.KIND_UCSV, UCSV_TRUE, Tu, 1998)[1]
+    pu = np.zeros((Tu, Mu, 3))
+    pu[:, :, 0], pu[:, :, 2] = 1.0, 1.0
+    bu = ctx.batch(smc.KIND_UCSV, Mu, Nu)
+    gu = {"workload": f"{Mu} θ × {Nu} particles, T={Tu}, UCSV at the true θ, systematic; κ = 1 (locally optimal trend move) against bootstrap"}
+    for name, q in (("bootstrap", None), ("guided", pu)):
+        bu.log_likelihood(Pu, yu, smc.SYSTEMATIC, 0, proposal=q)
+        z = bu.log_likelihood(Pu, yu, smc.SYSTEMATIC, 0, proposal=q)
+        ms = bu.timing()[0]
+        gu[name] = {"ms_per_sweep": ms, "particle_updates_per_s": Mu * Nu * Tu / (ms * 1e-3), "sd_logZ_over_theta": float(np.std(z)), "mean_logZ": float(np.mean(z))}
+    bu.close()
+    out["guided_ucsv"] = gu
     out["kalman_matched_init_logZ"] = float(ctx.kalman_loglik(LG_PARAMS, y, matched_init=True)[0][0])
     yhp = smc._lib.simulate(smc.KIND_LG1D, [1.0, 1.0, 0.05, 1.0, 0.0, 1.0], 241, 1998)[1]
     blocks = np.stack([smc.hodrick_prescott(λ=lam, y=yhp).block() for lam in np.geomspace(1.0, 1e5, 4096)])

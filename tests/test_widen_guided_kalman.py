@@ -309,11 +309,11 @@ def test_guided_stepping_api_and_python_mirror(ctx, oracle):
     logmu, w, _ = smc.particle_filter_(x, w, 0.25, lg, None, resampler="systematic")
     oracle.bootstrap_step(0, LG, xo, lwo, 0.25, T, oracle.SYSTEMATIC, 13, 5, 6)
     np.testing.assert_array_equal(np.asarray(x), xo[0])
-    # errors: UCSV has no guided kernel; a non-positive proposal sd is refused; coefficients must be three numbers
+    # errors: UCSV takes (κ, 0, 1) with κ in [0, 1] (SPEC §10b); a non-positive proposal sd is refused; coefficients must be three numbers
     b = ctx.batch(smc.KIND_UCSV, 2, 64)
     b.init(np.tile(smc._lib.params8([0.2, 0.2, 3.0, 1.0, 1.0]), (2, 1)), 1.0)
     with pytest.raises(smc.SMCBError):
-        b.step(1.0, smc.SYSTEMATIC, proposal=np.tile([0.0, 1.0, 1.0], (2, 1)))
+        b.step(1.0, smc.SYSTEMATIC, proposal=np.tile([1.5, 0.0, 1.0], (2, 1)))
     b.close()
     b = ctx.batch(smc.KIND_LG1D, 2, 64)
     b.init(np.tile(smc._lib.params8(LG), (2, 1)), 1.0)
