@@ -1071,8 +1071,6 @@ struct MnIndex {
 };
 constexpr int kMnLutBits = 13;
 constexpr int kMnLutMax = 1 << kMnLutBits;  // buckets of the level-1 lookup table
-constexpr int kMnHeavySpan = 24;  // lookup-table ranges at least this long are filled by the whole CTA
-constexpr int kMnHeavyCap = 96;
 constexpr int kMnSubBits = 12;
 constexpr int kMnSub = 1 << kMnSubBits;     // outputs per sub-pass of mn_cell_kernel = buckets of its counting sort
 
@@ -1241,8 +1239,6 @@ __global__ void __launch_bounds__(kMnCellThreads, 3)
   int* s_hist = s_lut + kMnSub + 4;                                                     // [kMnCell] offspring counts (16-byte aligned)
   __shared__ int s_w[kMnCellThreads / 32];
   __shared__ int s_item[2];
-  __shared__ int s_nheavy;
-  __shared__ int s_heavy[kMnHeavyCap][3];
   constexpr int PER = kMnCell / kMnCellThreads;  // 8 particles per thread
   constexpr int NW = kMnCellThreads / 32;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1309,41 +1305,52 @@ __global__ void __launch_bounds__(kMnCellThreads, 3)
     for (int k = 0; k < PER; k += 2) reinterpret_cast<ulonglong2*>(s_c)[(jf + k) >> 1] = make_ulonglong2(C[k], C[k + 1]);
     reinterpret_cast<int4*>(s_hist)[2 * tid] = make_int4(0, 0, 0, 0);
     reinterpret_cast<int4*>(s_hist)[2 * tid + 1] = make_int4(0, 0, 0, 0);
+    reinterpret_cast<int4*>(s_lut)[2 * tid] = make_int4(0, 0, 0, 0);
+    reinterpret_cast<int4*>(s_lut)[2 * tid + 1] = make_int4(0, 0, 0, 0);
   }
   __syncthreads();
-  // ---- lookup table: lut[b] = #{ j : (C_j >> s) < b }; particle j writes the buckets (C_{j-1} >> s, C_j >> s] — about one each.
-  // A particle that holds a large share of the cell's mass spans many buckets: those ranges go to a short list that the
-  // whole CTA fills together, so that very uneven weights do not serialise the CTA behind one thread.
-  if (tid == 0) s_nheavy = 0;
-  __syncthreads();
+  // ---- lookup table: lut[b] = #{ j : (C_j >> s) < b } = the first particle whose bucket C_j >> s is not below b.  Particle j OWNS
+  // the buckets (C_{j-1} >> s, C_j >> s]: it writes its index into the first one it owns (no two particles share a first bucket)
+  // and a max-scan over the buckets hands it the rest — no per-particle loop over buckets, so neither the divergence of a loop
+  // whose length varies from lane to lane nor a special path for a particle that holds most of the cell's mass.
+  // (the table was zeroed with the counters above; thread `tid` scans the 8 buckets 8 tid .. 8 tid + 7)
   if (jf < len) {
-    int b = jf ? (int)(s_c[jf - 1] >> s) + 1 : 0;
+    int bprev = jf ? (int)(s_c[jf - 1] >> s) : -1;
 #pragma unroll
     for (int k = 0; k < PER; ++k) {
       if (jf + k < len) {
         const int b_hi = (int)(C[k] >> s);
-        if (b_hi - b >= kMnHeavySpan) {
-          const int slot = atomicAdd(&s_nheavy, 1);
-          if (slot < kMnHeavyCap) {
-            s_heavy[slot][0] = b;
-            s_heavy[slot][1] = b_hi;
-            s_heavy[slot][2] = jf + k;
-            b = b_hi + 1;
-          }
-        }
-        for (; b <= b_hi; ++b) s_lut[b] = jf + k;
+        if (b_hi > bprev) s_lut[bprev + 1] = jf + k;
+        bprev = b_hi;
       }
     }
   }
   __syncthreads();
   {
-    const int nh = s_nheavy < kMnHeavyCap ? s_nheavy : kMnHeavyCap;
-    for (int e = 0; e < nh; ++e) {
-      const int b_hi = s_heavy[e][1], j = s_heavy[e][2];
-      for (int b = s_heavy[e][0] + tid; b <= b_hi; b += kMnCellThreads) s_lut[b] = j;
+    static_assert(kMnSub == kMnCellThreads * 8, "one thread scans 8 buckets");
+    const int4 l0 = reinterpret_cast<const int4*>(s_lut)[2 * tid], l1 = reinterpret_cast<const int4*>(s_lut)[2 * tid + 1];
+    int v[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+    for (int k = 1; k < 8; ++k) v[k] = v[k] > v[k - 1] ? v[k] : v[k - 1];
+    int inc = v[7];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(kFullMask, inc, o);
+      if (lane >= o) inc = u > inc ? u : inc;
     }
-    if (nh) __syncthreads();
+    const int wprev = __shfl_up_sync(kFullMask, inc, 1);
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    int carry = lane ? wprev : 0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+      if (w < warp) carry = s_w[w] > carry ? s_w[w] : carry;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = v[k] > carry ? v[k] : carry;
+    reinterpret_cast<int4*>(s_lut)[2 * tid] = make_int4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<int4*>(s_lut)[2 * tid + 1] = make_int4(v[4], v[5], v[6], v[7]);
   }
+  __syncthreads();  // (also: s_w is reused by the prefix sum below)
   // ---- in-cell thresholds (SPEC §5c level 2): output position g uses word (g & 3) of the Philox block at index g >> 2
   for (int p = (g0 >> 2) + tid; 4 * p < g1; p += kMnCellThreads) {
     const Philox4 blk = philox4x32_10((uint32_t)p, stream, t, purpose_word(PURPOSE_RESAMPLE_CELL, 0, key.epoch), key);

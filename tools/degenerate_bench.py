@@ -12,7 +12,7 @@ N, T = 1 << (int(sys.argv[1]) if len(sys.argv) > 1 else 24), 12
 y = rng.normal(size=T)
 for R in (0.8, 1e-2, 1e-4, 1e-6, 1e-8, 1e-10):
     P = [0.5, 1.0, 0.9, R, 0.0, 1.0]
-    for rs, name in ((smc.SYSTEMATIC, "systematic"), (smc.STRATIFIED, "stratified")):
+    for rs, name in ((smc.SYSTEMATIC, "systematic"), (smc.STRATIFIED, "stratified"), (smc.MULTINOMIAL, "multinomial")):
         ctx.log_likelihood(smc.KIND_LG1D, P, N, y[:3], rs)
         ctx.set_profiling(True)
         _, _, ess = ctx.log_likelihood(smc.KIND_LG1D, P, N, y, rs, per_step=True)
