@@ -451,6 +451,7 @@ ThetaSampler::ThetaSampler(int device, cudaStream_t stream, const Comm& comm, co
   }
   SMCB_CUDA_TRY(cudaSetDevice(device_));
   cur_.reset(new BatchFilter(device_, stream_, kind_, Mloc_, N_));
+  prop_.reset(new BatchFilter(device_, stream_, kind_, Mloc_, N_));  // the proposals' clouds: allocated here, not inside the first rejuvenation
   const size_t M = (size_t)M_;
   for (int i = 0; i < 2; ++i) {
     dev_alloc(theta_[i], M * d_);
@@ -750,6 +751,7 @@ void ThetaSampler::exchange(int64_t t_len) {
   n_batch_launches_retired_ += cur_->launches() + (prop_ ? prop_->launches() : 0);
   prop_.reset();
   cur_.reset(new BatchFilter(device_, stream_, kind_, Mloc_, N_));
+  prop_.reset(new BatchFilter(device_, stream_, kind_, Mloc_, N_));
   const uint32_t e = next_epoch();
   mark(SK_FILTER, true);
   cur_->run_dev(derived_[tcur_] + lo_ * kParamStride, nullptr, y_dev_, t_len, resampler_, key(e), (uint32_t)lo_, logmu_ + lo_);  // :174-180

@@ -1,0 +1,5 @@
+#!/bin/bash
+# final check of the round: smoke, whole GPU suite, the N=1 bench line
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r2_smoke_final.log 2>&1; tail -1 gpurun_out/r2_smoke_final.log
+python -m pytest tests -m gpu -q 2>&1 | tail -6 > gpurun_out/r2_pytest_gpu_full_final.log; cat gpurun_out/r2_pytest_gpu_full_final.log
+python bench.py 2> gpurun_out/r2_bench_n1_final.err | grep '^{' > gpurun_out/r2_bench_n1_final.json; tail -c 400 gpurun_out/r2_bench_n1_final.err
