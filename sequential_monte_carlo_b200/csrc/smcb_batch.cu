@@ -726,6 +726,30 @@ __global__ void proposal_prepare_kernel(const double* __restrict__ raw, double* 
   q[4] = 1.0 / c2;
 }
 
+}  // namespace
+
+// Steps per chunk of the dynamically scheduled launch, 0 = one CTA per θ for the whole series (host-only; smcb_batch_chunk_plan).
+// Whole series, one CTA per θ, waste two ways (measured: profiles/r2_chunk_*.jsonl).  More θ than resident CTAs: ceil(M / slots)
+// waves for M / slots waves of work (UCSV 4096: 512 θ on 148 slots, SV 2048: 1024 θ on 296 slots — 3.46 waves run as 4).
+// All resident but unevenly spread over SMs whose warps are saturated: the SMs that hold ceil(M / SMs) CTAs finish last
+// (LG1D 1024: 512 CTAs of 256 threads on 148 SMs).  Chunks pay when either wastes more than 3 %; a chunk boundary costs
+// 5-7 µs (publish, acquire, reload), so chunks are at least 8 steps of a cloud of >= 1024 particles.
+int64_t plan_batch_chunk(int64_t M, int64_t N, int64_t steps, int threads, int64_t slots, int num_sms) {
+  if (M <= num_sms || slots < 1 || num_sms < 1) return 0;
+  const double waves = (double)M / (double)slots, load = (double)M / (double)num_sms;
+  double eff = 1.0;
+  if (M > slots) eff = waves / std::ceil(waves);
+  else if ((int64_t)threads * (int64_t)std::ceil(load) >= 1024) eff = load / std::ceil(load);
+  const int64_t min_chunk = std::max<int64_t>(8, 8192 / std::max<int64_t>(N, 1));
+  if (!(eff < 0.97) || steps < 2 * min_chunk) return 0;
+  const int64_t want = (33 * slots + M - 1) / M;              // chunks per θ for >= 33 waves of units
+  const int64_t nch = std::max<int64_t>(1, std::min<int64_t>(want, steps / min_chunk));
+  const int64_t chunk = (steps + nch - 1) / nch;
+  return chunk >= steps ? 0 : chunk;
+}
+
+namespace {
+
 struct DynPlan {   // host side of the dynamic scheduling
   unsigned* sched;  // [1 + M]
   int num_sms;
@@ -744,23 +768,7 @@ void launch_batch(BatchArgs a, int64_t M, int threads, size_t smem, cudaStream_t
     SMCB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kdyn, threads, smem));
     slots = (int64_t)std::max(occ, 1) * dp.num_sms;
     if (dp.force_chunk > 0) chunk = dp.force_chunk;
-    else if (M > dp.num_sms) {
-      // Whole series, one CTA per θ, waste two ways (measured: profiles/r2_chunk_*.jsonl).  More θ than resident CTAs: ceil(M / slots)
-      // waves for M / slots waves of work (UCSV 4096: 512 θ on 148 slots, SV 2048: 1024 θ on 296 slots — 3.46 waves run as 4).
-      // All resident but unevenly spread over SMs whose warps are saturated: the SMs that hold ceil(M / SMs) CTAs finish last
-      // (LG1D 1024: 512 CTAs of 256 threads on 148 SMs).  Chunks pay when either wastes more than 3 %; a chunk boundary costs
-      // 5-7 µs (publish, acquire, reload), so chunks are at least 8 steps of a cloud of >= 1024 particles.
-      const double waves = (double)M / (double)slots, load = (double)M / (double)dp.num_sms;
-      double eff = 1.0;
-      if (M > slots) eff = waves / std::ceil(waves);
-      else if ((int64_t)threads * (int64_t)std::ceil(load) >= 1024) eff = load / std::ceil(load);
-      const int64_t min_chunk = std::max<int64_t>(8, 8192 / std::max<int64_t>(a.N, 1));
-      if (eff < 0.97 && steps >= 2 * min_chunk) {
-        const int64_t want = (33 * slots + M - 1) / M;              // chunks per θ for >= 33 waves of units
-        const int64_t nch = std::max<int64_t>(1, std::min<int64_t>(want, steps / min_chunk));
-        chunk = (steps + nch - 1) / nch;
-      }
-    }
+    else chunk = plan_batch_chunk(M, a.N, steps, threads, slots, dp.num_sms);
     if (chunk >= steps) chunk = 0;
   }
   if (chunk > 0) {

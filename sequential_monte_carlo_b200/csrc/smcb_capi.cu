@@ -525,6 +525,12 @@ int smcb_comm_destroy(smcb_ctx* ctx) {
   return SMCB_OK;
 }
 
+int smcb_batch_chunk_plan(int64_t M, int64_t N, int64_t steps, int threads, int64_t slots, int num_sms, int64_t* chunk) {
+  if (!chunk || M < 1 || N < 1 || steps < 1 || threads < 1) return SMCB_ERR_BAD_ARG;
+  *chunk = smcb::plan_batch_chunk(M, N, steps, threads, slots, num_sms);
+  return SMCB_OK;
+}
+
 int smcb_exchange_plan(const int32_t* parents, int64_t M, int rank, int nranks, int32_t* local_parents, int32_t* send_peer,
                        int32_t* send_slot, int64_t* n_send, int32_t* recv_peer, int32_t* recv_slot, int64_t* n_recv) {
   if (!parents || M < 1 || nranks < 1 || rank < 0 || rank >= nranks || M % nranks || !local_parents || !n_send || !n_recv)

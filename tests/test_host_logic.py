@@ -501,3 +501,30 @@ def test_proposal_arithmetic_is_the_frozen_one(oracle):
             np.testing.assert_allclose(ss._propose(th, Sg, False, scale, z), th + z @ np.linalg.cholesky(scale * Sg).T, rtol=1e-12, atol=1e-14)
     with pytest.raises(np.linalg.LinAlgError):
         _lib.cholesky_lower(np.array([[1.0, 2.0], [2.0, 1.0]]))
+
+
+def test_batch_chunk_plan_of_the_library():
+    """smcb_batch_chunk_plan (host-only C ABI entry): when the batched sweep is cut into dynamically scheduled (chunk, θ) units —
+    the shapes measured on the B200 (profiles/r2_chunk_auto.jsonl) and the cases that must stay one CTA per θ"""
+    from sequential_monte_carlo_b200 import _lib
+    plan = _lib.batch_chunk_plan
+    # config 5 per GPU at 8 GPUs: 512 UCSV clouds of 4096 particles, 1024-thread CTAs, one per SM: 3.46 waves -> chunks
+    k = plan(512, 4096, 240, 1024, 148)
+    assert 8 <= k <= 40 and -(-240 // k) >= 6
+    # the same at 1, 2, 4 GPUs fills its waves to within 1.2 %: left alone
+    assert plan(4096, 4096, 240, 1024, 148) == plan(2048, 4096, 240, 1024, 148) == plan(1024, 4096, 240, 1024, 148) == 0
+    # config 4 on one GPU: 1024 SV clouds of 2048 particles, two 512-thread CTAs per SM
+    assert plan(1024, 2048, 499, 512, 296) > 0
+    # config 3 on one GPU: all 512 CTAs (256 threads) resident, 3 or 4 to an SM whose warps are saturated
+    assert plan(512, 1024, 99, 256, 592) > 0
+    # every θ has an SM to itself; a short series; small clouds that do not saturate an SM; a single step
+    assert plan(148, 4096, 240, 1024, 148) == 0 and plan(64, 1024, 99, 512, 296) == 0
+    assert plan(512, 4096, 12, 1024, 148) == 0
+    assert plan(333, 301, 37, 160, 1184) == 0
+    assert plan(512, 4096, 1, 1024, 148) == 0
+    # chunks are at least 8 steps (more for small clouds) and never the whole series
+    for M, N, steps, thr, slots in ((300, 4096, 100, 1024, 148), (600, 1024, 100, 256, 592), (200, 8192, 40, 1024, 148), (5000, 64, 400, 32, 2368)):
+        k = plan(M, N, steps, thr, slots)
+        assert k == 0 or (max(8, 8192 // N) <= k < steps)
+    with pytest.raises(_lib.SMCBError):
+        plan(0, 1024, 10, 256, 148)
