@@ -112,8 +112,11 @@ KERNEL_BYTES_MOVED_LG1D = {"scan": 16, "bounds": 0, "anc": 12, "prop": 20}
 KERNEL_NAMES = {"scan": "sum_kernel", "bounds": "bounds_kernel", "anc": "anc_hist_kernel", "prop": "move_kernel"}
 
 
-def cpu_sample(steps, logn_sample=20, T_sample=64):
-    """The oracle's log_likelihood (port of particles.jl:132-147; single-threaded like the reference)."""
+def cpu_sample(steps, logn_sample=20, T_sample=64, style="reference"):
+    """The CPU arm, single-threaded like the reference's particle filter (particles.jl:122).
+    style="reference": the reference-STYLE port BASELINE.md §3 specifies (oracle/smc_oracle.c: smco_reference_style_log_likelihood —
+    alias-table multinomial resampling rebuilt on every step, fresh allocations per step, per-particle sqrt / log σ, xoshiro256++);
+    style="det": the parity oracle's log_likelihood (deterministic math + Philox, systematic resampling like the GPU arm)."""
     from oracle import oracle as o
     o.build()
     N = 1 << logn_sample
@@ -121,9 +124,14 @@ def cpu_sample(steps, logn_sample=20, T_sample=64):
     times = []
     for s in range(steps):
         t0 = time.perf_counter()
-        o.log_likelihood(0, LG_PARAMS, N, y, o.SYSTEMATIC, seed=DATA_SEED, epoch=s)
+        if style == "reference":
+            o.reference_style_log_likelihood(LG_PARAMS, N, y, DATA_SEED + s)
+        else:
+            o.log_likelihood(0, LG_PARAMS, N, y, o.SYSTEMATIC, seed=DATA_SEED, epoch=s)
         times.append(time.perf_counter() - t0)
-    return N * T_sample / statistics.mean(times), f"LG1D N=2^{logn_sample}, T={T_sample}, systematic, oracle/smc_oracle.c (gcc -O2), linear in N*T"
+    what = ("reference-style port (alias-table multinomial resampling and fresh allocations every step, as particles.jl:107-129 executes)"
+            if style == "reference" else "parity oracle (deterministic math + Philox, systematic resampling)")
+    return N * T_sample / statistics.mean(times), f"LG1D N=2^{logn_sample}, T={T_sample}, {what}, oracle/smc_oracle.c (gcc -O2), linear in N*T"
 
 
 def cpu_rejuvenation_sample(N=1024, T=100, seconds=8.0):
@@ -194,6 +202,7 @@ def run_reference(args, rank):
         return
     sample_logn, sample_T = 20, 32
     v, sample = cpu_sample(max(args.steps, 1), sample_logn, sample_T)
+    v_det, sample_det = cpu_sample(1, sample_logn, sample_T, style="det")
     N, T = 1 << args.logn, args.T
     line = {
         "impl": "reference", "metric": "particle-updates/sec (N×T) bootstrap PF", "value": v, "unit": "particle-updates/s",
@@ -204,9 +213,11 @@ def run_reference(args, rank):
         "ms_per_step_note": f"ms_per_step is the measured time of one sampled sweep (N=2^{sample_logn}, T={sample_T}); the value (particle-updates/s) "
                             "is linear in N·T for a per-particle loop, the full N=2^24 × T=1000 sweep (≈ 2000 s on one core) was not run",
         "cpu_baseline": {"value": v, "unit": "particle-updates/s", "cores": 1, "kind": "port", "sample": sample},
+        "cpu_baseline_parity_oracle": {"value": v_det, "unit": "particle-updates/s", "cores": 1, "kind": "port", "sample": sample_det},
         "e2e": {"value": v, "unit": "particle-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": note + "; the reference PF is single-threaded (particles.jl:122), so one core is all it can use; systematic resampling "
-                       "like the GPU arm (the reference's multinomial draw is timed in the 'multinomial' leg of the GPU arm's line)",
+        "note": note + "; the reference PF is single-threaded (particles.jl:122), so one core is all it can use; the arm is the "
+                       "reference-style port of BASELINE.md §3 (multinomial by alias table, allocations per step), the parity oracle's "
+                       "own speed rides along",
     }
     print(json.dumps(line), flush=True)
 
@@ -394,6 +405,8 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         v, sample = cpu_sample(2, 20, 64)
         line["cpu_baseline"] = {"value": v, "unit": "particle-updates/s", "cores": 1, "kind": "port", "sample": sample}
+        vd, sd_ = cpu_sample(1, 20, 32, style="det")
+        line["cpu_baseline_parity_oracle"] = {"value": vd, "unit": "particle-updates/s", "cores": 1, "kind": "port", "sample": sd_}
     # the reference's own resampling law (multinomial: particles.jl:17-19, the API default) on the same workload: two-level
     # draw of docs/SPEC.md §5c (sum -> mn_prep -> mn_count -> mn_cell -> move), against the same 56 B roofline
     try:
@@ -420,9 +433,13 @@ def main():
         if not args.no_cpu:
             from oracle import oracle as o
             t0 = time.perf_counter()
-            o.log_likelihood(0, LG_PARAMS, 1 << 20, y[:16], o.MULTINOMIAL, seed=DATA_SEED, epoch=0)
+            o.reference_style_log_likelihood(LG_PARAMS, 1 << 20, y[:16], DATA_SEED)
             line["multinomial"]["cpu_baseline"] = {"value": (1 << 20) * 16 / (time.perf_counter() - t0), "unit": "particle-updates/s", "cores": 1, "kind": "port",
-                                                   "sample": "LG1D N=2^20, T=16, multinomial (SPEC §5c two-level draw), oracle/smc_oracle.c"}
+                                                   "sample": "LG1D N=2^20, T=16, multinomial by alias table rebuilt every step (the reference-style port of BASELINE.md §3), oracle/smc_oracle.c"}
+            t0 = time.perf_counter()
+            o.log_likelihood(0, LG_PARAMS, 1 << 20, y[:16], o.MULTINOMIAL, seed=DATA_SEED, epoch=0)
+            line["multinomial"]["cpu_baseline_parity_oracle"] = {"value": (1 << 20) * 16 / (time.perf_counter() - t0), "unit": "particle-updates/s", "cores": 1, "kind": "port",
+                                                                 "sample": "LG1D N=2^20, T=16, multinomial (SPEC §5c two-level draw), oracle/smc_oracle.c"}
     except Exception as e:
         line["multinomial"] = {"error": repr(e)}
     if not args.no_smc2:

@@ -44,6 +44,7 @@ def lib():
         L.smco_kalman_step.restype = C.c_double
         L.smco_kalman_loglik.restype = C.c_double
         L.smco_guided_log_likelihood.restype = C.c_double
+        L.smco_reference_style_log_likelihood.restype = C.c_double
         L.smco_kalman_mv_step.restype = C.c_double
         L.smco_kalman_mv_loglik.restype = C.c_double
         _LIB = L
@@ -333,6 +334,15 @@ def batch_log_likelihood(kind, params, active, n, y, resampler, seed, epoch, str
                                     C.c_int64(y.size), C.c_int(resampler), C.c_uint64(seed), C.c_uint32(epoch),
                                     C.c_uint32(stream0), _p(logZ), _p(x), _p(logw))
     return logZ, x, logw
+
+
+def reference_style_log_likelihood(params, n, y, seed):
+    """The timed CPU arm of BASELINE.md §3 (LG1D): particles.jl:87-147 with the reference's own costs — alias-table multinomial
+    resampling rebuilt on every step, fresh allocations per step, per-particle sqrt / log σ; its own RNG (xoshiro256++, polar
+    normals), so it is checked distributionally only.  Returns logZ."""
+    y = np.ascontiguousarray(y, np.float64)
+    p = np.ascontiguousarray(np.asarray(params, np.float64).ravel()[:6])
+    return float(lib().smco_reference_style_log_likelihood(_p(p), C.c_int64(int(n)), _p(y), C.c_int64(y.size), C.c_uint64(int(seed))))
 
 
 # ---------------------------------------------------------------- N3 guided filter (SPEC §10)

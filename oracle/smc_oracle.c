@@ -725,3 +725,109 @@ void smco_simulate(int kind, const double *P, int64_t T, uint64_t seed, double *
     y[t] = fma(sd, zo, mean);
   }
 }
+
+/* ------------------------------------------------------------------ reference-STYLE timing arm
+ * What /root/reference/src/particles.jl:87-147 executes for a univariate LinearModel, with the costs the Julia code has:
+ *   - resample(w) = sample(1:n, Weights(w), n) (:17-19): StatsBase's alias method — a Walker/Vose alias table built on EVERY step
+ *     (four fresh arrays), then two uniforms and two random reads per draw; unsorted ancestors;
+ *   - xp = deepcopy(x[a]) (:119): a fresh array and a random gather;
+ *   - rand(Normal(A xp, sqrt(Q))) and logpdf(Normal(B x, sqrt(R)), y) per particle (:122-125, state_space_models.jl:87-103): the sqrt
+ *     and the log σ are recomputed for every particle, as the reference's distribution objects do;
+ *   - normalize (:5-15): max, exp, sum, a fresh weight vector, ess.
+ * Random numbers: xoshiro256++ (the generator behind Julia's default RNG) and the polar method for normals (Julia uses a ziggurat).
+ * NOT part of the parity oracle — its stream is its own; it is checked distributionally (E[Ẑ] = Z against the Kalman filter) and
+ * used only as the timed CPU arm. */
+typedef struct { uint64_t s[4]; double spare; int has; } rs_rng;
+static inline uint64_t rs_rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+static inline uint64_t rs_next(rs_rng *g) {
+  uint64_t *s = g->s, r = rs_rotl(s[0] + s[3], 23) + s[0], t = s[1] << 17;
+  s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = rs_rotl(s[3], 45);
+  return r;
+}
+static void rs_seed(rs_rng *g, uint64_t seed) {
+  for (int i = 0; i < 4; ++i) {                          /* splitmix64 */
+    uint64_t z = (seed += 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull; z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    g->s[i] = z ^ (z >> 31);
+  }
+  g->has = 0;
+}
+static inline double rs_uniform(rs_rng *g) { return (double)(rs_next(g) >> 11) * 0x1p-53; }
+static inline double rs_randn(rs_rng *g) {
+  if (g->has) { g->has = 0; return g->spare; }
+  double u, v, s;
+  do { u = 2.0 * rs_uniform(g) - 1.0; v = 2.0 * rs_uniform(g) - 1.0; s = u * u + v * v; } while (s >= 1.0 || s == 0.0);
+  double f = sqrt(-2.0 * log(s) / s);
+  g->spare = v * f; g->has = 1;
+  return u * f;
+}
+static inline double rs_normal_logpdf(double mu, double sigma, double y) {   /* logpdf(Normal(mu, sigma), y) */
+  double z = (y - mu) / sigma;
+  return -0.5 * z * z - log(sigma) - 0.9189385332046727;
+}
+/* normalize(logw) -> (logμ, w, ess)  particles.jl:5-15; w is a fresh vector */
+static double *rs_normalize(const double *logw, int64_t n, double *logmu, double *ess) {
+  double maxw = -INFINITY, sumw = 0.0, s2 = 0.0;
+  for (int64_t i = 0; i < n; ++i) if (logw[i] > maxw) maxw = logw[i];
+  double *w = (double *)malloc(sizeof(double) * (size_t)n);
+  for (int64_t i = 0; i < n; ++i) { w[i] = exp(logw[i] - maxw); sumw += w[i]; }
+  *logmu = maxw + log(sumw) - log((double)n);
+  for (int64_t i = 0; i < n; ++i) { w[i] /= sumw; s2 += w[i] * w[i]; }
+  *ess = 1.0 / s2;
+  return w;
+}
+/* sample(1:n, Weights(w), n): make_alias_table! + alias_sample! */
+static int64_t *rs_alias_sample(rs_rng *g, const double *w, int64_t n) {
+  double *ap = (double *)malloc(sizeof(double) * (size_t)n);
+  int64_t *alias = (int64_t *)malloc(sizeof(int64_t) * (size_t)n), *larges = (int64_t *)malloc(sizeof(int64_t) * (size_t)n),
+          *smalls = (int64_t *)malloc(sizeof(int64_t) * (size_t)n), *a = (int64_t *)malloc(sizeof(int64_t) * (size_t)n);
+  int64_t kl = 0, ks = 0;
+  for (int64_t i = 0; i < n; ++i) {
+    ap[i] = w[i] * (double)n;
+    alias[i] = i;
+    if (ap[i] > 1.0) larges[kl++] = i; else if (ap[i] < 1.0) smalls[ks++] = i;
+  }
+  while (kl > 0 && ks > 0) {
+    int64_t s = smalls[--ks], l = larges[--kl];
+    alias[s] = l;
+    ap[l] = (ap[l] + ap[s]) - 1.0;
+    if (ap[l] > 1.0) larges[kl++] = l; else if (ap[l] < 1.0) smalls[ks++] = l;
+  }
+  for (int64_t i = 0; i < n; ++i) {
+    int64_t j = (int64_t)(rs_uniform(g) * (double)n);
+    if (j >= n) j = n - 1;
+    a[i] = (rs_uniform(g) < ap[j]) ? j : alias[j];
+  }
+  free(ap); free(alias); free(larges); free(smalls);
+  return a;
+}
+double smco_reference_style_log_likelihood(const double *P, int64_t n, const double *y, int64_t T, uint64_t seed) {
+  const double A = P[0], B = P[1], Q = P[2], R = P[3], x0 = P[4], s0 = P[5];
+  rs_rng g;
+  rs_seed(&g, seed);
+  double *x = (double *)malloc(sizeof(double) * (size_t)n), *logw = (double *)malloc(sizeof(double) * (size_t)n);
+  for (int64_t i = 0; i < n; ++i) {                      /* bootstrap_filter :96-99 */
+    x[i] = x0 + sqrt(s0) * rs_randn(&g);
+    logw[i] = rs_normal_logpdf(B * x[i], sqrt(R), y[0]);
+  }
+  double logmu, ess, logZ;
+  double *w = rs_normalize(logw, n, &logmu, &ess);
+  free(logw);
+  logZ = logmu;
+  for (int64_t t = 1; t < T; ++t) {                      /* bootstrap_filter! :107-129 */
+    logw = (double *)malloc(sizeof(double) * (size_t)n);  /* logw = similar(weights) */
+    int64_t *a = rs_alias_sample(&g, w, n);               /* a = resample(weights) */
+    double *xp = (double *)malloc(sizeof(double) * (size_t)n);
+    for (int64_t i = 0; i < n; ++i) xp[i] = x[a[i]];      /* xp = deepcopy(x[a]) */
+    for (int64_t i = 0; i < n; ++i) {
+      x[i] = A * xp[i] + sqrt(Q) * rs_randn(&g);          /* rand(transition(model, xp[i])) */
+      logw[i] = rs_normal_logpdf(B * x[i], sqrt(R), y[t]);
+    }
+    free(w); free(a); free(xp);
+    w = rs_normalize(logw, n, &logmu, &ess);
+    free(logw);
+    logZ += logmu;
+  }
+  free(w); free(x);
+  return logZ;
+}

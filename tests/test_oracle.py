@@ -194,6 +194,20 @@ def test_kalman_matches_closed_form(oracle):
     assert x == pytest.approx(x1, rel=1e-14) and S == pytest.approx(S1, rel=1e-14) and l == pytest.approx(ll, rel=1e-14)
 
 
+def test_reference_style_cpu_arm_targets_the_same_likelihood(oracle):
+    """the timed CPU arm of BASELINE.md §3 (alias-table multinomial resampling rebuilt every step, fresh allocations, its own
+    xoshiro256++ stream) is a bootstrap filter of the same model: E[Ẑ] = Z against the matched-init Kalman likelihood, and the
+    scatter of logZ of a multinomial filter (larger than the systematic filter's, same order)"""
+    _, y = oracle.simulate(0, LG, 60, 1998)
+    _, _, kf = oracle.kalman_loglik(LG, y, matched_init=True)
+    z = np.array([oracle.reference_style_log_likelihood(LG, 4096, y, s) for s in range(48)])
+    lme = np.log(np.mean(np.exp(z - z.max()))) + z.max()
+    assert abs(lme - kf) < 4 * z.std() / np.sqrt(z.size) + 0.02
+    zs = np.array([oracle.log_likelihood(0, LG, 4096, y, oracle.MULTINOMIAL, s)["logZ"] for s in range(48)])
+    assert 0.5 < z.std() / zs.std() < 2.0
+    assert oracle.reference_style_log_likelihood(LG, 1, y[:3], 5) < 0.0          # a single particle runs
+
+
 def test_particle_filter_targets_kalman_likelihood(oracle):
     """E[Ẑ] = Z: log-mean-exp of PF estimates vs the matched-init Kalman likelihood."""
     _, y = oracle.simulate(0, LG, 60, 1998)
