@@ -65,13 +65,19 @@ class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+    def __init__(self, index, enabled=True):
+        """index: the GPU to watch, or None for every GPU of the box (ONE poller for a multi-rank job: a poller per rank at 100 ms
+        was measured to stall the ranks' launches and synchronisations — config 5 on 4 GPUs: single runs of 1.25-1.6 s among 0.75 s
+        ones, profiles/r2_c5_runs_n4_nvidia_smi_polling.jsonl); enabled=False: this rank does not sample."""
+        self.index, self.rows, self.proc, self.enabled = index, [], None, enabled
 
     def start(self):
+        if not self.enabled:
+            return
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            sel = ["-i", str(self.index)] if self.index is not None else []
+            self.proc = subprocess.Popen(["nvidia-smi"] + sel + [f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -82,6 +88,8 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if not self.enabled:
+            return None
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -526,7 +534,7 @@ def main_sharded(args, rank, world, local, barrier):
     ctx = smc.Context(local, seed=DATA_SEED)
     comm = ss.NcclComm.from_torch(ctx)
     rmax, rsum = _reducers(world)
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(None, enabled=(rank == 0))   # one poller for the whole box, on rank 0
     barrier()
     sampler.start()
     head = bench_smc2.run_config("c5", ctx, comm, rank, world, steps=args.steps, warmup=max(1, min(args.warmup, 3)), barrier=barrier)
@@ -549,7 +557,7 @@ def main_sharded(args, rank, world, local, barrier):
         "gpu_launches": int(head["kernel_launches"] * args.steps),
         "breakdown_ms_per_step": head["breakdown_ms"],
         "run": {k: head[k] for k in ("theta_sha", "logZ_sum", "final_ess", "posterior_mean", "rejuvenations", "sweeps", "clouds_received_all_ranks",
-                                     "s_per_plain_step", "s_per_rejuvenation_step", "stream_syncs", "wall_s", "device_span_s", "particle_updates")},
+                                     "s_per_plain_step", "s_per_rejuvenation_step", "stream_syncs", "wall_s", "wall_s_median", "walls_s", "device_span_s", "device_spans_s", "particle_updates")},
         "roofline": {"bound": "hbm", "achieved": 88 * (units / world) / filt_s / 1e9 if filt_s > 0 else None, "peak": peak, "unit": "GB/s",
                      "frac": (88 * (units / world) / filt_s / 1e9 / peak) if filt_s > 0 else None, "traffic": None, "peak_source": peak_src,
                      "kernel": "batch_kernel<ModelUCSV> (one CTA per θ, whole series in one launch): 88 algorithmic B per particle-update "

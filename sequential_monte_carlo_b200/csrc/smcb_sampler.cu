@@ -452,6 +452,18 @@ ThetaSampler::ThetaSampler(int device, cudaStream_t stream, const Comm& comm, co
   SMCB_CUDA_TRY(cudaSetDevice(device_));
   cur_.reset(new BatchFilter(device_, stream_, kind_, Mloc_, N_));
   prop_.reset(new BatchFilter(device_, stream_, kind_, Mloc_, N_));  // the proposals' clouds: allocated here, not inside the first rejuvenation
+  if (comm_.active()) {
+    // Staging buffers of the cloud exchange, sized once for "every local slot receives / sends one cloud".  They used to grow inside
+    // resample() by cudaFree + cudaMalloc whenever a θ-resample moved more clouds than any before it — a driver call that takes
+    // process-wide (and, on a shared box, machine-wide) locks and was measured to stall single rejuvenations by 0.1-1.1 s at random
+    // (profiles/r2_c5_steps_n4_before_preallocation.jsonl).  A resample that needs more (one parent with children all over the
+    // other ranks) still grows them.
+    for (int i = 0; i < 2; ++i) {
+      const int64_t bytes = Mloc_ * cur_->cloud_bytes();
+      SMCB_CUDA_TRY(cudaMalloc(&xbuf_[i], (size_t)bytes));
+      xbuf_cap_[i] = bytes;
+    }
+  }
   const size_t M = (size_t)M_;
   for (int i = 0; i < 2; ++i) {
     dev_alloc(theta_[i], M * d_);
