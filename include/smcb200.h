@@ -215,9 +215,10 @@ int smcb_comm_destroy(smcb_ctx* ctx);
 /* host-only (no GPU): how a whole-series sweep of M filters of N particles over `steps` observations is scheduled on a GPU that keeps
  * `slots` CTAs of `threads` threads resident on `num_sms` SMs: *chunk = 0 — one CTA per θ-particle for the whole series (the loops over θ
  * of smc_samplers.jl:112-121,223-229 as one launch); *chunk = K > 0 — a persistent grid claims (chunk of K steps, θ) units in order
- * (used when whole series would leave > 3 % of the launch idle; results are bit-identical either way).  SMCB_BATCH_CHUNK in the
+ * (used when whole series would leave > 3 % of the launch idle, and — masked != 0 — for every sweep that carries an `active` mask over
+ * more θ than resident CTAs: how many of them run is known only on the device; results are bit-identical either way).  SMCB_BATCH_CHUNK in the
  * environment overrides the plan (0, or a chunk length). */
-int smcb_batch_chunk_plan(int64_t M, int64_t N, int64_t steps, int threads, int64_t slots, int num_sms, int64_t* chunk);
+int smcb_batch_chunk_plan(int64_t M, int64_t N, int64_t steps, int threads, int64_t slots, int num_sms, int masked, int64_t* chunk);
 /* host-only (no GPU): who sends which cloud where after a θ-resample with (sorted) parents[M].  local_parents [M/G]:
  * rank-local parent slot (the slot itself where the parent is remote); send_* / recv_*: the clouds this rank sends /
  * receives as (peer rank, local slot), grouped by peer, increasing global slot — both sides enumerate the same order.

@@ -85,7 +85,7 @@ SIGNATURES = {
     "smcb_comm_rank": (C.c_int, [_c_ctx, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "smcb_comm_all_gather": (C.c_int, [_c_ctx, C.c_void_p, C.c_int64, C.c_void_p]),
     "smcb_comm_destroy": (C.c_int, [_c_ctx]),
-    "smcb_batch_chunk_plan": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_int, _i64p]),
+    "smcb_batch_chunk_plan": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int64, C.c_int, C.c_int, _i64p]),
     "smcb_exchange_plan": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, _i64p,
                                      C.c_void_p, C.c_void_p, _i64p]),
     "smcb_sampler_create": (C.c_int, [_c_ctx, C.POINTER(SamplerConfig), C.c_void_p, C.POINTER(_c_sampler)]),
@@ -205,10 +205,10 @@ def cholesky_lower(A, scale=1.0):
     return L
 
 
-def batch_chunk_plan(M, N, steps, threads, slots, num_sms=148):
+def batch_chunk_plan(M, N, steps, threads, slots, num_sms=148, masked=False):
     """smcb_batch_chunk_plan: steps per chunk of the dynamically scheduled batched sweep, 0 = one CTA per θ (host-only)"""
     out = C.c_int64(0)
-    rc = load().smcb_batch_chunk_plan(int(M), int(N), int(steps), int(threads), int(slots), int(num_sms), C.byref(out))
+    rc = load().smcb_batch_chunk_plan(int(M), int(N), int(steps), int(threads), int(slots), int(num_sms), int(bool(masked)), C.byref(out))
     if rc != 0:
         raise SMCBError(rc, "smcb_batch_chunk_plan: bad arguments")
     return int(out.value)

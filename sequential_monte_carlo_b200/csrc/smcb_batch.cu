@@ -734,11 +734,15 @@ __global__ void proposal_prepare_kernel(const double* __restrict__ raw, double* 
 // All resident but unevenly spread over SMs whose warps are saturated: the SMs that hold ceil(M / SMs) CTAs finish last
 // (LG1D 1024: 512 CTAs of 256 threads on 148 SMs).  Chunks pay when either wastes more than 3 %; a chunk boundary costs
 // 5-7 µs (publish, acquire, reload), so chunks are at least 8 steps of a cloud of >= 1024 particles.
-int64_t plan_batch_chunk(int64_t M, int64_t N, int64_t steps, int threads, int64_t slots, int num_sms) {
+// masked: the launch carries an `active` mask (the proposals of rejuvenate! that fell outside the prior's support do not run,
+// smc_samplers.jl:116): how many of the M CTAs do any work is only known on the device, so the waves of a one-CTA-per-θ launch are
+// ceil(M_active / slots) for an M_active nobody planned for (config 5 on 4 GPUs lost 7 % that way) — such sweeps are chunked
+// whenever there are more θ than resident CTAs.
+int64_t plan_batch_chunk(int64_t M, int64_t N, int64_t steps, int threads, int64_t slots, int num_sms, bool masked) {
   if (M <= num_sms || slots < 1 || num_sms < 1) return 0;
   const double waves = (double)M / (double)slots, load = (double)M / (double)num_sms;
   double eff = 1.0;
-  if (M > slots) eff = waves / std::ceil(waves);
+  if (M > slots) eff = masked ? 0.0 : waves / std::ceil(waves);
   else if ((int64_t)threads * (int64_t)std::ceil(load) >= 1024) eff = load / std::ceil(load);
   const int64_t min_chunk = std::max<int64_t>(8, 8192 / std::max<int64_t>(N, 1));
   if (!(eff < 0.97) || steps < 2 * min_chunk) return 0;
@@ -768,7 +772,7 @@ void launch_batch(BatchArgs a, int64_t M, int threads, size_t smem, cudaStream_t
     SMCB_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kdyn, threads, smem));
     slots = (int64_t)std::max(occ, 1) * dp.num_sms;
     if (dp.force_chunk > 0) chunk = dp.force_chunk;
-    else chunk = plan_batch_chunk(M, a.N, steps, threads, slots, dp.num_sms);
+    else chunk = plan_batch_chunk(M, a.N, steps, threads, slots, dp.num_sms, a.active != nullptr);
     if (chunk >= steps) chunk = 0;
   }
   if (chunk > 0) {

@@ -118,7 +118,7 @@ class BatchFilter {
 };
 
 // steps per chunk of the dynamically scheduled batched launch (0: one CTA per θ-particle for the whole series); host-only
-int64_t plan_batch_chunk(int64_t M, int64_t N, int64_t steps, int threads, int64_t slots, int num_sms);
+int64_t plan_batch_chunk(int64_t M, int64_t N, int64_t steps, int threads, int64_t slots, int num_sms, bool masked);
 
 // kalman_filter / log_likelihood(y, model) for M LG1D models (kalman_filter.jl:29-70).
 // use_state: start from x/sigma given by the caller (one-step API); else from (x0, σ0) of params.

@@ -525,9 +525,9 @@ int smcb_comm_destroy(smcb_ctx* ctx) {
   return SMCB_OK;
 }
 
-int smcb_batch_chunk_plan(int64_t M, int64_t N, int64_t steps, int threads, int64_t slots, int num_sms, int64_t* chunk) {
+int smcb_batch_chunk_plan(int64_t M, int64_t N, int64_t steps, int threads, int64_t slots, int num_sms, int masked, int64_t* chunk) {
   if (!chunk || M < 1 || N < 1 || steps < 1 || threads < 1) return SMCB_ERR_BAD_ARG;
-  *chunk = smcb::plan_batch_chunk(M, N, steps, threads, slots, num_sms);
+  *chunk = smcb::plan_batch_chunk(M, N, steps, threads, slots, num_sms, masked != 0);
   return SMCB_OK;
 }
 

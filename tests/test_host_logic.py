@@ -517,6 +517,12 @@ def test_batch_chunk_plan_of_the_library():
     assert plan(1024, 2048, 499, 512, 296) > 0
     # config 3 on one GPU: all 512 CTAs (256 threads) resident, 3 or 4 to an SM whose warps are saturated
     assert plan(512, 1024, 99, 256, 592) > 0
+    # a sweep with an `active` mask over more θ than resident CTAs is always chunked (the number of θ that run is known only on the
+    # device): the rejuvenation sweeps of config 5 at 1, 2, 4 GPUs; without a mask, or with every CTA resident, the rule above holds
+    for M in (4096, 2048, 1024):
+        k = plan(M, 4096, 240, 1024, 148, masked=True)
+        assert 8 <= k < 240
+    assert plan(148, 4096, 240, 1024, 148, masked=True) == 0 and plan(512, 4096, 12, 1024, 148, masked=True) == 0
     # every θ has an SM to itself; a short series; small clouds that do not saturate an SM; a single step
     assert plan(148, 4096, 240, 1024, 148) == 0 and plan(64, 1024, 99, 512, 296) == 0
     assert plan(512, 4096, 12, 1024, 148) == 0
