@@ -1228,86 +1228,96 @@ void BatchFilter::pack(const int32_t* slots, int64_t n, void* buf_dev, bool to_b
 }
 
 // ------------------------------------------------------------------------------------------------
-void kalman_batch(int device, cudaStream_t stream, const double* params, const uint8_t* active, int64_t M,
+void* DeviceScratch::get(size_t bytes) {
+  if (cap < bytes) {
+    cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    SMCB_CUDA_TRY(cudaMalloc(&p, bytes));
+    cap = bytes;
+  }
+  return p;
+}
+DeviceScratch::~DeviceScratch() { cudaFree(p); }
+
+namespace {
+// carve 256-byte aligned pieces out of one scratch allocation
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* b) : base(static_cast<char*>(b)) {}
+  static size_t up(size_t n) { return (n + 255) & ~size_t(255); }
+  template <class T>
+  T* take(size_t n) {
+    T* r = reinterpret_cast<T*>(base + off);
+    off += up(sizeof(T) * n);
+    return r;
+  }
+};
+}  // namespace
+
+void kalman_batch(int device, cudaStream_t stream, DeviceScratch& scratch, const double* params, const uint8_t* active, int64_t M,
                   const double* y, int64_t T, bool predict_first, double* loglik, double* x, double* sigma,
                   bool use_state) {
   SMCB_CUDA_TRY(cudaSetDevice(device));
-  double *dp = nullptr, *dy = nullptr, *dl = nullptr, *dx = nullptr, *ds = nullptr;
-  uint8_t* da = nullptr;
-  auto cleanup = [&] { cudaFree(dp); cudaFree(dy); cudaFree(dl); cudaFree(dx); cudaFree(ds); cudaFree(da); };
-  try {
-    SMCB_CUDA_TRY(cudaMalloc(&dp, sizeof(double) * M * kParamStride));
-    SMCB_CUDA_TRY(cudaMalloc(&dy, sizeof(double) * T));
-    SMCB_CUDA_TRY(cudaMalloc(&dl, sizeof(double) * M));
-    SMCB_CUDA_TRY(cudaMalloc(&dx, sizeof(double) * M));
-    SMCB_CUDA_TRY(cudaMalloc(&ds, sizeof(double) * M));
-    SMCB_CUDA_TRY(cudaMemcpyAsync(dp, params, sizeof(double) * M * kParamStride, cudaMemcpyHostToDevice, stream));
-    SMCB_CUDA_TRY(cudaMemcpyAsync(dy, y, sizeof(double) * T, cudaMemcpyHostToDevice, stream));
-    if (active) {
-      SMCB_CUDA_TRY(cudaMalloc(&da, M));
-      SMCB_CUDA_TRY(cudaMemcpyAsync(da, active, M, cudaMemcpyHostToDevice, stream));
-    }
-    if (use_state) {
-      SMCB_CUDA_TRY(cudaMemcpyAsync(dx, x, sizeof(double) * M, cudaMemcpyHostToDevice, stream));
-      SMCB_CUDA_TRY(cudaMemcpyAsync(ds, sigma, sizeof(double) * M, cudaMemcpyHostToDevice, stream));
-    }
-    kalman_kernel<<<(unsigned)((M + 127) / 128), 128, 0, stream>>>(dp, da, M, dy, T, predict_first ? 1 : 0, dl, dx, ds,
-                                                                   use_state ? 1 : 0);
-    SMCB_CUDA_TRY(cudaGetLastError());
-    SMCB_CUDA_TRY(cudaMemcpyAsync(loglik, dl, sizeof(double) * M, cudaMemcpyDeviceToHost, stream));
-    if (x) SMCB_CUDA_TRY(cudaMemcpyAsync(x, dx, sizeof(double) * M, cudaMemcpyDeviceToHost, stream));
-    if (sigma) SMCB_CUDA_TRY(cudaMemcpyAsync(sigma, ds, sizeof(double) * M, cudaMemcpyDeviceToHost, stream));
-    SMCB_CUDA_TRY(cudaStreamSynchronize(stream));
-  } catch (...) {
-    cleanup();
-    throw;
+  const size_t total = Carver::up(sizeof(double) * M * kParamStride) + Carver::up(sizeof(double) * T) + 3 * Carver::up(sizeof(double) * M) + Carver::up((size_t)M);
+  Carver c(scratch.get(total));
+  double* dp = c.take<double>((size_t)M * kParamStride);
+  double* dy = c.take<double>((size_t)T);
+  double* dl = c.take<double>((size_t)M);
+  double* dx = c.take<double>((size_t)M);
+  double* ds = c.take<double>((size_t)M);
+  uint8_t* da = active ? c.take<uint8_t>((size_t)M) : nullptr;
+  SMCB_CUDA_TRY(cudaMemcpyAsync(dp, params, sizeof(double) * M * kParamStride, cudaMemcpyHostToDevice, stream));
+  SMCB_CUDA_TRY(cudaMemcpyAsync(dy, y, sizeof(double) * T, cudaMemcpyHostToDevice, stream));
+  if (active) SMCB_CUDA_TRY(cudaMemcpyAsync(da, active, M, cudaMemcpyHostToDevice, stream));
+  if (use_state) {
+    SMCB_CUDA_TRY(cudaMemcpyAsync(dx, x, sizeof(double) * M, cudaMemcpyHostToDevice, stream));
+    SMCB_CUDA_TRY(cudaMemcpyAsync(ds, sigma, sizeof(double) * M, cudaMemcpyHostToDevice, stream));
   }
-  cleanup();
+  kalman_kernel<<<(unsigned)((M + 127) / 128), 128, 0, stream>>>(dp, da, M, dy, T, predict_first ? 1 : 0, dl, dx, ds, use_state ? 1 : 0);
+  SMCB_CUDA_TRY(cudaGetLastError());
+  SMCB_CUDA_TRY(cudaMemcpyAsync(loglik, dl, sizeof(double) * M, cudaMemcpyDeviceToHost, stream));
+  if (x) SMCB_CUDA_TRY(cudaMemcpyAsync(x, dx, sizeof(double) * M, cudaMemcpyDeviceToHost, stream));
+  if (sigma) SMCB_CUDA_TRY(cudaMemcpyAsync(sigma, ds, sizeof(double) * M, cudaMemcpyDeviceToHost, stream));
+  SMCB_CUDA_TRY(cudaStreamSynchronize(stream));
 }
 
-void kalman_mv_batch(int device, cudaStream_t stream, int d, const double* models, const uint8_t* active, int64_t M,
+void kalman_mv_batch(int device, cudaStream_t stream, DeviceScratch& scratch, int d, const double* models, const uint8_t* active, int64_t M,
                      const double* y, int64_t T, bool predict_first, double* loglik, double* x, double* sigma,
                      bool use_state) {
   if (d < 1 || d > 4) throw Error{SMCB_ERR_UNSUPPORTED, "matrix Kalman filter: state dimension must be in [1, 4]"};
   SMCB_CUDA_TRY(cudaSetDevice(device));
   const int64_t stride = 3 * d * d + 2 * d + 1;
-  double *dp = nullptr, *dy = nullptr, *dl = nullptr, *dx = nullptr, *ds = nullptr;
-  uint8_t* da = nullptr;
-  auto cleanup = [&] { cudaFree(dp); cudaFree(dy); cudaFree(dl); cudaFree(dx); cudaFree(ds); cudaFree(da); };
-  try {
-    SMCB_CUDA_TRY(cudaMalloc(&dp, sizeof(double) * M * stride));
-    SMCB_CUDA_TRY(cudaMalloc(&dy, sizeof(double) * T));
-    SMCB_CUDA_TRY(cudaMalloc(&dl, sizeof(double) * M));
-    SMCB_CUDA_TRY(cudaMalloc(&dx, sizeof(double) * M * d));
-    SMCB_CUDA_TRY(cudaMalloc(&ds, sizeof(double) * M * d * d));
-    SMCB_CUDA_TRY(cudaMemcpyAsync(dp, models, sizeof(double) * M * stride, cudaMemcpyHostToDevice, stream));
-    SMCB_CUDA_TRY(cudaMemcpyAsync(dy, y, sizeof(double) * T, cudaMemcpyHostToDevice, stream));
-    if (active) {
-      SMCB_CUDA_TRY(cudaMalloc(&da, M));
-      SMCB_CUDA_TRY(cudaMemcpyAsync(da, active, M, cudaMemcpyHostToDevice, stream));
-    }
-    if (use_state) {
-      SMCB_CUDA_TRY(cudaMemcpyAsync(dx, x, sizeof(double) * M * d, cudaMemcpyHostToDevice, stream));
-      SMCB_CUDA_TRY(cudaMemcpyAsync(ds, sigma, sizeof(double) * M * d * d, cudaMemcpyHostToDevice, stream));
-    }
-    const unsigned grid = (unsigned)((M + 127) / 128);
-    const int pf = predict_first ? 1 : 0, us = use_state ? 1 : 0;
-    switch (d) {
-      case 1: kalman_mv_kernel<1><<<grid, 128, 0, stream>>>(dp, da, M, dy, T, pf, dl, dx, ds, us); break;
-      case 2: kalman_mv_kernel<2><<<grid, 128, 0, stream>>>(dp, da, M, dy, T, pf, dl, dx, ds, us); break;
-      case 3: kalman_mv_kernel<3><<<grid, 128, 0, stream>>>(dp, da, M, dy, T, pf, dl, dx, ds, us); break;
-      default: kalman_mv_kernel<4><<<grid, 128, 0, stream>>>(dp, da, M, dy, T, pf, dl, dx, ds, us); break;
-    }
-    SMCB_CUDA_TRY(cudaGetLastError());
-    SMCB_CUDA_TRY(cudaMemcpyAsync(loglik, dl, sizeof(double) * M, cudaMemcpyDeviceToHost, stream));
-    if (x) SMCB_CUDA_TRY(cudaMemcpyAsync(x, dx, sizeof(double) * M * d, cudaMemcpyDeviceToHost, stream));
-    if (sigma) SMCB_CUDA_TRY(cudaMemcpyAsync(sigma, ds, sizeof(double) * M * d * d, cudaMemcpyDeviceToHost, stream));
-    SMCB_CUDA_TRY(cudaStreamSynchronize(stream));
-  } catch (...) {
-    cleanup();
-    throw;
+  const size_t total = Carver::up(sizeof(double) * M * stride) + Carver::up(sizeof(double) * T) + Carver::up(sizeof(double) * M) +
+                       Carver::up(sizeof(double) * M * d) + Carver::up(sizeof(double) * M * d * d) + Carver::up((size_t)M);
+  Carver c(scratch.get(total));
+  double* dp = c.take<double>((size_t)(M * stride));
+  double* dy = c.take<double>((size_t)T);
+  double* dl = c.take<double>((size_t)M);
+  double* dx = c.take<double>((size_t)(M * d));
+  double* ds = c.take<double>((size_t)(M * d * d));
+  uint8_t* da = active ? c.take<uint8_t>((size_t)M) : nullptr;
+  SMCB_CUDA_TRY(cudaMemcpyAsync(dp, models, sizeof(double) * M * stride, cudaMemcpyHostToDevice, stream));
+  SMCB_CUDA_TRY(cudaMemcpyAsync(dy, y, sizeof(double) * T, cudaMemcpyHostToDevice, stream));
+  if (active) SMCB_CUDA_TRY(cudaMemcpyAsync(da, active, M, cudaMemcpyHostToDevice, stream));
+  if (use_state) {
+    SMCB_CUDA_TRY(cudaMemcpyAsync(dx, x, sizeof(double) * M * d, cudaMemcpyHostToDevice, stream));
+    SMCB_CUDA_TRY(cudaMemcpyAsync(ds, sigma, sizeof(double) * M * d * d, cudaMemcpyHostToDevice, stream));
   }
-  cleanup();
+  const unsigned grid = (unsigned)((M + 127) / 128);
+  const int pf = predict_first ? 1 : 0, us = use_state ? 1 : 0;
+  switch (d) {
+    case 1: kalman_mv_kernel<1><<<grid, 128, 0, stream>>>(dp, da, M, dy, T, pf, dl, dx, ds, us); break;
+    case 2: kalman_mv_kernel<2><<<grid, 128, 0, stream>>>(dp, da, M, dy, T, pf, dl, dx, ds, us); break;
+    case 3: kalman_mv_kernel<3><<<grid, 128, 0, stream>>>(dp, da, M, dy, T, pf, dl, dx, ds, us); break;
+    default: kalman_mv_kernel<4><<<grid, 128, 0, stream>>>(dp, da, M, dy, T, pf, dl, dx, ds, us); break;
+  }
+  SMCB_CUDA_TRY(cudaGetLastError());
+  SMCB_CUDA_TRY(cudaMemcpyAsync(loglik, dl, sizeof(double) * M, cudaMemcpyDeviceToHost, stream));
+  if (x) SMCB_CUDA_TRY(cudaMemcpyAsync(x, dx, sizeof(double) * M * d, cudaMemcpyDeviceToHost, stream));
+  if (sigma) SMCB_CUDA_TRY(cudaMemcpyAsync(sigma, ds, sizeof(double) * M * d * d, cudaMemcpyDeviceToHost, stream));
+  SMCB_CUDA_TRY(cudaStreamSynchronize(stream));
 }
 
 }  // namespace smcb

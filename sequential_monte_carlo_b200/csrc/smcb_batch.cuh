@@ -120,9 +120,18 @@ class BatchFilter {
 // steps per chunk of the dynamically scheduled batched launch (0: one CTA per θ-particle for the whole series); host-only
 int64_t plan_batch_chunk(int64_t M, int64_t N, int64_t steps, int threads, int64_t slots, int num_sms, bool masked);
 
+// grow-only device scratch of the Kalman entry points (owned by the context: IBIS calls them once per observation, and a
+// cudaMalloc / cudaFree per call is a driver round trip that takes process-wide locks)
+struct DeviceScratch {
+  void* p = nullptr;
+  size_t cap = 0;
+  void* get(size_t bytes);   // >= bytes, 256-byte aligned; contents are not preserved across calls
+  ~DeviceScratch();
+};
+
 // kalman_filter / log_likelihood(y, model) for M LG1D models (kalman_filter.jl:29-70).
 // use_state: start from x/sigma given by the caller (one-step API); else from (x0, σ0) of params.
-void kalman_batch(int device, cudaStream_t stream, const double* params, const uint8_t* active, int64_t M,
+void kalman_batch(int device, cudaStream_t stream, DeviceScratch& scratch, const double* params, const uint8_t* active, int64_t M,
                   const double* y, int64_t T, bool predict_first, double* loglik, double* x, double* sigma,
                   bool use_state);
 
@@ -130,7 +139,7 @@ void kalman_batch(int device, cudaStream_t stream, const double* params, const u
 // kalman_filter / log_likelihood(y, model) for M multivariate LinearModels with a scalar observation
 // (MultivariateLinearGaussian, hodrick_prescott: state_space_models.jl:137-202; kalman_filter.jl:3-27,55-70).
 // models: [M][3d² + 2d + 1] = A[d][d], B[d], Q[d][d], R, x0[d], Σ0[d][d] row-major; x: [M][d], sigma: [M][d][d].
-void kalman_mv_batch(int device, cudaStream_t stream, int d, const double* models, const uint8_t* active, int64_t M,
+void kalman_mv_batch(int device, cudaStream_t stream, DeviceScratch& scratch, int d, const double* models, const uint8_t* active, int64_t M,
                      const double* y, int64_t T, bool predict_first, double* loglik, double* x, double* sigma,
                      bool use_state);
 

@@ -25,6 +25,7 @@ struct smcb_ctx {
   std::unique_ptr<SingleFilter> scratch;  // normalize / resample utilities
   std::vector<StepStats> stats;
   Comm comm;                              // θ-sharding across GPUs (smcb_comm_init); nranks == 1 without it
+  DeviceScratch kalman_scratch;           // device staging of the Kalman entry points, kept across calls
   double* comm_buf = nullptr;             // device staging of smcb_comm_all_gather
   int64_t comm_buf_cap = 0;
   RngKey key(uint32_t epoch) const { return make_rng_key((uint32_t)seed, (uint32_t)(seed >> 32), epoch & 0xFFFFFFu); }
@@ -639,7 +640,7 @@ int smcb_kalman_batch_step(smcb_ctx* ctx, const double* params, int64_t M, doubl
   if (!ctx) return SMCB_ERR_BAD_ARG;
   return guarded(ctx, [&] {
     need(params && x && sigma && loglik && M >= 1, "kalman_batch_step: bad arguments");
-    kalman_batch(ctx->device, ctx->stream, params, nullptr, M, &y, 1, /*predict_first=*/true, loglik, x, sigma,
+    kalman_batch(ctx->device, ctx->stream, ctx->kalman_scratch, params, nullptr, M, &y, 1, /*predict_first=*/true, loglik, x, sigma,
                  /*use_state=*/true);
   });
 }
@@ -649,7 +650,7 @@ int smcb_kalman_batch_loglik(smcb_ctx* ctx, const double* params, const uint8_t*
   if (!ctx) return SMCB_ERR_BAD_ARG;
   return guarded(ctx, [&] {
     need(params && y && loglik && M >= 1 && T >= 1, "kalman_batch_loglik: bad arguments");
-    kalman_batch(ctx->device, ctx->stream, params, active, M, y, T, /*predict_first=*/!matched_init, loglik, x, sigma,
+    kalman_batch(ctx->device, ctx->stream, ctx->kalman_scratch, params, active, M, y, T, /*predict_first=*/!matched_init, loglik, x, sigma,
                  /*use_state=*/false);
   });
 }
@@ -659,7 +660,7 @@ int smcb_kalman_mv_batch_step(smcb_ctx* ctx, int d, const double* models, int64_
   if (!ctx) return SMCB_ERR_BAD_ARG;
   return guarded(ctx, [&] {
     need(models && x && sigma && loglik && M >= 1, "kalman_mv_batch_step: bad arguments");
-    kalman_mv_batch(ctx->device, ctx->stream, d, models, nullptr, M, &y, 1, /*predict_first=*/true, loglik, x, sigma,
+    kalman_mv_batch(ctx->device, ctx->stream, ctx->kalman_scratch, d, models, nullptr, M, &y, 1, /*predict_first=*/true, loglik, x, sigma,
                     /*use_state=*/true);
   });
 }
@@ -669,7 +670,7 @@ int smcb_kalman_mv_batch_loglik(smcb_ctx* ctx, int d, const double* models, cons
   if (!ctx) return SMCB_ERR_BAD_ARG;
   return guarded(ctx, [&] {
     need(models && y && loglik && M >= 1 && T >= 1, "kalman_mv_batch_loglik: bad arguments");
-    kalman_mv_batch(ctx->device, ctx->stream, d, models, active, M, y, T, /*predict_first=*/!matched_init, loglik, x, sigma,
+    kalman_mv_batch(ctx->device, ctx->stream, ctx->kalman_scratch, d, models, active, M, y, T, /*predict_first=*/!matched_init, loglik, x, sigma,
                     /*use_state=*/false);
   });
 }
