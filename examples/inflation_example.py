@@ -4,7 +4,7 @@
      and after every observation the ω-mixture of the per-θ quartile bands of the trend and the cycle and the variance
      of the trend (`get_quantiles_uc`, :39-55) — computed on the device, no cloud is read back;
   2. a particle filter at the posterior mean (`get_latent_states_uc`, :145-172) through `particle_filter` /
-     `particle_filter!` — bootstrap as in the reference, or guided by the locally optimal proposal;
+     `particle_filter!` — bootstrap as in the reference, or guided (UC: the locally optimal proposal; UC-SV: the optimal trend move);
   3. the UC-SV model `ucsv_mod(θ) = StateSpaceModel(UCSV(θ[1],θ[2],(θ[3],θ[4])), (3,1))` with `ucsv_prior` (:229-253).
 
 The reference downloads the PCE inflation series from FRED (:12-19); there is no network here, so the series is
@@ -68,9 +68,10 @@ def get_latent_states(N, y, model, proposal=None, *, ctx=None):
     for t in range(T):
         if t > 0:
             _, w, _ = smc.particle_filter_(x, w, y[t], model, proposal, resampler="systematic")
-        xq[t] = smc.quantile(x, w, QUARTILES)
-        cq[t] = y[t] - smc.quantile(x, w, [1 - p for p in QUARTILES])      # quantile(y[t] .- x, p) = y[t] - quantile(x, 1-p)
-        variances[t] = smc.weighted_mean_var(x, w)[1]
+        q, qc = np.asarray(smc.quantile(x, w, QUARTILES)), np.asarray(smc.quantile(x, w, [1 - p for p in QUARTILES]))
+        xq[t] = q if q.ndim == 1 else q[:, 0]                               # UCSV: the trend is the first state component
+        cq[t] = y[t] - (qc if qc.ndim == 1 else qc[:, 0])                   # quantile(y[t] .- x, p) = y[t] - quantile(x, 1-p)
+        variances[t] = np.ravel(smc.weighted_mean_var(x, w)[1])[0]
     return xq, cq, variances
 
 
@@ -95,6 +96,10 @@ def main():
     ucsv, xqs, cqs, _ = run_smc2(ucsv_mod, ucsv_prior, y, args.N, args.M, 3)
     print("UCSV E[θ] = (γ, x0, log σε, log ση) =", np.round(smc.expected_parameters(ucsv).ravel(), 3), " ess =", round(ucsv.ess, 1))
     print("     trend quartiles at T:", np.round(xqs[-1], 3), " cycle quartiles at T:", np.round(cqs[-1], 3))
+    pred_sv = ucsv_mod(smc.expected_parameters(ucsv).ravel())                                  # get_latent_states_ucsv  :241-260
+    for name, proposal in (("bootstrap", None), ("guided: optimal trend move, docs/SPEC.md §10b", smc.UCSVTrendProposal(1.0))):
+        xq, _, _ = get_latent_states(args.N, y, pred_sv, proposal)
+        print(f"     particle filter at E[θ] ({name}): trend quartiles at T:", np.round(xq[-1], 3))
 
 
 if __name__ == "__main__":
