@@ -16,6 +16,11 @@ def build_sampler(smc, which, ctx, comm, engine="device"):
         model = lambda θ: smc.StateSpaceModel(smc.LinearGaussian(θ[0], 1.0, θ[1], θ[2], 0.0), (1, 1))
         y = smc.simulate(model([0.5, 0.9, 0.8]), 40, seed=1998)[1]
         return smc.SMC(256, 64, model, pg, 3, 0.5, seed=11, resampler="systematic", ctx=ctx, comm=comm, engine=engine), y, "smc2"
+    if which == "lg_dyn":     # more θ per GPU than resident CTAs (592 of 256 threads): the rejuvenation sweeps are dynamically scheduled
+        pg = smc.product_distribution([smc.TruncatedNormal(0, 1, -1, 1), smc.LogNormal(), smc.LogNormal()])
+        model = lambda θ: smc.StateSpaceModel(smc.LinearGaussian(θ[0], 1.0, θ[1], θ[2], 0.0), (1, 1))
+        y = smc.simulate(model([0.5, 0.9, 0.8]), 48, seed=1998)[1]
+        return smc.SMC(1024, 1400, model, pg, 2, 0.5, seed=5, resampler="systematic", ctx=ctx, comm=comm, engine=engine), y, "smc2"
     if which == "ucsv":
         pg = smc.product_distribution([smc.Uniform(0, 1), smc.Normal(3, 2), smc.Uniform(0, 2), smc.Uniform(0, 2)])
         model = lambda θ: smc.StateSpaceModel(smc.UCSV(θ[0], θ[1], (θ[2], θ[3])), (3, 1))

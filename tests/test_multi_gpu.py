@@ -20,7 +20,7 @@ def _gpu_count():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("which", ["lg", "ucsv", "sv_dt"])
+@pytest.mark.parametrize("which", ["lg", "ucsv", "sv_dt", "lg_dyn"])
 def test_two_nccl_ranks_equal_one_rank(ctx, which, tmp_path):
     if _gpu_count() < 2:
         pytest.skip("needs 2 GPUs")

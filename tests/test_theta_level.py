@@ -357,6 +357,33 @@ def test_ibis(ctx, oracle):
         smc.IBIS(8, lambda θ: smc.SV(θ[0], θ[1], θ[2]), pg, 1, 0.5, ctx=ctx)
 
 
+@pytest.mark.parametrize("which", ["lg_dyn", "ucsv_dyn"])
+def test_device_sampler_with_dynamic_scheduling_equals_static(ctx, which, monkeypatch):
+    """whole sampler runs whose rejuvenation sweeps are cut into dynamically scheduled (chunk, θ) units (more θ than resident CTAs,
+    some proposals inactive) against the same runs with one CTA per θ (SMCB_BATCH_CHUNK=0): θ, ω, logZ and every cloud bit for bit"""
+    from tests.dist_worker import build_sampler, run
+    out = {}
+    for mode in ("0", None):
+        if mode is None:
+            monkeypatch.delenv("SMCB_BATCH_CHUNK", raising=False)
+        else:
+            monkeypatch.setenv("SMCB_BATCH_CHUNK", mode)
+        if which == "lg_dyn":
+            s, y, algo = build_sampler(smc, "lg_dyn", ctx, None)
+        else:
+            pg = smc.product_distribution([smc.Uniform(0, 1), smc.Normal(3, 2), smc.Uniform(0, 2), smc.Uniform(0, 2)])
+            model = lambda θ: smc.StateSpaceModel(smc.UCSV(θ[0], θ[1], (θ[2], θ[3])), (3, 1))      # noqa: E731
+            y = smc.simulate(model([0.2, 3.0, 1.0, 1.0]), 40, seed=1998)[1]
+            s, algo = smc.SMC(4096, 300, model, pg, 2, 0.5, seed=3, resampler="systematic", ctx=ctx, engine="device"), "smc2"
+        rejuv = run(smc, s, y, algo)
+        out[mode] = (np.array(rejuv), s.θ.copy(), s.ω.copy(), s.logZ.copy(), np.array(s.x), np.array(s.w))
+        s.close()
+    monkeypatch.delenv("SMCB_BATCH_CHUNK", raising=False)
+    assert len(out["0"][0]) >= 2 and out["0"][0].max() >= 16          # at least one rejuvenation long enough to be chunked
+    for a, b in zip(out["0"], out[None]):
+        np.testing.assert_array_equal(a, b)
+
+
 def test_reference_docstring_trace_is_a_plausible_draw(ctx):
     """The only output the reference records for this path (smc_samplers.jl:207-219; README.md:88-91): density_tempered with
     512 θ-particles × 1024 state particles, chain 3, ESS 0.5 on lg_mod — six stages ξ = 0.00825, 0.03895, 0.11587, 0.27741,
