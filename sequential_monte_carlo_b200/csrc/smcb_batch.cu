@@ -89,6 +89,7 @@ __device__ __forceinline__ void batch_unit(const BatchArgs& a, const int64_t m, 
                                            const bool carry, unsigned char* smem_raw, unsigned long long (*s_wq)[32], double (*s_f)[32]) {
   constexpr int D = Model::D;
   static_assert(!GUIDED || D == 1 || Model::KIND == KIND_UCSV, "guided proposals: affine-Gaussian for D = 1 (SPEC §10), the tempered trend move for UCSV (§10b)");
+  __shared__ unsigned long long s_sys;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nthreads = blockDim.x, nwarps = nthreads >> 5;
   if (a.active && !a.active[m]) {
@@ -184,7 +185,7 @@ __device__ __forceinline__ void batch_unit(const BatchArgs& a, const int64_t m, 
       }
       // ---- normalize(previous logw) and its fixed-point CDF                         particles.jl:5-15,117
       unsigned long long q0[PAIRS], tq[PAIRS], winc[PAIRS];
-      double se = 0.0, se2 = 0.0;
+      double se = 0.0;  // (Σe² is only needed for the ess of the LAST step of the launch: the final normalisation below computes it)
 #pragma unroll
       for (int r = 0; r < PAIRS; ++r) {
         double e0 = 0.0, e1 = 0.0;
@@ -192,19 +193,18 @@ __device__ __forceinline__ void batch_unit(const BatchArgs& a, const int64_t m, 
         const int i = 2 * (r * nthreads + tid);
         if (i < N) det_exp_quant(lw[r][0] - mx, a.S, e0, qa);
         if (i + 1 < N) det_exp_quant(lw[r][1] - mx, a.S, e1, qb);
-        se += e0; se2 += e0 * e0;
-        se += e1; se2 += e1 * e1;
+        se += e0;
+        se += e1;
         q0[r] = qa;
         tq[r] = qa + qb;
         winc[r] = warp_scan_u64(tq[r], lane);
         if (lane == 31) s_wq[r][warp] = winc[r];
       }
       se = warp_sum(se);
-      se2 = warp_sum(se2);
-      if (lane == 0) {
-        s_f[0][warp] = se;
-        s_f[1][warp] = se2;
-      }
+      if (lane == 0) s_f[0][warp] = se;
+      // the one uniform of the systematic resampler (SPEC §5): a Philox block for thread 0, not for every thread of the CTA
+      if (tid == 0 && a.resampler == RESAMPLE_SYSTEMATIC)
+        s_sys = mulhi64(uniform64_at(a.key, 0u, stream, t, PURPOSE_RESAMPLE), a.R);
       __syncthreads();  // A
       unsigned long long segbase = 0;
 #pragma unroll
@@ -222,19 +222,15 @@ __device__ __forceinline__ void batch_unit(const BatchArgs& a, const int64_t m, 
         segbase += segtot;
       }
       const unsigned long long Q = segbase;
-      {
-        double e1 = (lane < nwarps) ? s_f[0][lane] : 0.0, e2 = (lane < nwarps) ? s_f[1][lane] : 0.0;
+      if (warp == 0) {  // logμ of the previous step (particles.jl:10): thread 0 carries Σ logμ, nobody else needs it
+        double e1 = (lane < nwarps) ? s_f[0][lane] : 0.0;
         e1 = warp_sum(e1);
-        e2 = warp_sum(e2);
-        if (account) logz += mx + log(e1) - logN;  // logμ of the previous step           particles.jl:10
-        account = true;
-        (void)e2;
+        if (account && tid == 0) logz += mx + log(e1) - logN;
       }
+      account = true;
       __syncthreads();  // B: CDF complete
       // ---- a = resample(w); xp = x[a]                                                particles.jl:117-119
-      uint64_t sys_off = 0;
-      if (a.resampler == RESAMPLE_SYSTEMATIC)
-        sys_off = mulhi64(uniform64_at(a.key, 0u, stream, t, PURPOSE_RESAMPLE), a.R);
+      const uint64_t sys_off = (a.resampler == RESAMPLE_SYSTEMATIC) ? s_sys : 0ull;
       double xpa[PAIRS][D], xpb[PAIRS][D];
 #pragma unroll
       for (int r = 0; r < PAIRS; ++r) {
@@ -335,7 +331,7 @@ __device__ __forceinline__ void batch_unit(const BatchArgs& a, const int64_t m, 
     double e1 = (lane < nwarps) ? s_f[0][lane] : 0.0, e2 = (lane < nwarps) ? s_f[1][lane] : 0.0;
     e1 = warp_sum(e1);
     e2 = warp_sum(e2);
-    if (account) logz += mx + log(e1) - logN;
+    if (account && tid == 0) logz += mx + log(e1) - logN;
     if (tid == 0) {
       a.stats[m].mx = mx;
       a.stats[m].sum = e1;
