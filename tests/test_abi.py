@@ -116,3 +116,62 @@ def test_bench_reference_arm_contract():
     assert d["config"]["N"] == 1 << 24 and d["config"]["T"] == 1000 and "workload" in d["config"]
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1 and d["cpu_baseline"]["value"] == d["value"] > 1e5
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_julia_shim_ccalls_match_the_header():
+    """julia/SequentialMonteCarloB200.jl cannot be executed here (no Julia in the image), so its bindings are checked statically:
+    every `ccall((:smcb_…, LIB), Ret, (ArgTypes…), …)` names a function the header declares, passes as many argument types as the
+    prototype has parameters, and each type is of the class of the C parameter (Float64 ↔ double, Cint ↔ int, Int64 ↔ int64_t,
+    UInt32 / UInt64 ↔ uint32_t / uint64_t, Ptr / Ref / arrays ↔ pointers)."""
+    import re
+    hdr = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "smcb200.h")).read(), flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|const char\s*\*|int64_t|void|double)\s+(smcb_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        args = m.group(2).strip()
+        protos[m.group(1)] = [] if args in ("", "void") else [a.strip() for a in args.split(",")]
+    assert len(protos) >= 70
+
+    def c_class(p):
+        if "*" in p or "[" in p:
+            return "ptr"
+        for t, k in (("double", "f64"), ("uint64_t", "u64"), ("uint32_t", "u32"), ("int64_t", "i64"), ("int", "i32")):
+            if re.search(r"\b" + t + r"\b", p):
+                return k
+        raise AssertionError("unclassified C parameter: " + p)
+
+    def jl_class(t):
+        t = t.strip()
+        if t.startswith(("Ptr{", "Ref{")) or t in ("Cstring",):
+            return "ptr"
+        return {"Float64": "f64", "Cdouble": "f64", "UInt64": "u64", "UInt32": "u32", "Int64": "i64", "Clonglong": "i64", "Cint": "i32", "Int32": "i32"}[t]
+
+    jl = open(os.path.join(ROOT, "julia", "SequentialMonteCarloB200.jl")).read()
+    seen, pos = set(), 0
+    while True:
+        k = jl.find("ccall((:", pos)
+        if k < 0:
+            break
+        pos = k + 6
+        m = re.match(r"ccall\(\(:(smcb_[a-z0-9_]+),\s*LIB\),\s*([A-Za-z0-9{}\. ]+?),\s*\(", jl[k:])
+        assert m, jl[k:k + 80]
+        name, start, depth = m.group(1), k + m.end() - 1, 0
+        for j in range(start, len(jl)):
+            depth += (jl[j] == "(") - (jl[j] == ")")
+            if depth == 0:
+                break
+        parts, d, cur = [], 0, ""
+        for ch in jl[start + 1:j]:
+            d += (ch in "({[") - (ch in ")}]")
+            if ch == "," and d == 0:
+                parts.append(cur.strip())
+                cur = ""
+            else:
+                cur += ch
+        if cur.strip():
+            parts.append(cur.strip())
+        assert name in protos, name + " is not declared in include/smcb200.h"
+        assert len(parts) == len(protos[name]), (name, protos[name], parts)
+        for cp, jt in zip(protos[name], parts):
+            assert c_class(cp) == jl_class(jt), (name, cp, jt)
+        seen.add(name)
+    assert len(seen) >= 35            # the shim binds the filter, batch, Kalman, sampler, communicator and host-only entry points
