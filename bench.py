@@ -155,13 +155,18 @@ def cpu_rejuvenation_sample(N=1024, T=100, seconds=8.0):
     while True:                                    # grow the sample until it runs for about `seconds`
         Pm = np.tile(P[:1], (M, 1))
         t0 = time.perf_counter()
-        o.batch_log_likelihood(0, Pm, None, N, y, o.MULTINOMIAL, 1998, 0, 0, want_state=False)
+        o.reference_style_batch(0, Pm, N, y, 1998)
         t1 = time.perf_counter() - t0
         if t1 > seconds / 4 or M >= 4096:
             break
         M *= 4
+    t0 = time.perf_counter()
+    o.batch_log_likelihood(0, Pm, None, N, y, o.MULTINOMIAL, 1998, 0, 0, want_state=False)
+    t2 = time.perf_counter() - t0
     return {"value": M * N * T / t1, "unit": "particle-updates/s", "cores": threads, "kind": "port",
-            "sample": f"one rejuvenation sweep: {M} theta x {N} particles x T={T}, multinomial, oracle/smc_oracle.c OpenMP over theta"}
+            "sample": f"one rejuvenation sweep: {M} theta x {N} particles x T={T}, reference-style filters (alias-table multinomial, allocations per step), "
+                      "oracle/smc_oracle.c OpenMP over theta",
+            "parity_oracle_value": M * N * T / t2}
 
 
 def cpu_sharded_sample(seconds=10.0):
@@ -178,13 +183,13 @@ def cpu_sharded_sample(seconds=10.0):
     while True:
         Pm = np.tile(P[None, :], (M, 1))
         t0 = time.perf_counter()
-        o.batch_log_likelihood(2, Pm, None, N, y, o.MULTINOMIAL, DATA_SEED, 0, 0, want_state=False)
+        o.reference_style_batch(2, Pm, N, y, DATA_SEED)      # the reference-style port, as at N = 1
         t1 = time.perf_counter() - t0
         if t1 > seconds / 4 or M >= 4096:
             break
         M *= 4
-    return M * N * T / t1, threads, f"one rejuvenation sweep of configs[4]'s inner filters: {M} theta x {N} particles x T={T}, UCSV, multinomial, " \
-                                    f"oracle/smc_oracle.c OpenMP over theta ({threads} threads)"
+    return M * N * T / t1, threads, f"one rejuvenation sweep of configs[4]'s inner filters: {M} theta x {N} particles x T={T}, UCSV, reference-style filters " \
+                                    f"(alias-table multinomial, allocations per step), oracle/smc_oracle.c OpenMP over theta ({threads} threads)"
 
 
 def run_reference(args, rank):

@@ -345,6 +345,19 @@ def reference_style_log_likelihood(params, n, y, seed):
     return float(lib().smco_reference_style_log_likelihood(_p(p), C.c_int64(int(n)), _p(y), C.c_int64(y.size), C.c_uint64(int(seed))))
 
 
+def reference_style_batch(kind, params, n, y, seed):
+    """M reference-style filters threaded over θ like `Threads.@threads for m` (smc_samplers.jl:112); kind 0 (LG1D) or 2 (UCSV);
+    params [M, 8].  Returns logZ [M].  Timing arm only (its own RNG)."""
+    params = np.ascontiguousarray(params, np.float64)
+    y = np.ascontiguousarray(y, np.float64)
+    z = np.empty(params.shape[0])
+    rc = lib().smco_reference_style_batch(C.c_int(int(kind)), _p(params), C.c_int64(params.shape[0]), C.c_int64(int(n)), _p(y), C.c_int64(y.size),
+                                          C.c_uint64(int(seed)), _p(z))
+    if rc != 0:
+        raise ValueError("reference-style arm: LG1D and UCSV only")
+    return z
+
+
 # ---------------------------------------------------------------- N3 guided filter (SPEC §10)
 def guided_step(kind, params, x, logw, y, t, resampler, prop, seed, epoch=0, stream=0):
     """particle_filter!(x, w, y, model, proposal) with proposal = Normal(c0 + c1 xp, c2): mutates x [1,n] / logw in

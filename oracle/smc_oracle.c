@@ -831,3 +831,54 @@ double smco_reference_style_log_likelihood(const double *P, int64_t n, const dou
   free(w); free(x);
   return logZ;
 }
+
+/* the reference-style arm for the UCSV model (state_space_models.jl:215-259): array-of-3-vectors state as the reference keeps it
+ * (x[i] is a 3-vector; kept contiguous here — the reference allocates a fresh heap vector per particle and step, which this port
+ * does NOT charge), alias-table resampling rebuilt every step, libm exp / log, per-step allocations. */
+double smco_reference_style_log_likelihood_ucsv(const double *P, int64_t n, const double *y, int64_t T, uint64_t seed) {
+  const double ge = P[0], gn = P[1], x0 = P[2], lse0 = P[3], lsn0 = P[4];
+  rs_rng g;
+  rs_seed(&g, seed);
+  double *x = (double *)malloc(sizeof(double) * 3 * (size_t)n), *logw = (double *)malloc(sizeof(double) * (size_t)n);
+  for (int64_t i = 0; i < n; ++i) {                      /* initial_dist :249-259 */
+    double *s = x + 3 * i;
+    s[0] = x0 + exp(0.5 * lse0) * rs_randn(&g);
+    s[1] = lse0 + ge * rs_randn(&g);
+    s[2] = lsn0 + gn * rs_randn(&g);
+    logw[i] = rs_normal_logpdf(s[0], exp(0.5 * s[2]), y[0]);   /* observation :244-247 */
+  }
+  double logmu, ess, logZ;
+  double *w = rs_normalize(logw, n, &logmu, &ess);
+  free(logw);
+  logZ = logmu;
+  for (int64_t t = 1; t < T; ++t) {
+    logw = (double *)malloc(sizeof(double) * (size_t)n);
+    int64_t *a = rs_alias_sample(&g, w, n);
+    double *xp = (double *)malloc(sizeof(double) * 3 * (size_t)n);
+    for (int64_t i = 0; i < n; ++i) memcpy(xp + 3 * i, x + 3 * a[i], sizeof(double) * 3);   /* xp = deepcopy(x[a]) */
+    for (int64_t i = 0; i < n; ++i) {
+      const double *p = xp + 3 * i;
+      double *s = x + 3 * i;
+      s[0] = p[0] + exp(0.5 * p[1]) * rs_randn(&g);      /* transition :233-242 (previous log σε) */
+      s[1] = p[1] + ge * rs_randn(&g);
+      s[2] = p[2] + gn * rs_randn(&g);
+      logw[i] = rs_normal_logpdf(s[0], exp(0.5 * s[2]), y[t]);
+    }
+    free(w); free(a); free(xp);
+    w = rs_normalize(logw, n, &logmu, &ess);
+    free(logw);
+    logZ += logmu;
+  }
+  free(w); free(x);
+  return logZ;
+}
+
+/* M reference-style filters, `Threads.@threads for m` (smc_samplers.jl:112): OpenMP over θ; kind 0 (LG1D) or 2 (UCSV) */
+int smco_reference_style_batch(int kind, const double *P, int64_t M, int64_t n, const double *y, int64_t T, uint64_t seed, double *logZ) {
+  if (kind != KIND_LG1D && kind != KIND_UCSV) return -1;
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int64_t m = 0; m < M; ++m)
+    logZ[m] = (kind == KIND_LG1D) ? smco_reference_style_log_likelihood(P + 8 * m, n, y, T, seed + (uint64_t)m)
+                                  : smco_reference_style_log_likelihood_ucsv(P + 8 * m, n, y, T, seed + (uint64_t)m);
+  return 0;
+}

@@ -206,6 +206,16 @@ def test_reference_style_cpu_arm_targets_the_same_likelihood(oracle):
     zs = np.array([oracle.log_likelihood(0, LG, 4096, y, oracle.MULTINOMIAL, s)["logZ"] for s in range(48)])
     assert 0.5 < z.std() / zs.std() < 2.0
     assert oracle.reference_style_log_likelihood(LG, 1, y[:3], 5) < 0.0          # a single particle runs
+    # the UCSV arm, threaded over θ like Threads.@threads: same likelihood estimate as the parity oracle's filters (two samples)
+    UC = [0.2, 0.2, 3.0, 1.0, 1.0]
+    _, yu = oracle.simulate(2, UC, 40, 1998)
+    P = np.tile(oracle.params8(UC), (48, 1))
+    zr = oracle.reference_style_batch(2, P, 1024, yu, 3)
+    zo, _, _ = oracle.batch_log_likelihood(2, P, None, 1024, yu, oracle.MULTINOMIAL, 3, 0, 0, want_state=False)
+    lme = lambda z: np.log(np.mean(np.exp(z - z.max()))) + z.max()      # noqa: E731
+    assert abs(lme(zr) - lme(zo)) < 4 * np.hypot(zr.std(), zo.std()) / np.sqrt(48) + 0.05 and 0.5 < zr.std() / zo.std() < 2.0
+    with pytest.raises(ValueError):
+        oracle.reference_style_batch(1, P, 64, yu, 3)
 
 
 def test_particle_filter_targets_kalman_likelihood(oracle):
