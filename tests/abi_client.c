@@ -5,7 +5,8 @@
  *
  *   abi_client <libsmcb200.so> symbols <name>...    every name must resolve; prints "resolved <n>"
  *   abi_client <libsmcb200.so> host                 host-side helpers only (no GPU): version, state dims, simulate
- *   abi_client <libsmcb200.so> gpu                  one bootstrap filter, one guided batch, one matrix Kalman run
+ *   abi_client <libsmcb200.so> gpu                  one bootstrap filter, one guided batch, one matrix Kalman run, one smc² run of the
+ *                                                   device-resident sampler
  */
 #include <dlfcn.h>
 #include <math.h>
@@ -99,6 +100,47 @@ int main(int argc, char** argv) {
   CHECK(p_smcb_kalman_mv_batch_loglik(ctx, 1, blk, NULL, 1, y, T, 0, &ll_mv, NULL, NULL));
   CHECK(p_smcb_kalman_batch_loglik(ctx, lg, NULL, 1, y, T, 0, &ll_sc, NULL, NULL));
   printf("kalman_mv %.17g\nkalman_scalar %.17g\n", ll_mv, ll_sc);
+
+  /* the device-resident θ-level sampler (mutable struct SMC, smc², smc²!: smc_samplers.jl:5-59,288-340): lg_mod(θ) with the README's
+   * lg_prior, 32 θ-particles × 128 state particles, chain 2.  θ0 is a fixed grid inside the prior's support (the host language draws
+   * it; any values do for the check: the test feeds the same θ0 to the Python-driven sampler and to the oracle). */
+  LOAD(smcb_sampler_create) LOAD(smcb_sampler_destroy) LOAD(smcb_sampler_set_data) LOAD(smcb_sampler_smc2_init)
+  LOAD(smcb_sampler_smc2_step) LOAD(smcb_sampler_get)
+  enum { MS = 32, NS = 128, DT = 3 };
+  smcb_sampler_config cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.kind = SMCB_LG1D; cfg.d_theta = DT; cfg.N = NS; cfg.M = MS; cfg.chain = 2;
+  cfg.resampler = SMCB_SYSTEMATIC; cfg.theta_resampler = SMCB_MULTINOMIAL;
+  cfg.ess_threshold = 0.5; cfg.min_ar = -1.0; cfg.seed = 11;
+  /* TruncatedNormal(0, 1, -1, 1), LogNormal(), LogNormal(): rows (family, p0, p1, lo, hi, c0, c1, 0) */
+  const double tn[8] = {3, 0.0, 1.0, -1.0, 1.0, 0.0, log(erf(1.0 / sqrt(2.0))), 0}, ln_[8] = {1, 0.0, 1.0, 0, 0, 0.0, 0, 0};
+  memcpy(cfg.prior[0], tn, sizeof tn); memcpy(cfg.prior[1], ln_, sizeof ln_); memcpy(cfg.prior[2], ln_, sizeof ln_);
+  const int32_t src[8] = {0, -1, 1, 2, -1, -1, -1, -1};            /* LinearGaussian(θ1, 1.0, θ2, θ3, 0.0), σ0 = 1 */
+  const double cst[8] = {0, 1.0, 0, 0, 0.0, 1.0, 0, 0};
+  memcpy(cfg.map_src, src, sizeof src); memcpy(cfg.map_const, cst, sizeof cst);
+  double theta0[MS * DT], th[MS * DT], om[MS], lz[MS], ess = 0, acc = 0;
+  for (int m = 0; m < MS; ++m) {
+    theta0[m * DT + 0] = -0.9 + 1.8 * (m + 0.5) / MS;
+    theta0[m * DT + 1] = 0.4 + 0.05 * ((m * 7) % MS);
+    theta0[m * DT + 2] = 0.5 + 0.04 * ((m * 11) % MS);
+  }
+  smcb_sampler* sp = NULL;
+  CHECK(p_smcb_sampler_create(ctx, &cfg, theta0, &sp));
+  CHECK(p_smcb_sampler_set_data(sp, y, T));
+  CHECK(p_smcb_sampler_smc2_init(sp));
+  int nrej = 0;
+  for (int t = 1; t < T; ++t) {
+    int rj = 0;
+    CHECK(p_smcb_sampler_smc2_step(sp, t, &ess, &rj));
+    nrej += rj;
+  }
+  int64_t Nfin = 0;
+  CHECK(p_smcb_sampler_get(sp, th, om, lz, &ess, &acc, &Nfin));
+  double sth = 0, slz = 0, som = 0;
+  for (int m = 0; m < MS; ++m) { slz += lz[m]; som += om[m]; for (int k = 0; k < DT; ++k) sth += th[m * DT + k]; }
+  printf("smc2_rejuvenations %d\nsmc2_ess %.17g\nsmc2_theta_sum %.17g\nsmc2_logZ_sum %.17g\nsmc2_omega_sum %.17g\nsmc2_N %lld\n", nrej, ess, sth, slz, som,
+         (long long)Nfin);
+  CHECK(p_smcb_sampler_destroy(sp));
   CHECK(p_smcb_destroy(ctx));
   return 0;
 }

@@ -491,8 +491,8 @@ def test_batch_weighted_moments(ctx, oracle):
 
 @pytest.mark.gpu
 def test_plain_c_client_runs_the_path(oracle):
-    """tests/abi_client.c (plain C, dlopen): one bootstrap filter, three guided filters with per-θ moments and the
-    Kalman entry points, checked against the oracle — the boundary works without Python or C++ on the caller's side"""
+    """tests/abi_client.c (plain C, dlopen): one bootstrap filter, three guided filters with per-θ moments, the
+    Kalman entry points and a whole smc² run of the device-resident sampler, checked against the oracle — the boundary works without Python or C++ on the caller's side"""
     from tests.test_abi import run_c_client
     got = {k: float(v) for k, v in run_c_client("gpu").items()}
     _, y = oracle.simulate(0, LG, 40, 1998)
@@ -512,6 +512,23 @@ def test_plain_c_client_runs_the_path(oracle):
         assert abs(got[f"guided_var{m}"] - float(((xo[m, 0] - mo) ** 2) @ w)) <= 1e-9
     lo = oracle.kalman_loglik(LG, y)[2]
     assert abs(got["kalman_mv"] - lo) <= 1e-12 * abs(lo) and abs(got["kalman_scalar"] - lo) <= 1e-12 * abs(lo)
+    # the device-resident sampler driven from C: the same θ0 through the oracle's smc² (theta overridden after construction)
+    from oracle import samplers as S
+    MS, NS = 32, 128
+    m_ = np.arange(MS)
+    th0 = np.stack([-0.9 + 1.8 * (m_ + 0.5) / MS, 0.4 + 0.05 * ((m_ * 7) % MS), 0.5 + 0.04 * ((m_ * 11) % MS)], 1)
+    po = S.OProduct([S.OTruncatedNormal(0, 1, -1, 1), S.OLogNormal(), S.OLogNormal()])
+    o_ = S.OSMC(NS, MS, lambda θ: (0, [θ[0], 1.0, θ[1], θ[2], 0.0, 1.0]), po, 2, 0.5, seed=11, resampler=oracle.SYSTEMATIC)
+    o_.theta = th0.copy()
+    S.o_smc2(o_, y)
+    nrej = 0
+    for t in range(1, len(y)):
+        S.o_smc2_step(o_, y, t)
+        nrej += int(o_.rejuvenated)
+    assert int(got["smc2_rejuvenations"]) == nrej and nrej >= 1 and int(got["smc2_N"]) == NS
+    assert got["smc2_theta_sum"] == pytest.approx(float(o_.theta.sum()), rel=1e-13)       # θ bit-identical: only the summation differs
+    assert got["smc2_logZ_sum"] == pytest.approx(float(o_.logZ.sum()), rel=1e-10)
+    assert got["smc2_ess"] == pytest.approx(o_.ess, rel=1e-9) and got["smc2_omega_sum"] == pytest.approx(1.0, abs=1e-12)
 
 
 @pytest.mark.gpu
